@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- scan-pixel*rays/s of the beam-simulation hot path on N B200 GPUs of one node.
+
+Workload (BASELINE.json configs[1], the far-field LAT simulation `ff_sim.py 140 0.25 20 1.32`):
+one step = one full 41x41-pixel far-field map, 100^2 rays launched per pixel, 140 GHz, focal plane
+1.32 m, E_rec = the 51x51 near-field map of config 0 produced by this build (outside the timed region).
+With N GPUs every rank computes one such map (focal-plane offset 1.32 m + 1 cm * rank, the
+quant-systematics sweep of configs[3]) and the (amp, phase) blocks are gathered to rank 0 inside the
+step: weak scaling, the only collective is the final gather.
+
+  value : whole-job pixel*rays/s with inputs resident in HBM, timed with CUDA events per step
+  e2e   : the same through the host-buffer C-ABI call (pinned host in, host out, copies inside)
+  --impl reference : the reference's CPU algorithm (oracle port, all host threads) on a bounded sample
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "scan_pixel_rays_per_s"
+UNIT = "pixel*rays/s"
+FREQ, RES_ARCMIN, NUM, OFFSET, N_SCAN = 140, 0.25, 20, 1.32, 100
+FLOP_PER_LAUNCHED_RAY = 626.0        # 1030 per valid ray, 20 per rejected, 60 % valid
+NOMINAL_FP64_TFLOPS = 37.2           # 148 SM x 64 DFMA lanes x 2 x 1.965 GHz
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "ff_sim.py 140 0.25 20 1.32: far-field LAT map, 41x41 px x 100^2 rays, 140 GHz, focal plane 1.32 m"
+                    + ("" if n_gpus == 1 else "; one map per rank (offset +1 cm*rank), gathered to rank 0"),
+        "pixels_per_map": (2 * NUM + 1) ** 2, "rays_per_pixel": N_SCAN ** 2, "maps": n_gpus,
+        "e_rec": "51x51 near-field map (holo_sim.py 140 defaults) computed by this build before timing",
+        "l2": "flushed between timed steps (256 MiB write); the path reads <1 MB per step",
+        "parallelism": "pixel-sharded x%d" % n_gpus,
+    }
+
+
+def cpu_e_rec_stub():
+    """Closed-form stand-in for E_rec used only by the CPU reference arm when no GPU is present
+    (the arithmetic per ray does not depend on E_rec's values)."""
+    ax = np.linspace(-50, 50, 51) / 1e1
+    y, x = np.meshgrid(ax, ax, indexing="ij")
+    return x, y, np.exp(-(x ** 2 + y ** 2) / 4.5) * np.exp(0.3j * (x ** 2 + y ** 2))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.004):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self._stop_evt = [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle port of the reference algorithm (brentq per surface per ray, both passes of
+    ff_sim.py:208-209) with all host threads, on a bounded sample of the same map per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle_lib as orc
+    from solat_optics_b200 import maps
+
+    tg = maps.ff_tele_geo(FREQ, OFFSET)
+    th, ph = maps.ff_fan(N_SCAN)
+    pixels = maps.ff_pixels(tg, RES_ARCMIN, NUM)
+    x, y, e = cpu_e_rec_stub()
+    geo = orc.ff_geo_vec(rx_y_m=-OFFSET)
+    cores = orc.num_threads()
+    stride = 8
+    sample = pixels[::stride]
+    rays = len(sample) * N_SCAN ** 2
+    for _ in range(args.warmup):
+        orc.ff_map(geo, sample[: max(1, len(sample) // 8)], th, ph, x, y, e, tg.k, two_pass=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.ff_map(geo, sample, th, ph, x, y, e, tg.k, two_pass=True)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = rays / dt
+    desc = "every %dth pixel of the 41x41 map (%d px x %d rays) per step, %d host threads" % (stride, len(sample), N_SCAN ** 2, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                         "note": "C restatement of the reference's Python algorithm (oracle/solat_oracle.c); the "
+                                 "unmodified Python reference measured 5.3e2 pixel*rays/s per core (BASELINE.md)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from solat_optics_b200 import _lib, maps
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    host_pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=dev)
+        host_pg = dist.new_group(backend="gloo")
+
+    ctx = _lib.context(local_rank)
+    # ---- untimed set-up: E_rec from our own near-field map (config 0), plans, pinned buffers
+    tgn = maps.holo_tele_geo(float(FREQ), 100)
+    rx_opl, rx_w = maps.receiver_field(tgn)
+    nplan = maps.NearFieldPlan(tgn, [tgn.k], rx_opl, rx_w, device=local_rank)
+    px_nf = maps.holo_pixels()
+    amp_nf, ph_nf, _ = nplan.run(px_nf)          # every rank builds the same 51x51 table (a few ms)
+    nplan.close()
+    data_x, data_y, e_rec = maps.near_field_to_e_rec(np.c_[px_nf[:, 0], px_nf[:, 1], amp_nf[0], ph_nf[0]])
+    tg = maps.ff_tele_geo(FREQ, OFFSET + 0.01 * rank)
+    th, ph = maps.ff_fan(N_SCAN)
+    plan = maps.FarFieldPlan(tg, th, ph, data_x, data_y, e_rec, device=local_rank)
+    pixels = maps.ff_pixels(tg, RES_ARCMIN, NUM)
+    npix = len(pixels)
+    rays_per_step = npix * N_SCAN ** 2 * world
+
+    h_azel = torch.from_numpy(pixels.copy()).pin_memory()
+    h_amp = torch.empty(npix, dtype=torch.float64).pin_memory()
+    h_phase = torch.empty(npix, dtype=torch.float64).pin_memory()
+    d_azel = h_azel.to(dev)
+    d_out = torch.empty((2, npix), dtype=torch.float64, device=dev)      # rows: amp, phase
+    gathered = [torch.empty_like(d_out) for _ in range(world)] if (world > 1 and rank == 0) else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def device_step():
+        plan.run_device(d_azel, d_out[0], d_out[1], stream)
+        if world > 1:
+            dist.gather(d_out, gathered, dst=0)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (value): CUDA events per step, L2 flushed between steps
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    sync_all()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    launches0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        device_step()
+        b.record()
+    sync_all()
+    launches = _lib.launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    kernel_ms = dev_ms / args.steps
+    # ---- end-to-end through the host-buffer C ABI (pinned host in, host out), gather of host results for N > 1
+    amp_np, phase_np, az_np = h_amp.numpy(), h_phase.numpy(), h_azel.numpy()
+    host_blocks = [torch.empty((2, npix), dtype=torch.float64) for _ in range(world)] if (world > 1 and rank == 0) else None
+    host_local = torch.empty((2, npix), dtype=torch.float64)
+
+    def e2e_step():
+        plan.run(az_np, amp_np, phase_np)
+        if world > 1:
+            host_local[0].copy_(h_amp); host_local[1].copy_(h_phase)
+            dist.gather(host_local, host_blocks, dst=0, group=host_pg)
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.finish()
+    status = plan.status()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ms_per_step = dev_ms_max / args.steps
+        value = rays_per_step / (ms_per_step * 1e-3)
+        e2e_value = rays_per_step / (e2e_ms_max / args.steps * 1e-3)
+        peak = ctx.fp64_peak_tflops(5)
+        flop_per_launch = FLOP_PER_LAUNCHED_RAY * npix * N_SCAN ** 2
+        if world == 1:
+            achieved = flop_per_launch / (kernel_ms * 1e-3) / 1e12
+            kernel_note = "ff_map_kernel, one launch per step, CUDA events around the launch"
+        else:
+            achieved = None
+            kernel_note = "per-step events include the NCCL gather at N>1; see the N=1 line for the kernel roofline"
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_azel.numel() * 8 * world),
+                    "d2h_bytes_per_step": int(2 * npix * 8 * world), "ms_per_step": e2e_ms_max / args.steps,
+                    "api": "solat_ff_map_host via maps.FarFieldPlan.run (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "peak_source": "DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure); nominal %.1f" % NOMINAL_FP64_TFLOPS,
+                         "frac_of_nominal": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None,
+                         "flop_per_unit": FLOP_PER_LAUNCHED_RAY, "units_per_launch": npix * N_SCAN ** 2, "kernel": kernel_note},
+            "ray_status": int(status),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(tg, th, ph, pixels, data_x, data_y, e_rec)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(tg, th, ph, pixels, data_x, data_y, e_rec):
+    from oracle import oracle_lib as orc
+
+    geo = orc.ff_geo_vec(rx_y_m=tg.rx_y)
+    cores = orc.num_threads()
+    sample = pixels[::4]
+    orc.ff_map(geo, sample[:8], th, ph, data_x, data_y, e_rec, tg.k, two_pass=True)
+    t0 = time.perf_counter()
+    orc.ff_map(geo, sample, th, ph, data_x, data_y, e_rec, tg.k, two_pass=True)
+    dt = time.perf_counter() - t0
+    return {"value": len(sample) * N_SCAN ** 2 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "every 4th pixel of the same 41x41 map (%d px x %d rays), both reference passes, %d threads, %.1f s"
+                      % (len(sample), N_SCAN ** 2, cores, dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,147 @@
+/*
+ * solat_b200.h -- C ABI of libsolat_b200.so, the B200 (sm_100a) implementation of the
+ * solat-optics beam-simulation hot path.
+ *
+ * The reference (McMahonCosmologyGroup/solat-optics) is pure Python and has no FFI layer;
+ * its boundary for this path is the Python call surface listed below.  Each entry point
+ * names the reference interface it replaces (file:line under the reference tree).  The
+ * Python package solat_optics_b200 binds these with ctypes.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all floating point is IEEE double; lengths in mm, angles in rad,
+ *    wavenumbers in rad/m exactly as in the reference.
+ *  - "host" entry points take HOST pointers (pageable or pinned), do the H2D/D2H copies
+ *    themselves and return after the result is in the output buffer.
+ *  - "device" entry points take DEVICE pointers, enqueue on the given CUDA stream
+ *    (a cudaStream_t passed as void*; NULL = legacy default stream) and return immediately.
+ *  - every function returns 0 on success and a negative solat_err on failure;
+ *    solat_last_error() gives a thread-local message.
+ *  - per-ray status bits (also OR-reduced per map): 1 = root outside the reference's brentq
+ *    bracket (the reference raises ValueError there), 2 = Newton not converged, 4 = NaN path.
+ *  - no global mutable state except the per-thread error string and a launch counter.
+ */
+#ifndef SOLAT_B200_H
+#define SOLAT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOLAT_ABI_VERSION 1
+#if defined(__GNUC__)
+#define SOLAT_API __attribute__((visibility("default")))
+#else
+#define SOLAT_API
+#endif
+
+enum solat_err {
+    SOLAT_OK = 0,
+    SOLAT_ERR_ARG = -1,     /* bad argument */
+    SOLAT_ERR_CUDA = -2,    /* CUDA runtime error, see solat_last_error() */
+    SOLAT_ERR_NODEV = -3    /* no usable sm_100 device */
+};
+enum solat_ray_status { SOLAT_ST_BRACKET = 1, SOLAT_ST_NOCONV = 2, SOLAT_ST_NAN = 4 };
+
+typedef struct solat_ctx solat_ctx;         /* one per device; owns scratch buffers */
+typedef struct solat_nf_plan solat_nf_plan; /* near-field map plan (tables resident in HBM) */
+typedef struct solat_ff_plan solat_ff_plan; /* far-field map plan */
+
+/* ot_geo.LatGeo (solat_optics/ot_geo.py:12-58): the attributes the tracers read */
+typedef struct {
+    double n_si, n_vac; /* refractive indices (3.4, 1.0) */
+    double th_fwhp;     /* feed full width at half power [rad] */
+    double y_ap;        /* source plane / aperture y [mm] */
+} solat_nf_geom;
+
+/* latrt_geo.initialize_telescope_geometry (solat_optics/latrt_geo.py:7-49) */
+typedef struct {
+    double th_1, th2;   /* mirror tilts; th2 = -pi/2 - atan(1/3) */
+    double rotc_mm[3];  /* (x,y,z)_rotc * 1e3 */
+    double src_mm[3];   /* (x,y,z)_tow * 1e3 */
+    double foc_y_mm;    /* rx_y * 1e3 (solat_apert_field.py:582) */
+} solat_ff_geom;
+
+SOLAT_API int solat_abi_version(void);
+SOLAT_API const char *solat_last_error(void);
+SOLAT_API int solat_device_count(void);
+SOLAT_API int solat_ctx_create(int device, solat_ctx **ctx);
+SOLAT_API void solat_ctx_destroy(solat_ctx *ctx);
+SOLAT_API int solat_ctx_info(const solat_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, long long *hbm_bytes);
+/* number of kernels this library has launched in the calling process so far */
+SOLAT_API long long solat_launch_count(void);
+/* DFMA-issue microbenchmark: measured FP64 FMA throughput of the device in TFLOP/s (roofline denominator) */
+SOLAT_API int solat_fp64_peak(solat_ctx *ctx, int repeats, double *tflops);
+
+/* ---------------- near field: reference-shaped per-ray arrays (host pointers) ----------------
+ * theta[nth], phi[nph] are the 1-D launch axes; ray ii uses theta[ii % nth], phi[ii / nth]
+ * (np.meshgrid(theta, phi) raveled, ray_trace_int.py:596-598).  out is (rows, nth*nph) row-major.
+ * nph == 0 selects PAIRED mode for the per-ray array functions (not the maps): phi then has nth
+ * entries and ray ii uses (theta[ii], phi[ii]) -- what trace_rays(ii) of the reference classes needs.
+ * status may be NULL; otherwise int[number of rays].                                             */
+
+/* replaces ray_trace_int.rx_to_lyot_model(p_rx, tele_geo, plotOpts).output(), rti:579-885; 20 rows */
+SOLAT_API int solat_nf_rx_trace(solat_ctx *ctx, const solat_nf_geom *g, const double p_rx[3], const double *theta, int nth,
+                      const double *phi, int nph, double *out20, int *status);
+/* replaces ray_trace_int.source_to_lyot_model(p_source, ...).output(), rti:888-1382; 26 rows */
+SOLAT_API int solat_nf_source_trace(solat_ctx *ctx, const solat_nf_geom *g, const double p_src[3], const double *theta, int nth,
+                          const double *phi, int nph, double *out26, int *status);
+/* replaces ray_trace_int.aperature_fields(P_rx, ...).output(), rti:33-576; 32 rows */
+SOLAT_API int solat_nf_toy_trace(solat_ctx *ctx, const solat_nf_geom *g, const double p_rx[3], const double *theta, int nth,
+                       const double *phi, int nph, double *out32, int *status);
+
+/* ---------------- near field: fused holography map --------------------------------------------
+ * replaces the worker body scripts/holo_sim.py:157-185 for a whole list of source positions:
+ * per pixel  sum_rays  rx_w * exp(i k (rx_opl + L_source)/1e3)  ->  amp = |.|, phase = atan2.
+ * rx_opl / rx_w [nth*nph]: receiver path length and (feed taper x Lyot mask) in ray-index space,
+ * i.e. rows 3 and 4 of the regridded rx field (rti:1385-1440, holo_sim.py:168-180); rays with
+ * rx_w == 0 are culled before tracing.  k_per_m[nfreq]: several wavenumbers share one trace.
+ * amp/phase are [nfreq][npix].                                                                   */
+SOLAT_API int solat_nf_plan_create(solat_ctx *ctx, const solat_nf_geom *g, const double *theta, int nth, const double *phi,
+                         int nph, const double *rx_opl, const double *rx_w, const double *k_per_m, int nfreq,
+                         solat_nf_plan **plan);
+SOLAT_API void solat_nf_plan_destroy(solat_nf_plan *plan);
+SOLAT_API int solat_nf_map_host(solat_nf_plan *plan, const double *src_xz, int npix, double *amp, double *phase, int *status);
+SOLAT_API int solat_nf_map_device(solat_nf_plan *plan, const double *d_src_xz, int npix, double *d_amp, double *d_phase,
+                        void *stream);
+/* traced rays per pixel after culling (for FLOP accounting) */
+SOLAT_API int solat_nf_plan_active_rays(const solat_nf_plan *plan);
+/* OR of the ray status bits of all device-side maps run on this plan since the last call (synchronises) */
+SOLAT_API int solat_nf_plan_status(solat_nf_plan *plan, int *status);
+
+/* ---------------- far field: reference-shaped per-ray arrays (host pointers) ------------------ */
+
+/* replaces solat_apert_field.ray_mirror_pts(tele_geo, theta, phi, el, az), saf:307-567; out (9, nth*nph) */
+SOLAT_API int solat_ff_ray_mirror_pts(solat_ctx *ctx, const solat_ff_geom *g, const double *theta, int nth, const double *phi,
+                            int nph, double el, double az, double *out9, int *status);
+/* replaces solat_apert_field.aperature_fields_from_panel_model(...), saf:570-1009; out (17, nth*nph).
+ * focal_centre = rxmirror[6:9,0].  pan_idx1/2[nth*nph]: column of pan1/pan2 of the first panel whose
+ * (row,col) matches the ray's identify_panel ids, or -1 (the host side of saf:609-628,775-779; panel
+ * identification itself belongs to the external pan_mod).  pan1 (10,np1), pan2 (10,np2) row-major
+ * [row,col,a,b,c,d,e,f,x0,y0] (saf:667-674).                                                      */
+SOLAT_API int solat_ff_apert_fields(solat_ctx *ctx, const solat_ff_geom *g, const double *theta, int nth, const double *phi,
+                          int nph, const double focal_centre[3], const int *pan_idx1, const int *pan_idx2,
+                          const double *pan1, int np1, const double *pan2, int np2, double el, double az,
+                          double *out17, int *status);
+/* replaces far_field_latrt.project_to_data(sim, data_x, data_y, tele_geo), ffl:9-32.
+ * sim (17, n_pts); data_x, data_y (M, M); out_reim (M, M) complex128 as interleaved re,im.       */
+SOLAT_API int solat_ff_project(solat_ctx *ctx, const double *sim17, int n_pts, const double *data_x, const double *data_y, int M,
+                     double k, double *out_reim);
+
+/* ---------------- far field: fused beam map ----------------------------------------------------
+ * replaces the worker body scripts/ff_sim.py:204-221 for a list of (az, el) pixels, with the
+ * single-panel / zero-error panel model (adjuster offsets are identically zero in ff_sim.py:61-62):
+ * per pixel  sum_cells  exp(i k L_winner/1e3) * e_rec[cell] / M^2 , winner = highest ray index
+ * landing in the cell (last write wins, ffl:28).  azel is [npix][2] = (az, el).                  */
+SOLAT_API int solat_ff_plan_create(solat_ctx *ctx, const solat_ff_geom *g, const double *theta, int nth, const double *phi,
+                         int nph, const double *data_x, const double *data_y, const double *e_rec_reim, int M,
+                         double k, solat_ff_plan **plan);
+SOLAT_API void solat_ff_plan_destroy(solat_ff_plan *plan);
+SOLAT_API int solat_ff_map_host(solat_ff_plan *plan, const double *azel, int npix, double *amp, double *phase, int *status);
+SOLAT_API int solat_ff_map_device(solat_ff_plan *plan, const double *d_azel, int npix, double *d_amp, double *d_phase,
+                        void *stream);
+SOLAT_API int solat_ff_plan_status(solat_ff_plan *plan, int *status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOLAT_B200_H */

@@ -1,0 +1,49 @@
+"""Far-field beam simulation of the LAT (two mirrors) on B200 GPUs.
+
+To run:   python3 ff_sim.py <freq_GHz> <res_arcmin> <num> <offset_m>
+          torchrun --nproc-per-node 8 ff_sim.py 150 1 10 1.33        (replaces mpiexec -n 10)
+
+Drop-in for the reference's scripts/ff_sim.py: same four positional arguments (:23-26), same az/el
+grid (:94,121-128), source 100 km away (:72-79), E_rec read from a near-field .txt (:46-59,81-88),
+same output format (:181-189).  The reference's hard-coded absolute paths (:46-49) become
+--nf-input / --out with repository-relative defaults.
+"""
+import argparse
+import time
+
+import numpy as np
+
+import _launch  # noqa: F401
+from solat_optics_b200 import maps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("freq", type=int)
+    ap.add_argument("res", type=float, help="pixel size [arcmin]")
+    ap.add_argument("num", type=int, help="pixels each side of the centre (map is (2 num + 1)^2)")
+    ap.add_argument("offset", type=float, help="focal-plane offset [m]")
+    ap.add_argument("--nf-input", default=None, help="near-field map (.txt from holo_sim.py)")
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--n-scan", type=int, default=100)
+    ap.add_argument("--strict", action="store_true")
+    a = ap.parse_args()
+
+    sim_d = 1.25 if a.freq <= 120 else 1.32                      # ff_sim.py:36-41
+    nf_path = a.nf_input or "data/source_test_%sm_%dGHz.txt" % (sim_d, a.freq)
+    out_path = a.out or "output_files/ff_%sm_%dGHz.txt" % (a.offset, a.freq)
+
+    rank, world = _launch.init_distributed()
+    t0 = time.perf_counter()
+    data_x, data_y, e_rec = maps.near_field_to_e_rec(np.loadtxt(nf_path))
+    res = maps.ff_map(a.freq, a.res, a.num, a.offset, data_x, data_y, e_rec, a.n_scan, strict=a.strict)
+    if res is not None:
+        pixels, amp, phase = res
+        maps.save_map_txt(out_path, pixels[:, 0], pixels[:, 1], amp, phase)
+        print("wrote %s  (%d px x %d rays, %d GPU(s), %.2f s)" % (
+            out_path, len(pixels), a.n_scan ** 2, world, time.perf_counter() - t0))
+    _launch.finish_distributed()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,926 @@
+// solat_kernels.cu -- sm_100a kernels and the C ABI (include/solat_b200.h) of libsolat_b200.so.
+//
+// Kernels (all FP64 SIMT; the path has no dense contraction, so no tensor cores -- DESIGN.md):
+//   nf_rows_kernel<KIND>   thread-per-ray dump of the reference's .output() arrays (rx / source / toy)
+//   nf_map_kernel<NF>      fused source trace + phase + aperture integral: one CTA per (pixel, ray tile),
+//                          rays culled by the receiver weight, warp-shuffle + shared-memory block reduce
+//   nf_finalize_kernel     fixed-order sum of tile partials -> amp, phase
+//   ff_rows_kernel<STAGE>  thread-per-ray dump of ray_mirror_pts / aperature_fields_from_panel_model
+//   ff_project_*           last-write-wins scatter (atomicMax on the ray index) + phasor fill
+//   ff_map_kernel          fused far-field pixel: one CTA per (az, el); cheap aperture test feeds a
+//                          shared-memory work queue so every warp of the expensive mirror trace is full;
+//                          winner table (ray index, OPL) in shared memory; winners-only phasor sum
+//   fp64_peak_kernel       DFMA issue-rate microbenchmark (roofline denominator)
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/solat_b200.h"
+#include "solat_math.cuh"
+
+using namespace solat;
+
+// ------------------------------------------------------------------------------------------------
+// host-side plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* what, const char* detail = "")
+{
+    g_err = std::string(what) + (detail[0] ? ": " : "") + detail;
+    return code;
+}
+#define CK(call)                                                                  \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) return fail(SOLAT_ERR_CUDA, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define LAUNCHED()                                                                \
+    do {                                                                          \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                       \
+        CK(cudaGetLastError());                                                   \
+    } while (0)
+
+struct solat_ctx {
+    int device;
+    cudaDeviceProp prop;
+    cudaStream_t stream;   // used by the host entry points
+};
+
+// device buffer with RAII, bound to the ctx device
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int reserve(size_t count)
+    {
+        if (count <= n) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        CK(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+        return 0;
+    }
+    int upload(const T* h, size_t count, cudaStream_t s)
+    {
+        int rc = reserve(count);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        return 0;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+struct AngleTabs {
+    const double *st, *ct, *sp, *cp;   // sin/cos of theta[nth], phi[nph]
+    int nth, nph;                      // nph == 0: paired mode, ray ii uses theta[ii], phi[ii] (phi has nth entries)
+    __host__ __device__ int rays() const { return nph == 0 ? nth : nth * nph; }
+};
+struct AngleTabsOwner {
+    DevBuf<double> buf;
+    AngleTabs tabs;
+    int init(const double* theta, int nth, const double* phi, int nph_arg, cudaStream_t s)
+    {
+        const int nph = nph_arg == 0 ? nth : nph_arg;
+        std::vector<double> h(2 * (size_t)nth + 2 * (size_t)nph);
+        for (int i = 0; i < nth; i++) { h[i] = sin(theta[i]); h[nth + i] = cos(theta[i]); }
+        for (int j = 0; j < nph; j++) { h[2 * nth + j] = sin(phi[j]); h[2 * nth + nph + j] = cos(phi[j]); }
+        int rc = buf.upload(h.data(), h.size(), s);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(s));   // h goes out of scope
+        tabs.st = buf.p; tabs.ct = buf.p + nth; tabs.sp = buf.p + 2 * nth; tabs.cp = buf.p + 2 * nth + nph;
+        tabs.nth = nth; tabs.nph = nph_arg;
+        return 0;
+    }
+};
+
+__device__ __forceinline__ vec3 ray_dir(const AngleTabs& a, int r)
+{
+    int j = r / a.nth, i = r - j * a.nth;   // meshgrid(theta, phi) raveled: theta is the fast index
+    if (a.nph == 0) { i = r; j = r; }
+    return launch_dir(__ldg(a.st + i), __ldg(a.ct + i), __ldg(a.sp + j), __ldg(a.cp + j));
+}
+
+// ------------------------------------------------------------------------------------------------
+// near field: per-ray dumps
+// ------------------------------------------------------------------------------------------------
+enum { NF_RX = 0, NF_SOURCE = 1, NF_TOY = 2 };
+struct NfRowsParams {
+    AngleTabs ang;
+    const double *theta, *phi;   // raw angles (rx taper needs them)
+    double p[3];
+    double n_si, n_vac, y_ap, inv_2sig2, th_mean, ph_mean;
+    double* out;
+    int* status;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(128) nf_rows_kernel(NfRowsParams q)
+{
+    const int n = q.ang.rays();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const vec3 p0 = mk(q.p[0], q.p[1], q.p[2]);
+    const vec3 d = ray_dir(q.ang, r);
+    constexpr int ROWS = KIND == NF_RX ? 20 : (KIND == NF_SOURCE ? 26 : 32);
+    double rows[ROWS];
+    int st;
+    if (KIND == NF_RX) {
+        NfRxRay ray;
+        nf_rx_ray(p0, d, q.n_si, q.n_vac, ray);
+        int j = r / q.ang.nth, i = r - j * q.ang.nth;
+        if (q.ang.nph == 0) { i = r; j = r; }
+        pack_nf_rx_rows(ray, p0, q.theta[i] - q.th_mean, q.phi[j] - q.ph_mean, q.inv_2sig2, rows);
+        st = ray.status;
+    } else if (KIND == NF_SOURCE) {
+        NfSourceRay ray;
+        nf_source_ray(p0, d, q.n_si, q.n_vac, ray);
+        pack_nf_source_rows(ray, p0, q.n_si, q.n_vac, rows);
+        st = ray.status;
+    } else {
+        NfToyRay ray;
+        nf_toy_ray(p0, d, q.y_ap, q.n_si, q.n_vac, ray);
+        pack_nf_toy_rows(ray, p0, q.inv_2sig2, rows);
+        st = ray.status;
+    }
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) q.out[(size_t)k * n + r] = rows[k];
+    if (q.status) q.status[r] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// near field: fused map
+// ------------------------------------------------------------------------------------------------
+constexpr int NF_MAXF = 4;
+struct NfMapParams {
+    AngleTabs ang;
+    const double* src_xz;      // [npix][2]
+    const int* act_idx;        // [n_act] ray indices with non-zero receiver weight
+    const double2* act_rx;     // [n_act] (rx_opl, rx_w)
+    double y_ap, n_si, n_vac;
+    double kk[NF_MAXF];        // k/1e3 [rad/mm]
+    int n_act, tiles, tile_len, nfreq_total, f0;
+    double2* partial;          // [npix][tiles][nfreq_total]
+    int* status;
+};
+
+template <int NF>
+__device__ __forceinline__ void block_reduce_store(double (&re)[NF], double (&im)[NF], double2* dst)
+{
+    __shared__ double sh[2 * NF_MAXF][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            re[f] += __shfl_down_sync(0xffffffffu, re[f], o);
+            im[f] += __shfl_down_sync(0xffffffffu, im[f], o);
+        }
+        if (lane == 0) { sh[2 * f][warp] = re[f]; sh[2 * f + 1][warp] = im[f]; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            double a = lane < nwarp ? sh[2 * f][lane] : 0.0, b = lane < nwarp ? sh[2 * f + 1][lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_down_sync(0xffffffffu, a, o);
+                b += __shfl_down_sync(0xffffffffu, b, o);
+            }
+            if (lane == 0) dst[f] = make_double2(a, b);
+        }
+    }
+}
+
+template <int NF>
+__global__ void __launch_bounds__(256, 2) nf_map_kernel(NfMapParams q)
+{
+    const int pix = blockIdx.x / q.tiles, tile = blockIdx.x - pix * q.tiles;
+    const vec3 p0 = mk(__ldg(q.src_xz + 2 * pix), q.y_ap, __ldg(q.src_xz + 2 * pix + 1));
+    double re[NF], im[NF];
+#pragma unroll
+    for (int f = 0; f < NF; f++) re[f] = im[f] = 0.0;
+    int st = 0;
+    const int q_end = min((tile + 1) * q.tile_len, q.n_act);
+    for (int a = tile * q.tile_len + threadIdx.x; a < q_end; a += blockDim.x) {
+        const int r = __ldg(q.act_idx + a);
+        const double2 rx = __ldg(q.act_rx + a);
+        NfSourceRay ray;
+        nf_source_ray(p0, ray_dir(q.ang, r), q.n_si, q.n_vac, ray);
+        st |= ray.status;
+        if (ray.valid) {
+            const double L = rx.x + ray.opl;   // holo_sim.py:176-177: exp(i k L_rx) exp(i k L_so)
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                double s, c;
+                sincos(L * q.kk[f], &s, &c);
+                re[f] = fma(rx.y, c, re[f]);
+                im[f] = fma(rx.y, s, im[f]);
+            }
+        }
+    }
+    if (st) atomicOr(q.status, st);
+    block_reduce_store<NF>(re, im, q.partial + ((size_t)pix * q.tiles + tile) * q.nfreq_total + q.f0);
+}
+
+__global__ void nf_finalize_kernel(const double2* partial, int npix, int tiles, int nfreq, double* amp, double* phase)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // f * npix + pix
+    if (idx >= npix * nfreq) return;
+    const int f = idx / npix, pix = idx - f * npix;
+    double re = 0.0, im = 0.0;
+    for (int t = 0; t < tiles; t++) {
+        const double2 v = partial[((size_t)pix * tiles + t) * nfreq + f];
+        re += v.x; im += v.y;
+    }
+    amp[idx] = hypot(re, im);     // holo_sim.py:181-182
+    phase[idx] = atan2(im, re);
+}
+
+// ------------------------------------------------------------------------------------------------
+// far field: per-ray dumps
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ FfGeom to_geom(const solat_ff_geom& g)
+{
+    FfGeom r;
+    r.th_1 = g.th_1; r.th2 = g.th2;
+    for (int i = 0; i < 3; i++) { r.rotc[i] = g.rotc_mm[i]; r.src[i] = g.src_mm[i]; }
+    r.foc_y = g.foc_y_mm;
+    return r;
+}
+
+struct FfRowsParams {
+    AngleTabs ang;
+    solat_ff_geom g;
+    double el, az;
+    double centre[3];
+    const int *pidx1, *pidx2;
+    const double *pan1, *pan2;
+    int np1, np2;
+    double* out;
+    int* status;
+};
+
+template <bool STAGE1>
+__global__ void __launch_bounds__(128) ff_rows_kernel(FfRowsParams q)
+{
+    __shared__ FfFrames fr;
+    __shared__ double t2e[9];
+    const FfGeom g = to_geom(q.g);
+    if (threadIdx.x == 0) {
+        ff_build_frames(g, q.el, q.az, fr);
+        for (int i = 0; i < 9; i++) t2e[i] = fr.t2.a[i];
+        if (g.src[2] != 0) for (int i = 0; i < 3; i++) t2e[3 * i + 2] /= cos(atan(1.0 / 3.0));   // saf:828-829
+    }
+    __syncthreads();
+    const int n = q.ang.rays();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    constexpr int ROWS = STAGE1 ? 9 : 17;
+    double rows[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) rows[k] = 0.0;
+    int st = 0;
+    bool go = true;
+    if (!STAGE1) go = (q.pidx1[r] >= 0) && (q.pidx2[r] >= 0);   // saf:626-628, :775-779
+    if (go) {
+        const vec3 d = ray_dir(q.ang, r);
+        vec3 Pa;
+        double t_ap;
+        if (ff_aperture(g, fr, d, t_ap, Pa)) {
+            FfRay ray;
+            if (STAGE1) {
+                ff_ray_trace<true, false>(fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+                rows[0] = ray.m2.x; rows[1] = ray.m2.y; rows[2] = ray.m2.z;
+                rows[3] = ray.m1.x; rows[4] = ray.m1.y; rows[5] = ray.m1.z;
+            } else {
+                PanelErr e1, e2;
+                const double* c = q.pan1 + q.pidx1[r];
+                e1.a = c[2 * q.np1]; e1.b = c[3 * q.np1]; e1.c = c[4 * q.np1]; e1.d = c[5 * q.np1]; e1.e = c[6 * q.np1];
+                e1.x0 = c[8 * q.np1]; e1.y0 = c[9 * q.np1];
+                c = q.pan2 + q.pidx2[r];
+                e2.a = c[2 * q.np2]; e2.b = c[3 * q.np2]; e2.c = c[4 * q.np2]; e2.d = c[5 * q.np2]; e2.e = c[6 * q.np2];
+                e2.x0 = c[8 * q.np2]; e2.y0 = c[9 * q.np2];
+                ff_ray_trace<false, true>(fr, d, t_ap, Pa, g.foc_y, &e1, &e2, t2e, ray);
+                pack_ff_rows(ray, q.centre, rows);
+            }
+            st = ray.status;
+        }
+    }
+    if (STAGE1 && r == 0) { rows[6] = fr.centre[0]; rows[7] = fr.centre[1]; rows[8] = fr.centre[2]; }   // saf:563-565
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) q.out[(size_t)k * n + r] = rows[k];
+    if (q.status) q.status[r] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// far field: project_to_data (far_field_latrt.py:9-32)
+// ------------------------------------------------------------------------------------------------
+__global__ void ff_project_scatter_kernel(const double* sim, int n_pts, const double* gx, const double* gy, int M,
+                                          double gx_max, double gy_max, int* win)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pts) return;
+    if (sim[(size_t)15 * n_pts + r] == 0.0) return;                               // ffl:10
+    const int c = ff_cell(sim[(size_t)9 * n_pts + r], sim[(size_t)11 * n_pts + r], gx, gy, M, gx_max, gy_max);
+    if (c >= 0) atomicMax(win + c, r);                                            // ffl:28: later rays overwrite
+}
+__global__ void ff_project_fill_kernel(const double* sim, int n_pts, const int* win, int cells, double k, double2* out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    double2 v = make_double2(0.0, 0.0);
+    const int r = win[c];
+    if (r >= 0) cis_large(k * sim[(size_t)15 * n_pts + r] / 1e3, v.x, v.y);       // ffl:28-30
+    out[c] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// far field: fused map
+// ------------------------------------------------------------------------------------------------
+constexpr int FF_T = 256;
+struct FfMapParams {
+    AngleTabs ang;
+    solat_ff_geom g;
+    const double* azel;      // [npix][2] (az, el)
+    const double* gx;        // data_x[0,:]
+    const double* gy;        // data_y (M, M)
+    const double2* e_rec;    // (M, M)
+    double gx_max, gy_max, k;
+    int M;
+    double* amp;
+    double* phase;
+    int* status;
+};
+
+__global__ void __launch_bounds__(FF_T, 2) ff_map_kernel(FfMapParams q)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cells = q.M * q.M;
+    FfFrames* fr = reinterpret_cast<FfFrames*>(smem_raw);
+    double* win_opl = reinterpret_cast<double*>(smem_raw + ((sizeof(FfFrames) + 15) / 16) * 16);
+    int* win_idx = reinterpret_cast<int*>(win_opl + cells);
+    int* queue = win_idx + cells;          // [2 * FF_T]
+    int* q_count = queue + 2 * FF_T;
+
+    const int tid = threadIdx.x, pix = blockIdx.x;
+    const FfGeom g = to_geom(q.g);
+    if (tid == 0) {
+        ff_build_frames(g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
+        *q_count = 0;
+    }
+    for (int c = tid; c < cells; c += FF_T) win_idx[c] = -1;
+    const int n_rays = q.ang.nth * q.ang.nph;
+    int base = 0, st = 0;
+    for (;;) {
+        __syncthreads();                                   // (A) queue counter and tables are stable
+        const int cnt = *q_count;
+        if (cnt < FF_T && base < n_rays) {
+            // fill: cheap aperture test on FF_T candidate rays, survivors appended to the queue
+            const int r = base + tid;
+            bool ok = false;
+            if (r < n_rays) {
+                vec3 Pa;
+                double t_ap;
+                ok = ff_aperture(g, *fr, ray_dir(q.ang, r), t_ap, Pa);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            const int lane = tid & 31;
+            int slot = 0;
+            if (lane == 0 && m) slot = atomicAdd(q_count, __popc(m));
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (ok) queue[slot + __popc(m & ((1u << lane) - 1u))] = r;
+            base += FF_T;
+            continue;
+        }
+        if (cnt == 0) break;
+        const int n_take = min(cnt, FF_T);
+        const int r = tid < n_take ? queue[cnt - 1 - tid] : -1;
+        __syncthreads();                                   // (B) everybody has read the queue
+        if (tid == 0) *q_count = cnt - n_take;
+        int cell = -1;
+        double opl = 0.0;
+        if (r >= 0) {
+            const vec3 d = ray_dir(q.ang, r);
+            vec3 Pa;
+            double t_ap;
+            ff_aperture(g, *fr, d, t_ap, Pa);
+            FfRay ray;
+            ff_ray_trace<false, false>(*fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+            st |= ray.status;
+            opl = ray.opl;
+            if (opl != 0.0)                                                        // ffl:10
+                cell = ff_cell(ray.foc.x - fr->centre[0], ray.foc.z - fr->centre[2], q.gx, q.gy, q.M, q.gx_max, q.gy_max);
+            if (cell >= 0) atomicMax(win_idx + cell, r);                           // ffl:28: last write wins
+        }
+        __syncthreads();                                   // (C) winners of this batch are known
+        if (cell >= 0 && win_idx[cell] == r) win_opl[cell] = opl;
+    }
+    // winners-only phasor sum: sum_cells exp(i k L/1e3) * E_rec / M^2   (ff_sim.py:215-221)
+    double re[1] = {0.0}, im[1] = {0.0};
+    for (int c = tid; c < cells; c += FF_T) {
+        if (win_idx[c] >= 0) {
+            double cs, sn;
+            cis_large(q.k * win_opl[c] / 1e3, cs, sn);
+            const double2 e = __ldg(q.e_rec + c);
+            re[0] += cs * e.x - sn * e.y;
+            im[0] += cs * e.y + sn * e.x;
+        }
+    }
+    if (st) atomicOr(q.status, st);
+    __shared__ double2 total;
+    block_reduce_store<1>(re, im, &total);
+    if (tid == 0) {
+        const double inv = 1.0 / ((double)q.M * (double)q.M);
+        const double a = total.x * inv, b = total.y * inv;
+        q.amp[pix] = hypot(a, b);
+        q.phase[pix] = atan2(b, a);
+    }
+}
+
+static size_t ff_map_smem(int M)
+{
+    const size_t cells = (size_t)M * M;
+    return ((sizeof(FfFrames) + 15) / 16) * 16 + cells * sizeof(double) + cells * sizeof(int) + (2 * FF_T + 4) * sizeof(int);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 peak microbenchmark
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int solat_abi_version(void) { return SOLAT_ABI_VERSION; }
+const char* solat_last_error(void) { return g_err.c_str(); }
+long long solat_launch_count(void) { return g_launches.load(); }
+
+int solat_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int solat_ctx_create(int device, solat_ctx** out)
+{
+    if (!out) return fail(SOLAT_ERR_ARG, "ctx out pointer is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(SOLAT_ERR_NODEV, "no CUDA device", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(SOLAT_ERR_ARG, "device index out of range");
+    solat_ctx* c = new solat_ctx();
+    c->device = device;
+    CK(cudaSetDevice(device));
+    CK(cudaGetDeviceProperties(&c->prop, device));
+    if (c->prop.major != 10) {
+        delete c;
+        return fail(SOLAT_ERR_NODEV, "libsolat_b200 is built for sm_100a only");
+    }
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return SOLAT_OK;
+}
+void solat_ctx_destroy(solat_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+int solat_ctx_info(const solat_ctx* c, int* sm, int* maj, int* min_, long long* hbm)
+{
+    if (!c) return fail(SOLAT_ERR_ARG, "ctx is NULL");
+    if (sm) *sm = c->prop.multiProcessorCount;
+    if (maj) *maj = c->prop.major;
+    if (min_) *min_ = c->prop.minor;
+    if (hbm) *hbm = (long long)c->prop.totalGlobalMem;
+    return SOLAT_OK;
+}
+
+int solat_fp64_peak(solat_ctx* c, int repeats, double* tflops)
+{
+    if (!c || !tflops) return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    const int blocks = c->prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    DevBuf<double> out;
+    if (int rc = out.reserve((size_t)blocks * threads)) return rc;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int r = 0; r < repeats + 2; r++) {
+        CK(cudaEventRecord(e0, c->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, c->stream>>>(out.p, iters, 0.999999, 1e-9);
+        LAUNCHED();
+        CK(cudaEventRecord(e1, c->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 64.0 * iters * (double)blocks * threads;
+        if (r >= 2) best = fmax(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = best;
+    return SOLAT_OK;
+}
+
+// ---------------------------------------------------------------- near field rows
+static int nf_rows(solat_ctx* c, int kind, const solat_nf_geom* g, const double* p, const double* theta, int nth,
+                   const double* phi, int nph, double* out, int* status)
+{
+    if (!c || !g || !p || !theta || !phi || !out || nth <= 0 || nph < 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    const int rows = kind == NF_RX ? 20 : (kind == NF_SOURCE ? 26 : 32);
+    const int nphi = nph == 0 ? nth : nph;                 // paired mode: phi has nth entries
+    const size_t n = nph == 0 ? (size_t)nth : (size_t)nth * nph;
+    AngleTabsOwner ang;
+    if (int rc = ang.init(theta, nth, phi, nph, c->stream)) return rc;
+    DevBuf<double> d_raw, d_out;
+    DevBuf<int> d_st;
+    std::vector<double> raw(nth + nphi);
+    memcpy(raw.data(), theta, sizeof(double) * nth);
+    memcpy(raw.data() + nth, phi, sizeof(double) * nphi);
+    if (int rc = d_raw.upload(raw.data(), raw.size(), c->stream)) return rc;
+    if (int rc = d_out.reserve(rows * n)) return rc;
+    if (status) if (int rc = d_st.reserve(n)) return rc;
+    NfRowsParams q;
+    q.ang = ang.tabs; q.theta = d_raw.p; q.phi = d_raw.p + nth;
+    q.p[0] = p[0]; q.p[1] = p[1]; q.p[2] = p[2];
+    q.n_si = g->n_si; q.n_vac = g->n_vac; q.y_ap = g->y_ap;
+    const double sig = g->th_fwhp / sqrt(8 * log(2.0));
+    q.inv_2sig2 = 0.5 / (sig * sig);
+    // np.mean over the raveled meshgrid == mean of the 1-D axis
+    double mt = 0, mp = 0;
+    for (int i = 0; i < nth; i++) mt += theta[i];
+    for (int j = 0; j < nphi; j++) mp += phi[j];
+    q.th_mean = mt / nth; q.ph_mean = mp / nphi;
+    q.out = d_out.p; q.status = status ? d_st.p : nullptr;
+    const int threads = 128, blocks = (int)((n + threads - 1) / threads);
+    if (kind == NF_RX) nf_rows_kernel<NF_RX><<<blocks, threads, 0, c->stream>>>(q);
+    else if (kind == NF_SOURCE) nf_rows_kernel<NF_SOURCE><<<blocks, threads, 0, c->stream>>>(q);
+    else nf_rows_kernel<NF_TOY><<<blocks, threads, 0, c->stream>>>(q);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(out, d_out.p, rows * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (status) CK(cudaMemcpyAsync(status, d_st.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SOLAT_OK;
+}
+int solat_nf_rx_trace(solat_ctx* c, const solat_nf_geom* g, const double p[3], const double* th, int nth,
+                      const double* ph, int nph, double* out, int* st)
+{
+    return nf_rows(c, NF_RX, g, p, th, nth, ph, nph, out, st);
+}
+int solat_nf_source_trace(solat_ctx* c, const solat_nf_geom* g, const double p[3], const double* th, int nth,
+                          const double* ph, int nph, double* out, int* st)
+{
+    return nf_rows(c, NF_SOURCE, g, p, th, nth, ph, nph, out, st);
+}
+int solat_nf_toy_trace(solat_ctx* c, const solat_nf_geom* g, const double p[3], const double* th, int nth,
+                       const double* ph, int nph, double* out, int* st)
+{
+    return nf_rows(c, NF_TOY, g, p, th, nth, ph, nph, out, st);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- near field map plan
+struct solat_nf_plan {
+    solat_ctx* ctx;
+    solat_nf_geom g;
+    AngleTabsOwner ang;
+    DevBuf<int> act_idx;
+    DevBuf<double2> act_rx;
+    DevBuf<double2> partial;
+    DevBuf<double> h_src, h_amp, h_phase;   // device staging for the host entry point
+    DevBuf<int> status;
+    std::vector<double> kk;
+    int n_act = 0, tiles = 1, tile_len = 0, threads = 256;
+};
+
+// choose (tiles) so that the ray loop fills its CTA and the grid has enough CTAs for all SMs
+static void nf_choose_tiling(solat_nf_plan* p, int npix)
+{
+    const int sms = p->ctx->prop.multiProcessorCount, resident = 2 * sms;
+    double best = -1.0;
+    int best_tiles = 1;
+    for (int tiles = 1; tiles <= 64; tiles++) {
+        const int len = (p->n_act + tiles - 1) / tiles;
+        if (len < p->threads && tiles > 1) break;
+        const int iters = (len + p->threads - 1) / p->threads;
+        const double thread_eff = (double)p->n_act / ((double)tiles * iters * p->threads);
+        const double waves = (double)npix * tiles / resident;
+        const double tail_eff = waves / ceil(waves);
+        const double score = thread_eff * tail_eff;
+        if (score > best + 1e-9) { best = score; best_tiles = tiles; }
+    }
+    p->tiles = best_tiles;
+    p->tile_len = (p->n_act + best_tiles - 1) / best_tiles;
+}
+
+static int nf_map_launch(solat_nf_plan* p, const double* d_src, int npix, double* d_amp, double* d_phase, cudaStream_t s)
+{
+    CK(cudaSetDevice(p->ctx->device));
+    const int nfreq = (int)p->kk.size();
+    if (p->n_act == 0) {   // nothing passes the receiver mask: the reference returns amp 0, phase 0
+        CK(cudaMemsetAsync(d_amp, 0, sizeof(double) * npix * nfreq, s));
+        CK(cudaMemsetAsync(d_phase, 0, sizeof(double) * npix * nfreq, s));
+        return SOLAT_OK;
+    }
+    nf_choose_tiling(p, npix);
+    if (int rc = p->partial.reserve((size_t)npix * p->tiles * nfreq)) return rc;
+    NfMapParams q;
+    q.ang = p->ang.tabs; q.src_xz = d_src; q.act_idx = p->act_idx.p; q.act_rx = p->act_rx.p;
+    q.y_ap = p->g.y_ap; q.n_si = p->g.n_si; q.n_vac = p->g.n_vac;
+    q.n_act = p->n_act; q.tiles = p->tiles; q.tile_len = p->tile_len; q.nfreq_total = nfreq;
+    q.partial = p->partial.p; q.status = p->status.p;
+    const int grid = npix * p->tiles;
+    for (int f0 = 0; f0 < nfreq; f0 += NF_MAXF) {
+        const int nf = std::min(NF_MAXF, nfreq - f0);
+        q.f0 = f0;
+        for (int f = 0; f < NF_MAXF; f++) q.kk[f] = f < nf ? p->kk[f0 + f] / 1e3 : 0.0;
+        switch (nf) {
+        case 1: nf_map_kernel<1><<<grid, p->threads, 0, s>>>(q); break;
+        case 2: nf_map_kernel<2><<<grid, p->threads, 0, s>>>(q); break;
+        case 3: nf_map_kernel<3><<<grid, p->threads, 0, s>>>(q); break;
+        default: nf_map_kernel<4><<<grid, p->threads, 0, s>>>(q); break;
+        }
+        LAUNCHED();
+    }
+    const int tot = npix * nfreq;
+    nf_finalize_kernel<<<(tot + 127) / 128, 128, 0, s>>>(p->partial.p, npix, p->tiles, nfreq, d_amp, d_phase);
+    LAUNCHED();
+    return SOLAT_OK;
+}
+
+extern "C" {
+
+int solat_nf_plan_create(solat_ctx* c, const solat_nf_geom* g, const double* theta, int nth, const double* phi, int nph,
+                         const double* rx_opl, const double* rx_w, const double* k_per_m, int nfreq,
+                         solat_nf_plan** out)
+{
+    if (!c || !g || !theta || !phi || !rx_opl || !rx_w || !k_per_m || !out || nth <= 0 || nph <= 0 || nfreq <= 0)
+        return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    solat_nf_plan* p = new solat_nf_plan();
+    p->ctx = c; p->g = *g;
+    p->kk.assign(k_per_m, k_per_m + nfreq);
+    int rc = p->ang.init(theta, nth, phi, nph, c->stream);
+    const size_t n = (size_t)nth * nph;
+    std::vector<int> idx;
+    std::vector<double2> rx;
+    idx.reserve(n); rx.reserve(n);
+    for (size_t r = 0; r < n; r++)
+        if (rx_w[r] != 0.0) { idx.push_back((int)r); rx.push_back(make_double2(rx_opl[r], rx_w[r])); }
+    p->n_act = (int)idx.size();
+    if (!rc && p->n_act) rc = p->act_idx.upload(idx.data(), idx.size(), c->stream);
+    if (!rc && p->n_act) rc = p->act_rx.upload(rx.data(), rx.size(), c->stream);
+    if (!rc) rc = p->status.reserve(1);
+    if (!rc && cudaMemsetAsync(p->status.p, 0, sizeof(int), c->stream) != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "memset");
+    if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "sync");
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return SOLAT_OK;
+}
+void solat_nf_plan_destroy(solat_nf_plan* p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    delete p;
+}
+int solat_nf_plan_active_rays(const solat_nf_plan* p) { return p ? p->n_act : 0; }
+
+int solat_nf_map_device(solat_nf_plan* p, const double* d_src, int npix, double* d_amp, double* d_phase, void* stream)
+{
+    if (!p || !d_src || !d_amp || !d_phase || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    return nf_map_launch(p, d_src, npix, d_amp, d_phase, (cudaStream_t)stream);
+}
+int solat_nf_plan_status(solat_nf_plan* p, int* status)
+{
+    if (!p || !status) return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(p->ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(status, p->status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(p->status.p, 0, sizeof(int)));
+    return SOLAT_OK;
+}
+int solat_nf_map_host(solat_nf_plan* p, const double* src_xz, int npix, double* amp, double* phase, int* status)
+{
+    if (!p || !src_xz || !amp || !phase || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(p->ctx->device));
+    cudaStream_t s = p->ctx->stream;
+    const size_t nf = p->kk.size();
+    if (int rc = p->h_src.upload(src_xz, 2 * (size_t)npix, s)) return rc;
+    if (int rc = p->h_amp.reserve(nf * npix)) return rc;
+    if (int rc = p->h_phase.reserve(nf * npix)) return rc;
+    if (int rc = nf_map_launch(p, p->h_src.p, npix, p->h_amp.p, p->h_phase.p, s)) return rc;
+    CK(cudaMemcpyAsync(amp, p->h_amp.p, nf * npix * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(phase, p->h_phase.p, nf * npix * sizeof(double), cudaMemcpyDeviceToHost, s));
+    int st = 0;
+    CK(cudaMemcpyAsync(&st, p->status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (st) CK(cudaMemset(p->status.p, 0, sizeof(int)));
+    if (status) *status = st;
+    return SOLAT_OK;
+}
+
+// ---------------------------------------------------------------- far field rows
+static int ff_rows(solat_ctx* c, bool stage1, const solat_ff_geom* g, const double* theta, int nth, const double* phi,
+                   int nph, const double* centre, const int* pidx1, const int* pidx2, const double* pan1, int np1,
+                   const double* pan2, int np2, double el, double az, double* out, int* status)
+{
+    if (!c || !g || !theta || !phi || !out || nth <= 0 || nph < 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    if (!stage1 && (!centre || !pidx1 || !pidx2 || !pan1 || !pan2 || np1 <= 0 || np2 <= 0))
+        return fail(SOLAT_ERR_ARG, "bad panel argument");
+    CK(cudaSetDevice(c->device));
+    const size_t n = nph == 0 ? (size_t)nth : (size_t)nth * nph;
+    const int rows = stage1 ? 9 : 17;
+    AngleTabsOwner ang;
+    if (int rc = ang.init(theta, nth, phi, nph, c->stream)) return rc;
+    DevBuf<double> d_out, d_p1, d_p2;
+    DevBuf<int> d_i1, d_i2, d_st;
+    if (int rc = d_out.reserve(rows * n)) return rc;
+    if (status) if (int rc = d_st.reserve(n)) return rc;
+    FfRowsParams q;
+    memset(&q, 0, sizeof(q));
+    q.ang = ang.tabs; q.g = *g; q.el = el; q.az = az;
+    if (!stage1) {
+        for (int i = 0; i < 3; i++) q.centre[i] = centre[i];
+        if (int rc = d_i1.upload(pidx1, n, c->stream)) return rc;
+        if (int rc = d_i2.upload(pidx2, n, c->stream)) return rc;
+        if (int rc = d_p1.upload(pan1, 10 * (size_t)np1, c->stream)) return rc;
+        if (int rc = d_p2.upload(pan2, 10 * (size_t)np2, c->stream)) return rc;
+        q.pidx1 = d_i1.p; q.pidx2 = d_i2.p; q.pan1 = d_p1.p; q.pan2 = d_p2.p; q.np1 = np1; q.np2 = np2;
+    }
+    q.out = d_out.p; q.status = status ? d_st.p : nullptr;
+    const int threads = 128, blocks = (int)((n + threads - 1) / threads);
+    if (stage1) ff_rows_kernel<true><<<blocks, threads, 0, c->stream>>>(q);
+    else ff_rows_kernel<false><<<blocks, threads, 0, c->stream>>>(q);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(out, d_out.p, rows * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (status) CK(cudaMemcpyAsync(status, d_st.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SOLAT_OK;
+}
+int solat_ff_ray_mirror_pts(solat_ctx* c, const solat_ff_geom* g, const double* th, int nth, const double* ph, int nph,
+                            double el, double az, double* out9, int* status)
+{
+    return ff_rows(c, true, g, th, nth, ph, nph, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, el, az, out9, status);
+}
+int solat_ff_apert_fields(solat_ctx* c, const solat_ff_geom* g, const double* th, int nth, const double* ph, int nph,
+                          const double centre[3], const int* pidx1, const int* pidx2, const double* pan1, int np1,
+                          const double* pan2, int np2, double el, double az, double* out17, int* status)
+{
+    return ff_rows(c, false, g, th, nth, ph, nph, centre, pidx1, pidx2, pan1, np1, pan2, np2, el, az, out17, status);
+}
+
+static void grid_max(const double* data_x, const double* data_y, int M, double* gx_max, double* gy_max)
+{
+    double a = data_x[0], b = data_y[0];
+    for (int i = 1; i < M; i++) { a = fmax(a, data_x[i]); b = fmax(b, data_y[(size_t)i * M]); }   // ffl:19
+    *gx_max = a; *gy_max = b;
+}
+
+int solat_ff_project(solat_ctx* c, const double* sim, int n_pts, const double* data_x, const double* data_y, int M,
+                     double k, double* out_reim)
+{
+    if (!c || !sim || !data_x || !data_y || !out_reim || n_pts <= 0 || M <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int cells = M * M;
+    DevBuf<double> d_sim, d_gx, d_gy;
+    DevBuf<int> d_win;
+    DevBuf<double2> d_out;
+    if (int rc = d_sim.upload(sim, 17 * (size_t)n_pts, s)) return rc;
+    if (int rc = d_gx.upload(data_x, M, s)) return rc;
+    if (int rc = d_gy.upload(data_y, cells, s)) return rc;
+    if (int rc = d_win.reserve(cells)) return rc;
+    if (int rc = d_out.reserve(cells)) return rc;
+    CK(cudaMemsetAsync(d_win.p, 0xff, sizeof(int) * cells, s));
+    double gx_max, gy_max;
+    grid_max(data_x, data_y, M, &gx_max, &gy_max);
+    ff_project_scatter_kernel<<<(n_pts + 127) / 128, 128, 0, s>>>(d_sim.p, n_pts, d_gx.p, d_gy.p, M, gx_max, gy_max, d_win.p);
+    LAUNCHED();
+    ff_project_fill_kernel<<<(cells + 127) / 128, 128, 0, s>>>(d_sim.p, n_pts, d_win.p, cells, k, d_out.p);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(out_reim, d_out.p, sizeof(double2) * cells, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SOLAT_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- far field map plan
+struct solat_ff_plan {
+    solat_ctx* ctx;
+    solat_ff_geom g;
+    AngleTabsOwner ang;
+    DevBuf<double> gx, gy;
+    DevBuf<double2> e_rec;
+    DevBuf<double> h_azel, h_amp, h_phase;
+    DevBuf<int> status;
+    double gx_max, gy_max, k;
+    int M;
+    size_t smem;
+};
+
+static int ff_map_launch(solat_ff_plan* p, const double* d_azel, int npix, double* d_amp, double* d_phase, cudaStream_t s)
+{
+    CK(cudaSetDevice(p->ctx->device));
+    FfMapParams q;
+    q.ang = p->ang.tabs; q.g = p->g; q.azel = d_azel; q.gx = p->gx.p; q.gy = p->gy.p; q.e_rec = p->e_rec.p;
+    q.gx_max = p->gx_max; q.gy_max = p->gy_max; q.k = p->k; q.M = p->M;
+    q.amp = d_amp; q.phase = d_phase; q.status = p->status.p;
+    ff_map_kernel<<<npix, FF_T, p->smem, s>>>(q);
+    LAUNCHED();
+    return SOLAT_OK;
+}
+
+extern "C" {
+
+int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* theta, int nth, const double* phi, int nph,
+                         const double* data_x, const double* data_y, const double* e_rec, int M, double k,
+                         solat_ff_plan** out)
+{
+    if (!c || !g || !theta || !phi || !data_x || !data_y || !e_rec || !out || nth <= 0 || nph <= 0 || M <= 0)
+        return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    const size_t smem = ff_map_smem(M);
+    if (smem > (size_t)c->prop.sharedMemPerBlockOptin)
+        return fail(SOLAT_ERR_ARG, "E_rec grid too large for the shared-memory winner table (M <= 136)");
+    CK(cudaFuncSetAttribute(ff_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    solat_ff_plan* p = new solat_ff_plan();
+    p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem;
+    grid_max(data_x, data_y, M, &p->gx_max, &p->gy_max);
+    cudaStream_t s = c->stream;
+    int rc = p->ang.init(theta, nth, phi, nph, s);
+    if (!rc) rc = p->gx.upload(data_x, M, s);                      // data_x[0, :]
+    if (!rc) rc = p->gy.upload(data_y, (size_t)M * M, s);
+    if (!rc) rc = p->e_rec.upload(reinterpret_cast<const double2*>(e_rec), (size_t)M * M, s);
+    if (!rc) rc = p->status.reserve(1);
+    if (!rc && cudaMemsetAsync(p->status.p, 0, sizeof(int), s) != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "memset");
+    if (!rc && cudaStreamSynchronize(s) != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "sync");
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return SOLAT_OK;
+}
+void solat_ff_plan_destroy(solat_ff_plan* p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    delete p;
+}
+int solat_ff_map_device(solat_ff_plan* p, const double* d_azel, int npix, double* d_amp, double* d_phase, void* stream)
+{
+    if (!p || !d_azel || !d_amp || !d_phase || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    return ff_map_launch(p, d_azel, npix, d_amp, d_phase, (cudaStream_t)stream);
+}
+int solat_ff_plan_status(solat_ff_plan* p, int* status)
+{
+    if (!p || !status) return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(p->ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(status, p->status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(p->status.p, 0, sizeof(int)));
+    return SOLAT_OK;
+}
+int solat_ff_map_host(solat_ff_plan* p, const double* azel, int npix, double* amp, double* phase, int* status)
+{
+    if (!p || !azel || !amp || !phase || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(p->ctx->device));
+    cudaStream_t s = p->ctx->stream;
+    if (int rc = p->h_azel.upload(azel, 2 * (size_t)npix, s)) return rc;
+    if (int rc = p->h_amp.reserve(npix)) return rc;
+    if (int rc = p->h_phase.reserve(npix)) return rc;
+    if (int rc = ff_map_launch(p, p->h_azel.p, npix, p->h_amp.p, p->h_phase.p, s)) return rc;
+    CK(cudaMemcpyAsync(amp, p->h_amp.p, npix * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(phase, p->h_phase.p, npix * sizeof(double), cudaMemcpyDeviceToHost, s));
+    int st = 0;
+    CK(cudaMemcpyAsync(&st, p->status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (st) CK(cudaMemset(p->status.p, 0, sizeof(int)));
+    if (status) *status = st;
+    return SOLAT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,353 @@
+"""Whole-map plans and multi-GPU sharding.
+
+Replaces the reference's MPI master/worker fan-out (scripts/holo_sim.py:87-189,
+scripts/ff_sim.py:135-227, scripts/beamsim_set.sh): the scan-pixel list is cut into contiguous
+blocks, one per rank (one process per GPU under torchrun), every rank runs ONE fused kernel over
+its block, and a single gather (NCCL over NVLink; gloo in the CPU tests) brings (amp, phase) to
+rank 0.  Pixels are independent, so there is no other exchange step.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib
+from . import ray_trace_int as rti
+
+R_LYOT = 136.54 / 2  # scripts/holo_sim.py:168
+
+
+class PlotOpts:
+    """Same role as the class in scripts/holo_sim.py:25-31 (no plotting)."""
+
+    plot = 0
+    color = "darkorange"
+    alpha = 0.2
+
+
+# ------------------------------------------------------------------------------------------------
+# sharding / gather
+# ------------------------------------------------------------------------------------------------
+def shard_bounds(n_items, rank, world_size):
+    """Contiguous block [lo, hi) of the flattened pixel index owned by `rank`."""
+    blk = -(-n_items // world_size)
+    lo = min(rank * blk, n_items)
+    return lo, min(lo + blk, n_items)
+
+
+def dist_info():
+    """(rank, world_size) from torch.distributed if initialised, else from the torchrun env, else (0, 1)."""
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def gather_blocks(local, n_items, dst=0):
+    """Gather per-rank blocks (torch tensors [n_local, C], block layout of shard_bounds) to rank `dst`.
+    Returns the [n_items, C] tensor on `dst`, None elsewhere.  One collective."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local[:n_items]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    blk = -(-n_items // world)
+    pad = torch.zeros((blk, local.shape[1]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, out, dst=dst)
+    if rank != dst:
+        return None
+    return torch.cat(out, dim=0)[:n_items]
+
+
+# ------------------------------------------------------------------------------------------------
+# near field
+# ------------------------------------------------------------------------------------------------
+def holo_tele_geo(freq, n_scan=100):
+    """tele_geo exactly as scripts/holo_sim.py:34-57 sets it up for `freq` [GHz]."""
+    from . import ot_geo
+
+    tg = ot_geo.LatGeo()
+    if freq <= 120:
+        tg.y_ap = -1213 - (6.5 * 10)
+        tg.th_fwhp = 40.5 * np.pi / 180
+    else:
+        tg.y_ap = -1213 - (12.2 * 10)
+        tg.th_fwhp = 25 * np.pi / 180
+    tg.x_ap = 0
+    tg.z_ap = 0
+    tg.lambda_ = 0.299792458 / freq
+    tg.k = 2 * np.pi / tg.lambda_
+    tg.n_scan = n_scan
+    return tg
+
+
+def receiver_field(tele_geo, p_rx=(0, 0, 0), n_scan_rx=None, n_scan_so=None):
+    """(rx_opl, rx_w) in the source's ray-index space: the pixel-independent half of
+    scripts/holo_sim.py:157-180 (rx trace -> regrid -> Lyot mask x feed taper)."""
+    n_so = int(tele_geo.n_scan if n_scan_so is None else n_scan_so)
+    n_rx = int(n_so if n_scan_rx is None else n_scan_rx)
+    keep = tele_geo.n_scan
+    try:
+        tele_geo.n_scan = n_rx
+        out_rx = rti.rx_to_lyot_model(list(p_rx), tele_geo, PlotOpts).output()
+    finally:
+        tele_geo.n_scan = keep
+    so_like = np.zeros((26, n_so * n_so))
+    _, rx_new = rti.regrid(out_rx, so_like)   # second return value carries the rx field (rti:1435-1438)
+    lyot_r = np.sqrt(rx_new[0, :] ** 2 + rx_new[2, :] ** 2)
+    w = np.where(lyot_r <= R_LYOT, rx_new[4, :], 0.0)
+    return np.ascontiguousarray(rx_new[3, :]), np.ascontiguousarray(w)
+
+
+class NearFieldPlan:
+    """Fused near-field map: per source position sum_rays w_rx exp(i k (L_rx + L_source)/1e3).
+    `k_per_m`: one or several wavenumbers [rad/m] sharing the geometry (same y_ap)."""
+
+    def __init__(self, tele_geo, k_per_m, rx_opl, rx_w, n_scan=None, device=None):
+        lib = _lib.load()
+        self.ctx = _lib.context(device)
+        n = int(tele_geo.n_scan if n_scan is None else n_scan)
+        self.n_scan = n
+        axis = np.linspace((np.pi / 2) - 0.22, (np.pi / 2) + 0.22, n)   # rti:908-909
+        self.k = _lib.as_f64(np.atleast_1d(k_per_m))
+        rx_opl = _lib.as_f64(rx_opl)
+        rx_w = _lib.as_f64(rx_w)
+        if rx_opl.shape != (n * n,) or rx_w.shape != (n * n,):
+            raise ValueError("receiver field must have n_scan^2 entries")
+        geom = _lib.nf_geom(tele_geo)
+        h = _lib.c_vp()
+        _lib.check(lib.solat_nf_plan_create(self.ctx.handle, ctypes.byref(geom), _lib.dptr(axis), n, _lib.dptr(axis), n,
+                                            _lib.dptr(rx_opl), _lib.dptr(rx_w), _lib.dptr(self.k), self.k.size,
+                                            ctypes.byref(h)))
+        self.handle = h
+        self.active_rays = int(lib.solat_nf_plan_active_rays(h))
+
+    def run(self, src_xz, amp=None, phase=None):
+        """Host buffers in, host buffers out (copies inside).  Returns amp, phase [nfreq, npix], status."""
+        src = _lib.as_f64(np.reshape(src_xz, (-1, 2)))
+        npix = src.shape[0]
+        amp = np.empty((self.k.size, npix)) if amp is None else amp
+        phase = np.empty((self.k.size, npix)) if phase is None else phase
+        st = _lib.c_i(0)
+        _lib.check(_lib.load().solat_nf_map_host(self.handle, _lib.dptr(src), npix, _lib.dptr(amp), _lib.dptr(phase),
+                                                 ctypes.byref(st)))
+        return amp, phase, st.value
+
+    def run_device(self, d_src, d_amp, d_phase, stream=0):
+        """torch CUDA float64 tensors ([npix,2], [nfreq*npix], [nfreq*npix]); asynchronous on `stream`."""
+        npix = d_src.shape[0]
+        _lib.check(_lib.load().solat_nf_map_device(self.handle, d_src.data_ptr(), npix, d_amp.data_ptr(),
+                                                   d_phase.data_ptr(), stream))
+
+    def status(self):
+        st = _lib.c_i(0)
+        _lib.check(_lib.load().solat_nf_plan_status(self.handle, ctypes.byref(st)))
+        return st.value
+
+    def close(self):
+        if self.handle:
+            _lib.load().solat_nf_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def holo_pixels(res=51, sweep=100, shift=0):
+    """Source-position grid of scripts/holo_sim.py:90-108: row index i*res+j <-> (x_i, z_j)."""
+    rx = np.linspace(-sweep / 2 + shift, sweep / 2 + shift, res)
+    xx, zz = np.meshgrid(rx, rx, indexing="ij")
+    return np.stack([xx.ravel(), zz.ravel()], axis=1)
+
+
+def holo_map(freqs, res=51, sweep=100, shift=0, n_scan=100, n_scan_rx=None, p_rx=(0, 0, 0), device=None,
+             strict=False):
+    """Near-field holography map(s) for one band.  `freqs`: scalar or list of GHz values that share
+    the band geometry (holo_sim.py:40-45).  Shards over ranks when torch.distributed is initialised.
+    Returns on rank 0: (pixels [npix,2], amp [nfreq,npix], phase [nfreq,npix]); None elsewhere."""
+    freqs = np.atleast_1d(np.asarray(freqs, dtype=np.float64))
+    geos = [holo_tele_geo(f, n_scan) for f in freqs]
+    if len({g.y_ap for g in geos}) != 1:
+        raise ValueError("frequencies of different bands (y_ap differs) need separate maps")
+    tg = geos[0]
+    # the feed taper differs per band only; one geometry -> one rx field
+    rx_opl, rx_w = receiver_field(tg, p_rx, n_scan_rx, n_scan)
+    plan = NearFieldPlan(tg, [g.k for g in geos], rx_opl, rx_w, n_scan, device)
+    pixels = holo_pixels(res, sweep, shift)
+    rank, world = dist_info()
+    lo, hi = shard_bounds(len(pixels), rank, world)
+    if hi > lo:
+        amp, phase, st = plan.run(pixels[lo:hi])
+    else:
+        amp, phase, st = np.zeros((len(freqs), 0)), np.zeros((len(freqs), 0)), 0
+    _lib.raise_on_status(st, strict)
+    plan.close()
+    if world == 1:
+        return pixels, amp, phase
+    import torch
+
+    dev = _gather_device(plan.ctx.device)
+    local = torch.from_numpy(np.concatenate([amp.T, phase.T], axis=1)).to(dev)
+    full = gather_blocks(local, len(pixels))
+    if full is None:
+        return None
+    full = full.cpu().numpy()
+    nf = len(freqs)
+    return pixels, np.ascontiguousarray(full[:, :nf].T), np.ascontiguousarray(full[:, nf:].T)
+
+
+def _gather_device(device_index):
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", device_index)
+    return torch.device("cpu")
+
+
+# ------------------------------------------------------------------------------------------------
+# far field
+# ------------------------------------------------------------------------------------------------
+def ff_tele_geo(freq, offset):
+    """tele_geo as scripts/ff_sim.py:29-44,72-79 sets it up."""
+    from . import latrt_geo
+
+    tg = latrt_geo.initialize_telescope_geometry()
+    tg.rx_x = 0
+    tg.rx_z = 0
+    tg.rx_y = 0 - offset
+    tg.lambda_ = (30.0 / freq) * 0.01
+    tg.k = 2 * np.pi / tg.lambda_
+    tg.N_scan = 100
+    tg.x_tow, tg.y_tow, tg.z_tow = 0, -7.2, 100e3
+    tg.el0 = np.arctan(-tg.y_tow / tg.z_tow)
+    return tg
+
+
+def ff_fan(n_scan=100):
+    """Polar launch fan of scripts/ff_sim.py:64-66."""
+    return np.linspace(np.pi - 0.00005, np.pi + 0.00005, n_scan), np.linspace(0, np.pi, n_scan)
+
+
+def ff_pixels(tele_geo, res_arcmin, num):
+    """(az, el) grid of scripts/ff_sim.py:94,121-128: row index i*len+j <-> (az_i, el_j)."""
+    de_ang = res_arcmin / 60 * np.pi / 180
+    n = int(num)
+    azs = np.linspace(-n * de_ang + tele_geo.az0, n * de_ang + tele_geo.az0, 2 * n + 1)
+    els = np.linspace(-n * de_ang + tele_geo.el0, n * de_ang + tele_geo.el0, 2 * n + 1)
+    aa, ee = np.meshgrid(azs, els, indexing="ij")
+    return np.stack([aa.ravel(), ee.ravel()], axis=1)
+
+
+def near_field_to_e_rec(foc_fields):
+    """Turn a near-field .txt table into the (data_x, data_y, E_rec) of scripts/ff_sim.py:51-59,81-88."""
+    from . import phase_correct
+
+    foc_fields = np.asarray(foc_fields, dtype=np.float64)
+    n = int(np.sqrt(len(foc_fields)))
+    x = np.reshape(foc_fields[:, 1], (n, n)) / 1e1
+    y = np.reshape(foc_fields[:, 0], (n, n)) / 1e1
+    amp = np.reshape(foc_fields[:, 2], (n, n))
+    phi = np.reshape(foc_fields[:, 3], (n, n))
+    pnew = phase_correct.do_unwrap(phi * 180 / np.pi) * np.pi / 180
+    e_rec = abs(amp) * np.exp(complex(0, 1) * np.mod(pnew, 2 * np.pi))
+    return x, y, e_rec
+
+
+class FarFieldPlan:
+    """Fused far-field map: per (az, el) the winners-only sum of ff_sim.py:208-221."""
+
+    def __init__(self, tele_geo, theta, phi, data_x, data_y, e_rec, device=None):
+        lib = _lib.load()
+        self.ctx = _lib.context(device)
+        theta = _lib.as_f64(theta)
+        phi = _lib.as_f64(phi)
+        data_x = _lib.as_f64(np.real(data_x))
+        data_y = _lib.as_f64(np.real(data_y))
+        e = np.ascontiguousarray(e_rec, dtype=np.complex128)
+        m = data_x.shape[0]
+        if data_x.shape != (m, m) or data_y.shape != (m, m) or e.shape != (m, m):
+            raise ValueError("data_x, data_y, e_rec must be (M, M)")
+        self.n_rays = theta.size * phi.size
+        geom = _lib.ff_geom(tele_geo)
+        h = _lib.c_vp()
+        _lib.check(lib.solat_ff_plan_create(self.ctx.handle, ctypes.byref(geom), _lib.dptr(theta), theta.size,
+                                            _lib.dptr(phi), phi.size, _lib.dptr(data_x), _lib.dptr(data_y),
+                                            e.ctypes.data_as(_lib.c_dp), m, float(tele_geo.k), ctypes.byref(h)))
+        self.handle = h
+
+    def run(self, azel, amp=None, phase=None):
+        azel = _lib.as_f64(np.reshape(azel, (-1, 2)))
+        npix = azel.shape[0]
+        amp = np.empty(npix) if amp is None else amp
+        phase = np.empty(npix) if phase is None else phase
+        st = _lib.c_i(0)
+        _lib.check(_lib.load().solat_ff_map_host(self.handle, _lib.dptr(azel), npix, _lib.dptr(amp), _lib.dptr(phase),
+                                                 ctypes.byref(st)))
+        return amp, phase, st.value
+
+    def run_device(self, d_azel, d_amp, d_phase, stream=0):
+        _lib.check(_lib.load().solat_ff_map_device(self.handle, d_azel.data_ptr(), d_azel.shape[0], d_amp.data_ptr(),
+                                                   d_phase.data_ptr(), stream))
+
+    def status(self):
+        st = _lib.c_i(0)
+        _lib.check(_lib.load().solat_ff_plan_status(self.handle, ctypes.byref(st)))
+        return st.value
+
+    def close(self):
+        if self.handle:
+            _lib.load().solat_ff_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ff_map(freq, res_arcmin, num, offset, data_x, data_y, e_rec, n_scan=100, device=None, strict=False):
+    """Far-field beam map `ff_sim.py <freq> <res> <num> <offset>`.  Returns on rank 0
+    (pixels [npix,2] (az, el), amp [npix], phase [npix]); None on the other ranks."""
+    tg = ff_tele_geo(freq, offset)
+    theta, phi = ff_fan(n_scan)
+    plan = FarFieldPlan(tg, theta, phi, data_x, data_y, e_rec, device)
+    pixels = ff_pixels(tg, res_arcmin, num)
+    rank, world = dist_info()
+    lo, hi = shard_bounds(len(pixels), rank, world)
+    if hi > lo:
+        amp, phase, st = plan.run(pixels[lo:hi])
+    else:
+        amp, phase, st = np.zeros(0), np.zeros(0), 0
+    _lib.raise_on_status(st, strict)
+    plan.close()
+    if world == 1:
+        return pixels, amp, phase
+    import torch
+
+    dev = _gather_device(plan.ctx.device)
+    local = torch.from_numpy(np.stack([amp, phase], axis=1)).to(dev)
+    full = gather_blocks(local, len(pixels))
+    if full is None:
+        return None
+    full = full.cpu().numpy()
+    return pixels, np.ascontiguousarray(full[:, 0]), np.ascontiguousarray(full[:, 1])
+
+
+def save_map_txt(path, c0, c1, amp, phase):
+    """The reference's output format (holo_sim.py:131-139, ff_sim.py:181-189): 4 columns, %.18e."""
+    d = os.path.dirname(path)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    np.savetxt(path, np.c_[np.ravel(c0), np.ravel(c1), np.ravel(amp), np.ravel(phase)])

@@ -1,0 +1,193 @@
+// Host shadow of the device math: compiles solat_optics_b200/csrc/solat_math.cuh with g++ so that the
+// EXACT per-ray source the kernels run can be checked against the golden fixtures in a container that
+// has no GPU.  Test infrastructure only (built into tests/_build/, never shipped, never loaded by the
+// product package).  The loops here stand in for the CUDA grid; they carry no arithmetic of their own.
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "../../solat_optics_b200/csrc/solat_math.cuh"
+
+using namespace solat;
+#define API extern "C" __attribute__((visibility("default")))
+
+API int shadow_nf_source_rows(const double* p, const double* th, int nth, const double* ph, int nph, double n_si,
+                              double n_vac, double* out, int* status)
+{
+    const int n = nth * nph;
+    int agg = 0;
+    for (int r = 0; r < n; r++) {
+        const int i = r % nth, j = r / nth;
+        NfSourceRay ray;
+        vec3 p0 = mk(p[0], p[1], p[2]);
+        nf_source_ray(p0, launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), n_si, n_vac, ray);
+        double rows[26];
+        pack_nf_source_rows(ray, p0, n_si, n_vac, rows);
+        for (int k = 0; k < 26; k++) out[(size_t)k * n + r] = rows[k];
+        if (status) status[r] = ray.status;
+        agg |= ray.status;
+    }
+    return agg;
+}
+API int shadow_nf_rx_rows(const double* p, const double* th, int nth, const double* ph, int nph, double th_mean,
+                          double ph_mean, double th_fwhp, double n_si, double n_vac, double* out)
+{
+    const int n = nth * nph;
+    int agg = 0;
+    const double sig = th_fwhp / sqrt(8 * log(2.0));
+    for (int r = 0; r < n; r++) {
+        const int i = r % nth, j = r / nth;
+        NfRxRay ray;
+        vec3 p0 = mk(p[0], p[1], p[2]);
+        nf_rx_ray(p0, launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), n_si, n_vac, ray);
+        double rows[20];
+        pack_nf_rx_rows(ray, p0, th[i] - th_mean, ph[j] - ph_mean, 0.5 / (sig * sig), rows);
+        for (int k = 0; k < 20; k++) out[(size_t)k * n + r] = rows[k];
+        agg |= ray.status;
+    }
+    return agg;
+}
+API int shadow_nf_toy_rows(const double* p, const double* th, int nth, const double* ph, int nph, double y_ap,
+                           double th_fwhp, double n_si, double n_vac, double* out)
+{
+    const int n = nth * nph;
+    int agg = 0;
+    const double sig = th_fwhp / sqrt(8 * log(2.0));
+    for (int r = 0; r < n; r++) {
+        const int i = r % nth, j = r / nth;
+        NfToyRay ray;
+        vec3 p0 = mk(p[0], p[1], p[2]);
+        nf_toy_ray(p0, launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), y_ap, n_si, n_vac, ray);
+        double rows[32];
+        pack_nf_toy_rows(ray, p0, 0.5 / (sig * sig), rows);
+        for (int k = 0; k < 32; k++) out[(size_t)k * n + r] = rows[k];
+        agg |= ray.status;
+    }
+    return agg;
+}
+// one near-field pixel: sum over rays of w * exp(i k (L_rx + L_so)/1e3)
+API int shadow_nf_pixel(const double* p, const double* th, int nth, const double* ph, int nph, double n_si,
+                        double n_vac, const double* rx_opl, const double* rx_w, double k, double* re_im)
+{
+    const int n = nth * nph;
+    double re = 0, im = 0;
+    int agg = 0;
+    for (int r = 0; r < n; r++) {
+        if (rx_w[r] == 0.0) continue;
+        const int i = r % nth, j = r / nth;
+        NfSourceRay ray;
+        nf_source_ray(mk(p[0], p[1], p[2]), launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), n_si, n_vac, ray);
+        agg |= ray.status;
+        if (!ray.valid) continue;
+        const double a = (rx_opl[r] + ray.opl) * (k / 1e3);
+        re += rx_w[r] * cos(a);
+        im += rx_w[r] * sin(a);
+    }
+    re_im[0] = re; re_im[1] = im;
+    return agg;
+}
+
+static FfGeom unpack(const double* g)
+{
+    FfGeom q;
+    q.th_1 = g[0]; q.th2 = g[1];
+    for (int i = 0; i < 3; i++) { q.rotc[i] = g[2 + i]; q.src[i] = g[5 + i]; }
+    q.foc_y = g[8];
+    return q;
+}
+API int shadow_ff_mirror_rows(const double* geo, const double* th, int nth, const double* ph, int nph, double el,
+                              double az, double* out)
+{
+    FfGeom g = unpack(geo);
+    FfFrames f;
+    ff_build_frames(g, el, az, f);
+    const int n = nth * nph;
+    int agg = 0;
+    memset(out, 0, sizeof(double) * 9 * n);
+    for (int r = 0; r < n; r++) {
+        const int i = r % nth, j = r / nth;
+        vec3 d = launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), Pa;
+        double t_ap;
+        if (!ff_aperture(g, f, d, t_ap, Pa)) continue;
+        FfRay ray;
+        ff_ray_trace<true, false>(f, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+        agg |= ray.status;
+        const double v[6] = {ray.m2.x, ray.m2.y, ray.m2.z, ray.m1.x, ray.m1.y, ray.m1.z};
+        for (int k = 0; k < 6; k++) out[(size_t)k * n + r] = v[k];
+    }
+    out[6 * (size_t)n] = f.centre[0]; out[7 * (size_t)n] = f.centre[1]; out[8 * (size_t)n] = f.centre[2];
+    return agg;
+}
+API int shadow_ff_field_rows(const double* geo, const double* th, int nth, const double* ph, int nph,
+                             const double* centre, const int* pidx1, const int* pidx2, const double* pan1, int np1,
+                             const double* pan2, int np2, double el, double az, double* out)
+{
+    FfGeom g = unpack(geo);
+    FfFrames f;
+    ff_build_frames(g, el, az, f);
+    double t2e[9];
+    for (int i = 0; i < 9; i++) t2e[i] = f.t2.a[i];
+    if (g.src[2] != 0) for (int i = 0; i < 3; i++) t2e[3 * i + 2] /= cos(atan(1.0 / 3.0));
+    const int n = nth * nph;
+    int agg = 0;
+    memset(out, 0, sizeof(double) * 17 * n);
+    for (int r = 0; r < n; r++) {
+        if (pidx1[r] < 0 || pidx2[r] < 0) continue;
+        const int i = r % nth, j = r / nth;
+        vec3 d = launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), Pa;
+        double t_ap;
+        if (!ff_aperture(g, f, d, t_ap, Pa)) continue;
+        PanelErr e1, e2;
+        const double* q = pan1 + pidx1[r];
+        e1.a = q[2 * np1]; e1.b = q[3 * np1]; e1.c = q[4 * np1]; e1.d = q[5 * np1]; e1.e = q[6 * np1]; e1.x0 = q[8 * np1]; e1.y0 = q[9 * np1];
+        q = pan2 + pidx2[r];
+        e2.a = q[2 * np2]; e2.b = q[3 * np2]; e2.c = q[4 * np2]; e2.d = q[5 * np2]; e2.e = q[6 * np2]; e2.x0 = q[8 * np2]; e2.y0 = q[9 * np2];
+        FfRay ray;
+        ff_ray_trace<false, true>(f, d, t_ap, Pa, g.foc_y, &e1, &e2, t2e, ray);
+        agg |= ray.status;
+        double rows[17];
+        pack_ff_rows(ray, centre, rows);
+        for (int k = 0; k < 17; k++) out[(size_t)k * n + r] = rows[k];
+    }
+    return agg;
+}
+// one far-field pixel, zero-error single-panel model (fused-map semantics)
+API int shadow_ff_pixel(const double* geo, const double* th, int nth, const double* ph, int nph, double el, double az,
+                        const double* gx_full, const double* gy, const double* e_rec, int M, double k, double* re_im,
+                        int* n_cells)
+{
+    FfGeom g = unpack(geo);
+    FfFrames f;
+    ff_build_frames(g, el, az, f);
+    const int n = nth * nph;
+    int agg = 0;
+    double gx_max = gx_full[0], gy_max = gy[0];
+    for (int i = 0; i < M; i++) { gx_max = fmax(gx_max, gx_full[i]); gy_max = fmax(gy_max, gy[(size_t)i * M]); }
+    std::vector<int> win(M * M, -1);
+    std::vector<double> opl(M * M, 0.0);
+    for (int r = 0; r < n; r++) {
+        const int i = r % nth, j = r / nth;
+        vec3 d = launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), Pa;
+        double t_ap;
+        if (!ff_aperture(g, f, d, t_ap, Pa)) continue;
+        FfRay ray;
+        ff_ray_trace<false, false>(f, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+        agg |= ray.status;
+        if (ray.opl == 0.0) continue;
+        const int c = ff_cell(ray.foc.x - f.centre[0], ray.foc.z - f.centre[2], gx_full, gy, M, gx_max, gy_max);
+        if (c < 0) continue;
+        if (r > win[c]) { win[c] = r; opl[c] = ray.opl; }
+    }
+    double re = 0, im = 0;
+    int cnt = 0;
+    for (int c = 0; c < M * M; c++) {
+        if (win[c] < 0) continue;
+        cnt++;
+        double cs, sn;
+        cis_large(k * opl[c] / 1e3, cs, sn);
+        re += cs * e_rec[2 * c] - sn * e_rec[2 * c + 1];
+        im += cs * e_rec[2 * c + 1] + sn * e_rec[2 * c];
+    }
+    re_im[0] = re / ((double)M * M); re_im[1] = im / ((double)M * M);
+    if (n_cells) *n_cells = cnt;
+    return agg;
+}

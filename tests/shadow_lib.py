@@ -1,0 +1,101 @@
+"""ctypes wrapper of tests/host_shadow/shadow.cpp (the product's device math compiled for the
+host).  Test infrastructure: lets the CPU-only suite check the exact per-ray source the kernels
+run against the golden fixtures."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "host_shadow", "shadow.cpp")
+_HDR = os.path.join(os.path.dirname(_HERE), "solat_optics_b200", "csrc", "solat_math.cuh")
+_SO = os.path.join(_HERE, "_build", "libsolat_shadow.so")
+_lib = None
+dp = ctypes.POINTER(ctypes.c_double)
+ip = ctypes.POINTER(ctypes.c_int)
+cd = ctypes.c_double
+ci = ctypes.c_int
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        newest = max(os.path.getmtime(_SRC), os.path.getmtime(_HDR))
+        if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                                   "-fvisibility=hidden", "-o", _SO, _SRC])
+        _lib = ctypes.CDLL(_SO)
+    return _lib
+
+
+def D(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(dp)
+
+
+def nf_source_rows(p, th, ph, n_si=3.4, n_vac=1.0):
+    th, thp = D(th); ph, php = D(ph); p, pp = D(p)
+    n = th.size * ph.size
+    out = np.zeros((26, n)); st = np.zeros(n, dtype=np.int32)
+    agg = lib().shadow_nf_source_rows(pp, thp, ci(th.size), php, ci(ph.size), cd(n_si), cd(n_vac),
+                                      out.ctypes.data_as(dp), st.ctypes.data_as(ip))
+    return out, st, agg
+
+
+def nf_rx_rows(p, th, ph, th_fwhp, n_si=3.4, n_vac=1.0):
+    th, thp = D(th); ph, php = D(ph); p, pp = D(p)
+    T, P = np.meshgrid(th, ph)
+    out = np.zeros((20, th.size * ph.size))
+    agg = lib().shadow_nf_rx_rows(pp, thp, ci(th.size), php, ci(ph.size), cd(np.mean(T.ravel())), cd(np.mean(P.ravel())),
+                                  cd(th_fwhp), cd(n_si), cd(n_vac), out.ctypes.data_as(dp))
+    return out, agg
+
+
+def nf_toy_rows(p, th, ph, y_ap, th_fwhp, n_si=3.4, n_vac=1.0):
+    th, thp = D(th); ph, php = D(ph); p, pp = D(p)
+    out = np.zeros((32, th.size * ph.size))
+    agg = lib().shadow_nf_toy_rows(pp, thp, ci(th.size), php, ci(ph.size), cd(y_ap), cd(th_fwhp), cd(n_si), cd(n_vac),
+                                   out.ctypes.data_as(dp))
+    return out, agg
+
+
+def nf_pixel(p, th, ph, rx_opl, rx_w, k, n_si=3.4, n_vac=1.0):
+    th, thp = D(th); ph, php = D(ph); p, pp = D(p); ro, rop = D(rx_opl); rw, rwp = D(rx_w)
+    o = np.zeros(2)
+    agg = lib().shadow_nf_pixel(pp, thp, ci(th.size), php, ci(ph.size), cd(n_si), cd(n_vac), rop, rwp, cd(k),
+                                o.ctypes.data_as(dp))
+    return complex(o[0], o[1]), agg
+
+
+def ff_mirror_rows(geo, th, ph, el, az):
+    g, gp = D(geo); th, thp = D(th); ph, php = D(ph)
+    out = np.zeros((9, th.size * ph.size))
+    agg = lib().shadow_ff_mirror_rows(gp, thp, ci(th.size), php, ci(ph.size), cd(el), cd(az), out.ctypes.data_as(dp))
+    return out, agg
+
+
+def ff_field_rows(geo, th, ph, centre, el, az, pidx1=None, pidx2=None, pan1=None, pan2=None):
+    g, gp = D(geo); th, thp = D(th); ph, php = D(ph); c, cp = D(centre)
+    n = th.size * ph.size
+    if pan1 is None:
+        pan1 = np.zeros((10, 1)); pan1[0, 0] = pan1[1, 0] = 1; pan2 = pan1.copy()
+        pidx1 = np.zeros(n, dtype=np.int32); pidx2 = np.zeros(n, dtype=np.int32)
+    p1, p1p = D(pan1); p2, p2p = D(pan2)
+    i1 = np.ascontiguousarray(pidx1, dtype=np.int32); i2 = np.ascontiguousarray(pidx2, dtype=np.int32)
+    out = np.zeros((17, n))
+    agg = lib().shadow_ff_field_rows(gp, thp, ci(th.size), php, ci(ph.size), cp, i1.ctypes.data_as(ip),
+                                     i2.ctypes.data_as(ip), p1p, ci(p1.shape[1]), p2p, ci(p2.shape[1]), cd(el), cd(az),
+                                     out.ctypes.data_as(dp))
+    return out, agg
+
+
+def ff_pixel(geo, th, ph, el, az, data_x, data_y, e_rec, k):
+    g, gp = D(geo); th, thp = D(th); ph, php = D(ph)
+    gx, gxp = D(np.asarray(data_x)[0, :]); gy, gyp = D(data_y)
+    e = np.ascontiguousarray(e_rec, dtype=np.complex128)
+    o = np.zeros(2); nc = ci(0)
+    agg = lib().shadow_ff_pixel(gp, thp, ci(th.size), php, ci(ph.size), cd(el), cd(az), gxp, gyp,
+                                e.ctypes.data_as(dp), ci(gx.size), cd(k), o.ctypes.data_as(dp), ctypes.byref(nc))
+    return complex(o[0], o[1]), nc.value, agg

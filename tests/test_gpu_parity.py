@@ -1,0 +1,393 @@
+"""Parity tests proper: the CUDA path, called through the reference-shaped Python API (which binds the
+C ABI of include/solat_b200.h), against the golden fixtures of the unmodified reference and against the
+CPU oracle.  Tolerances (BASELINE.json north_star): power 1e-6 relative, phase 1e-5 rad per pixel;
+diagnostics per ray: 1e-9 mm, far-field path length 2 ulp of 1e8 mm."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+ULP_1E8 = 1.4901161193847656e-08
+P_TOL, PHI_TOL, RAY_TOL = 1e-6, 1e-5, 1e-9
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class PlotOpts:
+    plot = 0
+
+
+def _assert_pixels(amp, phase, ref_amp, ref_phase, max_bad=0):
+    amp, phase, ref_amp, ref_phase = map(np.ravel, (amp, phase, ref_amp, ref_phase))
+    bad_p = np.abs(amp ** 2 - ref_amp ** 2) > P_TOL * ref_amp ** 2 + 1e-300
+    bad_f = (np.abs(gu.wrap(phase - ref_phase)) > PHI_TOL) & (ref_amp > 0)
+    bad = bad_p | bad_f
+    assert bad.sum() <= max_bad, "pixels out of tolerance: %s" % np.flatnonzero(bad)[:10]
+    return int(bad.sum())
+
+
+# ------------------------------------------------------------------------------------------------ near field
+def _nf_geo(freq, n):
+    from solat_optics_b200 import maps
+
+    return maps.holo_tele_geo(float(freq), int(n))
+
+
+def test_library_is_the_cuda_one():
+    from solat_optics_b200 import _lib
+
+    ctx = _lib.context(0)
+    assert ctx.cc[0] == 10 and ctx.sm_count >= 100
+    before = _lib.launch_count()
+    assert ctx.fp64_peak_tflops(2) > 1.0
+    assert _lib.launch_count() > before
+
+
+def test_nf_rx_rows():
+    from solat_optics_b200 import ray_trace_int as rti
+
+    d = gu.load("nf_rx_rays")
+    for i in range(int(d["n_cases"])):
+        tg = _nf_geo(d["in_freq"][i], d["in_n_scan"][i])
+        m = rti.rx_to_lyot_model(list(d["in_p_rx"][i]), tg, PlotOpts)
+        out = m.output()
+        assert out.shape == (20, m.n_pts) and out.flags["C_CONTIGUOUS"] and out is m.out
+        np.testing.assert_allclose(out, d["out_%d" % i], rtol=0, atol=RAY_TOL)
+
+
+def test_nf_source_rows_and_trace_rays():
+    from solat_optics_b200 import ray_trace_int as rti
+
+    d = gu.load("nf_so_rays")
+    for i in range(int(d["n_cases"])):
+        tg = _nf_geo(d["in_freq"][i], d["in_n_scan"][i])
+        m = rti.source_to_lyot_model([d["in_x"][i], tg.y_ap, d["in_z"][i]], tg, PlotOpts)
+        out = m.output()
+        ref = d["out_%d" % i]
+        assert out.shape == (26, m.n_pts)
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        assert np.array_equal(out[4] == 0, ref[4] == 0)
+        np.testing.assert_allclose(np.nan_to_num(out), np.nan_to_num(ref), rtol=0, atol=RAY_TOL)
+        if i == 1:
+            for ii in (0, 7, m.n_pts - 1):
+                one = np.array(m.trace_rays(ii))
+                np.testing.assert_array_equal(np.nan_to_num(one), np.nan_to_num(out[:, ii]))
+
+
+def test_nf_toy_rows():
+    from solat_optics_b200 import ray_trace_int as rti
+
+    d = gu.load("nf_toy_rays")
+    for i in range(int(d["n_cases"])):
+        tg = _nf_geo(d["in_freq"][i], d["in_n_scan"][i])
+        out = rti.aperature_fields(list(d["in_p_rx"][i]), tg, PlotOpts).output()
+        np.testing.assert_allclose(out, d["out_%d" % i], rtol=0, atol=RAY_TOL)
+
+
+def test_nf_edited_ray_list_uses_paired_mode():
+    from solat_optics_b200 import ray_trace_int as rti
+
+    tg = _nf_geo(140.0, 6)
+    m = rti.source_to_lyot_model([3.0, tg.y_ap, -8.0], tg, PlotOpts)
+    full = m.output().copy()
+    keep = np.array([5, 1, 30, 17])
+    m.theta, m.phi = m.theta[keep], m.phi[keep]
+    sub = m.output()
+    np.testing.assert_array_equal(np.nan_to_num(sub), np.nan_to_num(full[:, keep]))
+
+
+def test_nf_strict_mode_raises_like_brentq():
+    from solat_optics_b200 import ray_trace_int as rti
+
+    tg = _nf_geo(140.0, 4)
+    m = rti.source_to_lyot_model([0.0, -500.0, 0.0], tg, PlotOpts)    # behind lens 1: no root in [5, 14000]
+    rti.strict = True
+    try:
+        with pytest.raises(ValueError):
+            m.output()
+    finally:
+        rti.strict = False
+    m.output()
+    assert (m.status & 1).any()
+
+
+def _nf_pixel_gpu(freq, n, n_rx, p_rx, x, z):
+    from solat_optics_b200 import maps
+
+    tg = _nf_geo(freq, n)
+    rx_opl, rx_w = maps.receiver_field(tg, tuple(p_rx), n_rx, n)
+    plan = maps.NearFieldPlan(tg, [tg.k], rx_opl, rx_w, n, device=0)
+    amp, ph, st = plan.run([[x, z]])
+    plan.close()
+    return amp[0, 0], ph[0, 0], st
+
+
+def test_nf_pixel_known_answers():
+    d = gu.load("nf_pixels")
+    amps, phs = [], []
+    for i in range(int(d["n_cases"])):
+        a, p, st = _nf_pixel_gpu(d["in_freq"][i], int(d["in_n_scan"][i]), int(d["in_n_scan_rx"][i]), d["in_p_rx"][i],
+                                 d["in_x"][i], d["in_z"][i])
+        assert st == 0
+        amps.append(a); phs.append(p)
+    _assert_pixels(np.array(amps), np.array(phs), d["amp"], d["phi"])
+    fully_vignetted = d["amp"] == 0
+    assert fully_vignetted.any() and np.all(np.array(amps)[fully_vignetted] == 0)
+
+
+def test_nf_small_map_and_frequency_sweep(oracle):
+    from solat_optics_b200 import maps
+
+    d = gu.load("nf_map5")
+    px, amp, ph = maps.holo_map(140.0, res=5, sweep=100, n_scan=20, device=0)
+    np.testing.assert_array_equal(px, np.c_[d["in_x"], d["in_z"]])
+    _assert_pixels(amp[0], ph[0], d["amp"], d["phi"])
+    # three frequencies of one band share one trace (BASELINE config 3) == three separate maps, bit for bit
+    px, amp3, ph3 = maps.holo_map([150.0, 220.0, 280.0], res=5, n_scan=20, device=0)
+    for i, f in enumerate((150.0, 220.0, 280.0)):
+        _, a1, p1 = maps.holo_map(f, res=5, n_scan=20, device=0)
+        np.testing.assert_array_equal(amp3[i], a1[0]); np.testing.assert_array_equal(ph3[i], p1[0])
+    with pytest.raises(ValueError):
+        maps.holo_map([90.0, 150.0], res=3, n_scan=8, device=0)          # different bands: y_ap differs
+
+
+def test_nf_full_default_map_against_oracle(oracle):
+    """BASELINE config 1 at full size: 51x51 pixels x 100^2 rays, every pixel against the oracle."""
+    from solat_optics_b200 import maps
+
+    px, amp, ph = maps.holo_map(140.0, device=0)
+    assert amp.shape == (1, 2601)
+    tg = maps.holo_tele_geo(140.0, 100)
+    rx = oracle.nf_rx_trace([0, 0, 0], tg.th_fwhp, 100)
+    oa, op = oracle.nf_map(px, tg.y_ap, 100, rx[3], rx[4] * gu.lyot_mask(100), [tg.k])
+    _assert_pixels(amp, ph, oa, op)
+    # the two n_scan=100 reference KATs sit on this grid: (0,0) is pixel 25*51+25
+    d = gu.load("nf_pixels")
+    _assert_pixels(amp[0, 25 * 51 + 25], ph[0, 25 * 51 + 25], d["amp"][0], d["phi"][0])
+
+
+def test_nf_properties_at_full_size():
+    """Size-independent properties on the full config-1 workload: (a) splitting the pixel list across calls
+    (what N ranks do) is bit-identical to one call; (b) the device-pointer entry equals the host entry;
+    (c) linear in the receiver weight; (d) mirror symmetry x -> -x of the optics tube."""
+    import torch
+
+    from solat_optics_b200 import maps
+
+    tg = maps.holo_tele_geo(140.0, 100)
+    rx_opl, rx_w = maps.receiver_field(tg)
+    plan = maps.NearFieldPlan(tg, [tg.k], rx_opl, rx_w, device=0)
+    px = maps.holo_pixels()
+    amp, ph, st = plan.run(px)
+    assert st == 0 and plan.active_rays == int(np.count_nonzero(rx_w))
+    a1, p1, _ = plan.run(px[:1301]); a2, p2, _ = plan.run(px[1301:])
+    np.testing.assert_array_equal(np.c_[a1, a2], amp); np.testing.assert_array_equal(np.c_[p1, p2], ph)
+    d_src = torch.from_numpy(px).cuda(); d_amp = torch.empty(2601, dtype=torch.float64, device="cuda"); d_ph = torch.empty_like(d_amp)
+    plan.run_device(d_src, d_amp, d_ph, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d_amp.cpu().numpy(), amp[0]); np.testing.assert_array_equal(d_ph.cpu().numpy(), ph[0])
+    assert plan.status() == 0
+    plan2 = maps.NearFieldPlan(tg, [tg.k], rx_opl, 2.0 * rx_w, device=0)
+    b, q, _ = plan2.run(px[::50])
+    np.testing.assert_allclose(b, 2 * amp[:, ::50], rtol=1e-13); np.testing.assert_allclose(q, ph[:, ::50], atol=1e-12)
+    grid_a = amp[0].reshape(51, 51); grid_p = ph[0].reshape(51, 51)
+    np.testing.assert_allclose(grid_a[::-1], grid_a, rtol=1e-9)       # x -> -x
+    assert np.abs(gu.wrap(grid_p[::-1] - grid_p)).max() < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ far field
+def _ff_geo(freq, offset):
+    from solat_optics_b200 import maps
+
+    return maps.ff_tele_geo(int(freq), float(offset))
+
+
+def test_ff_rows():
+    from solat_optics_b200 import solat_apert_field as saf
+
+    d = gu.load("ff_rays")
+    pm = saf.panel_backend().panel_model_from_adjuster_offsets(1, np.zeros(1092), 1, 0)
+    for i in range(int(d["n_cases"])):
+        tg = _ff_geo(d["in_freq"][i], d["in_offset"][i])
+        th, ph = gu.ff_fan(int(d["in_n_scan"][i]))
+        el, az = float(d["in_el"][i]), float(d["in_az"][i])
+        m = saf.ray_mirror_pts(tg, th, ph, el, az)
+        np.testing.assert_allclose(m, d["mirror_%d" % i], rtol=0, atol=1e-9)
+        np.testing.assert_array_equal(saf.RayMirrorPts(tg, th, ph, el, az).output(), m)
+        f = saf.aperature_fields_from_panel_model(pm, pm, tg, th, ph, m, el, az)
+        ref = d["field_%d" % i]
+        assert f.shape == ref.shape and np.array_equal(f[15] != 0, ref[15] != 0)
+        np.testing.assert_allclose(f[:15], ref[:15], rtol=0, atol=1e-9)
+        assert np.abs(f[15] - ref[15]).max() <= 2 * ULP_1E8
+        np.testing.assert_array_equal(f[16], ref[16])
+
+
+def test_ff_panel_errors_against_oracle(oracle):
+    from solat_optics_b200 import solat_apert_field as saf
+
+    rng = np.random.default_rng(7)
+    n = 14
+    th, ph = gu.ff_fan(n)
+    tg = _ff_geo(140, 1.32)
+    el, az = gu.EL0 - 4 * gu.DE, 6 * gu.DE
+    pan1 = np.zeros((10, 3)); pan2 = np.zeros((10, 2))
+    for pm in (pan1, pan2):
+        pm[0] = np.arange(pm.shape[1]) + 1; pm[1] = 1
+        pm[2] = rng.normal(0, 0.02, pm.shape[1]); pm[3:5] = rng.normal(0, 2e-5, (2, pm.shape[1]))
+        pm[5:7] = rng.normal(0, 2e-8, (2, pm.shape[1])); pm[8:10] = rng.normal(0, 500, (2, pm.shape[1]))
+    rows1 = rng.integers(0, 4, (n, n)).astype(float); rows2 = rng.integers(0, 3, (n, n)).astype(float)   # 0 = no panel
+
+    class Backend:
+        calls = 0
+
+        @staticmethod
+        def get_single_vert_adj_positions():
+            z = np.zeros(1)
+            return [z, z, z, z, z], [z, z, z, z, z]
+
+        @classmethod
+        def identify_panel(cls, x2d, y2d, x_adj, y_adj, col, row):
+            cls.calls += 1
+            r = rows2 if cls.calls == 1 else rows1            # reference calls M2 first (saf:609-612)
+            return np.stack([r, np.ones_like(r)])
+
+    saf.set_panel_backend(Backend)
+    try:
+        m = saf.ray_mirror_pts(tg, th, ph, el, az)
+        out = saf.aperature_fields_from_panel_model(pan1, pan2, tg, th, ph, m, el, az)
+    finally:
+        saf.set_panel_backend(None)
+    geo = oracle.ff_geo_vec(rx_y_m=-1.32)
+    idx1 = rows1.ravel().astype(np.int32) - 1; idx2 = rows2.ravel().astype(np.int32) - 1
+    ref = oracle.ff_apert_fields(geo, th, ph, m[6:9, 0], el, az, idx1, idx2, pan1, pan2)
+    assert np.array_equal(out[15] != 0, ref[15] != 0) and (ref[15] != 0).sum() > 10
+    np.testing.assert_allclose(out[:15], ref[:15], rtol=0, atol=1e-9)
+    assert np.abs(out[15] - ref[15]).max() <= 3 * ULP_1E8
+
+
+def test_ff_project_to_data(oracle):
+    from solat_optics_b200 import far_field_latrt as ffl
+    from solat_optics_b200 import solat_apert_field as saf
+
+    tg = _ff_geo(140, 1.32)
+    pm = saf.panel_backend().panel_model_from_adjuster_offsets(1, None, 1, 0)
+    for kind in ("nf51", "wide61"):
+        x, y, e = gu.ff_grid(kind)
+        th, ph = gu.ff_fan(40)
+        el, az = gu.EL0 + 2 * gu.DE, -5 * gu.DE
+        m = saf.ray_mirror_pts(tg, th, ph, el, az)
+        f = saf.aperature_fields_from_panel_model(pm, pm, tg, th, ph, m, el, az)
+        out = ffl.project_to_data(f, x, y, tg)
+        ref = oracle.ff_project(f, x, y, tg.k)                   # same sim array in: cells must agree exactly
+        assert out.dtype == np.complex128 and out.shape == x.shape
+        assert np.array_equal(out != 0, ref != 0) and np.count_nonzero(ref) > 50
+        np.testing.assert_allclose(out, ref, rtol=0, atol=1e-9)   # same k*L/1e3 argument; reduction error only
+
+
+@pytest.mark.parametrize("name", ["ff_pixels", "ff_map5"])
+def test_ff_pixel_known_answers(name):
+    from solat_optics_b200 import maps
+
+    d = gu.load(name)
+    amps, phs = [], []
+    for i in range(int(d["n_cases"])):
+        tg = _ff_geo(d["in_freq"][i], d["in_offset"][i])
+        th, ph = gu.ff_fan(int(d["in_n_scan"][i]))
+        x, y, e = gu.ff_grid(str(d["in_grid"][i]))
+        plan = maps.FarFieldPlan(tg, th, ph, x, y, e, device=0)
+        a, p, st = plan.run([[d["in_az"][i], d["in_el"][i]]])
+        plan.close()
+        assert st == 0
+        amps.append(a[0]); phs.append(p[0])
+    _assert_pixels(np.array(amps), np.array(phs), d["amp"], d["phi"])
+
+
+def test_ff_full_map_against_oracle(oracle):
+    """BASELINE config 2 geometry at full size: ff_sim.py 140 0.25 20 1.32 -> 41x41 pixels x 100^2 rays, every
+    pixel against the oracle.  A ray within ~1e-8 mm of a bin edge may land in the neighbouring cell
+    (SURVEY.md section 7 'last-write-wins'); at most 2 such pixels are tolerated and none is expected."""
+    from solat_optics_b200 import maps
+
+    x, y, e = gu.ff_grid("wide61")
+    px, amp, ph = maps.ff_map(140, 0.25, 20, 1.32, x, y, e, device=0)
+    assert amp.shape == (1681,)
+    tg = maps.ff_tele_geo(140, 1.32)
+    th, phi = maps.ff_fan(100)
+    oa, op = oracle.ff_map(oracle.ff_geo_vec(rx_y_m=-1.32), px, th, phi, x, y, e, tg.k)
+    _assert_pixels(amp, ph, oa, op, max_bad=2)
+
+
+def test_ff_properties_at_full_size():
+    """(a) sharded == unsharded bit for bit; (b) device entry == host entry; (c) linear in E_rec;
+    (d) a global phase on E_rec rotates the result; (e) more than one batch per pixel (n_scan=100) and
+    a ragged last batch give the same winners as a single-batch fan restricted to the same rays."""
+    import torch
+
+    from solat_optics_b200 import maps
+
+    x, y, e = gu.ff_grid("wide61")
+    tg = maps.ff_tele_geo(140, 1.32)
+    th, phi = maps.ff_fan(100)
+    px = maps.ff_pixels(tg, 0.25, 20)
+    plan = maps.FarFieldPlan(tg, th, phi, x, y, e, device=0)
+    amp, ph, st = plan.run(px)
+    assert st == 0
+    a1, p1, _ = plan.run(px[:700]); a2, p2, _ = plan.run(px[700:])
+    np.testing.assert_array_equal(np.r_[a1, a2], amp); np.testing.assert_array_equal(np.r_[p1, p2], ph)
+    d_px = torch.from_numpy(px).cuda(); d_a = torch.empty(len(px), dtype=torch.float64, device="cuda"); d_p = torch.empty_like(d_a)
+    plan.run_device(d_px, d_a, d_p, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d_a.cpu().numpy(), amp); np.testing.assert_array_equal(d_p.cpu().numpy(), ph)
+    assert plan.status() == 0
+    sub = px[::40]
+    b, q, _ = maps.FarFieldPlan(tg, th, phi, x, y, 3.0 * e * np.exp(0.7j), device=0).run(sub)
+    np.testing.assert_allclose(b, 3 * amp[::40], rtol=1e-12)
+    assert np.abs(gu.wrap(q - ph[::40] - 0.7)).max() < 1e-12
+    # empty receiver field -> exactly zero
+    z, _, _ = maps.FarFieldPlan(tg, th, phi, x, y, 0 * e, device=0).run(sub[:3])
+    assert np.all(z == 0)
+
+
+def test_ff_odd_sizes_and_edge_grids(oracle):
+    """Ragged inputs: a fan that is not a multiple of the CTA size, a 1-pixel map, a 2x2 E_rec grid (every ray
+    piles into cell 0 or is skipped), a grid entirely below the beam (all rays skipped -> 0)."""
+    from solat_optics_b200 import maps
+
+    tg = maps.ff_tele_geo(140, 1.32)
+    geo = oracle.ff_geo_vec(rx_y_m=-1.32)
+    th, phi = gu.ff_fan(37)
+    for ax in (np.array([-1.0, 1.0]), np.linspace(-40, -35, 7), np.linspace(-3, 28, 11)):
+        yy, xx = np.meshgrid(ax, ax, indexing="ij")
+        e = (1 + 0.1 * xx) * np.exp(0.2j * yy)
+        a, p, st = maps.FarFieldPlan(tg, th, phi, xx, yy, e, device=0).run([[gu.DE, gu.EL0 - gu.DE]])
+        oa, op = oracle.ff_map(geo, [gu.DE, gu.EL0 - gu.DE], th, phi, xx, yy, e, tg.k)
+        assert st == 0
+        if oa[0] == 0:
+            assert a[0] == 0
+        else:
+            _assert_pixels(a, p, oa, op)
+
+
+# ------------------------------------------------------------------------------------------------ CLI
+def test_cli_holo_sim_writes_reference_format(tmp_path):
+    d = gu.load("nf_map5")
+    out = tmp_path / "nf.txt"
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "scripts", "holo_sim.py"), "140", "--res", "5", "--n-scan", "20",
+                           "--out", str(out)], env=env, cwd=str(tmp_path))
+    tab = np.loadtxt(out)
+    assert tab.shape == (25, 4)
+    np.testing.assert_array_equal(tab[:, 0], d["in_x"]); np.testing.assert_array_equal(tab[:, 1], d["in_z"])
+    _assert_pixels(tab[:, 2], tab[:, 3], d["amp"], d["phi"])
+    # chain into the far-field CLI (ff_sim.py reads the near-field table as E_rec)
+    ff = tmp_path / "ff.txt"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "scripts", "ff_sim.py"), "140", "0.25", "2", "1.32", "--nf-input", str(out),
+                           "--n-scan", "16", "--out", str(ff)], env=env, cwd=str(tmp_path))
+    t2 = np.loadtxt(ff)
+    assert t2.shape == (25, 4) and np.isfinite(t2).all()
+    np.testing.assert_allclose(t2[0, :2], (-2 * gu.DE, gu.EL0 - 2 * gu.DE), atol=1e-15)

@@ -1,0 +1,113 @@
+"""Pins the CPU oracle (oracle/solat_oracle.c) against fixtures produced by the UNMODIFIED
+reference (oracle/gen_golden.py -> tests/golden/*.npz).  CPU only."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+ULP_1E8 = 1.4901161193847656e-08   # one FP64 ulp of a 1e8 mm far-field path
+
+
+def _nf_axes(kind, n):
+    if kind == "rx":
+        return np.linspace(-np.pi / 2 - 0.28, -np.pi / 2 + 0.28, n), np.linspace(np.pi / 2 - 0.28, np.pi / 2 + 0.28, n)
+    return np.linspace(np.pi / 2 - 0.22, np.pi / 2 + 0.22, n), np.linspace(np.pi / 2 - 0.22, np.pi / 2 + 0.22, n)
+
+
+def test_nf_rx_rays(oracle):
+    d = gu.load("nf_rx_rays")
+    for i in range(int(d["n_cases"])):
+        _, fw = gu.nf_band(d["in_freq"][i])
+        out = oracle.nf_rx_trace(d["in_p_rx"][i], fw, int(d["in_n_scan"][i]))
+        np.testing.assert_allclose(out, d["out_%d" % i], rtol=0, atol=1e-10)
+
+
+def test_nf_source_rays(oracle):
+    d = gu.load("nf_so_rays")
+    for i in range(int(d["n_cases"])):
+        y_ap, _ = gu.nf_band(d["in_freq"][i])
+        out = oracle.nf_source_trace([d["in_x"][i], y_ap, d["in_z"][i]], int(d["in_n_scan"][i]))
+        ref = d["out_%d" % i]
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        assert np.array_equal(out[4] == 0, ref[4] == 0)          # vignetting mask identical
+        np.testing.assert_allclose(np.nan_to_num(out), np.nan_to_num(ref), rtol=0, atol=1e-10)
+
+
+def test_nf_toy_rays(oracle):
+    d = gu.load("nf_toy_rays")
+    for i in range(int(d["n_cases"])):
+        y_ap, fw = gu.nf_band(d["in_freq"][i])
+        out = oracle.nf_toy_trace(d["in_p_rx"][i], y_ap, fw, int(d["in_n_scan"][i]))
+        np.testing.assert_allclose(out, d["out_%d" % i], rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", ["nf_pixels", "nf_map5"])
+def test_nf_pixels(oracle, name):
+    d = gu.load(name)
+    for i in range(int(d["n_cases"])):
+        f, n = float(d["in_freq"][i]), int(d["in_n_scan"][i])
+        n_rx = int(d["in_n_scan_rx"][i]) if "in_n_scan_rx" in d else n
+        if n_rx != n:
+            continue   # unequal grids go through the host spline; covered by test_host_logic
+        p_rx = d["in_p_rx"][i] if "in_p_rx" in d else (0, 0, 0)
+        y_ap, fw = gu.nf_band(f)
+        rx = oracle.nf_rx_trace(p_rx, fw, n)
+        amp, ph = oracle.nf_map([d["in_x"][i], d["in_z"][i]], y_ap, n, rx[3], rx[4] * gu.lyot_mask(n), [gu.nf_k(f)])
+        ra, rp = d["amp"][i], d["phi"][i]
+        assert abs(amp[0, 0] ** 2 - ra ** 2) <= 1e-9 * ra ** 2 + 1e-300
+        if ra > 0:
+            assert abs(gu.wrap(ph[0, 0] - rp)) <= 1e-9
+
+
+def test_ff_rays(oracle):
+    d = gu.load("ff_rays")
+    for i in range(int(d["n_cases"])):
+        n = int(d["in_n_scan"][i])
+        th, ph = gu.ff_fan(n)
+        geo = oracle.ff_geo_vec(rx_y_m=-float(d["in_offset"][i]))
+        el, az = float(d["in_el"][i]), float(d["in_az"][i])
+        m = oracle.ff_ray_mirror_pts(geo, th, ph, el, az)
+        np.testing.assert_allclose(m, d["mirror_%d" % i], rtol=0, atol=1e-9)
+        f = oracle.ff_apert_fields(geo, th, ph, m[6:9, 0], el, az)
+        ref = d["field_%d" % i]
+        assert np.array_equal(f[15] != 0, ref[15] != 0)
+        np.testing.assert_allclose(f[:15], ref[:15], rtol=0, atol=1e-9)
+        assert np.abs(f[15] - ref[15]).max() <= 2 * ULP_1E8
+
+
+@pytest.mark.parametrize("name", ["ff_pixels", "ff_map5"])
+def test_ff_pixels(oracle, name):
+    d = gu.load(name)
+    for i in range(int(d["n_cases"])):
+        n = int(d["in_n_scan"][i])
+        th, ph = gu.ff_fan(n)
+        geo = oracle.ff_geo_vec(rx_y_m=-float(d["in_offset"][i]))
+        x, y, e = gu.ff_grid(str(d["in_grid"][i]))
+        amp, pha = oracle.ff_map(geo, [d["in_az"][i], d["in_el"][i]], th, ph, x, y, e, gu.ff_k(float(d["in_freq"][i])),
+                                 two_pass=True, nthreads=1)
+        assert abs(amp[0] ** 2 - d["amp"][i] ** 2) <= 1e-9 * d["amp"][i] ** 2
+        assert abs(gu.wrap(pha[0] - d["phi"][i])) <= 1e-9
+
+
+def test_ff_project_matches_map(oracle):
+    """orc_ff_project (ffl:9-32 restated) + the sum of ff_sim.py:216-217 == orc_ff_map."""
+    n = 20
+    th, ph = gu.ff_fan(n)
+    geo = oracle.ff_geo_vec(rx_y_m=-1.32)
+    x, y, e = gu.ff_grid("wide61")
+    el, az = gu.EL0 + 3 * gu.DE, -2 * gu.DE
+    m = oracle.ff_ray_mirror_pts(geo, th, ph, el, az)
+    f = oracle.ff_apert_fields(geo, th, ph, m[6:9, 0], el, az)
+    k = gu.ff_k(140)
+    proj = oracle.ff_project(f, x, y, k)
+    beam = np.sum(proj * e) / len(proj) ** 2
+    amp, pha = oracle.ff_map(geo, [az, el], th, ph, x, y, e, k)
+    assert abs(abs(beam) - amp[0]) <= 1e-12 * amp[0]
+    assert abs(gu.wrap(np.angle(beam) - pha[0])) <= 1e-12
+
+
+def test_bracket_error_reported(oracle):
+    """The reference raises ValueError from brentq when a bracket has no sign change; the oracle
+    reports that as OracleBracketError.  A source BEHIND lens 1 (y > -975) has no 1B root in [5, 14000]."""
+    with pytest.raises(ValueError):
+        oracle.nf_source_trace([0.0, -500.0, 0.0], 4)

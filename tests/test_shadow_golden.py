@@ -1,0 +1,147 @@
+"""The product's per-ray device math (solat_optics_b200/csrc/solat_math.cuh compiled for the host by
+tests/host_shadow) against the reference fixtures and against the oracle.  CPU only.  Tolerances are
+the north-star ones: power 1e-6 relative, phase 1e-5 rad; per ray 1e-9 mm / 2 ulp(1e8 mm)."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+ULP_1E8 = 1.4901161193847656e-08
+P_TOL, PHI_TOL, RAY_TOL = 1e-6, 1e-5, 1e-9
+
+
+def _src_axis(n):
+    return np.linspace(np.pi / 2 - 0.22, np.pi / 2 + 0.22, n)
+
+
+def _rx_axes(n):
+    return np.linspace(-np.pi / 2 - 0.28, -np.pi / 2 + 0.28, n), np.linspace(np.pi / 2 - 0.28, np.pi / 2 + 0.28, n)
+
+
+def test_nf_source_rows(shadow):
+    d = gu.load("nf_so_rays")
+    for i in range(int(d["n_cases"])):
+        y_ap, _ = gu.nf_band(d["in_freq"][i])
+        a = _src_axis(int(d["in_n_scan"][i]))
+        out, st, agg = shadow.nf_source_rows([d["in_x"][i], y_ap, d["in_z"][i]], a, a)
+        ref = d["out_%d" % i]
+        assert agg == 0
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        assert np.array_equal(out[4] == 0, ref[4] == 0)
+        np.testing.assert_allclose(np.nan_to_num(out), np.nan_to_num(ref), rtol=0, atol=RAY_TOL)
+
+
+def test_nf_rx_rows(shadow):
+    d = gu.load("nf_rx_rays")
+    for i in range(int(d["n_cases"])):
+        _, fw = gu.nf_band(d["in_freq"][i])
+        th, ph = _rx_axes(int(d["in_n_scan"][i]))
+        out, agg = shadow.nf_rx_rows(d["in_p_rx"][i], th, ph, fw)
+        assert agg == 0
+        np.testing.assert_allclose(out, d["out_%d" % i], rtol=0, atol=RAY_TOL)
+
+
+def test_nf_toy_rows(shadow):
+    d = gu.load("nf_toy_rays")
+    for i in range(int(d["n_cases"])):
+        y_ap, fw = gu.nf_band(d["in_freq"][i])
+        n = int(d["in_n_scan"][i])
+        th = np.linspace(-np.pi / 2 - 0.25, -np.pi / 2 + 0.25, n)
+        ph = np.linspace(np.pi / 2 - 0.25, np.pi / 2 + 0.25, n)
+        out, agg = shadow.nf_toy_rows(d["in_p_rx"][i], th, ph, y_ap, fw)
+        assert agg == 0
+        np.testing.assert_allclose(out, d["out_%d" % i], rtol=0, atol=RAY_TOL)
+
+
+@pytest.mark.parametrize("name", ["nf_pixels", "nf_map5"])
+def test_nf_pixels(shadow, name):
+    d = gu.load(name)
+    for i in range(int(d["n_cases"])):
+        f, n = float(d["in_freq"][i]), int(d["in_n_scan"][i])
+        n_rx = int(d["in_n_scan_rx"][i]) if "in_n_scan_rx" in d else n
+        if n_rx != n:
+            continue
+        p_rx = d["in_p_rx"][i] if "in_p_rx" in d else (0, 0, 0)
+        y_ap, fw = gu.nf_band(f)
+        th, ph = _rx_axes(n)
+        rx, _ = shadow.nf_rx_rows(p_rx, th, ph, fw)
+        a = _src_axis(n)
+        z, agg = shadow.nf_pixel([d["in_x"][i], y_ap, d["in_z"][i]], a, a, rx[3], rx[4] * gu.lyot_mask(n), gu.nf_k(f))
+        ra, rp = d["amp"][i], d["phi"][i]
+        assert agg == 0
+        assert abs(abs(z) ** 2 - ra ** 2) <= P_TOL * ra ** 2 + 1e-300
+        if ra > 0:
+            assert abs(gu.wrap(np.angle(z) - rp)) <= PHI_TOL
+
+
+def test_ff_rows(shadow, oracle):
+    d = gu.load("ff_rays")
+    for i in range(int(d["n_cases"])):
+        n = int(d["in_n_scan"][i])
+        th, ph = gu.ff_fan(n)
+        geo = oracle.ff_geo_vec(rx_y_m=-float(d["in_offset"][i]))
+        el, az = float(d["in_el"][i]), float(d["in_az"][i])
+        m, a1 = shadow.ff_mirror_rows(geo, th, ph, el, az)
+        f, a2 = shadow.ff_field_rows(geo, th, ph, m[6:9, 0], el, az)
+        ref = d["field_%d" % i]
+        assert a1 == 0 and a2 == 0
+        np.testing.assert_allclose(m, d["mirror_%d" % i], rtol=0, atol=1e-9)
+        assert np.array_equal(f[15] != 0, ref[15] != 0)
+        np.testing.assert_allclose(f[:15], ref[:15], rtol=0, atol=1e-9)
+        assert np.abs(f[15] - ref[15]).max() <= 2 * ULP_1E8
+
+
+@pytest.mark.parametrize("name", ["ff_pixels", "ff_map5"])
+def test_ff_pixels(shadow, oracle, name):
+    d = gu.load(name)
+    for i in range(int(d["n_cases"])):
+        n = int(d["in_n_scan"][i])
+        th, ph = gu.ff_fan(n)
+        geo = oracle.ff_geo_vec(rx_y_m=-float(d["in_offset"][i]))
+        x, y, e = gu.ff_grid(str(d["in_grid"][i]))
+        z, nc, agg = shadow.ff_pixel(geo, th, ph, float(d["in_el"][i]), float(d["in_az"][i]), x, y, e,
+                                     gu.ff_k(float(d["in_freq"][i])))
+        assert agg == 0
+        assert nc == int(d["n_cells"][i])
+        assert abs(abs(z) ** 2 - d["amp"][i] ** 2) <= P_TOL * d["amp"][i] ** 2
+        assert abs(gu.wrap(np.angle(z) - d["phi"][i])) <= PHI_TOL
+
+
+def test_panel_error_matches_oracle(shadow, oracle):
+    """Non-zero panel-error polynomials (saf:676-703, :820-852): several panels, some rays with no
+    panel.  Only the oracle can pin this (the real pan_mod is not available: parity unpinned there)."""
+    rng = np.random.default_rng(7)
+    n = 14
+    th, ph = gu.ff_fan(n)
+    geo = oracle.ff_geo_vec(rx_y_m=-1.32)
+    el, az = gu.EL0 - 4 * gu.DE, 6 * gu.DE
+    pan1 = np.zeros((10, 3)); pan2 = np.zeros((10, 2))
+    for pm in (pan1, pan2):
+        pm[0] = np.arange(pm.shape[1]) + 1; pm[1] = 1
+        pm[2] = rng.normal(0, 0.02, pm.shape[1])        # a  [mm]
+        pm[3:5] = rng.normal(0, 2e-5, (2, pm.shape[1]))  # b, c
+        pm[5:7] = rng.normal(0, 2e-8, (2, pm.shape[1]))  # d, e
+        pm[8:10] = rng.normal(0, 500, (2, pm.shape[1]))  # x0, y0
+    idx1 = rng.integers(-1, 3, n * n).astype(np.int32)
+    idx2 = rng.integers(-1, 2, n * n).astype(np.int32)
+    m = oracle.ff_ray_mirror_pts(geo, th, ph, el, az)
+    ref = oracle.ff_apert_fields(geo, th, ph, m[6:9, 0], el, az, idx1, idx2, pan1, pan2)
+    out, agg = shadow.ff_field_rows(geo, th, ph, m[6:9, 0], el, az, idx1, idx2, pan1, pan2)
+    assert agg == 0
+    assert np.array_equal(out[15] != 0, ref[15] != 0) and (ref[15] != 0).sum() > 10
+    np.testing.assert_allclose(out[:15], ref[:15], rtol=0, atol=1e-9)
+    assert np.abs(out[15] - ref[15]).max() <= 3 * ULP_1E8
+    # and the error terms really moved the path (otherwise this test pins nothing)
+    ideal = oracle.ff_apert_fields(geo, th, ph, m[6:9, 0], el, az)
+    both = (ref[15] != 0) & (ideal[15] != 0)
+    assert np.abs(ref[15][both] - ideal[15][both]).max() > 1e-3
+
+
+def test_status_flags(shadow):
+    a = _src_axis(4)
+    # source behind lens 1: the 1B plane root is negative -> reference brentq ValueError -> bracket flag
+    _, st, agg = shadow.nf_source_rows([0.0, -500.0, 0.0], a, a)
+    assert agg & 1
+    # far off-axis source: every ray vignetted, no flag raised
+    out, st, agg = shadow.nf_source_rows([600.0, -1335.0, 0.0], a, a)
+    assert agg == 0 and not out.any()
