@@ -618,21 +618,19 @@ struct solat_nf_plan {
     int n_act = 0, tiles = 1, tile_len = 0, threads = 256;
 };
 
-// choose (tiles) so that the ray loop fills its CTA and the grid has enough CTAs for all SMs
-static void nf_choose_tiling(solat_nf_plan* p, int npix)
+// Ray tiling of one pixel.  It depends on the ray count ONLY (never on the number of pixels), so the
+// summation order of a pixel -- and therefore its bits -- is the same however the pixel list is sharded
+// over calls or ranks.  Picks the tile count with the fewest idle threads in the last loop iteration.
+static void nf_choose_tiling(solat_nf_plan* p)
 {
-    const int sms = p->ctx->prop.multiProcessorCount, resident = 2 * sms;
+    const int min_tiles = std::max(1, (p->n_act + 4095) / 4096);
     double best = -1.0;
-    int best_tiles = 1;
-    for (int tiles = 1; tiles <= 64; tiles++) {
+    int best_tiles = min_tiles;
+    for (int tiles = min_tiles; tiles < min_tiles + 6; tiles++) {
         const int len = (p->n_act + tiles - 1) / tiles;
-        if (len < p->threads && tiles > 1) break;
         const int iters = (len + p->threads - 1) / p->threads;
         const double thread_eff = (double)p->n_act / ((double)tiles * iters * p->threads);
-        const double waves = (double)npix * tiles / resident;
-        const double tail_eff = waves / ceil(waves);
-        const double score = thread_eff * tail_eff;
-        if (score > best + 1e-9) { best = score; best_tiles = tiles; }
+        if (thread_eff > best + 1e-9) { best = thread_eff; best_tiles = tiles; }
     }
     p->tiles = best_tiles;
     p->tile_len = (p->n_act + best_tiles - 1) / best_tiles;
@@ -647,7 +645,7 @@ static int nf_map_launch(solat_nf_plan* p, const double* d_src, int npix, double
         CK(cudaMemsetAsync(d_phase, 0, sizeof(double) * npix * nfreq, s));
         return SOLAT_OK;
     }
-    nf_choose_tiling(p, npix);
+    nf_choose_tiling(p);
     if (int rc = p->partial.reserve((size_t)npix * p->tiles * nfreq)) return rc;
     NfMapParams q;
     q.ang = p->ang.tabs; q.src_xz = d_src; q.act_idx = p->act_idx.p; q.act_rx = p->act_rx.p;
