@@ -6,7 +6,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "solat_kernels.cu")
 HDRS = [os.path.join(_HERE, "csrc", "solat_math.cuh"), os.path.join(os.path.dirname(_HERE), "include", "solat_b200.h")]
-LIB = os.path.join(_HERE, "libsolat_b200.so")
+LIB = os.environ.get("SOLAT_B200_LIB") or os.path.join(_HERE, "libsolat_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
@@ -22,6 +22,8 @@ def nvcc_path():
 
 
 def stale():
+    if os.environ.get("SOLAT_B200_LIB"):
+        return False
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
@@ -30,6 +32,8 @@ def stale():
 
 def build(force=False, verbose=False, extra=()):
     """Compile the CUDA library if it is missing or older than its sources."""
+    if os.environ.get("SOLAT_B200_LIB"):
+        return LIB          # an explicitly chosen prebuilt variant is never rebuilt
     if not force and not stale():
         return LIB
     cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ["-o", LIB, SRC]

@@ -43,6 +43,7 @@ SIGNATURES = {
     "solat_ctx_info": (c_i, [c_vp, c_ip, c_ip, c_ip, ctypes.POINTER(ctypes.c_longlong)]),
     "solat_launch_count": (ctypes.c_longlong, []),
     "solat_fp64_peak": (c_i, [c_vp, c_i, c_dp]),
+    "solat_selftest_math": (c_i, [c_vp, c_dp, c_i, c_dp]),
     "solat_nf_rx_trace": (c_i, [c_vp, ctypes.POINTER(NfGeom), c_dp, c_dp, c_i, c_dp, c_i, c_dp, c_ip]),
     "solat_nf_source_trace": (c_i, [c_vp, ctypes.POINTER(NfGeom), c_dp, c_dp, c_i, c_dp, c_i, c_dp, c_ip]),
     "solat_nf_toy_trace": (c_i, [c_vp, ctypes.POINTER(NfGeom), c_dp, c_dp, c_i, c_dp, c_i, c_dp, c_ip]),
@@ -150,6 +151,14 @@ def context(device=None):
         with _lock:
             _contexts[device] = ctx
     return ctx
+
+
+def selftest_math(x, device=None):
+    """(8, n) accuracy probe of the device fast-math primitives; see include/solat_b200.h."""
+    x = as_f64(x)
+    out = np.empty((8, x.size))
+    check(load().solat_selftest_math(context(device).handle, dptr(x), x.size, dptr(out)))
+    return out
 
 
 def launch_count():

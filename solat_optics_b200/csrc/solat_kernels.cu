@@ -25,6 +25,17 @@
 
 using namespace solat;
 
+// launch-shape tunables (tools/variant_bench.py A/B-tests them on the B200)
+#ifndef SOLAT_FF_T
+#define SOLAT_FF_T 256      // threads per far-field CTA (= rays per batch)
+#endif
+#ifndef SOLAT_FF_MINB
+#define SOLAT_FF_MINB 3     // resident far-field CTAs per SM the register allocation is capped for
+#endif
+#ifndef SOLAT_NF_MINB
+#define SOLAT_NF_MINB 3
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // host-side plumbing
 // ------------------------------------------------------------------------------------------------
@@ -200,7 +211,7 @@ __device__ __forceinline__ void block_reduce_store(double (&re)[NF], double (&im
 }
 
 template <int NF>
-__global__ void __launch_bounds__(256, 2) nf_map_kernel(NfMapParams q)
+__global__ void __launch_bounds__(256, SOLAT_NF_MINB) nf_map_kernel(NfMapParams q)
 {
     const int pix = blockIdx.x / q.tiles, tile = blockIdx.x - pix * q.tiles;
     const vec3 p0 = mk(__ldg(q.src_xz + 2 * pix), q.y_ap, __ldg(q.src_xz + 2 * pix + 1));
@@ -345,7 +356,7 @@ __global__ void ff_project_fill_kernel(const double* sim, int n_pts, const int* 
 // ------------------------------------------------------------------------------------------------
 // far field: fused map
 // ------------------------------------------------------------------------------------------------
-constexpr int FF_T = 256;
+constexpr int FF_T = SOLAT_FF_T;
 struct FfMapParams {
     AngleTabs ang;
     solat_ff_geom g;
@@ -360,7 +371,7 @@ struct FfMapParams {
     int* status;
 };
 
-__global__ void __launch_bounds__(FF_T, 2) ff_map_kernel(FfMapParams q)
+__global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams q)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cells = q.M * q.M;
@@ -467,10 +478,42 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+// accuracy probe of the fast-math primitives: out[v][i], v = rcp with 0..3 Newton steps, rsqrt with 0..1 polish
+__global__ void selftest_math_kernel(const double* x, int n, double* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = x[i];
+    out[0 * n + i] = rcp_n<0>(a);
+    out[1 * n + i] = rcp_n<1>(a);
+    out[2 * n + i] = rcp_n<2>(a);
+    out[3 * n + i] = rcp_n<3>(a);
+    out[4 * n + i] = rsqrt_n<0>(a);
+    out[5 * n + i] = rsqrt_n<1>(a);
+    double c, s;
+    cis_large(a, c, s);
+    out[6 * n + i] = c;
+    out[7 * n + i] = s;
+}
+
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
 extern "C" {
+
+int solat_selftest_math(solat_ctx* c, const double* x, int n, double* out8)
+{
+    if (!c || !x || !out8 || n <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    DevBuf<double> dx, dout;
+    if (int rc = dx.upload(x, n, c->stream)) return rc;
+    if (int rc = dout.reserve(8 * (size_t)n)) return rc;
+    selftest_math_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(dx.p, n, dout.p);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(out8, dout.p, 8 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SOLAT_OK;
+}
 
 int solat_abi_version(void) { return SOLAT_ABI_VERSION; }
 const char* solat_last_error(void) { return g_err.c_str(); }

@@ -2,7 +2,7 @@
 // LAT mirrors (far field).  Product code: every function here runs inside the sm_100a kernels of
 // solat_kernels.cu.  The functions are also marked __host__ so that tests/host_shadow can compile
 // the SAME source with g++ and check it against the golden fixtures in a container without a
-// GPU; nothing in the shipped library calls the host instantiations.
+// GPU; under nvcc every function here is __device__ only.
 //
 // Formulation (differs from the reference on purpose; see DESIGN.md "Kernel math"):
 //  * Near field: every ot_geo frame is a +-pi/2 tilt about x (ot_geo.py:61-66), so all surfaces
@@ -20,9 +20,23 @@
 #include <math.h>
 
 #if defined(__CUDACC__)
-#define SOLAT_HD __host__ __device__ __forceinline__
-#else
+#define SOLAT_HD __device__ __forceinline__
+#define SOLAT_TABLE __constant__          // coefficient tables live in the constant bank: DFMA reads c[bank][ofs]
+#else                                     // directly, where a literal would cost two UMOVs per use
 #define SOLAT_HD inline
+#define SOLAT_TABLE static const
+#endif
+
+// Newton steps after the MUFU seed.  Measured on B200 (tools/variant_bench.py math, profiles/r01_variants.md):
+// seed 9.5e-7, 1 step 8.9e-13, 2 steps 1.1e-16 (full); rsqrt third-order step alone 2.2e-16 (full).
+#ifndef SOLAT_RCP_ITERS
+#define SOLAT_RCP_ITERS 2        // geometry: full precision
+#endif
+#ifndef SOLAT_RCP_STEP_ITERS
+#define SOLAT_RCP_STEP_ITERS 1   // Newton step sizes: 9e-13 relative, self-correcting
+#endif
+#ifndef SOLAT_RSQRT_POLISH
+#define SOLAT_RSQRT_POLISH 0
 #endif
 
 namespace solat {
@@ -44,39 +58,48 @@ SOLAT_HD vec3 mk(double x, double y, double z) { vec3 r; r.x = x; r.y = y; r.z =
 SOLAT_HD double dot(const vec3& a, const vec3& b) { return fma(a.x, b.x, fma(a.y, b.y, a.z * b.z)); }
 SOLAT_HD vec3 axpy(const vec3& p, const vec3& d, double t) { return mk(fma(d.x, t, p.x), fma(d.y, t, p.y), fma(d.z, t, p.z)); }
 
-// Reciprocal / reciprocal-sqrt.  Device: MUFU seed (rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64,
-// ~2^-22 relative) + Newton in FMA form; two rcp steps / one third-order rsqrt step + one
-// second-order step bring the error to <= 2 ulp without the IEEE slow-path branch that the
-// compiler's a/b carries.  Operands on this path are O(1e-4 .. 1e9) and never denormal.
-SOLAT_HD double rcp_fast(double a)
+// Reciprocal / reciprocal-sqrt.  Device: MUFU seed (rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64)
+// + Newton in FMA form, without the IEEE slow-path branch that the compiler's a/b carries.  Operands on
+// this path are O(1e-4 .. 1e9) and never denormal.  ITERS Newton steps; accuracy per variant is measured on
+// the device by solat_selftest_math (tests/test_gpu_parity.py::test_fast_math_primitives).
+template <int ITERS>
+SOLAT_HD double rcp_n(double a)
 {
 #if defined(__CUDA_ARCH__) && !defined(SOLAT_EXACT_DIV)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
-    double e = fma(-a, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-a, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-a, r, 1.0);
-    return fma(r, e, r);
+#pragma unroll
+    for (int i = 0; i < ITERS; i++) {
+        const double e = fma(-a, r, 1.0);
+        r = fma(r, e, r);
+    }
+    return r;
 #else
     return 1.0 / a;
 #endif
 }
-SOLAT_HD double rsqrt_fast(double a)
+SOLAT_HD double rcp_fast(double a) { return rcp_n<SOLAT_RCP_ITERS>(a); }      // geometry (path lengths, normals)
+SOLAT_HD double rcp_step(double a) { return rcp_n<SOLAT_RCP_STEP_ITERS>(a); } // Newton step sizes: self-correcting
+template <int POLISH>
+SOLAT_HD double rsqrt_n(double a)
 {
 #if defined(__CUDA_ARCH__) && !defined(SOLAT_EXACT_DIV)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    // e = 1 - a y^2 ;  y <- y (1 + e/2 + 3 e^2/8)   (third order), then one second-order polish
+    // e = 1 - a y^2 ;  y <- y (1 + e/2 + 3 e^2/8)   (third order), then optional second-order polish
     double e = fma(-a * y, y, 1.0);
     y = fma(y * e, fma(0.375, e, 0.5), y);
-    e = fma(-a * y, y, 1.0);
-    return fma(y * 0.5, e, y);
+#pragma unroll
+    for (int i = 0; i < POLISH; i++) {
+        e = fma(-a * y, y, 1.0);
+        y = fma(y * 0.5, e, y);
+    }
+    return y;
 #else
     return 1.0 / sqrt(a);
 #endif
 }
+SOLAT_HD double rsqrt_fast(double a) { return rsqrt_n<SOLAT_RSQRT_POLISH>(a); }
 
 // Snell refraction, same vector law as ray_trace_int.py:20-30 written without cross products:
 //   s2 = mu (s - (N.s) N) - N sqrt(1 - mu^2 (1 - (N.s)^2)),   N pointing against propagation.
@@ -103,7 +126,7 @@ struct Asphere {
     double g1, g2, g3, g4;     // slope polynomial 2a1, 4a2, 6a3, 8a4
     double y0;                 // surface vertex at y = -y0 in the telescope frame
 };
-SOLAT_HD constexpr Asphere make_asphere(double R, double k, double a1, double a2, double a3, double a4, double y0)
+constexpr Asphere make_asphere(double R, double k, double a1, double a2, double a3, double a4, double y0)
 {
     return Asphere{1.0 / R, (1.0 + k) * (1.0 / R) * (1.0 / R), 1.0 / ((1.0 + k) * (1.0 / R)),
                    a1, a2, a3, a4, 2.0 * a1, 4.0 * a2, 6.0 * a3, 8.0 * a4, y0};
@@ -112,46 +135,54 @@ constexpr double LENS1_Y = 975.08;                                             /
 constexpr double LENS2_Y = 592.76;                                             // ot_geo.py:69
 constexpr double LENS3_Y = 180.8 - ((2.5 + 1.513) - (35.16 - 32.19));          // ot_geo.py:70
 constexpr double LYOT_Y = 453.62;                                              // ot_geo.py:71
-constexpr double Y_1B = LENS1_Y;                                               // ot_geo.py:166
-constexpr double Y_2B = LENS2_Y;                                               // ot_geo.py:277
+// plane offsets: [0] 1B (ot_geo.py:166), [1] 2B (:277), [2] Lyot (:526)
+SOLAT_TABLE double K_NF_PLANE[] = {LENS1_Y, LENS2_Y, LYOT_Y};
+#define Y_1B (K_NF_PLANE[0])
+#define Y_2B (K_NF_PLANE[1])
+#define Y_LYOT (K_NF_PLANE[2])
 // ot_geo.py:85-91, :197-203, :301-307, :323-329 with the offsets of :178, :289, :478, :490
 enum { SURF_1A = 0, SURF_2A = 1, SURF_3A = 2, SURF_3B = 3 };
-template <int S>
-SOLAT_HD constexpr Asphere asphere_of()
-{
-    return S == SURF_1A ? make_asphere(-1510.61, 12.0966, -5.876941e-5, 1.769198e-9, -1.310183e-15, 1.994766e-19, LENS1_Y - 19.32)
-         : S == SURF_2A ? make_asphere(-871.25, -10.201256, -1.147640e-04, 1.103643e-10, -2.969608e-14, 5.980271e-19, LENS2_Y - 26.47)
-         : S == SURF_3A ? make_asphere(6608.30, 414.142695, -2.981594e-06, 3.955202e-10, 3.180727e-16, 0.0, LENS3_Y)
-                        : make_asphere(604.44, -3.177341, 2.366829e-05, -1.000417e-10, -6.565681e-15, 0.0, LENS3_Y + 35.16);
-}
+SOLAT_TABLE Asphere K_ASPH[4] = {
+    make_asphere(-1510.61, 12.0966, -5.876941e-5, 1.769198e-9, -1.310183e-15, 1.994766e-19, LENS1_Y - 19.32),
+    make_asphere(-871.25, -10.201256, -1.147640e-04, 1.103643e-10, -2.969608e-14, 5.980271e-19, LENS2_Y - 26.47),
+    make_asphere(6608.30, 414.142695, -2.981594e-06, 3.955202e-10, 3.180727e-16, 0.0, LENS3_Y),
+    make_asphere(604.44, -3.177341, 2.366829e-05, -1.000417e-10, -6.565681e-15, 0.0, LENS3_Y + 35.16)};
 
 // Hit of the ray P + t d with asphere S.  On return H is the hit point, N the unit normal in the
 // telescope frame with N.y > 0 (= reference n_hat rotated back), t the ray parameter.
 template <int S>
 SOLAT_HD int asphere_hit(const vec3& P, const vec3& d, double lo, double hi, double& t, vec3& H, vec3& N)
 {
-    constexpr Asphere A = asphere_of<S>();
+    const Asphere& A = K_ASPH[S];
     const double py = P.y + A.y0;
     t = -py * rcp_fast(d.y);
     double x, z, u, w, rs, G, dt = 0.0;
-    int it = 0;
-    bool done = false;
-    for (;;) {
-        x = fma(d.x, t, P.x);
-        z = fma(d.z, t, P.z);
-        u = fma(x, x, z * z);
-        w = fma(-A.K, u, 1.0);
-        rs = rsqrt_fast(w);
-        G = fma(A.c, rs, fma(u, fma(u, fma(u, A.g4, A.g3), A.g2), A.g1));
-        if (done) break;            // normally after 3 updates (the third is ~1e-13 mm)
-        const double sag = fma(fma(-w, rs, 1.0), A.Kinv, u * fma(u, fma(u, fma(u, A.a4, A.a3), A.a2), A.a1));
-        const double f = fma(d.y, t, py) - sag;
-        const double fp = fma(-G, fma(x, d.x, z * d.z), d.y);
-        dt = f * rcp_fast(fp);
-        t -= dt;
-        ++it;
-        done = (it >= 3 && !(fabs(dt) > 1e-9)) || it >= 10;
+    // one Newton update: evaluates (u, G) at t, then moves t
+#define SOLAT_ASPH_EVAL()                                                              \
+    x = fma(d.x, t, P.x);                                                              \
+    z = fma(d.z, t, P.z);                                                              \
+    u = fma(x, x, z * z);                                                              \
+    w = fma(-A.K, u, 1.0);                                                             \
+    rs = rsqrt_fast(w);                                                                \
+    G = fma(A.c, rs, fma(u, fma(u, fma(u, A.g4, A.g3), A.g2), A.g1));
+#define SOLAT_ASPH_STEP()                                                              \
+    {                                                                                  \
+        const double sag = fma(fma(-w, rs, 1.0), A.Kinv, u * fma(u, fma(u, fma(u, A.a4, A.a3), A.a2), A.a1)); \
+        const double f = fma(d.y, t, py) - sag;                                        \
+        const double fp = fma(-G, fma(x, d.x, z * d.z), d.y);                          \
+        dt = f * rcp_step(fp);                                                         \
+        t -= dt;                                                                       \
     }
+    SOLAT_ASPH_EVAL() SOLAT_ASPH_STEP()
+    SOLAT_ASPH_EVAL() SOLAT_ASPH_STEP()
+    SOLAT_ASPH_EVAL() SOLAT_ASPH_STEP()          // third update is ~1e-13 mm on nominal rays
+    SOLAT_ASPH_EVAL()
+    for (int it = 3; fabs(dt) > 1e-9 && it < 10; ++it) {   // off-nominal rays only
+        SOLAT_ASPH_STEP()
+        SOLAT_ASPH_EVAL()
+    }
+#undef SOLAT_ASPH_EVAL
+#undef SOLAT_ASPH_STEP
     H = mk(x, fma(d.y, t, P.y), z);
     const double nn = rsqrt_fast(fma(G * G, u, 1.0));
     N = mk(-x * G * nn, nn, -z * G * nn);
@@ -195,7 +226,7 @@ SOLAT_HD void nf_source_ray(const vec3& p0, const vec3& d0, double n_si, double 
     d = refract(d, mk(0.0, -1.0, 0.0), mu_in);                                  // rti:1154 (-n_hat)
     st |= asphere_hit<SURF_2A>(r.p2b, d, 0.0, 100.0, t4, r.p2a, N);            // rti:1228
     d = refract(d, mk(-N.x, -N.y, -N.z), mu_out);                               // rti:1254
-    st |= plane_hit(r.p2a, d, LYOT_Y, 10.0, 900.0, t5, r.lyot);                // rti:1295
+    st |= plane_hit(r.p2a, d, Y_LYOT, 10.0, 900.0, t5, r.lyot);                // rti:1295
     r.d_out = d;
     r.opl = (t1) + (t2 * n_si) + (t3) + (t4 * n_si) + t5;                       // rti:1341-1343
     if (r.opl != r.opl) st |= ST_NAN;
@@ -222,7 +253,7 @@ SOLAT_HD void nf_rx_ray(const vec3& p0, const vec3& d0, double n_si, double n_va
     d = refract(d0, N, n_vac / n_si);                                           // rti:679
     st |= asphere_hit<SURF_3B>(r.p3a, d, 5.0, 200.0, t2, r.p3b, N);            // rti:719
     d = refract(d, N, n_si / n_vac);                                            // rti:743
-    st |= plane_hit(r.p3b, d, LYOT_Y, 1.0, 2000.0, t3, r.lyot);                // rti:784
+    st |= plane_hit(r.p3b, d, Y_LYOT, 1.0, 2000.0, t3, r.lyot);                // rti:784
     r.d_out = d;
     // rti:848: Euclidean leg lengths, n_si inside lens 3
     r.opl = (dist3(r.p3b, r.p3a) * n_si) + dist3(r.p3a, p0) + dist3(r.lyot, r.p3b);
@@ -269,41 +300,63 @@ SOLAT_HD void nf_toy_ray(const vec3& p0, const vec3& d0, double y_ap, double n_s
 // Only even powers of x occur; Horner in v = y/R per power of u^2.
 // ------------------------------------------------------------------------------------------
 constexpr double FF_RN = 3000.0;
-constexpr double FF_INV_RN = 1.0 / 3000.0;
-constexpr double Y_CENT_M1 = -7201.003729431267;                                // saf:19
+// [0] 1/R_N, [1] 2/R_N, [2] y_cent_m1 (saf:19), [3] aperture radius^2 (saf:378), [4] aperture plane z (latrt_geo.py:244)
+SOLAT_TABLE double K_FF[] = {1.0 / 3000.0, 2.0 / 3000.0, -7201.003729431267, 3e3 * 3e3, 4000.0};
+#define FF_INV_RN (K_FF[0])
+#define Y_CENT_M1 (K_FF[2])
+
+// Horner tables: rows i = 0, 2, 4, 6 of a1 / a2 (latrt_geo.py:55-61, :63-71) as polynomials in v = y/R,
+// followed by their v-derivatives.  z = P0 + w (P2 + w (P4 + w P6)), w = (x/R)^2.
+SOLAT_TABLE double K_M1[] = {
+    /* P0/v^2 [0..4] */ -57.74022, 1.5373825, 1.154294, -0.441762, 0.0906601,
+    /* P2 [5..9]     */ -72.17349, 1.8691899, 2.8859421, -1.026471, 0.2610568,
+    /* P4 [10..12]   */ 1.8083973, -0.603195, 0.2177414,
+    /* P6 [13]       */ 0.0394559,
+    /* dP0/v [14..18]*/ 2 * -57.74022, 3 * 1.5373825, 4 * 1.154294, 5 * -0.441762, 6 * 0.0906601,
+    /* dP2 [19..22]  */ 1.8691899, 2 * 2.8859421, 3 * -1.026471, 4 * 0.2610568,
+    /* dP4 [23..24]  */ -0.603195, 2 * 0.2177414,
+    /* 2P4, 3P6 scale handled in code */};
+SOLAT_TABLE double K_M2[] = {
+    /* P0/v^2 [0..5] */ 103.90461, 6.6513025, 2.8405781, -0.7819705, -0.0400483, 0.0896645,
+    /* P2 [6..11]    */ 115.44758, 7.3024355, 5.7640389, -1.578144, -0.0354326, 0.2781226,
+    /* P4 [12..15]   */ 2.9130983, -0.8104051, -0.0185283, 0.2626023,
+    /* P6 [16..17]   */ -0.0250794, 0.0709672,
+    /* dP0/v [18..23]*/ 2 * 103.90461, 3 * 6.6513025, 4 * 2.8405781, 5 * -0.7819705, 6 * -0.0400483, 7 * 0.0896645,
+    /* dP2 [24..28]  */ 7.3024355, 2 * 5.7640389, 3 * -1.578144, 4 * -0.0354326, 5 * 0.2781226,
+    /* dP4 [29..31]  */ -0.8104051, 2 * -0.0185283, 3 * 0.2626023,
+    /* dP6 [32]      */ 0.0709672};
 
 // z and its partials wrt the LOCAL coordinates x, y (mm)
 SOLAT_HD void m1_sag(double x, double y, double& z, double& zx, double& zy)
 {
+    const double* K = K_M1;
     const double u = x * FF_INV_RN, v = y * FF_INV_RN, w = u * u;
-    // rows i = 0, 2, 4, 6 of a1 (latrt_geo.py:55-61)
-    const double p0 = v * v * fma(v, fma(v, fma(v, fma(v, 0.0906601, -0.441762), 1.154294), 1.5373825), -57.74022);
-    const double p2 = fma(v, fma(v, fma(v, fma(v, 0.2610568, -1.026471), 2.8859421), 1.8691899), -72.17349);
-    const double p4 = fma(v, fma(v, 0.2177414, -0.603195), 1.8083973);
-    const double p6 = 0.0394559;
+    const double p0 = v * v * fma(v, fma(v, fma(v, fma(v, K[4], K[3]), K[2]), K[1]), K[0]);
+    const double p2 = fma(v, fma(v, fma(v, fma(v, K[9], K[8]), K[7]), K[6]), K[5]);
+    const double p4 = fma(v, fma(v, K[12], K[11]), K[10]);
+    const double p6 = K[13];
     z = fma(w, fma(w, fma(w, p6, p4), p2), p0);
-    // d/dv
-    const double q0 = v * fma(v, fma(v, fma(v, fma(v, 6 * 0.0906601, 5 * -0.441762), 4 * 1.154294), 3 * 1.5373825), 2 * -57.74022);
-    const double q2 = fma(v, fma(v, fma(v, 4 * 0.2610568, 3 * -1.026471), 2 * 2.8859421), 1.8691899);
-    const double q4 = fma(v, 2 * 0.2177414, -0.603195);
+    const double q0 = v * fma(v, fma(v, fma(v, fma(v, K[18], K[17]), K[16]), K[15]), K[14]);
+    const double q2 = fma(v, fma(v, fma(v, K[22], K[21]), K[20]), K[19]);
+    const double q4 = fma(v, K[24], K[23]);
     zy = fma(w, fma(w, q4, q2), q0) * FF_INV_RN;
-    zx = 2.0 * u * fma(w, fma(w, 3.0 * p6, 2.0 * p4), p2) * FF_INV_RN;
+    zx = K_FF[1] * u * fma(w, fma(w, 3.0 * p6, 2.0 * p4), p2);
 }
 SOLAT_HD void m2_sag(double x, double y, double& z, double& zx, double& zy)
 {
+    const double* K = K_M2;
     const double u = x * FF_INV_RN, v = y * FF_INV_RN, w = u * u;
-    // rows i = 0, 2, 4, 6 of a2 (latrt_geo.py:63-71)
-    const double p0 = v * v * fma(v, fma(v, fma(v, fma(v, fma(v, 0.0896645, -0.0400483), -0.7819705), 2.8405781), 6.6513025), 103.90461);
-    const double p2 = fma(v, fma(v, fma(v, fma(v, fma(v, 0.2781226, -0.0354326), -1.578144), 5.7640389), 7.3024355), 115.44758);
-    const double p4 = fma(v, fma(v, fma(v, 0.2626023, -0.0185283), -0.8104051), 2.9130983);
-    const double p6 = fma(v, 0.0709672, -0.0250794);
+    const double p0 = v * v * fma(v, fma(v, fma(v, fma(v, fma(v, K[5], K[4]), K[3]), K[2]), K[1]), K[0]);
+    const double p2 = fma(v, fma(v, fma(v, fma(v, fma(v, K[11], K[10]), K[9]), K[8]), K[7]), K[6]);
+    const double p4 = fma(v, fma(v, fma(v, K[15], K[14]), K[13]), K[12]);
+    const double p6 = fma(v, K[17], K[16]);
     z = fma(w, fma(w, fma(w, p6, p4), p2), p0);
-    const double q0 = v * fma(v, fma(v, fma(v, fma(v, fma(v, 7 * 0.0896645, 6 * -0.0400483), 5 * -0.7819705), 4 * 2.8405781), 3 * 6.6513025), 2 * 103.90461);
-    const double q2 = fma(v, fma(v, fma(v, fma(v, 5 * 0.2781226, 4 * -0.0354326), 3 * -1.578144), 2 * 5.7640389), 7.3024355);
-    const double q4 = fma(v, fma(v, 3 * 0.2626023, 2 * -0.0185283), -0.8104051);
-    const double q6 = 0.0709672;
+    const double q0 = v * fma(v, fma(v, fma(v, fma(v, fma(v, K[23], K[22]), K[21]), K[20]), K[19]), K[18]);
+    const double q2 = fma(v, fma(v, fma(v, fma(v, K[28], K[27]), K[26]), K[25]), K[24]);
+    const double q4 = fma(v, fma(v, K[31], K[30]), K[29]);
+    const double q6 = K[32];
     zy = fma(w, fma(w, fma(w, q6, q4), q2), q0) * FF_INV_RN;
-    zx = 2.0 * u * fma(w, fma(w, 3.0 * p6, 2.0 * p4), p2) * FF_INV_RN;
+    zx = K_FF[1] * u * fma(w, fma(w, 3.0 * p6, 2.0 * p4), p2);
 }
 
 struct Affine {          // y = A x + b, row-major A
@@ -364,7 +417,7 @@ SOLAT_HD void ff_build_frames(const FfGeom& g, double el, double az, FfFrames& f
     const double C[3] = {g.rotc[0], g.rotc[1], g.rotc[2]};
     // aperture plane
     f.ap_row[0] = Rm[6]; f.ap_row[1] = Rm[7]; f.ap_row[2] = Rm[8];
-    f.ap_num = 4000.0 - C[2] - (Rm[6] * (g.src[0] - C[0]) + Rm[7] * (g.src[1] - C[1]) + Rm[8] * (g.src[2] - C[2]));
+    f.ap_num = K_FF[4] - C[2] - (Rm[6] * (g.src[0] - C[0]) + Rm[7] * (g.src[1] - C[1]) + Rm[8] * (g.src[2] - C[2]));
     // F1 = diag(-1,1,-1) Rx(-th1), F2 = diag(-1,-1,1) Rx(-th2)
     const double c1 = cos(g.th_1), s1 = sin(g.th_1), c2 = cos(g.th2), s2 = sin(g.th2);
     const double F1[9] = {-1, 0, 0, 0, c1, s1, 0, s1, -c1};
@@ -420,11 +473,9 @@ SOLAT_HD int mirror_hit(const vec3& P, const vec3& D, double lo, double hi, cons
                         const vec3& dE, double& t, vec3& H, vec3& N)
 {
     t = -P.z * rcp_fast(D.z);
-    double dt = 0.0, z, zx, zy, x, y;
-    int it = 0;
-    for (;;) {
-        x = fma(D.x, t, P.x);
-        y = fma(D.y, t, P.y);
+    double dt = 0.0, z, zx, zy;
+    auto update = [&]() {
+        const double x = fma(D.x, t, P.x), y = fma(D.y, t, P.y);
         if (M == 1) m1_sag(x, y, z, zx, zy); else m2_sag(x, y, z, zx, zy);
         double f = fma(D.z, t, P.z) - z;
         double fp = D.z - fma(zx, D.x, zy * D.y);
@@ -435,12 +486,13 @@ SOLAT_HD int mirror_hit(const vec3& P, const vec3& D, double lo, double hi, cons
             f -= pe->a + pe->b * xpc + pe->c * ypc + pe->d * (xpc * xpc + ypc * ypc) + pe->e * (xpc * ypc);
             fp -= -dE.x * (pe->b + 2.0 * pe->d * xpc + pe->e * ypc) + dE.y * (pe->c + 2.0 * pe->d * ypc + pe->e * xpc);
         }
-        dt = f * rcp_fast(fp);
+        dt = f * rcp_step(fp);
         t -= dt;
-        ++it;
-        if (it >= 3 && !(fabs(dt) > 1e-8)) break;
-        if (it >= 12) break;
-    }
+    };
+    update();
+    update();
+    update();                                             // ~1e-11 mm on nominal rays
+    for (int it = 3; fabs(dt) > 1e-8 && it < 12; ++it) update();   // off-nominal rays only
     H = mk(fma(D.x, t, P.x), fma(D.y, t, P.y), fma(D.z, t, P.z));
     if (PANEL) {   // reference normal = ideal-mirror gradient at the final point (saf:718-720, :869-871)
         if (M == 1) m1_sag(H.x, H.y, z, zx, zy); else m2_sag(H.x, H.y, z, zx, zy);
@@ -460,7 +512,7 @@ SOLAT_HD int ff_aperture(const FfGeom& g, const FfFrames& f, const vec3& d, doub
     t_ap = f.ap_num * rcp_fast(dot(mk(f.ap_row[0], f.ap_row[1], f.ap_row[2]), d));
     Pa = mk(fma(d.x, t_ap, g.src[0]), fma(d.y, t_ap, g.src[1]), fma(d.z, t_ap, g.src[2]));
     const double dy = Pa.y - Y_CENT_M1;
-    return !(fma(Pa.x, Pa.x, dy * dy) > 3e3 * 3e3);
+    return !(fma(Pa.x, Pa.x, dy * dy) > K_FF[3]);
 }
 
 struct FfRay {
