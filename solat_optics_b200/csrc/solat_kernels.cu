@@ -91,6 +91,7 @@ struct DevBuf {
 struct AngleTabs {
     const double *st, *ct, *sp, *cp;   // sin/cos of theta[nth], phi[nph]
     int nth, nph;                      // nph == 0: paired mode, ray ii uses theta[ii], phi[ii] (phi has nth entries)
+    unsigned magic;                    // ceil(2^32 / nth): r / nth == __umulhi(r, magic) (+1 fix-up) for r < 2^32 / nth
     __host__ __device__ int rays() const { return nph == 0 ? nth : nth * nph; }
 };
 struct AngleTabsOwner {
@@ -107,13 +108,26 @@ struct AngleTabsOwner {
         CK(cudaStreamSynchronize(s));   // h goes out of scope
         tabs.st = buf.p; tabs.ct = buf.p + nth; tabs.sp = buf.p + 2 * nth; tabs.cp = buf.p + 2 * nth + nph;
         tabs.nth = nth; tabs.nph = nph_arg;
+        const unsigned long long rays = (unsigned long long)nth * (unsigned long long)nph;
+        tabs.magic = (rays * (unsigned long long)nth < 0x100000000ull && nth > 1)
+                         ? (unsigned)((0x100000000ull + (unsigned long long)nth - 1) / (unsigned long long)nth) : 0u;
         return 0;
     }
 };
 
 __device__ __forceinline__ vec3 ray_dir(const AngleTabs& a, int r)
 {
-    int j = r / a.nth, i = r - j * a.nth;   // meshgrid(theta, phi) raveled: theta is the fast index
+    // meshgrid(theta, phi) raveled: theta is the fast index.  r / nth by multiply-high: the estimate is at most
+    // one too large while r * nth < 2^32 (the compare fixes it up); larger fans take the plain division.
+    int j, i;
+    if (a.magic) {
+        j = (int)__umulhi((unsigned)r, a.magic);
+        i = r - j * a.nth;
+        if (i < 0) { i += a.nth; --j; }
+    } else {
+        j = r / a.nth;
+        i = r - j * a.nth;
+    }
     if (a.nph == 0) { i = r; j = r; }
     return launch_dir(__ldg(a.st + i), __ldg(a.ct + i), __ldg(a.sp + j), __ldg(a.cp + j));
 }

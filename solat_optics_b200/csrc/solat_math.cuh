@@ -142,6 +142,19 @@ SOLAT_TABLE double K_NF_PLANE[] = {LENS1_Y, LENS2_Y, LYOT_Y};
 #define Y_LYOT (K_NF_PLANE[2])
 // ot_geo.py:85-91, :197-203, :301-307, :323-329 with the offsets of :178, :289, :478, :490
 enum { SURF_1A = 0, SURF_2A = 1, SURF_3A = 2, SURF_3B = 3 };
+struct AsphereF {   // single-precision copy for the coarse first Newton update
+    float c, K, a1, a2, a3, a4, g1, g2, g3, g4;
+};
+constexpr AsphereF make_asphere_f(double R, double k, double a1, double a2, double a3, double a4)
+{
+    return AsphereF{(float)(1.0 / R), (float)((1.0 + k) * (1.0 / R) * (1.0 / R)), (float)a1, (float)a2, (float)a3, (float)a4,
+                    (float)(2.0 * a1), (float)(4.0 * a2), (float)(6.0 * a3), (float)(8.0 * a4)};
+}
+SOLAT_TABLE AsphereF K_ASPHF[4] = {
+    make_asphere_f(-1510.61, 12.0966, -5.876941e-5, 1.769198e-9, -1.310183e-15, 1.994766e-19),
+    make_asphere_f(-871.25, -10.201256, -1.147640e-04, 1.103643e-10, -2.969608e-14, 5.980271e-19),
+    make_asphere_f(6608.30, 414.142695, -2.981594e-06, 3.955202e-10, 3.180727e-16, 0.0),
+    make_asphere_f(604.44, -3.177341, 2.366829e-05, -1.000417e-10, -6.565681e-15, 0.0)};
 SOLAT_TABLE Asphere K_ASPH[4] = {
     make_asphere(-1510.61, 12.0966, -5.876941e-5, 1.769198e-9, -1.310183e-15, 1.994766e-19, LENS1_Y - 19.32),
     make_asphere(-871.25, -10.201256, -1.147640e-04, 1.103643e-10, -2.969608e-14, 5.980271e-19, LENS2_Y - 26.47),
@@ -150,40 +163,66 @@ SOLAT_TABLE Asphere K_ASPH[4] = {
 
 // Hit of the ray P + t d with asphere S.  On return H is the hit point, N the unit normal in the
 // telescope frame with N.y > 0 (= reference n_hat rotated back), t the ray parameter.
+SOLAT_HD float rsqrt_f(float a)
+{
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(a);
+#else
+    return 1.0f / sqrtf(a);
+#endif
+}
+SOLAT_HD float div_f(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+
+// Newton schedule shared by all curved surfaces (DESIGN.md "Mixed-precision Newton"):
+//   update 1 from the vertex-plane hit is evaluated in FP32 on the otherwise idle FMA pipe -- its own
+//            truncation error (curvature x step^2 ~ 1e-4 .. 1e-2 mm) dwarfs FP32 rounding (~1e-5 mm);
+//   updates 2 and 3 are FP64 and converge quadratically to < 1e-12 mm; the unit normal uses the slope of the
+//            last evaluation (the last step is < 1e-9 mm, i.e. < 1e-13 rad in the normal).
 template <int S>
 SOLAT_HD int asphere_hit(const vec3& P, const vec3& d, double lo, double hi, double& t, vec3& H, vec3& N)
 {
     const Asphere& A = K_ASPH[S];
     const double py = P.y + A.y0;
-    t = -py * rcp_fast(d.y);
+    t = -py * rcp_step(d.y);
+    {   // coarse update in single precision; on the vertex plane the residual is just -sag
+        const AsphereF& F = K_ASPHF[S];
+        const float dxf = (float)d.x, dyf = (float)d.y, dzf = (float)d.z;
+        const float xf = (float)fma(d.x, t, P.x), zf = (float)fma(d.z, t, P.z);
+        const float uf = fmaf(xf, xf, zf * zf);
+        const float rsf = rsqrt_f(fmaf(-F.K, uf, 1.0f));
+        const float sagf = fmaf(div_f(F.c * uf, 1.0f + div_f(1.0f, rsf)), 1.0f, uf * fmaf(uf, fmaf(uf, fmaf(uf, F.a4, F.a3), F.a2), F.a1));
+        const float Gf = fmaf(F.c, rsf, fmaf(uf, fmaf(uf, fmaf(uf, F.g4, F.g3), F.g2), F.g1));
+        const float fpf = fmaf(-Gf, fmaf(xf, dxf, zf * dzf), dyf);
+        t += (double)div_f(sagf, fpf);
+    }
     double x, z, u, w, rs, G, dt = 0.0;
-    // one Newton update: evaluates (u, G) at t, then moves t
-#define SOLAT_ASPH_EVAL()                                                              \
-    x = fma(d.x, t, P.x);                                                              \
-    z = fma(d.z, t, P.z);                                                              \
-    u = fma(x, x, z * z);                                                              \
-    w = fma(-A.K, u, 1.0);                                                             \
-    rs = rsqrt_fast(w);                                                                \
-    G = fma(A.c, rs, fma(u, fma(u, fma(u, A.g4, A.g3), A.g2), A.g1));
-#define SOLAT_ASPH_STEP()                                                              \
+#define SOLAT_ASPH_UPDATE()                                                            \
     {                                                                                  \
+        x = fma(d.x, t, P.x);                                                          \
+        z = fma(d.z, t, P.z);                                                          \
+        u = fma(x, x, z * z);                                                          \
+        w = fma(-A.K, u, 1.0);                                                         \
+        rs = rsqrt_fast(w);                                                            \
+        G = fma(A.c, rs, fma(u, fma(u, fma(u, A.g4, A.g3), A.g2), A.g1));              \
         const double sag = fma(fma(-w, rs, 1.0), A.Kinv, u * fma(u, fma(u, fma(u, A.a4, A.a3), A.a2), A.a1)); \
         const double f = fma(d.y, t, py) - sag;                                        \
         const double fp = fma(-G, fma(x, d.x, z * d.z), d.y);                          \
         dt = f * rcp_step(fp);                                                         \
         t -= dt;                                                                       \
     }
-    SOLAT_ASPH_EVAL() SOLAT_ASPH_STEP()
-    SOLAT_ASPH_EVAL() SOLAT_ASPH_STEP()
-    SOLAT_ASPH_EVAL() SOLAT_ASPH_STEP()          // third update is ~1e-13 mm on nominal rays
-    SOLAT_ASPH_EVAL()
-    for (int it = 3; fabs(dt) > 1e-9 && it < 10; ++it) {   // off-nominal rays only
-        SOLAT_ASPH_STEP()
-        SOLAT_ASPH_EVAL()
-    }
-#undef SOLAT_ASPH_EVAL
-#undef SOLAT_ASPH_STEP
-    H = mk(x, fma(d.y, t, P.y), z);
+    SOLAT_ASPH_UPDATE()
+    SOLAT_ASPH_UPDATE()
+    for (int it = 3; fabs(dt) > 1e-9 && it < 10; ++it) SOLAT_ASPH_UPDATE()   // off-nominal rays only
+#undef SOLAT_ASPH_UPDATE
+    // hit point: (x, z) of the last evaluation moved by the last (sub-1e-9 mm) step
+    H = mk(fma(d.x, t, P.x), fma(d.y, t, P.y), fma(d.z, t, P.z));
     const double nn = rsqrt_fast(fma(G * G, u, 1.0));
     N = mk(-x * G * nn, nn, -z * G * nn);
     int st = ST_OK;
@@ -326,37 +365,64 @@ SOLAT_TABLE double K_M2[] = {
     /* dP4 [29..31]  */ -0.8104051, 2 * -0.0185283, 3 * 0.2626023,
     /* dP6 [32]      */ 0.0709672};
 
+// single-precision copies (same layout) for the coarse first Newton update
+SOLAT_TABLE float K_M1F[] = {
+    -57.74022f, 1.5373825f, 1.154294f, -0.441762f, 0.0906601f, -72.17349f, 1.8691899f, 2.8859421f, -1.026471f, 0.2610568f,
+    1.8083973f, -0.603195f, 0.2177414f, 0.0394559f,
+    2 * -57.74022f, 3 * 1.5373825f, 4 * 1.154294f, 5 * -0.441762f, 6 * 0.0906601f,
+    1.8691899f, 2 * 2.8859421f, 3 * -1.026471f, 4 * 0.2610568f, -0.603195f, 2 * 0.2177414f};
+SOLAT_TABLE float K_M2F[] = {
+    103.90461f, 6.6513025f, 2.8405781f, -0.7819705f, -0.0400483f, 0.0896645f,
+    115.44758f, 7.3024355f, 5.7640389f, -1.578144f, -0.0354326f, 0.2781226f,
+    2.9130983f, -0.8104051f, -0.0185283f, 0.2626023f, -0.0250794f, 0.0709672f,
+    2 * 103.90461f, 3 * 6.6513025f, 4 * 2.8405781f, 5 * -0.7819705f, 6 * -0.0400483f, 7 * 0.0896645f,
+    7.3024355f, 2 * 5.7640389f, 3 * -1.578144f, 4 * -0.0354326f, 5 * 0.2781226f,
+    -0.8104051f, 2 * -0.0185283f, 3 * 0.2626023f, 0.0709672f};
+
+// The Horner bodies are written once for both precisions (T = double with fma, T = float with fmaf).
+#define SOLAT_M1_BODY(T, FMA, K, INV_RN, TWO_INV_RN)                                                     \
+    const T u = x * INV_RN, v = y * INV_RN, w = u * u;                                                   \
+    const T p0 = v * v * FMA(v, FMA(v, FMA(v, FMA(v, K[4], K[3]), K[2]), K[1]), K[0]);                   \
+    const T p2 = FMA(v, FMA(v, FMA(v, FMA(v, K[9], K[8]), K[7]), K[6]), K[5]);                           \
+    const T p4 = FMA(v, FMA(v, K[12], K[11]), K[10]);                                                    \
+    const T p6 = K[13];                                                                                  \
+    z = FMA(w, FMA(w, FMA(w, p6, p4), p2), p0);                                                          \
+    const T q0 = v * FMA(v, FMA(v, FMA(v, FMA(v, K[18], K[17]), K[16]), K[15]), K[14]);                  \
+    const T q2 = FMA(v, FMA(v, FMA(v, K[22], K[21]), K[20]), K[19]);                                     \
+    const T q4 = FMA(v, K[24], K[23]);                                                                   \
+    zy = FMA(w, FMA(w, q4, q2), q0) * INV_RN;                                                            \
+    zx = TWO_INV_RN * u * FMA(w, FMA(w, (T)3 * p6, (T)2 * p4), p2);
+#define SOLAT_M2_BODY(T, FMA, K, INV_RN, TWO_INV_RN)                                                     \
+    const T u = x * INV_RN, v = y * INV_RN, w = u * u;                                                   \
+    const T p0 = v * v * FMA(v, FMA(v, FMA(v, FMA(v, FMA(v, K[5], K[4]), K[3]), K[2]), K[1]), K[0]);     \
+    const T p2 = FMA(v, FMA(v, FMA(v, FMA(v, FMA(v, K[11], K[10]), K[9]), K[8]), K[7]), K[6]);           \
+    const T p4 = FMA(v, FMA(v, FMA(v, K[15], K[14]), K[13]), K[12]);                                     \
+    const T p6 = FMA(v, K[17], K[16]);                                                                   \
+    z = FMA(w, FMA(w, FMA(w, p6, p4), p2), p0);                                                          \
+    const T q0 = v * FMA(v, FMA(v, FMA(v, FMA(v, FMA(v, K[23], K[22]), K[21]), K[20]), K[19]), K[18]);   \
+    const T q2 = FMA(v, FMA(v, FMA(v, FMA(v, K[28], K[27]), K[26]), K[25]), K[24]);                      \
+    const T q4 = FMA(v, FMA(v, K[31], K[30]), K[29]);                                                    \
+    const T q6 = K[32];                                                                                  \
+    zy = FMA(w, FMA(w, FMA(w, q6, q4), q2), q0) * INV_RN;                                                \
+    zx = TWO_INV_RN * u * FMA(w, FMA(w, (T)3 * p6, (T)2 * p4), p2);
+
+SOLAT_HD void m1_sag_f(float x, float y, float& z, float& zx, float& zy)
+{
+    SOLAT_M1_BODY(float, fmaf, K_M1F, (1.0f / 3000.0f), (2.0f / 3000.0f))
+}
+SOLAT_HD void m2_sag_f(float x, float y, float& z, float& zx, float& zy)
+{
+    SOLAT_M2_BODY(float, fmaf, K_M2F, (1.0f / 3000.0f), (2.0f / 3000.0f))
+}
+
 // z and its partials wrt the LOCAL coordinates x, y (mm)
 SOLAT_HD void m1_sag(double x, double y, double& z, double& zx, double& zy)
 {
-    const double* K = K_M1;
-    const double u = x * FF_INV_RN, v = y * FF_INV_RN, w = u * u;
-    const double p0 = v * v * fma(v, fma(v, fma(v, fma(v, K[4], K[3]), K[2]), K[1]), K[0]);
-    const double p2 = fma(v, fma(v, fma(v, fma(v, K[9], K[8]), K[7]), K[6]), K[5]);
-    const double p4 = fma(v, fma(v, K[12], K[11]), K[10]);
-    const double p6 = K[13];
-    z = fma(w, fma(w, fma(w, p6, p4), p2), p0);
-    const double q0 = v * fma(v, fma(v, fma(v, fma(v, K[18], K[17]), K[16]), K[15]), K[14]);
-    const double q2 = fma(v, fma(v, fma(v, K[22], K[21]), K[20]), K[19]);
-    const double q4 = fma(v, K[24], K[23]);
-    zy = fma(w, fma(w, q4, q2), q0) * FF_INV_RN;
-    zx = K_FF[1] * u * fma(w, fma(w, 3.0 * p6, 2.0 * p4), p2);
+    SOLAT_M1_BODY(double, fma, K_M1, K_FF[0], K_FF[1])
 }
 SOLAT_HD void m2_sag(double x, double y, double& z, double& zx, double& zy)
 {
-    const double* K = K_M2;
-    const double u = x * FF_INV_RN, v = y * FF_INV_RN, w = u * u;
-    const double p0 = v * v * fma(v, fma(v, fma(v, fma(v, fma(v, K[5], K[4]), K[3]), K[2]), K[1]), K[0]);
-    const double p2 = fma(v, fma(v, fma(v, fma(v, fma(v, K[11], K[10]), K[9]), K[8]), K[7]), K[6]);
-    const double p4 = fma(v, fma(v, fma(v, K[15], K[14]), K[13]), K[12]);
-    const double p6 = fma(v, K[17], K[16]);
-    z = fma(w, fma(w, fma(w, p6, p4), p2), p0);
-    const double q0 = v * fma(v, fma(v, fma(v, fma(v, fma(v, K[23], K[22]), K[21]), K[20]), K[19]), K[18]);
-    const double q2 = fma(v, fma(v, fma(v, fma(v, K[28], K[27]), K[26]), K[25]), K[24]);
-    const double q4 = fma(v, fma(v, K[31], K[30]), K[29]);
-    const double q6 = K[32];
-    zy = fma(w, fma(w, fma(w, q6, q4), q2), q0) * FF_INV_RN;
-    zx = K_FF[1] * u * fma(w, fma(w, 3.0 * p6, 2.0 * p4), p2);
+    SOLAT_M2_BODY(double, fma, K_M2, K_FF[0], K_FF[1])
 }
 
 struct Affine {          // y = A x + b, row-major A
@@ -465,14 +531,21 @@ struct PanelErr {
 };
 
 // Newton hit of P + t D (mirror-local frame) with mirror M (1 or 2), starting on the local z=0 plane.
-// Three (z, grad) evaluations: two full updates, then a third update whose gradient is also used for
+// One FP32 coarse update, then two FP64 updates; the gradient of the last evaluation is also used for
 // the normal (the last step is ~1e-11 mm, so the normal is exact to 1e-16).  PE: optional panel
 // error, evaluated along its own affine image (pe + t de) of the ray (saf:676-703, :820-852).
 template <int M, bool PANEL>
 SOLAT_HD int mirror_hit(const vec3& P, const vec3& D, double lo, double hi, const PanelErr* pe, const vec3& pE,
                         const vec3& dE, double& t, vec3& H, vec3& N)
 {
-    t = -P.z * rcp_fast(D.z);
+    t = -P.z * rcp_step(D.z);
+    {   // coarse update in single precision (see asphere_hit); on the local z = 0 plane the residual is -z
+        const float xf = (float)fma(D.x, t, P.x), yf = (float)fma(D.y, t, P.y);
+        float zf, zxf, zyf;
+        if (M == 1) m1_sag_f(xf, yf, zf, zxf, zyf); else m2_sag_f(xf, yf, zf, zxf, zyf);
+        const float fpf = (float)D.z - fmaf(zxf, (float)D.x, zyf * (float)D.y);
+        t += (double)div_f(zf, fpf);
+    }
     double dt = 0.0, z, zx, zy;
     auto update = [&]() {
         const double x = fma(D.x, t, P.x), y = fma(D.y, t, P.y);
@@ -489,7 +562,6 @@ SOLAT_HD int mirror_hit(const vec3& P, const vec3& D, double lo, double hi, cons
         dt = f * rcp_step(fp);
         t -= dt;
     };
-    update();
     update();
     update();                                             // ~1e-11 mm on nominal rays
     for (int it = 3; fabs(dt) > 1e-8 && it < 12; ++it) update();   // off-nominal rays only
