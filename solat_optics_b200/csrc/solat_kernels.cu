@@ -29,8 +29,17 @@ using namespace solat;
 #ifndef SOLAT_FF_T
 #define SOLAT_FF_T 256      // threads per far-field CTA (= rays per batch)
 #endif
+#ifndef SOLAT_FF_PACK
+#define SOLAT_FF_PACK 1     // rays traced in lock step per thread (1: scalar, 2: d2 packs)
+#endif
 #ifndef SOLAT_FF_MINB
 #define SOLAT_FF_MINB 3     // resident far-field CTAs per SM the register allocation is capped for
+#endif
+#ifndef SOLAT_NF_T
+#define SOLAT_NF_T 256      // threads per near-field CTA
+#endif
+#ifndef SOLAT_NF_PACK
+#define SOLAT_NF_PACK 1     // rays traced in lock step per thread in the near-field map kernel
 #endif
 #ifndef SOLAT_NF_MINB
 #define SOLAT_NF_MINB 3
@@ -132,6 +141,12 @@ __device__ __forceinline__ vec3 ray_dir(const AngleTabs& a, int r)
     return launch_dir(__ldg(a.st + i), __ldg(a.ct + i), __ldg(a.sp + j), __ldg(a.cp + j));
 }
 
+__device__ __forceinline__ vec3t<d2> ray_dir2(const AngleTabs& a, int r0, int r1)
+{
+    const vec3 u = ray_dir(a, r0), v = ray_dir(a, r1);
+    return mk<d2>(d2(u.x, v.x), d2(u.y, v.y), d2(u.z, v.z));
+}
+
 // ------------------------------------------------------------------------------------------------
 // near field: per-ray dumps
 // ------------------------------------------------------------------------------------------------
@@ -183,6 +198,7 @@ __global__ void __launch_bounds__(128) nf_rows_kernel(NfRowsParams q)
 // near field: fused map
 // ------------------------------------------------------------------------------------------------
 constexpr int NF_MAXF = 4;
+constexpr int NF_T = SOLAT_NF_T;
 struct NfMapParams {
     AngleTabs ang;
     const double* src_xz;      // [npix][2]
@@ -224,33 +240,62 @@ __device__ __forceinline__ void block_reduce_store(double (&re)[NF], double (&im
     }
 }
 
+// SOLAT_NF_PACK rays per thread per loop trip.
 template <int NF>
-__global__ void __launch_bounds__(256, SOLAT_NF_MINB) nf_map_kernel(NfMapParams q)
+__global__ void __launch_bounds__(NF_T, SOLAT_NF_MINB) nf_map_kernel(NfMapParams q)
 {
     const int pix = blockIdx.x / q.tiles, tile = blockIdx.x - pix * q.tiles;
-    const vec3 p0 = mk(__ldg(q.src_xz + 2 * pix), q.y_ap, __ldg(q.src_xz + 2 * pix + 1));
+    const d2 px = d2(__ldg(q.src_xz + 2 * pix)), pz = d2(__ldg(q.src_xz + 2 * pix + 1));
+    const vec3t<d2> p0 = mk<d2>(px, d2(q.y_ap), pz);
     double re[NF], im[NF];
 #pragma unroll
     for (int f = 0; f < NF; f++) re[f] = im[f] = 0.0;
     int st = 0;
     const int q_end = min((tile + 1) * q.tile_len, q.n_act);
-    for (int a = tile * q.tile_len + threadIdx.x; a < q_end; a += blockDim.x) {
+#if SOLAT_NF_PACK == 2
+    // two rays per thread in lock step (d2 packs): thread t takes active rays base + t and base + T + t
+    for (int a0 = tile * q.tile_len + threadIdx.x; a0 < q_end; a0 += 2 * NF_T) {
+        const int a1 = a0 + NF_T;
+        const bool two = a1 < q_end;
+        const int r0 = __ldg(q.act_idx + a0), r1 = two ? __ldg(q.act_idx + a1) : r0;
+        const double2 rx0 = __ldg(q.act_rx + a0);
+        double2 rx1 = two ? __ldg(q.act_rx + a1) : rx0;
+        if (!two) rx1.y = 0.0;                         // the odd ray out is traced twice, counted once
+        NfSourceRayT<d2> ray;
+        nf_source_ray(p0, ray_dir2(q.ang, r0, r1), q.n_si, q.n_vac, ray);
+        st |= ray.status.a | (two ? ray.status.b : 0);
+        // holo_sim.py:176-177: exp(i k L_rx) exp(i k L_so); vignetted rays carry amplitude 0
+        const double L0 = rx0.x + ray.opl.a, L1 = rx1.x + ray.opl.b;
+        const double w0 = ray.valid.a ? rx0.y : 0.0, w1 = ray.valid.b ? rx1.y : 0.0;
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            double s0, c0, s1, c1;
+            sincos(L0 * q.kk[f], &s0, &c0);
+            sincos(L1 * q.kk[f], &s1, &c1);
+            re[f] = fma(w0, c0, fma(w1, c1, re[f]));
+            im[f] = fma(w0, s0, fma(w1, s1, im[f]));
+        }
+    }
+#else
+    const vec3 p0s = mk(px.a, q.y_ap, pz.a);
+    for (int a = tile * q.tile_len + threadIdx.x; a < q_end; a += NF_T) {
         const int r = __ldg(q.act_idx + a);
         const double2 rx = __ldg(q.act_rx + a);
         NfSourceRay ray;
-        nf_source_ray(p0, ray_dir(q.ang, r), q.n_si, q.n_vac, ray);
+        nf_source_ray(p0s, ray_dir(q.ang, r), q.n_si, q.n_vac, ray);
         st |= ray.status;
         if (ray.valid) {
             const double L = rx.x + ray.opl;   // holo_sim.py:176-177: exp(i k L_rx) exp(i k L_so)
 #pragma unroll
             for (int f = 0; f < NF; f++) {
-                double s, c;
-                sincos(L * q.kk[f], &s, &c);
-                re[f] = fma(rx.y, c, re[f]);
-                im[f] = fma(rx.y, s, im[f]);
+                double sn, cs;
+                sincos(L * q.kk[f], &sn, &cs);
+                re[f] = fma(rx.y, cs, re[f]);
+                im[f] = fma(rx.y, sn, im[f]);
             }
         }
     }
+#endif
     if (st) atomicOr(q.status, st);
     block_reduce_store<NF>(re, im, q.partial + ((size_t)pix * q.tiles + tile) * q.nfreq_total + q.f0);
 }
@@ -348,13 +393,12 @@ __global__ void __launch_bounds__(128) ff_rows_kernel(FfRowsParams q)
 // ------------------------------------------------------------------------------------------------
 // far field: project_to_data (far_field_latrt.py:9-32)
 // ------------------------------------------------------------------------------------------------
-__global__ void ff_project_scatter_kernel(const double* sim, int n_pts, const double* gx, const double* gy, int M,
-                                          double gx_max, double gy_max, int* win)
+__global__ void ff_project_scatter_kernel(const double* sim, int n_pts, FfGrid G, int* win)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_pts) return;
     if (sim[(size_t)15 * n_pts + r] == 0.0) return;                               // ffl:10
-    const int c = ff_cell(sim[(size_t)9 * n_pts + r], sim[(size_t)11 * n_pts + r], gx, gy, M, gx_max, gy_max);
+    const int c = ff_cell(sim[(size_t)9 * n_pts + r], sim[(size_t)11 * n_pts + r], G);
     if (c >= 0) atomicMax(win + c, r);                                            // ffl:28: later rays overwrite
 }
 __global__ void ff_project_fill_kernel(const double* sim, int n_pts, const int* win, int cells, double k, double2* out)
@@ -371,45 +415,54 @@ __global__ void ff_project_fill_kernel(const double* sim, int n_pts, const int* 
 // far field: fused map
 // ------------------------------------------------------------------------------------------------
 constexpr int FF_T = SOLAT_FF_T;
+constexpr int FF_WARPS = FF_T / 32;
+constexpr int FF_WQ = 32 * (SOLAT_FF_PACK + 1);   // per-warp queue capacity
 struct FfMapParams {
     AngleTabs ang;
     solat_ff_geom g;
     const double* azel;      // [npix][2] (az, el)
-    const double* gx;        // data_x[0,:]
-    const double* gy;        // data_y (M, M)
+    FfGrid grid;
     const double2* e_rec;    // (M, M)
-    double gx_max, gy_max, k;
-    int M;
+    double k;
+    double key_base, key_unit, key_inv_unit;   // fixed-point frame of the winner keys
     double* amp;
     double* phase;
     int* status;
 };
 
+// One CTA per (az, el) pixel, warps fully autonomous inside the ray loop (no CTA barrier):
+//   * each warp walks its share of the launch fan in chunks of 32 candidate rays, runs the cheap aperture test
+//     and compacts the survivors into its own shared-memory queue (ballot + popc);
+//   * whenever the queue holds a full batch, every lane pops SOLAT_FF_PACK rays and traces them (two mirrors,
+//     Newton in lock step for the pack) -- so the expensive stage always runs with full warps although 40 % of
+//     the fan misses the aperture;
+//   * the reference's "later ray overwrites the cell" becomes one 64-bit shared-memory atomicMax per ray on a
+//     key that carries the ray index above an exact fixed-point copy of its path length;
+//   * after one barrier the winners -- and only they -- get their phasor, are weighted by E_rec and reduced.
 __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams q)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int cells = q.M * q.M;
+    const int cells = q.grid.M * q.grid.M;
     FfFrames* fr = reinterpret_cast<FfFrames*>(smem_raw);
-    double* win_opl = reinterpret_cast<double*>(smem_raw + ((sizeof(FfFrames) + 15) / 16) * 16);
-    int* win_idx = reinterpret_cast<int*>(win_opl + cells);
-    int* queue = win_idx + cells;          // [2 * FF_T]
-    int* q_count = queue + 2 * FF_T;
+    unsigned long long* win = reinterpret_cast<unsigned long long*>(smem_raw + ((sizeof(FfFrames) + 15) / 16) * 16);
+    int* queues = reinterpret_cast<int*>(win + cells);          // [FF_WARPS][FF_WQ]
 
-    const int tid = threadIdx.x, pix = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
     const FfGeom g = to_geom(q.g);
-    if (tid == 0) {
-        ff_build_frames(g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
-        *q_count = 0;
-    }
-    for (int c = tid; c < cells; c += FF_T) win_idx[c] = -1;
+    if (tid == 0) ff_build_frames(g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
+    for (int c = tid; c < cells; c += FF_T) win[c] = 0ull;
+    __syncthreads();
+
+    int* wq = queues + warp * FF_WQ;
     const int n_rays = q.ang.nth * q.ang.nph;
-    int base = 0, st = 0;
+    const double cx = fr->centre[0], cz = fr->centre[2];
+    int st = 0, cnt = 0;                                   // cnt: queue fill, identical in all lanes of the warp
+    int chunk = warp;
     for (;;) {
-        __syncthreads();                                   // (A) queue counter and tables are stable
-        const int cnt = *q_count;
-        if (cnt < FF_T && base < n_rays) {
-            // fill: cheap aperture test on FF_T candidate rays, survivors appended to the queue
-            const int r = base + tid;
+        const bool more = chunk * 32 < n_rays;
+        if (cnt < 32 * SOLAT_FF_PACK && more) {
+            // fill: aperture test (saf:359-379) on 32 candidate rays
+            const int r = chunk * 32 + lane;
             bool ok = false;
             if (r < n_rays) {
                 vec3 Pa;
@@ -417,43 +470,66 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
                 ok = ff_aperture(g, *fr, ray_dir(q.ang, r), t_ap, Pa);
             }
             const unsigned m = __ballot_sync(0xffffffffu, ok);
-            const int lane = tid & 31;
-            int slot = 0;
-            if (lane == 0 && m) slot = atomicAdd(q_count, __popc(m));
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            if (ok) queue[slot + __popc(m & ((1u << lane) - 1u))] = r;
-            base += FF_T;
+            if (ok) wq[cnt + __popc(m & ((1u << lane) - 1u))] = r;
+            cnt += __popc(m);
+            chunk += FF_WARPS;
+            __syncwarp();
             continue;
         }
         if (cnt == 0) break;
-        const int n_take = min(cnt, FF_T);
-        const int r = tid < n_take ? queue[cnt - 1 - tid] : -1;
-        __syncthreads();                                   // (B) everybody has read the queue
-        if (tid == 0) *q_count = cnt - n_take;
-        int cell = -1;
-        double opl = 0.0;
-        if (r >= 0) {
-            const vec3 d = ray_dir(q.ang, r);
+        const int n_take = min(cnt, 32 * SOLAT_FF_PACK);
+        const int r0 = lane < n_take ? wq[cnt - 1 - lane] : -1;
+#if SOLAT_FF_PACK == 2
+        const int r1 = lane + 32 < n_take ? wq[cnt - 33 - lane] : -1;
+#endif
+        cnt -= n_take;
+        __syncwarp();
+        if (r0 >= 0) {
+#if SOLAT_FF_PACK == 2
+            const vec3t<d2> d = ray_dir2(q.ang, r0, r1 >= 0 ? r1 : r0);
+            vec3t<d2> Pa;
+            d2 t_ap;
+            ff_aperture(g, *fr, d, t_ap, Pa);
+            FfRayT<d2> ray;
+            ff_ray_trace<false, false, d2>(*fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+            st |= ray.status.a | (r1 >= 0 ? ray.status.b : 0);
+            const int rr[2] = {r0, r1};
+            const double oo[2] = {ray.opl.a, ray.opl.b}, fx[2] = {ray.foc.x.a, ray.foc.x.b}, fz[2] = {ray.foc.z.a, ray.foc.z.b};
+#pragma unroll
+            for (int l = 0; l < 2; l++) {
+#else
+            const vec3 d = ray_dir(q.ang, r0);
             vec3 Pa;
             double t_ap;
             ff_aperture(g, *fr, d, t_ap, Pa);
             FfRay ray;
-            ff_ray_trace<false, false>(*fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+            ff_ray_trace<false, false, double>(*fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
             st |= ray.status;
-            opl = ray.opl;
-            if (opl != 0.0)                                                        // ffl:10
-                cell = ff_cell(ray.foc.x - fr->centre[0], ray.foc.z - fr->centre[2], q.gx, q.gy, q.M, q.gx_max, q.gy_max);
-            if (cell >= 0) atomicMax(win_idx + cell, r);                           // ffl:28: last write wins
+            const int rr[1] = {r0};
+            const double oo[1] = {ray.opl}, fx[1] = {ray.foc.x}, fz[1] = {ray.foc.z};
+            {
+                const int l = 0;
+#endif
+                if (rr[l] >= 0 && oo[l] != 0.0) {                                   // ffl:10
+                    const int cell = ff_cell(fx[l] - cx, fz[l] - cz, q.grid);
+                    if (cell >= 0) {
+                        bool exact;
+                        const unsigned long long key = ff_key(rr[l], oo[l], q.key_base, q.key_inv_unit, exact, q.key_unit);
+                        if (!exact) st |= 8;
+                        atomicMax(win + cell, key);                                 // ffl:28: last write wins
+                    }
+                }
+            }
         }
-        __syncthreads();                                   // (C) winners of this batch are known
-        if (cell >= 0 && win_idx[cell] == r) win_opl[cell] = opl;
     }
+    __syncthreads();
     // winners-only phasor sum: sum_cells exp(i k L/1e3) * E_rec / M^2   (ff_sim.py:215-221)
     double re[1] = {0.0}, im[1] = {0.0};
     for (int c = tid; c < cells; c += FF_T) {
-        if (win_idx[c] >= 0) {
+        const unsigned long long key = win[c];
+        if (key != 0ull) {
             double cs, sn;
-            cis_large(q.k * win_opl[c] / 1e3, cs, sn);
+            cis_large(q.k * ff_key_opl(key, q.key_base, q.key_unit) / 1e3, cs, sn);
             const double2 e = __ldg(q.e_rec + c);
             re[0] += cs * e.x - sn * e.y;
             im[0] += cs * e.y + sn * e.x;
@@ -463,7 +539,7 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
     __shared__ double2 total;
     block_reduce_store<1>(re, im, &total);
     if (tid == 0) {
-        const double inv = 1.0 / ((double)q.M * (double)q.M);
+        const double inv = 1.0 / ((double)q.grid.M * (double)q.grid.M);
         const double a = total.x * inv, b = total.y * inv;
         q.amp[pix] = hypot(a, b);
         q.phase[pix] = atan2(b, a);
@@ -473,7 +549,7 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
 static size_t ff_map_smem(int M)
 {
     const size_t cells = (size_t)M * M;
-    return ((sizeof(FfFrames) + 15) / 16) * 16 + cells * sizeof(double) + cells * sizeof(int) + (2 * FF_T + 4) * sizeof(int);
+    return ((sizeof(FfFrames) + 15) / 16) * 16 + cells * sizeof(unsigned long long) + (size_t)FF_WARPS * FF_WQ * sizeof(int);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -672,7 +748,7 @@ struct solat_nf_plan {
     DevBuf<double> h_src, h_amp, h_phase;   // device staging for the host entry point
     DevBuf<int> status;
     std::vector<double> kk;
-    int n_act = 0, tiles = 1, tile_len = 0, threads = 256;
+    int n_act = 0, tiles = 1, tile_len = 0, threads = NF_T;
 };
 
 // Ray tiling of one pixel.  It depends on the ray count ONLY (never on the number of pixels), so the
@@ -685,8 +761,9 @@ static void nf_choose_tiling(solat_nf_plan* p)
     int best_tiles = min_tiles;
     for (int tiles = min_tiles; tiles < min_tiles + 6; tiles++) {
         const int len = (p->n_act + tiles - 1) / tiles;
-        const int iters = (len + p->threads - 1) / p->threads;
-        const double thread_eff = (double)p->n_act / ((double)tiles * iters * p->threads);
+        const int granule = SOLAT_NF_PACK * p->threads;   // rays per CTA per loop trip
+        const int iters = (len + granule - 1) / granule;
+        const double thread_eff = (double)p->n_act / ((double)tiles * iters * granule);
         if (thread_eff > best + 1e-9) { best = thread_eff; best_tiles = tiles; }
     }
     p->tiles = best_tiles;
@@ -849,11 +926,17 @@ int solat_ff_apert_fields(solat_ctx* c, const solat_ff_geom* g, const double* th
     return ff_rows(c, false, g, th, nth, ph, nph, centre, pidx1, pidx2, pan1, np1, pan2, np2, el, az, out17, status);
 }
 
-static void grid_max(const double* data_x, const double* data_y, int M, double* gx_max, double* gy_max)
+static FfGrid make_grid(const double* data_x, const double* data_y, int M, const double* d_gx, const double* d_gy)
 {
+    FfGrid G;
+    G.gx = d_gx; G.gy = d_gy; G.M = M;
     double a = data_x[0], b = data_y[0];
     for (int i = 1; i < M; i++) { a = fmax(a, data_x[i]); b = fmax(b, data_y[(size_t)i * M]); }   // ffl:19
-    *gx_max = a; *gy_max = b;
+    G.gx_max = a; G.gy_max = b;
+    const double sx = data_x[M - 1] - data_x[0], sy = data_y[(size_t)(M - 1) * M] - data_y[0];
+    G.inv_dx = (M > 1 && sx > 0) ? (M - 1) / sx : 0.0;     // first guess of searchsorted; the fix-up makes it exact
+    G.inv_dy = (M > 1 && sy > 0) ? (M - 1) / sy : 0.0;
+    return G;
 }
 
 int solat_ff_project(solat_ctx* c, const double* sim, int n_pts, const double* data_x, const double* data_y, int M,
@@ -872,9 +955,8 @@ int solat_ff_project(solat_ctx* c, const double* sim, int n_pts, const double* d
     if (int rc = d_win.reserve(cells)) return rc;
     if (int rc = d_out.reserve(cells)) return rc;
     CK(cudaMemsetAsync(d_win.p, 0xff, sizeof(int) * cells, s));
-    double gx_max, gy_max;
-    grid_max(data_x, data_y, M, &gx_max, &gy_max);
-    ff_project_scatter_kernel<<<(n_pts + 127) / 128, 128, 0, s>>>(d_sim.p, n_pts, d_gx.p, d_gy.p, M, gx_max, gy_max, d_win.p);
+    const FfGrid G = make_grid(data_x, data_y, M, d_gx.p, d_gy.p);
+    ff_project_scatter_kernel<<<(n_pts + 127) / 128, 128, 0, s>>>(d_sim.p, n_pts, G, d_win.p);
     LAUNCHED();
     ff_project_fill_kernel<<<(cells + 127) / 128, 128, 0, s>>>(d_sim.p, n_pts, d_win.p, cells, k, d_out.p);
     LAUNCHED();
@@ -894,8 +976,9 @@ struct solat_ff_plan {
     DevBuf<double2> e_rec;
     DevBuf<double> h_azel, h_amp, h_phase;
     DevBuf<int> status;
-    double gx_max, gy_max, k;
-    int M;
+    FfGrid grid;
+    double k, key_base, key_unit;
+    int M, n_rays;
     size_t smem;
 };
 
@@ -903,8 +986,8 @@ static int ff_map_launch(solat_ff_plan* p, const double* d_azel, int npix, doubl
 {
     CK(cudaSetDevice(p->ctx->device));
     FfMapParams q;
-    q.ang = p->ang.tabs; q.g = p->g; q.azel = d_azel; q.gx = p->gx.p; q.gy = p->gy.p; q.e_rec = p->e_rec.p;
-    q.gx_max = p->gx_max; q.gy_max = p->gy_max; q.k = p->k; q.M = p->M;
+    q.ang = p->ang.tabs; q.g = p->g; q.azel = d_azel; q.grid = p->grid; q.e_rec = p->e_rec.p;
+    q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
     q.amp = d_amp; q.phase = d_phase; q.status = p->status.p;
     ff_map_kernel<<<npix, FF_T, p->smem, s>>>(q);
     LAUNCHED();
@@ -922,15 +1005,24 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
     CK(cudaSetDevice(c->device));
     const size_t smem = ff_map_smem(M);
     if (smem > (size_t)c->prop.sharedMemPerBlockOptin)
-        return fail(SOLAT_ERR_ARG, "E_rec grid too large for the shared-memory winner table (M <= 136)");
+        return fail(SOLAT_ERR_ARG, "E_rec grid too large for the shared-memory winner table (M <= 168)");
+    if ((long long)nth * nph > FF_MAX_RAYS)
+        return fail(SOLAT_ERR_ARG, "launch fan too large for the 20-bit ray index of the winner key (<= 1048575 rays)");
     CK(cudaFuncSetAttribute(ff_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     solat_ff_plan* p = new solat_ff_plan();
-    p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem;
-    grid_max(data_x, data_y, M, &p->gx_max, &p->gy_max);
+    p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem; p->n_rays = nth * nph;
+    // fixed-point frame of the winner keys: every path length of this telescope lies within a few tens of metres
+    // of |source - rotation centre| + 2.2e4 mm; unit = half an ulp of that, so the offsets are exact integers
+    {
+        const double dx = g->src_mm[0] - g->rotc_mm[0], dy = g->src_mm[1] - g->rotc_mm[1], dz = g->src_mm[2] - g->rotc_mm[2];
+        p->key_base = rint(sqrt(dx * dx + dy * dy + dz * dz) + 2.2e4);
+        p->key_unit = ldexp(1.0, ilogb(p->key_base) - 53);
+    }
     cudaStream_t s = c->stream;
     int rc = p->ang.init(theta, nth, phi, nph, s);
     if (!rc) rc = p->gx.upload(data_x, M, s);                      // data_x[0, :]
     if (!rc) rc = p->gy.upload(data_y, (size_t)M * M, s);
+    if (!rc) p->grid = make_grid(data_x, data_y, M, p->gx.p, p->gy.p);
     if (!rc) rc = p->e_rec.upload(reinterpret_cast<const double2*>(e_rec), (size_t)M * M, s);
     if (!rc) rc = p->status.reserve(1);
     if (!rc && cudaMemsetAsync(p->status.p, 0, sizeof(int), s) != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "memset");

@@ -1,14 +1,14 @@
 // solat_math.cuh -- FP64 per-ray geometric optics for the LATR optics tube (near field) and the
 // LAT mirrors (far field).  Product code: every function here runs inside the sm_100a kernels of
-// solat_kernels.cu.  The functions are also marked __host__ so that tests/host_shadow can compile
-// the SAME source with g++ and check it against the golden fixtures in a container without a
-// GPU; under nvcc every function here is __device__ only.
+// solat_kernels.cu.  tests/host_shadow compiles the SAME source with g++ so that the per-ray math can
+// be checked against the golden fixtures in a container without a GPU; under nvcc every function
+// here is __device__ only.
 //
 // Formulation (differs from the reference on purpose; see DESIGN.md "Kernel math"):
 //  * Near field: every ot_geo frame is a +-pi/2 tilt about x (ot_geo.py:61-66), so all surfaces
 //    are written directly in the telescope frame as  y = -Y0 + sag(x^2+z^2)  and no per-surface
 //    frame transform is evaluated.  Intersection = Newton on the ray parameter from the
-//    vertex-plane hit (3 updates reach 1e-13 mm) instead of scipy brentq.
+//    vertex-plane hit instead of scipy brentq.
 //  * The conic term uses  c*u/(1+S) == (1-S)/((1+k)c)  and the gradient collapses to
 //    G = c/S + 2a1 + 4a2 u + 6a3 u^2 + 8a4 u^3  (ot_geo.py:125-135 sum to exactly this),
 //    so one rsqrt serves both sag and slope.
@@ -16,13 +16,18 @@
 //    maps that are built once per pixel (FfFrames) -- including the reference's (+el,+az)
 //    back-rotation that is not the inverse of its (-el,-az) forward rotation
 //    (solat_apert_field.py:249-257 vs latrt_geo.py:280-288), which parity needs.
+//  * Mixed-precision Newton: the first update from the vertex-plane hit is evaluated in FP32 on the
+//    otherwise idle FMA pipe (its truncation error dwarfs FP32 rounding); two FP64 updates follow.
+//  * Every routine is a template over the real type R: `double` traces one ray, `d2` traces two rays in
+//    lock step.  The fused map kernels use d2: two independent dependency chains per thread hide the
+//    8-cycle DFMA latency, and every coefficient / frame load and every barrier serves two rays.
 #pragma once
 #include <math.h>
 
 #if defined(__CUDACC__)
 #define SOLAT_HD __device__ __forceinline__
-#define SOLAT_TABLE __constant__          // coefficient tables live in the constant bank: DFMA reads c[bank][ofs]
-#else                                     // directly, where a literal would cost two UMOVs per use
+#define SOLAT_TABLE __constant__          // coefficient tables live in the constant bank (a literal double
+#else                                     // costs two UMOVs per use on sm_100)
 #define SOLAT_HD inline
 #define SOLAT_TABLE static const
 #endif
@@ -41,6 +46,11 @@
 
 namespace solat {
 
+using ::fabs;   // the pack overloads below must not hide the scalar library functions
+using ::fma;
+using ::fmaf;
+using ::sqrt;
+
 // ------------------------------------------------------------------------------------------
 // status flags (per ray / OR-reduced per launch)
 // ------------------------------------------------------------------------------------------
@@ -51,17 +61,9 @@ enum : int {
     ST_NAN = 4        // NaN in the optical path (total internal reflection / sqrt domain)
 };
 
-struct vec3 {
-    double x, y, z;
-};
-SOLAT_HD vec3 mk(double x, double y, double z) { vec3 r; r.x = x; r.y = y; r.z = z; return r; }
-SOLAT_HD double dot(const vec3& a, const vec3& b) { return fma(a.x, b.x, fma(a.y, b.y, a.z * b.z)); }
-SOLAT_HD vec3 axpy(const vec3& p, const vec3& d, double t) { return mk(fma(d.x, t, p.x), fma(d.y, t, p.y), fma(d.z, t, p.z)); }
-
-// Reciprocal / reciprocal-sqrt.  Device: MUFU seed (rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64)
-// + Newton in FMA form, without the IEEE slow-path branch that the compiler's a/b carries.  Operands on
-// this path are O(1e-4 .. 1e9) and never denormal.  ITERS Newton steps; accuracy per variant is measured on
-// the device by solat_selftest_math (tests/test_gpu_parity.py::test_fast_math_primitives).
+// ------------------------------------------------------------------------------------------
+// scalar primitives
+// ------------------------------------------------------------------------------------------
 template <int ITERS>
 SOLAT_HD double rcp_n(double a)
 {
@@ -78,8 +80,6 @@ SOLAT_HD double rcp_n(double a)
     return 1.0 / a;
 #endif
 }
-SOLAT_HD double rcp_fast(double a) { return rcp_n<SOLAT_RCP_ITERS>(a); }      // geometry (path lengths, normals)
-SOLAT_HD double rcp_step(double a) { return rcp_n<SOLAT_RCP_STEP_ITERS>(a); } // Newton step sizes: self-correcting
 template <int POLISH>
 SOLAT_HD double rsqrt_n(double a)
 {
@@ -99,70 +99,9 @@ SOLAT_HD double rsqrt_n(double a)
     return 1.0 / sqrt(a);
 #endif
 }
+SOLAT_HD double rcp_fast(double a) { return rcp_n<SOLAT_RCP_ITERS>(a); }      // geometry (path lengths, normals)
+SOLAT_HD double rcp_step(double a) { return rcp_n<SOLAT_RCP_STEP_ITERS>(a); } // Newton step sizes
 SOLAT_HD double rsqrt_fast(double a) { return rsqrt_n<SOLAT_RSQRT_POLISH>(a); }
-
-// Snell refraction, same vector law as ray_trace_int.py:20-30 written without cross products:
-//   s2 = mu (s - (N.s) N) - N sqrt(1 - mu^2 (1 - (N.s)^2)),   N pointing against propagation.
-// Returns NaN components on total internal reflection exactly like the reference's np.sqrt.
-SOLAT_HD vec3 refract(const vec3& s, const vec3& N, double mu)
-{
-    double c = -dot(N, s);
-    double k = fma(-mu * mu, fma(-c, c, 1.0), 1.0);
-    double f = fma(mu, c, -sqrt(k));
-    return mk(fma(f, N.x, mu * s.x), fma(f, N.y, mu * s.y), fma(f, N.z, mu * s.z));
-}
-SOLAT_HD vec3 reflect(const vec3& s, const vec3& N)
-{
-    double c = -2.0 * dot(s, N);
-    return mk(fma(c, N.x, s.x), fma(c, N.y, s.y), fma(c, N.z, s.z));
-}
-
-// ------------------------------------------------------------------------------------------
-// Near field: even aspheres of ot_geo.py:81-100,193-212,297-338 and axial offsets :68-71.
-// ------------------------------------------------------------------------------------------
-struct Asphere {
-    double c, K, Kinv;         // 1/R, (1+k)c^2, 1/((1+k)c)
-    double a1, a2, a3, a4;     // sag polynomial in u = r^2
-    double g1, g2, g3, g4;     // slope polynomial 2a1, 4a2, 6a3, 8a4
-    double y0;                 // surface vertex at y = -y0 in the telescope frame
-};
-constexpr Asphere make_asphere(double R, double k, double a1, double a2, double a3, double a4, double y0)
-{
-    return Asphere{1.0 / R, (1.0 + k) * (1.0 / R) * (1.0 / R), 1.0 / ((1.0 + k) * (1.0 / R)),
-                   a1, a2, a3, a4, 2.0 * a1, 4.0 * a2, 6.0 * a3, 8.0 * a4, y0};
-}
-constexpr double LENS1_Y = 975.08;                                             // ot_geo.py:68
-constexpr double LENS2_Y = 592.76;                                             // ot_geo.py:69
-constexpr double LENS3_Y = 180.8 - ((2.5 + 1.513) - (35.16 - 32.19));          // ot_geo.py:70
-constexpr double LYOT_Y = 453.62;                                              // ot_geo.py:71
-// plane offsets: [0] 1B (ot_geo.py:166), [1] 2B (:277), [2] Lyot (:526)
-SOLAT_TABLE double K_NF_PLANE[] = {LENS1_Y, LENS2_Y, LYOT_Y};
-#define Y_1B (K_NF_PLANE[0])
-#define Y_2B (K_NF_PLANE[1])
-#define Y_LYOT (K_NF_PLANE[2])
-// ot_geo.py:85-91, :197-203, :301-307, :323-329 with the offsets of :178, :289, :478, :490
-enum { SURF_1A = 0, SURF_2A = 1, SURF_3A = 2, SURF_3B = 3 };
-struct AsphereF {   // single-precision copy for the coarse first Newton update
-    float c, K, a1, a2, a3, a4, g1, g2, g3, g4;
-};
-constexpr AsphereF make_asphere_f(double R, double k, double a1, double a2, double a3, double a4)
-{
-    return AsphereF{(float)(1.0 / R), (float)((1.0 + k) * (1.0 / R) * (1.0 / R)), (float)a1, (float)a2, (float)a3, (float)a4,
-                    (float)(2.0 * a1), (float)(4.0 * a2), (float)(6.0 * a3), (float)(8.0 * a4)};
-}
-SOLAT_TABLE AsphereF K_ASPHF[4] = {
-    make_asphere_f(-1510.61, 12.0966, -5.876941e-5, 1.769198e-9, -1.310183e-15, 1.994766e-19),
-    make_asphere_f(-871.25, -10.201256, -1.147640e-04, 1.103643e-10, -2.969608e-14, 5.980271e-19),
-    make_asphere_f(6608.30, 414.142695, -2.981594e-06, 3.955202e-10, 3.180727e-16, 0.0),
-    make_asphere_f(604.44, -3.177341, 2.366829e-05, -1.000417e-10, -6.565681e-15, 0.0)};
-SOLAT_TABLE Asphere K_ASPH[4] = {
-    make_asphere(-1510.61, 12.0966, -5.876941e-5, 1.769198e-9, -1.310183e-15, 1.994766e-19, LENS1_Y - 19.32),
-    make_asphere(-871.25, -10.201256, -1.147640e-04, 1.103643e-10, -2.969608e-14, 5.980271e-19, LENS2_Y - 26.47),
-    make_asphere(6608.30, 414.142695, -2.981594e-06, 3.955202e-10, 3.180727e-16, 0.0, LENS3_Y),
-    make_asphere(604.44, -3.177341, 2.366829e-05, -1.000417e-10, -6.565681e-15, 0.0, LENS3_Y + 35.16)};
-
-// Hit of the ray P + t d with asphere S.  On return H is the hit point, N the unit normal in the
-// telescope frame with N.y > 0 (= reference n_hat rotated back), t the ray parameter.
 SOLAT_HD float rsqrt_f(float a)
 {
 #if defined(__CUDA_ARCH__)
@@ -179,97 +118,273 @@ SOLAT_HD float div_f(float a, float b)
     return a / b;
 #endif
 }
+SOLAT_HD float to_f(double a) { return (float)a; }
+SOLAT_HD double to_r(float a, double) { return (double)a; }
+SOLAT_HD bool lt(double a, double b) { return a < b; }
+SOLAT_HD bool gt(double a, double b) { return a > b; }
+SOLAT_HD bool le(double a, double b) { return a <= b; }
+SOLAT_HD bool ge(double a, double b) { return a >= b; }
+SOLAT_HD bool is_nan(double a) { return a != a; }
+SOLAT_HD bool bnot(bool a) { return !a; }
+SOLAT_HD bool band(bool a, bool b) { return a && b; }
+SOLAT_HD bool any(bool a) { return a; }
+SOLAT_HD double select(bool m, double a, double b) { return m ? a : b; }
+SOLAT_HD int flag(bool m, int bit) { return m ? bit : 0; }
+SOLAT_HD int imask(bool m, int v) { return m ? v : 0; }
+
+// ------------------------------------------------------------------------------------------
+// two-ray packs: all operations element-wise
+// ------------------------------------------------------------------------------------------
+struct d2 {
+    double a, b;
+    SOLAT_HD d2() {}
+    SOLAT_HD d2(double s) : a(s), b(s) {}
+    SOLAT_HD d2(double x, double y) : a(x), b(y) {}
+};
+struct f2 {
+    float a, b;
+    SOLAT_HD f2() {}
+    SOLAT_HD f2(float s) : a(s), b(s) {}
+    SOLAT_HD f2(float x, float y) : a(x), b(y) {}
+};
+struct b2 {
+    bool a, b;
+};
+struct i2 {
+    int a, b;
+    SOLAT_HD i2() {}
+    SOLAT_HD i2(int s) : a(s), b(s) {}
+    SOLAT_HD i2(int x, int y) : a(x), b(y) {}
+};
+SOLAT_HD b2 mkb(bool a, bool b) { b2 r; r.a = a; r.b = b; return r; }
+SOLAT_HD d2 operator+(d2 x, d2 y) { return d2(x.a + y.a, x.b + y.b); }
+SOLAT_HD d2 operator-(d2 x, d2 y) { return d2(x.a - y.a, x.b - y.b); }
+SOLAT_HD d2 operator*(d2 x, d2 y) { return d2(x.a * y.a, x.b * y.b); }
+SOLAT_HD d2 operator-(d2 x) { return d2(-x.a, -x.b); }
+SOLAT_HD d2& operator-=(d2& x, d2 y) { x.a -= y.a; x.b -= y.b; return x; }
+SOLAT_HD d2& operator+=(d2& x, d2 y) { x.a += y.a; x.b += y.b; return x; }
+SOLAT_HD d2 fma(d2 x, d2 y, d2 z) { return d2(fma(x.a, y.a, z.a), fma(x.b, y.b, z.b)); }
+SOLAT_HD d2 sqrt(d2 x) { return d2(sqrt(x.a), sqrt(x.b)); }
+SOLAT_HD d2 fabs(d2 x) { return d2(fabs(x.a), fabs(x.b)); }
+SOLAT_HD d2 rcp_fast(d2 x) { return d2(rcp_fast(x.a), rcp_fast(x.b)); }
+SOLAT_HD d2 rcp_step(d2 x) { return d2(rcp_step(x.a), rcp_step(x.b)); }
+SOLAT_HD d2 rsqrt_fast(d2 x) { return d2(rsqrt_fast(x.a), rsqrt_fast(x.b)); }
+SOLAT_HD f2 operator+(f2 x, f2 y) { return f2(x.a + y.a, x.b + y.b); }
+SOLAT_HD f2 operator-(f2 x, f2 y) { return f2(x.a - y.a, x.b - y.b); }
+SOLAT_HD f2 operator*(f2 x, f2 y) { return f2(x.a * y.a, x.b * y.b); }
+SOLAT_HD f2 operator-(f2 x) { return f2(-x.a, -x.b); }
+SOLAT_HD f2 fmaf(f2 x, f2 y, f2 z) { return f2(fmaf(x.a, y.a, z.a), fmaf(x.b, y.b, z.b)); }
+SOLAT_HD f2 rsqrt_f(f2 x) { return f2(rsqrt_f(x.a), rsqrt_f(x.b)); }
+SOLAT_HD f2 div_f(f2 x, f2 y) { return f2(div_f(x.a, y.a), div_f(x.b, y.b)); }
+SOLAT_HD f2 to_f(d2 x) { return f2((float)x.a, (float)x.b); }
+SOLAT_HD d2 to_r(f2 x, d2) { return d2((double)x.a, (double)x.b); }
+SOLAT_HD b2 lt(d2 x, d2 y) { return mkb(x.a < y.a, x.b < y.b); }
+SOLAT_HD b2 gt(d2 x, d2 y) { return mkb(x.a > y.a, x.b > y.b); }
+SOLAT_HD b2 le(d2 x, d2 y) { return mkb(x.a <= y.a, x.b <= y.b); }
+SOLAT_HD b2 ge(d2 x, d2 y) { return mkb(x.a >= y.a, x.b >= y.b); }
+SOLAT_HD b2 is_nan(d2 x) { return mkb(x.a != x.a, x.b != x.b); }
+SOLAT_HD b2 bnot(b2 x) { return mkb(!x.a, !x.b); }
+SOLAT_HD b2 band(b2 x, b2 y) { return mkb(x.a && y.a, x.b && y.b); }
+SOLAT_HD bool any(b2 x) { return x.a || x.b; }
+SOLAT_HD d2 select(b2 m, d2 x, d2 y) { return d2(m.a ? x.a : y.a, m.b ? x.b : y.b); }
+SOLAT_HD i2 flag(b2 m, int bit) { return i2(m.a ? bit : 0, m.b ? bit : 0); }
+SOLAT_HD i2 imask(b2 m, i2 v) { return i2(m.a ? v.a : 0, m.b ? v.b : 0); }
+SOLAT_HD i2 operator|(i2 x, i2 y) { return i2(x.a | y.a, x.b | y.b); }
+SOLAT_HD i2& operator|=(i2& x, i2 y) { x.a |= y.a; x.b |= y.b; return x; }
+
+template <class R> struct Pack;
+template <> struct Pack<double> { using F = float; using I = int; using B = bool; };
+template <> struct Pack<d2> { using F = f2; using I = i2; using B = b2; };
+
+template <class R>
+struct vec3t {
+    R x, y, z;
+};
+using vec3 = vec3t<double>;
+template <class R> SOLAT_HD vec3t<R> mk(R x, R y, R z) { vec3t<R> r; r.x = x; r.y = y; r.z = z; return r; }
+SOLAT_HD vec3 mk(double x, double y, double z) { return mk<double>(x, y, z); }
+template <class R> SOLAT_HD R dot(const vec3t<R>& a, const vec3t<R>& b) { return fma(a.x, b.x, fma(a.y, b.y, a.z * b.z)); }
+template <class R> SOLAT_HD vec3t<R> axpy(const vec3t<R>& p, const vec3t<R>& d, R t)
+{
+    return mk<R>(fma(d.x, t, p.x), fma(d.y, t, p.y), fma(d.z, t, p.z));
+}
+template <class R> SOLAT_HD vec3t<R> neg(const vec3t<R>& a) { return mk<R>(-a.x, -a.y, -a.z); }
+
+// Snell refraction, same vector law as ray_trace_int.py:20-30 written without cross products:
+//   s2 = mu (s - (N.s) N) - N sqrt(1 - mu^2 (1 - (N.s)^2)),   N pointing against propagation.
+// Returns NaN components on total internal reflection exactly like the reference's np.sqrt.
+template <class R>
+SOLAT_HD vec3t<R> refract(const vec3t<R>& s, const vec3t<R>& N, double mu)
+{
+    const R c = -dot(N, s);
+    const R k = fma(R(-mu * mu), fma(-c, c, R(1.0)), R(1.0));
+    const R f = fma(R(mu), c, -sqrt(k));
+    return mk<R>(fma(f, N.x, mu * s.x), fma(f, N.y, mu * s.y), fma(f, N.z, mu * s.z));
+}
+// refraction at a flat whose normal is (0, ny, 0), ny = +-1 pointing against propagation
+template <class R>
+SOLAT_HD vec3t<R> refract_flat(const vec3t<R>& s, double ny, double mu)
+{
+    const R c = -(ny * s.y);
+    const R k = fma(R(-mu * mu), fma(-c, c, R(1.0)), R(1.0));
+    const R f = fma(R(mu), c, -sqrt(k));
+    // the x and z components keep the reference's NaN behaviour: f * 0 is NaN when f is
+    return mk<R>(fma(f, R(0.0), mu * s.x), fma(f, R(ny), mu * s.y), fma(f, R(0.0), mu * s.z));
+}
+template <class R>
+SOLAT_HD vec3t<R> reflect(const vec3t<R>& s, const vec3t<R>& N)
+{
+    const R c = R(-2.0) * dot(s, N);
+    return mk<R>(fma(c, N.x, s.x), fma(c, N.y, s.y), fma(c, N.z, s.z));
+}
+
+// ------------------------------------------------------------------------------------------
+// Near field: even aspheres of ot_geo.py:81-100,193-212,297-338 and axial offsets :68-71.
+// ------------------------------------------------------------------------------------------
+struct Asphere {
+    double c, K, Kinv;         // 1/R, (1+k)c^2, 1/((1+k)c)
+    double a1, a2, a3, a4;     // sag polynomial in u = r^2
+    double g1, g2, g3, g4;     // slope polynomial 2a1, 4a2, 6a3, 8a4
+    double y0;                 // surface vertex at y = -y0 in the telescope frame
+};
+struct AsphereF {              // single-precision copy for the coarse first Newton update
+    float c, K, a1, a2, a3, a4, g1, g2, g3, g4;
+};
+constexpr Asphere make_asphere(double R, double k, double a1, double a2, double a3, double a4, double y0)
+{
+    return Asphere{1.0 / R, (1.0 + k) * (1.0 / R) * (1.0 / R), 1.0 / ((1.0 + k) * (1.0 / R)),
+                   a1, a2, a3, a4, 2.0 * a1, 4.0 * a2, 6.0 * a3, 8.0 * a4, y0};
+}
+constexpr AsphereF make_asphere_f(double R, double k, double a1, double a2, double a3, double a4)
+{
+    return AsphereF{(float)(1.0 / R), (float)((1.0 + k) * (1.0 / R) * (1.0 / R)), (float)a1, (float)a2, (float)a3, (float)a4,
+                    (float)(2.0 * a1), (float)(4.0 * a2), (float)(6.0 * a3), (float)(8.0 * a4)};
+}
+constexpr double LENS1_Y = 975.08;                                             // ot_geo.py:68
+constexpr double LENS2_Y = 592.76;                                             // ot_geo.py:69
+constexpr double LENS3_Y = 180.8 - ((2.5 + 1.513) - (35.16 - 32.19));          // ot_geo.py:70
+constexpr double LYOT_Y = 453.62;                                              // ot_geo.py:71
+// plane offsets: [0] 1B (ot_geo.py:166), [1] 2B (:277), [2] Lyot (:526)
+SOLAT_TABLE double K_NF_PLANE[] = {LENS1_Y, LENS2_Y, LYOT_Y};
+#define Y_1B (K_NF_PLANE[0])
+#define Y_2B (K_NF_PLANE[1])
+#define Y_LYOT (K_NF_PLANE[2])
+// ot_geo.py:85-91, :197-203, :301-307, :323-329 with the offsets of :178, :289, :478, :490
+enum { SURF_1A = 0, SURF_2A = 1, SURF_3A = 2, SURF_3B = 3 };
+SOLAT_TABLE AsphereF K_ASPHF[4] = {
+    make_asphere_f(-1510.61, 12.0966, -5.876941e-5, 1.769198e-9, -1.310183e-15, 1.994766e-19),
+    make_asphere_f(-871.25, -10.201256, -1.147640e-04, 1.103643e-10, -2.969608e-14, 5.980271e-19),
+    make_asphere_f(6608.30, 414.142695, -2.981594e-06, 3.955202e-10, 3.180727e-16, 0.0),
+    make_asphere_f(604.44, -3.177341, 2.366829e-05, -1.000417e-10, -6.565681e-15, 0.0)};
+SOLAT_TABLE Asphere K_ASPH[4] = {
+    make_asphere(-1510.61, 12.0966, -5.876941e-5, 1.769198e-9, -1.310183e-15, 1.994766e-19, LENS1_Y - 19.32),
+    make_asphere(-871.25, -10.201256, -1.147640e-04, 1.103643e-10, -2.969608e-14, 5.980271e-19, LENS2_Y - 26.47),
+    make_asphere(6608.30, 414.142695, -2.981594e-06, 3.955202e-10, 3.180727e-16, 0.0, LENS3_Y),
+    make_asphere(604.44, -3.177341, 2.366829e-05, -1.000417e-10, -6.565681e-15, 0.0, LENS3_Y + 35.16)};
 
 // Newton schedule shared by all curved surfaces (DESIGN.md "Mixed-precision Newton"):
 //   update 1 from the vertex-plane hit is evaluated in FP32 on the otherwise idle FMA pipe -- its own
 //            truncation error (curvature x step^2 ~ 1e-4 .. 1e-2 mm) dwarfs FP32 rounding (~1e-5 mm);
 //   updates 2 and 3 are FP64 and converge quadratically to < 1e-12 mm; the unit normal uses the slope of the
 //            last evaluation (the last step is < 1e-9 mm, i.e. < 1e-13 rad in the normal).
-template <int S>
-SOLAT_HD int asphere_hit(const vec3& P, const vec3& d, double lo, double hi, double& t, vec3& H, vec3& N)
+// Hit of the ray P + t d with asphere S.  On return H is the hit point, N the unit normal in the
+// telescope frame with N.y > 0 (= reference n_hat rotated back), t the ray parameter.
+template <int S, class R>
+SOLAT_HD typename Pack<R>::I asphere_hit(const vec3t<R>& P, const vec3t<R>& d, double lo, double hi, R& t, vec3t<R>& H,
+                                         vec3t<R>& N)
 {
+    using F = typename Pack<R>::F;
+    using I = typename Pack<R>::I;
     const Asphere& A = K_ASPH[S];
-    const double py = P.y + A.y0;
+    const R py = P.y + A.y0;
     t = -py * rcp_step(d.y);
     {   // coarse update in single precision; on the vertex plane the residual is just -sag
-        const AsphereF& F = K_ASPHF[S];
-        const float dxf = (float)d.x, dyf = (float)d.y, dzf = (float)d.z;
-        const float xf = (float)fma(d.x, t, P.x), zf = (float)fma(d.z, t, P.z);
-        const float uf = fmaf(xf, xf, zf * zf);
-        const float rsf = rsqrt_f(fmaf(-F.K, uf, 1.0f));
-        const float sagf = fmaf(div_f(F.c * uf, 1.0f + div_f(1.0f, rsf)), 1.0f, uf * fmaf(uf, fmaf(uf, fmaf(uf, F.a4, F.a3), F.a2), F.a1));
-        const float Gf = fmaf(F.c, rsf, fmaf(uf, fmaf(uf, fmaf(uf, F.g4, F.g3), F.g2), F.g1));
-        const float fpf = fmaf(-Gf, fmaf(xf, dxf, zf * dzf), dyf);
-        t += (double)div_f(sagf, fpf);
+        const AsphereF& Af = K_ASPHF[S];
+        const F dxf = to_f(d.x), dyf = to_f(d.y), dzf = to_f(d.z);
+        const F xf = to_f(fma(d.x, t, P.x)), zf = to_f(fma(d.z, t, P.z));
+        const F uf = fmaf(xf, xf, zf * zf);
+        const F rsf = rsqrt_f(fmaf(F(-Af.K), uf, F(1.0f)));
+        const F sagf = div_f(F(Af.c) * uf, F(1.0f) + div_f(F(1.0f), rsf)) +
+                       uf * fmaf(uf, fmaf(uf, fmaf(uf, F(Af.a4), F(Af.a3)), F(Af.a2)), F(Af.a1));
+        const F Gf = fmaf(F(Af.c), rsf, fmaf(uf, fmaf(uf, fmaf(uf, F(Af.g4), F(Af.g3)), F(Af.g2)), F(Af.g1)));
+        const F fpf = fmaf(-Gf, fmaf(xf, dxf, zf * dzf), dyf);
+        t += to_r(div_f(sagf, fpf), t);
     }
-    double x, z, u, w, rs, G, dt = 0.0;
-#define SOLAT_ASPH_UPDATE()                                                            \
-    {                                                                                  \
-        x = fma(d.x, t, P.x);                                                          \
-        z = fma(d.z, t, P.z);                                                          \
-        u = fma(x, x, z * z);                                                          \
-        w = fma(-A.K, u, 1.0);                                                         \
-        rs = rsqrt_fast(w);                                                            \
-        G = fma(A.c, rs, fma(u, fma(u, fma(u, A.g4, A.g3), A.g2), A.g1));              \
-        const double sag = fma(fma(-w, rs, 1.0), A.Kinv, u * fma(u, fma(u, fma(u, A.a4, A.a3), A.a2), A.a1)); \
-        const double f = fma(d.y, t, py) - sag;                                        \
-        const double fp = fma(-G, fma(x, d.x, z * d.z), d.y);                          \
-        dt = f * rcp_step(fp);                                                         \
-        t -= dt;                                                                       \
+    R x, z, u, w, rs, G, dt = R(0.0);
+#define SOLAT_ASPH_UPDATE()                                                                        \
+    {                                                                                              \
+        x = fma(d.x, t, P.x);                                                                      \
+        z = fma(d.z, t, P.z);                                                                      \
+        u = fma(x, x, z * z);                                                                      \
+        w = fma(R(-A.K), u, R(1.0));                                                               \
+        rs = rsqrt_fast(w);                                                                        \
+        G = fma(R(A.c), rs, fma(u, fma(u, fma(u, R(A.g4), R(A.g3)), R(A.g2)), R(A.g1)));           \
+        const R sag = fma(fma(-w, rs, R(1.0)), R(A.Kinv), u * fma(u, fma(u, fma(u, R(A.a4), R(A.a3)), R(A.a2)), R(A.a1))); \
+        const R f = fma(d.y, t, py) - sag;                                                         \
+        const R fp = fma(-G, fma(x, d.x, z * d.z), d.y);                                           \
+        dt = f * rcp_step(fp);                                                                     \
+        t -= dt;                                                                                   \
     }
     SOLAT_ASPH_UPDATE()
     SOLAT_ASPH_UPDATE()
-    for (int it = 3; fabs(dt) > 1e-9 && it < 10; ++it) SOLAT_ASPH_UPDATE()   // off-nominal rays only
+    for (int it = 3; any(gt(fabs(dt), R(1e-9))) && it < 10; ++it) SOLAT_ASPH_UPDATE()   // off-nominal rays only
 #undef SOLAT_ASPH_UPDATE
-    // hit point: (x, z) of the last evaluation moved by the last (sub-1e-9 mm) step
-    H = mk(fma(d.x, t, P.x), fma(d.y, t, P.y), fma(d.z, t, P.z));
-    const double nn = rsqrt_fast(fma(G * G, u, 1.0));
-    N = mk(-x * G * nn, nn, -z * G * nn);
-    int st = ST_OK;
-    if (!(fabs(dt) <= 1e-9)) st |= (dt != dt) ? ST_NAN : ST_NOCONV;
-    if (!(t >= lo && t <= hi)) st |= ST_BRACKET;
+    H = axpy(P, d, t);
+    const R nn = rsqrt_fast(fma(G * G, u, R(1.0)));
+    N = mk<R>(-x * G * nn, nn, -z * G * nn);
+    I st = imask(bnot(is_nan(dt)), flag(bnot(le(fabs(dt), R(1e-9))), ST_NOCONV)) | flag(is_nan(dt), ST_NAN);
+    st |= flag(bnot(band(ge(t, R(lo)), le(t, R(hi)))), ST_BRACKET);
     return st;
 }
 
-SOLAT_HD int plane_hit(const vec3& P, const vec3& d, double y0, double lo, double hi, double& t, vec3& H)
+template <class R>
+SOLAT_HD typename Pack<R>::I plane_hit(const vec3t<R>& P, const vec3t<R>& d, double y0, double lo, double hi, R& t,
+                                       vec3t<R>& H)
 {
-    t = (-y0 - P.y) * rcp_fast(d.y);
-    H = mk(fma(d.x, t, P.x), fma(d.y, t, P.y), fma(d.z, t, P.z));
-    return (t >= lo && t <= hi) ? ST_OK : ST_BRACKET;
+    t = (R(-y0) - P.y) * rcp_fast(d.y);
+    H = axpy(P, d, t);
+    return flag(bnot(band(ge(t, R(lo)), le(t, R(hi)))), ST_BRACKET);
 }
 
 // -- source_to_lyot_model.trace_rays, ray_trace_int.py:929-1373 --------------------------------
-struct NfSourceRay {
-    vec3 lyot, p2b, p2a, p1b, p1a, d_out;   // hit points; d_out = direction arriving at the Lyot stop
-    double opl;
-    int valid;                              // 0 when vignetted (reference returns a zero column)
-    int status;
+template <class R>
+struct NfSourceRayT {
+    vec3t<R> lyot, p2b, p2a, p1b, p1a, d_out;   // hit points; d_out = direction arriving at the Lyot stop
+    R opl;
+    typename Pack<R>::B valid;                  // false when vignetted (reference returns a zero column)
+    typename Pack<R>::I status;
 };
-SOLAT_HD void nf_source_ray(const vec3& p0, const vec3& d0, double n_si, double n_vac, NfSourceRay& r)
+using NfSourceRay = NfSourceRayT<double>;
+template <class R>
+SOLAT_HD void nf_source_ray(const vec3t<R>& p0, const vec3t<R>& d0, double n_si, double n_vac, NfSourceRayT<R>& r)
 {
+    using I = typename Pack<R>::I;
+    using B = typename Pack<R>::B;
     const double mu_in = n_vac / n_si, mu_out = n_si / n_vac;
-    double t1, t2, t3, t4, t5;
-    vec3 N, d;
-    int st = plane_hit(p0, d0, Y_1B, 5.0, 14000.0, t1, r.p1b);                 // rti:967
-    d = refract(d0, mk(0.0, -1.0, 0.0), mu_in);                                 // rti:992
-    const int st1a = asphere_hit<SURF_1A>(r.p1b, d, 1.0, 900.0, t2, r.p1a, N); // rti:1033
-    r.valid = 0; r.opl = 0.0; r.status = st;
+    R t1, t2, t3, t4, t5;
+    vec3t<R> N, d;
+    I st = plane_hit(p0, d0, Y_1B, 5.0, 14000.0, t1, r.p1b);                   // rti:967
+    d = refract_flat(d0, -1.0, mu_in);                                          // rti:992
+    const I st1a = asphere_hit<SURF_1A>(r.p1b, d, 1.0, 900.0, t2, r.p1a, N);   // rti:1033
     // rti:1086 (>= 196 -> zero column).  A NaN radius means the iterate left the domain of the conic
     // (r > 417 mm), where the reference's root function substitutes sag = 0 and then vignettes too.
-    if (!(sqrt(fma(r.p1a.x, r.p1a.x, r.p1a.z * r.p1a.z)) < 196.0)) return;
-    st |= st1a;
-    d = refract(d, mk(-N.x, -N.y, -N.z), mu_out);                               // rti:1058
-    st |= plane_hit(r.p1a, d, Y_2B, 5.0, 600.0, t3, r.p2b);                    // rti:1130
-    r.status = st;
-    if (!(sqrt(fma(r.p2b.x, r.p2b.x, r.p2b.z * r.p2b.z)) < 176.0)) return;     // rti:1177
-    d = refract(d, mk(0.0, -1.0, 0.0), mu_in);                                  // rti:1154 (-n_hat)
-    st |= asphere_hit<SURF_2A>(r.p2b, d, 0.0, 100.0, t4, r.p2a, N);            // rti:1228
-    d = refract(d, mk(-N.x, -N.y, -N.z), mu_out);                               // rti:1254
-    st |= plane_hit(r.p2a, d, Y_LYOT, 10.0, 900.0, t5, r.lyot);                // rti:1295
+    B alive = lt(sqrt(fma(r.p1a.x, r.p1a.x, r.p1a.z * r.p1a.z)), R(196.0));
+    r.valid = alive; r.opl = R(0.0); r.status = st;
+    if (!any(alive)) return;
+    st |= imask(alive, st1a);
+    d = refract(d, neg(N), mu_out);                                             // rti:1058
+    st |= imask(alive, plane_hit(r.p1a, d, Y_2B, 5.0, 600.0, t3, r.p2b));      // rti:1130
+    alive = band(alive, lt(sqrt(fma(r.p2b.x, r.p2b.x, r.p2b.z * r.p2b.z)), R(176.0)));   // rti:1177
+    r.valid = alive; r.status = st;
+    if (!any(alive)) return;
+    d = refract_flat(d, -1.0, mu_in);                                           // rti:1154 (-n_hat)
+    st |= imask(alive, asphere_hit<SURF_2A>(r.p2b, d, 0.0, 100.0, t4, r.p2a, N));   // rti:1228
+    d = refract(d, neg(N), mu_out);                                             // rti:1254
+    st |= imask(alive, plane_hit(r.p2a, d, Y_LYOT, 10.0, 900.0, t5, r.lyot));  // rti:1295
     r.d_out = d;
-    r.opl = (t1) + (t2 * n_si) + (t3) + (t4 * n_si) + t5;                       // rti:1341-1343
-    if (r.opl != r.opl) st |= ST_NAN;
-    r.valid = 1;
+    const R opl = (t1) + (t2 * n_si) + (t3) + (t4 * n_si) + t5;                 // rti:1341-1343
+    st |= flag(band(alive, is_nan(opl)), ST_NAN);
+    r.opl = select(alive, opl, R(0.0));
     r.status = st;
 }
 
@@ -319,12 +434,12 @@ SOLAT_HD void nf_toy_ray(const vec3& p0, const vec3& d0, double y_ap, double n_s
     st |= asphere_hit<SURF_2A>(r.p3b, d, 10.0, 2000.0, t, r.p2a, N);           // rti:243
     d = refract(d, N, mu_in);                                                   // rti:268
     st |= plane_hit(r.p2a, d, Y_2B, 5.0, 400.0, t, r.p2b);                     // rti:308
-    d = refract(d, mk(0.0, 1.0, 0.0), mu_out);                                  // rti:332
+    d = refract_flat(d, 1.0, mu_out);                                           // rti:332
     st |= asphere_hit<SURF_1A>(r.p2b, d, 5.0, 500.0, t, r.p1a, N);             // rti:373
     d = refract(d, N, mu_in);                                                   // rti:398
     st |= plane_hit(r.p1a, d, Y_1B, 5.0, 200.0, t, r.p1b);                     // rti:440
     // rti:465: snell(n_si, n_vac, N_hat, -tan) with the 1B normal (tele frame (0,-1,0))
-    d = refract(mk(-d.x, -d.y, -d.z), mk(0.0, -1.0, 0.0), mu_out);
+    d = refract_flat(neg(d), -1.0, mu_out);
     r.d_out = d;
     double d_ap = fabs((y_ap - r.p1b.y) / d.y);                                 // rti:489
     r.opl = dist3(r.p3a, p0) + dist3(r.p3b, r.p3a) * n_si + dist3(r.p2a, r.p3b) + dist3(r.p2b, r.p2a) * n_si +
@@ -341,7 +456,6 @@ SOLAT_HD void nf_toy_ray(const vec3& p0, const vec3& d0, double y_ap, double n_s
 constexpr double FF_RN = 3000.0;
 // [0] 1/R_N, [1] 2/R_N, [2] y_cent_m1 (saf:19), [3] aperture radius^2 (saf:378), [4] aperture plane z (latrt_geo.py:244)
 SOLAT_TABLE double K_FF[] = {1.0 / 3000.0, 2.0 / 3000.0, -7201.003729431267, 3e3 * 3e3, 4000.0};
-#define FF_INV_RN (K_FF[0])
 #define Y_CENT_M1 (K_FF[2])
 
 // Horner tables: rows i = 0, 2, 4, 6 of a1 / a2 (latrt_geo.py:55-61, :63-71) as polynomials in v = y/R,
@@ -353,8 +467,7 @@ SOLAT_TABLE double K_M1[] = {
     /* P6 [13]       */ 0.0394559,
     /* dP0/v [14..18]*/ 2 * -57.74022, 3 * 1.5373825, 4 * 1.154294, 5 * -0.441762, 6 * 0.0906601,
     /* dP2 [19..22]  */ 1.8691899, 2 * 2.8859421, 3 * -1.026471, 4 * 0.2610568,
-    /* dP4 [23..24]  */ -0.603195, 2 * 0.2177414,
-    /* 2P4, 3P6 scale handled in code */};
+    /* dP4 [23..24]  */ -0.603195, 2 * 0.2177414};
 SOLAT_TABLE double K_M2[] = {
     /* P0/v^2 [0..5] */ 103.90461, 6.6513025, 2.8405781, -0.7819705, -0.0400483, 0.0896645,
     /* P2 [6..11]    */ 115.44758, 7.3024355, 5.7640389, -1.578144, -0.0354326, 0.2781226,
@@ -364,7 +477,6 @@ SOLAT_TABLE double K_M2[] = {
     /* dP2 [24..28]  */ 7.3024355, 2 * 5.7640389, 3 * -1.578144, 4 * -0.0354326, 5 * 0.2781226,
     /* dP4 [29..31]  */ -0.8104051, 2 * -0.0185283, 3 * 0.2626023,
     /* dP6 [32]      */ 0.0709672};
-
 // single-precision copies (same layout) for the coarse first Newton update
 SOLAT_TABLE float K_M1F[] = {
     -57.74022f, 1.5373825f, 1.154294f, -0.441762f, 0.0906601f, -72.17349f, 1.8691899f, 2.8859421f, -1.026471f, 0.2610568f,
@@ -379,66 +491,62 @@ SOLAT_TABLE float K_M2F[] = {
     7.3024355f, 2 * 5.7640389f, 3 * -1.578144f, 4 * -0.0354326f, 5 * 0.2781226f,
     -0.8104051f, 2 * -0.0185283f, 3 * 0.2626023f, 0.0709672f};
 
-// The Horner bodies are written once for both precisions (T = double with fma, T = float with fmaf).
-#define SOLAT_M1_BODY(T, FMA, K, INV_RN, TWO_INV_RN)                                                     \
-    const T u = x * INV_RN, v = y * INV_RN, w = u * u;                                                   \
-    const T p0 = v * v * FMA(v, FMA(v, FMA(v, FMA(v, K[4], K[3]), K[2]), K[1]), K[0]);                   \
-    const T p2 = FMA(v, FMA(v, FMA(v, FMA(v, K[9], K[8]), K[7]), K[6]), K[5]);                           \
-    const T p4 = FMA(v, FMA(v, K[12], K[11]), K[10]);                                                    \
-    const T p6 = K[13];                                                                                  \
-    z = FMA(w, FMA(w, FMA(w, p6, p4), p2), p0);                                                          \
-    const T q0 = v * FMA(v, FMA(v, FMA(v, FMA(v, K[18], K[17]), K[16]), K[15]), K[14]);                  \
-    const T q2 = FMA(v, FMA(v, FMA(v, K[22], K[21]), K[20]), K[19]);                                     \
-    const T q4 = FMA(v, K[24], K[23]);                                                                   \
-    zy = FMA(w, FMA(w, q4, q2), q0) * INV_RN;                                                            \
-    zx = TWO_INV_RN * u * FMA(w, FMA(w, (T)3 * p6, (T)2 * p4), p2);
-#define SOLAT_M2_BODY(T, FMA, K, INV_RN, TWO_INV_RN)                                                     \
-    const T u = x * INV_RN, v = y * INV_RN, w = u * u;                                                   \
-    const T p0 = v * v * FMA(v, FMA(v, FMA(v, FMA(v, FMA(v, K[5], K[4]), K[3]), K[2]), K[1]), K[0]);     \
-    const T p2 = FMA(v, FMA(v, FMA(v, FMA(v, FMA(v, K[11], K[10]), K[9]), K[8]), K[7]), K[6]);           \
-    const T p4 = FMA(v, FMA(v, FMA(v, K[15], K[14]), K[13]), K[12]);                                     \
-    const T p6 = FMA(v, K[17], K[16]);                                                                   \
-    z = FMA(w, FMA(w, FMA(w, p6, p4), p2), p0);                                                          \
-    const T q0 = v * FMA(v, FMA(v, FMA(v, FMA(v, FMA(v, K[23], K[22]), K[21]), K[20]), K[19]), K[18]);   \
-    const T q2 = FMA(v, FMA(v, FMA(v, FMA(v, K[28], K[27]), K[26]), K[25]), K[24]);                      \
-    const T q4 = FMA(v, FMA(v, K[31], K[30]), K[29]);                                                    \
-    const T q6 = K[32];                                                                                  \
-    zy = FMA(w, FMA(w, FMA(w, q6, q4), q2), q0) * INV_RN;                                                \
-    zx = TWO_INV_RN * u * FMA(w, FMA(w, (T)3 * p6, (T)2 * p4), p2);
+// The Horner bodies are written once for both precisions (T = R with fma, T = F with fmaf).
+#define SOLAT_M1_BODY(T, FMA, K, INV_RN, TWO_INV_RN)                                                             \
+    const T u = x * T(INV_RN), v = y * T(INV_RN), w = u * u;                                                     \
+    const T p0 = v * v * FMA(v, FMA(v, FMA(v, FMA(v, T(K[4]), T(K[3])), T(K[2])), T(K[1])), T(K[0]));            \
+    const T p2 = FMA(v, FMA(v, FMA(v, FMA(v, T(K[9]), T(K[8])), T(K[7])), T(K[6])), T(K[5]));                    \
+    const T p4 = FMA(v, FMA(v, T(K[12]), T(K[11])), T(K[10]));                                                   \
+    const T p6 = T(K[13]);                                                                                       \
+    z = FMA(w, FMA(w, FMA(w, p6, p4), p2), p0);                                                                  \
+    const T q0 = v * FMA(v, FMA(v, FMA(v, FMA(v, T(K[18]), T(K[17])), T(K[16])), T(K[15])), T(K[14]));           \
+    const T q2 = FMA(v, FMA(v, FMA(v, T(K[22]), T(K[21])), T(K[20])), T(K[19]));                                 \
+    const T q4 = FMA(v, T(K[24]), T(K[23]));                                                                     \
+    zy = FMA(w, FMA(w, q4, q2), q0) * T(INV_RN);                                                                 \
+    zx = T(TWO_INV_RN) * u * FMA(w, FMA(w, p6 + p6 + p6, p4 + p4), p2);
+#define SOLAT_M2_BODY(T, FMA, K, INV_RN, TWO_INV_RN)                                                             \
+    const T u = x * T(INV_RN), v = y * T(INV_RN), w = u * u;                                                     \
+    const T p0 = v * v * FMA(v, FMA(v, FMA(v, FMA(v, FMA(v, T(K[5]), T(K[4])), T(K[3])), T(K[2])), T(K[1])), T(K[0])); \
+    const T p2 = FMA(v, FMA(v, FMA(v, FMA(v, FMA(v, T(K[11]), T(K[10])), T(K[9])), T(K[8])), T(K[7])), T(K[6])); \
+    const T p4 = FMA(v, FMA(v, FMA(v, T(K[15]), T(K[14])), T(K[13])), T(K[12]));                                 \
+    const T p6 = FMA(v, T(K[17]), T(K[16]));                                                                     \
+    z = FMA(w, FMA(w, FMA(w, p6, p4), p2), p0);                                                                  \
+    const T q0 = v * FMA(v, FMA(v, FMA(v, FMA(v, FMA(v, T(K[23]), T(K[22])), T(K[21])), T(K[20])), T(K[19])), T(K[18])); \
+    const T q2 = FMA(v, FMA(v, FMA(v, FMA(v, T(K[28]), T(K[27])), T(K[26])), T(K[25])), T(K[24]));               \
+    const T q4 = FMA(v, FMA(v, T(K[31]), T(K[30])), T(K[29]));                                                   \
+    const T q6 = T(K[32]);                                                                                       \
+    zy = FMA(w, FMA(w, FMA(w, q6, q4), q2), q0) * T(INV_RN);                                                     \
+    zx = T(TWO_INV_RN) * u * FMA(w, FMA(w, p6 + p6 + p6, p4 + p4), p2);
 
-SOLAT_HD void m1_sag_f(float x, float y, float& z, float& zx, float& zy)
+// z and its partials wrt the LOCAL coordinates x, y (mm); M = 1 primary, 2 secondary
+template <int M, class R>
+SOLAT_HD void mirror_sag(R x, R y, R& z, R& zx, R& zy)
 {
-    SOLAT_M1_BODY(float, fmaf, K_M1F, (1.0f / 3000.0f), (2.0f / 3000.0f))
+    if (M == 1) { SOLAT_M1_BODY(R, fma, K_M1, K_FF[0], K_FF[1]) } else { SOLAT_M2_BODY(R, fma, K_M2, K_FF[0], K_FF[1]) }
 }
-SOLAT_HD void m2_sag_f(float x, float y, float& z, float& zx, float& zy)
+template <int M, class F>
+SOLAT_HD void mirror_sag_f(F x, F y, F& z, F& zx, F& zy)
 {
-    SOLAT_M2_BODY(float, fmaf, K_M2F, (1.0f / 3000.0f), (2.0f / 3000.0f))
-}
-
-// z and its partials wrt the LOCAL coordinates x, y (mm)
-SOLAT_HD void m1_sag(double x, double y, double& z, double& zx, double& zy)
-{
-    SOLAT_M1_BODY(double, fma, K_M1, K_FF[0], K_FF[1])
-}
-SOLAT_HD void m2_sag(double x, double y, double& z, double& zx, double& zy)
-{
-    SOLAT_M2_BODY(double, fma, K_M2, K_FF[0], K_FF[1])
+    if (M == 1) { SOLAT_M1_BODY(F, fmaf, K_M1F, (1.0f / 3000.0f), (2.0f / 3000.0f)) }
+    else { SOLAT_M2_BODY(F, fmaf, K_M2F, (1.0f / 3000.0f), (2.0f / 3000.0f)) }
 }
 
 struct Affine {          // y = A x + b, row-major A
     double a[9];
     double b[3];
 };
-SOLAT_HD vec3 apply(const Affine& T, const vec3& p)
+template <class R>
+SOLAT_HD vec3t<R> apply(const Affine& T, const vec3t<R>& p)
 {
-    return mk(fma(T.a[0], p.x, fma(T.a[1], p.y, fma(T.a[2], p.z, T.b[0]))),
-              fma(T.a[3], p.x, fma(T.a[4], p.y, fma(T.a[5], p.z, T.b[1]))),
-              fma(T.a[6], p.x, fma(T.a[7], p.y, fma(T.a[8], p.z, T.b[2]))));
+    return mk<R>(fma(R(T.a[0]), p.x, fma(R(T.a[1]), p.y, fma(R(T.a[2]), p.z, R(T.b[0])))),
+                 fma(R(T.a[3]), p.x, fma(R(T.a[4]), p.y, fma(R(T.a[5]), p.z, R(T.b[1])))),
+                 fma(R(T.a[6]), p.x, fma(R(T.a[7]), p.y, fma(R(T.a[8]), p.z, R(T.b[2])))));
 }
-SOLAT_HD vec3 apply_lin(const double* a, const vec3& p)
+template <class R>
+SOLAT_HD vec3t<R> apply_lin(const double* a, const vec3t<R>& p)
 {
-    return mk(fma(a[0], p.x, fma(a[1], p.y, a[2] * p.z)), fma(a[3], p.x, fma(a[4], p.y, a[5] * p.z)),
-              fma(a[6], p.x, fma(a[7], p.y, a[8] * p.z)));
+    return mk<R>(fma(R(a[0]), p.x, fma(R(a[1]), p.y, R(a[2]) * p.z)), fma(R(a[3]), p.x, fma(R(a[4]), p.y, R(a[5]) * p.z)),
+                 fma(R(a[6]), p.x, fma(R(a[7]), p.y, R(a[8]) * p.z)));
 }
 
 // Telescope geometry that does not depend on the pixel (latrt_geo.py:7-49, ff_sim.py:72-79)
@@ -504,25 +612,14 @@ SOLAT_HD void ff_build_frames(const FfGeom& g, double el, double az, FfFrames& f
     mat3_mul(Rp, F2t, f.b2);
     f.foc_row[0] = Rp[3]; f.foc_row[1] = Rp[4]; f.foc_row[2] = Rp[5];
     f.foc_off = C[1] - (Rp[3] * C[0] + Rp[4] * C[1] + Rp[5] * C[2]);
-    // focal centre: mean over the r<3600 part of row 50 / column 50 of a 100x100 grid on +-4000 mm
-    // pushed through foc_into_tele(el, az) (latrt_geo.py:248-258).  The grid is symmetric, so the
-    // means are taken point by point exactly as the reference does.
-    const double step = 8000.0 / 99.0, a50 = -4000.0 + 50 * step;
-    double sx = 0, sy = 0, sz = 0;
-    int cnt = 0;
-    for (int i = 0; i < 100; i++) {
-        const double ai = (i == 99) ? 4000.0 : -4000.0 + i * step;
-        if (sqrt(ai * ai + a50 * a50) < 3600.0) {
-            // row 50: (X, Y) = (ai, a50) -> focal->tele (x, 0, Y); column 50: (a50, ai)
-            const double rx_ = ai - C[0], ry_ = 0.0 - C[1], rz_ = a50 - C[2];
-            sx += Rp[0] * rx_ + Rp[1] * ry_ + Rp[2] * rz_ + C[0];
-            const double cx_ = a50 - C[0], cy_ = 0.0 - C[1], cz_ = ai - C[2];
-            sy += Rp[3] * cx_ + Rp[4] * cy_ + Rp[5] * cz_ + C[1];
-            sz += Rp[6] * cx_ + Rp[7] * cy_ + Rp[8] * cz_ + C[2];
-            cnt++;
-        }
-    }
-    f.centre[0] = sx / cnt; f.centre[1] = sy / cnt; f.centre[2] = sz / cnt;
+    // Focal centre (saf:323-339): means over the r < 3600 mm part of row 50 / column 50 of a 100x100 grid on
+    // +-4000 mm pushed through foc_into_tele(el, az) (latrt_geo.py:248-258).  The grid is symmetric about 0, so
+    // the masked mean of the running coordinate is 0 (to the reference's own 1e-12 mm rounding) and the means
+    // are the images of (0, 0, a50) [x component] and (a50, 0, 0) [y, z components], a50 = -4000 + 50*8000/99.
+    const double a50 = -4000.0 + 50.0 * (8000.0 / 99.0);
+    f.centre[0] = Rp[0] * (0.0 - C[0]) + Rp[1] * (0.0 - C[1]) + Rp[2] * (a50 - C[2]) + C[0];
+    f.centre[1] = Rp[3] * (a50 - C[0]) + Rp[4] * (0.0 - C[1]) + Rp[5] * (0.0 - C[2]) + C[1];
+    f.centre[2] = Rp[6] * (a50 - C[0]) + Rp[7] * (0.0 - C[1]) + Rp[8] * (0.0 - C[2]) + C[2];
 }
 
 // Panel-error polynomial of one panel (rows 2..9 of the reference's panel model, saf:667-674)
@@ -532,101 +629,105 @@ struct PanelErr {
 
 // Newton hit of P + t D (mirror-local frame) with mirror M (1 or 2), starting on the local z=0 plane.
 // One FP32 coarse update, then two FP64 updates; the gradient of the last evaluation is also used for
-// the normal (the last step is ~1e-11 mm, so the normal is exact to 1e-16).  PE: optional panel
-// error, evaluated along its own affine image (pe + t de) of the ray (saf:676-703, :820-852).
-template <int M, bool PANEL>
-SOLAT_HD int mirror_hit(const vec3& P, const vec3& D, double lo, double hi, const PanelErr* pe, const vec3& pE,
-                        const vec3& dE, double& t, vec3& H, vec3& N)
+// the normal (the last step is ~1e-11 mm, so the normal is exact to 1e-16).  PE (scalar rays only): optional
+// panel error, evaluated along its own affine image (pe + t de) of the ray (saf:676-703, :820-852).
+template <int M, bool PANEL, class R>
+SOLAT_HD typename Pack<R>::I mirror_hit(const vec3t<R>& P, const vec3t<R>& D, double lo, double hi, const PanelErr* pe,
+                                        const vec3t<R>& pE, const vec3t<R>& dE, R& t, vec3t<R>& H, vec3t<R>& N)
 {
+    using F = typename Pack<R>::F;
+    using I = typename Pack<R>::I;
     t = -P.z * rcp_step(D.z);
     {   // coarse update in single precision (see asphere_hit); on the local z = 0 plane the residual is -z
-        const float xf = (float)fma(D.x, t, P.x), yf = (float)fma(D.y, t, P.y);
-        float zf, zxf, zyf;
-        if (M == 1) m1_sag_f(xf, yf, zf, zxf, zyf); else m2_sag_f(xf, yf, zf, zxf, zyf);
-        const float fpf = (float)D.z - fmaf(zxf, (float)D.x, zyf * (float)D.y);
-        t += (double)div_f(zf, fpf);
+        const F xf = to_f(fma(D.x, t, P.x)), yf = to_f(fma(D.y, t, P.y));
+        F zf, zxf, zyf;
+        mirror_sag_f<M, F>(xf, yf, zf, zxf, zyf);
+        const F fpf = to_f(D.z) - fmaf(zxf, to_f(D.x), zyf * to_f(D.y));
+        t += to_r(div_f(zf, fpf), t);
     }
-    double dt = 0.0, z, zx, zy;
+    R dt = R(0.0), z, zx, zy;
     auto update = [&]() {
-        const double x = fma(D.x, t, P.x), y = fma(D.y, t, P.y);
-        if (M == 1) m1_sag(x, y, z, zx, zy); else m2_sag(x, y, z, zx, zy);
-        double f = fma(D.z, t, P.z) - z;
-        double fp = D.z - fma(zx, D.x, zy * D.y);
+        const R x = fma(D.x, t, P.x), y = fma(D.y, t, P.y);
+        mirror_sag<M, R>(x, y, z, zx, zy);
+        R f = fma(D.z, t, P.z) - z;
+        R fp = D.z - fma(zx, D.x, zy * D.y);
         if (PANEL) {
             // xpc = -x_e - x0, ypc = y_e - y0 with (x_e, y_e) the error-frame image of the point
-            const double xe = fma(dE.x, t, pE.x), ye = fma(dE.y, t, pE.y);
-            const double xpc = -xe - pe->x0, ypc = ye - pe->y0;
-            f -= pe->a + pe->b * xpc + pe->c * ypc + pe->d * (xpc * xpc + ypc * ypc) + pe->e * (xpc * ypc);
-            fp -= -dE.x * (pe->b + 2.0 * pe->d * xpc + pe->e * ypc) + dE.y * (pe->c + 2.0 * pe->d * ypc + pe->e * xpc);
+            const R xe = fma(dE.x, t, pE.x), ye = fma(dE.y, t, pE.y);
+            const R xpc = -xe - R(pe->x0), ypc = ye - R(pe->y0);
+            f -= R(pe->a) + R(pe->b) * xpc + R(pe->c) * ypc + R(pe->d) * (xpc * xpc + ypc * ypc) + R(pe->e) * (xpc * ypc);
+            fp -= -dE.x * (R(pe->b) + R(2.0 * pe->d) * xpc + R(pe->e) * ypc) + dE.y * (R(pe->c) + R(2.0 * pe->d) * ypc + R(pe->e) * xpc);
         }
         dt = f * rcp_step(fp);
         t -= dt;
     };
     update();
     update();                                             // ~1e-11 mm on nominal rays
-    for (int it = 3; fabs(dt) > 1e-8 && it < 12; ++it) update();   // off-nominal rays only
-    H = mk(fma(D.x, t, P.x), fma(D.y, t, P.y), fma(D.z, t, P.z));
-    if (PANEL) {   // reference normal = ideal-mirror gradient at the final point (saf:718-720, :869-871)
-        if (M == 1) m1_sag(H.x, H.y, z, zx, zy); else m2_sag(H.x, H.y, z, zx, zy);
-    }
-    const double nn = rsqrt_fast(fma(zx, zx, fma(zy, zy, 1.0)));
-    N = mk(-zx * nn, -zy * nn, nn);
-    int st = ST_OK;
-    if (!(fabs(dt) <= 1e-8)) st |= (dt != dt) ? ST_NAN : ST_NOCONV;
-    if (!(t >= lo && t <= hi)) st |= ST_BRACKET;
+    for (int it = 3; any(gt(fabs(dt), R(1e-8))) && it < 12; ++it) update();   // off-nominal rays only
+    H = axpy(P, D, t);
+    if (PANEL) mirror_sag<M, R>(H.x, H.y, z, zx, zy);   // reference normal = ideal-mirror gradient (saf:718-720, :869-871)
+    const R nn = rsqrt_fast(fma(zx, zx, fma(zy, zy, R(1.0))));
+    N = mk<R>(-zx * nn, -zy * nn, nn);
+    I st = imask(bnot(is_nan(dt)), flag(bnot(le(fabs(dt), R(1e-8))), ST_NOCONV)) | flag(is_nan(dt), ST_NAN);
+    st |= flag(bnot(band(ge(t, R(lo)), le(t, R(hi)))), ST_BRACKET);
     return st;
 }
 
 // cheap first stage of every far-field ray: aperture-plane hit and the 3 m radius test
-// (saf:359-379 == :644-665).  Returns 1 if the ray continues.
-SOLAT_HD int ff_aperture(const FfGeom& g, const FfFrames& f, const vec3& d, double& t_ap, vec3& Pa)
+// (saf:359-379 == :644-665).  Returns the lanes that continue.
+template <class R>
+SOLAT_HD typename Pack<R>::B ff_aperture(const FfGeom& g, const FfFrames& f, const vec3t<R>& d, R& t_ap, vec3t<R>& Pa)
 {
-    t_ap = f.ap_num * rcp_fast(dot(mk(f.ap_row[0], f.ap_row[1], f.ap_row[2]), d));
-    Pa = mk(fma(d.x, t_ap, g.src[0]), fma(d.y, t_ap, g.src[1]), fma(d.z, t_ap, g.src[2]));
-    const double dy = Pa.y - Y_CENT_M1;
-    return !(fma(Pa.x, Pa.x, dy * dy) > K_FF[3]);
+    t_ap = R(f.ap_num) * rcp_fast(fma(R(f.ap_row[0]), d.x, fma(R(f.ap_row[1]), d.y, R(f.ap_row[2]) * d.z)));
+    Pa = mk<R>(fma(d.x, t_ap, R(g.src[0])), fma(d.y, t_ap, R(g.src[1])), fma(d.z, t_ap, R(g.src[2])));
+    const R dy = Pa.y - R(Y_CENT_M1);
+    return bnot(gt(fma(Pa.x, Pa.x, dy * dy), R(K_FF[3])));
 }
 
-struct FfRay {
-    vec3 m1, m2, n2, foc, d_out;   // telescope-frame M1/M2 hits, M2 normal, focal hit, outgoing direction
-    double opl;
-    int status;
+template <class R>
+struct FfRayT {
+    vec3t<R> m1, m2, n2, foc, d_out;   // telescope-frame M1/M2 hits, M2 normal, focal hit, outgoing direction
+    R opl;
+    typename Pack<R>::I status;
 };
+using FfRay = FfRayT<double>;
 // Remainder of the ray after ff_aperture.  STAGE1 = ray_mirror_pts brackets (saf:396,490), no focal
 // plane; otherwise aperature_fields_from_panel_model brackets (saf:706,855,962).
-template <bool STAGE1, bool PANEL>
-SOLAT_HD void ff_ray_trace(const FfFrames& f, const vec3& d, double t_ap, const vec3& Pa, double foc_y,
-                           const PanelErr* pe1, const PanelErr* pe2, const double* t2e_a, FfRay& r)
+template <bool STAGE1, bool PANEL, class R>
+SOLAT_HD void ff_ray_trace(const FfFrames& f, const vec3t<R>& d, R t_ap, const vec3t<R>& Pa, double foc_y,
+                           const PanelErr* pe1, const PanelErr* pe2, const double* t2e_a, FfRayT<R>& r)
 {
-    double t1, t2;
-    vec3 H, N;
-    const vec3 none = mk(0, 0, 0);
+    using I = typename Pack<R>::I;
+    R t1, t2;
+    vec3t<R> H, N;
+    const vec3t<R> none = mk<R>(R(0.0), R(0.0), R(0.0));
     // M1
-    vec3 p1 = apply(f.t1, Pa), d1 = apply_lin(f.t1.a, d);
-    int st = mirror_hit<1, PANEL>(p1, d1, 0.0, STAGE1 ? 5e4 : 1e4, pe1, p1, d1, t1, H, N);
+    const vec3t<R> p1 = apply(f.t1, Pa), d1 = apply_lin(f.t1.a, d);
+    I st = mirror_hit<1, PANEL, R>(p1, d1, 0.0, STAGE1 ? 5e4 : 1e4, pe1, p1, d1, t1, H, N);
     r.m1 = axpy(Pa, d, t1);
-    vec3 dt2 = apply_lin(f.b1, reflect(d1, N));                                // saf:208-257
+    const vec3t<R> dt2 = apply_lin(f.b1, reflect(d1, N));                       // saf:208-257
     // M2
-    vec3 p2 = apply(f.t2, r.m1), d2 = apply_lin(f.t2.a, dt2);
-    vec3 pE = none, dE = none;
+    const vec3t<R> p2 = apply(f.t2, r.m1), d2 = apply_lin(f.t2.a, dt2);
+    vec3t<R> pE = none, dE = none;
     if (PANEL) {   // error coordinates use the z-stretched point, saf:828-832
-        Affine te; for (int i = 0; i < 9; i++) te.a[i] = t2e_a[i];
+        Affine te;
+        for (int i = 0; i < 9; i++) te.a[i] = t2e_a[i];
         te.b[0] = f.t2.b[0]; te.b[1] = f.t2.b[1]; te.b[2] = f.t2.b[2];
         pE = apply(te, r.m1); dE = apply_lin(te.a, dt2);
     }
-    st |= mirror_hit<2, PANEL>(p2, d2, STAGE1 ? 0.0 : 1e3, STAGE1 ? 20e3 : 13e3, pe2, pE, dE, t2, H, N);
+    st |= mirror_hit<2, PANEL, R>(p2, d2, STAGE1 ? 0.0 : 1e3, STAGE1 ? 20e3 : 13e3, pe2, pE, dE, t2, H, N);
     r.m2 = axpy(r.m1, dt2, t2);
-    r.opl = 0.0;
+    r.opl = R(0.0);
     if (!STAGE1) {
         r.n2 = apply_lin(f.b2, N);
-        vec3 dt3 = apply_lin(f.b2, reflect(d2, N));                            // saf:883-930
-        const vec3 fr = mk(f.foc_row[0], f.foc_row[1], f.foc_row[2]);
-        const double tf = (foc_y - (dot(fr, r.m2) + f.foc_off)) * rcp_fast(dot(fr, dt3));   // saf:947-962
-        if (!(tf >= 1e3 && tf <= 15e3)) st |= ST_BRACKET;
+        const vec3t<R> dt3 = apply_lin(f.b2, reflect(d2, N));                   // saf:883-930
+        const vec3t<R> fr = mk<R>(R(f.foc_row[0]), R(f.foc_row[1]), R(f.foc_row[2]));
+        const R tf = (R(foc_y) - (dot(fr, r.m2) + R(f.foc_off))) * rcp_fast(dot(fr, dt3));   // saf:947-962
+        st |= flag(bnot(band(ge(tf, R(1e3)), le(tf, R(15e3)))), ST_BRACKET);
         r.foc = axpy(r.m2, dt3, tf);
         r.d_out = dt3;
         r.opl = ((t_ap + t1) + t2) + tf;                                        // saf:970
-        if (r.opl != r.opl) st |= ST_NAN;
+        st |= flag(is_nan(r.opl), ST_NAN);
     }
     r.status = st;
 }
@@ -673,7 +774,7 @@ SOLAT_HD void pack_nf_source_rows(const NfSourceRay& r, const vec3& p0, double n
 {
     if (!r.valid) { for (int i = 0; i < 26; i++) rows[i] = 0.0; return; }     // rti:1086-1114
     // rti:1305-1339: Snell (si -> vac) applied to the vector pointing from the Lyot hit back to 2A
-    const vec3 og = refract(mk(-r.d_out.x, -r.d_out.y, -r.d_out.z), mk(0.0, 1.0, 0.0), n_si / n_vac);
+    const vec3 og = refract_flat(neg(r.d_out), 1.0, n_si / n_vac);
     const double v[26] = {r.lyot.x, r.lyot.y, r.lyot.z, r.opl, 1.0, 0.0, 1.0, 0.0, og.x, og.y, og.z,
                           r.p2b.x, r.p2b.y, r.p2b.z, r.p2a.x, r.p2a.y, r.p2a.z, r.p1b.x, r.p1b.y, r.p1b.z,
                           r.p1a.x, r.p1a.y, r.p1a.z, p0.x, p0.y, p0.z};
@@ -709,15 +810,59 @@ SOLAT_HD void pack_ff_rows(const FfRay& r, const double* centre, double* rows)
     for (int i = 0; i < 17; i++) rows[i] = v[i];
 }
 
+// np.searchsorted(a, v, 'left') from an interpolated first guess, then an exact fix-up against the array
+// itself: one or two loads on a uniform grid, still exact (only slower) on any sorted grid.
+SOLAT_HD int searchsorted_guess(const double* a, int n, int stride, double v, double a0, double inv_step)
+{
+    double g = ceil((v - a0) * inv_step);
+    int i = g > 0.0 ? (g < (double)n ? (int)g : n) : 0;
+    while (i > 0 && !(a[(long)(i - 1) * stride] < v)) --i;
+    while (i < n && a[(long)i * stride] < v) ++i;
+    return i;
+}
+
+// x / 10 correctly rounded without the division subroutine: q = RN(x * 0.1) is within 1 ulp, the FMA
+// residual r = x - 10 q is exact, and RN(q + r * 0.1) is the correctly rounded quotient (Markstein).
+SOLAT_HD double div10(double x)
+{
+    const double q = x * 0.1;
+    return fma(fma(-q, 10.0, x), 0.1, q);
+}
+
 // far_field_latrt.py:14-26 for one ray: focal-plane offsets (mm) -> cell index iy*M+ix, or -1 when
 // the reference skips the ray.  gx = data_x[0,:] (M), gy = data_y (M x M row-major).
-SOLAT_HD int ff_cell(double fx_mm, double fz_mm, const double* gx, const double* gy, int M, double gx_max, double gy_max)
+struct FfGrid {
+    const double* gx;      // data_x[0, :]
+    const double* gy;      // data_y, (M, M) row-major
+    int M;
+    double gx_max, gy_max; // ffl:19: rays beyond these are skipped
+    double inv_dx, inv_dy; // (M-1)/(last-first) of gx and of gy[:,0]; 0 when not usable as a guess
+};
+SOLAT_HD int ff_cell(double fx_mm, double fz_mm, const FfGrid& G)
 {
-    const double xx = fx_mm / 1e1, yy = fz_mm / 1e1;
-    if (gx_max < xx || gy_max < yy) return -1;
-    const int ix = searchsorted_left(gx, M, 1, xx);
-    const int iy = searchsorted_left(gy + ix, M, M, yy);
-    return iy * M + ix;
+    const double xx = div10(fx_mm), yy = div10(fz_mm);                          // ffl:12-13: / 1e1
+    if (G.gx_max < xx || G.gy_max < yy) return -1;
+    const int ix = searchsorted_guess(G.gx, G.M, 1, xx, G.gx[0], G.inv_dx);     // ffl:22
+    const int iy = searchsorted_guess(G.gy + ix, G.M, G.M, yy, G.gy[ix], G.inv_dy);   // ffl:23
+    return iy * G.M + ix;
+}
+
+// Last-write-wins table entry (ffl:28: a later ray overwrites an earlier one): the ray index in the top 20 bits
+// so that a 64-bit atomicMax keeps the highest index, and the ray's path length below it as an exact
+// fixed-point offset from a per-pixel base (unit = half an ulp of the base, 44 bits = +-65 m at 1e8 mm).
+constexpr int FF_KEY_SHIFT = 44;
+constexpr int FF_MAX_RAYS = (1 << 20) - 1;
+SOLAT_HD unsigned long long ff_key(int ray, double opl, double base, double inv_unit, bool& exact, double unit)
+{
+    const double q = (opl - base) * inv_unit;
+    const long long qi = (long long)rint(q);
+    exact = (base + (double)qi * unit == opl) && (qi > -(1ll << 43)) && (qi < (1ll << 43));
+    return ((unsigned long long)(ray + 1) << FF_KEY_SHIFT) | (unsigned long long)(qi + (1ll << 43));
+}
+SOLAT_HD double ff_key_opl(unsigned long long key, double base, double unit)
+{
+    const long long qi = (long long)(key & ((1ull << FF_KEY_SHIFT) - 1)) - (1ll << 43);
+    return base + (double)qi * unit;
 }
 
 }  // namespace solat

@@ -86,6 +86,45 @@ API int shadow_nf_pixel(const double* p, const double* th, int nth, const double
     return agg;
 }
 
+// the same pixel with the two-rays-per-thread packs the fused map kernels use (d2 lock-step tracing)
+API int shadow_nf_pixel2(const double* p, const double* th, int nth, const double* ph, int nph, double n_si,
+                         double n_vac, const double* rx_opl, const double* rx_w, double k, double* re_im)
+{
+    const int n = nth * nph;
+    std::vector<int> act;
+    for (int r = 0; r < n; r++) if (rx_w[r] != 0.0) act.push_back(r);
+    double re = 0, im = 0;
+    int agg = 0;
+    const vec3t<d2> p0 = mk<d2>(d2(p[0]), d2(p[1]), d2(p[2]));
+    for (size_t a = 0; a < act.size(); a += 2) {
+        const bool two = a + 1 < act.size();
+        const int r0 = act[a], r1 = two ? act[a + 1] : r0;
+        const vec3 u = launch_dir(sin(th[r0 % nth]), cos(th[r0 % nth]), sin(ph[r0 / nth]), cos(ph[r0 / nth]));
+        const vec3 v = launch_dir(sin(th[r1 % nth]), cos(th[r1 % nth]), sin(ph[r1 / nth]), cos(ph[r1 / nth]));
+        NfSourceRayT<d2> ray;
+        nf_source_ray(p0, mk<d2>(d2(u.x, v.x), d2(u.y, v.y), d2(u.z, v.z)), n_si, n_vac, ray);
+        agg |= ray.status.a | (two ? ray.status.b : 0);
+        const double w0 = ray.valid.a ? rx_w[r0] : 0.0, w1 = (two && ray.valid.b) ? rx_w[r1] : 0.0;
+        const double a0 = (rx_opl[r0] + ray.opl.a) * (k / 1e3), a1 = (rx_opl[r1] + ray.opl.b) * (k / 1e3);
+        re += w0 * cos(a0) + w1 * cos(a1);
+        im += w0 * sin(a0) + w1 * sin(a1);
+    }
+    re_im[0] = re; re_im[1] = im;
+    return agg;
+}
+
+static FfGrid make_grid(const double* gx_full, const double* gy, int M)
+{
+    FfGrid G;
+    G.gx = gx_full; G.gy = gy; G.M = M;
+    G.gx_max = gx_full[0]; G.gy_max = gy[0];
+    for (int i = 0; i < M; i++) { G.gx_max = fmax(G.gx_max, gx_full[i]); G.gy_max = fmax(G.gy_max, gy[(size_t)i * M]); }
+    const double sx = gx_full[M - 1] - gx_full[0], sy = gy[(size_t)(M - 1) * M] - gy[0];
+    G.inv_dx = (M > 1 && sx > 0) ? (M - 1) / sx : 0.0;
+    G.inv_dy = (M > 1 && sy > 0) ? (M - 1) / sy : 0.0;
+    return G;
+}
+
 static FfGeom unpack(const double* g)
 {
     FfGeom q;
@@ -150,6 +189,65 @@ API int shadow_ff_field_rows(const double* geo, const double* th, int nth, const
     }
     return agg;
 }
+// far-field pixel traced two rays at a time (d2 packs), as the fused map kernel does
+API int shadow_ff_pixel2(const double* geo, const double* th, int nth, const double* ph, int nph, double el, double az,
+                         const double* gx_full, const double* gy, const double* e_rec, int M, double k, double* re_im,
+                         int* n_cells)
+{
+    FfGeom g = unpack(geo);
+    FfFrames f;
+    ff_build_frames(g, el, az, f);
+    const int n = nth * nph;
+    int agg = 0;
+    const FfGrid G = make_grid(gx_full, gy, M);
+    std::vector<int> win(M * M, -1), queue;
+    std::vector<double> opl(M * M, 0.0);
+    for (int r = 0; r < n; r++) {
+        vec3 d = launch_dir(sin(th[r % nth]), cos(th[r % nth]), sin(ph[r / nth]), cos(ph[r / nth])), Pa;
+        double t_ap;
+        if (ff_aperture(g, f, d, t_ap, Pa)) queue.push_back(r);
+    }
+    for (size_t a = 0; a < queue.size(); a += 2) {
+        const bool two = a + 1 < queue.size();
+        const int r0 = queue[a], r1 = two ? queue[a + 1] : r0;
+        const vec3 u = launch_dir(sin(th[r0 % nth]), cos(th[r0 % nth]), sin(ph[r0 / nth]), cos(ph[r0 / nth]));
+        const vec3 v = launch_dir(sin(th[r1 % nth]), cos(th[r1 % nth]), sin(ph[r1 / nth]), cos(ph[r1 / nth]));
+        const vec3t<d2> d = mk<d2>(d2(u.x, v.x), d2(u.y, v.y), d2(u.z, v.z));
+        vec3t<d2> Pa;
+        d2 t_ap;
+        ff_aperture(g, f, d, t_ap, Pa);
+        FfRayT<d2> ray;
+        ff_ray_trace<false, false, d2>(f, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+        agg |= ray.status.a | (two ? ray.status.b : 0);
+        const int rr[2] = {r0, r1};
+        const double oo[2] = {ray.opl.a, ray.opl.b}, fx[2] = {ray.foc.x.a, ray.foc.x.b}, fz[2] = {ray.foc.z.a, ray.foc.z.b};
+        for (int l = 0; l < (two ? 2 : 1); l++) {
+            if (oo[l] == 0.0) continue;
+            const int c = ff_cell(fx[l] - f.centre[0], fz[l] - f.centre[2], G);
+            if (c < 0) continue;
+            // through the packed 64-bit key of the fused kernel (exact fixed-point path length)
+            bool exact;
+            const double base = 1.0002e8, unit = ldexp(1.0, ilogb(base) - 53);
+            const unsigned long long key = ff_key(rr[l], oo[l], base, 1.0 / unit, exact, unit);
+            if (!exact) agg |= 8;
+            if (rr[l] > win[c]) { win[c] = rr[l]; opl[c] = ff_key_opl(key, base, unit); }
+        }
+    }
+    double re = 0, im = 0;
+    int cnt = 0;
+    for (int c = 0; c < M * M; c++) {
+        if (win[c] < 0) continue;
+        cnt++;
+        double cs, sn;
+        cis_large(k * opl[c] / 1e3, cs, sn);
+        re += cs * e_rec[2 * c] - sn * e_rec[2 * c + 1];
+        im += cs * e_rec[2 * c + 1] + sn * e_rec[2 * c];
+    }
+    re_im[0] = re / ((double)M * M); re_im[1] = im / ((double)M * M);
+    if (n_cells) *n_cells = cnt;
+    return agg;
+}
+
 // one far-field pixel, zero-error single-panel model (fused-map semantics)
 API int shadow_ff_pixel(const double* geo, const double* th, int nth, const double* ph, int nph, double el, double az,
                         const double* gx_full, const double* gy, const double* e_rec, int M, double k, double* re_im,
@@ -160,8 +258,7 @@ API int shadow_ff_pixel(const double* geo, const double* th, int nth, const doub
     ff_build_frames(g, el, az, f);
     const int n = nth * nph;
     int agg = 0;
-    double gx_max = gx_full[0], gy_max = gy[0];
-    for (int i = 0; i < M; i++) { gx_max = fmax(gx_max, gx_full[i]); gy_max = fmax(gy_max, gy[(size_t)i * M]); }
+    const FfGrid G = make_grid(gx_full, gy, M);
     std::vector<int> win(M * M, -1);
     std::vector<double> opl(M * M, 0.0);
     for (int r = 0; r < n; r++) {
@@ -173,7 +270,7 @@ API int shadow_ff_pixel(const double* geo, const double* th, int nth, const doub
         ff_ray_trace<false, false>(f, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
         agg |= ray.status;
         if (ray.opl == 0.0) continue;
-        const int c = ff_cell(ray.foc.x - f.centre[0], ray.foc.z - f.centre[2], gx_full, gy, M, gx_max, gy_max);
+        const int c = ff_cell(ray.foc.x - f.centre[0], ray.foc.z - f.centre[2], G);
         if (c < 0) continue;
         if (r > win[c]) { win[c] = r; opl[c] = ray.opl; }
     }

@@ -61,10 +61,12 @@ def nf_toy_rows(p, th, ph, y_ap, th_fwhp, n_si=3.4, n_vac=1.0):
     return out, agg
 
 
-def nf_pixel(p, th, ph, rx_opl, rx_w, k, n_si=3.4, n_vac=1.0):
+def nf_pixel(p, th, ph, rx_opl, rx_w, k, n_si=3.4, n_vac=1.0, packed=False):
+    """packed=True traces two rays per step with the d2 packs, as the fused map kernel does."""
     th, thp = D(th); ph, php = D(ph); p, pp = D(p); ro, rop = D(rx_opl); rw, rwp = D(rx_w)
     o = np.zeros(2)
-    agg = lib().shadow_nf_pixel(pp, thp, ci(th.size), php, ci(ph.size), cd(n_si), cd(n_vac), rop, rwp, cd(k),
+    fn = lib().shadow_nf_pixel2 if packed else lib().shadow_nf_pixel
+    agg = fn(pp, thp, ci(th.size), php, ci(ph.size), cd(n_si), cd(n_vac), rop, rwp, cd(k),
                                 o.ctypes.data_as(dp))
     return complex(o[0], o[1]), agg
 
@@ -91,11 +93,12 @@ def ff_field_rows(geo, th, ph, centre, el, az, pidx1=None, pidx2=None, pan1=None
     return out, agg
 
 
-def ff_pixel(geo, th, ph, el, az, data_x, data_y, e_rec, k):
+def ff_pixel(geo, th, ph, el, az, data_x, data_y, e_rec, k, packed=False):
     g, gp = D(geo); th, thp = D(th); ph, php = D(ph)
     gx, gxp = D(np.asarray(data_x)[0, :]); gy, gyp = D(data_y)
     e = np.ascontiguousarray(e_rec, dtype=np.complex128)
     o = np.zeros(2); nc = ci(0)
-    agg = lib().shadow_ff_pixel(gp, thp, ci(th.size), php, ci(ph.size), cd(el), cd(az), gxp, gyp,
+    fn = lib().shadow_ff_pixel2 if packed else lib().shadow_ff_pixel
+    agg = fn(gp, thp, ci(th.size), php, ci(ph.size), cd(el), cd(az), gxp, gyp,
                                 e.ctypes.data_as(dp), ci(gx.size), cd(k), o.ctypes.data_as(dp), ctypes.byref(nc))
     return complex(o[0], o[1]), nc.value, agg

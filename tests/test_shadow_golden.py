@@ -53,8 +53,9 @@ def test_nf_toy_rows(shadow):
         np.testing.assert_allclose(out, d["out_%d" % i], rtol=0, atol=RAY_TOL)
 
 
+@pytest.mark.parametrize("packed", [False, True])
 @pytest.mark.parametrize("name", ["nf_pixels", "nf_map5"])
-def test_nf_pixels(shadow, name):
+def test_nf_pixels(shadow, name, packed):
     d = gu.load(name)
     for i in range(int(d["n_cases"])):
         f, n = float(d["in_freq"][i]), int(d["in_n_scan"][i])
@@ -66,7 +67,8 @@ def test_nf_pixels(shadow, name):
         th, ph = _rx_axes(n)
         rx, _ = shadow.nf_rx_rows(p_rx, th, ph, fw)
         a = _src_axis(n)
-        z, agg = shadow.nf_pixel([d["in_x"][i], y_ap, d["in_z"][i]], a, a, rx[3], rx[4] * gu.lyot_mask(n), gu.nf_k(f))
+        z, agg = shadow.nf_pixel([d["in_x"][i], y_ap, d["in_z"][i]], a, a, rx[3], rx[4] * gu.lyot_mask(n), gu.nf_k(f),
+                                packed=packed)
         ra, rp = d["amp"][i], d["phi"][i]
         assert agg == 0
         assert abs(abs(z) ** 2 - ra ** 2) <= P_TOL * ra ** 2 + 1e-300
@@ -91,8 +93,9 @@ def test_ff_rows(shadow, oracle):
         assert np.abs(f[15] - ref[15]).max() <= 2 * ULP_1E8
 
 
+@pytest.mark.parametrize("packed", [False, True])
 @pytest.mark.parametrize("name", ["ff_pixels", "ff_map5"])
-def test_ff_pixels(shadow, oracle, name):
+def test_ff_pixels(shadow, oracle, name, packed):
     d = gu.load(name)
     for i in range(int(d["n_cases"])):
         n = int(d["in_n_scan"][i])
@@ -100,7 +103,7 @@ def test_ff_pixels(shadow, oracle, name):
         geo = oracle.ff_geo_vec(rx_y_m=-float(d["in_offset"][i]))
         x, y, e = gu.ff_grid(str(d["in_grid"][i]))
         z, nc, agg = shadow.ff_pixel(geo, th, ph, float(d["in_el"][i]), float(d["in_az"][i]), x, y, e,
-                                     gu.ff_k(float(d["in_freq"][i])))
+                                     gu.ff_k(float(d["in_freq"][i])), packed=packed)
         assert agg == 0
         assert nc == int(d["n_cells"][i])
         assert abs(abs(z) ** 2 - d["amp"][i] ** 2) <= P_TOL * d["amp"][i] ** 2
