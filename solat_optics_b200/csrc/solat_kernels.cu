@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
     for (int i = 0; i < iters; i++) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < 16; u++) {
             x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
             x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
         }
@@ -662,7 +662,7 @@ int solat_fp64_peak(solat_ctx* c, int repeats, double* tflops)
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     double best = 0.0;
-    for (int r = 0; r < repeats + 2; r++) {
+    for (int r = 0; r < repeats + 3; r++) {   // the first runs also ramp the clocks
         CK(cudaEventRecord(e0, c->stream));
         fp64_peak_kernel<<<blocks, threads, 0, c->stream>>>(out.p, iters, 0.999999, 1e-9);
         LAUNCHED();
@@ -670,8 +670,8 @@ int solat_fp64_peak(solat_ctx* c, int repeats, double* tflops)
         CK(cudaEventSynchronize(e1));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, e0, e1));
-        const double fl = 2.0 * 64.0 * iters * (double)blocks * threads;
-        if (r >= 2) best = fmax(best, fl / (ms * 1e-3) / 1e12);
+        const double fl = 2.0 * 128.0 * iters * (double)blocks * threads;
+        if (r >= 3) best = fmax(best, fl / (ms * 1e-3) / 1e12);
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *tflops = best;

@@ -210,6 +210,9 @@ template <class R> SOLAT_HD vec3t<R> axpy(const vec3t<R>& p, const vec3t<R>& d, 
 }
 template <class R> SOLAT_HD vec3t<R> neg(const vec3t<R>& a) { return mk<R>(-a.x, -a.y, -a.z); }
 
+// sqrt without the library's correctly-rounded slow path: k * rsqrt(k), <= 2 ulp; NaN for k < 0 like sqrt.
+template <class R> SOLAT_HD R sqrt_fast(R k) { return k * rsqrt_fast(k); }
+
 // Snell refraction, same vector law as ray_trace_int.py:20-30 written without cross products:
 //   s2 = mu (s - (N.s) N) - N sqrt(1 - mu^2 (1 - (N.s)^2)),   N pointing against propagation.
 // Returns NaN components on total internal reflection exactly like the reference's np.sqrt.
@@ -218,7 +221,7 @@ SOLAT_HD vec3t<R> refract(const vec3t<R>& s, const vec3t<R>& N, double mu)
 {
     const R c = -dot(N, s);
     const R k = fma(R(-mu * mu), fma(-c, c, R(1.0)), R(1.0));
-    const R f = fma(R(mu), c, -sqrt(k));
+    const R f = fma(R(mu), c, -sqrt_fast(k));
     return mk<R>(fma(f, N.x, mu * s.x), fma(f, N.y, mu * s.y), fma(f, N.z, mu * s.z));
 }
 // refraction at a flat whose normal is (0, ny, 0), ny = +-1 pointing against propagation
@@ -227,7 +230,7 @@ SOLAT_HD vec3t<R> refract_flat(const vec3t<R>& s, double ny, double mu)
 {
     const R c = -(ny * s.y);
     const R k = fma(R(-mu * mu), fma(-c, c, R(1.0)), R(1.0));
-    const R f = fma(R(mu), c, -sqrt(k));
+    const R f = fma(R(mu), c, -sqrt_fast(k));
     // the x and z components keep the reference's NaN behaviour: f * 0 is NaN when f is
     return mk<R>(fma(f, R(0.0), mu * s.x), fma(f, R(ny), mu * s.y), fma(f, R(0.0), mu * s.z));
 }
@@ -366,15 +369,15 @@ SOLAT_HD void nf_source_ray(const vec3t<R>& p0, const vec3t<R>& d0, double n_si,
     I st = plane_hit(p0, d0, Y_1B, 5.0, 14000.0, t1, r.p1b);                   // rti:967
     d = refract_flat(d0, -1.0, mu_in);                                          // rti:992
     const I st1a = asphere_hit<SURF_1A>(r.p1b, d, 1.0, 900.0, t2, r.p1a, N);   // rti:1033
-    // rti:1086 (>= 196 -> zero column).  A NaN radius means the iterate left the domain of the conic
+    // rti:1086 (radius >= 196 -> zero column; compared squared).  A NaN radius means the iterate left the domain of the conic
     // (r > 417 mm), where the reference's root function substitutes sag = 0 and then vignettes too.
-    B alive = lt(sqrt(fma(r.p1a.x, r.p1a.x, r.p1a.z * r.p1a.z)), R(196.0));
+    B alive = lt(fma(r.p1a.x, r.p1a.x, r.p1a.z * r.p1a.z), R(196.0 * 196.0));
     r.valid = alive; r.opl = R(0.0); r.status = st;
     if (!any(alive)) return;
     st |= imask(alive, st1a);
     d = refract(d, neg(N), mu_out);                                             // rti:1058
     st |= imask(alive, plane_hit(r.p1a, d, Y_2B, 5.0, 600.0, t3, r.p2b));      // rti:1130
-    alive = band(alive, lt(sqrt(fma(r.p2b.x, r.p2b.x, r.p2b.z * r.p2b.z)), R(176.0)));   // rti:1177
+    alive = band(alive, lt(fma(r.p2b.x, r.p2b.x, r.p2b.z * r.p2b.z), R(176.0 * 176.0)));   // rti:1177
     r.valid = alive; r.status = st;
     if (!any(alive)) return;
     d = refract_flat(d, -1.0, mu_in);                                           // rti:1154 (-n_hat)
@@ -458,64 +461,60 @@ constexpr double FF_RN = 3000.0;
 SOLAT_TABLE double K_FF[] = {1.0 / 3000.0, 2.0 / 3000.0, -7201.003729431267, 3e3 * 3e3, 4000.0};
 #define Y_CENT_M1 (K_FF[2])
 
-// Horner tables: rows i = 0, 2, 4, 6 of a1 / a2 (latrt_geo.py:55-61, :63-71) as polynomials in v = y/R,
-// followed by their v-derivatives.  z = P0 + w (P2 + w (P4 + w P6)), w = (x/R)^2.
+// Horner tables: rows i = 0, 2, 4, 6 of a1 / a2 (latrt_geo.py:55-61, :63-71) as polynomials in v = y/R.
+// z = P0 + w (P2 + w (P4 + w P6)), w = (x/R)^2, P0 = v^2 H0(v).
 SOLAT_TABLE double K_M1[] = {
-    /* P0/v^2 [0..4] */ -57.74022, 1.5373825, 1.154294, -0.441762, 0.0906601,
-    /* P2 [5..9]     */ -72.17349, 1.8691899, 2.8859421, -1.026471, 0.2610568,
-    /* P4 [10..12]   */ 1.8083973, -0.603195, 0.2177414,
-    /* P6 [13]       */ 0.0394559,
-    /* dP0/v [14..18]*/ 2 * -57.74022, 3 * 1.5373825, 4 * 1.154294, 5 * -0.441762, 6 * 0.0906601,
-    /* dP2 [19..22]  */ 1.8691899, 2 * 2.8859421, 3 * -1.026471, 4 * 0.2610568,
-    /* dP4 [23..24]  */ -0.603195, 2 * 0.2177414};
+    /* H0 [0..4]   */ -57.74022, 1.5373825, 1.154294, -0.441762, 0.0906601,
+    /* P2 [5..9]   */ -72.17349, 1.8691899, 2.8859421, -1.026471, 0.2610568,
+    /* P4 [10..12] */ 1.8083973, -0.603195, 0.2177414,
+    /* P6 [13]     */ 0.0394559};
 SOLAT_TABLE double K_M2[] = {
-    /* P0/v^2 [0..5] */ 103.90461, 6.6513025, 2.8405781, -0.7819705, -0.0400483, 0.0896645,
-    /* P2 [6..11]    */ 115.44758, 7.3024355, 5.7640389, -1.578144, -0.0354326, 0.2781226,
-    /* P4 [12..15]   */ 2.9130983, -0.8104051, -0.0185283, 0.2626023,
-    /* P6 [16..17]   */ -0.0250794, 0.0709672,
-    /* dP0/v [18..23]*/ 2 * 103.90461, 3 * 6.6513025, 4 * 2.8405781, 5 * -0.7819705, 6 * -0.0400483, 7 * 0.0896645,
-    /* dP2 [24..28]  */ 7.3024355, 2 * 5.7640389, 3 * -1.578144, 4 * -0.0354326, 5 * 0.2781226,
-    /* dP4 [29..31]  */ -0.8104051, 2 * -0.0185283, 3 * 0.2626023,
-    /* dP6 [32]      */ 0.0709672};
+    /* H0 [0..5]   */ 103.90461, 6.6513025, 2.8405781, -0.7819705, -0.0400483, 0.0896645,
+    /* P2 [6..11]  */ 115.44758, 7.3024355, 5.7640389, -1.578144, -0.0354326, 0.2781226,
+    /* P4 [12..15] */ 2.9130983, -0.8104051, -0.0185283, 0.2626023,
+    /* P6 [16..17] */ -0.0250794, 0.0709672};
 // single-precision copies (same layout) for the coarse first Newton update
-SOLAT_TABLE float K_M1F[] = {
-    -57.74022f, 1.5373825f, 1.154294f, -0.441762f, 0.0906601f, -72.17349f, 1.8691899f, 2.8859421f, -1.026471f, 0.2610568f,
-    1.8083973f, -0.603195f, 0.2177414f, 0.0394559f,
-    2 * -57.74022f, 3 * 1.5373825f, 4 * 1.154294f, 5 * -0.441762f, 6 * 0.0906601f,
-    1.8691899f, 2 * 2.8859421f, 3 * -1.026471f, 4 * 0.2610568f, -0.603195f, 2 * 0.2177414f};
-SOLAT_TABLE float K_M2F[] = {
-    103.90461f, 6.6513025f, 2.8405781f, -0.7819705f, -0.0400483f, 0.0896645f,
-    115.44758f, 7.3024355f, 5.7640389f, -1.578144f, -0.0354326f, 0.2781226f,
-    2.9130983f, -0.8104051f, -0.0185283f, 0.2626023f, -0.0250794f, 0.0709672f,
-    2 * 103.90461f, 3 * 6.6513025f, 4 * 2.8405781f, 5 * -0.7819705f, 6 * -0.0400483f, 7 * 0.0896645f,
-    7.3024355f, 2 * 5.7640389f, 3 * -1.578144f, 4 * -0.0354326f, 5 * 0.2781226f,
-    -0.8104051f, 2 * -0.0185283f, 3 * 0.2626023f, 0.0709672f};
+SOLAT_TABLE float K_M1F[] = {-57.74022f, 1.5373825f, 1.154294f, -0.441762f, 0.0906601f, -72.17349f, 1.8691899f,
+                             2.8859421f, -1.026471f, 0.2610568f, 1.8083973f, -0.603195f, 0.2177414f, 0.0394559f};
+SOLAT_TABLE float K_M2F[] = {103.90461f, 6.6513025f, 2.8405781f, -0.7819705f, -0.0400483f, 0.0896645f,
+                             115.44758f, 7.3024355f, 5.7640389f, -1.578144f, -0.0354326f, 0.2781226f,
+                             2.9130983f, -0.8104051f, -0.0185283f, 0.2626023f, -0.0250794f, 0.0709672f};
 
-// The Horner bodies are written once for both precisions (T = R with fma, T = F with fmaf).
+// Value and v-derivative of each row polynomial by dual-number Horner (p <- p v + c, dp <- dp v + p): every
+// coefficient is fetched once per evaluation -- on sm_100 a DFMA cannot take a constant-bank operand, so each
+// coefficient costs a load, and separate derivative tables would double them.  Written once for both precisions.
+#define SOLAT_DUAL_START(T, FMA, K, hi, p, dp) T p = FMA(T(K[hi]), v, T(K[(hi) - 1])), dp = T(K[hi]);
+#define SOLAT_DUAL_STEP(T, FMA, K, k, p, dp) dp = FMA(dp, v, p); p = FMA(p, v, T(K[k]));
 #define SOLAT_M1_BODY(T, FMA, K, INV_RN, TWO_INV_RN)                                                             \
     const T u = x * T(INV_RN), v = y * T(INV_RN), w = u * u;                                                     \
-    const T p0 = v * v * FMA(v, FMA(v, FMA(v, FMA(v, T(K[4]), T(K[3])), T(K[2])), T(K[1])), T(K[0]));            \
-    const T p2 = FMA(v, FMA(v, FMA(v, FMA(v, T(K[9]), T(K[8])), T(K[7])), T(K[6])), T(K[5]));                    \
-    const T p4 = FMA(v, FMA(v, T(K[12]), T(K[11])), T(K[10]));                                                   \
+    SOLAT_DUAL_START(T, FMA, K, 4, h0, dh0)                                                                      \
+    SOLAT_DUAL_STEP(T, FMA, K, 2, h0, dh0) SOLAT_DUAL_STEP(T, FMA, K, 1, h0, dh0) SOLAT_DUAL_STEP(T, FMA, K, 0, h0, dh0) \
+    SOLAT_DUAL_START(T, FMA, K, 9, p2, dp2)                                                                      \
+    SOLAT_DUAL_STEP(T, FMA, K, 7, p2, dp2) SOLAT_DUAL_STEP(T, FMA, K, 6, p2, dp2) SOLAT_DUAL_STEP(T, FMA, K, 5, p2, dp2) \
+    SOLAT_DUAL_START(T, FMA, K, 12, p4, dp4)                                                                     \
+    SOLAT_DUAL_STEP(T, FMA, K, 10, p4, dp4)                                                                      \
     const T p6 = T(K[13]);                                                                                       \
-    z = FMA(w, FMA(w, FMA(w, p6, p4), p2), p0);                                                                  \
-    const T q0 = v * FMA(v, FMA(v, FMA(v, FMA(v, T(K[18]), T(K[17])), T(K[16])), T(K[15])), T(K[14]));           \
-    const T q2 = FMA(v, FMA(v, FMA(v, T(K[22]), T(K[21])), T(K[20])), T(K[19]));                                 \
-    const T q4 = FMA(v, T(K[24]), T(K[23]));                                                                     \
-    zy = FMA(w, FMA(w, q4, q2), q0) * T(INV_RN);                                                                 \
+    const T vv = v * v;                                                                                          \
+    z = FMA(w, FMA(w, FMA(w, p6, p4), p2), vv * h0);                                                             \
+    const T dp0 = v * FMA(v, dh0, h0 + h0);                                                                      \
+    zy = FMA(w, FMA(w, dp4, dp2), dp0) * T(INV_RN);                                                              \
     zx = T(TWO_INV_RN) * u * FMA(w, FMA(w, p6 + p6 + p6, p4 + p4), p2);
 #define SOLAT_M2_BODY(T, FMA, K, INV_RN, TWO_INV_RN)                                                             \
     const T u = x * T(INV_RN), v = y * T(INV_RN), w = u * u;                                                     \
-    const T p0 = v * v * FMA(v, FMA(v, FMA(v, FMA(v, FMA(v, T(K[5]), T(K[4])), T(K[3])), T(K[2])), T(K[1])), T(K[0])); \
-    const T p2 = FMA(v, FMA(v, FMA(v, FMA(v, FMA(v, T(K[11]), T(K[10])), T(K[9])), T(K[8])), T(K[7])), T(K[6])); \
-    const T p4 = FMA(v, FMA(v, FMA(v, T(K[15]), T(K[14])), T(K[13])), T(K[12]));                                 \
-    const T p6 = FMA(v, T(K[17]), T(K[16]));                                                                     \
-    z = FMA(w, FMA(w, FMA(w, p6, p4), p2), p0);                                                                  \
-    const T q0 = v * FMA(v, FMA(v, FMA(v, FMA(v, FMA(v, T(K[23]), T(K[22])), T(K[21])), T(K[20])), T(K[19])), T(K[18])); \
-    const T q2 = FMA(v, FMA(v, FMA(v, FMA(v, T(K[28]), T(K[27])), T(K[26])), T(K[25])), T(K[24]));               \
-    const T q4 = FMA(v, FMA(v, T(K[31]), T(K[30])), T(K[29]));                                                   \
-    const T q6 = T(K[32]);                                                                                       \
-    zy = FMA(w, FMA(w, FMA(w, q6, q4), q2), q0) * T(INV_RN);                                                     \
+    SOLAT_DUAL_START(T, FMA, K, 5, h0, dh0)                                                                      \
+    SOLAT_DUAL_STEP(T, FMA, K, 3, h0, dh0) SOLAT_DUAL_STEP(T, FMA, K, 2, h0, dh0) SOLAT_DUAL_STEP(T, FMA, K, 1, h0, dh0) \
+    SOLAT_DUAL_STEP(T, FMA, K, 0, h0, dh0)                                                                       \
+    SOLAT_DUAL_START(T, FMA, K, 11, p2, dp2)                                                                     \
+    SOLAT_DUAL_STEP(T, FMA, K, 9, p2, dp2) SOLAT_DUAL_STEP(T, FMA, K, 8, p2, dp2) SOLAT_DUAL_STEP(T, FMA, K, 7, p2, dp2) \
+    SOLAT_DUAL_STEP(T, FMA, K, 6, p2, dp2)                                                                       \
+    SOLAT_DUAL_START(T, FMA, K, 15, p4, dp4)                                                                     \
+    SOLAT_DUAL_STEP(T, FMA, K, 13, p4, dp4) SOLAT_DUAL_STEP(T, FMA, K, 12, p4, dp4)                              \
+    const T dp6 = T(K[17]);                                                                                      \
+    const T p6 = FMA(dp6, v, T(K[16]));                                                                          \
+    const T vv = v * v;                                                                                          \
+    z = FMA(w, FMA(w, FMA(w, p6, p4), p2), vv * h0);                                                             \
+    const T dp0 = v * FMA(v, dh0, h0 + h0);                                                                      \
+    zy = FMA(w, FMA(w, FMA(w, dp6, dp4), dp2), dp0) * T(INV_RN);                                                 \
     zx = T(TWO_INV_RN) * u * FMA(w, FMA(w, p6 + p6 + p6, p4 + p4), p2);
 
 // z and its partials wrt the LOCAL coordinates x, y (mm); M = 1 primary, 2 secondary
