@@ -17,7 +17,8 @@
  *  - every function returns 0 on success and a negative solat_err on failure;
  *    solat_last_error() gives a thread-local message.
  *  - per-ray status bits (also OR-reduced per map): 1 = root outside the reference's brentq
- *    bracket (the reference raises ValueError there), 2 = Newton not converged, 4 = NaN path.
+ *    bracket (the reference raises ValueError there), 2 = Newton not converged, 4 = NaN path,
+ *    8 = far-field path length outside the fixed-point range of the last-write-wins key.
  *  - no global mutable state except the per-thread error string and a launch counter.
  */
 #ifndef SOLAT_B200_H
@@ -40,7 +41,7 @@ enum solat_err {
     SOLAT_ERR_CUDA = -2,    /* CUDA runtime error, see solat_last_error() */
     SOLAT_ERR_NODEV = -3    /* no usable sm_100 device */
 };
-enum solat_ray_status { SOLAT_ST_BRACKET = 1, SOLAT_ST_NOCONV = 2, SOLAT_ST_NAN = 4 };
+enum solat_ray_status { SOLAT_ST_BRACKET = 1, SOLAT_ST_NOCONV = 2, SOLAT_ST_NAN = 4, SOLAT_ST_RANGE = 8 };
 
 typedef struct solat_ctx solat_ctx;         /* one per device; owns scratch buffers */
 typedef struct solat_nf_plan solat_nf_plan; /* near-field map plan (tables resident in HBM) */

@@ -1,0 +1,6 @@
+"""Alias of solat_optics_b200.phase_correct (same public names as the reference module)."""
+import sys as _sys
+
+import solat_optics_b200.phase_correct as _impl
+
+_sys.modules[__name__] = _impl

@@ -18,7 +18,7 @@ c_vp = ctypes.c_void_p
 c_d = ctypes.c_double
 c_i = ctypes.c_int
 
-ST_BRACKET, ST_NOCONV, ST_NAN = 1, 2, 4
+ST_BRACKET, ST_NOCONV, ST_NAN, ST_RANGE = 1, 2, 4, 8
 
 
 class SolatError(RuntimeError):

@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
                     if (cell >= 0) {
                         bool exact;
                         const unsigned long long key = ff_key(rr[l], oo[l], q.key_base, q.key_inv_unit, exact, q.key_unit);
-                        if (!exact) st |= 8;
+                        if (!exact) st |= ST_RANGE;
                         atomicMax(win + cell, key);                                 // ffl:28: last write wins
                     }
                 }

@@ -58,7 +58,8 @@ enum : int {
     ST_OK = 0,
     ST_BRACKET = 1,   // root outside the reference's brentq bracket (reference: ValueError)
     ST_NOCONV = 2,    // Newton did not reach 1e-9 mm
-    ST_NAN = 4        // NaN in the optical path (total internal reflection / sqrt domain)
+    ST_NAN = 4,       // NaN in the optical path (total internal reflection / sqrt domain)
+    ST_RANGE = 8      // far-field path length not exactly representable in the winner key
 };
 
 // ------------------------------------------------------------------------------------------
