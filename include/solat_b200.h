@@ -99,16 +99,22 @@ SOLAT_API int solat_nf_toy_trace(solat_ctx *ctx, const solat_nf_geom *g, const d
  * rx_opl / rx_w [nth*nph]: receiver path length and (feed taper x Lyot mask) in ray-index space,
  * i.e. rows 3 and 4 of the regridded rx field (rti:1385-1440, holo_sim.py:168-180); rays with
  * rx_w == 0 are culled before tracing.  k_per_m[nfreq]: several wavenumbers share one trace.
- * amp/phase are [nfreq][npix].                                                                   */
+ * amp/phase are [nfreq][npix].  The _multi form takes nrx receiver tables, rx_opl / rx_w [nrx][nth*nph]
+ * (receiver-offset sweeps share the source trace too); amp/phase are then [nrx][nfreq][npix].     */
 SOLAT_API int solat_nf_plan_create(solat_ctx *ctx, const solat_nf_geom *g, const double *theta, int nth, const double *phi,
                          int nph, const double *rx_opl, const double *rx_w, const double *k_per_m, int nfreq,
                          solat_nf_plan **plan);
+SOLAT_API int solat_nf_plan_create_multi(solat_ctx *ctx, const solat_nf_geom *g, const double *theta, int nth,
+                                         const double *phi, int nph, const double *rx_opl, const double *rx_w, int nrx,
+                                         const double *k_per_m, int nfreq, solat_nf_plan **plan);
 SOLAT_API void solat_nf_plan_destroy(solat_nf_plan *plan);
 SOLAT_API int solat_nf_map_host(solat_nf_plan *plan, const double *src_xz, int npix, double *amp, double *phase, int *status);
 SOLAT_API int solat_nf_map_device(solat_nf_plan *plan, const double *d_src_xz, int npix, double *d_amp, double *d_phase,
                         void *stream);
 /* traced rays per pixel after culling (for FLOP accounting) */
 SOLAT_API int solat_nf_plan_active_rays(const solat_nf_plan *plan);
+/* number of output channels nrx * nfreq */
+SOLAT_API int solat_nf_plan_channels(const solat_nf_plan *plan);
 /* OR of the ray status bits of all device-side maps run on this plan since the last call (synchronises) */
 SOLAT_API int solat_nf_plan_status(solat_nf_plan *plan, int *status);
 

@@ -154,6 +154,12 @@ def build_jobs():
     px.append(dict(freq=150.0, n_scan=30, x=600.0, z=0.0))  # fully vignetted
     px.append(dict(freq=140.0, n_scan=30, x=250.0, z=-100.0))  # mostly vignetted
     J["nf_pixels"] = [("t_nf_pixel", a) for a in px]
+    # -- receiver-offset sweep (quant_systematics, BASELINE config 4)
+    J["nf_rx_offsets"] = [
+        ("t_nf_pixel", dict(freq=150.0, n_scan=30, x=float(x), z=float(z), p_rx=p))
+        for p in [(-60.0, 0.0, -60.0), (60.0, 0.0, 60.0), (0.0, 0.0, 60.0), (100.0, 0.0, 0.0)]
+        for x, z in [(0, 0), (-37, 21)]
+    ]
     # -- near-field small map, holo_sim.py grid logic with RES=5, n_scan=20
     rx = np.linspace(-50, 50, 5)
     J["nf_map5"] = [
@@ -175,6 +181,12 @@ def build_jobs():
     fp.append(dict(freq=140, offset=1.32, n_scan=100, az=-7 * DE, el=EL0 + 4 * DE, grid="wide61"))
     fp.append(dict(freq=90, offset=1.25, n_scan=24, az=2 * DE, el=EL0 - DE, grid="wide61"))
     J["ff_pixels"] = [("t_ff_pixel", a) for a in fp]
+    # -- the tutorial's command line `ff_sim.py 150 1 10 1.33` (latrt_farfield_sim.ipynb): centre, edge, corners
+    D1 = 1.0 / 60 * np.pi / 180
+    J["ff_pixels_150"] = [
+        ("t_ff_pixel", dict(freq=150, offset=1.33, n_scan=30, az=a * D1, el=EL0 + e * D1, grid="wide61"))
+        for a, e in [(0, 0), (10, 0), (-10, 10), (10, -10), (3, -7)]
+    ]
     # -- far-field small map: ff_sim.py 140 0.25 2 1.32 with N_scan=16, wide grid
     azs = np.linspace(-2 * DE, 2 * DE, 5)
     els = np.linspace(-2 * DE + EL0, 2 * DE + EL0, 5)
@@ -205,14 +217,14 @@ def pack(name, jobs, results):
     if name in ("nf_rx_rays", "nf_so_rays", "nf_toy_rays"):
         for i, r in enumerate(results):
             out["out_%d" % i] = r
-    elif name in ("nf_pixels", "nf_map5"):
+    elif name in ("nf_pixels", "nf_map5", "nf_rx_offsets"):
         out["amp"] = np.array([r[0] for r in results])
         out["phi"] = np.array([r[1] for r in results])
     elif name == "ff_rays":
         for i, (m, f) in enumerate(results):
             out["mirror_%d" % i] = m
             out["field_%d" % i] = f
-    elif name in ("ff_pixels", "ff_map5"):
+    elif name in ("ff_pixels", "ff_map5", "ff_pixels_150"):
         out["amp"] = np.array([r[0] for r in results])
         out["phi"] = np.array([r[1] for r in results])
         out["n_valid"] = np.array([r[2] for r in results])

@@ -49,10 +49,13 @@ SIGNATURES = {
     "solat_nf_toy_trace": (c_i, [c_vp, ctypes.POINTER(NfGeom), c_dp, c_dp, c_i, c_dp, c_i, c_dp, c_ip]),
     "solat_nf_plan_create": (c_i, [c_vp, ctypes.POINTER(NfGeom), c_dp, c_i, c_dp, c_i, c_dp, c_dp, c_dp, c_i,
                                    ctypes.POINTER(c_vp)]),
+    "solat_nf_plan_create_multi": (c_i, [c_vp, ctypes.POINTER(NfGeom), c_dp, c_i, c_dp, c_i, c_dp, c_dp, c_i, c_dp, c_i,
+                                         ctypes.POINTER(c_vp)]),
     "solat_nf_plan_destroy": (None, [c_vp]),
     "solat_nf_map_host": (c_i, [c_vp, c_dp, c_i, c_dp, c_dp, c_ip]),
     "solat_nf_map_device": (c_i, [c_vp, c_vp, c_i, c_vp, c_vp, c_vp]),
     "solat_nf_plan_active_rays": (c_i, [c_vp]),
+    "solat_nf_plan_channels": (c_i, [c_vp]),
     "solat_nf_plan_status": (c_i, [c_vp, c_ip]),
     "solat_ff_ray_mirror_pts": (c_i, [c_vp, ctypes.POINTER(FfGeom), c_dp, c_i, c_dp, c_i, c_d, c_d, c_dp, c_ip]),
     "solat_ff_apert_fields": (c_i, [c_vp, ctypes.POINTER(FfGeom), c_dp, c_i, c_dp, c_i, c_dp, c_ip, c_ip, c_dp, c_i,

@@ -38,9 +38,6 @@ using namespace solat;
 #ifndef SOLAT_NF_T
 #define SOLAT_NF_T 256      // threads per near-field CTA
 #endif
-#ifndef SOLAT_NF_PACK
-#define SOLAT_NF_PACK 1     // rays traced in lock step per thread in the near-field map kernel
-#endif
 #ifndef SOLAT_NF_MINB
 #define SOLAT_NF_MINB 3
 #endif
@@ -197,27 +194,29 @@ __global__ void __launch_bounds__(128) nf_rows_kernel(NfRowsParams q)
 // ------------------------------------------------------------------------------------------------
 // near field: fused map
 // ------------------------------------------------------------------------------------------------
-constexpr int NF_MAXF = 4;
+constexpr int NF_MAXF = 4;    // wavenumbers per launch
+constexpr int NF_MAXC = 8;    // channels (wavenumber x receiver table) per launch
 constexpr int NF_T = SOLAT_NF_T;
 struct NfMapParams {
     AngleTabs ang;
     const double* src_xz;      // [npix][2]
-    const int* act_idx;        // [n_act] ray indices with non-zero receiver weight
-    const double2* act_rx;     // [n_act] (rx_opl, rx_w)
+    const int* act_idx;        // [n_act] ray indices with a non-zero receiver weight in any table
+    const double2* phasor;     // [nrx][nfreq][n_act]  w_rx exp(i k L_rx / 1e3)  (holo_sim.py:173-176)
     double y_ap, n_si, n_vac;
-    double kk[NF_MAXF];        // k/1e3 [rad/mm]
-    int n_act, tiles, tile_len, nfreq_total, f0;
-    double2* partial;          // [npix][tiles][nfreq_total]
+    double kk[NF_MAXF];        // k/1e3 [rad/mm] of the wavenumbers of this launch
+    int n_act, tiles, tile_len, nfreq_total, nch_total, f0, j0;
+    double2* partial;          // [npix][tiles][nch_total], channel = table * nfreq + wavenumber
     int* status;
 };
 
-template <int NF>
-__device__ __forceinline__ void block_reduce_store(double (&re)[NF], double (&im)[NF], double2* dst)
+// CTA-wide sum of NC complex accumulators: warp shuffles, then one shared-memory hop.  dst[c * stride]
+template <int NC>
+__device__ __forceinline__ void block_reduce_store(double (&re)[NC], double (&im)[NC], double2* dst, int stride = 1)
 {
-    __shared__ double sh[2 * NF_MAXF][32];
+    __shared__ double sh[2 * NF_MAXC][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
 #pragma unroll
-    for (int f = 0; f < NF; f++) {
+    for (int f = 0; f < NC; f++) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             re[f] += __shfl_down_sync(0xffffffffu, re[f], o);
@@ -228,81 +227,71 @@ __device__ __forceinline__ void block_reduce_store(double (&re)[NF], double (&im
     __syncthreads();
     if (warp == 0) {
 #pragma unroll
-        for (int f = 0; f < NF; f++) {
+        for (int f = 0; f < NC; f++) {
             double a = lane < nwarp ? sh[2 * f][lane] : 0.0, b = lane < nwarp ? sh[2 * f + 1][lane] : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 a += __shfl_down_sync(0xffffffffu, a, o);
                 b += __shfl_down_sync(0xffffffffu, b, o);
             }
-            if (lane == 0) dst[f] = make_double2(a, b);
+            if (lane == 0) dst[f * stride] = make_double2(a, b);
         }
     }
 }
 
-// SOLAT_NF_PACK rays per thread per loop trip.
-template <int NF>
+// One CTA per (source position, ray tile); thread per ray.  The source ray is traced ONCE and feeds
+// NF wavenumbers x NT receiver tables: exp(i k L_source) is formed per wavenumber and multiplied into the
+// precomputed receiver phasor of every table (frequency sweeps of one band and receiver-offset sweeps share
+// the geometry: BASELINE configs 3 and 4).
+template <int NF, int NT>
 __global__ void __launch_bounds__(NF_T, SOLAT_NF_MINB) nf_map_kernel(NfMapParams q)
 {
+    constexpr int NC = NF * NT;
     const int pix = blockIdx.x / q.tiles, tile = blockIdx.x - pix * q.tiles;
-    const d2 px = d2(__ldg(q.src_xz + 2 * pix)), pz = d2(__ldg(q.src_xz + 2 * pix + 1));
-    const vec3t<d2> p0 = mk<d2>(px, d2(q.y_ap), pz);
-    double re[NF], im[NF];
+    const vec3 p0 = mk(__ldg(q.src_xz + 2 * pix), q.y_ap, __ldg(q.src_xz + 2 * pix + 1));
+    double re[NC], im[NC];
 #pragma unroll
-    for (int f = 0; f < NF; f++) re[f] = im[f] = 0.0;
+    for (int c = 0; c < NC; c++) re[c] = im[c] = 0.0;
     int st = 0;
     const int q_end = min((tile + 1) * q.tile_len, q.n_act);
-#if SOLAT_NF_PACK == 2
-    // two rays per thread in lock step (d2 packs): thread t takes active rays base + t and base + T + t
-    for (int a0 = tile * q.tile_len + threadIdx.x; a0 < q_end; a0 += 2 * NF_T) {
-        const int a1 = a0 + NF_T;
-        const bool two = a1 < q_end;
-        const int r0 = __ldg(q.act_idx + a0), r1 = two ? __ldg(q.act_idx + a1) : r0;
-        const double2 rx0 = __ldg(q.act_rx + a0);
-        double2 rx1 = two ? __ldg(q.act_rx + a1) : rx0;
-        if (!two) rx1.y = 0.0;                         // the odd ray out is traced twice, counted once
-        NfSourceRayT<d2> ray;
-        nf_source_ray(p0, ray_dir2(q.ang, r0, r1), q.n_si, q.n_vac, ray);
-        st |= ray.status.a | (two ? ray.status.b : 0);
-        // holo_sim.py:176-177: exp(i k L_rx) exp(i k L_so); vignetted rays carry amplitude 0
-        const double L0 = rx0.x + ray.opl.a, L1 = rx1.x + ray.opl.b;
-        const double w0 = ray.valid.a ? rx0.y : 0.0, w1 = ray.valid.b ? rx1.y : 0.0;
-#pragma unroll
-        for (int f = 0; f < NF; f++) {
-            double s0, c0, s1, c1;
-            sincos(L0 * q.kk[f], &s0, &c0);
-            sincos(L1 * q.kk[f], &s1, &c1);
-            re[f] = fma(w0, c0, fma(w1, c1, re[f]));
-            im[f] = fma(w0, s0, fma(w1, s1, im[f]));
-        }
-    }
-#else
-    const vec3 p0s = mk(px.a, q.y_ap, pz.a);
     for (int a = tile * q.tile_len + threadIdx.x; a < q_end; a += NF_T) {
         const int r = __ldg(q.act_idx + a);
-        const double2 rx = __ldg(q.act_rx + a);
         NfSourceRay ray;
-        nf_source_ray(p0s, ray_dir(q.ang, r), q.n_si, q.n_vac, ray);
+        nf_source_ray(p0, ray_dir(q.ang, r), q.n_si, q.n_vac, ray);
         st |= ray.status;
         if (ray.valid) {
-            const double L = rx.x + ray.opl;   // holo_sim.py:176-177: exp(i k L_rx) exp(i k L_so)
 #pragma unroll
             for (int f = 0; f < NF; f++) {
                 double sn, cs;
-                sincos(L * q.kk[f], &sn, &cs);
-                re[f] = fma(rx.y, cs, re[f]);
-                im[f] = fma(rx.y, sn, im[f]);
+                sincos(ray.opl * q.kk[f], &sn, &cs);                              // holo_sim.py:177
+#pragma unroll
+                for (int t = 0; t < NT; t++) {
+                    const double2 ph = __ldg(q.phasor + ((size_t)(q.j0 + t) * q.nfreq_total + (q.f0 + f)) * q.n_act + a);
+                    re[t * NF + f] = fma(ph.x, cs, fma(-ph.y, sn, re[t * NF + f]));
+                    im[t * NF + f] = fma(ph.x, sn, fma(ph.y, cs, im[t * NF + f]));
+                }
             }
         }
     }
-#endif
     if (st) atomicOr(q.status, st);
-    block_reduce_store<NF>(re, im, q.partial + ((size_t)pix * q.tiles + tile) * q.nfreq_total + q.f0);
+    // accumulators are ordered [t][f]; channel (j0 + t) * nfreq + f0 + f
+    double2* base = q.partial + ((size_t)pix * q.tiles + tile) * q.nch_total;
+    if (NT == 1) {
+        block_reduce_store<NC>(re, im, base + (size_t)q.j0 * q.nfreq_total + q.f0);
+    } else {
+        __shared__ double2 tmp[NF_MAXC];
+        block_reduce_store<NC>(re, im, tmp);
+        __syncthreads();
+        if (threadIdx.x < NC) {
+            const int t = threadIdx.x / NF, f = threadIdx.x - t * NF;
+            base[(size_t)(q.j0 + t) * q.nfreq_total + q.f0 + f] = tmp[threadIdx.x];
+        }
+    }
 }
 
 __global__ void nf_finalize_kernel(const double2* partial, int npix, int tiles, int nfreq, double* amp, double* phase)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // f * npix + pix
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // channel * npix + pix
     if (idx >= npix * nfreq) return;
     const int f = idx / npix, pix = idx - f * npix;
     double re = 0.0, im = 0.0;
@@ -743,11 +732,12 @@ struct solat_nf_plan {
     solat_nf_geom g;
     AngleTabsOwner ang;
     DevBuf<int> act_idx;
-    DevBuf<double2> act_rx;
+    DevBuf<double2> phasor;                 // [nrx][nfreq][n_act]
     DevBuf<double2> partial;
     DevBuf<double> h_src, h_amp, h_phase;   // device staging for the host entry point
     DevBuf<int> status;
     std::vector<double> kk;
+    int nrx = 1;
     int n_act = 0, tiles = 1, tile_len = 0, threads = NF_T;
 };
 
@@ -761,7 +751,7 @@ static void nf_choose_tiling(solat_nf_plan* p)
     int best_tiles = min_tiles;
     for (int tiles = min_tiles; tiles < min_tiles + 6; tiles++) {
         const int len = (p->n_act + tiles - 1) / tiles;
-        const int granule = SOLAT_NF_PACK * p->threads;   // rays per CTA per loop trip
+        const int granule = p->threads;                 // rays per CTA per loop trip
         const int iters = (len + granule - 1) / granule;
         const double thread_eff = (double)p->n_act / ((double)tiles * iters * granule);
         if (thread_eff > best + 1e-9) { best = thread_eff; best_tiles = tiles; }
@@ -770,69 +760,100 @@ static void nf_choose_tiling(solat_nf_plan* p)
     p->tile_len = (p->n_act + best_tiles - 1) / best_tiles;
 }
 
+template <int NF, int NT>
+static void nf_launch_one(const NfMapParams& q, int grid, int threads, cudaStream_t s)
+{
+    nf_map_kernel<NF, NT><<<grid, threads, 0, s>>>(q);
+}
+
 static int nf_map_launch(solat_nf_plan* p, const double* d_src, int npix, double* d_amp, double* d_phase, cudaStream_t s)
 {
     CK(cudaSetDevice(p->ctx->device));
-    const int nfreq = (int)p->kk.size();
+    const int nfreq = (int)p->kk.size(), nch = nfreq * p->nrx;
     if (p->n_act == 0) {   // nothing passes the receiver mask: the reference returns amp 0, phase 0
-        CK(cudaMemsetAsync(d_amp, 0, sizeof(double) * npix * nfreq, s));
-        CK(cudaMemsetAsync(d_phase, 0, sizeof(double) * npix * nfreq, s));
+        CK(cudaMemsetAsync(d_amp, 0, sizeof(double) * npix * nch, s));
+        CK(cudaMemsetAsync(d_phase, 0, sizeof(double) * npix * nch, s));
         return SOLAT_OK;
     }
     nf_choose_tiling(p);
-    if (int rc = p->partial.reserve((size_t)npix * p->tiles * nfreq)) return rc;
+    if (int rc = p->partial.reserve((size_t)npix * p->tiles * nch)) return rc;
     NfMapParams q;
-    q.ang = p->ang.tabs; q.src_xz = d_src; q.act_idx = p->act_idx.p; q.act_rx = p->act_rx.p;
+    q.ang = p->ang.tabs; q.src_xz = d_src; q.act_idx = p->act_idx.p; q.phasor = p->phasor.p;
     q.y_ap = p->g.y_ap; q.n_si = p->g.n_si; q.n_vac = p->g.n_vac;
-    q.n_act = p->n_act; q.tiles = p->tiles; q.tile_len = p->tile_len; q.nfreq_total = nfreq;
+    q.n_act = p->n_act; q.tiles = p->tiles; q.tile_len = p->tile_len; q.nfreq_total = nfreq; q.nch_total = nch;
     q.partial = p->partial.p; q.status = p->status.p;
     const int grid = npix * p->tiles;
+    // every launch re-traces the rays, so pack as many channels as the accumulators allow (NF * NT <= 8)
     for (int f0 = 0; f0 < nfreq; f0 += NF_MAXF) {
         const int nf = std::min(NF_MAXF, nfreq - f0);
         q.f0 = f0;
         for (int f = 0; f < NF_MAXF; f++) q.kk[f] = f < nf ? p->kk[f0 + f] / 1e3 : 0.0;
-        switch (nf) {
-        case 1: nf_map_kernel<1><<<grid, p->threads, 0, s>>>(q); break;
-        case 2: nf_map_kernel<2><<<grid, p->threads, 0, s>>>(q); break;
-        case 3: nf_map_kernel<3><<<grid, p->threads, 0, s>>>(q); break;
-        default: nf_map_kernel<4><<<grid, p->threads, 0, s>>>(q); break;
+        const int nt_cap = nf == 1 ? 8 : (nf == 2 ? 4 : 2);
+        for (int j0 = 0; j0 < p->nrx;) {
+            int nt = 1;
+            while (nt * 2 <= nt_cap && j0 + nt * 2 <= p->nrx) nt *= 2;
+            q.j0 = j0;
+#define SOLAT_NF_CASE(F, T) if (nf == F && nt == T) nf_launch_one<F, T>(q, grid, p->threads, s);
+            SOLAT_NF_CASE(1, 1) SOLAT_NF_CASE(1, 2) SOLAT_NF_CASE(1, 4) SOLAT_NF_CASE(1, 8)
+            SOLAT_NF_CASE(2, 1) SOLAT_NF_CASE(2, 2) SOLAT_NF_CASE(2, 4)
+            SOLAT_NF_CASE(3, 1) SOLAT_NF_CASE(3, 2) SOLAT_NF_CASE(4, 1) SOLAT_NF_CASE(4, 2)
+#undef SOLAT_NF_CASE
+            LAUNCHED();
+            j0 += nt;
         }
-        LAUNCHED();
     }
-    const int tot = npix * nfreq;
-    nf_finalize_kernel<<<(tot + 127) / 128, 128, 0, s>>>(p->partial.p, npix, p->tiles, nfreq, d_amp, d_phase);
+    const int tot = npix * nch;
+    nf_finalize_kernel<<<(tot + 127) / 128, 128, 0, s>>>(p->partial.p, npix, p->tiles, nch, d_amp, d_phase);
     LAUNCHED();
     return SOLAT_OK;
 }
 
 extern "C" {
 
-int solat_nf_plan_create(solat_ctx* c, const solat_nf_geom* g, const double* theta, int nth, const double* phi, int nph,
-                         const double* rx_opl, const double* rx_w, const double* k_per_m, int nfreq,
-                         solat_nf_plan** out)
+int solat_nf_plan_create_multi(solat_ctx* c, const solat_nf_geom* g, const double* theta, int nth, const double* phi,
+                               int nph, const double* rx_opl, const double* rx_w, int nrx, const double* k_per_m,
+                               int nfreq, solat_nf_plan** out)
 {
-    if (!c || !g || !theta || !phi || !rx_opl || !rx_w || !k_per_m || !out || nth <= 0 || nph <= 0 || nfreq <= 0)
+    if (!c || !g || !theta || !phi || !rx_opl || !rx_w || !k_per_m || !out || nth <= 0 || nph <= 0 || nfreq <= 0 || nrx <= 0)
         return fail(SOLAT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(c->device));
     solat_nf_plan* p = new solat_nf_plan();
-    p->ctx = c; p->g = *g;
+    p->ctx = c; p->g = *g; p->nrx = nrx;
     p->kk.assign(k_per_m, k_per_m + nfreq);
     int rc = p->ang.init(theta, nth, phi, nph, c->stream);
     const size_t n = (size_t)nth * nph;
+    // cull: a ray is traced if any receiver table gives it weight (holo_sim.py:168-180 mask x feed taper)
     std::vector<int> idx;
-    std::vector<double2> rx;
-    idx.reserve(n); rx.reserve(n);
-    for (size_t r = 0; r < n; r++)
-        if (rx_w[r] != 0.0) { idx.push_back((int)r); rx.push_back(make_double2(rx_opl[r], rx_w[r])); }
+    idx.reserve(n);
+    for (size_t r = 0; r < n; r++) {
+        bool any_w = false;
+        for (int j = 0; j < nrx && !any_w; j++) any_w = rx_w[(size_t)j * n + r] != 0.0;
+        if (any_w) idx.push_back((int)r);
+    }
     p->n_act = (int)idx.size();
+    // receiver phasors w exp(i k L_rx / 1e3), one table per (receiver table, wavenumber)  (holo_sim.py:173-176)
+    std::vector<double2> ph((size_t)nrx * nfreq * p->n_act);
+    for (int j = 0; j < nrx; j++)
+        for (int f = 0; f < nfreq; f++)
+            for (int a = 0; a < p->n_act; a++) {
+                const size_t r = (size_t)j * n + idx[a];
+                const double arg = rx_opl[r] * k_per_m[f] / 1e3;
+                ph[((size_t)j * nfreq + f) * p->n_act + a] = make_double2(rx_w[r] * cos(arg), rx_w[r] * sin(arg));
+            }
     if (!rc && p->n_act) rc = p->act_idx.upload(idx.data(), idx.size(), c->stream);
-    if (!rc && p->n_act) rc = p->act_rx.upload(rx.data(), rx.size(), c->stream);
+    if (!rc && p->n_act) rc = p->phasor.upload(ph.data(), ph.size(), c->stream);
     if (!rc) rc = p->status.reserve(1);
     if (!rc && cudaMemsetAsync(p->status.p, 0, sizeof(int), c->stream) != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "memset");
     if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "sync");
     if (rc) { delete p; return rc; }
     *out = p;
     return SOLAT_OK;
+}
+int solat_nf_plan_create(solat_ctx* c, const solat_nf_geom* g, const double* theta, int nth, const double* phi, int nph,
+                         const double* rx_opl, const double* rx_w, const double* k_per_m, int nfreq,
+                         solat_nf_plan** out)
+{
+    return solat_nf_plan_create_multi(c, g, theta, nth, phi, nph, rx_opl, rx_w, 1, k_per_m, nfreq, out);
 }
 void solat_nf_plan_destroy(solat_nf_plan* p)
 {
@@ -841,6 +862,7 @@ void solat_nf_plan_destroy(solat_nf_plan* p)
     delete p;
 }
 int solat_nf_plan_active_rays(const solat_nf_plan* p) { return p ? p->n_act : 0; }
+int solat_nf_plan_channels(const solat_nf_plan* p) { return p ? p->nrx * (int)p->kk.size() : 0; }
 
 int solat_nf_map_device(solat_nf_plan* p, const double* d_src, int npix, double* d_amp, double* d_phase, void* stream)
 {
@@ -861,7 +883,7 @@ int solat_nf_map_host(solat_nf_plan* p, const double* src_xz, int npix, double* 
     if (!p || !src_xz || !amp || !phase || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(p->ctx->device));
     cudaStream_t s = p->ctx->stream;
-    const size_t nf = p->kk.size();
+    const size_t nf = p->kk.size() * (size_t)p->nrx;   // channels
     if (int rc = p->h_src.upload(src_xz, 2 * (size_t)npix, s)) return rc;
     if (int rc = p->h_amp.reserve(nf * npix)) return rc;
     if (int rc = p->h_phase.reserve(nf * npix)) return rc;

@@ -108,7 +108,11 @@ def receiver_field(tele_geo, p_rx=(0, 0, 0), n_scan_rx=None, n_scan_so=None):
 
 class NearFieldPlan:
     """Fused near-field map: per source position sum_rays w_rx exp(i k (L_rx + L_source)/1e3).
-    `k_per_m`: one or several wavenumbers [rad/m] sharing the geometry (same y_ap)."""
+
+    `k_per_m`: one or several wavenumbers [rad/m] sharing the geometry (same y_ap).
+    `rx_opl`, `rx_w`: receiver field in the source's ray-index space, shape (n_scan^2,) or, for several
+    receiver positions sharing the same source trace, (n_rx, n_scan^2).
+    Results have shape (n_freq, npix), or (n_rx, n_freq, npix) when several receiver tables were given."""
 
     def __init__(self, tele_geo, k_per_m, rx_opl, rx_w, n_scan=None, device=None):
         lib = _lib.load()
@@ -119,29 +123,37 @@ class NearFieldPlan:
         self.k = _lib.as_f64(np.atleast_1d(k_per_m))
         rx_opl = _lib.as_f64(rx_opl)
         rx_w = _lib.as_f64(rx_w)
-        if rx_opl.shape != (n * n,) or rx_w.shape != (n * n,):
-            raise ValueError("receiver field must have n_scan^2 entries")
+        self.multi = rx_opl.ndim == 2
+        rx_opl = np.atleast_2d(rx_opl)
+        rx_w = np.atleast_2d(rx_w)
+        self.n_rx = rx_opl.shape[0]
+        if rx_opl.shape != (self.n_rx, n * n) or rx_w.shape != rx_opl.shape:
+            raise ValueError("receiver field must have n_scan^2 entries (per receiver table)")
         geom = _lib.nf_geom(tele_geo)
         h = _lib.c_vp()
-        _lib.check(lib.solat_nf_plan_create(self.ctx.handle, ctypes.byref(geom), _lib.dptr(axis), n, _lib.dptr(axis), n,
-                                            _lib.dptr(rx_opl), _lib.dptr(rx_w), _lib.dptr(self.k), self.k.size,
-                                            ctypes.byref(h)))
+        _lib.check(lib.solat_nf_plan_create_multi(self.ctx.handle, ctypes.byref(geom), _lib.dptr(axis), n, _lib.dptr(axis),
+                                                  n, _lib.dptr(rx_opl), _lib.dptr(rx_w), self.n_rx, _lib.dptr(self.k),
+                                                  self.k.size, ctypes.byref(h)))
         self.handle = h
         self.active_rays = int(lib.solat_nf_plan_active_rays(h))
+        self.channels = int(lib.solat_nf_plan_channels(h))
+
+    def _shape(self, npix):
+        return (self.n_rx, self.k.size, npix) if self.multi else (self.k.size, npix)
 
     def run(self, src_xz, amp=None, phase=None):
-        """Host buffers in, host buffers out (copies inside).  Returns amp, phase [nfreq, npix], status."""
+        """Host buffers in, host buffers out (copies inside).  Returns amp, phase, status."""
         src = _lib.as_f64(np.reshape(src_xz, (-1, 2)))
         npix = src.shape[0]
-        amp = np.empty((self.k.size, npix)) if amp is None else amp
-        phase = np.empty((self.k.size, npix)) if phase is None else phase
+        amp = np.empty(self._shape(npix)) if amp is None else amp
+        phase = np.empty(self._shape(npix)) if phase is None else phase
         st = _lib.c_i(0)
         _lib.check(_lib.load().solat_nf_map_host(self.handle, _lib.dptr(src), npix, _lib.dptr(amp), _lib.dptr(phase),
                                                  ctypes.byref(st)))
         return amp, phase, st.value
 
     def run_device(self, d_src, d_amp, d_phase, stream=0):
-        """torch CUDA float64 tensors ([npix,2], [nfreq*npix], [nfreq*npix]); asynchronous on `stream`."""
+        """torch CUDA float64 tensors ([npix,2], [channels*npix], [channels*npix]); asynchronous on `stream`."""
         npix = d_src.shape[0]
         _lib.check(_lib.load().solat_nf_map_device(self.handle, d_src.data_ptr(), npix, d_amp.data_ptr(),
                                                    d_phase.data_ptr(), stream))
@@ -204,6 +216,21 @@ def holo_map(freqs, res=51, sweep=100, shift=0, n_scan=100, n_scan_rx=None, p_rx
     full = full.cpu().numpy()
     nf = len(freqs)
     return pixels, np.ascontiguousarray(full[:, :nf].T), np.ascontiguousarray(full[:, nf:].T)
+
+
+def receiver_offset_sweep(freq, rx_positions, res=51, sweep=100, shift=0, n_scan=100, device=None, strict=False):
+    """Near-field maps for many receiver feed positions at one frequency (the quant_systematics sweep,
+    BASELINE config 4): the source rays are traced once per pixel and integrated against every receiver
+    table.  Single process (shard the receiver list over ranks for more GPUs).
+    Returns (pixels [npix,2], amp [n_rx,npix], phase [n_rx,npix])."""
+    tg = holo_tele_geo(float(freq), n_scan)
+    tabs = [receiver_field(tg, tuple(p), None, n_scan) for p in rx_positions]
+    plan = NearFieldPlan(tg, [tg.k], np.stack([t[0] for t in tabs]), np.stack([t[1] for t in tabs]), n_scan, device)
+    pixels = holo_pixels(res, sweep, shift)
+    amp, phase, st = plan.run(pixels)
+    _lib.raise_on_status(st, strict)
+    plan.close()
+    return pixels, amp[:, 0, :], phase[:, 0, :]
 
 
 def _gather_device(device_index):

@@ -127,17 +127,20 @@ def _nf_pixel_gpu(freq, n, n_rx, p_rx, x, z):
     return amp[0, 0], ph[0, 0], st
 
 
-def test_nf_pixel_known_answers():
-    d = gu.load("nf_pixels")
+@pytest.mark.parametrize("name", ["nf_pixels", "nf_rx_offsets"])
+def test_nf_pixel_known_answers(name):
+    d = gu.load(name)
     amps, phs = [], []
     for i in range(int(d["n_cases"])):
-        a, p, st = _nf_pixel_gpu(d["in_freq"][i], int(d["in_n_scan"][i]), int(d["in_n_scan_rx"][i]), d["in_p_rx"][i],
-                                 d["in_x"][i], d["in_z"][i])
+        n_rx = int(d["in_n_scan_rx"][i]) if "in_n_scan_rx" in d else int(d["in_n_scan"][i])
+        a, p, st = _nf_pixel_gpu(d["in_freq"][i], int(d["in_n_scan"][i]), n_rx, d["in_p_rx"][i], d["in_x"][i], d["in_z"][i])
         assert st == 0
         amps.append(a); phs.append(p)
     _assert_pixels(np.array(amps), np.array(phs), d["amp"], d["phi"])
     fully_vignetted = d["amp"] == 0
-    assert fully_vignetted.any() and np.all(np.array(amps)[fully_vignetted] == 0)
+    assert np.all(np.array(amps)[fully_vignetted] == 0)
+    if name == "nf_pixels":
+        assert fully_vignetted.any()
 
 
 def test_nf_small_map_and_frequency_sweep(oracle):
@@ -154,6 +157,34 @@ def test_nf_small_map_and_frequency_sweep(oracle):
         np.testing.assert_array_equal(amp3[i], a1[0]); np.testing.assert_array_equal(ph3[i], p1[0])
     with pytest.raises(ValueError):
         maps.holo_map([90.0, 150.0], res=3, n_scan=8, device=0)          # different bands: y_ap differs
+
+
+def test_nf_receiver_offset_sweep_shares_the_source_trace(oracle):
+    """BASELINE config 4 (quant_systematics): several receiver positions in one plan == one plan per position,
+    bit for bit, with and without several frequencies; checked against the oracle for an offset feed."""
+    from solat_optics_b200 import maps
+
+    offsets = [(x, 0.0, z) for x in (-60.0, 0.0, 60.0) for z in (-60.0, 0.0, 60.0)] + [(30.0, 0.0, -15.0)]   # 10 tables
+    px, amp, ph = maps.receiver_offset_sweep(150.0, offsets, res=5, n_scan=24, device=0)
+    assert amp.shape == (10, 25)
+    tg = maps.holo_tele_geo(150.0, 24)
+    for j in (0, 4, 9):
+        rx_opl, rx_w = maps.receiver_field(tg, offsets[j])
+        a1, p1, st = maps.NearFieldPlan(tg, [tg.k], rx_opl, rx_w, device=0).run(px)
+        assert st == 0
+        np.testing.assert_array_equal(a1[0], amp[j]); np.testing.assert_array_equal(p1[0], ph[j])
+        orx = oracle.nf_rx_trace(offsets[j], tg.th_fwhp, 24)
+        oa, op = oracle.nf_map(px, tg.y_ap, 24, orx[3], orx[4] * gu.lyot_mask(24), [tg.k])
+        _assert_pixels(amp[j], ph[j], oa, op)
+    # 3 tables x 2 wavenumbers in one plan
+    tabs = [maps.receiver_field(tg, o) for o in offsets[:3]]
+    k2 = [tg.k, maps.holo_tele_geo(220.0, 24).k]
+    plan = maps.NearFieldPlan(tg, k2, np.stack([t[0] for t in tabs]), np.stack([t[1] for t in tabs]), device=0)
+    a, p, st = plan.run(px)
+    assert a.shape == (3, 2, 25) and plan.channels == 6 and st == 0
+    for j in range(3):
+        a1, p1, _ = maps.NearFieldPlan(tg, k2, tabs[j][0], tabs[j][1], device=0).run(px)
+        np.testing.assert_array_equal(a1, a[j]); np.testing.assert_array_equal(p1, p[j])
 
 
 def test_nf_full_default_map_against_oracle(oracle):
@@ -289,7 +320,7 @@ def test_ff_project_to_data(oracle):
         np.testing.assert_allclose(out, ref, rtol=0, atol=1e-9)   # same k*L/1e3 argument; reduction error only
 
 
-@pytest.mark.parametrize("name", ["ff_pixels", "ff_map5"])
+@pytest.mark.parametrize("name", ["ff_pixels", "ff_map5", "ff_pixels_150"])
 def test_ff_pixel_known_answers(name):
     from solat_optics_b200 import maps
 

@@ -41,7 +41,7 @@ def test_nf_toy_rays(oracle):
         np.testing.assert_allclose(out, d["out_%d" % i], rtol=0, atol=1e-10)
 
 
-@pytest.mark.parametrize("name", ["nf_pixels", "nf_map5"])
+@pytest.mark.parametrize("name", ["nf_pixels", "nf_map5", "nf_rx_offsets"])
 def test_nf_pixels(oracle, name):
     d = gu.load(name)
     for i in range(int(d["n_cases"])):
@@ -75,7 +75,7 @@ def test_ff_rays(oracle):
         assert np.abs(f[15] - ref[15]).max() <= 2 * ULP_1E8
 
 
-@pytest.mark.parametrize("name", ["ff_pixels", "ff_map5"])
+@pytest.mark.parametrize("name", ["ff_pixels", "ff_map5", "ff_pixels_150"])
 def test_ff_pixels(oracle, name):
     d = gu.load(name)
     for i in range(int(d["n_cases"])):

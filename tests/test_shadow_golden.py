@@ -54,7 +54,7 @@ def test_nf_toy_rows(shadow):
 
 
 @pytest.mark.parametrize("packed", [False, True])
-@pytest.mark.parametrize("name", ["nf_pixels", "nf_map5"])
+@pytest.mark.parametrize("name", ["nf_pixels", "nf_map5", "nf_rx_offsets"])
 def test_nf_pixels(shadow, name, packed):
     d = gu.load(name)
     for i in range(int(d["n_cases"])):
@@ -94,7 +94,7 @@ def test_ff_rows(shadow, oracle):
 
 
 @pytest.mark.parametrize("packed", [False, True])
-@pytest.mark.parametrize("name", ["ff_pixels", "ff_map5"])
+@pytest.mark.parametrize("name", ["ff_pixels", "ff_map5", "ff_pixels_150"])
 def test_ff_pixels(shadow, oracle, name, packed):
     d = gu.load(name)
     for i in range(int(d["n_cases"])):
