@@ -270,7 +270,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "peak_source": "DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure); nominal %.1f" % NOMINAL_FP64_TFLOPS,
+                         "peak_source": "burst DFMA issue-rate probe run in this process (best of 5 x 2 ms launches; MEASURED_PEAKS.json "
+                                        "has no FP64 figure); nominal %.1f = 148 SM x 64 lanes x 2 x 1.965 GHz" % NOMINAL_FP64_TFLOPS,
                          "frac_of_nominal": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None,
                          "flop_per_unit": FLOP_PER_LAUNCHED_RAY, "units_per_launch": npix * N_SCAN ** 2, "kernel": kernel_note},
             "ray_status": int(status),

@@ -147,6 +147,8 @@ class NearFieldPlan:
         npix = src.shape[0]
         amp = np.empty(self._shape(npix)) if amp is None else amp
         phase = np.empty(self._shape(npix)) if phase is None else phase
+        if npix == 0:
+            return amp, phase, 0
         st = _lib.c_i(0)
         _lib.check(_lib.load().solat_nf_map_host(self.handle, _lib.dptr(src), npix, _lib.dptr(amp), _lib.dptr(phase),
                                                  ctypes.byref(st)))
@@ -318,6 +320,8 @@ class FarFieldPlan:
         npix = azel.shape[0]
         amp = np.empty(npix) if amp is None else amp
         phase = np.empty(npix) if phase is None else phase
+        if npix == 0:
+            return amp, phase, 0
         st = _lib.c_i(0)
         _lib.check(_lib.load().solat_ff_map_host(self.handle, _lib.dptr(azel), npix, _lib.dptr(amp), _lib.dptr(phase),
                                                  ctypes.byref(st)))

@@ -404,6 +404,49 @@ def test_ff_odd_sizes_and_edge_grids(oracle):
             _assert_pixels(a, p, oa, op)
 
 
+def test_tiny_and_empty_inputs(oracle):
+    """Degenerate sizes the reference's loops handle trivially: a 1-ray fan, a 1-pixel map, an empty pixel list,
+    a 1x1 E_rec grid, a 3-ray fan in paired mode."""
+    from solat_optics_b200 import maps
+    from solat_optics_b200 import ray_trace_int as rti
+
+    for n in (1, 2, 3):
+        tg = maps.holo_tele_geo(140.0, n)
+        out = rti.source_to_lyot_model([2.0, tg.y_ap, -3.0], tg, PlotOpts).output()
+        ref = oracle.nf_source_trace([2.0, tg.y_ap, -3.0], n)
+        np.testing.assert_allclose(np.nan_to_num(out), np.nan_to_num(ref), rtol=0, atol=RAY_TOL)
+        px, amp, ph = maps.holo_map(140.0, res=1 if n == 1 else 2, n_scan=n, device=0)
+        rx = oracle.nf_rx_trace([0, 0, 0], tg.th_fwhp, n)
+        oa, op = oracle.nf_map(px, tg.y_ap, n, rx[3], rx[4] * gu.lyot_mask(n), [tg.k])
+        _assert_pixels(amp, ph, oa, op)
+    tg = maps.holo_tele_geo(140.0, 8)
+    rx_opl, rx_w = maps.receiver_field(tg)
+    plan = maps.NearFieldPlan(tg, [tg.k], rx_opl, rx_w, device=0)
+    a, p, st = plan.run(np.zeros((0, 2)))
+    assert a.shape == (1, 0) and st == 0
+    a, p, st = maps.NearFieldPlan(tg, [tg.k], rx_opl, 0 * rx_w, device=0).run([[0.0, 0.0]])     # nothing passes the mask
+    assert a[0, 0] == 0 and p[0, 0] == 0
+    # far field
+    tgf = maps.ff_tele_geo(140, 1.32)
+    geo = oracle.ff_geo_vec(rx_y_m=-1.32)
+    one = np.array([[0.0]])
+    for n in (1, 2, 5):
+        th, phi = gu.ff_fan(n)
+        x, y, e = gu.ff_grid("wide61")
+        a, p, st = maps.FarFieldPlan(tgf, th, phi, x, y, e, device=0).run([[0.0, gu.EL0]])
+        oa, op = oracle.ff_map(geo, [0.0, gu.EL0], th, phi, x, y, e, tgf.k)
+        assert st == 0
+        if oa[0] == 0:
+            assert a[0] == 0
+        else:
+            _assert_pixels(a, p, oa, op)
+    th, phi = gu.ff_fan(9)
+    a, p, st = maps.FarFieldPlan(tgf, th, phi, one + 100.0, one + 100.0, one + 2j, device=0).run([[0.0, gu.EL0], [gu.DE, gu.EL0]])
+    oa, op = oracle.ff_map(geo, [[0.0, gu.EL0], [gu.DE, gu.EL0]], th, phi, one + 100.0, one + 100.0, one + 2j, tgf.k)
+    _assert_pixels(a, p, oa, op)          # 1x1 grid: every ray below the maximum piles into the single cell
+    assert maps.FarFieldPlan(tgf, th, phi, x, y, e, device=0).run(np.zeros((0, 2)))[0].shape == (0,)
+
+
 # ------------------------------------------------------------------------------------------------ CLI
 def test_cli_holo_sim_writes_reference_format(tmp_path):
     d = gu.load("nf_map5")
