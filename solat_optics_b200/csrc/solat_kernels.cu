@@ -96,12 +96,14 @@ struct DevBuf {
 
 struct AngleTabs {
     const double *st, *ct, *sp, *cp;   // sin/cos of theta[nth], phi[nph]
+    const float *stf, *ctf, *spf, *cpf; // single-precision copies (far-field aperture prefilter)
     int nth, nph;                      // nph == 0: paired mode, ray ii uses theta[ii], phi[ii] (phi has nth entries)
     unsigned magic;                    // ceil(2^32 / nth): r / nth == __umulhi(r, magic) (+1 fix-up) for r < 2^32 / nth
     __host__ __device__ int rays() const { return nph == 0 ? nth : nth * nph; }
 };
 struct AngleTabsOwner {
     DevBuf<double> buf;
+    DevBuf<float> fbuf;
     AngleTabs tabs;
     int init(const double* theta, int nth, const double* phi, int nph_arg, cudaStream_t s)
     {
@@ -109,9 +111,13 @@ struct AngleTabsOwner {
         std::vector<double> h(2 * (size_t)nth + 2 * (size_t)nph);
         for (int i = 0; i < nth; i++) { h[i] = sin(theta[i]); h[nth + i] = cos(theta[i]); }
         for (int j = 0; j < nph; j++) { h[2 * nth + j] = sin(phi[j]); h[2 * nth + nph + j] = cos(phi[j]); }
+        std::vector<float> hf(h.size());
+        for (size_t i = 0; i < h.size(); i++) hf[i] = (float)h[i];
         int rc = buf.upload(h.data(), h.size(), s);
+        if (!rc) rc = fbuf.upload(hf.data(), hf.size(), s);
         if (rc) return rc;
-        CK(cudaStreamSynchronize(s));   // h goes out of scope
+        CK(cudaStreamSynchronize(s));   // h, hf go out of scope
+        tabs.stf = fbuf.p; tabs.ctf = fbuf.p + nth; tabs.spf = fbuf.p + 2 * nth; tabs.cpf = fbuf.p + 2 * nth + nph;
         tabs.st = buf.p; tabs.ct = buf.p + nth; tabs.sp = buf.p + 2 * nth; tabs.cp = buf.p + 2 * nth + nph;
         tabs.nth = nth; tabs.nph = nph_arg;
         const unsigned long long rays = (unsigned long long)nth * (unsigned long long)nph;
@@ -120,6 +126,19 @@ struct AngleTabsOwner {
         return 0;
     }
 };
+
+__device__ __forceinline__ void ray_ij(const AngleTabs& a, int r, int& i, int& j)
+{
+    if (a.magic) {
+        j = (int)__umulhi((unsigned)r, a.magic);
+        i = r - j * a.nth;
+        if (i < 0) { i += a.nth; --j; }
+    } else {
+        j = r / a.nth;
+        i = r - j * a.nth;
+    }
+    if (a.nph == 0) { i = r; j = r; }
+}
 
 __device__ __forceinline__ vec3 ray_dir(const AngleTabs& a, int r)
 {
@@ -170,19 +189,19 @@ __global__ void __launch_bounds__(128) nf_rows_kernel(NfRowsParams q)
     int st;
     if (KIND == NF_RX) {
         NfRxRay ray;
-        nf_rx_ray(p0, d, q.n_si, q.n_vac, ray);
+        nf_rx_ray(K_COEF, p0, d, q.n_si, q.n_vac, ray);
         int j = r / q.ang.nth, i = r - j * q.ang.nth;
         if (q.ang.nph == 0) { i = r; j = r; }
         pack_nf_rx_rows(ray, p0, q.theta[i] - q.th_mean, q.phi[j] - q.ph_mean, q.inv_2sig2, rows);
         st = ray.status;
     } else if (KIND == NF_SOURCE) {
         NfSourceRay ray;
-        nf_source_ray(p0, d, q.n_si, q.n_vac, ray);
+        nf_source_ray(K_COEF, p0, d, q.n_si, q.n_vac, ray);
         pack_nf_source_rows(ray, p0, q.n_si, q.n_vac, rows);
         st = ray.status;
     } else {
         NfToyRay ray;
-        nf_toy_ray(p0, d, q.y_ap, q.n_si, q.n_vac, ray);
+        nf_toy_ray(K_COEF, p0, d, q.y_ap, q.n_si, q.n_vac, ray);
         pack_nf_toy_rows(ray, p0, q.inv_2sig2, rows);
         st = ray.status;
     }
@@ -247,6 +266,7 @@ template <int NF, int NT>
 __global__ void __launch_bounds__(NF_T, SOLAT_NF_MINB) nf_map_kernel(NfMapParams q)
 {
     constexpr int NC = NF * NT;
+    const Coef& sC = K_COEF;   // constant bank; a shared-memory copy measured 2-4 % slower (profiles/r01_variants.md)
     const int pix = blockIdx.x / q.tiles, tile = blockIdx.x - pix * q.tiles;
     const vec3 p0 = mk(__ldg(q.src_xz + 2 * pix), q.y_ap, __ldg(q.src_xz + 2 * pix + 1));
     double re[NC], im[NC];
@@ -257,7 +277,7 @@ __global__ void __launch_bounds__(NF_T, SOLAT_NF_MINB) nf_map_kernel(NfMapParams
     for (int a = tile * q.tile_len + threadIdx.x; a < q_end; a += NF_T) {
         const int r = __ldg(q.act_idx + a);
         NfSourceRay ray;
-        nf_source_ray(p0, ray_dir(q.ang, r), q.n_si, q.n_vac, ray);
+        nf_source_ray(sC, p0, ray_dir(q.ang, r), q.n_si, q.n_vac, ray);
         st |= ray.status;
         if (ray.valid) {
 #pragma unroll
@@ -334,7 +354,7 @@ __global__ void __launch_bounds__(128) ff_rows_kernel(FfRowsParams q)
     __shared__ double t2e[9];
     const FfGeom g = to_geom(q.g);
     if (threadIdx.x == 0) {
-        ff_build_frames(g, q.el, q.az, fr);
+        ff_build_frames(K_COEF, g, q.el, q.az, fr);
         for (int i = 0; i < 9; i++) t2e[i] = fr.t2.a[i];
         if (g.src[2] != 0) for (int i = 0; i < 3; i++) t2e[3 * i + 2] /= cos(atan(1.0 / 3.0));   // saf:828-829
     }
@@ -353,10 +373,10 @@ __global__ void __launch_bounds__(128) ff_rows_kernel(FfRowsParams q)
         const vec3 d = ray_dir(q.ang, r);
         vec3 Pa;
         double t_ap;
-        if (ff_aperture(g, fr, d, t_ap, Pa)) {
+        if (ff_aperture(K_COEF, g, fr, d, t_ap, Pa)) {
             FfRay ray;
             if (STAGE1) {
-                ff_ray_trace<true, false>(fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+                ff_ray_trace<true, false>(K_COEF, fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
                 rows[0] = ray.m2.x; rows[1] = ray.m2.y; rows[2] = ray.m2.z;
                 rows[3] = ray.m1.x; rows[4] = ray.m1.y; rows[5] = ray.m1.z;
             } else {
@@ -367,7 +387,7 @@ __global__ void __launch_bounds__(128) ff_rows_kernel(FfRowsParams q)
                 c = q.pan2 + q.pidx2[r];
                 e2.a = c[2 * q.np2]; e2.b = c[3 * q.np2]; e2.c = c[4 * q.np2]; e2.d = c[5 * q.np2]; e2.e = c[6 * q.np2];
                 e2.x0 = c[8 * q.np2]; e2.y0 = c[9 * q.np2];
-                ff_ray_trace<false, true>(fr, d, t_ap, Pa, g.foc_y, &e1, &e2, t2e, ray);
+                ff_ray_trace<false, true>(K_COEF, fr, d, t_ap, Pa, g.foc_y, &e1, &e2, t2e, ray);
                 pack_ff_rows(ray, q.centre, rows);
             }
             st = ray.status;
@@ -438,7 +458,8 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
     const FfGeom g = to_geom(q.g);
-    if (tid == 0) ff_build_frames(g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
+    const Coef& sC = K_COEF;   // constant bank; a shared-memory copy measured 4 % slower (profiles/r01_variants.md)
+    if (tid == 0) ff_build_frames(K_COEF, g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
     for (int c = tid; c < cells; c += FF_T) win[c] = 0ull;
     __syncthreads();
 
@@ -454,9 +475,17 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
             const int r = chunk * 32 + lane;
             bool ok = false;
             if (r < n_rays) {
-                vec3 Pa;
-                double t_ap;
-                ok = ff_aperture(g, *fr, ray_dir(q.ang, r), t_ap, Pa);
+                // FP32 prefilter on the FMA pipe; only rays within ~0.02 mm of the rim need the FP64 test
+                int i, j;
+                ray_ij(q.ang, r, i, j);
+                const float stf = __ldg(q.ang.stf + i);
+                const int v = ff_aperture_coarse(*fr, stf * __ldg(q.ang.cpf + j), stf * __ldg(q.ang.spf + j), __ldg(q.ang.ctf + i));
+                ok = v > 0;
+                if (v < 0) {
+                    vec3 Pa;
+                    double t_ap;
+                    ok = ff_aperture(sC, g, *fr, ray_dir(q.ang, r), t_ap, Pa);
+                }
             }
             const unsigned m = __ballot_sync(0xffffffffu, ok);
             if (ok) wq[cnt + __popc(m & ((1u << lane) - 1u))] = r;
@@ -478,9 +507,9 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
             const vec3t<d2> d = ray_dir2(q.ang, r0, r1 >= 0 ? r1 : r0);
             vec3t<d2> Pa;
             d2 t_ap;
-            ff_aperture(g, *fr, d, t_ap, Pa);
+            ff_aperture(sC, g, *fr, d, t_ap, Pa);
             FfRayT<d2> ray;
-            ff_ray_trace<false, false, d2>(*fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+            ff_ray_trace<false, false, d2>(sC, *fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
             st |= ray.status.a | (r1 >= 0 ? ray.status.b : 0);
             const int rr[2] = {r0, r1};
             const double oo[2] = {ray.opl.a, ray.opl.b}, fx[2] = {ray.foc.x.a, ray.foc.x.b}, fz[2] = {ray.foc.z.a, ray.foc.z.b};
@@ -490,9 +519,9 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
             const vec3 d = ray_dir(q.ang, r0);
             vec3 Pa;
             double t_ap;
-            ff_aperture(g, *fr, d, t_ap, Pa);
+            ff_aperture(sC, g, *fr, d, t_ap, Pa);
             FfRay ray;
-            ff_ray_trace<false, false, double>(*fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+            ff_ray_trace<false, false, double>(sC, *fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
             st |= ray.status;
             const int rr[1] = {r0};
             const double oo[1] = {ray.opl}, fx[1] = {ray.foc.x}, fz[1] = {ray.foc.z};

@@ -268,23 +268,36 @@ constexpr double LENS1_Y = 975.08;                                             /
 constexpr double LENS2_Y = 592.76;                                             // ot_geo.py:69
 constexpr double LENS3_Y = 180.8 - ((2.5 + 1.513) - (35.16 - 32.19));          // ot_geo.py:70
 constexpr double LYOT_Y = 453.62;                                              // ot_geo.py:71
-// plane offsets: [0] 1B (ot_geo.py:166), [1] 2B (:277), [2] Lyot (:526)
-SOLAT_TABLE double K_NF_PLANE[] = {LENS1_Y, LENS2_Y, LYOT_Y};
-#define Y_1B (K_NF_PLANE[0])
-#define Y_2B (K_NF_PLANE[1])
-#define Y_LYOT (K_NF_PLANE[2])
 // ot_geo.py:85-91, :197-203, :301-307, :323-329 with the offsets of :178, :289, :478, :490
 enum { SURF_1A = 0, SURF_2A = 1, SURF_3A = 2, SURF_3B = 3 };
+enum { PLANE_1B = 0, PLANE_2B = 1, PLANE_LYOT = 2 };      // ot_geo.py:166, :277, :526
 SOLAT_TABLE AsphereF K_ASPHF[4] = {
     make_asphere_f(-1510.61, 12.0966, -5.876941e-5, 1.769198e-9, -1.310183e-15, 1.994766e-19),
     make_asphere_f(-871.25, -10.201256, -1.147640e-04, 1.103643e-10, -2.969608e-14, 5.980271e-19),
     make_asphere_f(6608.30, 414.142695, -2.981594e-06, 3.955202e-10, 3.180727e-16, 0.0),
     make_asphere_f(604.44, -3.177341, 2.366829e-05, -1.000417e-10, -6.565681e-15, 0.0)};
-SOLAT_TABLE Asphere K_ASPH[4] = {
-    make_asphere(-1510.61, 12.0966, -5.876941e-5, 1.769198e-9, -1.310183e-15, 1.994766e-19, LENS1_Y - 19.32),
-    make_asphere(-871.25, -10.201256, -1.147640e-04, 1.103643e-10, -2.969608e-14, 5.980271e-19, LENS2_Y - 26.47),
-    make_asphere(6608.30, 414.142695, -2.981594e-06, 3.955202e-10, 3.180727e-16, 0.0, LENS3_Y),
-    make_asphere(604.44, -3.177341, 2.366829e-05, -1.000417e-10, -6.565681e-15, 0.0, LENS3_Y + 35.16)};
+
+// All FP64 coefficients of the path in one table in the constant bank (every routine takes it by reference, so a
+// kernel could stage it elsewhere: a shared-memory copy was measured 2-4 % slower on B200, profiles/r01_variants.md).
+struct Coef {
+    double m1[14];        // LAT primary,  rows i = 0,2,4,6 of a1 (latrt_geo.py:55-61) as polynomials in v = y/R
+    double m2[18];        // LAT secondary, rows of a2 (latrt_geo.py:63-71)
+    double ff[5];         // 1/R_N, 2/R_N, y_cent_m1 (saf:19), aperture radius^2 (saf:378), aperture plane z (latrt_geo.py:244)
+    double plane[3];      // near-field plane offsets 1B, 2B, Lyot
+    Asphere asph[4];      // near-field aspheres 1A, 2A, 3A, 3B
+};
+SOLAT_TABLE Coef K_COEF = {
+    {/* H0 */ -57.74022, 1.5373825, 1.154294, -0.441762, 0.0906601, /* P2 */ -72.17349, 1.8691899, 2.8859421, -1.026471, 0.2610568,
+     /* P4 */ 1.8083973, -0.603195, 0.2177414, /* P6 */ 0.0394559},
+    {/* H0 */ 103.90461, 6.6513025, 2.8405781, -0.7819705, -0.0400483, 0.0896645,
+     /* P2 */ 115.44758, 7.3024355, 5.7640389, -1.578144, -0.0354326, 0.2781226,
+     /* P4 */ 2.9130983, -0.8104051, -0.0185283, 0.2626023, /* P6 */ -0.0250794, 0.0709672},
+    {1.0 / 3000.0, 2.0 / 3000.0, -7201.003729431267, 3e3 * 3e3, 4000.0},
+    {LENS1_Y, LENS2_Y, LYOT_Y},
+    {make_asphere(-1510.61, 12.0966, -5.876941e-5, 1.769198e-9, -1.310183e-15, 1.994766e-19, LENS1_Y - 19.32),
+     make_asphere(-871.25, -10.201256, -1.147640e-04, 1.103643e-10, -2.969608e-14, 5.980271e-19, LENS2_Y - 26.47),
+     make_asphere(6608.30, 414.142695, -2.981594e-06, 3.955202e-10, 3.180727e-16, 0.0, LENS3_Y),
+     make_asphere(604.44, -3.177341, 2.366829e-05, -1.000417e-10, -6.565681e-15, 0.0, LENS3_Y + 35.16)}};
 
 // Newton schedule shared by all curved surfaces (DESIGN.md "Mixed-precision Newton"):
 //   update 1 from the vertex-plane hit is evaluated in FP32 on the otherwise idle FMA pipe -- its own
@@ -294,12 +307,12 @@ SOLAT_TABLE Asphere K_ASPH[4] = {
 // Hit of the ray P + t d with asphere S.  On return H is the hit point, N the unit normal in the
 // telescope frame with N.y > 0 (= reference n_hat rotated back), t the ray parameter.
 template <int S, class R>
-SOLAT_HD typename Pack<R>::I asphere_hit(const vec3t<R>& P, const vec3t<R>& d, double lo, double hi, R& t, vec3t<R>& H,
-                                         vec3t<R>& N)
+SOLAT_HD typename Pack<R>::I asphere_hit(const Coef& C, const vec3t<R>& P, const vec3t<R>& d, double lo, double hi, R& t,
+                                         vec3t<R>& H, vec3t<R>& N)
 {
     using F = typename Pack<R>::F;
     using I = typename Pack<R>::I;
-    const Asphere& A = K_ASPH[S];
+    const Asphere& A = C.asph[S];
     const R py = P.y + A.y0;
     t = -py * rcp_step(d.y);
     {   // coarse update in single precision; on the vertex plane the residual is just -sag
@@ -360,16 +373,16 @@ struct NfSourceRayT {
 };
 using NfSourceRay = NfSourceRayT<double>;
 template <class R>
-SOLAT_HD void nf_source_ray(const vec3t<R>& p0, const vec3t<R>& d0, double n_si, double n_vac, NfSourceRayT<R>& r)
+SOLAT_HD void nf_source_ray(const Coef& C, const vec3t<R>& p0, const vec3t<R>& d0, double n_si, double n_vac, NfSourceRayT<R>& r)
 {
     using I = typename Pack<R>::I;
     using B = typename Pack<R>::B;
     const double mu_in = n_vac / n_si, mu_out = n_si / n_vac;
     R t1, t2, t3, t4, t5;
     vec3t<R> N, d;
-    I st = plane_hit(p0, d0, Y_1B, 5.0, 14000.0, t1, r.p1b);                   // rti:967
+    I st = plane_hit(p0, d0, C.plane[PLANE_1B], 5.0, 14000.0, t1, r.p1b);                   // rti:967
     d = refract_flat(d0, -1.0, mu_in);                                          // rti:992
-    const I st1a = asphere_hit<SURF_1A>(r.p1b, d, 1.0, 900.0, t2, r.p1a, N);   // rti:1033
+    const I st1a = asphere_hit<SURF_1A>(C, r.p1b, d, 1.0, 900.0, t2, r.p1a, N);   // rti:1033
     // rti:1086 (radius >= 196 -> zero column; compared squared).  A NaN radius means the iterate left the domain of the conic
     // (r > 417 mm), where the reference's root function substitutes sag = 0 and then vignettes too.
     B alive = lt(fma(r.p1a.x, r.p1a.x, r.p1a.z * r.p1a.z), R(196.0 * 196.0));
@@ -377,14 +390,14 @@ SOLAT_HD void nf_source_ray(const vec3t<R>& p0, const vec3t<R>& d0, double n_si,
     if (!any(alive)) return;
     st |= imask(alive, st1a);
     d = refract(d, neg(N), mu_out);                                             // rti:1058
-    st |= imask(alive, plane_hit(r.p1a, d, Y_2B, 5.0, 600.0, t3, r.p2b));      // rti:1130
+    st |= imask(alive, plane_hit(r.p1a, d, C.plane[PLANE_2B], 5.0, 600.0, t3, r.p2b));      // rti:1130
     alive = band(alive, lt(fma(r.p2b.x, r.p2b.x, r.p2b.z * r.p2b.z), R(176.0 * 176.0)));   // rti:1177
     r.valid = alive; r.status = st;
     if (!any(alive)) return;
     d = refract_flat(d, -1.0, mu_in);                                           // rti:1154 (-n_hat)
-    st |= imask(alive, asphere_hit<SURF_2A>(r.p2b, d, 0.0, 100.0, t4, r.p2a, N));   // rti:1228
+    st |= imask(alive, asphere_hit<SURF_2A>(C, r.p2b, d, 0.0, 100.0, t4, r.p2a, N));   // rti:1228
     d = refract(d, neg(N), mu_out);                                             // rti:1254
-    st |= imask(alive, plane_hit(r.p2a, d, Y_LYOT, 10.0, 900.0, t5, r.lyot));  // rti:1295
+    st |= imask(alive, plane_hit(r.p2a, d, C.plane[PLANE_LYOT], 10.0, 900.0, t5, r.lyot));  // rti:1295
     r.d_out = d;
     const R opl = (t1) + (t2 * n_si) + (t3) + (t4 * n_si) + t5;                 // rti:1341-1343
     st |= flag(band(alive, is_nan(opl)), ST_NAN);
@@ -403,15 +416,15 @@ SOLAT_HD double dist3(const vec3& a, const vec3& b)
     double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
     return sqrt(fma(dx, dx, fma(dy, dy, dz * dz)));
 }
-SOLAT_HD void nf_rx_ray(const vec3& p0, const vec3& d0, double n_si, double n_vac, NfRxRay& r)
+SOLAT_HD void nf_rx_ray(const Coef& C, const vec3& p0, const vec3& d0, double n_si, double n_vac, NfRxRay& r)
 {
     double t1, t2, t3;
     vec3 N, d;
-    int st = asphere_hit<SURF_3A>(p0, d0, 40.0, 700.0, t1, r.p3a, N);          // rti:653
+    int st = asphere_hit<SURF_3A>(C, p0, d0, 40.0, 700.0, t1, r.p3a, N);          // rti:653
     d = refract(d0, N, n_vac / n_si);                                           // rti:679
-    st |= asphere_hit<SURF_3B>(r.p3a, d, 5.0, 200.0, t2, r.p3b, N);            // rti:719
+    st |= asphere_hit<SURF_3B>(C, r.p3a, d, 5.0, 200.0, t2, r.p3b, N);            // rti:719
     d = refract(d, N, n_si / n_vac);                                            // rti:743
-    st |= plane_hit(r.p3b, d, Y_LYOT, 1.0, 2000.0, t3, r.lyot);                // rti:784
+    st |= plane_hit(r.p3b, d, C.plane[PLANE_LYOT], 1.0, 2000.0, t3, r.lyot);                // rti:784
     r.d_out = d;
     // rti:848: Euclidean leg lengths, n_si inside lens 3
     r.opl = (dist3(r.p3b, r.p3a) * n_si) + dist3(r.p3a, p0) + dist3(r.lyot, r.p3b);
@@ -425,23 +438,23 @@ struct NfToyRay {
     double opl;
     int status;
 };
-SOLAT_HD void nf_toy_ray(const vec3& p0, const vec3& d0, double y_ap, double n_si, double n_vac, NfToyRay& r)
+SOLAT_HD void nf_toy_ray(const Coef& C, const vec3& p0, const vec3& d0, double y_ap, double n_si, double n_vac, NfToyRay& r)
 {
     const double mu_in = n_vac / n_si, mu_out = n_si / n_vac;
     double t;
     vec3 N, d;
-    int st = asphere_hit<SURF_3A>(p0, d0, 2.0, 1600.0, t, r.p3a, N);           // rti:111
+    int st = asphere_hit<SURF_3A>(C, p0, d0, 2.0, 1600.0, t, r.p3a, N);           // rti:111
     r.d_first = d0;
     d = refract(d0, N, mu_in);                                                  // rti:138
-    st |= asphere_hit<SURF_3B>(r.p3a, d, 5.0, 200.0, t, r.p3b, N);             // rti:178
+    st |= asphere_hit<SURF_3B>(C, r.p3a, d, 5.0, 200.0, t, r.p3b, N);             // rti:178
     d = refract(d, N, mu_out);                                                  // rti:202
-    st |= asphere_hit<SURF_2A>(r.p3b, d, 10.0, 2000.0, t, r.p2a, N);           // rti:243
+    st |= asphere_hit<SURF_2A>(C, r.p3b, d, 10.0, 2000.0, t, r.p2a, N);           // rti:243
     d = refract(d, N, mu_in);                                                   // rti:268
-    st |= plane_hit(r.p2a, d, Y_2B, 5.0, 400.0, t, r.p2b);                     // rti:308
+    st |= plane_hit(r.p2a, d, C.plane[PLANE_2B], 5.0, 400.0, t, r.p2b);                     // rti:308
     d = refract_flat(d, 1.0, mu_out);                                           // rti:332
-    st |= asphere_hit<SURF_1A>(r.p2b, d, 5.0, 500.0, t, r.p1a, N);             // rti:373
+    st |= asphere_hit<SURF_1A>(C, r.p2b, d, 5.0, 500.0, t, r.p1a, N);             // rti:373
     d = refract(d, N, mu_in);                                                   // rti:398
-    st |= plane_hit(r.p1a, d, Y_1B, 5.0, 200.0, t, r.p1b);                     // rti:440
+    st |= plane_hit(r.p1a, d, C.plane[PLANE_1B], 5.0, 200.0, t, r.p1b);                     // rti:440
     // rti:465: snell(n_si, n_vac, N_hat, -tan) with the 1B normal (tele frame (0,-1,0))
     d = refract_flat(neg(d), -1.0, mu_out);
     r.d_out = d;
@@ -458,22 +471,9 @@ SOLAT_HD void nf_toy_ray(const vec3& p0, const vec3& d0, double y_ap, double n_s
 // Only even powers of x occur; Horner in v = y/R per power of u^2.
 // ------------------------------------------------------------------------------------------
 constexpr double FF_RN = 3000.0;
-// [0] 1/R_N, [1] 2/R_N, [2] y_cent_m1 (saf:19), [3] aperture radius^2 (saf:378), [4] aperture plane z (latrt_geo.py:244)
-SOLAT_TABLE double K_FF[] = {1.0 / 3000.0, 2.0 / 3000.0, -7201.003729431267, 3e3 * 3e3, 4000.0};
-#define Y_CENT_M1 (K_FF[2])
-
-// Horner tables: rows i = 0, 2, 4, 6 of a1 / a2 (latrt_geo.py:55-61, :63-71) as polynomials in v = y/R.
-// z = P0 + w (P2 + w (P4 + w P6)), w = (x/R)^2, P0 = v^2 H0(v).
-SOLAT_TABLE double K_M1[] = {
-    /* H0 [0..4]   */ -57.74022, 1.5373825, 1.154294, -0.441762, 0.0906601,
-    /* P2 [5..9]   */ -72.17349, 1.8691899, 2.8859421, -1.026471, 0.2610568,
-    /* P4 [10..12] */ 1.8083973, -0.603195, 0.2177414,
-    /* P6 [13]     */ 0.0394559};
-SOLAT_TABLE double K_M2[] = {
-    /* H0 [0..5]   */ 103.90461, 6.6513025, 2.8405781, -0.7819705, -0.0400483, 0.0896645,
-    /* P2 [6..11]  */ 115.44758, 7.3024355, 5.7640389, -1.578144, -0.0354326, 0.2781226,
-    /* P4 [12..15] */ 2.9130983, -0.8104051, -0.0185283, 0.2626023,
-    /* P6 [16..17] */ -0.0250794, 0.0709672};
+// Coefficient layout of Coef::m1 / Coef::m2: rows i = 0, 2, 4, 6 of a1 / a2 as polynomials in v = y/R:
+// z = P0 + w (P2 + w (P4 + w P6)), w = (x/R)^2, P0 = v^2 H0(v).   m1: H0 [0..4] P2 [5..9] P4 [10..12] P6 [13];
+// m2: H0 [0..5] P2 [6..11] P4 [12..15] P6 [16..17].
 // single-precision copies (same layout) for the coarse first Newton update
 SOLAT_TABLE float K_M1F[] = {-57.74022f, 1.5373825f, 1.154294f, -0.441762f, 0.0906601f, -72.17349f, 1.8691899f,
                              2.8859421f, -1.026471f, 0.2610568f, 1.8083973f, -0.603195f, 0.2177414f, 0.0394559f};
@@ -520,9 +520,9 @@ SOLAT_TABLE float K_M2F[] = {103.90461f, 6.6513025f, 2.8405781f, -0.7819705f, -0
 
 // z and its partials wrt the LOCAL coordinates x, y (mm); M = 1 primary, 2 secondary
 template <int M, class R>
-SOLAT_HD void mirror_sag(R x, R y, R& z, R& zx, R& zy)
+SOLAT_HD void mirror_sag(const Coef& C, R x, R y, R& z, R& zx, R& zy)
 {
-    if (M == 1) { SOLAT_M1_BODY(R, fma, K_M1, K_FF[0], K_FF[1]) } else { SOLAT_M2_BODY(R, fma, K_M2, K_FF[0], K_FF[1]) }
+    if (M == 1) { SOLAT_M1_BODY(R, fma, C.m1, C.ff[0], C.ff[1]) } else { SOLAT_M2_BODY(R, fma, C.m2, C.ff[0], C.ff[1]) }
 }
 template <int M, class F>
 SOLAT_HD void mirror_sag_f(F x, F y, F& z, F& zx, F& zy)
@@ -568,6 +568,7 @@ struct FfFrames {
     double foc_row[3];     // second row of R(+el,+az)
     double foc_off;        // C.y - foc_row.C
     double centre[3];      // focal-plane centre, saf:323-339
+    float apf[8];          // single-precision copy for the aperture prefilter: ap_row[3], ap_num, src.x, src.y - y_cent, R^2, margin
 };
 
 SOLAT_HD void mat3_mul(const double* A, const double* B, double* C)
@@ -583,7 +584,7 @@ SOLAT_HD void rot_el_az(double el, double az, double* R)
     R[3] = 0.0; R[4] = ce;       R[5] = -se;
     R[6] = -sa; R[7] = ca * se;  R[8] = ca * ce;
 }
-SOLAT_HD void ff_build_frames(const FfGeom& g, double el, double az, FfFrames& f)
+SOLAT_HD void ff_build_frames(const Coef& C_, const FfGeom& g, double el, double az, FfFrames& f)
 {
     double Rm[9], Rp[9];
     rot_el_az(-el, -az, Rm);
@@ -591,7 +592,7 @@ SOLAT_HD void ff_build_frames(const FfGeom& g, double el, double az, FfFrames& f
     const double C[3] = {g.rotc[0], g.rotc[1], g.rotc[2]};
     // aperture plane
     f.ap_row[0] = Rm[6]; f.ap_row[1] = Rm[7]; f.ap_row[2] = Rm[8];
-    f.ap_num = K_FF[4] - C[2] - (Rm[6] * (g.src[0] - C[0]) + Rm[7] * (g.src[1] - C[1]) + Rm[8] * (g.src[2] - C[2]));
+    f.ap_num = C_.ff[4] - C[2] - (Rm[6] * (g.src[0] - C[0]) + Rm[7] * (g.src[1] - C[1]) + Rm[8] * (g.src[2] - C[2]));
     // F1 = diag(-1,1,-1) Rx(-th1), F2 = diag(-1,-1,1) Rx(-th2)
     const double c1 = cos(g.th_1), s1 = sin(g.th_1), c2 = cos(g.th2), s2 = sin(g.th2);
     const double F1[9] = {-1, 0, 0, 0, c1, s1, 0, s1, -c1};
@@ -612,6 +613,11 @@ SOLAT_HD void ff_build_frames(const FfGeom& g, double el, double az, FfFrames& f
     mat3_mul(Rp, F2t, f.b2);
     f.foc_row[0] = Rp[3]; f.foc_row[1] = Rp[4]; f.foc_row[2] = Rp[5];
     f.foc_off = C[1] - (Rp[3] * C[0] + Rp[4] * C[1] + Rp[5] * C[2]);
+    f.apf[0] = (float)f.ap_row[0]; f.apf[1] = (float)f.ap_row[1]; f.apf[2] = (float)f.ap_row[2]; f.apf[3] = (float)f.ap_num;
+    f.apf[4] = (float)g.src[0]; f.apf[5] = (float)(g.src[1] - C_.ff[2]); f.apf[6] = (float)C_.ff[3];
+    // |r^2 - R^2| below this is left to the FP64 test: FP32 carries ~3e-7 relative on a ~5 m lever arm, i.e.
+    // ~2e-3 mm in radius, 10 mm^2 in r^2; the margin is 20x that (an annulus holding ~1e-5 of the rays)
+    f.apf[7] = 2.0e-5f * (float)C_.ff[3];
     // Focal centre (saf:323-339): means over the r < 3600 mm part of row 50 / column 50 of a 100x100 grid on
     // +-4000 mm pushed through foc_into_tele(el, az) (latrt_geo.py:248-258).  The grid is symmetric about 0, so
     // the masked mean of the running coordinate is 0 (to the reference's own 1e-12 mm rounding) and the means
@@ -632,7 +638,7 @@ struct PanelErr {
 // the normal (the last step is ~1e-11 mm, so the normal is exact to 1e-16).  PE (scalar rays only): optional
 // panel error, evaluated along its own affine image (pe + t de) of the ray (saf:676-703, :820-852).
 template <int M, bool PANEL, class R>
-SOLAT_HD typename Pack<R>::I mirror_hit(const vec3t<R>& P, const vec3t<R>& D, double lo, double hi, const PanelErr* pe,
+SOLAT_HD typename Pack<R>::I mirror_hit(const Coef& C, const vec3t<R>& P, const vec3t<R>& D, double lo, double hi, const PanelErr* pe,
                                         const vec3t<R>& pE, const vec3t<R>& dE, R& t, vec3t<R>& H, vec3t<R>& N)
 {
     using F = typename Pack<R>::F;
@@ -648,7 +654,7 @@ SOLAT_HD typename Pack<R>::I mirror_hit(const vec3t<R>& P, const vec3t<R>& D, do
     R dt = R(0.0), z, zx, zy;
     auto update = [&]() {
         const R x = fma(D.x, t, P.x), y = fma(D.y, t, P.y);
-        mirror_sag<M, R>(x, y, z, zx, zy);
+        mirror_sag<M, R>(C, x, y, z, zx, zy);
         R f = fma(D.z, t, P.z) - z;
         R fp = D.z - fma(zx, D.x, zy * D.y);
         if (PANEL) {
@@ -665,7 +671,7 @@ SOLAT_HD typename Pack<R>::I mirror_hit(const vec3t<R>& P, const vec3t<R>& D, do
     update();                                             // ~1e-11 mm on nominal rays
     for (int it = 3; any(gt(fabs(dt), R(1e-8))) && it < 12; ++it) update();   // off-nominal rays only
     H = axpy(P, D, t);
-    if (PANEL) mirror_sag<M, R>(H.x, H.y, z, zx, zy);   // reference normal = ideal-mirror gradient (saf:718-720, :869-871)
+    if (PANEL) mirror_sag<M, R>(C, H.x, H.y, z, zx, zy);   // reference normal = ideal-mirror gradient (saf:718-720, :869-871)
     const R nn = rsqrt_fast(fma(zx, zx, fma(zy, zy, R(1.0))));
     N = mk<R>(-zx * nn, -zy * nn, nn);
     I st = imask(bnot(is_nan(dt)), flag(bnot(le(fabs(dt), R(1e-8))), ST_NOCONV)) | flag(is_nan(dt), ST_NAN);
@@ -676,12 +682,24 @@ SOLAT_HD typename Pack<R>::I mirror_hit(const vec3t<R>& P, const vec3t<R>& D, do
 // cheap first stage of every far-field ray: aperture-plane hit and the 3 m radius test
 // (saf:359-379 == :644-665).  Returns the lanes that continue.
 template <class R>
-SOLAT_HD typename Pack<R>::B ff_aperture(const FfGeom& g, const FfFrames& f, const vec3t<R>& d, R& t_ap, vec3t<R>& Pa)
+SOLAT_HD typename Pack<R>::B ff_aperture(const Coef& C, const FfGeom& g, const FfFrames& f, const vec3t<R>& d, R& t_ap, vec3t<R>& Pa)
 {
     t_ap = R(f.ap_num) * rcp_fast(fma(R(f.ap_row[0]), d.x, fma(R(f.ap_row[1]), d.y, R(f.ap_row[2]) * d.z)));
     Pa = mk<R>(fma(d.x, t_ap, R(g.src[0])), fma(d.y, t_ap, R(g.src[1])), fma(d.z, t_ap, R(g.src[2])));
-    const R dy = Pa.y - R(Y_CENT_M1);
-    return bnot(gt(fma(Pa.x, Pa.x, dy * dy), R(K_FF[3])));
+    const R dy = Pa.y - R(C.ff[2]);
+    return bnot(gt(fma(Pa.x, Pa.x, dy * dy), R(C.ff[3])));
+}
+
+// Single-precision prefilter of the same test: +1 inside, 0 outside, -1 too close to the rim to call in FP32
+// (the caller then runs ff_aperture in FP64, so the accepted set is exactly the FP64 one).
+SOLAT_HD int ff_aperture_coarse(const FfFrames& f, float dx, float dy, float dz)
+{
+    const float den = fmaf(f.apf[0], dx, fmaf(f.apf[1], dy, f.apf[2] * dz));
+    const float t = div_f(f.apf[3], den);
+    const float xa = fmaf(dx, t, f.apf[4]), ya = fmaf(dy, t, f.apf[5]);
+    const float e = fmaf(xa, xa, ya * ya) - f.apf[6];
+    if (!(fabsf(e) > f.apf[7])) return -1;
+    return e > 0.0f ? 0 : 1;
 }
 
 template <class R>
@@ -694,7 +712,7 @@ using FfRay = FfRayT<double>;
 // Remainder of the ray after ff_aperture.  STAGE1 = ray_mirror_pts brackets (saf:396,490), no focal
 // plane; otherwise aperature_fields_from_panel_model brackets (saf:706,855,962).
 template <bool STAGE1, bool PANEL, class R>
-SOLAT_HD void ff_ray_trace(const FfFrames& f, const vec3t<R>& d, R t_ap, const vec3t<R>& Pa, double foc_y,
+SOLAT_HD void ff_ray_trace(const Coef& C, const FfFrames& f, const vec3t<R>& d, R t_ap, const vec3t<R>& Pa, double foc_y,
                            const PanelErr* pe1, const PanelErr* pe2, const double* t2e_a, FfRayT<R>& r)
 {
     using I = typename Pack<R>::I;
@@ -703,7 +721,7 @@ SOLAT_HD void ff_ray_trace(const FfFrames& f, const vec3t<R>& d, R t_ap, const v
     const vec3t<R> none = mk<R>(R(0.0), R(0.0), R(0.0));
     // M1
     const vec3t<R> p1 = apply(f.t1, Pa), d1 = apply_lin(f.t1.a, d);
-    I st = mirror_hit<1, PANEL, R>(p1, d1, 0.0, STAGE1 ? 5e4 : 1e4, pe1, p1, d1, t1, H, N);
+    I st = mirror_hit<1, PANEL, R>(C, p1, d1, 0.0, STAGE1 ? 5e4 : 1e4, pe1, p1, d1, t1, H, N);
     r.m1 = axpy(Pa, d, t1);
     const vec3t<R> dt2 = apply_lin(f.b1, reflect(d1, N));                       // saf:208-257
     // M2
@@ -715,7 +733,7 @@ SOLAT_HD void ff_ray_trace(const FfFrames& f, const vec3t<R>& d, R t_ap, const v
         te.b[0] = f.t2.b[0]; te.b[1] = f.t2.b[1]; te.b[2] = f.t2.b[2];
         pE = apply(te, r.m1); dE = apply_lin(te.a, dt2);
     }
-    st |= mirror_hit<2, PANEL, R>(p2, d2, STAGE1 ? 0.0 : 1e3, STAGE1 ? 20e3 : 13e3, pe2, pE, dE, t2, H, N);
+    st |= mirror_hit<2, PANEL, R>(C, p2, d2, STAGE1 ? 0.0 : 1e3, STAGE1 ? 20e3 : 13e3, pe2, pE, dE, t2, H, N);
     r.m2 = axpy(r.m1, dt2, t2);
     r.opl = R(0.0);
     if (!STAGE1) {

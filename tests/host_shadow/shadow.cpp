@@ -19,7 +19,7 @@ API int shadow_nf_source_rows(const double* p, const double* th, int nth, const 
         const int i = r % nth, j = r / nth;
         NfSourceRay ray;
         vec3 p0 = mk(p[0], p[1], p[2]);
-        nf_source_ray(p0, launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), n_si, n_vac, ray);
+        nf_source_ray(K_COEF, p0, launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), n_si, n_vac, ray);
         double rows[26];
         pack_nf_source_rows(ray, p0, n_si, n_vac, rows);
         for (int k = 0; k < 26; k++) out[(size_t)k * n + r] = rows[k];
@@ -38,7 +38,7 @@ API int shadow_nf_rx_rows(const double* p, const double* th, int nth, const doub
         const int i = r % nth, j = r / nth;
         NfRxRay ray;
         vec3 p0 = mk(p[0], p[1], p[2]);
-        nf_rx_ray(p0, launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), n_si, n_vac, ray);
+        nf_rx_ray(K_COEF, p0, launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), n_si, n_vac, ray);
         double rows[20];
         pack_nf_rx_rows(ray, p0, th[i] - th_mean, ph[j] - ph_mean, 0.5 / (sig * sig), rows);
         for (int k = 0; k < 20; k++) out[(size_t)k * n + r] = rows[k];
@@ -56,7 +56,7 @@ API int shadow_nf_toy_rows(const double* p, const double* th, int nth, const dou
         const int i = r % nth, j = r / nth;
         NfToyRay ray;
         vec3 p0 = mk(p[0], p[1], p[2]);
-        nf_toy_ray(p0, launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), y_ap, n_si, n_vac, ray);
+        nf_toy_ray(K_COEF, p0, launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), y_ap, n_si, n_vac, ray);
         double rows[32];
         pack_nf_toy_rows(ray, p0, 0.5 / (sig * sig), rows);
         for (int k = 0; k < 32; k++) out[(size_t)k * n + r] = rows[k];
@@ -75,7 +75,7 @@ API int shadow_nf_pixel(const double* p, const double* th, int nth, const double
         if (rx_w[r] == 0.0) continue;
         const int i = r % nth, j = r / nth;
         NfSourceRay ray;
-        nf_source_ray(mk(p[0], p[1], p[2]), launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), n_si, n_vac, ray);
+        nf_source_ray(K_COEF, mk(p[0], p[1], p[2]), launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), n_si, n_vac, ray);
         agg |= ray.status;
         if (!ray.valid) continue;
         const double a = (rx_opl[r] + ray.opl) * (k / 1e3);
@@ -102,7 +102,7 @@ API int shadow_nf_pixel2(const double* p, const double* th, int nth, const doubl
         const vec3 u = launch_dir(sin(th[r0 % nth]), cos(th[r0 % nth]), sin(ph[r0 / nth]), cos(ph[r0 / nth]));
         const vec3 v = launch_dir(sin(th[r1 % nth]), cos(th[r1 % nth]), sin(ph[r1 / nth]), cos(ph[r1 / nth]));
         NfSourceRayT<d2> ray;
-        nf_source_ray(p0, mk<d2>(d2(u.x, v.x), d2(u.y, v.y), d2(u.z, v.z)), n_si, n_vac, ray);
+        nf_source_ray(K_COEF, p0, mk<d2>(d2(u.x, v.x), d2(u.y, v.y), d2(u.z, v.z)), n_si, n_vac, ray);
         agg |= ray.status.a | (two ? ray.status.b : 0);
         const double w0 = ray.valid.a ? rx_w[r0] : 0.0, w1 = (two && ray.valid.b) ? rx_w[r1] : 0.0;
         const double a0 = (rx_opl[r0] + ray.opl.a) * (k / 1e3), a1 = (rx_opl[r1] + ray.opl.b) * (k / 1e3);
@@ -138,7 +138,7 @@ API int shadow_ff_mirror_rows(const double* geo, const double* th, int nth, cons
 {
     FfGeom g = unpack(geo);
     FfFrames f;
-    ff_build_frames(g, el, az, f);
+    ff_build_frames(K_COEF, g, el, az, f);
     const int n = nth * nph;
     int agg = 0;
     memset(out, 0, sizeof(double) * 9 * n);
@@ -146,9 +146,9 @@ API int shadow_ff_mirror_rows(const double* geo, const double* th, int nth, cons
         const int i = r % nth, j = r / nth;
         vec3 d = launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), Pa;
         double t_ap;
-        if (!ff_aperture(g, f, d, t_ap, Pa)) continue;
+        if (!ff_aperture(K_COEF, g, f, d, t_ap, Pa)) continue;
         FfRay ray;
-        ff_ray_trace<true, false>(f, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+        ff_ray_trace<true, false>(K_COEF, f, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
         agg |= ray.status;
         const double v[6] = {ray.m2.x, ray.m2.y, ray.m2.z, ray.m1.x, ray.m1.y, ray.m1.z};
         for (int k = 0; k < 6; k++) out[(size_t)k * n + r] = v[k];
@@ -162,7 +162,7 @@ API int shadow_ff_field_rows(const double* geo, const double* th, int nth, const
 {
     FfGeom g = unpack(geo);
     FfFrames f;
-    ff_build_frames(g, el, az, f);
+    ff_build_frames(K_COEF, g, el, az, f);
     double t2e[9];
     for (int i = 0; i < 9; i++) t2e[i] = f.t2.a[i];
     if (g.src[2] != 0) for (int i = 0; i < 3; i++) t2e[3 * i + 2] /= cos(atan(1.0 / 3.0));
@@ -174,14 +174,14 @@ API int shadow_ff_field_rows(const double* geo, const double* th, int nth, const
         const int i = r % nth, j = r / nth;
         vec3 d = launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), Pa;
         double t_ap;
-        if (!ff_aperture(g, f, d, t_ap, Pa)) continue;
+        if (!ff_aperture(K_COEF, g, f, d, t_ap, Pa)) continue;
         PanelErr e1, e2;
         const double* q = pan1 + pidx1[r];
         e1.a = q[2 * np1]; e1.b = q[3 * np1]; e1.c = q[4 * np1]; e1.d = q[5 * np1]; e1.e = q[6 * np1]; e1.x0 = q[8 * np1]; e1.y0 = q[9 * np1];
         q = pan2 + pidx2[r];
         e2.a = q[2 * np2]; e2.b = q[3 * np2]; e2.c = q[4 * np2]; e2.d = q[5 * np2]; e2.e = q[6 * np2]; e2.x0 = q[8 * np2]; e2.y0 = q[9 * np2];
         FfRay ray;
-        ff_ray_trace<false, true>(f, d, t_ap, Pa, g.foc_y, &e1, &e2, t2e, ray);
+        ff_ray_trace<false, true>(K_COEF, f, d, t_ap, Pa, g.foc_y, &e1, &e2, t2e, ray);
         agg |= ray.status;
         double rows[17];
         pack_ff_rows(ray, centre, rows);
@@ -196,7 +196,7 @@ API int shadow_ff_pixel2(const double* geo, const double* th, int nth, const dou
 {
     FfGeom g = unpack(geo);
     FfFrames f;
-    ff_build_frames(g, el, az, f);
+    ff_build_frames(K_COEF, g, el, az, f);
     const int n = nth * nph;
     int agg = 0;
     const FfGrid G = make_grid(gx_full, gy, M);
@@ -205,7 +205,12 @@ API int shadow_ff_pixel2(const double* geo, const double* th, int nth, const dou
     for (int r = 0; r < n; r++) {
         vec3 d = launch_dir(sin(th[r % nth]), cos(th[r % nth]), sin(ph[r / nth]), cos(ph[r / nth])), Pa;
         double t_ap;
-        if (ff_aperture(g, f, d, t_ap, Pa)) queue.push_back(r);
+        const bool exact = ff_aperture(K_COEF, g, f, d, t_ap, Pa);
+        // the kernel's FP32 prefilter must agree with the FP64 test wherever it commits to an answer
+        const float stf = (float)sin(th[r % nth]);
+        const int v = ff_aperture_coarse(f, stf * (float)cos(ph[r / nth]), stf * (float)sin(ph[r / nth]), (float)cos(th[r % nth]));
+        if (v >= 0 && (v > 0) != exact) agg |= 16;
+        if (exact) queue.push_back(r);
     }
     for (size_t a = 0; a < queue.size(); a += 2) {
         const bool two = a + 1 < queue.size();
@@ -215,9 +220,9 @@ API int shadow_ff_pixel2(const double* geo, const double* th, int nth, const dou
         const vec3t<d2> d = mk<d2>(d2(u.x, v.x), d2(u.y, v.y), d2(u.z, v.z));
         vec3t<d2> Pa;
         d2 t_ap;
-        ff_aperture(g, f, d, t_ap, Pa);
+        ff_aperture(K_COEF, g, f, d, t_ap, Pa);
         FfRayT<d2> ray;
-        ff_ray_trace<false, false, d2>(f, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+        ff_ray_trace<false, false, d2>(K_COEF, f, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
         agg |= ray.status.a | (two ? ray.status.b : 0);
         const int rr[2] = {r0, r1};
         const double oo[2] = {ray.opl.a, ray.opl.b}, fx[2] = {ray.foc.x.a, ray.foc.x.b}, fz[2] = {ray.foc.z.a, ray.foc.z.b};
@@ -255,7 +260,7 @@ API int shadow_ff_pixel(const double* geo, const double* th, int nth, const doub
 {
     FfGeom g = unpack(geo);
     FfFrames f;
-    ff_build_frames(g, el, az, f);
+    ff_build_frames(K_COEF, g, el, az, f);
     const int n = nth * nph;
     int agg = 0;
     const FfGrid G = make_grid(gx_full, gy, M);
@@ -265,9 +270,9 @@ API int shadow_ff_pixel(const double* geo, const double* th, int nth, const doub
         const int i = r % nth, j = r / nth;
         vec3 d = launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), Pa;
         double t_ap;
-        if (!ff_aperture(g, f, d, t_ap, Pa)) continue;
+        if (!ff_aperture(K_COEF, g, f, d, t_ap, Pa)) continue;
         FfRay ray;
-        ff_ray_trace<false, false>(f, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+        ff_ray_trace<false, false>(K_COEF, f, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
         agg |= ray.status;
         if (ray.opl == 0.0) continue;
         const int c = ff_cell(ray.foc.x - f.centre[0], ray.foc.z - f.centre[2], G);
