@@ -94,6 +94,22 @@ struct DevBuf {
     ~DevBuf() { if (p) cudaFree(p); }
 };
 
+// pinned host staging buffer (one D2H per host-entry call instead of three)
+struct PinnedBuf {
+    double* p = nullptr;
+    size_t n = 0;
+    int reserve(size_t count)
+    {
+        if (count <= n) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        CK(cudaHostAlloc(&p, count * sizeof(double), cudaHostAllocDefault));
+        n = count;
+        return 0;
+    }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+
 struct AngleTabs {
     const double *st, *ct, *sp, *cp;   // sin/cos of theta[nth], phi[nph]
     const float *stf, *ctf, *spf, *cpf; // single-precision copies (far-field aperture prefilter)
@@ -508,11 +524,12 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
             vec3t<d2> Pa;
             d2 t_ap;
             ff_aperture(sC, g, *fr, d, t_ap, Pa);
-            FfRayT<d2> ray;
-            ff_ray_trace<false, false, d2>(sC, *fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
-            st |= ray.status.a | (r1 >= 0 ? ray.status.b : 0);
+            d2 opl2, fx2, fz2;
+            i2 st2;
+            ff_ray_lean<d2>(sC, *fr, d, t_ap, Pa, g.foc_y, opl2, fx2, fz2, st2);
+            st |= st2.a | (r1 >= 0 ? st2.b : 0);
             const int rr[2] = {r0, r1};
-            const double oo[2] = {ray.opl.a, ray.opl.b}, fx[2] = {ray.foc.x.a, ray.foc.x.b}, fz[2] = {ray.foc.z.a, ray.foc.z.b};
+            const double oo[2] = {opl2.a, opl2.b}, fx[2] = {fx2.a, fx2.b}, fz[2] = {fz2.a, fz2.b};
 #pragma unroll
             for (int l = 0; l < 2; l++) {
 #else
@@ -520,11 +537,12 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
             vec3 Pa;
             double t_ap;
             ff_aperture(sC, g, *fr, d, t_ap, Pa);
-            FfRay ray;
-            ff_ray_trace<false, false, double>(sC, *fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
-            st |= ray.status;
+            double ropl, rfx, rfz;
+            int rst;
+            ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, ropl, rfx, rfz, rst);
+            st |= rst;
             const int rr[1] = {r0};
-            const double oo[1] = {ray.opl}, fx[1] = {ray.foc.x}, fz[1] = {ray.foc.z};
+            const double oo[1] = {ropl}, fx[1] = {rfx}, fz[1] = {rfz};
             {
                 const int l = 0;
 #endif
@@ -765,7 +783,8 @@ struct solat_nf_plan {
     DevBuf<int> act_idx;
     DevBuf<double2> phasor;                 // [nrx][nfreq][n_act]
     DevBuf<double2> partial;
-    DevBuf<double> h_src, h_amp, h_phase;   // device staging for the host entry point
+    DevBuf<double> h_src, h_out;            // device staging for the host entry point: [amp | phase | status word]
+    PinnedBuf pin;
     DevBuf<int> status;
     std::vector<double> kk;
     int nrx = 1;
@@ -909,21 +928,26 @@ int solat_nf_plan_status(solat_nf_plan* p, int* status)
     CK(cudaMemset(p->status.p, 0, sizeof(int)));
     return SOLAT_OK;
 }
+// copy the plan's persistent status word next to the results so that one D2H brings everything back
+__global__ void pack_status_kernel(const int* status, double* slot) { *slot = (double)*status; }
+
 int solat_nf_map_host(solat_nf_plan* p, const double* src_xz, int npix, double* amp, double* phase, int* status)
 {
     if (!p || !src_xz || !amp || !phase || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(p->ctx->device));
     cudaStream_t s = p->ctx->stream;
-    const size_t nf = p->kk.size() * (size_t)p->nrx;   // channels
+    const size_t n = p->kk.size() * (size_t)p->nrx * npix;   // channels x pixels
     if (int rc = p->h_src.upload(src_xz, 2 * (size_t)npix, s)) return rc;
-    if (int rc = p->h_amp.reserve(nf * npix)) return rc;
-    if (int rc = p->h_phase.reserve(nf * npix)) return rc;
-    if (int rc = nf_map_launch(p, p->h_src.p, npix, p->h_amp.p, p->h_phase.p, s)) return rc;
-    CK(cudaMemcpyAsync(amp, p->h_amp.p, nf * npix * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(phase, p->h_phase.p, nf * npix * sizeof(double), cudaMemcpyDeviceToHost, s));
-    int st = 0;
-    CK(cudaMemcpyAsync(&st, p->status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (int rc = p->h_out.reserve(2 * n + 1)) return rc;
+    if (int rc = p->pin.reserve(2 * n + 1)) return rc;
+    if (int rc = nf_map_launch(p, p->h_src.p, npix, p->h_out.p, p->h_out.p + n, s)) return rc;
+    pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->h_out.p + 2 * n);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(p->pin.p, p->h_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    memcpy(amp, p->pin.p, n * sizeof(double));
+    memcpy(phase, p->pin.p + n, n * sizeof(double));
+    const int st = (int)p->pin.p[2 * n];
     if (st) CK(cudaMemset(p->status.p, 0, sizeof(int)));
     if (status) *status = st;
     return SOLAT_OK;
@@ -1027,7 +1051,8 @@ struct solat_ff_plan {
     AngleTabsOwner ang;
     DevBuf<double> gx, gy;
     DevBuf<double2> e_rec;
-    DevBuf<double> h_azel, h_amp, h_phase;
+    DevBuf<double> h_azel, h_out;           // [amp | phase | status word]
+    PinnedBuf pin;
     DevBuf<int> status;
     FfGrid grid;
     double k, key_base, key_unit;
@@ -1109,15 +1134,18 @@ int solat_ff_map_host(solat_ff_plan* p, const double* azel, int npix, double* am
     if (!p || !azel || !amp || !phase || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(p->ctx->device));
     cudaStream_t s = p->ctx->stream;
-    if (int rc = p->h_azel.upload(azel, 2 * (size_t)npix, s)) return rc;
-    if (int rc = p->h_amp.reserve(npix)) return rc;
-    if (int rc = p->h_phase.reserve(npix)) return rc;
-    if (int rc = ff_map_launch(p, p->h_azel.p, npix, p->h_amp.p, p->h_phase.p, s)) return rc;
-    CK(cudaMemcpyAsync(amp, p->h_amp.p, npix * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(phase, p->h_phase.p, npix * sizeof(double), cudaMemcpyDeviceToHost, s));
-    int st = 0;
-    CK(cudaMemcpyAsync(&st, p->status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    const size_t n = (size_t)npix;
+    if (int rc = p->h_azel.upload(azel, 2 * n, s)) return rc;
+    if (int rc = p->h_out.reserve(2 * n + 1)) return rc;
+    if (int rc = p->pin.reserve(2 * n + 1)) return rc;
+    if (int rc = ff_map_launch(p, p->h_azel.p, npix, p->h_out.p, p->h_out.p + n, s)) return rc;
+    pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->h_out.p + 2 * n);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(p->pin.p, p->h_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    memcpy(amp, p->pin.p, n * sizeof(double));
+    memcpy(phase, p->pin.p + n, n * sizeof(double));
+    const int st = (int)p->pin.p[2 * n];
     if (st) CK(cudaMemset(p->status.p, 0, sizeof(int)));
     if (status) *status = st;
     return SOLAT_OK;

@@ -557,7 +557,7 @@ struct FfGeom {
     double foc_y;          // focal plane at y' = foc_y in the (+el,+az) frame: rx_y*1e3 (saf:582,955-957)
 };
 
-// Everything about one (az, el) pixel.  65 doubles; lives in shared memory.
+// Everything about one (az, el) pixel; lives in shared memory.
 struct FfFrames {
     double ap_row[3];      // third row of R(-el,-az)
     double ap_num;         // 4000 - C.z - ap_row.(src - C)            (aperture plane, latrt_geo.py:237-245)
@@ -569,6 +569,13 @@ struct FfFrames {
     double foc_off;        // C.y - foc_row.C
     double centre[3];      // focal-plane centre, saf:323-339
     float apf[8];          // single-precision copy for the aperture prefilter: ap_row[3], ap_num, src.x, src.y - y_cent, R^2, margin
+    // composites used by the fused map (ff_ray_lean): the ray stays in mirror-local coordinates from M1 on
+    Affine t21;            // M1 local point  -> M2 local point   (t2 o t1^-1)
+    double b12[9];         // M1 local vector -> M2 local vector  (t2.a * b1)
+    double foc_l[4];       // focal-plane row in M2-local point coordinates: foc_row . (t2^-1 H) + foc_off = foc_l[0..2].H + foc_l[3]
+    double foc_d[3];       // foc_row . (b2 v) = foc_d . v  for an M2-local vector v
+    double fx_l[4], fx_d[3];   // telescope x of an M2-local point / vector
+    double fz_l[4], fz_d[3];   // telescope z of an M2-local point / vector
 };
 
 SOLAT_HD void mat3_mul(const double* A, const double* B, double* C)
@@ -613,6 +620,28 @@ SOLAT_HD void ff_build_frames(const Coef& C_, const FfGeom& g, double el, double
     mat3_mul(Rp, F2t, f.b2);
     f.foc_row[0] = Rp[3]; f.foc_row[1] = Rp[4]; f.foc_row[2] = Rp[5];
     f.foc_off = C[1] - (Rp[3] * C[0] + Rp[4] * C[1] + Rp[5] * C[2]);
+    {   // t1, t2 are rigid (orthogonal matrix A, offset b):  p = A^T (l - b)
+        double A1t[9], A2t[9], t1i_b[3], t2i_b[3];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) { A1t[3 * i + j] = f.t1.a[3 * j + i]; A2t[3 * i + j] = f.t2.a[3 * j + i]; }
+        for (int i = 0; i < 3; i++) {
+            t1i_b[i] = -(A1t[3 * i] * f.t1.b[0] + A1t[3 * i + 1] * f.t1.b[1] + A1t[3 * i + 2] * f.t1.b[2]);
+            t2i_b[i] = -(A2t[3 * i] * f.t2.b[0] + A2t[3 * i + 1] * f.t2.b[1] + A2t[3 * i + 2] * f.t2.b[2]);
+        }
+        mat3_mul(f.t2.a, A1t, f.t21.a);
+        for (int i = 0; i < 3; i++)
+            f.t21.b[i] = f.t2.a[3 * i] * t1i_b[0] + f.t2.a[3 * i + 1] * t1i_b[1] + f.t2.a[3 * i + 2] * t1i_b[2] + f.t2.b[i];
+        mat3_mul(f.t2.a, f.b1, f.b12);
+        for (int j = 0; j < 3; j++) {
+            f.foc_l[j] = f.foc_row[0] * A2t[j] + f.foc_row[1] * A2t[3 + j] + f.foc_row[2] * A2t[6 + j];
+            f.foc_d[j] = f.foc_row[0] * f.b2[j] + f.foc_row[1] * f.b2[3 + j] + f.foc_row[2] * f.b2[6 + j];
+            f.fx_l[j] = A2t[j];      f.fx_d[j] = f.b2[j];
+            f.fz_l[j] = A2t[6 + j];  f.fz_d[j] = f.b2[6 + j];
+        }
+        f.foc_l[3] = f.foc_row[0] * t2i_b[0] + f.foc_row[1] * t2i_b[1] + f.foc_row[2] * t2i_b[2] + f.foc_off;
+        f.fx_l[3] = t2i_b[0];
+        f.fz_l[3] = t2i_b[2];
+    }
     f.apf[0] = (float)f.ap_row[0]; f.apf[1] = (float)f.ap_row[1]; f.apf[2] = (float)f.ap_row[2]; f.apf[3] = (float)f.ap_num;
     f.apf[4] = (float)g.src[0]; f.apf[5] = (float)(g.src[1] - C_.ff[2]); f.apf[6] = (float)C_.ff[3];
     // |r^2 - R^2| below this is left to the FP64 test: FP32 carries ~3e-7 relative on a ~5 m lever arm, i.e.
@@ -748,6 +777,36 @@ SOLAT_HD void ff_ray_trace(const Coef& C, const FfFrames& f, const vec3t<R>& d, 
         st |= flag(is_nan(r.opl), ST_NAN);
     }
     r.status = st;
+}
+
+// The same ray for the fused map, where only the path length and the focal-plane (x, z) are needed: after the
+// aperture point the ray never returns to the telescope frame (M1 local -> M2 local -> focal row), which saves a
+// third of the frame arithmetic and, more importantly, keeps nothing but (point, direction, path sum) alive
+// across each Newton solve.  Differs from ff_ray_trace only by rounding (1e-12 mm).
+template <class R>
+SOLAT_HD void ff_ray_lean(const Coef& C, const FfFrames& f, const vec3t<R>& d, R t_ap, const vec3t<R>& Pa, double foc_y,
+                          R& opl, R& fx, R& fz, typename Pack<R>::I& status)
+{
+    using I = typename Pack<R>::I;
+    R t1, t2;
+    vec3t<R> H, N;
+    const vec3t<R> none = mk<R>(R(0.0), R(0.0), R(0.0));
+    const vec3t<R> p1 = apply(f.t1, Pa), d1 = apply_lin(f.t1.a, d);
+    I st = mirror_hit<1, false, R>(C, p1, d1, 0.0, 1e4, nullptr, none, none, t1, H, N);
+    const vec3t<R> p2 = apply(f.t21, H), d2 = apply_lin(f.b12, reflect(d1, N));
+    st |= mirror_hit<2, false, R>(C, p2, d2, 1e3, 13e3, nullptr, none, none, t2, H, N);
+    const vec3t<R> r2 = reflect(d2, N);
+    const R num = R(foc_y) - fma(R(f.foc_l[0]), H.x, fma(R(f.foc_l[1]), H.y, fma(R(f.foc_l[2]), H.z, R(f.foc_l[3]))));
+    const R den = fma(R(f.foc_d[0]), r2.x, fma(R(f.foc_d[1]), r2.y, R(f.foc_d[2]) * r2.z));
+    const R tf = num * rcp_fast(den);                                                        // saf:947-962
+    st |= flag(bnot(band(ge(tf, R(1e3)), le(tf, R(15e3)))), ST_BRACKET);
+    fx = fma(tf, fma(R(f.fx_d[0]), r2.x, fma(R(f.fx_d[1]), r2.y, R(f.fx_d[2]) * r2.z)),
+             fma(R(f.fx_l[0]), H.x, fma(R(f.fx_l[1]), H.y, fma(R(f.fx_l[2]), H.z, R(f.fx_l[3])))));
+    fz = fma(tf, fma(R(f.fz_d[0]), r2.x, fma(R(f.fz_d[1]), r2.y, R(f.fz_d[2]) * r2.z)),
+             fma(R(f.fz_l[0]), H.x, fma(R(f.fz_l[1]), H.y, fma(R(f.fz_l[2]), H.z, R(f.fz_l[3])))));
+    opl = ((t_ap + t1) + t2) + tf;                                                           // saf:970
+    st |= flag(is_nan(opl), ST_NAN);
+    status = st;
 }
 
 // np.searchsorted(a, v, side='left') over a strided sorted array

@@ -221,11 +221,12 @@ API int shadow_ff_pixel2(const double* geo, const double* th, int nth, const dou
         vec3t<d2> Pa;
         d2 t_ap;
         ff_aperture(K_COEF, g, f, d, t_ap, Pa);
-        FfRayT<d2> ray;
-        ff_ray_trace<false, false, d2>(K_COEF, f, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
-        agg |= ray.status.a | (two ? ray.status.b : 0);
+        d2 opl2, fx2, fz2;
+        i2 st2;
+        ff_ray_lean<d2>(K_COEF, f, d, t_ap, Pa, g.foc_y, opl2, fx2, fz2, st2);
+        agg |= st2.a | (two ? st2.b : 0);
         const int rr[2] = {r0, r1};
-        const double oo[2] = {ray.opl.a, ray.opl.b}, fx[2] = {ray.foc.x.a, ray.foc.x.b}, fz[2] = {ray.foc.z.a, ray.foc.z.b};
+        const double oo[2] = {opl2.a, opl2.b}, fx[2] = {fx2.a, fx2.b}, fz[2] = {fz2.a, fz2.b};
         for (int l = 0; l < (two ? 2 : 1); l++) {
             if (oo[l] == 0.0) continue;
             const int c = ff_cell(fx[l] - f.centre[0], fz[l] - f.centre[2], G);
@@ -271,13 +272,14 @@ API int shadow_ff_pixel(const double* geo, const double* th, int nth, const doub
         vec3 d = launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), Pa;
         double t_ap;
         if (!ff_aperture(K_COEF, g, f, d, t_ap, Pa)) continue;
-        FfRay ray;
-        ff_ray_trace<false, false>(K_COEF, f, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
-        agg |= ray.status;
-        if (ray.opl == 0.0) continue;
-        const int c = ff_cell(ray.foc.x - f.centre[0], ray.foc.z - f.centre[2], G);
+        double ropl, rfx, rfz;
+        int rst;
+        ff_ray_lean<double>(K_COEF, f, d, t_ap, Pa, g.foc_y, ropl, rfx, rfz, rst);
+        agg |= rst;
+        if (ropl == 0.0) continue;
+        const int c = ff_cell(rfx - f.centre[0], rfz - f.centre[2], G);
         if (c < 0) continue;
-        if (r > win[c]) { win[c] = r; opl[c] = ray.opl; }
+        if (r > win[c]) { win[c] = r; opl[c] = ropl; }
     }
     double re = 0, im = 0;
     int cnt = 0;
