@@ -93,6 +93,11 @@ SOLAT_API int solat_nf_source_trace(solat_ctx *ctx, const solat_nf_geom *g, cons
 SOLAT_API int solat_nf_toy_trace(solat_ctx *ctx, const solat_nf_geom *g, const double p_rx[3], const double *theta, int nth,
                        const double *phi, int nph, double *out32, int *status);
 
+/* replaces the four interp2d(kind="cubic") resamples of ray_trace_int.regrid, rti:1403-1425: interpolating bicubic
+ * (not-a-knot) spline of field (n_old, n_old), given on linspace(-70, 70, n_old) in both axes, evaluated on
+ * linspace(-70, 70, n_new); out is (n_new, n_new).  Host pointers.                                          */
+SOLAT_API int solat_regrid_bicubic(solat_ctx *ctx, const double *field, int n_old, int n_new, double *out);
+
 /* ---------------- near field: fused holography map --------------------------------------------
  * replaces the worker body scripts/holo_sim.py:157-185 for a whole list of source positions:
  * per pixel  sum_rays  rx_w * exp(i k (rx_opl + L_source)/1e3)  ->  amp = |.|, phase = atan2.

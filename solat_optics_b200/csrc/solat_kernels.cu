@@ -589,6 +589,28 @@ static size_t ff_map_smem(int M)
 }
 
 // ------------------------------------------------------------------------------------------------
+// regrid: interpolating bicubic spline resample in ray-index space (ray_trace_int.py:1385-1440)
+// ------------------------------------------------------------------------------------------------
+// The reference resamples a (n_old x n_old) field given on linspace(-70, 70, n_old) onto linspace(-70, 70, n_new)
+// with interp2d(kind="cubic") = FITPACK's interpolating bicubic spline (s = 0), whose knot choice is the
+// not-a-knot one.  A tensor-product interpolant is separable: a 1-D not-a-knot cubic spline along x for every row,
+// then along y for every new column.  One thread per 1-D problem; second derivatives M by the Thomas algorithm.
+__global__ void regrid_rows_kernel(const double* field, int n_old, int n_new, double* tmp, double* scratch)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;      // old row: spline along the fast axis
+    if (r >= n_old) return;
+    double* M = scratch + (size_t)r * 2 * n_old;
+    spline_line(field + (size_t)r * n_old, 1, n_old, M, M + n_old, n_new, tmp + (size_t)r * n_new, 1);
+}
+__global__ void regrid_cols_kernel(const double* tmp, int n_old, int n_new, double* out, double* scratch)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;      // new column: spline along the slow axis
+    if (c >= n_new) return;
+    double* M = scratch + (size_t)c * 2 * n_old;
+    spline_line(tmp + c, n_new, n_old, M, M + n_old, n_new, out + c, n_new);
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 peak microbenchmark
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b)
@@ -626,6 +648,25 @@ __global__ void selftest_math_kernel(const double* x, int n, double* out)
 // C ABI
 // ------------------------------------------------------------------------------------------------
 extern "C" {
+
+int solat_regrid_bicubic(solat_ctx* c, const double* field, int n_old, int n_new, double* out)
+{
+    if (!c || !field || !out || n_old <= 0 || n_new <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    DevBuf<double> d_in, d_tmp, d_out, d_scr;
+    if (int rc = d_in.upload(field, (size_t)n_old * n_old, s)) return rc;
+    if (int rc = d_tmp.reserve((size_t)n_old * n_new)) return rc;
+    if (int rc = d_out.reserve((size_t)n_new * n_new)) return rc;
+    if (int rc = d_scr.reserve((size_t)2 * n_old * (size_t)std::max(n_old, n_new))) return rc;
+    regrid_rows_kernel<<<(n_old + 63) / 64, 64, 0, s>>>(d_in.p, n_old, n_new, d_tmp.p, d_scr.p);
+    LAUNCHED();
+    regrid_cols_kernel<<<(n_new + 63) / 64, 64, 0, s>>>(d_tmp.p, n_old, n_new, d_out.p, d_scr.p);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(out, d_out.p, (size_t)n_new * n_new * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SOLAT_OK;
+}
 
 int solat_selftest_math(solat_ctx* c, const double* x, int n, double* out8)
 {

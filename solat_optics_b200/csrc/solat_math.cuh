@@ -942,4 +942,59 @@ SOLAT_HD double ff_key_opl(unsigned long long key, double base, double unit)
     return base + (double)qi * unit;
 }
 
+// ------------------------------------------------------------------------------------------
+// regrid (ray_trace_int.py:1385-1440): one line of the separable interpolating bicubic spline.
+// y: n samples at unit spacing (stride ystride); M, cp: scratch of n doubles each; writes n_new samples of the
+// not-a-knot cubic spline at u_j = j (n-1)/(n_new-1).
+// ------------------------------------------------------------------------------------------
+SOLAT_HD void spline_line(const double* y, int ystride, int n, double* M, double* cp, int n_new, double* out, int ostride)
+{
+    // uniform unit spacing in old-index units; not-a-knot: M1 = d1, M(n-2) = d(n-2), d_i = y(i-1) - 2 y(i) + y(i+1)
+    if (n < 4) {   // parabola through 3 points / straight line through 2 / constant
+        for (int j = 0; j < n_new; j++) {
+            const double u = n_new > 1 ? (double)j * (double)(n - 1) / (double)(n_new - 1) : 0.0;
+            double v;
+            if (n == 1) v = y[0];
+            else if (n == 2) v = y[0] + (y[ystride] - y[0]) * u;
+            else {
+                const double y0 = y[0], y1 = y[ystride], y2 = y[2 * ystride];
+                v = y0 * (u - 1) * (u - 2) * 0.5 - y1 * u * (u - 2) + y2 * u * (u - 1) * 0.5;
+            }
+            out[(size_t)j * ostride] = v;
+        }
+        return;
+    }
+#define SOLAT_SPL_Y(i) (y[(size_t)(i) * ystride])
+#define SOLAT_SPL_D(i) (SOLAT_SPL_Y((i) - 1) - 2.0 * SOLAT_SPL_Y(i) + SOLAT_SPL_Y((i) + 1))
+    M[1] = SOLAT_SPL_D(1);
+    M[n - 2] = SOLAT_SPL_D(n - 2);
+    if (n > 4) {
+        // M(i-1) + 4 M(i) + M(i+1) = 6 d(i),  i = 2 .. n-3, with M(1) and M(n-2) known
+        const int lo = 2, hi = n - 3;
+        double bprev = 4.0, rprev = 6.0 * SOLAT_SPL_D(lo) - M[1];
+        if (lo == hi) rprev -= M[n - 2];
+        cp[lo] = 1.0 / bprev;             // c'(lo)
+        M[lo] = rprev / bprev;            // d'(lo)
+        for (int i = lo + 1; i <= hi; i++) {
+            double r = 6.0 * SOLAT_SPL_D(i);
+            if (i == hi) r -= M[n - 2];
+            const double b = 4.0 - cp[i - 1];
+            cp[i] = 1.0 / b;
+            M[i] = (r - M[i - 1]) / b;
+        }
+        for (int i = hi - 1; i >= lo; i--) M[i] -= cp[i] * M[i + 1];
+    }
+    M[0] = 2.0 * M[1] - M[2];
+    M[n - 1] = 2.0 * M[n - 2] - M[n - 3];
+    for (int j = 0; j < n_new; j++) {
+        const double u = n_new > 1 ? (double)j * (double)(n - 1) / (double)(n_new - 1) : 0.0;
+        int i = (int)u;
+        if (i > n - 2) i = n - 2;
+        const double t = u - i, w = 1.0 - t;
+        out[(size_t)j * ostride] = w * SOLAT_SPL_Y(i) + t * SOLAT_SPL_Y(i + 1) + ((w * w * w - w) * M[i] + (t * t * t - t) * M[i + 1]) / 6.0;
+    }
+#undef SOLAT_SPL_Y
+#undef SOLAT_SPL_D
+}
+
 }  // namespace solat

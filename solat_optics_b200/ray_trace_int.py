@@ -127,16 +127,16 @@ class aperature_fields(_LyotTracer):
 
 def _resample_index_grid(values, res_new):
     """Interpolating bicubic spline of a (res, res) field defined on linspace(-70, 70, res) in both
-    axes, evaluated on linspace(-70, 70, res_new) (what interp2d(kind='cubic') did, rti:1417-1425)."""
+    axes, evaluated on linspace(-70, 70, res_new) (what interp2d(kind='cubic') did, rti:1417-1425).
+    Runs on the GPU (solat_regrid_bicubic: separable not-a-knot cubic splines)."""
     res_old = values.shape[0]
     if res_old == res_new:
         return values  # an interpolating spline evaluated at its own knots
-    from scipy.interpolate import RectBivariateSpline
-
-    ax_old = np.linspace(-70, 70, res_old)
-    ax_new = np.linspace(-70, 70, res_new)
-    spline = RectBivariateSpline(ax_old, ax_old, values.T, kx=3, ky=3, s=0)
-    return spline(ax_new, ax_new).T
+    values = _lib.as_f64(values)
+    out = np.empty((res_new, res_new), dtype=np.float64)
+    _lib.check(_lib.load().solat_regrid_bicubic(_lib.context().handle, _lib.dptr(values), res_old, res_new,
+                                                _lib.dptr(out)))
+    return out
 
 
 def regrid(beam1, beam2):
@@ -145,7 +145,7 @@ def regrid(beam1, beam2):
     Like the reference it works in ray-index space on a nominal uniform +-70 mm grid and returns
     (field of beam2, field of beam1 resampled), rows 0,2 = grid X,Z, row 3 = path length, row 4 =
     amplitude.  Resampling a field onto its own grid is the identity, so only the unequal-grid case
-    does any arithmetic (once per map, on the host)."""
+    does any arithmetic (once per map, two small kernels)."""
     res_so = int(np.sqrt(len(beam2[0, :])))
     res_rx = int(np.sqrt(len(beam1[0, :])))
     axis = np.linspace(-70, 70, res_so)

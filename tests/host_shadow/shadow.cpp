@@ -295,3 +295,13 @@ API int shadow_ff_pixel(const double* geo, const double* th, int nth, const doub
     if (n_cells) *n_cells = cnt;
     return agg;
 }
+
+// regrid: the separable not-a-knot bicubic resample the CUDA kernels run (rows, then columns)
+API void shadow_regrid(const double* field, int n_old, int n_new, double* out)
+{
+    std::vector<double> tmp((size_t)n_old * n_new), M(2 * (size_t)n_old);
+    for (int r = 0; r < n_old; r++)
+        spline_line(field + (size_t)r * n_old, 1, n_old, M.data(), M.data() + n_old, n_new, tmp.data() + (size_t)r * n_new, 1);
+    for (int c = 0; c < n_new; c++)
+        spline_line(tmp.data() + c, n_new, n_old, M.data(), M.data() + n_old, n_new, out + c, n_new);
+}

@@ -102,3 +102,10 @@ def ff_pixel(geo, th, ph, el, az, data_x, data_y, e_rec, k, packed=False):
     agg = fn(gp, thp, ci(th.size), php, ci(ph.size), cd(el), cd(az), gxp, gyp,
                                 e.ctypes.data_as(dp), ci(gx.size), cd(k), o.ctypes.data_as(dp), ctypes.byref(nc))
     return complex(o[0], o[1]), nc.value, agg
+
+
+def regrid(field, n_new):
+    f, fp = D(field)
+    out = np.zeros((n_new, n_new))
+    lib().shadow_regrid(fp, ci(f.shape[0]), ci(n_new), out.ctypes.data_as(dp))
+    return out

@@ -404,6 +404,27 @@ def test_ff_odd_sizes_and_edge_grids(oracle):
             _assert_pixels(a, p, oa, op)
 
 
+def test_regrid_on_device_matches_fitpack_and_reference():
+    """ray_trace_int.regrid with unequal grids runs the device spline; the n_rx=16 -> n_so=30 reference KAT is in
+    test_nf_pixel_known_answers (nf_pixels case 12).  Here: layout and agreement with FITPACK."""
+    from scipy.interpolate import RectBivariateSpline
+
+    from solat_optics_b200 import ray_trace_int as rti
+
+    rng = np.random.default_rng(3)
+    n_rx, n_so = 20, 33
+    ax = np.linspace(-70, 70, n_rx)
+    X, Z = np.meshgrid(ax, ax)
+    rx = np.zeros((20, n_rx * n_rx)); so = rng.normal(size=(26, n_so * n_so))
+    rx[3] = (1500 + 0.01 * (X ** 2 + 0.5 * Z ** 2)).ravel(); rx[4] = np.exp(-(X ** 2 + Z ** 2) / 5e3).ravel()
+    b1, b2 = rti.regrid(rx, so)
+    new = np.linspace(-70, 70, n_so)
+    for row in (3, 4):
+        ref = RectBivariateSpline(ax, ax, rx[row].reshape(n_rx, n_rx).T, kx=3, ky=3, s=0)(new, new).T
+        np.testing.assert_allclose(b2[row].reshape(n_so, n_so), ref, rtol=0, atol=1e-10)
+        np.testing.assert_array_equal(b1[row], so[row])
+
+
 def test_tiny_and_empty_inputs(oracle):
     """Degenerate sizes the reference's loops handle trivially: a 1-ray fan, a 1-pixel map, an empty pixel list,
     a 1x1 E_rec grid, a 3-ray fan in paired mode."""

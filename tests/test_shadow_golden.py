@@ -148,3 +148,39 @@ def test_status_flags(shadow):
     # far off-axis source: every ray vignetted, no flag raised
     out, st, agg = shadow.nf_source_rows([600.0, -1335.0, 0.0], a, a)
     assert agg == 0 and not out.any()
+
+
+def test_regrid_spline_matches_fitpack(shadow):
+    """The device resample (separable not-a-knot cubic splines) against FITPACK's interpolating bicubic spline,
+    which is what the reference's interp2d(kind="cubic") evaluates (ray_trace_int.py:1417-1425)."""
+    from scipy.interpolate import RectBivariateSpline
+
+    for n_old, n_new in [(16, 30), (4, 9), (5, 7), (80, 150), (30, 16), (3, 5), (2, 4)]:
+        ax = np.linspace(-70, 70, n_old)
+        X, Z = np.meshgrid(ax, ax)
+        F = 1500 + 0.01 * (X ** 2 + 0.5 * Z ** 2) + 0.3 * np.sin(X / 20) * np.cos(Z / 15)
+        out = shadow.regrid(F, n_new)
+        if n_old >= 4:
+            new = np.linspace(-70, 70, n_new)
+            ref = RectBivariateSpline(ax, ax, F.T, kx=3, ky=3, s=0)(new, new).T
+            np.testing.assert_allclose(out, ref, rtol=0, atol=1e-10)
+        assert np.isfinite(out).all()
+        np.testing.assert_allclose(out[0, 0], F[0, 0], atol=1e-12)
+        np.testing.assert_allclose(out[-1, -1], F[-1, -1], atol=1e-10)
+
+
+def test_regrid_unequal_grids_known_answer(shadow):
+    """Reference KAT with n_rx=16 resampled onto n_so=30 (tests/golden/nf_pixels case 12): spline resample +
+    per-ray math reproduce the reference, and the answer differs from the equal-grid one at 3e-7."""
+    d = gu.load("nf_pixels")
+    i = [j for j in range(int(d["n_cases"])) if int(d["in_n_scan_rx"][j]) != int(d["in_n_scan"][j])][0]
+    f, n, n_rx = float(d["in_freq"][i]), int(d["in_n_scan"][i]), int(d["in_n_scan_rx"][i])
+    y_ap, fw = gu.nf_band(f)
+    th, ph = _rx_axes(n_rx)
+    rx, _ = shadow.nf_rx_rows((0, 0, 0), th, ph, fw)
+    opl = shadow.regrid(rx[3].reshape(n_rx, n_rx), n).ravel()
+    amp = shadow.regrid(rx[4].reshape(n_rx, n_rx), n).ravel()
+    a = _src_axis(n)
+    z, _ = shadow.nf_pixel([d["in_x"][i], y_ap, d["in_z"][i]], a, a, opl, amp * gu.lyot_mask(n), gu.nf_k(f))
+    assert abs(abs(z) ** 2 - d["amp"][i] ** 2) <= P_TOL * d["amp"][i] ** 2
+    assert abs(gu.wrap(np.angle(z) - d["phi"][i])) <= PHI_TOL
