@@ -72,9 +72,10 @@ SOLAT_API int solat_ctx_info(const solat_ctx *ctx, int *sm_count, int *cc_major,
 SOLAT_API long long solat_launch_count(void);
 /* DFMA-issue microbenchmark: measured FP64 FMA throughput of the device in TFLOP/s (roofline denominator) */
 SOLAT_API int solat_fp64_peak(solat_ctx *ctx, int repeats, double *tflops);
-/* accuracy probe of the device fast-math primitives on x[n] (host pointers).  out8 is (8, n): reciprocal with
- * 0..3 Newton steps, reciprocal square root with 0..1 polish steps, cos and sin of the large-argument reducer */
-SOLAT_API int solat_selftest_math(solat_ctx *ctx, const double *x, int n, double *out8);
+/* accuracy probe of the device fast-math primitives on x[n] (host pointers).  out10 is (10, n): reciprocal with
+ * 0..3 Newton steps, reciprocal square root with 0..1 polish steps, cos and sin of the large-argument reducer,
+ * cos and sin of the mid-range (|x| < 1e5) routine */
+SOLAT_API int solat_selftest_math(solat_ctx *ctx, const double *x, int n, double *out10);
 
 /* ---------------- near field: reference-shaped per-ray arrays (host pointers) ----------------
  * theta[nth], phi[nph] are the 1-D launch axes; ray ii uses theta[ii % nth], phi[ii / nth]

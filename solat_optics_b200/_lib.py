@@ -158,9 +158,9 @@ def context(device=None):
 
 
 def selftest_math(x, device=None):
-    """(8, n) accuracy probe of the device fast-math primitives; see include/solat_b200.h."""
+    """(10, n) accuracy probe of the device fast-math primitives; see include/solat_b200.h."""
     x = as_f64(x)
-    out = np.empty((8, x.size))
+    out = np.empty((10, x.size))
     check(load().solat_selftest_math(context(device).handle, dptr(x), x.size, dptr(out)))
     return out
 

@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(NF_T, SOLAT_NF_MINB) nf_map_kernel(NfMapParams
 #pragma unroll
             for (int f = 0; f < NF; f++) {
                 double sn, cs;
-                sincos(ray.opl * q.kk[f], &sn, &cs);                              // holo_sim.py:177
+                sincos_mid(ray.opl * q.kk[f], sn, cs);                            // holo_sim.py:177
 #pragma unroll
                 for (int t = 0; t < NT; t++) {
                     const double2 ph = __ldg(q.phasor + ((size_t)(q.j0 + t) * q.nfreq_total + (q.f0 + f)) * q.n_act + a);
@@ -626,7 +627,8 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
-// accuracy probe of the fast-math primitives: out[v][i], v = rcp with 0..3 Newton steps, rsqrt with 0..1 polish
+// accuracy probe of the fast-math primitives: out[v][i], v = rcp with 0..3 Newton steps, rsqrt with 0..1 polish,
+// cos/sin of the large-argument reducer, cos/sin of the mid-range routine
 __global__ void selftest_math_kernel(const double* x, int n, double* out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -642,6 +644,9 @@ __global__ void selftest_math_kernel(const double* x, int n, double* out)
     cis_large(a, c, s);
     out[6 * n + i] = c;
     out[7 * n + i] = s;
+    sincos_mid(a, s, c);
+    out[8 * n + i] = c;
+    out[9 * n + i] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -668,16 +673,16 @@ int solat_regrid_bicubic(solat_ctx* c, const double* field, int n_old, int n_new
     return SOLAT_OK;
 }
 
-int solat_selftest_math(solat_ctx* c, const double* x, int n, double* out8)
+int solat_selftest_math(solat_ctx* c, const double* x, int n, double* out10)
 {
-    if (!c || !x || !out8 || n <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    if (!c || !x || !out10 || n <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(c->device));
     DevBuf<double> dx, dout;
     if (int rc = dx.upload(x, n, c->stream)) return rc;
-    if (int rc = dout.reserve(8 * (size_t)n)) return rc;
+    if (int rc = dout.reserve(10 * (size_t)n)) return rc;
     selftest_math_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(dx.p, n, dout.p);
     LAUNCHED();
-    CK(cudaMemcpyAsync(out8, dout.p, 8 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out10, dout.p, 10 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return SOLAT_OK;
 }
@@ -1122,7 +1127,8 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
     if (!c || !g || !theta || !phi || !data_x || !data_y || !e_rec || !out || nth <= 0 || nph <= 0 || M <= 0)
         return fail(SOLAT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(c->device));
-    const size_t smem = ff_map_smem(M);
+    size_t smem = ff_map_smem(M);
+    if (const char* pad = getenv("SOLAT_FF_SMEM_PAD")) smem += (size_t)atol(pad);   // occupancy experiments only
     if (smem > (size_t)c->prop.sharedMemPerBlockOptin)
         return fail(SOLAT_ERR_ARG, "E_rec grid too large for the shared-memory winner table (M <= 168)");
     if ((long long)nth * nph > FF_MAX_RAYS)

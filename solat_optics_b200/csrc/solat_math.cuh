@@ -23,6 +23,7 @@
 //    8-cycle DFMA latency, and every coefficient / frame load and every barrier serves two rays.
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define SOLAT_HD __device__ __forceinline__
@@ -302,8 +303,10 @@ SOLAT_TABLE Coef K_COEF = {
 // Newton schedule shared by all curved surfaces (DESIGN.md "Mixed-precision Newton"):
 //   update 1 from the vertex-plane hit is evaluated in FP32 on the otherwise idle FMA pipe -- its own
 //            truncation error (curvature x step^2 ~ 1e-4 .. 1e-2 mm) dwarfs FP32 rounding (~1e-5 mm);
-//   updates 2 and 3 are FP64 and converge quadratically to < 1e-12 mm; the unit normal uses the slope of the
-//            last evaluation (the last step is < 1e-9 mm, i.e. < 1e-13 rad in the normal).
+//   mirrors: updates 2 and 3 are FP64 and converge quadratically to < 1e-12 mm; the unit normal uses the slope of
+//            the last evaluation (the last step is < 1e-9 mm, i.e. < 1e-13 rad in the normal);
+//   lenses:  one FP64 update already lands within ~1e-13 mm (checked: more only while |dt| > 1e-3 mm), then only
+//            the slope is re-evaluated at the final point.
 // Hit of the ray P + t d with asphere S.  On return H is the hit point, N the unit normal in the
 // telescope frame with N.y > 0 (= reference n_hat rotated back), t the ray parameter.
 template <int S, class R>
@@ -328,28 +331,33 @@ SOLAT_HD typename Pack<R>::I asphere_hit(const Coef& C, const vec3t<R>& P, const
         t += to_r(div_f(sagf, fpf), t);
     }
     R x, z, u, w, rs, G, dt = R(0.0);
+#define SOLAT_ASPH_SLOPE()                                                                         \
+    x = fma(d.x, t, P.x);                                                                          \
+    z = fma(d.z, t, P.z);                                                                          \
+    u = fma(x, x, z * z);                                                                          \
+    w = fma(R(-A.K), u, R(1.0));                                                                   \
+    rs = rsqrt_fast(w);                                                                            \
+    G = fma(R(A.c), rs, fma(u, fma(u, fma(u, R(A.g4), R(A.g3)), R(A.g2)), R(A.g1)));
 #define SOLAT_ASPH_UPDATE()                                                                        \
     {                                                                                              \
-        x = fma(d.x, t, P.x);                                                                      \
-        z = fma(d.z, t, P.z);                                                                      \
-        u = fma(x, x, z * z);                                                                      \
-        w = fma(R(-A.K), u, R(1.0));                                                               \
-        rs = rsqrt_fast(w);                                                                        \
-        G = fma(R(A.c), rs, fma(u, fma(u, fma(u, R(A.g4), R(A.g3)), R(A.g2)), R(A.g1)));           \
+        SOLAT_ASPH_SLOPE()                                                                         \
         const R sag = fma(fma(-w, rs, R(1.0)), R(A.Kinv), u * fma(u, fma(u, fma(u, R(A.a4), R(A.a3)), R(A.a2)), R(A.a1))); \
         const R f = fma(d.y, t, py) - sag;                                                         \
         const R fp = fma(-G, fma(x, d.x, z * d.z), d.y);                                           \
         dt = f * rcp_step(fp);                                                                     \
         t -= dt;                                                                                   \
     }
+    // One FP64 update after the FP32 one leaves an error of C dt^2 with C <~ 4e-5 / mm for these lenses (nominal
+    // rays: dt ~ 1e-4 mm, error ~ 1e-13 mm).  More updates only while |dt| > 1e-3 mm (error bound 4e-11 mm).
     SOLAT_ASPH_UPDATE()
-    SOLAT_ASPH_UPDATE()
-    for (int it = 3; any(gt(fabs(dt), R(1e-9))) && it < 10; ++it) SOLAT_ASPH_UPDATE()   // off-nominal rays only
+    for (int it = 2; any(gt(fabs(dt), R(1e-3))) && it < 10; ++it) SOLAT_ASPH_UPDATE()
+    SOLAT_ASPH_SLOPE()                     // slope at the converged point, for the normal
 #undef SOLAT_ASPH_UPDATE
-    H = axpy(P, d, t);
+#undef SOLAT_ASPH_SLOPE
+    H = mk<R>(x, fma(d.y, t, P.y), z);
     const R nn = rsqrt_fast(fma(G * G, u, R(1.0)));
     N = mk<R>(-x * G * nn, nn, -z * G * nn);
-    I st = imask(bnot(is_nan(dt)), flag(bnot(le(fabs(dt), R(1e-9))), ST_NOCONV)) | flag(is_nan(dt), ST_NAN);
+    I st = imask(bnot(is_nan(dt)), flag(bnot(le(fabs(dt), R(1e-3))), ST_NOCONV)) | flag(is_nan(dt), ST_NAN);
     st |= flag(bnot(band(ge(t, R(lo)), le(t, R(hi)))), ST_BRACKET);
     return st;
 }
@@ -818,6 +826,37 @@ SOLAT_HD int searchsorted_left(const double* a, int n, int stride, double v)
         if (a[(long)mid * stride] < v) lo = mid + 1; else hi = mid;
     }
     return lo;
+}
+
+// sin, cos for |x| < ~1e5 rad (near-field phases k L ~ 1e4): FP64 Cody-Waite reduction by pi/2 (fdlibm's 33-bit
+// split) and the FP64 leading terms (r - r^3/6 + r^5/120, 1 - r^2/2 + r^4/24 - r^6/720); the remaining tails
+// (|.| < 4e-5) run in FP32 on the FMA pipe.  Absolute error ~1e-11 (tests: test_fast_math_primitives).
+SOLAT_HD void sincos_mid(double x, double& sn, double& cs)
+{
+    const double TWO_OVER_PI = 0.6366197723675814, MAGIC = 6755399441055744.0;        // 1.5 * 2^52
+    const double P1 = 1.57079632673412561417e+00, P2 = 6.07710050630396597660e-11, P3 = 2.02226624879595063154e-21;
+    const double nb = fma(x, TWO_OVER_PI, MAGIC);        // round-to-nearest integer lands in the low mantissa bits
+    const double n = nb - MAGIC;
+    double r = fma(-n, P1, x);
+    r = fma(-n, P2, r);
+    r = fma(-n, P3, r);
+#if defined(__CUDA_ARCH__)
+    const int q = __double2loint(nb);
+#else
+    long long bits;
+    memcpy(&bits, &nb, 8);
+    const int q = (int)(bits & 0xffffffff);
+#endif
+    const double r2 = r * r;
+    const float rf = (float)r, r2f = rf * rf, r4f = r2f * r2f;
+    // tails: sin: r^7 (-1/5040 + r^2/362880 - r^4/39916800);  cos: r^8 (1/40320 - r^2/3628800 + r^4/479001600)
+    const float ts = rf * r2f * r4f * fmaf(r2f, fmaf(r2f, -2.5052108e-8f, 2.7557319e-6f), -1.9841270e-4f);
+    const float tc = r4f * r4f * fmaf(r2f, fmaf(r2f, 2.0876757e-9f, -2.7557319e-7f), 2.4801587e-5f);
+    const double s0 = fma(r * r2, fma(r2, 1.0 / 120.0, -1.0 / 6.0), r) + (double)ts;
+    const double c0 = fma(r2, fma(r2, fma(r2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0) + (double)tc;
+    const double s1 = (q & 1) ? c0 : s0, c1 = (q & 1) ? s0 : c0;
+    sn = (q & 2) ? -s1 : s1;
+    cs = ((q + 1) & 2) ? -c1 : c1;
 }
 
 // exp(i x) for x up to ~1e9 rad with absolute error ~1e-15: three-term Cody-Waite reduction by

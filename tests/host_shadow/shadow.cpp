@@ -78,9 +78,12 @@ API int shadow_nf_pixel(const double* p, const double* th, int nth, const double
         nf_source_ray(K_COEF, mk(p[0], p[1], p[2]), launch_dir(sin(th[i]), cos(th[i]), sin(ph[j]), cos(ph[j])), n_si, n_vac, ray);
         agg |= ray.status;
         if (!ray.valid) continue;
-        const double a = (rx_opl[r] + ray.opl) * (k / 1e3);
-        re += rx_w[r] * cos(a);
-        im += rx_w[r] * sin(a);
+        // as in nf_map_kernel: receiver phasor (libm, host side) x exp(i k L_source) from sincos_mid
+        const double ar = rx_opl[r] * k / 1e3;
+        double sn, cs;
+        sincos_mid(ray.opl * (k / 1e3), sn, cs);
+        re += rx_w[r] * (cos(ar) * cs - sin(ar) * sn);
+        im += rx_w[r] * (cos(ar) * sn + sin(ar) * cs);
     }
     re_im[0] = re; re_im[1] = im;
     return agg;

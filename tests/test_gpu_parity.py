@@ -48,6 +48,24 @@ def test_library_is_the_cuda_one():
     assert _lib.launch_count() > before
 
 
+def test_fast_math_primitives():
+    """Device rcp / rsqrt / sincos building blocks against libm (the accuracy the Newton schedule relies on)."""
+    from solat_optics_b200 import _lib
+
+    rng = np.random.default_rng(1)
+    xs = np.concatenate([rng.uniform(0.5, 2.0, 5000), 10 ** rng.uniform(-4, 9, 5000)])
+    o = _lib.selftest_math(xs)
+    assert np.max(np.abs(o[1] * xs - 1)) < 5e-12          # one Newton step: Newton step sizes
+    assert np.max(np.abs(o[2] * xs - 1)) < 4e-16          # two steps: geometry
+    assert np.max(np.abs(o[4] * np.sqrt(xs) - 1)) < 6e-16
+    big = rng.uniform(2.8e8, 3.0e8, 5000)                 # far-field phases k L / 1e3
+    o = _lib.selftest_math(big)
+    assert np.max(np.abs(o[6] - np.cos(big))) < 2e-15 and np.max(np.abs(o[7] - np.sin(big))) < 2e-15
+    mid = rng.uniform(-3e4, 3e4, 20000)                   # near-field phases
+    o = _lib.selftest_math(mid)
+    assert np.max(np.abs(o[8] - np.cos(mid))) < 1e-10 and np.max(np.abs(o[9] - np.sin(mid))) < 1e-10
+
+
 def test_nf_rx_rows():
     from solat_optics_b200 import ray_trace_int as rti
 
