@@ -560,17 +560,34 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
         }
     }
     __syncthreads();
-    // winners-only phasor sum: sum_cells exp(i k L/1e3) * E_rec / M^2   (ff_sim.py:215-221)
+    // winners-only phasor sum: sum_cells exp(i k L/1e3) * E_rec / M^2   (ff_sim.py:215-221).  Only a fraction of the
+    // cells holds a winner, so each warp compacts its winners through its queue and evaluates phasors with full lanes.
     double re[1] = {0.0}, im[1] = {0.0};
-    for (int c = tid; c < cells; c += FF_T) {
-        const unsigned long long key = win[c];
-        if (key != 0ull) {
-            double cs, sn;
-            cis_large(q.k * ff_key_opl(key, q.key_base, q.key_unit) / 1e3, cs, sn);
-            const double2 e = __ldg(q.e_rec + c);
-            re[0] += cs * e.x - sn * e.y;
-            im[0] += cs * e.y + sn * e.x;
+    cnt = 0;
+    for (int c0 = warp * 32;; c0 += FF_WARPS * 32) {
+        const bool more = c0 < cells;
+        if (more) {
+            const int c = c0 + lane;
+            const bool has = c < cells && win[c] != 0ull;
+            const unsigned m = __ballot_sync(0xffffffffu, has);
+            if (has) wq[cnt + __popc(m & ((1u << lane) - 1u))] = c;
+            cnt += __popc(m);
+            __syncwarp();
         }
+        if (cnt >= 32 || (!more && cnt > 0)) {
+            const int n_take = min(cnt, 32);
+            const int c = lane < n_take ? wq[cnt - 1 - lane] : -1;
+            cnt -= n_take;
+            __syncwarp();
+            if (c >= 0) {
+                double cs, sn;
+                cis_large(q.k * ff_key_opl(win[c], q.key_base, q.key_unit) / 1e3, cs, sn);
+                const double2 e = __ldg(q.e_rec + c);
+                re[0] += cs * e.x - sn * e.y;
+                im[0] += cs * e.y + sn * e.x;
+            }
+        }
+        if (!more && cnt == 0) break;
     }
     if (st) atomicOr(q.status, st);
     __shared__ double2 total;
