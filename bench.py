@@ -163,11 +163,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    host_pg = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=dev)
-        host_pg = dist.new_group(backend="gloo")
 
     ctx = _lib.context(local_rank)
     # ---- untimed set-up: E_rec from our own near-field map (config 0), plans, pinned buffers
@@ -221,16 +219,23 @@ def run_ours(args):
     launches = _lib.launch_count() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     kernel_ms = dev_ms / args.steps
-    # ---- end-to-end through the host-buffer C ABI (pinned host in, host out), gather of host results for N > 1
+    # ---- end-to-end: pinned host buffers in, host buffer out on rank 0, copies inside the timed region.
+    #      N = 1: the host-buffer C-ABI call (solat_ff_map_host).  N > 1: the same kernel through the device-pointer
+    #      entry with explicit H2D from pinned memory, one NCCL gather, and the D2H of the gathered map on rank 0.
     amp_np, phase_np, az_np = h_amp.numpy(), h_phase.numpy(), h_azel.numpy()
-    host_blocks = [torch.empty((2, npix), dtype=torch.float64) for _ in range(world)] if (world > 1 and rank == 0) else None
-    host_local = torch.empty((2, npix), dtype=torch.float64)
+    h_all = torch.empty((world, 2, npix), dtype=torch.float64).pin_memory() if rank == 0 else None
 
     def e2e_step():
-        plan.run(az_np, amp_np, phase_np)
-        if world > 1:
-            host_local[0].copy_(h_amp); host_local[1].copy_(h_phase)
-            dist.gather(host_local, host_blocks, dst=0, group=host_pg)
+        if world == 1:
+            plan.run(az_np, amp_np, phase_np)
+            return
+        d_azel.copy_(h_azel, non_blocking=True)
+        plan.run_device(d_azel, d_out[0], d_out[1], stream)
+        dist.gather(d_out, gathered, dst=0)
+        if rank == 0:
+            for r in range(world):
+                h_all[r].copy_(gathered[r], non_blocking=True)
+        torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
         e2e_step()
@@ -266,7 +271,8 @@ def run_ours(args):
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_azel.numel() * 8 * world),
                     "d2h_bytes_per_step": int(2 * npix * 8 * world), "ms_per_step": e2e_ms_max / args.steps,
-                    "api": "solat_ff_map_host via maps.FarFieldPlan.run (pinned host buffers)"},
+                    "api": "solat_ff_map_host via maps.FarFieldPlan.run (pinned host buffers)" if world == 1 else
+                           "pinned H2D + solat_ff_map_device + NCCL gather + D2H of the gathered map on rank 0"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,

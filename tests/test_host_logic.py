@@ -198,6 +198,21 @@ def test_output_txt_format(tmp_path):
     assert abs(back[0, 0] + 1.4544410433e-3) < 1e-12 and abs(back[0, 1] - (7.2e-5 - 1.4544410433e-3)) < 1e-11
 
 
+def test_far_field_grid_matches_shipped_reference_output():
+    """Coordinates of the one result file the reference ships (output_files/ff_1.32m_140GHz_highres.txt, produced by
+    `ff_sim.py 140 0.25 20 <offset>`): rows 0, 1, 41, 840, 1680 of its (az, el) columns, copied here as known
+    answers.  Its amplitude/phase columns cannot be reproduced (near-field input and pan_mod are not shipped)."""
+    from solat_optics_b200 import maps
+
+    shipped = {0: (-0.001454441043328608, -0.001382441043453024), 1: (-0.001454441043328608, -0.0013097189912865937),
+               41: (-0.0013817189911621776, -0.001382441043453024), 840: (0.0, 7.199999987558391e-05),
+               1680: (0.001454441043328608, 0.0015264410432041919)}
+    px = maps.ff_pixels(maps.ff_tele_geo(140, 1.32), 0.25, 20)
+    assert len(px) == 1681
+    for row, (az, el) in shipped.items():
+        assert px[row, 0] == az and abs(px[row, 1] - el) <= 1e-18
+
+
 def test_near_field_table_to_e_rec():
     from solat_optics_b200 import maps
 
