@@ -127,6 +127,26 @@ SOLAT_HD bool gt(double a, double b) { return a > b; }
 SOLAT_HD bool le(double a, double b) { return a <= b; }
 SOLAT_HD bool ge(double a, double b) { return a >= b; }
 SOLAT_HD bool is_nan(double a) { return a != a; }
+// Status tests on the integer pipe (a DSETP costs two FP64-pipe cycles; these compare the high word only, so a
+// boundary is resolved to ~1e-6 relative -- ample for "did the root stay in the reference's bracket").
+SOLAT_HD int hi_word(double a)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(a);
+#else
+    long long b;
+    memcpy(&b, &a, 8);
+    return (int)(b >> 32);
+#endif
+}
+// true unless lo <= t <= hi (0 <= lo < hi); NaN and negative t report out of range
+SOLAT_HD bool out_of_range(double t, double lo, double hi)
+{
+    const unsigned h = (unsigned)hi_word(t);              // negative numbers and NaN have huge unsigned high words
+    return h < (unsigned)hi_word(lo) || h > (unsigned)hi_word(hi);
+}
+SOLAT_HD bool abs_gt(double a, double tol) { return (hi_word(a) & 0x7fffffff) > hi_word(tol); }   // NaN: true
+SOLAT_HD bool not_finite(double a) { return (hi_word(a) & 0x7ff00000) == 0x7ff00000; }
 SOLAT_HD bool bnot(bool a) { return !a; }
 SOLAT_HD bool band(bool a, bool b) { return a && b; }
 SOLAT_HD bool any(bool a) { return a; }
@@ -185,6 +205,9 @@ SOLAT_HD b2 gt(d2 x, d2 y) { return mkb(x.a > y.a, x.b > y.b); }
 SOLAT_HD b2 le(d2 x, d2 y) { return mkb(x.a <= y.a, x.b <= y.b); }
 SOLAT_HD b2 ge(d2 x, d2 y) { return mkb(x.a >= y.a, x.b >= y.b); }
 SOLAT_HD b2 is_nan(d2 x) { return mkb(x.a != x.a, x.b != x.b); }
+SOLAT_HD b2 out_of_range(d2 t, double lo, double hi) { return mkb(out_of_range(t.a, lo, hi), out_of_range(t.b, lo, hi)); }
+SOLAT_HD b2 abs_gt(d2 a, double tol) { return mkb(abs_gt(a.a, tol), abs_gt(a.b, tol)); }
+SOLAT_HD b2 not_finite(d2 a) { return mkb(not_finite(a.a), not_finite(a.b)); }
 SOLAT_HD b2 bnot(b2 x) { return mkb(!x.a, !x.b); }
 SOLAT_HD b2 band(b2 x, b2 y) { return mkb(x.a && y.a, x.b && y.b); }
 SOLAT_HD bool any(b2 x) { return x.a || x.b; }
@@ -235,6 +258,14 @@ SOLAT_HD vec3t<R> refract_flat(const vec3t<R>& s, double ny, double mu)
     const R f = fma(R(mu), c, -sqrt_fast(k));
     // the x and z components keep the reference's NaN behaviour: f * 0 is NaN when f is
     return mk<R>(fma(f, R(0.0), mu * s.x), fma(f, R(ny), mu * s.y), fma(f, R(0.0), mu * s.z));
+}
+// refraction INTO the denser medium (mu < 1: no total internal reflection) at a flat with normal (0, -1, 0), ray
+// travelling towards +y: (mu sx, sqrt(1 - mu^2 (1 - sy^2)), mu sz)
+template <class R>
+SOLAT_HD vec3t<R> refract_flat_in(const vec3t<R>& s, double mu)
+{
+    const R k = fma(R(mu * mu), fma(s.y, s.y, R(-1.0)), R(1.0));
+    return mk<R>(mu * s.x, sqrt_fast(k), mu * s.z);
 }
 template <class R>
 SOLAT_HD vec3t<R> reflect(const vec3t<R>& s, const vec3t<R>& N)
@@ -350,15 +381,15 @@ SOLAT_HD typename Pack<R>::I asphere_hit(const Coef& C, const vec3t<R>& P, const
     // One FP64 update after the FP32 one leaves an error of C dt^2 with C <~ 4e-5 / mm for these lenses (nominal
     // rays: dt ~ 1e-4 mm, error ~ 1e-13 mm).  More updates only while |dt| > 1e-3 mm (error bound 4e-11 mm).
     SOLAT_ASPH_UPDATE()
-    for (int it = 2; any(gt(fabs(dt), R(1e-3))) && it < 10; ++it) SOLAT_ASPH_UPDATE()
+    for (int it = 2; any(abs_gt(dt, 1e-3)) && it < 10; ++it) SOLAT_ASPH_UPDATE()
     SOLAT_ASPH_SLOPE()                     // slope at the converged point, for the normal
 #undef SOLAT_ASPH_UPDATE
 #undef SOLAT_ASPH_SLOPE
     H = mk<R>(x, fma(d.y, t, P.y), z);
     const R nn = rsqrt_fast(fma(G * G, u, R(1.0)));
     N = mk<R>(-x * G * nn, nn, -z * G * nn);
-    I st = imask(bnot(is_nan(dt)), flag(bnot(le(fabs(dt), R(1e-3))), ST_NOCONV)) | flag(is_nan(dt), ST_NAN);
-    st |= flag(bnot(band(ge(t, R(lo)), le(t, R(hi)))), ST_BRACKET);
+    I st = imask(bnot(not_finite(dt)), flag(abs_gt(dt, 1e-3), ST_NOCONV)) | flag(not_finite(dt), ST_NAN);
+    st |= flag(out_of_range(t, lo, hi), ST_BRACKET);
     return st;
 }
 
@@ -368,7 +399,7 @@ SOLAT_HD typename Pack<R>::I plane_hit(const vec3t<R>& P, const vec3t<R>& d, dou
 {
     t = (R(-y0) - P.y) * rcp_fast(d.y);
     H = axpy(P, d, t);
-    return flag(bnot(band(ge(t, R(lo)), le(t, R(hi)))), ST_BRACKET);
+    return flag(out_of_range(t, lo, hi), ST_BRACKET);
 }
 
 // -- source_to_lyot_model.trace_rays, ray_trace_int.py:929-1373 --------------------------------
@@ -389,7 +420,7 @@ SOLAT_HD void nf_source_ray(const Coef& C, const vec3t<R>& p0, const vec3t<R>& d
     R t1, t2, t3, t4, t5;
     vec3t<R> N, d;
     I st = plane_hit(p0, d0, C.plane[PLANE_1B], 5.0, 14000.0, t1, r.p1b);                   // rti:967
-    d = refract_flat(d0, -1.0, mu_in);                                          // rti:992
+    d = refract_flat_in(d0, mu_in);                                             // rti:992
     const I st1a = asphere_hit<SURF_1A>(C, r.p1b, d, 1.0, 900.0, t2, r.p1a, N);   // rti:1033
     // rti:1086 (radius >= 196 -> zero column; compared squared).  A NaN radius means the iterate left the domain of the conic
     // (r > 417 mm), where the reference's root function substitutes sag = 0 and then vignettes too.
@@ -402,13 +433,13 @@ SOLAT_HD void nf_source_ray(const Coef& C, const vec3t<R>& p0, const vec3t<R>& d
     alive = band(alive, lt(fma(r.p2b.x, r.p2b.x, r.p2b.z * r.p2b.z), R(176.0 * 176.0)));   // rti:1177
     r.valid = alive; r.status = st;
     if (!any(alive)) return;
-    d = refract_flat(d, -1.0, mu_in);                                           // rti:1154 (-n_hat)
+    d = refract_flat_in(d, mu_in);                                              // rti:1154 (-n_hat)
     st |= imask(alive, asphere_hit<SURF_2A>(C, r.p2b, d, 0.0, 100.0, t4, r.p2a, N));   // rti:1228
     d = refract(d, neg(N), mu_out);                                             // rti:1254
     st |= imask(alive, plane_hit(r.p2a, d, C.plane[PLANE_LYOT], 10.0, 900.0, t5, r.lyot));  // rti:1295
     r.d_out = d;
     const R opl = (t1) + (t2 * n_si) + (t3) + (t4 * n_si) + t5;                 // rti:1341-1343
-    st |= flag(band(alive, is_nan(opl)), ST_NAN);
+    st |= flag(band(alive, not_finite(opl)), ST_NAN);
     r.opl = select(alive, opl, R(0.0));
     r.status = st;
 }
@@ -706,13 +737,13 @@ SOLAT_HD typename Pack<R>::I mirror_hit(const Coef& C, const vec3t<R>& P, const 
     };
     update();
     update();                                             // ~1e-11 mm on nominal rays
-    for (int it = 3; any(gt(fabs(dt), R(1e-8))) && it < 12; ++it) update();   // off-nominal rays only
+    for (int it = 3; any(abs_gt(dt, 1e-8)) && it < 12; ++it) update();   // off-nominal rays only
     H = axpy(P, D, t);
     if (PANEL) mirror_sag<M, R>(C, H.x, H.y, z, zx, zy);   // reference normal = ideal-mirror gradient (saf:718-720, :869-871)
     const R nn = rsqrt_fast(fma(zx, zx, fma(zy, zy, R(1.0))));
     N = mk<R>(-zx * nn, -zy * nn, nn);
-    I st = imask(bnot(is_nan(dt)), flag(bnot(le(fabs(dt), R(1e-8))), ST_NOCONV)) | flag(is_nan(dt), ST_NAN);
-    st |= flag(bnot(band(ge(t, R(lo)), le(t, R(hi)))), ST_BRACKET);
+    I st = imask(bnot(not_finite(dt)), flag(abs_gt(dt, 1e-8), ST_NOCONV)) | flag(not_finite(dt), ST_NAN);
+    st |= flag(out_of_range(t, lo, hi), ST_BRACKET);
     return st;
 }
 
@@ -778,11 +809,11 @@ SOLAT_HD void ff_ray_trace(const Coef& C, const FfFrames& f, const vec3t<R>& d, 
         const vec3t<R> dt3 = apply_lin(f.b2, reflect(d2, N));                   // saf:883-930
         const vec3t<R> fr = mk<R>(R(f.foc_row[0]), R(f.foc_row[1]), R(f.foc_row[2]));
         const R tf = (R(foc_y) - (dot(fr, r.m2) + R(f.foc_off))) * rcp_fast(dot(fr, dt3));   // saf:947-962
-        st |= flag(bnot(band(ge(tf, R(1e3)), le(tf, R(15e3)))), ST_BRACKET);
+        st |= flag(out_of_range(tf, 1e3, 15e3), ST_BRACKET);
         r.foc = axpy(r.m2, dt3, tf);
         r.d_out = dt3;
         r.opl = ((t_ap + t1) + t2) + tf;                                        // saf:970
-        st |= flag(is_nan(r.opl), ST_NAN);
+        st |= flag(not_finite(r.opl), ST_NAN);
     }
     r.status = st;
 }
@@ -807,13 +838,13 @@ SOLAT_HD void ff_ray_lean(const Coef& C, const FfFrames& f, const vec3t<R>& d, R
     const R num = R(foc_y) - fma(R(f.foc_l[0]), H.x, fma(R(f.foc_l[1]), H.y, fma(R(f.foc_l[2]), H.z, R(f.foc_l[3]))));
     const R den = fma(R(f.foc_d[0]), r2.x, fma(R(f.foc_d[1]), r2.y, R(f.foc_d[2]) * r2.z));
     const R tf = num * rcp_fast(den);                                                        // saf:947-962
-    st |= flag(bnot(band(ge(tf, R(1e3)), le(tf, R(15e3)))), ST_BRACKET);
+    st |= flag(out_of_range(tf, 1e3, 15e3), ST_BRACKET);
     fx = fma(tf, fma(R(f.fx_d[0]), r2.x, fma(R(f.fx_d[1]), r2.y, R(f.fx_d[2]) * r2.z)),
              fma(R(f.fx_l[0]), H.x, fma(R(f.fx_l[1]), H.y, fma(R(f.fx_l[2]), H.z, R(f.fx_l[3])))));
     fz = fma(tf, fma(R(f.fz_d[0]), r2.x, fma(R(f.fz_d[1]), r2.y, R(f.fz_d[2]) * r2.z)),
              fma(R(f.fz_l[0]), H.x, fma(R(f.fz_l[1]), H.y, fma(R(f.fz_l[2]), H.z, R(f.fz_l[3])))));
     opl = ((t_ap + t1) + t2) + tf;                                                           // saf:970
-    st |= flag(is_nan(opl), ST_NAN);
+    st |= flag(not_finite(opl), ST_NAN);
     status = st;
 }
 
