@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
             {
                 const int l = 0;
 #endif
-                if (rr[l] >= 0 && oo[l] != 0.0) {                                   // ffl:10
+                if (rr[l] >= 0 && oo[l] != 0.0 && !not_finite(oo[l])) {              // ffl:10
                     const int cell = ff_cell(fx[l] - cx, fz[l] - cz, q.grid);
                     if (cell >= 0) {
                         bool exact;

@@ -989,8 +989,11 @@ SOLAT_HD int ff_cell(double fx_mm, double fz_mm, const FfGrid& G)
 {
     const double xx = div10(fx_mm), yy = div10(fz_mm);                          // ffl:12-13: / 1e1
     if (G.gx_max < xx || G.gy_max < yy) return -1;
+    if (not_finite(xx) || not_finite(yy)) return -1;       // a NaN ray never reaches a cell (flagged ST_NAN upstream)
     const int ix = searchsorted_guess(G.gx, G.M, 1, xx, G.gx[0], G.inv_dx);     // ffl:22
+    if (ix >= G.M) return -1;                              // only possible on an unsorted grid
     const int iy = searchsorted_guess(G.gy + ix, G.M, G.M, yy, G.gy[ix], G.inv_dy);   // ffl:23
+    if (iy >= G.M) return -1;
     return iy * G.M + ix;
 }
 
