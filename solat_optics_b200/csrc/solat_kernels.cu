@@ -472,12 +472,21 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
     FfFrames* fr = reinterpret_cast<FfFrames*>(smem_raw);
     unsigned long long* win = reinterpret_cast<unsigned long long*>(smem_raw + ((sizeof(FfFrames) + 15) / 16) * 16);
     int* queues = reinterpret_cast<int*>(win + cells);          // [FF_WARPS][FF_WQ]
+    double* s_gx = reinterpret_cast<double*>(queues + FF_WARPS * FF_WQ);   // [M] data_x[0, :]
+    double* s_gy = s_gx + q.grid.M;                                        // [M] data_y[:, 0] when all columns agree
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
     const FfGeom g = to_geom(q.g);
     const Coef& sC = K_COEF;   // constant bank; a shared-memory copy measured 4 % slower (profiles/r01_variants.md)
     if (tid == 0) ff_build_frames(K_COEF, g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
     for (int c = tid; c < cells; c += FF_T) win[c] = 0ull;
+    FfGrid grid = q.grid;                                   // grid axes on chip: the binning does 2-4 dependent reads per ray
+    for (int i = tid; i < grid.M; i += FF_T) {
+        s_gx[i] = __ldg(q.grid.gx + i);
+        if (grid.y_uniform) s_gy[i] = __ldg(q.grid.gy + (size_t)i * grid.M);
+    }
+    grid.gx = s_gx;
+    if (grid.y_uniform) { grid.gy = s_gy; grid.gy_cs = 0; grid.gy_rs = 1; }
     __syncthreads();
 
     int* wq = queues + warp * FF_WQ;
@@ -548,7 +557,7 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
                 const int l = 0;
 #endif
                 if (rr[l] >= 0 && oo[l] != 0.0 && !not_finite(oo[l])) {              // ffl:10
-                    const int cell = ff_cell(fx[l] - cx, fz[l] - cz, q.grid);
+                    const int cell = ff_cell(fx[l] - cx, fz[l] - cz, grid);
                     if (cell >= 0) {
                         bool exact;
                         const unsigned long long key = ff_key(rr[l], oo[l], q.key_base, q.key_inv_unit, exact, q.key_unit);
@@ -603,7 +612,8 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
 static size_t ff_map_smem(int M)
 {
     const size_t cells = (size_t)M * M;
-    return ((sizeof(FfFrames) + 15) / 16) * 16 + cells * sizeof(unsigned long long) + (size_t)FF_WARPS * FF_WQ * sizeof(int);
+    return ((sizeof(FfFrames) + 15) / 16) * 16 + cells * sizeof(unsigned long long) + (size_t)FF_WARPS * FF_WQ * sizeof(int) +
+           2 * (size_t)M * sizeof(double);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1069,13 +1079,17 @@ int solat_ff_apert_fields(solat_ctx* c, const solat_ff_geom* g, const double* th
 static FfGrid make_grid(const double* data_x, const double* data_y, int M, const double* d_gx, const double* d_gy)
 {
     FfGrid G;
-    G.gx = d_gx; G.gy = d_gy; G.M = M;
+    G.gx = d_gx; G.gy = d_gy; G.M = M; G.gy_cs = 1; G.gy_rs = M;
+    G.y_uniform = 1;
+    for (int i = 0; i < M && G.y_uniform; i++)
+        for (int j = 1; j < M; j++)
+            if (data_y[(size_t)i * M + j] != data_y[(size_t)i * M]) { G.y_uniform = 0; break; }
     double a = data_x[0], b = data_y[0];
     for (int i = 1; i < M; i++) { a = fmax(a, data_x[i]); b = fmax(b, data_y[(size_t)i * M]); }   // ffl:19
     G.gx_max = a; G.gy_max = b;
     const double sx = data_x[M - 1] - data_x[0], sy = data_y[(size_t)(M - 1) * M] - data_y[0];
-    G.inv_dx = (M > 1 && sx > 0) ? (M - 1) / sx : 0.0;     // first guess of searchsorted; the fix-up makes it exact
-    G.inv_dy = (M > 1 && sy > 0) ? (M - 1) / sy : 0.0;
+    G.inv_dx = (M > 1 && sx > 0) ? (float)((M - 1) / sx) : 0.0f;   // first guess of searchsorted; the fix-up makes it exact
+    G.inv_dy = (M > 1 && sy > 0) ? (float)((M - 1) / sy) : 0.0f;
     return G;
 }
 

@@ -957,12 +957,13 @@ SOLAT_HD void pack_ff_rows(const FfRay& r, const double* centre, double* rows)
     for (int i = 0; i < 17; i++) rows[i] = v[i];
 }
 
-// np.searchsorted(a, v, 'left') from an interpolated first guess, then an exact fix-up against the array
-// itself: one or two loads on a uniform grid, still exact (only slower) on any sorted grid.
-SOLAT_HD int searchsorted_guess(const double* a, int n, int stride, double v, double a0, double inv_step)
+// np.searchsorted(a, v, 'left') from an interpolated first guess (single precision is enough for a guess), then an
+// exact fix-up against the array itself: one or two loads on a uniform grid, still exact (only slower) on any
+// sorted grid.
+SOLAT_HD int searchsorted_guess(const double* a, int n, int stride, double v, double a0, float inv_step)
 {
-    double g = ceil((v - a0) * inv_step);
-    int i = g > 0.0 ? (g < (double)n ? (int)g : n) : 0;
+    const float g = ceilf((float)(v - a0) * inv_step);
+    int i = g > 0.0f ? (g < (float)n ? (int)g : n) : 0;
     while (i > 0 && !(a[(long)(i - 1) * stride] < v)) --i;
     while (i < n && a[(long)i * stride] < v) ++i;
     return i;
@@ -980,10 +981,11 @@ SOLAT_HD double div10(double x)
 // the reference skips the ray.  gx = data_x[0,:] (M), gy = data_y (M x M row-major).
 struct FfGrid {
     const double* gx;      // data_x[0, :]
-    const double* gy;      // data_y, (M, M) row-major
-    int M;
+    const double* gy;      // data_y, (M, M) row-major; column ix is gy[ix * gy_cs + i * gy_rs]
+    int M, gy_cs, gy_rs;   // (1, M) for the full array; (0, 1) when every column is the same and gy holds just one
+    int y_uniform;         // host: all columns of data_y are identical (a kernel may then stage one column on chip)
     double gx_max, gy_max; // ffl:19: rays beyond these are skipped
-    double inv_dx, inv_dy; // (M-1)/(last-first) of gx and of gy[:,0]; 0 when not usable as a guess
+    float inv_dx, inv_dy;  // (M-1)/(last-first) of gx and of gy[:,0]; 0 when not usable as a guess
 };
 SOLAT_HD int ff_cell(double fx_mm, double fz_mm, const FfGrid& G)
 {
@@ -992,7 +994,8 @@ SOLAT_HD int ff_cell(double fx_mm, double fz_mm, const FfGrid& G)
     if (not_finite(xx) || not_finite(yy)) return -1;       // a NaN ray never reaches a cell (flagged ST_NAN upstream)
     const int ix = searchsorted_guess(G.gx, G.M, 1, xx, G.gx[0], G.inv_dx);     // ffl:22
     if (ix >= G.M) return -1;                              // only possible on an unsorted grid
-    const int iy = searchsorted_guess(G.gy + ix, G.M, G.M, yy, G.gy[ix], G.inv_dy);   // ffl:23
+    const double* col = G.gy + ix * G.gy_cs;
+    const int iy = searchsorted_guess(col, G.M, G.gy_rs, yy, col[0], G.inv_dy);      // ffl:23
     if (iy >= G.M) return -1;
     return iy * G.M + ix;
 }

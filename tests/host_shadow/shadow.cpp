@@ -119,12 +119,12 @@ API int shadow_nf_pixel2(const double* p, const double* th, int nth, const doubl
 static FfGrid make_grid(const double* gx_full, const double* gy, int M)
 {
     FfGrid G;
-    G.gx = gx_full; G.gy = gy; G.M = M;
+    G.gx = gx_full; G.gy = gy; G.M = M; G.gy_cs = 1; G.gy_rs = M; G.y_uniform = 0;
     G.gx_max = gx_full[0]; G.gy_max = gy[0];
     for (int i = 0; i < M; i++) { G.gx_max = fmax(G.gx_max, gx_full[i]); G.gy_max = fmax(G.gy_max, gy[(size_t)i * M]); }
     const double sx = gx_full[M - 1] - gx_full[0], sy = gy[(size_t)(M - 1) * M] - gy[0];
-    G.inv_dx = (M > 1 && sx > 0) ? (M - 1) / sx : 0.0;
-    G.inv_dy = (M > 1 && sy > 0) ? (M - 1) / sy : 0.0;
+    G.inv_dx = (M > 1 && sx > 0) ? (float)((M - 1) / sx) : 0.0f;
+    G.inv_dy = (M > 1 && sy > 0) ? (float)((M - 1) / sy) : 0.0f;
     return G;
 }
 
