@@ -30,9 +30,6 @@ using namespace solat;
 #ifndef SOLAT_FF_T
 #define SOLAT_FF_T 256      // threads per far-field CTA (= rays per batch)
 #endif
-#ifndef SOLAT_FF_PACK
-#define SOLAT_FF_PACK 1     // rays traced in lock step per thread (1: scalar, 2: d2 packs)
-#endif
 #ifndef SOLAT_FF_MINB
 #define SOLAT_FF_MINB 3     // resident far-field CTAs per SM the register allocation is capped for
 #endif
@@ -442,7 +439,8 @@ __global__ void ff_project_fill_kernel(const double* sim, int n_pts, const int* 
 // ------------------------------------------------------------------------------------------------
 constexpr int FF_T = SOLAT_FF_T;
 constexpr int FF_WARPS = FF_T / 32;
-constexpr int FF_WQ = 32 * (SOLAT_FF_PACK + 1);   // per-warp queue capacity
+constexpr int FF_WQ = 64;            // per-warp queue capacity
+constexpr int FF_MAX_ROWS = 4096;    // phi rows the interval walk keeps on chip; larger fans take the queue walk
 struct FfMapParams {
     AngleTabs ang;
     solat_ff_geom g;
@@ -454,14 +452,19 @@ struct FfMapParams {
     double* amp;
     double* phase;
     int* status;
+    int rows;                // host: theta is strictly monotone inside one branch of tan -> interval walk allowed
 };
 
-// One CTA per (az, el) pixel, warps fully autonomous inside the ray loop (no CTA barrier):
-//   * each warp walks its share of the launch fan in chunks of 32 candidate rays, runs the cheap aperture test
-//     and compacts the survivors into its own shared-memory queue (ballot + popc);
-//   * whenever the queue holds a full batch, every lane pops SOLAT_FF_PACK rays and traces them (two mirrors,
-//     Newton in lock step for the pack) -- so the expensive stage always runs with full warps although 40 % of
-//     the fan misses the aperture;
+// One CTA per (az, el) pixel, warps fully autonomous inside the ray loop (no CTA barrier).
+//   * Which rays pass the aperture (saf:378, 60 % of the default fan):
+//     - interval walk (theta monotone, the reference's linspace fans): the rays of one phi row hit the aperture
+//       plane along a straight line, so the accepted rays of a row are ONE index interval.  One thread per row finds
+//       it with the exact FP64 test (bisection for the closest ray, then for both rim crossings: ~4 log2(nth)
+//       evaluations instead of nth); a prefix sum turns the intervals into a dense list every warp indexes directly.
+//     - queue walk (any other fan, or a pixel whose plane-hit denominator changes sign along a row): each warp
+//       tests chunks of 32 candidate rays (FP32 prefilter, FP64 near the rim) and compacts the survivors into its
+//       own shared-memory queue (ballot + popc), popping a full batch whenever there is one.
+//     Either way the expensive two-mirror trace always runs with full warps.
 //   * the reference's "later ray overwrites the cell" becomes one 64-bit shared-memory atomicMax per ray on a
 //     key that carries the ray index above an exact fixed-point copy of its path length;
 //   * after one barrier the winners -- and only they -- get their phasor, are weighted by E_rec and reduced.
@@ -474,11 +477,17 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
     int* queues = reinterpret_cast<int*>(win + cells);          // [FF_WARPS][FF_WQ]
     double* s_gx = reinterpret_cast<double*>(queues + FF_WARPS * FF_WQ);   // [M] data_x[0, :]
     double* s_gy = s_gx + q.grid.M;                                        // [M] data_y[:, 0] when all columns agree
+    int* row_lo = reinterpret_cast<int*>(s_gy + q.grid.M);                 // [nph] first accepted theta index of a row
+    int* row_pre = row_lo + (q.rows ? q.ang.nph : 0);                      // [nph + 1] accepted rays before the row
+    __shared__ int s_queue_walk;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
     const FfGeom g = to_geom(q.g);
     const Coef& sC = K_COEF;   // constant bank; a shared-memory copy measured 4 % slower (profiles/r01_variants.md)
-    if (tid == 0) ff_build_frames(K_COEF, g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
+    if (tid == 0) {
+        ff_build_frames(K_COEF, g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
+        s_queue_walk = !q.rows;
+    }
     for (int c = tid; c < cells; c += FF_T) win[c] = 0ull;
     FfGrid grid = q.grid;                                   // grid axes on chip: the binning does 2-4 dependent reads per ray
     for (int i = tid; i < grid.M; i += FF_T) {
@@ -489,81 +498,111 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
     if (grid.y_uniform) { grid.gy = s_gy; grid.gy_cs = 0; grid.gy_rs = 1; }
     __syncthreads();
 
+    const int nth = q.ang.nth, n_rays = nth * q.ang.nph;
+    if (q.rows) {
+        // accepted interval [lo, hi) of every phi row
+        for (int j = tid; j < q.ang.nph; j += FF_T) {
+            int lo, hi;
+            if (!ff_row_interval(sC, g, *fr, q.ang.st, q.ang.ct, nth, __ldg(q.ang.sp + j), __ldg(q.ang.cp + j), lo, hi))
+                s_queue_walk = 1;                                // the row does not stay on one side of the plane's horizon
+            row_lo[j] = lo;
+            row_pre[j + 1] = hi - lo;
+        }
+        __syncthreads();
+        if (warp == 0) {                                         // exclusive prefix sum of the row counts
+            int carry = 0;
+            for (int base = 0; base < q.ang.nph; base += 32) {
+                const int j = base + lane;
+                int v = j < q.ang.nph ? row_pre[j + 1] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += u;
+                }
+                if (j < q.ang.nph) row_pre[j + 1] = carry + v;
+                carry += __shfl_sync(0xffffffffu, v, 31);
+            }
+            if (lane == 0) row_pre[0] = 0;
+        }
+        __syncthreads();
+    }
+    const bool queue_walk = s_queue_walk != 0;
+
     int* wq = queues + warp * FF_WQ;
-    const int n_rays = q.ang.nth * q.ang.nph;
     const double cx = fr->centre[0], cz = fr->centre[2];
     int st = 0, cnt = 0;                                   // cnt: queue fill, identical in all lanes of the warp
     int chunk = warp;
-    for (;;) {
-        const bool more = chunk * 32 < n_rays;
-        if (cnt < 32 * SOLAT_FF_PACK && more) {
-            // fill: aperture test (saf:359-379) on 32 candidate rays
-            const int r = chunk * 32 + lane;
-            bool ok = false;
-            if (r < n_rays) {
-                // FP32 prefilter on the FMA pipe; only rays within ~0.02 mm of the rim need the FP64 test
-                int i, j;
-                ray_ij(q.ang, r, i, j);
-                const float stf = __ldg(q.ang.stf + i);
-                const int v = ff_aperture_coarse(*fr, stf * __ldg(q.ang.cpf + j), stf * __ldg(q.ang.spf + j), __ldg(q.ang.ctf + i));
-                ok = v > 0;
-                if (v < 0) {
-                    vec3 Pa;
-                    double t_ap;
-                    ok = ff_aperture(sC, g, *fr, ray_dir(q.ang, r), t_ap, Pa);
-                }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) wq[cnt + __popc(m & ((1u << lane) - 1u))] = r;
-            cnt += __popc(m);
-            chunk += FF_WARPS;
-            __syncwarp();
-            continue;
+    // interval walk: warp w owns accepted rays [v, v_end) of the pixel's dense list, 32 per step
+    int v = 0, v_end = 0, row = 0;
+    if (!queue_walk) {
+        const int n_acc = row_pre[q.ang.nph];
+        const int per = (n_acc + FF_WARPS - 1) / FF_WARPS;
+        v = min(warp * per, n_acc) + lane;
+        v_end = min((warp + 1) * per, n_acc);
+        int a = 0, b = q.ang.nph - 1;                      // row of the lane's first ray: last row with row_pre[row] <= v
+        while (a < b) {
+            const int m = (a + b + 1) >> 1;
+            if (row_pre[m] <= v) a = m; else b = m - 1;
         }
-        if (cnt == 0) break;
-        const int n_take = min(cnt, 32 * SOLAT_FF_PACK);
-        const int r0 = lane < n_take ? wq[cnt - 1 - lane] : -1;
-#if SOLAT_FF_PACK == 2
-        const int r1 = lane + 32 < n_take ? wq[cnt - 33 - lane] : -1;
-#endif
-        cnt -= n_take;
-        __syncwarp();
+        row = a;
+    }
+    for (;;) {
+        int r0 = -1;
+        if (!queue_walk) {
+            if (v - lane >= v_end) break;
+            if (v < v_end) {
+                while (row_pre[row + 1] <= v) ++row;
+                r0 = row * nth + row_lo[row] + (v - row_pre[row]);
+            }
+            v += 32;
+        } else {
+            const bool more = chunk * 32 < n_rays;
+            if (cnt < 32 && more) {
+                // fill: aperture test (saf:359-379) on 32 candidate rays
+                const int r = chunk * 32 + lane;
+                bool ok = false;
+                if (r < n_rays) {
+                    // FP32 prefilter on the FMA pipe; only rays within ~0.02 mm of the rim need the FP64 test
+                    int i, j;
+                    ray_ij(q.ang, r, i, j);
+                    const float stf = __ldg(q.ang.stf + i);
+                    const int c = ff_aperture_coarse(*fr, stf * __ldg(q.ang.cpf + j), stf * __ldg(q.ang.spf + j), __ldg(q.ang.ctf + i));
+                    ok = c > 0;
+                    if (c < 0) {
+                        vec3 Pa;
+                        double t_ap;
+                        ok = ff_aperture(sC, g, *fr, ray_dir(q.ang, r), t_ap, Pa);
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) wq[cnt + __popc(m & ((1u << lane) - 1u))] = r;
+                cnt += __popc(m);
+                chunk += FF_WARPS;
+                __syncwarp();
+                continue;
+            }
+            if (cnt == 0) break;
+            const int n_take = min(cnt, 32);
+            r0 = lane < n_take ? wq[cnt - 1 - lane] : -1;
+            cnt -= n_take;
+            __syncwarp();
+        }
         if (r0 >= 0) {
-#if SOLAT_FF_PACK == 2
-            const vec3t<d2> d = ray_dir2(q.ang, r0, r1 >= 0 ? r1 : r0);
-            vec3t<d2> Pa;
-            d2 t_ap;
-            ff_aperture(sC, g, *fr, d, t_ap, Pa);
-            d2 opl2, fx2, fz2;
-            i2 st2;
-            ff_ray_lean<d2>(sC, *fr, d, t_ap, Pa, g.foc_y, opl2, fx2, fz2, st2);
-            st |= st2.a | (r1 >= 0 ? st2.b : 0);
-            const int rr[2] = {r0, r1};
-            const double oo[2] = {opl2.a, opl2.b}, fx[2] = {fx2.a, fx2.b}, fz[2] = {fz2.a, fz2.b};
-#pragma unroll
-            for (int l = 0; l < 2; l++) {
-#else
             const vec3 d = ray_dir(q.ang, r0);
             vec3 Pa;
             double t_ap;
             ff_aperture(sC, g, *fr, d, t_ap, Pa);
-            double ropl, rfx, rfz;
+            double opl, fx, fz;
             int rst;
-            ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, ropl, rfx, rfz, rst);
+            ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);
             st |= rst;
-            const int rr[1] = {r0};
-            const double oo[1] = {ropl}, fx[1] = {rfx}, fz[1] = {rfz};
-            {
-                const int l = 0;
-#endif
-                if (rr[l] >= 0 && oo[l] != 0.0 && !not_finite(oo[l])) {              // ffl:10
-                    const int cell = ff_cell(fx[l] - cx, fz[l] - cz, grid);
-                    if (cell >= 0) {
-                        bool exact;
-                        const unsigned long long key = ff_key(rr[l], oo[l], q.key_base, q.key_inv_unit, exact, q.key_unit);
-                        if (!exact) st |= ST_RANGE;
-                        atomicMax(win + cell, key);                                 // ffl:28: last write wins
-                    }
+            if (opl != 0.0 && !not_finite(opl)) {                                   // ffl:10
+                const int cell = ff_cell(fx - cx, fz - cz, grid);
+                if (cell >= 0) {
+                    bool exact;
+                    const unsigned long long key = ff_key(r0, opl, q.key_base, q.key_inv_unit, exact, q.key_unit);
+                    if (!exact) st |= ST_RANGE;
+                    atomicMax(win + cell, key);                                     // ffl:28: last write wins
                 }
             }
         }
@@ -609,11 +648,28 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
     }
 }
 
-static size_t ff_map_smem(int M)
+// The interval walk needs the rays of a phi row to move monotonically along their line in the aperture plane:
+// theta strictly monotone, inside one branch of tan (cos theta keeps its sign, never ~0), steps far above the
+// rounding of the radius test.
+static bool ff_rows_usable(const double* theta, int nth, int nph)
+{
+    if (nph <= 0 || nph > FF_MAX_ROWS || nth < 2) return false;
+    const char* env = getenv("SOLAT_FF_QUEUE_WALK");
+    if (env && env[0] == '1') return false;
+    const double dir = theta[1] - theta[0];
+    for (int i = 0; i < nth; i++) {
+        const double c = cos(theta[i]);
+        if (!(c * cos(theta[0]) > 0.0) || !(fabs(c) > 1e-6)) return false;
+        if (i && !((theta[i] - theta[i - 1]) * dir > 0.0 && fabs(theta[i] - theta[i - 1]) >= 1e-10)) return false;
+    }
+    return true;
+}
+
+static size_t ff_map_smem(int M, int rows_nph)
 {
     const size_t cells = (size_t)M * M;
     return ((sizeof(FfFrames) + 15) / 16) * 16 + cells * sizeof(unsigned long long) + (size_t)FF_WARPS * FF_WQ * sizeof(int) +
-           2 * (size_t)M * sizeof(double);
+           2 * (size_t)M * sizeof(double) + (rows_nph ? (2 * (size_t)rows_nph + 1) * sizeof(int) : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1133,7 +1189,7 @@ struct solat_ff_plan {
     DevBuf<int> status;
     FfGrid grid;
     double k, key_base, key_unit;
-    int M, n_rays;
+    int M, n_rays, rows;
     size_t smem;
 };
 
@@ -1143,7 +1199,7 @@ static int ff_map_launch(solat_ff_plan* p, const double* d_azel, int npix, doubl
     FfMapParams q;
     q.ang = p->ang.tabs; q.g = p->g; q.azel = d_azel; q.grid = p->grid; q.e_rec = p->e_rec.p;
     q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
-    q.amp = d_amp; q.phase = d_phase; q.status = p->status.p;
+    q.amp = d_amp; q.phase = d_phase; q.status = p->status.p; q.rows = p->rows;
     ff_map_kernel<<<npix, FF_T, p->smem, s>>>(q);
     LAUNCHED();
     return SOLAT_OK;
@@ -1158,7 +1214,8 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
     if (!c || !g || !theta || !phi || !data_x || !data_y || !e_rec || !out || nth <= 0 || nph <= 0 || M <= 0)
         return fail(SOLAT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(c->device));
-    size_t smem = ff_map_smem(M);
+    const int rows = ff_rows_usable(theta, nth, nph) ? 1 : 0;
+    size_t smem = ff_map_smem(M, rows ? nph : 0);
     if (const char* pad = getenv("SOLAT_FF_SMEM_PAD")) smem += (size_t)atol(pad);   // occupancy experiments only
     if (smem > (size_t)c->prop.sharedMemPerBlockOptin)
         return fail(SOLAT_ERR_ARG, "E_rec grid too large for the shared-memory winner table (M <= 168)");
@@ -1166,7 +1223,7 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
         return fail(SOLAT_ERR_ARG, "launch fan too large for the 20-bit ray index of the winner key (<= 1048575 rays)");
     CK(cudaFuncSetAttribute(ff_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     solat_ff_plan* p = new solat_ff_plan();
-    p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem; p->n_rays = nth * nph;
+    p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem; p->n_rays = nth * nph; p->rows = rows;
     // fixed-point frame of the winner keys: every path length of this telescope lies within a few tens of metres
     // of |source - rotation centre| + 2.2e4 mm; unit = half an ulp of that, so the offsets are exact integers
     {

@@ -758,6 +758,58 @@ SOLAT_HD typename Pack<R>::B ff_aperture(const Coef& C, const FfGeom& g, const F
     return bnot(gt(fma(Pa.x, Pa.x, dy * dy), R(C.ff[3])));
 }
 
+// unit launch direction of ray (theta, phi)
+SOLAT_HD vec3 launch_dir(double sin_th, double cos_th, double sin_ph, double cos_ph)
+{
+    return mk(sin_th * cos_ph, sin_th * sin_ph, cos_th);   // rti:628, saf:345
+}
+
+// Accepted rays of one phi row of a launch fan whose theta is strictly monotone inside one branch of tan: the rays
+// of the row hit the aperture plane along a straight line, monotonically, so the squared radius about the M1 centre
+// is unimodal in the theta index and the accepted rays (ff_aperture, the same FP64 operations) are ONE interval
+// [lo, hi).  Bisection for the closest ray, then for both rim crossings: ~4 log2(nth) evaluations instead of nth.
+// Returns false when the plane-hit denominator changes sign along the row (rays skimming the aperture plane's
+// horizon: the caller must test every ray instead).
+SOLAT_HD bool ff_row_interval(const Coef& C, const FfGeom& g, const FfFrames& f, const double* st, const double* ct, int nth,
+                              double sp, double cp, int& lo, int& hi)
+{
+    auto r2 = [&](int i) {
+        const vec3 d = launch_dir(st[i], ct[i], sp, cp);
+        vec3 Pa;
+        double t_ap;
+        ff_aperture(C, g, f, d, t_ap, Pa);
+        const double dy = Pa.y - C.ff[2];
+        return fma(Pa.x, Pa.x, dy * dy);
+    };
+    auto den = [&](int i) {
+        const vec3 d = launch_dir(st[i], ct[i], sp, cp);
+        return fma(f.ap_row[0], d.x, fma(f.ap_row[1], d.y, f.ap_row[2] * d.z));
+    };
+    const bool one_sided = den(0) * den(nth - 1) > 0.0;
+    int a = 0, b = nth - 1;
+    while (a < b) {
+        const int m = (a + b) >> 1;
+        if (r2(m + 1) < r2(m)) a = m + 1; else b = m;
+    }
+    const int imin = a;
+    lo = hi = 0;
+    if (!(r2(imin) > C.ff[3])) {
+        a = -1; b = imin;                                    // a rejected (or before the row), b accepted
+        while (a + 1 < b) {
+            const int m = (a + b) >> 1;
+            if (r2(m) > C.ff[3]) a = m; else b = m;
+        }
+        lo = b;
+        a = imin; b = nth;                                   // a accepted, b rejected (or past the row)
+        while (a + 1 < b) {
+            const int m = (a + b) >> 1;
+            if (r2(m) > C.ff[3]) b = m; else a = m;
+        }
+        hi = b;
+    }
+    return one_sided;
+}
+
 // Single-precision prefilter of the same test: +1 inside, 0 outside, -1 too close to the rim to call in FP32
 // (the caller then runs ff_aperture in FP64, so the accepted set is exactly the FP64 one).
 SOLAT_HD int ff_aperture_coarse(const FfFrames& f, float dx, float dy, float dz)
@@ -911,11 +963,6 @@ SOLAT_HD void cis_large(double x, double& c, double& s)
 // ------------------------------------------------------------------------------------------
 // Row packers: the reference's `.output()` column layouts.
 // ------------------------------------------------------------------------------------------
-SOLAT_HD vec3 launch_dir(double sin_th, double cos_th, double sin_ph, double cos_ph)
-{
-    return mk(sin_th * cos_ph, sin_th * sin_ph, cos_th);   // rti:628, saf:345
-}
-
 // source_to_lyot_model rows, rti:1346-1373.  rows[26]
 SOLAT_HD void pack_nf_source_rows(const NfSourceRay& r, const vec3& p0, double n_si, double n_vac, double* rows)
 {

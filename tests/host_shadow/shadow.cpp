@@ -257,6 +257,38 @@ API int shadow_ff_pixel2(const double* geo, const double* th, int nth, const dou
     return agg;
 }
 
+// accepted rays of every phi row: interval search (what the fused map runs) next to the per-ray test; returns the
+// number of rows whose interval differs from the brute-force accepted set (-1: some accepted set is not one
+// interval), and how many rows asked for the per-ray walk.
+API int shadow_ff_row_intervals(const double* geo, const double* th, int nth, const double* ph, int nph, double el, double az,
+                                int* lo_hi, int* n_fallback)
+{
+    FfGeom g = unpack(geo);
+    FfFrames f;
+    ff_build_frames(K_COEF, g, el, az, f);
+    std::vector<double> st(nth), ct(nth);
+    for (int i = 0; i < nth; i++) { st[i] = sin(th[i]); ct[i] = cos(th[i]); }
+    int bad = 0;
+    *n_fallback = 0;
+    for (int j = 0; j < nph; j++) {
+        int lo, hi;
+        const bool ok = ff_row_interval(K_COEF, g, f, st.data(), ct.data(), nth, sin(ph[j]), cos(ph[j]), lo, hi);
+        lo_hi[2 * j] = lo; lo_hi[2 * j + 1] = hi;
+        if (!ok) { ++*n_fallback; continue; }
+        int first = -1, last = -1, count = 0;
+        for (int i = 0; i < nth; i++) {
+            vec3 d = launch_dir(st[i], ct[i], sin(ph[j]), cos(ph[j])), Pa;
+            double t_ap;
+            if (!ff_aperture(K_COEF, g, f, d, t_ap, Pa)) continue;
+            if (first < 0) first = i;
+            last = i; ++count;
+        }
+        if (count && last - first + 1 != count) return -1;
+        if (count == 0 ? hi != lo : (lo != first || hi != last + 1)) ++bad;
+    }
+    return bad;
+}
+
 // one far-field pixel, zero-error single-panel model (fused-map semantics)
 API int shadow_ff_pixel(const double* geo, const double* th, int nth, const double* ph, int nph, double el, double az,
                         const double* gx_full, const double* gy, const double* e_rec, int M, double k, double* re_im,

@@ -104,6 +104,15 @@ def ff_pixel(geo, th, ph, el, az, data_x, data_y, e_rec, k, packed=False):
     return complex(o[0], o[1]), nc.value, agg
 
 
+def ff_row_intervals(geo, th, ph, el, az):
+    """-> (rows whose interval differs from the per-ray test, rows that asked for the per-ray walk, (nph, 2) lo/hi)"""
+    g, gp = D(geo); th, thp = D(th); ph, php = D(ph)
+    lo_hi = np.zeros((ph.size, 2), dtype=np.int32); nf = ci(0)
+    bad = lib().shadow_ff_row_intervals(gp, thp, ci(th.size), php, ci(ph.size), cd(el), cd(az),
+                                        lo_hi.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), ctypes.byref(nf))
+    return bad, nf.value, lo_hi
+
+
 def regrid(field, n_new):
     f, fp = D(field)
     out = np.zeros((n_new, n_new))

@@ -402,6 +402,46 @@ def test_ff_properties_at_full_size():
     assert np.all(z == 0)
 
 
+def test_ff_ray_walks_agree(oracle, monkeypatch):
+    """The fused map finds the rays that pass the aperture either as one index interval per phi row (monotone
+    theta, the reference's linspace fans) or by testing every ray (any other fan).  Both must give the oracle's map:
+    on the default fan bit for bit between themselves, on reversed / shuffled / far-off-axis fans against the oracle."""
+    from solat_optics_b200 import maps
+
+    tgf = maps.ff_tele_geo(140, 1.32)
+    geo = oracle.ff_geo_vec(rx_y_m=-1.32)
+    x, y, e = gu.ff_grid("wide61")
+    th, phi = gu.ff_fan(60)
+    azel = np.array([[0.3 * gu.DE, gu.EL0], [20 * gu.DE, gu.EL0 - 20 * gu.DE], [-7.3 * gu.DE, gu.EL0 + 11.1 * gu.DE],
+                     [40 * gu.DE, gu.EL0 + 40 * gu.DE]])
+    a_rows, p_rows, st = maps.FarFieldPlan(tgf, th, phi, x, y, e, device=0).run(azel)
+    assert st == 0
+    monkeypatch.setenv("SOLAT_FF_QUEUE_WALK", "1")
+    a_q, p_q, st = maps.FarFieldPlan(tgf, th, phi, x, y, e, device=0).run(azel)
+    monkeypatch.delenv("SOLAT_FF_QUEUE_WALK")
+    assert st == 0
+    np.testing.assert_array_equal(a_rows, a_q)
+    np.testing.assert_array_equal(p_rows, p_q)
+    oa, op = oracle.ff_map(geo, azel, th, phi, x, y, e, tgf.k)
+    _assert_pixels(a_rows, p_rows, oa, op)
+    # a fan that crosses the aperture plane's horizon at this pointing: the interval walk must hand the pixel over
+    t_h = np.linspace(np.pi - 1.0, np.pi + 1.0, 33)
+    a_h, p_h, _ = maps.FarFieldPlan(tgf, t_h, phi, x, y, e, device=0).run([[0.0, 1.2], [0.0, gu.EL0]])
+    monkeypatch.setenv("SOLAT_FF_QUEUE_WALK", "1")
+    a_hq, p_hq, _ = maps.FarFieldPlan(tgf, t_h, phi, x, y, e, device=0).run([[0.0, 1.2], [0.0, gu.EL0]])
+    monkeypatch.delenv("SOLAT_FF_QUEUE_WALK")
+    np.testing.assert_array_equal(a_h, a_hq)
+    np.testing.assert_array_equal(p_h, p_hq)
+    rng = np.random.default_rng(5)
+    fans = {"reversed": th[::-1].copy(), "shuffled": rng.permutation(th), "uneven": np.sort(th[0] + (th[-1] - th[0]) * rng.random(60)),
+            "wide": np.linspace(np.pi - 9e-5, np.pi + 9e-5, 60), "one_sided": np.linspace(np.pi + 1e-6, np.pi + 5e-5, 60)}
+    for name, t in fans.items():
+        a, p, st = maps.FarFieldPlan(tgf, t, phi, x, y, e, device=0).run(azel)
+        oa, op = oracle.ff_map(geo, azel, t, phi, x, y, e, tgf.k)
+        assert st == 0, name
+        _assert_pixels(a, p, oa, op)
+
+
 def test_ff_odd_sizes_and_edge_grids(oracle):
     """Ragged inputs: a fan that is not a multiple of the CTA size, a 1-pixel map, a 2x2 E_rec grid (every ray
     piles into cell 0 or is skipped), a grid entirely below the beam (all rays skipped -> 0)."""

@@ -184,3 +184,26 @@ def test_regrid_unequal_grids_known_answer(shadow):
     z, _ = shadow.nf_pixel([d["in_x"][i], y_ap, d["in_z"][i]], a, a, opl, amp * gu.lyot_mask(n), gu.nf_k(f))
     assert abs(abs(z) ** 2 - d["amp"][i] ** 2) <= P_TOL * d["amp"][i] ** 2
     assert abs(gu.wrap(np.angle(z) - d["phi"][i])) <= PHI_TOL
+
+
+def test_ff_row_intervals_equal_the_per_ray_aperture_test(shadow, oracle):
+    """The fused map's interval walk: per phi row the accepted rays must be exactly the interval the bisection finds,
+    for on- and far-off-axis pixels, reversed / uneven / one-sided / dense fans, and pixels that miss the aperture."""
+    geo = oracle.ff_geo_vec(rx_y_m=-1.32)
+    rng = np.random.default_rng(11)
+    th, phi = gu.ff_fan(100)
+    fans = [th, th[::-1].copy(), np.sort(th[0] + (th[-1] - th[0]) * rng.random(100)), np.linspace(np.pi + 1e-6, np.pi + 5e-5, 64),
+            np.linspace(np.pi - 2e-4, np.pi + 2e-4, 257), np.linspace(np.pi - 5e-5, np.pi + 5e-5, 1000),
+            np.linspace(np.pi - 3.2e-5, np.pi - 2.9e-5, 50), np.array([np.pi - 1e-5, np.pi + 2e-5])]
+    pixels = [(0.0, gu.EL0), (20 * gu.DE, gu.EL0 - 20 * gu.DE), (-3e-3, 4e-3), (1e-4, -2.5e-5), (0.2, 0.1)]
+    for t in fans:
+        for az, el in pixels:
+            bad, fallback, lo_hi = shadow.ff_row_intervals(geo, t, phi, el, az)
+            assert bad == 0 and fallback == 0, (t.size, az, el, bad, fallback)
+            assert (lo_hi[:, 0] <= lo_hi[:, 1]).all() and lo_hi.min() >= 0 and lo_hi.max() <= t.size
+    # the default fan at the map centre: 60 % of the rays pass (SURVEY 8d)
+    _, _, lo_hi = shadow.ff_row_intervals(geo, th, phi, gu.EL0, 0.0)
+    assert int((lo_hi[:, 1] - lo_hi[:, 0]).sum()) == 6000
+    # a fan that crosses the aperture plane's horizon asks for the per-ray walk
+    _, fallback, _ = shadow.ff_row_intervals(geo, np.linspace(np.pi - 1.0, np.pi + 1.0, 9), phi[48:53], 1.2, 0.0)
+    assert fallback > 0
