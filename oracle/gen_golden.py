@@ -102,6 +102,39 @@ def t_ff_pixel(a):
     return amp, phi, int(np.count_nonzero(f[15])), int(np.count_nonzero(out_new))
 
 
+def panel_layout(seed=3):
+    """Synthetic multi-panel layout for pinning the reference's panel arithmetic (the real layout lives in the
+    external pan_mod): 1 m x 1 m panels, ids (row, col) = floor(coordinate / 1000) + 10, a few panels missing
+    from the model (rays there are dropped, saf:626-628,805-809), seeded piston / tilt / curvature errors."""
+    rng = np.random.default_rng(seed)
+    mods = []
+    for lo_r, hi_r in ((6, 14), (2, 16)):           # M1: y - y_cent within +-3 m; M2: telescope z of the hit
+        ids = [(r, c) for r in range(lo_r, hi_r) for c in range(6, 14) if (r + 2 * c) % 7 != 0]
+        pm = np.zeros((10, len(ids)))
+        pm[0] = [r for r, _ in ids]; pm[1] = [c for _, c in ids]
+        pm[2] = rng.normal(0, 0.02, len(ids))
+        pm[3:5] = rng.normal(0, 2e-5, (2, len(ids)))
+        pm[5:7] = rng.normal(0, 2e-8, (2, len(ids)))
+        pm[7] = rng.normal(0, 1.0, len(ids))        # f: carried by the model, unused by the reference (saf:672)
+        pm[8] = (pm[1] - 10 + 0.5) * 1000.0; pm[9] = (pm[0] - 10 + 0.5) * 1000.0
+        mods.append(pm)
+    return mods[0], mods[1]
+
+
+def panel_identify(x2d, y2d, x_adj, y_adj, col, row):
+    """(2, n, n): [0] = row ids, [1] = col ids (saf:609-617)"""
+    return np.stack([np.floor(np.asarray(y2d) / 1000.0) + 10, np.floor(np.asarray(x2d) / 1000.0) + 10])
+
+
+def t_ff_pixel_panels(a):
+    rl, ref = _get_ref()
+    x, y, e = ff_grid(a["grid"])
+    pan1, pan2 = panel_layout()
+    amp, phi, m, f = rl.ff_pixel_panels(ref, a["freq"], a["offset"], a["n_scan"], a["az"], a["el"], x, y, e, pan1, pan2,
+                                        panel_identify)
+    return amp, phi, m, f
+
+
 def t_unwrap(a):
     rl, ref = _get_ref()
     return ref.phase_correct.do_unwrap(a["phi_deg"].copy())
@@ -195,6 +228,11 @@ def build_jobs():
         for a in azs
         for e in els
     ]
+    # -- far-field pixels with non-zero panel errors on a synthetic multi-panel layout (rays + pixel answers)
+    J["ff_panels"] = [
+        ("t_ff_pixel_panels", dict(freq=140, offset=1.32, n_scan=16, az=float(az), el=float(el), grid="wide61"))
+        for az, el in [(0.3 * DE, EL0), (20 * DE, EL0 - 20 * DE), (-3 * DE, EL0 + 7 * DE)]
+    ]
     # -- phase unwrap (phase_correct.py:8-92): smooth quadratic phase wrapped to +-180 deg
     ax = np.linspace(-1, 1, 21)
     xx, yy = np.meshgrid(ax, ax)
@@ -229,6 +267,13 @@ def pack(name, jobs, results):
         out["phi"] = np.array([r[1] for r in results])
         out["n_valid"] = np.array([r[2] for r in results])
         out["n_cells"] = np.array([r[3] for r in results])
+    elif name == "ff_panels":
+        out["amp"] = np.array([r[0] for r in results])
+        out["phi"] = np.array([r[1] for r in results])
+        for i, r in enumerate(results):
+            out["mirror_%d" % i] = r[2]
+            out["field_%d" % i] = r[3]
+        out["pan1"], out["pan2"] = panel_layout()
     elif name == "unwrap":
         out["phi_deg"] = jobs[0][1]["phi_deg"]
         out["unwrapped_deg"] = results[0]

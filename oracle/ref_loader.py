@@ -173,3 +173,23 @@ def ff_pixel(ref, freq, offset, n_scan, az, el, data_x, data_y, e_rec, want_arra
     if want_arrays:
         return amp, phi, apert_rx, f_out, out_new
     return amp, phi
+
+
+def ff_pixel_panels(ref, freq, offset, n_scan, az, el, data_x, data_y, e_rec, pan1, pan2, identify):
+    """scripts/ff_sim.py:204-221 with non-trivial panel models: `identify` stands in for pan_mod.identify_panel
+    (the reference's own panel arithmetic, saf:587-703,805-852, runs unmodified)."""
+    import numpy as np
+
+    tg = ff_tele_geo(ref, freq, offset, n_scan)
+    th, ph = ff_fan(n_scan)
+    keep = ref.saf.identify_panel
+    ref.saf.identify_panel = identify
+    try:
+        apert_rx = ref.saf.ray_mirror_pts(tg, th, ph, el, az)
+        f_out = ref.saf.aperature_fields_from_panel_model(pan1, pan2, tg, th, ph, apert_rx, el, az)
+    finally:
+        ref.saf.identify_panel = keep
+    out_new = ref.ffl.project_to_data(f_out, data_x, data_y, tg)
+    npts = len(out_new)
+    out_beam = np.sum(out_new * e_rec) / npts ** 2
+    return abs(out_beam), np.arctan2(np.imag(out_beam), np.real(out_beam)), apert_rx, f_out

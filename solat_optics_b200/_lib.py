@@ -14,6 +14,7 @@ from . import _build
 
 c_dp = ctypes.POINTER(ctypes.c_double)
 c_ip = ctypes.POINTER(ctypes.c_int)
+c_sp = ctypes.POINTER(ctypes.c_short)
 c_vp = ctypes.c_void_p
 c_d = ctypes.c_double
 c_i = ctypes.c_int
@@ -68,6 +69,8 @@ SIGNATURES = {
     "solat_ff_map_host": (c_i, [c_vp, c_dp, c_i, c_dp, c_dp, c_ip]),
     "solat_ff_map_device": (c_i, [c_vp, c_vp, c_i, c_vp, c_vp, c_vp]),
     "solat_ff_plan_status": (c_i, [c_vp, c_ip]),
+    "solat_ff_map_mirror_xy_host": (c_i, [c_vp, c_dp, c_i, c_dp, c_ip]),
+    "solat_ff_map_panels_host": (c_i, [c_vp, c_dp, c_i, c_sp, c_sp, c_dp, c_i, c_dp, c_i, c_dp, c_dp, c_ip]),
 }
 
 _lib = None

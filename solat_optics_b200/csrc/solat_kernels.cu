@@ -453,7 +453,20 @@ struct FfMapParams {
     double* phase;
     int* status;
     int rows;                // host: theta is strictly monotone inside one branch of tan -> interval walk allowed
+    // panel models (ff_map_kernel<true> only): per (pixel, ray) column of pan1 / pan2, -1 = the ray sits on no panel
+    const short *pidx1, *pidx2;
+    const double *pan1, *pan2;   // (10, np) row-major [row, col, a, b, c, d, e, f, x0, y0]  (saf:667-674)
+    int np1, np2;
 };
+
+__device__ __forceinline__ PanelErr load_panel(const double* pan, int np, int col)
+{
+    const double* c = pan + col;
+    PanelErr e;
+    e.a = __ldg(c + 2 * np); e.b = __ldg(c + 3 * np); e.c = __ldg(c + 4 * np); e.d = __ldg(c + 5 * np); e.e = __ldg(c + 6 * np);
+    e.x0 = __ldg(c + 8 * np); e.y0 = __ldg(c + 9 * np);
+    return e;
+}
 
 // One CTA per (az, el) pixel, warps fully autonomous inside the ray loop (no CTA barrier).
 //   * Which rays pass the aperture (saf:378, 60 % of the default fan):
@@ -468,6 +481,10 @@ struct FfMapParams {
 //   * the reference's "later ray overwrites the cell" becomes one 64-bit shared-memory atomicMax per ray on a
 //     key that carries the ray index above an exact fixed-point copy of its path length;
 //   * after one barrier the winners -- and only they -- get their phasor, are weighted by E_rec and reduced.
+//   * PANEL (adjuster-error studies, ff_sim.py:61-70 with non-zero offsets): every ray carries the panel-model
+//     columns the host derived with pan_mod.identify_panel; rays on no panel are dropped (saf:626-628,805-809), the
+//     others see their panels' error polynomials inside both Newton solves.  Always the queue walk.
+template <bool PANEL>
 __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams q)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -480,6 +497,7 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
     int* row_lo = reinterpret_cast<int*>(s_gy + q.grid.M);                 // [nph] first accepted theta index of a row
     int* row_pre = row_lo + (q.rows ? q.ang.nph : 0);                      // [nph + 1] accepted rays before the row
     __shared__ int s_queue_walk;
+    __shared__ double s_t2e[9];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
     const FfGeom g = to_geom(q.g);
@@ -487,6 +505,10 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
     if (tid == 0) {
         ff_build_frames(K_COEF, g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
         s_queue_walk = !q.rows;
+        if (PANEL) {
+            for (int i = 0; i < 9; i++) s_t2e[i] = fr->t2.a[i];
+            if (g.src[2] != 0) for (int i = 0; i < 3; i++) s_t2e[3 * i + 2] /= cos(atan(1.0 / 3.0));   // saf:828-829
+        }
     }
     for (int c = tid; c < cells; c += FF_T) win[c] = 0ull;
     FfGrid grid = q.grid;                                   // grid axes on chip: the binning does 2-4 dependent reads per ray
@@ -499,7 +521,7 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
     __syncthreads();
 
     const int nth = q.ang.nth, n_rays = nth * q.ang.nph;
-    if (q.rows) {
+    if (!PANEL && q.rows) {
         // accepted interval [lo, hi) of every phi row
         for (int j = tid; j < q.ang.nph; j += FF_T) {
             int lo, hi;
@@ -526,7 +548,7 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
         }
         __syncthreads();
     }
-    const bool queue_walk = s_queue_walk != 0;
+    const bool queue_walk = PANEL || s_queue_walk != 0;
 
     int* wq = queues + warp * FF_WQ;
     const double cx = fr->centre[0], cz = fr->centre[2];
@@ -573,6 +595,10 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
                         double t_ap;
                         ok = ff_aperture(sC, g, *fr, ray_dir(q.ang, r), t_ap, Pa);
                     }
+                    if (PANEL) {
+                        const size_t at = (size_t)pix * n_rays + r;
+                        ok = ok && __ldg(q.pidx1 + at) >= 0 && __ldg(q.pidx2 + at) >= 0;
+                    }
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
                 if (ok) wq[cnt + __popc(m & ((1u << lane) - 1u))] = r;
@@ -594,7 +620,15 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
             ff_aperture(sC, g, *fr, d, t_ap, Pa);
             double opl, fx, fz;
             int rst;
-            ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);
+            if (PANEL) {
+                const size_t at = (size_t)pix * n_rays + r0;
+                const PanelErr e1 = load_panel(q.pan1, q.np1, __ldg(q.pidx1 + at)), e2 = load_panel(q.pan2, q.np2, __ldg(q.pidx2 + at));
+                FfRay ray;
+                ff_ray_trace<false, true>(sC, *fr, d, t_ap, Pa, g.foc_y, &e1, &e2, s_t2e, ray);
+                opl = ray.opl; fx = ray.foc.x; fz = ray.foc.z; rst = ray.status;
+            } else {
+                ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);
+            }
             st |= rst;
             if (opl != 0.0 && !not_finite(opl)) {                                   // ffl:10
                 const int cell = ff_cell(fx - cx, fz - cz, grid);
@@ -646,6 +680,33 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
         q.amp[pix] = hypot(a, b);
         q.phase[pix] = atan2(b, a);
     }
+}
+
+// What the reference hands to pan_mod.identify_panel for every pixel (saf:596-612 = rows 0, 2, 3, 4 of ray_mirror_pts'
+// output): telescope-frame M2 hit (x, z) and M1 hit (x, y) on the error-free mirrors, 0 where the ray misses the
+// aperture.  xy[(pix * 4 + k) * n_rays + r].
+__global__ void __launch_bounds__(128) ff_mirror_xy_kernel(AngleTabs ang, solat_ff_geom gg, const double* azel, double* xy, int* status)
+{
+    __shared__ FfFrames fr;
+    const FfGeom g = to_geom(gg);
+    const int pix = blockIdx.y;
+    if (threadIdx.x == 0) ff_build_frames(K_COEF, g, __ldg(azel + 2 * pix + 1), __ldg(azel + 2 * pix), fr);
+    __syncthreads();
+    const int n = ang.rays();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    const vec3 d = ray_dir(ang, r);
+    vec3 Pa;
+    double t_ap;
+    if (ff_aperture(K_COEF, g, fr, d, t_ap, Pa)) {
+        FfRay ray;
+        ff_ray_trace<true, false>(K_COEF, fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+        v[0] = ray.m2.x; v[1] = ray.m2.z; v[2] = ray.m1.x; v[3] = ray.m1.y;
+        if (ray.status) atomicOr(status, ray.status);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) xy[((size_t)pix * 4 + k) * n + r] = v[k];
 }
 
 // The interval walk needs the rays of a phi row to move monotonically along their line in the aperture plane:
@@ -1187,6 +1248,8 @@ struct solat_ff_plan {
     DevBuf<double> h_azel, h_out;           // [amp | phase | status word]
     PinnedBuf pin;
     DevBuf<int> status;
+    DevBuf<short> pidx;                     // [2][npix][n_rays] panel columns of a panel-model map
+    DevBuf<double> pan, xy;                 // panel models; mirror coordinates for identify_panel
     FfGrid grid;
     double k, key_base, key_unit;
     int M, n_rays, rows;
@@ -1200,7 +1263,8 @@ static int ff_map_launch(solat_ff_plan* p, const double* d_azel, int npix, doubl
     q.ang = p->ang.tabs; q.g = p->g; q.azel = d_azel; q.grid = p->grid; q.e_rec = p->e_rec.p;
     q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
     q.amp = d_amp; q.phase = d_phase; q.status = p->status.p; q.rows = p->rows;
-    ff_map_kernel<<<npix, FF_T, p->smem, s>>>(q);
+    q.pidx1 = q.pidx2 = nullptr; q.pan1 = q.pan2 = nullptr; q.np1 = q.np2 = 0;
+    ff_map_kernel<false><<<npix, FF_T, p->smem, s>>>(q);
     LAUNCHED();
     return SOLAT_OK;
 }
@@ -1221,7 +1285,8 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
         return fail(SOLAT_ERR_ARG, "E_rec grid too large for the shared-memory winner table (M <= 168)");
     if ((long long)nth * nph > FF_MAX_RAYS)
         return fail(SOLAT_ERR_ARG, "launch fan too large for the 20-bit ray index of the winner key (<= 1048575 rays)");
-    CK(cudaFuncSetAttribute(ff_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(ff_map_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(ff_map_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     solat_ff_plan* p = new solat_ff_plan();
     p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem; p->n_rays = nth * nph; p->rows = rows;
     // fixed-point frame of the winner keys: every path length of this telescope lies within a few tens of metres
@@ -1274,6 +1339,63 @@ int solat_ff_map_host(solat_ff_plan* p, const double* azel, int npix, double* am
     if (int rc = p->h_out.reserve(2 * n + 1)) return rc;
     if (int rc = p->pin.reserve(2 * n + 1)) return rc;
     if (int rc = ff_map_launch(p, p->h_azel.p, npix, p->h_out.p, p->h_out.p + n, s)) return rc;
+    pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->h_out.p + 2 * n);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(p->pin.p, p->h_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(amp, p->pin.p, n * sizeof(double));
+    memcpy(phase, p->pin.p + n, n * sizeof(double));
+    const int st = (int)p->pin.p[2 * n];
+    if (st) CK(cudaMemset(p->status.p, 0, sizeof(int)));
+    if (status) *status = st;
+    return SOLAT_OK;
+}
+
+int solat_ff_map_mirror_xy_host(solat_ff_plan* p, const double* azel, int npix, double* xy, int* status)
+{
+    if (!p || !azel || !xy || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(p->ctx->device));
+    cudaStream_t s = p->ctx->stream;
+    const size_t n = (size_t)npix * 4 * p->n_rays;
+    if (int rc = p->h_azel.upload(azel, 2 * (size_t)npix, s)) return rc;
+    if (int rc = p->xy.reserve(n)) return rc;
+    if (npix > 65535) return fail(SOLAT_ERR_ARG, "at most 65535 pixels per call");
+    ff_mirror_xy_kernel<<<dim3((p->n_rays + 127) / 128, npix), 128, 0, s>>>(p->ang.tabs, p->g, p->h_azel.p, p->xy.p, p->status.p);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(xy, p->xy.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    int st = 0;
+    CK(cudaMemcpyAsync(&st, p->status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (st) CK(cudaMemset(p->status.p, 0, sizeof(int)));
+    if (status) *status = st;
+    return SOLAT_OK;
+}
+int solat_ff_map_panels_host(solat_ff_plan* p, const double* azel, int npix, const short* pan_idx1, const short* pan_idx2,
+                             const double* pan1, int np1, const double* pan2, int np2, double* amp, double* phase, int* status)
+{
+    if (!p || !azel || !pan_idx1 || !pan_idx2 || !pan1 || !pan2 || !amp || !phase || npix <= 0 || np1 <= 0 || np2 <= 0)
+        return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(p->ctx->device));
+    cudaStream_t s = p->ctx->stream;
+    const size_t n = (size_t)npix, nr = n * p->n_rays;
+    for (size_t i = 0; i < nr; i++)
+        if (pan_idx1[i] >= np1 || pan_idx2[i] >= np2) return fail(SOLAT_ERR_ARG, "panel index outside its panel model");
+    if (int rc = p->h_azel.upload(azel, 2 * n, s)) return rc;
+    if (int rc = p->h_out.reserve(2 * n + 1)) return rc;
+    if (int rc = p->pin.reserve(2 * n + 1)) return rc;
+    if (int rc = p->pidx.reserve(2 * nr)) return rc;
+    if (int rc = p->pan.reserve(10 * ((size_t)np1 + np2))) return rc;
+    CK(cudaMemcpyAsync(p->pidx.p, pan_idx1, nr * sizeof(short), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->pidx.p + nr, pan_idx2, nr * sizeof(short), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->pan.p, pan1, 10 * (size_t)np1 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->pan.p + 10 * (size_t)np1, pan2, 10 * (size_t)np2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    FfMapParams q;
+    q.ang = p->ang.tabs; q.g = p->g; q.azel = p->h_azel.p; q.grid = p->grid; q.e_rec = p->e_rec.p;
+    q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
+    q.amp = p->h_out.p; q.phase = p->h_out.p + n; q.status = p->status.p; q.rows = 0;
+    q.pidx1 = p->pidx.p; q.pidx2 = p->pidx.p + nr; q.pan1 = p->pan.p; q.pan2 = p->pan.p + 10 * (size_t)np1; q.np1 = np1; q.np2 = np2;
+    ff_map_kernel<true><<<npix, FF_T, p->smem, s>>>(q);
+    LAUNCHED();
     pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->h_out.p + 2 * n);
     LAUNCHED();
     CK(cudaMemcpyAsync(p->pin.p, p->h_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));

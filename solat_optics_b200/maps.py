@@ -331,6 +331,66 @@ class FarFieldPlan:
         _lib.check(_lib.load().solat_ff_map_device(self.handle, d_azel.data_ptr(), d_azel.shape[0], d_amp.data_ptr(),
                                                    d_phase.data_ptr(), stream))
 
+    def mirror_xy(self, azel):
+        """(npix, 4, n_rays): M2 hit x, z and M1 hit x, y of the error-free trace -- the coordinates the reference
+        hands to pan_mod.identify_panel (saf:596-612).  Returns (xy, status)."""
+        azel = _lib.as_f64(np.reshape(azel, (-1, 2)))
+        xy = np.empty((azel.shape[0], 4, self.n_rays))
+        st = _lib.c_i(0)
+        if azel.shape[0]:
+            _lib.check(_lib.load().solat_ff_map_mirror_xy_host(self.handle, _lib.dptr(azel), azel.shape[0], _lib.dptr(xy),
+                                                               ctypes.byref(st)))
+        return xy, st.value
+
+    def run_panels(self, azel, pan_idx1, pan_idx2, panel_model1, panel_model2):
+        """Fused map with panel models: pan_idx1/2 (npix, n_rays) = column of panel_model1/2 every ray sits on
+        (-1: none, the ray is dropped); the panel-error polynomials enter both mirror intersections."""
+        azel = _lib.as_f64(np.reshape(azel, (-1, 2)))
+        npix = azel.shape[0]
+        amp, phase = np.empty(npix), np.empty(npix)
+        if npix == 0:
+            return amp, phase, 0
+        i1 = np.ascontiguousarray(pan_idx1, dtype=np.int16).reshape(npix, self.n_rays)
+        i2 = np.ascontiguousarray(pan_idx2, dtype=np.int16).reshape(npix, self.n_rays)
+        pm1, pm2 = _lib.as_f64(panel_model1), _lib.as_f64(panel_model2)
+        if pm1.ndim != 2 or pm2.ndim != 2 or pm1.shape[0] != 10 or pm2.shape[0] != 10:
+            raise ValueError("panel models must be (10, n_panels)")
+        st = _lib.c_i(0)
+        _lib.check(_lib.load().solat_ff_map_panels_host(
+            self.handle, _lib.dptr(azel), npix, i1.ctypes.data_as(_lib.c_sp), i2.ctypes.data_as(_lib.c_sp), _lib.dptr(pm1),
+            pm1.shape[1], _lib.dptr(pm2), pm2.shape[1], _lib.dptr(amp), _lib.dptr(phase), ctypes.byref(st)))
+        return amp, phase, st.value
+
+    def run_panel_models(self, azel, panel_model1, panel_model2, backend=None, batch=64):
+        """ff_sim.py:204-221 for a list of pixels with the panel models of pan_mod: mirror coordinates on the GPU ->
+        `identify_panel` of the panel backend on the host, pixel by pixel exactly as the reference calls it
+        (saf:587-621) -> fused GPU map.  `batch` pixels share one round trip."""
+        from . import solat_apert_field as saf
+
+        backend = backend or saf.panel_backend()
+        azel = _lib.as_f64(np.reshape(azel, (-1, 2)))
+        adj1, adj2 = backend.get_single_vert_adj_positions()
+        n = int(round(np.sqrt(self.n_rays)))
+        if n * n != self.n_rays:
+            raise ValueError("panel identification needs a square fan (saf:596-607)")
+        amp, phase, status = np.empty(len(azel)), np.empty(len(azel)), 0
+        for lo in range(0, len(azel), batch):
+            px = azel[lo:lo + batch]
+            xy, st = self.mirror_xy(px)
+            status |= st
+            i1 = np.empty((len(px), self.n_rays), dtype=np.int16)
+            i2 = np.empty_like(i1)
+            for p in range(len(px)):
+                id2 = backend.identify_panel(xy[p, 0].reshape(n, n), xy[p, 1].reshape(n, n), adj2[4], adj2[3], adj2[0], adj2[1])
+                id1 = backend.identify_panel(xy[p, 2].reshape(n, n), xy[p, 3].reshape(n, n) - saf.y_cent_m1, adj1[2], adj1[3],
+                                             adj1[0], adj1[1])
+                i1[p] = saf._first_match_index(panel_model1, np.ravel(id1[0]), np.ravel(id1[1]))
+                i2[p] = saf._first_match_index(panel_model2, np.ravel(id2[0]), np.ravel(id2[1]))
+            a, ph, st = self.run_panels(px, i1, i2, panel_model1, panel_model2)
+            status |= st
+            amp[lo:lo + batch], phase[lo:lo + batch] = a, ph
+        return amp, phase, status
+
     def status(self):
         st = _lib.c_i(0)
         _lib.check(_lib.load().solat_ff_plan_status(self.handle, ctypes.byref(st)))
@@ -348,16 +408,21 @@ class FarFieldPlan:
             pass
 
 
-def ff_map(freq, res_arcmin, num, offset, data_x, data_y, e_rec, n_scan=100, device=None, strict=False):
+def ff_map(freq, res_arcmin, num, offset, data_x, data_y, e_rec, n_scan=100, device=None, strict=False, panel_models=None):
     """Far-field beam map `ff_sim.py <freq> <res> <num> <offset>`.  Returns on rank 0
-    (pixels [npix,2] (az, el), amp [npix], phase [npix]); None on the other ranks."""
+    (pixels [npix,2] (az, el), amp [npix], phase [npix]); None on the other ranks.
+    `panel_models` = (pan_mod1, pan_mod2) of ff_sim.py:69-70 switches on panel identification through the panel
+    backend (solat_apert_field.set_panel_backend / an importable pan_mod) and the panel-error polynomials; without
+    it every ray sits on an error-free panel (the zero-offset case of ff_sim.py:61-62 with the stand-in layout)."""
     tg = ff_tele_geo(freq, offset)
     theta, phi = ff_fan(n_scan)
     plan = FarFieldPlan(tg, theta, phi, data_x, data_y, e_rec, device)
     pixels = ff_pixels(tg, res_arcmin, num)
     rank, world = dist_info()
     lo, hi = shard_bounds(len(pixels), rank, world)
-    if hi > lo:
+    if hi > lo and panel_models is not None:
+        amp, phase, st = plan.run_panel_models(pixels[lo:hi], panel_models[0], panel_models[1])
+    elif hi > lo:
         amp, phase, st = plan.run(pixels[lo:hi])
     else:
         amp, phase, st = np.zeros(0), np.zeros(0), 0

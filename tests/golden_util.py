@@ -56,3 +56,29 @@ def lyot_mask(n_scan, r_lyot=136.54 / 2):
     ax = np.linspace(-70, 70, n_scan)
     X2, Z2 = np.meshgrid(ax, ax)
     return np.sqrt(np.ravel(X2) ** 2 + np.ravel(Z2) ** 2) <= r_lyot
+
+
+Y_CENT_M1 = -7201.003729431267   # solat_apert_field.py:19
+
+
+def panel_identify(x2d, y2d, x_adj=None, y_adj=None, col=None, row=None):
+    """Same synthetic panel layout as oracle/gen_golden.py:panel_identify (1 m x 1 m panels): (2, n, n) row, col ids."""
+    return np.stack([np.floor(np.asarray(y2d) / 1000.0) + 10, np.floor(np.asarray(x2d) / 1000.0) + 10])
+
+
+def panel_columns(panel_model, ids):
+    """First column of the panel model whose (row, col) equals the ray's ids, -1 if none (saf:626, :805-809)."""
+    rows, cols = np.ravel(ids[0]), np.ravel(ids[1])
+    out = np.full(rows.size, -1, dtype=np.int32)
+    for idx in range(panel_model.shape[1] - 1, -1, -1):
+        out[(rows == panel_model[0, idx]) & (cols == panel_model[1, idx])] = idx
+    return out
+
+
+def panel_indices(mirror, pan1, pan2):
+    """Per-ray panel-model columns the way saf:596-621 derives them from ray_mirror_pts' output."""
+    n = int(round(np.sqrt(mirror.shape[1])))
+    sh = (n, n)
+    id2 = panel_identify(mirror[0].reshape(sh), mirror[2].reshape(sh))
+    id1 = panel_identify(mirror[3].reshape(sh), mirror[4].reshape(sh) - Y_CENT_M1)
+    return panel_columns(pan1, id1), panel_columns(pan2, id2)

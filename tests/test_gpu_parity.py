@@ -319,6 +319,65 @@ def test_ff_panel_errors_against_oracle(oracle):
     assert np.abs(out[15] - ref[15]).max() <= 3 * ULP_1E8
 
 
+def test_ff_panel_model_map(oracle):
+    """Fused far-field map with panel models (ff_sim.py:204-221 with non-zero adjuster errors): mirror coordinates on
+    the GPU -> identify_panel on the host -> fused map.  Pinned on the reference fixture ff_panels (synthetic 1 m
+    panels, only identify_panel stood in), then a larger fan against the oracle's per-pixel composition, then the
+    error-free single-panel layout against the plain fused map."""
+    from solat_optics_b200 import maps
+    from solat_optics_b200 import solat_apert_field as saf
+
+    class Backend:
+        @staticmethod
+        def get_single_vert_adj_positions():
+            z = np.zeros(1)
+            return [z, z, z, z, z], [z, z, z, z, z]
+
+        identify_panel = staticmethod(gu.panel_identify)
+
+    d = gu.load("ff_panels")
+    pan1, pan2 = d["pan1"], d["pan2"]
+    n = int(d["in_n_scan"][0])
+    th, ph = gu.ff_fan(n)
+    x, y, e = gu.ff_grid("wide61")
+    tgf = maps.ff_tele_geo(140, 1.32)
+    azel = np.c_[d["in_az"], d["in_el"]]
+    plan = maps.FarFieldPlan(tgf, th, ph, x, y, e, device=0)
+    xy, st = plan.mirror_xy(azel)
+    assert st == 0
+    for i in range(len(azel)):
+        m = d["mirror_%d" % i]
+        np.testing.assert_allclose(xy[i], m[[0, 2, 3, 4]], rtol=0, atol=1e-9)
+    a, p, st = plan.run_panel_models(azel, pan1, pan2, backend=Backend, batch=2)
+    assert st == 0
+    _assert_pixels(a, p, d["amp"], d["phi"])
+    # larger fan, more pixels: the oracle's ray_mirror_pts -> apert_fields -> project -> sum, pixel by pixel
+    n = 40
+    th, ph = gu.ff_fan(n)
+    geo = oracle.ff_geo_vec(rx_y_m=-1.32)
+    azel = np.array([[0.3 * gu.DE, gu.EL0], [11 * gu.DE, gu.EL0 - 7 * gu.DE], [-20 * gu.DE, gu.EL0 + 20 * gu.DE]])
+    plan = maps.FarFieldPlan(tgf, th, ph, x, y, e, device=0)
+    a, p, st = plan.run_panel_models(azel, pan1, pan2, backend=Backend)
+    assert st == 0
+    plain, _, _ = plan.run(azel)
+    for i, (az, el) in enumerate(azel):
+        m = oracle.ff_ray_mirror_pts(geo, th, ph, el, az)
+        idx1, idx2 = gu.panel_indices(m, pan1, pan2)
+        f = oracle.ff_apert_fields(geo, th, ph, m[6:9, 0], el, az, idx1, idx2, pan1, pan2)
+        beam = np.sum(oracle.ff_project(f, x, y, tgf.k) * e) / len(x) ** 2
+        _assert_pixels(a[i:i + 1], p[i:i + 1], [abs(beam)], [np.angle(beam)])
+        assert abs(a[i] - plain[i]) > 1e-4 * plain[i]          # the panel errors and gaps really changed the pixel
+    # error-free single panel = the plain fused map
+    saf.set_panel_backend(None)
+    pm = saf.panel_backend().panel_model_from_adjuster_offsets(1, np.zeros(1092), 1, 0)
+    a0, p0, st = plan.run_panel_models(azel, pm, pm)
+    _assert_pixels(a0, p0, plain, plan.run(azel)[1])
+    # through maps.ff_map (the CLI path)
+    px, am, phs = maps.ff_map(140, 0.25, 1, 1.32, x, y, e, n_scan=n, device=0, panel_models=(pm, pm))
+    px2, am2, phs2 = maps.ff_map(140, 0.25, 1, 1.32, x, y, e, n_scan=n, device=0)
+    _assert_pixels(am, phs, am2, phs2)
+
+
 def test_ff_project_to_data(oracle):
     from solat_optics_b200 import far_field_latrt as ffl
     from solat_optics_b200 import solat_apert_field as saf

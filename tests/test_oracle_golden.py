@@ -89,6 +89,32 @@ def test_ff_pixels(oracle, name):
         assert abs(gu.wrap(pha[0] - d["phi"][i])) <= 1e-9
 
 
+def test_ff_panel_errors(oracle):
+    """Non-zero panel-error polynomials and missing panels on a synthetic multi-panel layout: the reference's own
+    arithmetic (saf:587-703,805-852) with only identify_panel stood in; per-ray rows and the projected pixel."""
+    d = gu.load("ff_panels")
+    pan1, pan2 = d["pan1"], d["pan2"]
+    for i in range(int(d["n_cases"])):
+        n = int(d["in_n_scan"][i])
+        th, ph = gu.ff_fan(n)
+        geo = oracle.ff_geo_vec(rx_y_m=-float(d["in_offset"][i]))
+        el, az = float(d["in_el"][i]), float(d["in_az"][i])
+        m = oracle.ff_ray_mirror_pts(geo, th, ph, el, az)
+        np.testing.assert_allclose(m, d["mirror_%d" % i], rtol=0, atol=1e-9)
+        idx1, idx2 = gu.panel_indices(d["mirror_%d" % i], pan1, pan2)
+        assert (idx1 < 0).any() and (idx2 >= 0).any()
+        f = oracle.ff_apert_fields(geo, th, ph, m[6:9, 0], el, az, idx1, idx2, pan1, pan2)
+        ref = d["field_%d" % i]
+        assert np.array_equal(f[15] != 0, ref[15] != 0) and 0 < (ref[15] != 0).sum() < (m[0] != 0).sum()
+        np.testing.assert_allclose(f[:15], ref[:15], rtol=0, atol=1e-9)
+        assert np.abs(f[15] - ref[15]).max() <= 2 * ULP_1E8
+        x, y, e = gu.ff_grid(str(d["in_grid"][i]))
+        proj = oracle.ff_project(f, x, y, gu.ff_k(float(d["in_freq"][i])))
+        beam = np.sum(proj * e) / len(proj) ** 2
+        assert abs(abs(beam) ** 2 - d["amp"][i] ** 2) <= 1e-9 * d["amp"][i] ** 2
+        assert abs(gu.wrap(np.angle(beam) - d["phi"][i])) <= 1e-9
+
+
 def test_ff_project_matches_map(oracle):
     """orc_ff_project (ffl:9-32 restated) + the sum of ff_sim.py:216-217 == orc_ff_map."""
     n = 20

@@ -140,6 +140,24 @@ def test_panel_error_matches_oracle(shadow, oracle):
     assert np.abs(ref[15][both] - ideal[15][both]).max() > 1e-3
 
 
+def test_panel_error_matches_reference_fixture(shadow):
+    """The same per-ray source against the reference's own panel arithmetic (fixture ff_panels: synthetic 1 m panels,
+    seeded errors, missing panels; only identify_panel stood in)."""
+    d = gu.load("ff_panels")
+    pan1, pan2 = d["pan1"], d["pan2"]
+    for i in range(int(d["n_cases"])):
+        th, ph = gu.ff_fan(int(d["in_n_scan"][i]))
+        geo = np.array([np.arctan(0.5), -np.pi / 2 - np.arctan(1 / 3), 0, -7200.0, 0, 0, -7200.0, 1e8, -1e3 * float(d["in_offset"][i])])
+        m = d["mirror_%d" % i]
+        idx1, idx2 = gu.panel_indices(m, pan1, pan2)
+        out, agg = shadow.ff_field_rows(geo, th, ph, m[6:9, 0], float(d["in_el"][i]), float(d["in_az"][i]), idx1, idx2, pan1, pan2)
+        ref = d["field_%d" % i]
+        assert agg == 0
+        assert np.array_equal(out[15] != 0, ref[15] != 0)
+        np.testing.assert_allclose(out[:15], ref[:15], rtol=0, atol=1e-9)
+        assert np.abs(out[15] - ref[15]).max() <= 3 * ULP_1E8
+
+
 def test_status_flags(shadow):
     a = _src_axis(4)
     # source behind lens 1: the 1B plane root is negative -> reference brentq ValueError -> bracket flag
