@@ -17,6 +17,21 @@ import _launch  # noqa: F401
 from solat_optics_b200 import maps
 
 
+def panel_models(a):
+    """ff_sim.py:61-70: panel models from the external pan_mod, if the user has it on PYTHONPATH."""
+    if a.panels == "off":
+        return None
+    try:
+        import pan_mod as pm
+    except ImportError:
+        if a.adj_offsets:
+            raise SystemExit("--adj-offsets needs holosim-ml's pan_mod on PYTHONPATH")
+        return None
+    adj = np.load(a.adj_offsets) if a.adj_offsets else np.zeros((2, 1092))
+    save = 0
+    return pm.panel_model_from_adjuster_offsets(1, adj[0], 1, save), pm.panel_model_from_adjuster_offsets(2, adj[1], 1, save)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("freq", type=int)
@@ -27,6 +42,12 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--n-scan", type=int, default=100)
     ap.add_argument("--strict", action="store_true")
+    ap.add_argument("--panels", choices=["auto", "off"], default="auto",
+                    help="auto: when holosim-ml's pan_mod is importable, build the panel models as ff_sim.py:61-70 does "
+                         "(identify_panel on the host, panel errors in the kernel); off: every ray on an error-free panel")
+    ap.add_argument("--adj-offsets", default=None,
+                    help=".npy with the adjuster offsets (2, 1092) [M1, M2] fed to pan_mod.panel_model_from_adjuster_offsets "
+                         "(default: zeros, ff_sim.py:61-62)")
     a = ap.parse_args()
 
     sim_d = 1.25 if a.freq <= 120 else 1.32                      # ff_sim.py:36-41
@@ -36,7 +57,8 @@ def main():
     rank, world = _launch.init_distributed()
     t0 = time.perf_counter()
     data_x, data_y, e_rec = maps.near_field_to_e_rec(np.loadtxt(nf_path))
-    res = maps.ff_map(a.freq, a.res, a.num, a.offset, data_x, data_y, e_rec, a.n_scan, strict=a.strict)
+    res = maps.ff_map(a.freq, a.res, a.num, a.offset, data_x, data_y, e_rec, a.n_scan, strict=a.strict,
+                      panel_models=panel_models(a))
     if res is not None:
         pixels, amp, phase = res
         maps.save_map_txt(out_path, pixels[:, 0], pixels[:, 1], amp, phase)
