@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -62,13 +63,35 @@ static int fail(int code, const char* what, const char* detail = "")
         CK(cudaGetLastError());                                                   \
     } while (0)
 
-struct solat_ctx {
-    int device;
-    cudaDeviceProp prop;
-    cudaStream_t stream;   // used by the host entry points
-};
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync on one private stream per device, pool
+// kept warm): a plan is created and destroyed per map by the Python layer, and plain cudaMalloc / cudaFree cost more
+// than the map kernels themselves.  Allocation synchronises the private stream, so the pointer is valid on every
+// stream; a buffer is only released after the work that used it was synchronised (host entries synchronise their
+// stream before returning, plan destruction synchronises the device).
+static cudaStream_t pool_stream()
+{
+    static cudaStream_t streams[64] = {};
+    static std::atomic<bool> ready[64] = {};
+    static std::mutex mu;
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (!ready[d].load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!ready[d].load(std::memory_order_relaxed)) {
+            cudaStreamCreateWithFlags(&streams[d], cudaStreamNonBlocking);
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            ready[d].store(true, std::memory_order_release);
+        }
+    }
+    return streams[d];
+}
 
-// device buffer with RAII, bound to the ctx device
+// device buffer with RAII, bound to the current device
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -76,9 +99,14 @@ struct DevBuf {
     int reserve(size_t count)
     {
         if (count <= n) return 0;
-        if (p) cudaFree(p);
+        cudaStream_t ps = pool_stream();
+        if (p) {
+            cudaDeviceSynchronize();          // growing a buffer earlier launches may still read
+            cudaFreeAsync(p, ps);
+        }
         p = nullptr; n = 0;
-        CK(cudaMalloc(&p, count * sizeof(T)));
+        CK(cudaMallocAsync(&p, count * sizeof(T), ps));
+        CK(cudaStreamSynchronize(ps));
         n = count;
         return 0;
     }
@@ -89,7 +117,7 @@ struct DevBuf {
         CK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
         return 0;
     }
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, pool_stream()); }
 };
 
 // pinned host staging buffer (one D2H per host-entry call instead of three)
@@ -106,6 +134,16 @@ struct PinnedBuf {
         return 0;
     }
     ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+
+struct solat_ctx {
+    int device;
+    cudaDeviceProp prop;
+    cudaStream_t stream;   // used by the host entry points
+    // staging of the host-buffer map entries (calls on one context are synchronous, one at a time): pixel list in,
+    // [amp | phase | status word] out, and its pinned mirror for a single D2H
+    DevBuf<double> stage_in, stage_out;
+    PinnedBuf pin;
 };
 
 struct AngleTabs {
@@ -496,7 +534,7 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
     double* s_gy = s_gx + q.grid.M;                                        // [M] data_y[:, 0] when all columns agree
     int* row_lo = reinterpret_cast<int*>(s_gy + q.grid.M);                 // [nph] first accepted theta index of a row
     int* row_pre = row_lo + (q.rows ? q.ang.nph : 0);                      // [nph + 1] accepted rays before the row
-    __shared__ int s_queue_walk;
+    __shared__ int s_queue_walk, s_next_chunk;
     __shared__ double s_t2e[9];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
@@ -505,6 +543,7 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
     if (tid == 0) {
         ff_build_frames(K_COEF, g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
         s_queue_walk = !q.rows;
+        s_next_chunk = 0;
         if (PANEL) {
             for (int i = 0; i < 9; i++) s_t2e[i] = fr->t2.a[i];
             if (g.src[2] != 0) for (int i = 0; i < 3; i++) s_t2e[3 * i + 2] /= cos(atan(1.0 / 3.0));   // saf:828-829
@@ -554,29 +593,22 @@ __global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams
     const double cx = fr->centre[0], cz = fr->centre[2];
     int st = 0, cnt = 0;                                   // cnt: queue fill, identical in all lanes of the warp
     int chunk = warp;
-    // interval walk: warp w owns accepted rays [v, v_end) of the pixel's dense list, 32 per step
-    int v = 0, v_end = 0, row = 0;
-    if (!queue_walk) {
-        const int n_acc = row_pre[q.ang.nph];
-        const int per = (n_acc + FF_WARPS - 1) / FF_WARPS;
-        v = min(warp * per, n_acc) + lane;
-        v_end = min((warp + 1) * per, n_acc);
-        int a = 0, b = q.ang.nph - 1;                      // row of the lane's first ray: last row with row_pre[row] <= v
-        while (a < b) {
-            const int m = (a + b + 1) >> 1;
-            if (row_pre[m] <= v) a = m; else b = m - 1;
-        }
-        row = a;
-    }
+    // interval walk: warps draw chunks of 32 consecutive accepted rays of the pixel's dense list from a shared counter
+    // (only the pixel's last chunk is partial, and the warps reach the end-of-pixel barrier together)
+    const int n_acc = queue_walk ? 0 : row_pre[q.ang.nph];
+    int row = 0;
     for (;;) {
         int r0 = -1;
         if (!queue_walk) {
-            if (v - lane >= v_end) break;
-            if (v < v_end) {
-                while (row_pre[row + 1] <= v) ++row;
+            int c = 0;
+            if (lane == 0) c = atomicAdd(&s_next_chunk, 1);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c * 32 >= n_acc) break;
+            const int v = c * 32 + lane;
+            if (v < n_acc) {
+                while (row_pre[row + 1] <= v) ++row;      // chunks only grow, so the row cursor only moves forward
                 r0 = row * nth + row_lo[row] + (v - row_pre[row]);
             }
-            v += 32;
         } else {
             const bool more = chunk * 32 < n_rays;
             if (cnt < 32 && more) {
@@ -865,6 +897,7 @@ void solat_ctx_destroy(solat_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -973,8 +1006,6 @@ struct solat_nf_plan {
     DevBuf<int> act_idx;
     DevBuf<double2> phasor;                 // [nrx][nfreq][n_act]
     DevBuf<double2> partial;
-    DevBuf<double> h_src, h_out;            // device staging for the host entry point: [amp | phase | status word]
-    PinnedBuf pin;
     DevBuf<int> status;
     std::vector<double> kk;
     int nrx = 1;
@@ -1099,6 +1130,7 @@ void solat_nf_plan_destroy(solat_nf_plan* p)
 {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
+    cudaDeviceSynchronize();   // device-pointer maps may still be in flight on the caller's streams
     delete p;
 }
 int solat_nf_plan_active_rays(const solat_nf_plan* p) { return p ? p->n_act : 0; }
@@ -1127,17 +1159,17 @@ int solat_nf_map_host(solat_nf_plan* p, const double* src_xz, int npix, double* 
     CK(cudaSetDevice(p->ctx->device));
     cudaStream_t s = p->ctx->stream;
     const size_t n = p->kk.size() * (size_t)p->nrx * npix;   // channels x pixels
-    if (int rc = p->h_src.upload(src_xz, 2 * (size_t)npix, s)) return rc;
-    if (int rc = p->h_out.reserve(2 * n + 1)) return rc;
-    if (int rc = p->pin.reserve(2 * n + 1)) return rc;
-    if (int rc = nf_map_launch(p, p->h_src.p, npix, p->h_out.p, p->h_out.p + n, s)) return rc;
-    pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->h_out.p + 2 * n);
+    if (int rc = p->ctx->stage_in.upload(src_xz, 2 * (size_t)npix, s)) return rc;
+    if (int rc = p->ctx->stage_out.reserve(2 * n + 1)) return rc;
+    if (int rc = p->ctx->pin.reserve(2 * n + 1)) return rc;
+    if (int rc = nf_map_launch(p, p->ctx->stage_in.p, npix, p->ctx->stage_out.p, p->ctx->stage_out.p + n, s)) return rc;
+    pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->ctx->stage_out.p + 2 * n);
     LAUNCHED();
-    CK(cudaMemcpyAsync(p->pin.p, p->h_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->ctx->pin.p, p->ctx->stage_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    memcpy(amp, p->pin.p, n * sizeof(double));
-    memcpy(phase, p->pin.p + n, n * sizeof(double));
-    const int st = (int)p->pin.p[2 * n];
+    memcpy(amp, p->ctx->pin.p, n * sizeof(double));
+    memcpy(phase, p->ctx->pin.p + n, n * sizeof(double));
+    const int st = (int)p->ctx->pin.p[2 * n];
     if (st) CK(cudaMemset(p->status.p, 0, sizeof(int)));
     if (status) *status = st;
     return SOLAT_OK;
@@ -1245,8 +1277,6 @@ struct solat_ff_plan {
     AngleTabsOwner ang;
     DevBuf<double> gx, gy;
     DevBuf<double2> e_rec;
-    DevBuf<double> h_azel, h_out;           // [amp | phase | status word]
-    PinnedBuf pin;
     DevBuf<int> status;
     DevBuf<short> pidx;                     // [2][npix][n_rays] panel columns of a panel-model map
     DevBuf<double> pan, xy;                 // panel models; mirror coordinates for identify_panel
@@ -1313,6 +1343,7 @@ void solat_ff_plan_destroy(solat_ff_plan* p)
 {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
+    cudaDeviceSynchronize();   // device-pointer maps may still be in flight on the caller's streams
     delete p;
 }
 int solat_ff_map_device(solat_ff_plan* p, const double* d_azel, int npix, double* d_amp, double* d_phase, void* stream)
@@ -1335,17 +1366,17 @@ int solat_ff_map_host(solat_ff_plan* p, const double* azel, int npix, double* am
     CK(cudaSetDevice(p->ctx->device));
     cudaStream_t s = p->ctx->stream;
     const size_t n = (size_t)npix;
-    if (int rc = p->h_azel.upload(azel, 2 * n, s)) return rc;
-    if (int rc = p->h_out.reserve(2 * n + 1)) return rc;
-    if (int rc = p->pin.reserve(2 * n + 1)) return rc;
-    if (int rc = ff_map_launch(p, p->h_azel.p, npix, p->h_out.p, p->h_out.p + n, s)) return rc;
-    pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->h_out.p + 2 * n);
+    if (int rc = p->ctx->stage_in.upload(azel, 2 * n, s)) return rc;
+    if (int rc = p->ctx->stage_out.reserve(2 * n + 1)) return rc;
+    if (int rc = p->ctx->pin.reserve(2 * n + 1)) return rc;
+    if (int rc = ff_map_launch(p, p->ctx->stage_in.p, npix, p->ctx->stage_out.p, p->ctx->stage_out.p + n, s)) return rc;
+    pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->ctx->stage_out.p + 2 * n);
     LAUNCHED();
-    CK(cudaMemcpyAsync(p->pin.p, p->h_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->ctx->pin.p, p->ctx->stage_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    memcpy(amp, p->pin.p, n * sizeof(double));
-    memcpy(phase, p->pin.p + n, n * sizeof(double));
-    const int st = (int)p->pin.p[2 * n];
+    memcpy(amp, p->ctx->pin.p, n * sizeof(double));
+    memcpy(phase, p->ctx->pin.p + n, n * sizeof(double));
+    const int st = (int)p->ctx->pin.p[2 * n];
     if (st) CK(cudaMemset(p->status.p, 0, sizeof(int)));
     if (status) *status = st;
     return SOLAT_OK;
@@ -1357,10 +1388,10 @@ int solat_ff_map_mirror_xy_host(solat_ff_plan* p, const double* azel, int npix, 
     CK(cudaSetDevice(p->ctx->device));
     cudaStream_t s = p->ctx->stream;
     const size_t n = (size_t)npix * 4 * p->n_rays;
-    if (int rc = p->h_azel.upload(azel, 2 * (size_t)npix, s)) return rc;
+    if (int rc = p->ctx->stage_in.upload(azel, 2 * (size_t)npix, s)) return rc;
     if (int rc = p->xy.reserve(n)) return rc;
     if (npix > 65535) return fail(SOLAT_ERR_ARG, "at most 65535 pixels per call");
-    ff_mirror_xy_kernel<<<dim3((p->n_rays + 127) / 128, npix), 128, 0, s>>>(p->ang.tabs, p->g, p->h_azel.p, p->xy.p, p->status.p);
+    ff_mirror_xy_kernel<<<dim3((p->n_rays + 127) / 128, npix), 128, 0, s>>>(p->ang.tabs, p->g, p->ctx->stage_in.p, p->xy.p, p->status.p);
     LAUNCHED();
     CK(cudaMemcpyAsync(xy, p->xy.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     int st = 0;
@@ -1380,9 +1411,9 @@ int solat_ff_map_panels_host(solat_ff_plan* p, const double* azel, int npix, con
     const size_t n = (size_t)npix, nr = n * p->n_rays;
     for (size_t i = 0; i < nr; i++)
         if (pan_idx1[i] >= np1 || pan_idx2[i] >= np2) return fail(SOLAT_ERR_ARG, "panel index outside its panel model");
-    if (int rc = p->h_azel.upload(azel, 2 * n, s)) return rc;
-    if (int rc = p->h_out.reserve(2 * n + 1)) return rc;
-    if (int rc = p->pin.reserve(2 * n + 1)) return rc;
+    if (int rc = p->ctx->stage_in.upload(azel, 2 * n, s)) return rc;
+    if (int rc = p->ctx->stage_out.reserve(2 * n + 1)) return rc;
+    if (int rc = p->ctx->pin.reserve(2 * n + 1)) return rc;
     if (int rc = p->pidx.reserve(2 * nr)) return rc;
     if (int rc = p->pan.reserve(10 * ((size_t)np1 + np2))) return rc;
     CK(cudaMemcpyAsync(p->pidx.p, pan_idx1, nr * sizeof(short), cudaMemcpyHostToDevice, s));
@@ -1390,19 +1421,19 @@ int solat_ff_map_panels_host(solat_ff_plan* p, const double* azel, int npix, con
     CK(cudaMemcpyAsync(p->pan.p, pan1, 10 * (size_t)np1 * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(p->pan.p + 10 * (size_t)np1, pan2, 10 * (size_t)np2 * sizeof(double), cudaMemcpyHostToDevice, s));
     FfMapParams q;
-    q.ang = p->ang.tabs; q.g = p->g; q.azel = p->h_azel.p; q.grid = p->grid; q.e_rec = p->e_rec.p;
+    q.ang = p->ang.tabs; q.g = p->g; q.azel = p->ctx->stage_in.p; q.grid = p->grid; q.e_rec = p->e_rec.p;
     q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
-    q.amp = p->h_out.p; q.phase = p->h_out.p + n; q.status = p->status.p; q.rows = 0;
+    q.amp = p->ctx->stage_out.p; q.phase = p->ctx->stage_out.p + n; q.status = p->status.p; q.rows = 0;
     q.pidx1 = p->pidx.p; q.pidx2 = p->pidx.p + nr; q.pan1 = p->pan.p; q.pan2 = p->pan.p + 10 * (size_t)np1; q.np1 = np1; q.np2 = np2;
     ff_map_kernel<true><<<npix, FF_T, p->smem, s>>>(q);
     LAUNCHED();
-    pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->h_out.p + 2 * n);
+    pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->ctx->stage_out.p + 2 * n);
     LAUNCHED();
-    CK(cudaMemcpyAsync(p->pin.p, p->h_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->ctx->pin.p, p->ctx->stage_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    memcpy(amp, p->pin.p, n * sizeof(double));
-    memcpy(phase, p->pin.p + n, n * sizeof(double));
-    const int st = (int)p->pin.p[2 * n];
+    memcpy(amp, p->ctx->pin.p, n * sizeof(double));
+    memcpy(phase, p->ctx->pin.p + n, n * sizeof(double));
+    const int st = (int)p->ctx->pin.p[2 * n];
     if (st) CK(cudaMemset(p->status.p, 0, sizeof(int)));
     if (status) *status = st;
     return SOLAT_OK;

@@ -767,25 +767,50 @@ SOLAT_HD vec3 launch_dir(double sin_th, double cos_th, double sin_ph, double cos
 // Accepted rays of one phi row of a launch fan whose theta is strictly monotone inside one branch of tan: the rays
 // of the row hit the aperture plane along a straight line, monotonically, so the squared radius about the M1 centre
 // is unimodal in the theta index and the accepted rays (ff_aperture, the same FP64 operations) are ONE interval
-// [lo, hi).  Bisection for the closest ray, then for both rim crossings: ~4 log2(nth) evaluations instead of nth.
-// Returns false when the plane-hit denominator changes sign along the row (rays skimming the aperture plane's
-// horizon: the caller must test every ray instead).
+// [lo, hi).  First a guess: the chord of the aperture circle on the line through the row's two end rays, taken as
+// uniform in the index (true for the reference's narrow linspace fans); it is accepted only if the exact test
+// confirms both rim crossings (accepted at lo and hi-1, rejected at lo-1 and hi), 6 evaluations per row.  Otherwise
+// bisection: the closest ray, then both crossings, ~4 log2(nth) evaluations.  Either way the interval is exactly the
+// set a per-ray test would accept.  Returns false when the plane-hit denominator changes sign along the row (rays
+// skimming the aperture plane's horizon: the caller must test every ray instead).
 SOLAT_HD bool ff_row_interval(const Coef& C, const FfGeom& g, const FfFrames& f, const double* st, const double* ct, int nth,
                               double sp, double cp, int& lo, int& hi)
 {
-    auto r2 = [&](int i) {
+    auto hit = [&](int i, double& px, double& py, double& den) {
         const vec3 d = launch_dir(st[i], ct[i], sp, cp);
+        den = fma(f.ap_row[0], d.x, fma(f.ap_row[1], d.y, f.ap_row[2] * d.z));
         vec3 Pa;
         double t_ap;
         ff_aperture(C, g, f, d, t_ap, Pa);
-        const double dy = Pa.y - C.ff[2];
-        return fma(Pa.x, Pa.x, dy * dy);
+        px = Pa.x; py = Pa.y - C.ff[2];
+        return fma(px, px, py * py);
     };
-    auto den = [&](int i) {
-        const vec3 d = launch_dir(st[i], ct[i], sp, cp);
-        return fma(f.ap_row[0], d.x, fma(f.ap_row[1], d.y, f.ap_row[2] * d.z));
+    auto r2 = [&](int i) {
+        double px, py, den;
+        return hit(i, px, py, den);
     };
-    const bool one_sided = den(0) * den(nth - 1) > 0.0;
+    auto rejected = [&](int i) { return r2(i) > C.ff[3]; };
+    double x0, y0, x1, y1, den0, den1;
+    const double r2_0 = hit(0, x0, y0, den0), r2_1 = hit(nth - 1, x1, y1, den1);
+    const bool one_sided = den0 * den1 > 0.0;
+    {   // chord guess
+        const double dx = x1 - x0, dy = y1 - y0;
+        const double qa = fma(dx, dx, dy * dy), qb = fma(x0, dx, y0 * dy), qc = r2_0 - C.ff[3];
+        const double disc = fma(qb, qb, -qa * qc);
+        if (disc > 0.0 && qa > 0.0) {
+            const double sq = sqrt(disc), scale = (double)(nth - 1) / qa;
+            const double s_lo = (-qb - sq) * scale, s_hi = (-qb + sq) * scale;
+            if (s_hi >= 0.0 && s_lo <= (double)(nth - 1)) {
+                const int gl = s_lo > 0.0 ? (int)ceil(s_lo) : 0;
+                const int gh = s_hi < (double)(nth - 1) ? (int)floor(s_hi) + 1 : nth;
+                if (gl < gh && gl < nth && gh > 0) {
+                    const bool ok_lo = (gl == 0 ? !(r2_0 > C.ff[3]) : (!rejected(gl) && rejected(gl - 1)));
+                    const bool ok_hi = ok_lo && (gh == nth ? !(r2_1 > C.ff[3]) : (!rejected(gh - 1) && rejected(gh)));
+                    if (ok_hi) { lo = gl; hi = gh; return one_sided; }
+                }
+            }
+        }
+    }
     int a = 0, b = nth - 1;
     while (a < b) {
         const int m = (a + b) >> 1;
@@ -793,17 +818,17 @@ SOLAT_HD bool ff_row_interval(const Coef& C, const FfGeom& g, const FfFrames& f,
     }
     const int imin = a;
     lo = hi = 0;
-    if (!(r2(imin) > C.ff[3])) {
+    if (!rejected(imin)) {
         a = -1; b = imin;                                    // a rejected (or before the row), b accepted
         while (a + 1 < b) {
             const int m = (a + b) >> 1;
-            if (r2(m) > C.ff[3]) a = m; else b = m;
+            if (rejected(m)) a = m; else b = m;
         }
         lo = b;
         a = imin; b = nth;                                   // a accepted, b rejected (or past the row)
         while (a + 1 < b) {
             const int m = (a + b) >> 1;
-            if (r2(m) > C.ff[3]) b = m; else a = m;
+            if (rejected(m)) b = m; else a = m;
         }
         hi = b;
     }
