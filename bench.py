@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+NCU_DRAM_BYTES_PER_LAUNCH = 151808 + 6400   # ff_map_kernel, r1f capture (read + write)
 METRIC = "scan_pixel_rays_per_s"
 UNIT = "pixel*rays/s"
 FREQ, RES_ARCMIN, NUM, OFFSET, N_SCAN = 140, 0.25, 20, 1.32, 100
@@ -271,7 +272,10 @@ def run_ours(args):
                            "pinned H2D + solat_ff_map_device + NCCL gather + D2H of the gathered map on rank 0"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of ff_map_kernel, bytes per launch, ncu --set full "
+                                           "capture profiles/r01f_raw_metrics.csv (algorithmic: 27 kB pixel list + 27 kB results + "
+                                           "~45 kB E_rec and angle tables); the kernel is compute bound",
                          "peak_source": "burst DFMA issue-rate probe run in this process (best of 5 x 2 ms launches; MEASURED_PEAKS.json "
                                         "has no FP64 figure); nominal %.1f = 148 SM x 64 lanes x 2 x 1.965 GHz" % NOMINAL_FP64_TFLOPS,
                          "frac_of_nominal": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None,
