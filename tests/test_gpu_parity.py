@@ -501,6 +501,44 @@ def test_ff_ray_walks_agree(oracle, monkeypatch):
         _assert_pixels(a, p, oa, op)
 
 
+def test_seeded_sweep_against_oracle(oracle):
+    """Seeded random inputs over the ranges the reference's scripts sweep: near-field source and receiver positions,
+    frequencies of both bands, odd ray counts; far-field pointings over and beyond the shipped map, focal offsets,
+    fan sizes, both E_rec grids.  Every pixel within the north-star tolerance of the oracle."""
+    from solat_optics_b200 import maps
+
+    rng = np.random.default_rng(20251020)
+    for trial in range(6):
+        freq = float(rng.choice([90.0, 140.0, 150.0, 220.0, 280.0]))
+        n = int(rng.choice([17, 23, 30, 41]))
+        p_rx = tuple(np.r_[rng.uniform(-80, 80), 0.0, rng.uniform(-80, 80)]) if trial % 2 else (0.0, 0.0, 0.0)
+        tg = maps.holo_tele_geo(freq, n)
+        rx_opl, rx_w = maps.receiver_field(tg, p_rx)
+        src = np.c_[rng.uniform(-120, 120, 24), rng.uniform(-120, 120, 24)]
+        src[:4] *= 3.0                                              # far off axis: mostly or fully vignetted
+        amp, ph, st = maps.NearFieldPlan(tg, [tg.k], rx_opl, rx_w, device=0).run(src)
+        assert st == 0
+        rx = oracle.nf_rx_trace(p_rx, tg.th_fwhp, n)
+        oa, op = oracle.nf_map(src, tg.y_ap, n, rx[3], rx[4] * gu.lyot_mask(n), [tg.k])
+        _assert_pixels(amp[0][oa[0] > 0], ph[0][oa[0] > 0], oa[0][oa[0] > 0], op[0][oa[0] > 0])
+        assert (amp[0][oa[0] == 0] == 0).all()
+    for trial in range(6):
+        offset = float(rng.choice([1.25, 1.32, 1.33, 1.4]))
+        freq = int(rng.choice([90, 140, 150, 280]))
+        n = int(rng.choice([21, 32, 45, 64]))
+        tgf = maps.ff_tele_geo(freq, offset)
+        geo = oracle.ff_geo_vec(rx_y_m=-offset)
+        th, phi = gu.ff_fan(n)
+        x, y, e = gu.ff_grid("wide61" if trial % 3 else "nf51")
+        azel = np.c_[rng.uniform(-30, 30, 16) * gu.DE, gu.EL0 + rng.uniform(-30, 30, 16) * gu.DE]
+        a, p, st = maps.FarFieldPlan(tgf, th, phi, x, y, e, device=0).run(azel)
+        assert st == 0
+        oa, op = oracle.ff_map(geo, azel, th, phi, x, y, e, tgf.k)
+        ok = oa > 0
+        _assert_pixels(a[ok], p[ok], oa[ok], op[ok])
+        assert (a[~ok] == 0).all()
+
+
 def test_ff_odd_sizes_and_edge_grids(oracle):
     """Ragged inputs: a fan that is not a multiple of the CTA size, a 1-pixel map, a 2x2 E_rec grid (every ray
     piles into cell 0 or is skipped), a grid entirely below the beam (all rays skipped -> 0)."""
