@@ -1308,7 +1308,8 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
     if (!c || !g || !theta || !phi || !data_x || !data_y || !e_rec || !out || nth <= 0 || nph <= 0 || M <= 0)
         return fail(SOLAT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(c->device));
-    const int rows = ff_rows_usable(theta, nth, nph) ? 1 : 0;
+    int rows = ff_rows_usable(theta, nth, nph) ? 1 : 0;
+    if (rows && ff_map_smem(M, nph) > (size_t)c->prop.sharedMemPerBlockOptin) rows = 0;   // no room for the row tables: queue walk
     size_t smem = ff_map_smem(M, rows ? nph : 0);
     if (const char* pad = getenv("SOLAT_FF_SMEM_PAD")) smem += (size_t)atol(pad);   // occupancy experiments only
     if (smem > (size_t)c->prop.sharedMemPerBlockOptin)
