@@ -13,6 +13,7 @@
 //   fp64_peak_kernel       DFMA issue-rate microbenchmark (roofline denominator)
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -29,7 +30,7 @@ using namespace solat;
 
 // launch-shape tunables (tools/variant_bench.py A/B-tests them on the B200)
 #ifndef SOLAT_FF_T
-#define SOLAT_FF_T 256      // threads per far-field CTA (= rays per batch)
+#define SOLAT_FF_T 256      // threads per far-field CTA while three CTAs fit on an SM (E_rec grids up to ~94 x 94)
 #endif
 #ifndef SOLAT_FF_MINB
 #define SOLAT_FF_MINB 3     // resident far-field CTAs per SM the register allocation is capped for
@@ -475,8 +476,10 @@ __global__ void ff_project_fill_kernel(const double* sim, int n_pts, const int* 
 // ------------------------------------------------------------------------------------------------
 // far field: fused map
 // ------------------------------------------------------------------------------------------------
+// CTA shapes of the fused far-field map.  The winner table (8 B per E_rec cell) lives in shared memory, so a large grid
+// limits the CTAs per SM; the shape is chosen per plan so that 24 warps stay resident (80 registers per thread):
+// 256 threads x 3 CTAs, 384 x 2 (grids up to ~118 x 118), 768 x 1 (up to 168 x 168).
 constexpr int FF_T = SOLAT_FF_T;
-constexpr int FF_WARPS = FF_T / 32;
 constexpr int FF_WQ = 64;            // per-warp queue capacity
 constexpr int FF_MAX_ROWS = 4096;    // phi rows the interval walk keeps on chip; larger fans take the queue walk
 struct FfMapParams {
@@ -522,9 +525,10 @@ __device__ __forceinline__ PanelErr load_panel(const double* pan, int np, int co
 //   * PANEL (adjuster-error studies, ff_sim.py:61-70 with non-zero offsets): every ray carries the panel-model
 //     columns the host derived with pan_mod.identify_panel; rays on no panel are dropped (saf:626-628,805-809), the
 //     others see their panels' error polynomials inside both Newton solves.  Always the queue walk.
-template <bool PANEL>
-__global__ void __launch_bounds__(FF_T, SOLAT_FF_MINB) ff_map_kernel(FfMapParams q)
+template <bool PANEL, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
 {
+    constexpr int FF_T = T, FF_WARPS = T / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cells = q.grid.M * q.grid.M;
     FfFrames* fr = reinterpret_cast<FfFrames*>(smem_raw);
@@ -758,10 +762,10 @@ static bool ff_rows_usable(const double* theta, int nth, int nph)
     return true;
 }
 
-static size_t ff_map_smem(int M, int rows_nph)
+static size_t ff_map_smem(int M, int rows_nph, int threads)
 {
     const size_t cells = (size_t)M * M;
-    return ((sizeof(FfFrames) + 15) / 16) * 16 + cells * sizeof(unsigned long long) + (size_t)FF_WARPS * FF_WQ * sizeof(int) +
+    return ((sizeof(FfFrames) + 15) / 16) * 16 + cells * sizeof(unsigned long long) + (size_t)(threads / 32) * FF_WQ * sizeof(int) +
            2 * (size_t)M * sizeof(double) + (rows_nph ? (2 * (size_t)rows_nph + 1) * sizeof(int) : 0);
 }
 
@@ -1282,9 +1286,34 @@ struct solat_ff_plan {
     DevBuf<double> pan, xy;                 // panel models; mirror coordinates for identify_panel
     FfGrid grid;
     double k, key_base, key_unit;
-    int M, n_rays, rows;
+    int M, n_rays, rows, shape;
     size_t smem;
 };
+
+constexpr int FF_NSHAPES = 3;
+static const int FF_SHAPES[FF_NSHAPES][2] = {{FF_T, SOLAT_FF_MINB}, {384, 2}, {768, 1}};   // threads, CTAs per SM
+template <bool PANEL>
+static void ff_map_dispatch(int shape, const FfMapParams& q, int npix, size_t smem, cudaStream_t s)
+{
+    if (shape == 0) ff_map_kernel<PANEL, FF_T, SOLAT_FF_MINB><<<npix, FF_T, smem, s>>>(q);
+    else if (shape == 1) ff_map_kernel<PANEL, 384, 2><<<npix, 384, smem, s>>>(q);
+    else ff_map_kernel<PANEL, 768, 1><<<npix, 768, smem, s>>>(q);
+}
+static int ff_map_set_smem(int shape, size_t smem)
+{
+    const int b = (int)smem;
+    if (shape == 0) {
+        CK(cudaFuncSetAttribute(ff_map_kernel<false, FF_T, SOLAT_FF_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+        CK(cudaFuncSetAttribute(ff_map_kernel<true, FF_T, SOLAT_FF_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    } else if (shape == 1) {
+        CK(cudaFuncSetAttribute(ff_map_kernel<false, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+        CK(cudaFuncSetAttribute(ff_map_kernel<true, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    } else {
+        CK(cudaFuncSetAttribute(ff_map_kernel<false, 768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+        CK(cudaFuncSetAttribute(ff_map_kernel<true, 768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    }
+    return SOLAT_OK;
+}
 
 static int ff_map_launch(solat_ff_plan* p, const double* d_azel, int npix, double* d_amp, double* d_phase, cudaStream_t s)
 {
@@ -1294,7 +1323,7 @@ static int ff_map_launch(solat_ff_plan* p, const double* d_azel, int npix, doubl
     q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
     q.amp = d_amp; q.phase = d_phase; q.status = p->status.p; q.rows = p->rows;
     q.pidx1 = q.pidx2 = nullptr; q.pan1 = q.pan2 = nullptr; q.np1 = q.np2 = 0;
-    ff_map_kernel<false><<<npix, FF_T, p->smem, s>>>(q);
+    ff_map_dispatch<false>(p->shape, q, npix, p->smem, s);
     LAUNCHED();
     return SOLAT_OK;
 }
@@ -1309,17 +1338,28 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
         return fail(SOLAT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(c->device));
     int rows = ff_rows_usable(theta, nth, nph) ? 1 : 0;
-    if (rows && ff_map_smem(M, nph) > (size_t)c->prop.sharedMemPerBlockOptin) rows = 0;   // no room for the row tables: queue walk
-    size_t smem = ff_map_smem(M, rows ? nph : 0);
+    // CTA shape: the one that keeps the most warps resident next to the shared-memory winner table
+    const size_t sm_smem = (size_t)c->prop.sharedMemPerMultiprocessor, cta_max = (size_t)c->prop.sharedMemPerBlockOptin;
+    int shape = -1;
+    size_t smem = 0;
+    for (int pass = 0; pass < 2 && shape < 0; pass++) {          // second pass: without the row tables (queue walk)
+        if (pass == 1) rows = 0;
+        int best_warps = 0;
+        for (int k = 0; k < FF_NSHAPES; k++) {
+            const size_t need = ff_map_smem(M, rows ? nph : 0, FF_SHAPES[k][0]) + 4400;     // + static shared memory
+            if (need > cta_max) continue;
+            const int ctas = (int)std::min<size_t>((size_t)FF_SHAPES[k][1], sm_smem / (need + 1024));   // 1 KB reserved per CTA
+            const int warps = ctas * FF_SHAPES[k][0] / 32;
+            if (warps > best_warps) { best_warps = warps; shape = k; smem = need - 4400; }
+        }
+    }
+    if (shape < 0) return fail(SOLAT_ERR_ARG, "E_rec grid too large for the shared-memory winner table (M <= 168)");
     if (const char* pad = getenv("SOLAT_FF_SMEM_PAD")) smem += (size_t)atol(pad);   // occupancy experiments only
-    if (smem > (size_t)c->prop.sharedMemPerBlockOptin)
-        return fail(SOLAT_ERR_ARG, "E_rec grid too large for the shared-memory winner table (M <= 168)");
     if ((long long)nth * nph > FF_MAX_RAYS)
         return fail(SOLAT_ERR_ARG, "launch fan too large for the 20-bit ray index of the winner key (<= 1048575 rays)");
-    CK(cudaFuncSetAttribute(ff_map_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(ff_map_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = ff_map_set_smem(shape, smem)) return rc;
     solat_ff_plan* p = new solat_ff_plan();
-    p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem; p->n_rays = nth * nph; p->rows = rows;
+    p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem; p->n_rays = nth * nph; p->rows = rows; p->shape = shape;
     // fixed-point frame of the winner keys: every path length of this telescope lies within a few tens of metres
     // of |source - rotation centre| + 2.2e4 mm; unit = half an ulp of that, so the offsets are exact integers
     {
@@ -1426,7 +1466,7 @@ int solat_ff_map_panels_host(solat_ff_plan* p, const double* azel, int npix, con
     q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
     q.amp = p->ctx->stage_out.p; q.phase = p->ctx->stage_out.p + n; q.status = p->status.p; q.rows = 0;
     q.pidx1 = p->pidx.p; q.pidx2 = p->pidx.p + nr; q.pan1 = p->pan.p; q.pan2 = p->pan.p + 10 * (size_t)np1; q.np1 = np1; q.np2 = np2;
-    ff_map_kernel<true><<<npix, FF_T, p->smem, s>>>(q);
+    ff_map_dispatch<true>(p->shape, q, npix, p->smem, s);
     LAUNCHED();
     pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->ctx->stage_out.p + 2 * n);
     LAUNCHED();

@@ -547,7 +547,10 @@ def test_ff_odd_sizes_and_edge_grids(oracle):
     tg = maps.ff_tele_geo(140, 1.32)
     geo = oracle.ff_geo_vec(rx_y_m=-1.32)
     th, phi = gu.ff_fan(37)
-    for ax in (np.array([-1.0, 1.0]), np.linspace(-40, -35, 7), np.linspace(-3, 28, 11)):
+    # (the 101- and 150-point grids switch the kernel to its 384- and 768-thread CTA shapes: the winner table of a
+    #  large grid leaves room for fewer CTAs per SM)
+    for ax in (np.array([-1.0, 1.0]), np.linspace(-40, -35, 7), np.linspace(-3, 28, 11), np.linspace(-30, 30, 101),
+               np.linspace(-28, 31, 150)):
         yy, xx = np.meshgrid(ax, ax, indexing="ij")
         e = (1 + 0.1 * xx) * np.exp(0.2j * yy)
         a, p, st = maps.FarFieldPlan(tg, th, phi, xx, yy, e, device=0).run([[gu.DE, gu.EL0 - gu.DE]])
