@@ -191,7 +191,9 @@ def run_ours(args):
     h_phase = torch.empty(npix, dtype=torch.float64).pin_memory()
     d_azel = h_azel.to(dev)
     d_out = torch.empty((2, npix), dtype=torch.float64, device=dev)      # rows: amp, phase
-    gathered = [torch.empty_like(d_out) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # rank 0 gathers into views of ONE device tensor, so the gathered map leaves with a single D2H copy
+    d_all = torch.empty((world, 2, npix), dtype=torch.float64, device=dev) if (world > 1 and rank == 0) else None
+    gathered = list(d_all.unbind(0)) if d_all is not None else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -234,8 +236,7 @@ def run_ours(args):
         plan.run_device(d_azel, d_out[0], d_out[1], stream)
         dist.gather(d_out, gathered, dst=0)
         if rank == 0:
-            for r in range(world):
-                h_all[r].copy_(gathered[r], non_blocking=True)
+            h_all.copy_(d_all, non_blocking=True)
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
