@@ -145,6 +145,7 @@ struct solat_ctx {
     // [amp | phase | status word] out, and its pinned mirror for a single D2H
     DevBuf<double> stage_in, stage_out;
     PinnedBuf pin;
+    std::mutex stage_mu;   // host-buffer map entries of one context run one at a time
 };
 
 struct AngleTabs {
@@ -1160,6 +1161,7 @@ __global__ void pack_status_kernel(const int* status, double* slot) { *slot = (d
 int solat_nf_map_host(solat_nf_plan* p, const double* src_xz, int npix, double* amp, double* phase, int* status)
 {
     if (!p || !src_xz || !amp || !phase || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lock(p->ctx->stage_mu);
     CK(cudaSetDevice(p->ctx->device));
     cudaStream_t s = p->ctx->stream;
     const size_t n = p->kk.size() * (size_t)p->nrx * npix;   // channels x pixels
@@ -1404,6 +1406,7 @@ int solat_ff_plan_status(solat_ff_plan* p, int* status)
 int solat_ff_map_host(solat_ff_plan* p, const double* azel, int npix, double* amp, double* phase, int* status)
 {
     if (!p || !azel || !amp || !phase || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lock(p->ctx->stage_mu);
     CK(cudaSetDevice(p->ctx->device));
     cudaStream_t s = p->ctx->stream;
     const size_t n = (size_t)npix;
@@ -1426,6 +1429,7 @@ int solat_ff_map_host(solat_ff_plan* p, const double* azel, int npix, double* am
 int solat_ff_map_mirror_xy_host(solat_ff_plan* p, const double* azel, int npix, double* xy, int* status)
 {
     if (!p || !azel || !xy || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lock(p->ctx->stage_mu);
     CK(cudaSetDevice(p->ctx->device));
     cudaStream_t s = p->ctx->stream;
     const size_t n = (size_t)npix * 4 * p->n_rays;
@@ -1447,6 +1451,7 @@ int solat_ff_map_panels_host(solat_ff_plan* p, const double* azel, int npix, con
 {
     if (!p || !azel || !pan_idx1 || !pan_idx2 || !pan1 || !pan2 || !amp || !phase || npix <= 0 || np1 <= 0 || np2 <= 0)
         return fail(SOLAT_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lock(p->ctx->stage_mu);
     CK(cudaSetDevice(p->ctx->device));
     cudaStream_t s = p->ctx->stream;
     const size_t n = (size_t)npix, nr = n * p->n_rays;

@@ -61,3 +61,10 @@ if label == "math":
     big = rng.uniform(2.8e8, 3.0e8, 20000)
     o = _lib.selftest_math(big)
     print("  cis_large max abs err cos %.2e sin %.2e" % (np.max(np.abs(o[6] - np.cos(big))), np.max(np.abs(o[7] - np.sin(big)))))
+if label == "overhead":
+    # per-pixel fixed cost of the far-field kernel: the same 1681 pixels with fans of 2x2 ... 100x100 rays
+    for n in (2, 10, 30, 50, 70, 100):
+        t, p_ = maps.ff_fan(n)
+        pl = maps.FarFieldPlan(tg, t, p_, x, y, e, device=0)
+        med, mn = timed(lambda: pl.run_device(d_fp, d_fa, d_fph, stream))
+        print("  fan %3d x %3d: %.3f ms (min %.3f)" % (n, n, med, mn))
