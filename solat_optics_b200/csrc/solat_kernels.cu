@@ -597,11 +597,14 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     int* wq = queues + warp * FF_WQ;
     const double cx = fr->centre[0], cz = fr->centre[2];
     int st = 0, cnt = 0;                                   // cnt: queue fill, identical in all lanes of the warp
-    int chunk = warp;
+    // Both walks run from the LAST ray of the fan down to the first: the later ray wins a cell (ffl:28), so the rays
+    // met first are the likely winners and the crowded cells (every ray beyond the low edge of the E_rec grid piles
+    // into row / column 0, ffl:22-23) settle at once -- the later, smaller ray indices only read the cell and move on.
+    int chunk = (n_rays + 31) / 32 - 1 - warp;
     // interval walk: warps draw chunks of 32 consecutive accepted rays of the pixel's dense list from a shared counter
     // (only the pixel's last chunk is partial, and the warps reach the end-of-pixel barrier together)
     const int n_acc = queue_walk ? 0 : row_pre[q.ang.nph];
-    int row = 0;
+    int row = max(q.ang.nph - 1, 0);
     for (;;) {
         int r0 = -1;
         if (!queue_walk) {
@@ -609,13 +612,13 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             if (lane == 0) c = atomicAdd(&s_next_chunk, 1);
             c = __shfl_sync(0xffffffffu, c, 0);
             if (c * 32 >= n_acc) break;
-            const int v = c * 32 + lane;
-            if (v < n_acc) {
-                while (row_pre[row + 1] <= v) ++row;      // chunks only grow, so the row cursor only moves forward
+            const int v = n_acc - 1 - (c * 32 + lane);
+            if (v >= 0) {
+                while (row_pre[row] > v) --row;           // chunks only move down the list, so does the row cursor
                 r0 = row * nth + row_lo[row] + (v - row_pre[row]);
             }
         } else {
-            const bool more = chunk * 32 < n_rays;
+            const bool more = chunk >= 0;
             if (cnt < 32 && more) {
                 // fill: aperture test (saf:359-379) on 32 candidate rays
                 const int r = chunk * 32 + lane;
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
                 if (ok) wq[cnt + __popc(m & ((1u << lane) - 1u))] = r;
                 cnt += __popc(m);
-                chunk += FF_WARPS;
+                chunk -= FF_WARPS;
                 __syncwarp();
                 continue;
             }
@@ -669,7 +672,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             st |= rst;
             if (opl != 0.0 && !not_finite(opl)) {                                   // ffl:10
                 const int cell = ff_cell(fx - cx, fz - cz, grid);
-                if (cell >= 0) {
+                if (cell >= 0 && (win[cell] >> FF_KEY_SHIFT) < (unsigned long long)(r0 + 1)) {   // a later ray holds the cell already?
                     bool exact;
                     const unsigned long long key = ff_key(r0, opl, q.key_base, q.key_inv_unit, exact, q.key_unit);
                     if (!exact) st |= ST_RANGE;
