@@ -495,6 +495,7 @@ struct FfMapParams {
     double* phase;
     int* status;
     int rows;                // host: theta is strictly monotone inside one branch of tan -> interval walk allowed
+    int prefilter;           // interval walk: drop rays the focal-position predictor puts far beyond the E_rec grid
     // panel models (ff_map_kernel<true> only): per (pixel, ray) column of pan1 / pan2, -1 = the ray sits on no panel
     const short *pidx1, *pidx2;
     const double *pan1, *pan2;   // (10, np) row-major [row, col, a, b, c, d, e, f, x0, y0]  (saf:667-674)
@@ -540,6 +541,9 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     int* row_lo = reinterpret_cast<int*>(s_gy + q.grid.M);                 // [nph] first accepted theta index of a row
     int* row_pre = row_lo + (q.rows ? q.ang.nph : 0);                      // [nph + 1] accepted rays before the row
     __shared__ int s_queue_walk, s_next_chunk;
+    __shared__ FfPred s_pred;
+    __shared__ double s_psum[2][12];
+    __shared__ float s_pres[2];
     __shared__ double s_t2e[9];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
@@ -549,6 +553,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
         ff_build_frames(K_COEF, g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
         s_queue_walk = !q.rows;
         s_next_chunk = 0;
+        s_pred.on = 0;
         if (PANEL) {
             for (int i = 0; i < 9; i++) s_t2e[i] = fr->t2.a[i];
             if (g.src[2] != 0) for (int i = 0; i < 3; i++) s_t2e[3 * i + 2] /= cos(atan(1.0 / 3.0));   // saf:828-829
@@ -591,6 +596,57 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             if (lane == 0) row_pre[0] = 0;
         }
         __syncthreads();
+        // focal-position predictor of this pixel (see FfPred): sample rays spread over the dense accepted list
+        const int n_list = row_pre[q.ang.nph];
+        if (q.prefilter && !s_queue_walk && n_list >= 512) {
+            float su = 0.0f, sv = 0.0f;
+            double sX = 0.0, sZ = 0.0;
+            if (tid < FF_PRED_SAMPLES) {
+                const int v = (int)((long long)tid * (n_list - 1) / (FF_PRED_SAMPLES - 1));
+                int a = 0, b = q.ang.nph - 1;              // last row with row_pre[row] <= v
+                while (a < b) {
+                    const int m = (a + b + 1) >> 1;
+                    if (row_pre[m] <= v) a = m; else b = m - 1;
+                }
+                const int i = row_lo[a] + (v - row_pre[a]);
+                const vec3 d = launch_dir(__ldg(q.ang.st + i), __ldg(q.ang.ct + i), __ldg(q.ang.sp + a), __ldg(q.ang.cp + a));
+                vec3 Pa;
+                double t_ap, opl, fx, fz;
+                int rst;
+                ff_aperture(sC, g, *fr, d, t_ap, Pa);
+                ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);
+                const float sf = __ldg(q.ang.stf + i) * FF_PRED_SCALE;
+                su = sf * __ldg(q.ang.cpf + a); sv = sf * __ldg(q.ang.spf + a);
+                sX = fx - fr->centre[0]; sZ = fz - fr->centre[2];
+                const double u = su, w = sv;
+                double S[12] = {1.0, u, w, u * u, u * w, w * w, sX, u * sX, w * sX, sZ, u * sZ, w * sZ};
+#pragma unroll
+                for (int k = 0; k < 12; k++) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) S[k] += __shfl_down_sync(0xffffffffu, S[k], o);
+                    if (lane == 0) s_psum[warp][k] = S[k];
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double S[12];
+                for (int k = 0; k < 12; k++) S[k] = s_psum[0][k] + s_psum[1][k];
+                ff_pred_solve(S, s_pred);
+            }
+            __syncthreads();
+            if (tid < FF_PRED_SAMPLES) {
+                float x, z;
+                ff_pred_eval(s_pred, su, sv, x, z);
+                float e = fmaxf(fabsf(x - (float)sX), fabsf(z - (float)sZ));
+                if (!(e == e)) e = 1e30f;                   // a sample that is not finite switches the predictor off
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) e = fmaxf(e, __shfl_down_sync(0xffffffffu, e, o));
+                if (lane == 0) s_pres[warp] = e;
+            }
+            __syncthreads();
+            if (tid == 0) ff_pred_set_margin(s_pred, fmaxf(s_pres[0], s_pres[1]));
+            __syncthreads();
+        }
     }
     const bool queue_walk = PANEL || s_queue_walk != 0;
 
@@ -605,17 +661,51 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     // (only the pixel's last chunk is partial, and the warps reach the end-of-pixel barrier together)
     const int n_acc = queue_walk ? 0 : row_pre[q.ang.nph];
     int row = max(q.ang.nph - 1, 0);
+    bool drained = false, prefilter = !queue_walk && s_pred.on != 0;
+    int seen = 0, kept = 0;
     for (;;) {
         int r0 = -1;
         if (!queue_walk) {
-            int c = 0;
-            if (lane == 0) c = atomicAdd(&s_next_chunk, 1);
-            c = __shfl_sync(0xffffffffu, c, 0);
-            if (c * 32 >= n_acc) break;
-            const int v = n_acc - 1 - (c * 32 + lane);
-            if (v >= 0) {
-                while (row_pre[row] > v) --row;           // chunks only move down the list, so does the row cursor
-                r0 = row * nth + row_lo[row] + (v - row_pre[row]);
+            if (cnt < 32 && !drained) {
+                int c = 0;
+                if (lane == 0) c = atomicAdd(&s_next_chunk, 1);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c * 32 >= n_acc) { drained = true; continue; }
+                const int v = n_acc - 1 - (c * 32 + lane);
+                int r = -1, i = 0;
+                if (v >= 0) {
+                    while (row_pre[row] > v) --row;       // chunks only move down the list, so does the row cursor
+                    i = row_lo[row] + (v - row_pre[row]);
+                    r = row * nth + i;
+                }
+                if (!prefilter && cnt == 0) {
+                    r0 = r;                               // straight to the trace
+                } else {
+                    // rays the predictor puts far beyond the high edge of the E_rec grid are dropped here (ffl:19 would
+                    // skip them after the trace); the others queue up so that the FP64 trace runs with full warps
+                    bool keep = r >= 0;
+                    if (prefilter && keep) {
+                        const float sf = __ldg(q.ang.stf + i) * FF_PRED_SCALE;
+                        keep = !ff_pred_miss(s_pred, sf * __ldg(q.ang.cpf + row), sf * __ldg(q.ang.spf + row), (float)grid.gx_max,
+                                             (float)grid.gy_max);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (keep) wq[cnt + __popc(m & ((1u << lane) - 1u))] = r;
+                    cnt += __popc(m);
+                    if (prefilter) {                      // a grid that catches (nearly) every ray: stop predicting
+                        seen += min(32, n_acc - c * 32);
+                        kept += __popc(m);
+                        if (seen >= 128 && kept * 8 > seen * 7) prefilter = false;
+                    }
+                    __syncwarp();
+                    continue;
+                }
+            } else {
+                if (cnt == 0) break;
+                const int n_take = min(cnt, 32);
+                r0 = lane < n_take ? wq[cnt - 1 - lane] : -1;
+                cnt -= n_take;
+                __syncwarp();
             }
         } else {
             const bool more = chunk >= 0;
@@ -1291,7 +1381,7 @@ struct solat_ff_plan {
     DevBuf<double> pan, xy;                 // panel models; mirror coordinates for identify_panel
     FfGrid grid;
     double k, key_base, key_unit;
-    int M, n_rays, rows, shape;
+    int M, n_rays, rows, shape, prefilter;
     size_t smem;
 };
 
@@ -1326,7 +1416,7 @@ static int ff_map_launch(solat_ff_plan* p, const double* d_azel, int npix, doubl
     FfMapParams q;
     q.ang = p->ang.tabs; q.g = p->g; q.azel = d_azel; q.grid = p->grid; q.e_rec = p->e_rec.p;
     q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
-    q.amp = d_amp; q.phase = d_phase; q.status = p->status.p; q.rows = p->rows;
+    q.amp = d_amp; q.phase = d_phase; q.status = p->status.p; q.rows = p->rows; q.prefilter = p->prefilter;
     q.pidx1 = q.pidx2 = nullptr; q.pan1 = q.pan2 = nullptr; q.np1 = q.np2 = 0;
     ff_map_dispatch<false>(p->shape, q, npix, p->smem, s);
     LAUNCHED();
@@ -1351,11 +1441,11 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
         if (pass == 1) rows = 0;
         int best_warps = 0;
         for (int k = 0; k < FF_NSHAPES; k++) {
-            const size_t need = ff_map_smem(M, rows ? nph : 0, FF_SHAPES[k][0]) + 4400;     // + static shared memory
+            const size_t need = ff_map_smem(M, rows ? nph : 0, FF_SHAPES[k][0]) + 4608;     // + static shared memory
             if (need > cta_max) continue;
             const int ctas = (int)std::min<size_t>((size_t)FF_SHAPES[k][1], sm_smem / (need + 1024));   // 1 KB reserved per CTA
             const int warps = ctas * FF_SHAPES[k][0] / 32;
-            if (warps > best_warps) { best_warps = warps; shape = k; smem = need - 4400; }
+            if (warps > best_warps) { best_warps = warps; shape = k; smem = need - 4608; }
         }
     }
     if (shape < 0) return fail(SOLAT_ERR_ARG, "E_rec grid too large for the shared-memory winner table (M <= 168)");
@@ -1365,6 +1455,10 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
     if (int rc = ff_map_set_smem(shape, smem)) return rc;
     solat_ff_plan* p = new solat_ff_plan();
     p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem; p->n_rays = nth * nph; p->rows = rows; p->shape = shape;
+    {
+        const char* env = getenv("SOLAT_FF_PREFILTER");   // "0": trace every accepted ray (experiments, strict status)
+        p->prefilter = !(env && env[0] == '0');
+    }
     // fixed-point frame of the winner keys: every path length of this telescope lies within a few tens of metres
     // of |source - rotation centre| + 2.2e4 mm; unit = half an ulp of that, so the offsets are exact integers
     {
@@ -1472,7 +1566,7 @@ int solat_ff_map_panels_host(solat_ff_plan* p, const double* azel, int npix, con
     FfMapParams q;
     q.ang = p->ang.tabs; q.g = p->g; q.azel = p->ctx->stage_in.p; q.grid = p->grid; q.e_rec = p->e_rec.p;
     q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
-    q.amp = p->ctx->stage_out.p; q.phase = p->ctx->stage_out.p + n; q.status = p->status.p; q.rows = 0;
+    q.amp = p->ctx->stage_out.p; q.phase = p->ctx->stage_out.p + n; q.status = p->status.p; q.rows = 0; q.prefilter = 0;
     q.pidx1 = p->pidx.p; q.pidx2 = p->pidx.p + nr; q.pan1 = p->pan.p; q.pan2 = p->pan.p + 10 * (size_t)np1; q.np1 = np1; q.np2 = np2;
     ff_map_dispatch<true>(p->shape, q, npix, p->smem, s);
     LAUNCHED();

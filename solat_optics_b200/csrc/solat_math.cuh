@@ -925,6 +925,56 @@ SOLAT_HD void ff_ray_lean(const Coef& C, const FfFrames& f, const vec3t<R>& d, R
     status = st;
 }
 
+// Where on the focal plane will a ray land?  For one pixel the focal-plane position is, to a few mm over the whole
+// aperture, an affine function of the ray's launch direction cosines (the beam is a defocused image of the aperture;
+// the rest is aberration).  The fused map fits that affine map per pixel to a sample of exactly traced rays, measures
+// its worst error on the sample, and uses it ONLY to drop rays that the reference's projection would skip anyway
+// (ffl:19: x > max(data_x[0, :]) or y > max(data_y[:, 0])) when they miss the high edge of the E_rec grid by more
+// than 5 x that error + 2 mm; every other ray is traced in FP64 and binned exactly.  With the +-5 cm grid of
+// ff_sim.py about half of the accepted rays land beyond the grid.
+constexpr float FF_PRED_SCALE = 2.0e4f;   // launch direction cosines of the fan are ~5e-5
+constexpr int FF_PRED_SAMPLES = 64;
+struct FfPred {
+    float cx[3], cz[3];    // x - centre.x = cx[0] + cx[1] u + cx[2] v  [mm], u = d.x * FF_PRED_SCALE, v = d.y * FF_PRED_SCALE
+    float margin_cm;       // (5 x worst sample error + 2 mm) / 10
+    int on;
+};
+// Least squares over the sample.  S = {n, Su, Sv, Suu, Suv, Svv, SX, SuX, SvX, SZ, SuZ, SvZ}
+SOLAT_HD void ff_pred_solve(const double* S, FfPred& p)
+{
+    const double a = S[0], b = S[1], c = S[2], d = S[3], e = S[4], f = S[5];
+    // inverse of the symmetric normal matrix [[a b c] [b d e] [c e f]] by cofactors
+    const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d, c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
+    const double det = a * c00 + b * c01 + c * c02;
+    p.on = det > 1e-9 * a * d * f && det == det;
+    const double id = p.on ? 1.0 / det : 0.0;
+    for (int k = 0; k < 2; k++) {
+        const double r0 = S[6 + 3 * k], r1 = S[7 + 3 * k], r2 = S[8 + 3 * k];
+        float* o = k ? p.cz : p.cx;
+        o[0] = (float)((c00 * r0 + c01 * r1 + c02 * r2) * id);
+        o[1] = (float)((c01 * r0 + c11 * r1 + c12 * r2) * id);
+        o[2] = (float)((c02 * r0 + c12 * r1 + c22 * r2) * id);
+    }
+    p.margin_cm = 0.0f;
+}
+SOLAT_HD void ff_pred_eval(const FfPred& p, float u, float v, float& x, float& z)
+{
+    x = fmaf(p.cx[1], u, fmaf(p.cx[2], v, p.cx[0]));
+    z = fmaf(p.cz[1], u, fmaf(p.cz[2], v, p.cz[0]));
+}
+// worst sample error [mm] -> margin; a sample that is not finite or an error above 5 cm switches the predictor off
+SOLAT_HD void ff_pred_set_margin(FfPred& p, float worst_mm)
+{
+    p.on = p.on && worst_mm < 50.0f;     // NaN compares false
+    p.margin_cm = 0.1f * (5.0f * worst_mm + 2.0f);
+}
+SOLAT_HD bool ff_pred_miss(const FfPred& p, float u, float v, float gx_max_cm, float gy_max_cm)
+{
+    float x, z;
+    ff_pred_eval(p, u, v, x, z);
+    return 0.1f * x > gx_max_cm + p.margin_cm || 0.1f * z > gy_max_cm + p.margin_cm;
+}
+
 // np.searchsorted(a, v, side='left') over a strided sorted array
 SOLAT_HD int searchsorted_left(const double* a, int n, int stride, double v)
 {

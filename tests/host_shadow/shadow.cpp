@@ -289,6 +289,75 @@ API int shadow_ff_row_intervals(const double* geo, const double* th, int nth, co
     return bad;
 }
 
+// The fused map's focal-position predictor, as the kernel builds it: FF_PRED_SAMPLES rays spread over the pixel's
+// dense list of accepted rays are traced exactly, the affine map is fitted and its worst sample error sets the
+// margin.  out4: worst predictor error over ALL accepted rays [mm], worst sample error [mm], rays the predictor
+// drops for a grid with high edges gx_max, gy_max [cm], rays it drops although the exact test (ffl:19) keeps them.
+API int shadow_ff_pred_check(const double* geo, const double* th, int nth, const double* ph, int nph, double el, double az,
+                             double gx_max, double gy_max, double* out4)
+{
+    FfGeom g = unpack(geo);
+    FfFrames f;
+    ff_build_frames(K_COEF, g, el, az, f);
+    std::vector<double> st(nth), ct(nth);
+    for (int i = 0; i < nth; i++) { st[i] = sin(th[i]); ct[i] = cos(th[i]); }
+    std::vector<int> rays;
+    for (int j = 0; j < nph; j++) {
+        int lo, hi;
+        ff_row_interval(K_COEF, g, f, st.data(), ct.data(), nth, sin(ph[j]), cos(ph[j]), lo, hi);
+        for (int i = lo; i < hi; i++) rays.push_back(j * nth + i);
+    }
+    const int n_acc = (int)rays.size();
+    auto trace = [&](int r, float& u, float& v, double& X, double& Z) {
+        const int i = r % nth, j = r / nth;
+        vec3 d = launch_dir(st[i], ct[i], sin(ph[j]), cos(ph[j])), Pa;
+        double t_ap, opl, fx, fz;
+        int rst;
+        ff_aperture(K_COEF, g, f, d, t_ap, Pa);
+        ff_ray_lean<double>(K_COEF, f, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);
+        u = (float)st[i] * (float)cos(ph[j]) * FF_PRED_SCALE; v = (float)st[i] * (float)sin(ph[j]) * FF_PRED_SCALE;
+        X = fx - f.centre[0]; Z = fz - f.centre[2];
+    };
+    FfPred p;
+    p.on = 0;
+    double worst_sample = 0.0;
+    if (n_acc >= 512) {
+        double S[12] = {0};
+        float us[FF_PRED_SAMPLES], vs[FF_PRED_SAMPLES];
+        double Xs[FF_PRED_SAMPLES], Zs[FF_PRED_SAMPLES];
+        for (int k = 0; k < FF_PRED_SAMPLES; k++) {
+            const int r = rays[(long)k * (n_acc - 1) / (FF_PRED_SAMPLES - 1)];
+            trace(r, us[k], vs[k], Xs[k], Zs[k]);
+            const double u = us[k], v = vs[k];
+            S[0] += 1; S[1] += u; S[2] += v; S[3] += u * u; S[4] += u * v; S[5] += v * v;
+            S[6] += Xs[k]; S[7] += u * Xs[k]; S[8] += v * Xs[k]; S[9] += Zs[k]; S[10] += u * Zs[k]; S[11] += v * Zs[k];
+        }
+        ff_pred_solve(S, p);
+        for (int k = 0; k < FF_PRED_SAMPLES; k++) {
+            float x, z;
+            ff_pred_eval(p, us[k], vs[k], x, z);
+            worst_sample = fmax(worst_sample, fmax(fabs(x - Xs[k]), fabs(z - Zs[k])));
+        }
+        ff_pred_set_margin(p, (float)worst_sample);
+    }
+    double worst = 0.0;
+    long dropped = 0, wrong = 0;
+    if (p.on)
+        for (int r : rays) {
+            float u, v, x, z;
+            double X, Z;
+            trace(r, u, v, X, Z);
+            ff_pred_eval(p, u, v, x, z);
+            worst = fmax(worst, fmax(fabs(x - X), fabs(z - Z)));
+            if (ff_pred_miss(p, u, v, (float)gx_max, (float)gy_max)) {
+                ++dropped;
+                if (!(div10(X) > gx_max || div10(Z) > gy_max)) ++wrong;
+            }
+        }
+    out4[0] = worst; out4[1] = worst_sample; out4[2] = (double)dropped; out4[3] = (double)wrong;
+    return p.on ? n_acc : -n_acc;
+}
+
 // one far-field pixel, zero-error single-panel model (fused-map semantics)
 API int shadow_ff_pixel(const double* geo, const double* th, int nth, const double* ph, int nph, double el, double az,
                         const double* gx_full, const double* gy, const double* e_rec, int M, double k, double* re_im,

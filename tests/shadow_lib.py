@@ -113,6 +113,16 @@ def ff_row_intervals(geo, th, ph, el, az):
     return bad, nf.value, lo_hi
 
 
+def ff_pred_check(geo, th, ph, el, az, gx_max, gy_max):
+    """-> (accepted rays (negative: predictor off), worst predictor error over all rays [mm], worst sample error [mm],
+    rays the predictor drops, wrongly dropped rays)"""
+    g, gp = D(geo); th, thp = D(th); ph, php = D(ph)
+    o = np.zeros(4)
+    nv = lib().shadow_ff_pred_check(gp, thp, ci(th.size), php, ci(ph.size), cd(el), cd(az), cd(gx_max), cd(gy_max),
+                                    o.ctypes.data_as(dp))
+    return nv, o[0], o[1], int(o[2]), int(o[3])
+
+
 def regrid(field, n_new):
     f, fp = D(field)
     out = np.zeros((n_new, n_new))

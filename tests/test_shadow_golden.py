@@ -225,3 +225,29 @@ def test_ff_row_intervals_equal_the_per_ray_aperture_test(shadow, oracle):
     # a fan that crosses the aperture plane's horizon asks for the per-ray walk
     _, fallback, _ = shadow.ff_row_intervals(geo, np.linspace(np.pi - 1.0, np.pi + 1.0, 9), phi[48:53], 1.2, 0.0)
     assert fallback > 0
+
+
+def test_ff_focal_predictor_is_conservative(shadow, oracle):
+    """The fused far-field map drops rays before the FP64 trace when an affine predictor of the focal-plane position
+    (fitted per pixel to 64 exactly traced rays) puts them beyond the high edge of the E_rec grid by more than
+    5 x its worst sample error + 2 mm.  A dropped ray must be one the exact comparison (ffl:19) skips: checked on
+    every accepted ray for on- and far-off-axis pixels, three focal offsets, small and large fans, four grid sizes."""
+    ratio = 0.0
+    for n in (100, 40, 317):
+        th, phi = gu.ff_fan(n)
+        for offset in (1.25, 1.32, 1.4):
+            geo = oracle.ff_geo_vec(rx_y_m=-offset)
+            for az, el in [(0.0, gu.EL0), (20 * gu.DE, gu.EL0 - 20 * gu.DE), (-30 * gu.DE, gu.EL0 + 30 * gu.DE), (3e-3, -2e-3), (0.02, 0.01)]:
+                for gmax in (5.0, 0.0, 20.0, 30.0) if n == 100 else (5.0,):
+                    nv, worst, worst_sample, dropped, wrong = shadow.ff_pred_check(geo, th, phi, el, az, gmax, gmax)
+                    assert nv > 0 and wrong == 0
+                    assert worst < 5.0 * worst_sample + 2.0                    # the margin really covers every ray
+                    ratio = max(ratio, worst / worst_sample)
+                    if gmax == 5.0 and abs(az) < 1e-3 and n >= 100:
+                        assert dropped > 0.3 * nv      # the +-5 cm grid of ff_sim.py: about half of the rays miss it
+                    if gmax == 30.0 and abs(az) < 1e-3:
+                        assert dropped == 0
+    assert ratio < 2.0, ratio          # worst error anywhere stays within 2x the sampled one (margin is 5x + 2 mm)
+    # tiny fans: predictor off
+    th, phi = gu.ff_fan(12)
+    assert shadow.ff_pred_check(oracle.ff_geo_vec(rx_y_m=-1.32), th, phi, gu.EL0, 0.0, 5.0, 5.0)[0] < 0
