@@ -511,6 +511,24 @@ __device__ __forceinline__ PanelErr load_panel(const double* pan, int np, int co
     return e;
 }
 
+// In place: row_pre[j + 1] = count of row j  ->  row_pre[j] = rays before row j (row_pre[nph] = total).  One warp.
+__device__ __forceinline__ void ff_prefix_rows(int* row_pre, int nph, int lane)
+{
+    int carry = 0;
+    for (int base = 0; base < nph; base += 32) {
+        const int j = base + lane;
+        int v = j < nph ? row_pre[j + 1] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        if (j < nph) row_pre[j + 1] = carry + v;
+        carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+    if (lane == 0) row_pre[0] = 0;
+}
+
 // One CTA per (az, el) pixel, warps fully autonomous inside the ray loop (no CTA barrier).
 //   * Which rays pass the aperture (saf:378, 60 % of the default fan):
 //     - interval walk (theta monotone, the reference's linspace fans): the rays of one phi row hit the aperture
@@ -540,7 +558,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     double* s_gy = s_gx + q.grid.M;                                        // [M] data_y[:, 0] when all columns agree
     int* row_lo = reinterpret_cast<int*>(s_gy + q.grid.M);                 // [nph] first accepted theta index of a row
     int* row_pre = row_lo + (q.rows ? q.ang.nph : 0);                      // [nph + 1] accepted rays before the row
-    __shared__ int s_queue_walk, s_next_chunk;
+    __shared__ int s_queue_walk;
     __shared__ FfPred s_pred;
     __shared__ double s_psum[2][12];
     __shared__ float s_pres[2];
@@ -552,7 +570,6 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     if (tid == 0) {
         ff_build_frames(K_COEF, g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
         s_queue_walk = !q.rows;
-        s_next_chunk = 0;
         s_pred.on = 0;
         if (PANEL) {
             for (int i = 0; i < 9; i++) s_t2e[i] = fr->t2.a[i];
@@ -580,21 +597,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             row_pre[j + 1] = hi - lo;
         }
         __syncthreads();
-        if (warp == 0) {                                         // exclusive prefix sum of the row counts
-            int carry = 0;
-            for (int base = 0; base < q.ang.nph; base += 32) {
-                const int j = base + lane;
-                int v = j < q.ang.nph ? row_pre[j + 1] : 0;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(0xffffffffu, v, o);
-                    if (lane >= o) v += u;
-                }
-                if (j < q.ang.nph) row_pre[j + 1] = carry + v;
-                carry += __shfl_sync(0xffffffffu, v, 31);
-            }
-            if (lane == 0) row_pre[0] = 0;
-        }
+        if (warp == 0) ff_prefix_rows(row_pre, q.ang.nph, lane);
         __syncthreads();
         // focal-position predictor of this pixel (see FfPred): sample rays spread over the dense accepted list
         const int n_list = row_pre[q.ang.nph];
@@ -646,6 +649,24 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             __syncthreads();
             if (tid == 0) ff_pred_set_margin(s_pred, fmaxf(s_pres[0], s_pres[1]));
             __syncthreads();
+            if (s_pred.on) {
+                // keep only the rays the predictor cannot rule out: per row again one interval
+                // (batches from the last row down: a batch replaces entries (j0, j0 + FF_T] and the next one reads [.., j0])
+                for (int j0 = ((q.ang.nph - 1) / FF_T) * FF_T; j0 >= 0; j0 -= FF_T) {
+                    const int j = j0 + tid;
+                    int lo = 0, hi = 0;
+                    if (j < q.ang.nph) {
+                        lo = row_lo[j]; hi = lo + (row_pre[j + 1] - row_pre[j]);
+                        ff_pred_shrink(s_pred, q.ang.stf, __ldg(q.ang.cpf + j), __ldg(q.ang.spf + j), (float)grid.gx_max,
+                                       (float)grid.gy_max, lo, hi);
+                    }
+                    __syncthreads();                         // every count of this batch was read before any is replaced
+                    if (j < q.ang.nph) { row_lo[j] = lo; row_pre[j + 1] = hi - lo; }
+                }
+                __syncthreads();
+                if (warp == 0) ff_prefix_rows(row_pre, q.ang.nph, lane);
+                __syncthreads();
+            }
         }
     }
     const bool queue_walk = PANEL || s_queue_walk != 0;
@@ -657,56 +678,31 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     // met first are the likely winners and the crowded cells (every ray beyond the low edge of the E_rec grid piles
     // into row / column 0, ffl:22-23) settle at once -- the later, smaller ray indices only read the cell and move on.
     int chunk = (n_rays + 31) / 32 - 1 - warp;
-    // interval walk: warps draw chunks of 32 consecutive accepted rays of the pixel's dense list from a shared counter
-    // (only the pixel's last chunk is partial, and the warps reach the end-of-pixel barrier together)
+    // interval walk: every warp owns a contiguous share of the pixel's dense list of rays to trace, 32 per step
     const int n_acc = queue_walk ? 0 : row_pre[q.ang.nph];
     int row = max(q.ang.nph - 1, 0);
-    bool drained = false, prefilter = !queue_walk && s_pred.on != 0;
-    int seen = 0, kept = 0;
+    // warp w owns rays [v_bot, v_top] of the list
+    const int per_warp = (n_acc + FF_WARPS - 1) / FF_WARPS;
+    const int v_bot = min(warp * per_warp, n_acc);
+    int v_top = min(v_bot + per_warp, n_acc) - 1;
+    if (!queue_walk && v_top >= v_bot) {                  // row of the warp's first ray: last row with row_pre[row] <= v_top
+        int a = 0, b = q.ang.nph - 1;
+        while (a < b) {
+            const int m = (a + b + 1) >> 1;
+            if (row_pre[m] <= v_top) a = m; else b = m - 1;
+        }
+        row = a;
+    }
     for (;;) {
         int r0 = -1;
         if (!queue_walk) {
-            if (cnt < 32 && !drained) {
-                int c = 0;
-                if (lane == 0) c = atomicAdd(&s_next_chunk, 1);
-                c = __shfl_sync(0xffffffffu, c, 0);
-                if (c * 32 >= n_acc) { drained = true; continue; }
-                const int v = n_acc - 1 - (c * 32 + lane);
-                int r = -1, i = 0;
-                if (v >= 0) {
-                    while (row_pre[row] > v) --row;       // chunks only move down the list, so does the row cursor
-                    i = row_lo[row] + (v - row_pre[row]);
-                    r = row * nth + i;
-                }
-                if (!prefilter && cnt == 0) {
-                    r0 = r;                               // straight to the trace
-                } else {
-                    // rays the predictor puts far beyond the high edge of the E_rec grid are dropped here (ffl:19 would
-                    // skip them after the trace); the others queue up so that the FP64 trace runs with full warps
-                    bool keep = r >= 0;
-                    if (prefilter && keep) {
-                        const float sf = __ldg(q.ang.stf + i) * FF_PRED_SCALE;
-                        keep = !ff_pred_miss(s_pred, sf * __ldg(q.ang.cpf + row), sf * __ldg(q.ang.spf + row), (float)grid.gx_max,
-                                             (float)grid.gy_max);
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, keep);
-                    if (keep) wq[cnt + __popc(m & ((1u << lane) - 1u))] = r;
-                    cnt += __popc(m);
-                    if (prefilter) {                      // a grid that catches (nearly) every ray: stop predicting
-                        seen += min(32, n_acc - c * 32);
-                        kept += __popc(m);
-                        if (seen >= 128 && kept * 8 > seen * 7) prefilter = false;
-                    }
-                    __syncwarp();
-                    continue;
-                }
-            } else {
-                if (cnt == 0) break;
-                const int n_take = min(cnt, 32);
-                r0 = lane < n_take ? wq[cnt - 1 - lane] : -1;
-                cnt -= n_take;
-                __syncwarp();
+            if (v_top < v_bot) break;
+            const int v = v_top - lane;
+            if (v >= v_bot) {
+                while (row_pre[row] > v) --row;           // the walk only moves down the list, so does the row cursor
+                r0 = row * nth + row_lo[row] + (v - row_pre[row]);
             }
+            v_top -= 32;
         } else {
             const bool more = chunk >= 0;
             if (cnt < 32 && more) {

@@ -968,11 +968,26 @@ SOLAT_HD void ff_pred_set_margin(FfPred& p, float worst_mm)
     p.on = p.on && worst_mm < 50.0f;     // NaN compares false
     p.margin_cm = 0.1f * (5.0f * worst_mm + 2.0f);
 }
-SOLAT_HD bool ff_pred_miss(const FfPred& p, float u, float v, float gx_max_cm, float gy_max_cm)
+// Rays of one phi row [lo, hi) the predictor keeps.  Along a row u and v are the row constants cos(phi), sin(phi)
+// times sin(theta_i), so the predicted x and z are monotone in i (sin(theta) is monotone on the fans the interval
+// walk accepts, and so are its single-precision table, the product and the FMA): the rays beyond one edge of the
+// grid are a prefix or a suffix of the row and the kept rays are again ONE interval, found by bisection.
+SOLAT_HD void ff_pred_shrink(const FfPred& p, const float* stf, float cpf, float spf, float gx_max_cm, float gy_max_cm, int& lo, int& hi)
 {
-    float x, z;
-    ff_pred_eval(p, u, v, x, z);
-    return 0.1f * x > gx_max_cm + p.margin_cm || 0.1f * z > gy_max_cm + p.margin_cm;
+    for (int k = 0; k < 2 && lo < hi; k++) {
+        const float* c = k ? p.cz : p.cx;
+        const float slope = fmaf(c[1], cpf, c[2] * spf), c0 = c[0], edge = (k ? gy_max_cm : gx_max_cm) + p.margin_cm;
+        auto miss = [&](int i) { return 0.1f * fmaf(stf[i] * FF_PRED_SCALE, slope, c0) > edge; };
+        const bool m_lo = miss(lo), m_hi = miss(hi - 1);
+        if (m_lo && m_hi) { hi = lo; return; }
+        if (!m_lo && !m_hi) continue;
+        int a = lo, b = hi - 1;                 // miss(a) != miss(b): bisect for the crossing
+        while (a + 1 < b) {
+            const int m = (a + b) >> 1;
+            if (miss(m) == m_lo) a = m; else b = m;
+        }
+        if (m_lo) lo = b; else hi = b;
+    }
 }
 
 // np.searchsorted(a, v, side='left') over a strided sorted array

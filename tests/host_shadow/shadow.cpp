@@ -342,18 +342,29 @@ API int shadow_ff_pred_check(const double* geo, const double* th, int nth, const
     }
     double worst = 0.0;
     long dropped = 0, wrong = 0;
-    if (p.on)
-        for (int r : rays) {
-            float u, v, x, z;
-            double X, Z;
-            trace(r, u, v, X, Z);
-            ff_pred_eval(p, u, v, x, z);
-            worst = fmax(worst, fmax(fabs(x - X), fabs(z - Z)));
-            if (ff_pred_miss(p, u, v, (float)gx_max, (float)gy_max)) {
-                ++dropped;
-                if (!(div10(X) > gx_max || div10(Z) > gy_max)) ++wrong;
+    if (p.on) {
+        std::vector<float> stf(nth);
+        for (int i = 0; i < nth; i++) stf[i] = (float)st[i];
+        size_t at = 0;
+        for (int j = 0; j < nph; j++) {
+            int lo, hi;
+            ff_row_interval(K_COEF, g, f, st.data(), ct.data(), nth, sin(ph[j]), cos(ph[j]), lo, hi);
+            int klo = lo, khi = hi;
+            ff_pred_shrink(p, stf.data(), (float)cos(ph[j]), (float)sin(ph[j]), (float)gx_max, (float)gy_max, klo, khi);
+            if (klo < lo || khi > hi || klo > khi) return 0;          // must stay inside the accepted interval
+            for (int i = lo; i < hi; i++, at++) {
+                float u, v, x, z;
+                double X, Z;
+                trace(j * nth + i, u, v, X, Z);
+                ff_pred_eval(p, u, v, x, z);
+                worst = fmax(worst, fmax(fabs(x - X), fabs(z - Z)));
+                if (i < klo || i >= khi) {
+                    ++dropped;
+                    if (!(div10(X) > gx_max || div10(Z) > gy_max)) ++wrong;
+                }
             }
         }
+    }
     out4[0] = worst; out4[1] = worst_sample; out4[2] = (double)dropped; out4[3] = (double)wrong;
     return p.on ? n_acc : -n_acc;
 }
