@@ -27,7 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-NCU_DRAM_BYTES_PER_LAUNCH = 151808 + 6400   # ff_map_kernel, r1f capture (read + write)
+NCU_DRAM_BYTES_PER_LAUNCH = 173568 + 6400   # ff_map_kernel, r1i capture (read + write)
+NCU_EXECUTED_FP64_FLOP_PER_LAUNCH = 2 * 1373304599 + 414808890 + 203512374   # DFMA x2 + DMUL + DADD thread instructions, r1i
 METRIC = "scan_pixel_rays_per_s"
 UNIT = "pixel*rays/s"
 FREQ, RES_ARCMIN, NUM, OFFSET, N_SCAN = 140, 0.25, 20, 1.32, 100
@@ -275,12 +276,21 @@ def run_ours(args):
             "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of ff_map_kernel, bytes per launch, ncu --set full "
-                                           "capture profiles/r01f_raw_metrics.csv (algorithmic: 27 kB pixel list + 27 kB results + "
+                                           "capture profiles/r01i_raw_metrics.csv (algorithmic: 27 kB pixel list + 27 kB results + "
                                            "~45 kB E_rec and angle tables); the kernel is compute bound",
                          "peak_source": "burst DFMA issue-rate probe run in this process (best of 5 x 2 ms launches; MEASURED_PEAKS.json "
                                         "has no FP64 figure); nominal %.1f = 148 SM x 64 lanes x 2 x 1.965 GHz" % NOMINAL_FP64_TFLOPS,
                          "frac_of_nominal": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None,
-                         "flop_per_unit": FLOP_PER_LAUNCHED_RAY, "units_per_launch": npix * N_SCAN ** 2, "kernel": kernel_note},
+                         "flop_per_unit": FLOP_PER_LAUNCHED_RAY, "units_per_launch": npix * N_SCAN ** 2, "kernel": kernel_note,
+                         "executed_tflops": NCU_EXECUTED_FP64_FLOP_PER_LAUNCH / (kernel_ms * 1e-3) / 1e12,
+                         "executed_frac": NCU_EXECUTED_FP64_FLOP_PER_LAUNCH / (kernel_ms * 1e-3) / 1e12 / peak,
+                         "fp64_pipe_pct_ncu": 44.1,
+                         "note": "achieved/frac follow the contract: SURVEY 8d's reference-shaped model (626 FLOP per launched ray: the "
+                                 "reference traces every accepted ray) over the measured time.  The kernel executes far fewer FP64 "
+                                 "operations (mixed-precision Newton, mirror-local frames, and about half of the accepted rays are "
+                                 "culled before the trace because the reference's projection would skip them), so frac can exceed "
+                                 "1; executed_* = ncu thread-level DFMA/DMUL/DADD counts of profiles/r01i_op_counts.csv over the "
+                                 "same measured time, fp64_pipe_pct_ncu = sm__inst_executed_pipe_fp64 of that capture"},
             "ray_status": int(status),
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -495,7 +495,8 @@ struct FfMapParams {
     double* phase;
     int* status;
     int rows;                // host: theta is strictly monotone inside one branch of tan -> interval walk allowed
-    int prefilter;           // interval walk: drop rays the focal-position predictor puts far beyond the E_rec grid
+    const unsigned char* rec;   // per-pixel records of ff_prep_kernel
+    size_t rec_stride;
     // panel models (ff_map_kernel<true> only): per (pixel, ray) column of pan1 / pan2, -1 = the ray sits on no panel
     const short *pidx1, *pidx2;
     const double *pan1, *pan2;   // (10, np) row-major [row, col, a, b, c, d, e, f, x0, y0]  (saf:667-674)
@@ -545,49 +546,48 @@ __device__ __forceinline__ void ff_prefix_rows(int* row_pre, int nph, int lane)
 //   * PANEL (adjuster-error studies, ff_sim.py:61-70 with non-zero offsets): every ray carries the panel-model
 //     columns the host derived with pan_mod.identify_panel; rays on no panel are dropped (saf:626-628,805-809), the
 //     others see their panels' error polynomials inside both Newton solves.  Always the queue walk.
-template <bool PANEL, int T, int MINB>
-__global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
+// Per-pixel set-up of the fused map, one small CTA per pixel, all pixels of a launch in flight at once (the set-up is
+// latency bound: one thread builds the frames, one thread per phi row finds its interval): frames, and for the
+// interval walk the per-row ray intervals already shrunk by the focal-position predictor, as a record in global
+// memory the map kernel copies into its shared memory.  Record: FfFrames | int queue_walk, n_list, pad[2] |
+// row_lo[nph] | row_pre[nph + 1].
+constexpr int FF_PREP_T = 128;
+constexpr size_t FF_REC_FRAMES = ((sizeof(FfFrames) + 15) / 16) * 16;
+constexpr size_t FF_REC_HEAD = FF_REC_FRAMES + 16;
+struct FfPrepParams {
+    AngleTabs ang;
+    solat_ff_geom g;
+    const double* azel;
+    int rows, prefilter;
+    float gx_max, gy_max;
+    unsigned char* rec;
+    size_t stride;
+};
+static size_t ff_rec_stride(int rows_nph) { return FF_REC_HEAD + (rows_nph ? ((2 * (size_t)rows_nph + 1) * sizeof(int) + 15) / 16 * 16 : 0); }
+
+__global__ void __launch_bounds__(FF_PREP_T) ff_prep_kernel(FfPrepParams q)
 {
-    constexpr int FF_T = T, FF_WARPS = T / 32;
+    constexpr int FF_T = FF_PREP_T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int cells = q.grid.M * q.grid.M;
     FfFrames* fr = reinterpret_cast<FfFrames*>(smem_raw);
-    unsigned long long* win = reinterpret_cast<unsigned long long*>(smem_raw + ((sizeof(FfFrames) + 15) / 16) * 16);
-    int* queues = reinterpret_cast<int*>(win + cells);          // [FF_WARPS][FF_WQ]
-    double* s_gx = reinterpret_cast<double*>(queues + FF_WARPS * FF_WQ);   // [M] data_x[0, :]
-    double* s_gy = s_gx + q.grid.M;                                        // [M] data_y[:, 0] when all columns agree
-    int* row_lo = reinterpret_cast<int*>(s_gy + q.grid.M);                 // [nph] first accepted theta index of a row
-    int* row_pre = row_lo + (q.rows ? q.ang.nph : 0);                      // [nph + 1] accepted rays before the row
+    int* row_lo = reinterpret_cast<int*>(smem_raw + FF_REC_FRAMES);        // [nph] first ray of a row
+    int* row_pre = row_lo + (q.rows ? q.ang.nph : 0);                      // [nph + 1] rays before the row
     __shared__ int s_queue_walk;
     __shared__ FfPred s_pred;
     __shared__ double s_psum[2][12];
     __shared__ float s_pres[2];
-    __shared__ double s_t2e[9];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
     const FfGeom g = to_geom(q.g);
-    const Coef& sC = K_COEF;   // constant bank; a shared-memory copy measured 4 % slower (profiles/r01_variants.md)
+    const Coef& sC = K_COEF;
     if (tid == 0) {
         ff_build_frames(K_COEF, g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
         s_queue_walk = !q.rows;
         s_pred.on = 0;
-        if (PANEL) {
-            for (int i = 0; i < 9; i++) s_t2e[i] = fr->t2.a[i];
-            if (g.src[2] != 0) for (int i = 0; i < 3; i++) s_t2e[3 * i + 2] /= cos(atan(1.0 / 3.0));   // saf:828-829
-        }
     }
-    for (int c = tid; c < cells; c += FF_T) win[c] = 0ull;
-    FfGrid grid = q.grid;                                   // grid axes on chip: the binning does 2-4 dependent reads per ray
-    for (int i = tid; i < grid.M; i += FF_T) {
-        s_gx[i] = __ldg(q.grid.gx + i);
-        if (grid.y_uniform) s_gy[i] = __ldg(q.grid.gy + (size_t)i * grid.M);
-    }
-    grid.gx = s_gx;
-    if (grid.y_uniform) { grid.gy = s_gy; grid.gy_cs = 0; grid.gy_rs = 1; }
     __syncthreads();
-
-    const int nth = q.ang.nth, n_rays = nth * q.ang.nph;
-    if (!PANEL && q.rows) {
+    const int nth = q.ang.nth;
+    if (q.rows) {
         // accepted interval [lo, hi) of every phi row
         for (int j = tid; j < q.ang.nph; j += FF_T) {
             int lo, hi;
@@ -657,8 +657,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
                     int lo = 0, hi = 0;
                     if (j < q.ang.nph) {
                         lo = row_lo[j]; hi = lo + (row_pre[j + 1] - row_pre[j]);
-                        ff_pred_shrink(s_pred, q.ang.stf, __ldg(q.ang.cpf + j), __ldg(q.ang.spf + j), (float)grid.gx_max,
-                                       (float)grid.gy_max, lo, hi);
+                        ff_pred_shrink(s_pred, q.ang.stf, __ldg(q.ang.cpf + j), __ldg(q.ang.spf + j), q.gx_max, q.gy_max, lo, hi);
                     }
                     __syncthreads();                         // every count of this batch was read before any is replaced
                     if (j < q.ang.nph) { row_lo[j] = lo; row_pre[j + 1] = hi - lo; }
@@ -669,6 +668,69 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             }
         }
     }
+    // the record
+    unsigned char* rec = q.rec + (size_t)pix * q.stride;
+    {
+        const int* src = reinterpret_cast<const int*>(fr);
+        int* dst = reinterpret_cast<int*>(rec);
+        for (int i = tid; i < (int)(sizeof(FfFrames) / sizeof(int)); i += FF_T) dst[i] = src[i];
+        int* head = reinterpret_cast<int*>(rec + FF_REC_FRAMES);
+        if (tid == 0) { head[0] = s_queue_walk; head[1] = q.rows ? row_pre[q.ang.nph] : 0; head[2] = head[3] = 0; }
+        if (q.rows) {
+            int* rows = reinterpret_cast<int*>(rec + FF_REC_HEAD);
+            for (int i = tid; i < 2 * q.ang.nph + 1; i += FF_T) rows[i] = row_lo[i];   // row_lo and row_pre are contiguous
+        }
+    }
+}
+
+template <bool PANEL, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
+{
+    constexpr int FF_T = T, FF_WARPS = T / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cells = q.grid.M * q.grid.M;
+    FfFrames* fr = reinterpret_cast<FfFrames*>(smem_raw);
+    unsigned long long* win = reinterpret_cast<unsigned long long*>(smem_raw + ((sizeof(FfFrames) + 15) / 16) * 16);
+    int* queues = reinterpret_cast<int*>(win + cells);          // [FF_WARPS][FF_WQ]
+    double* s_gx = reinterpret_cast<double*>(queues + FF_WARPS * FF_WQ);   // [M] data_x[0, :]
+    double* s_gy = s_gx + q.grid.M;                                        // [M] data_y[:, 0] when all columns agree
+    int* row_lo = reinterpret_cast<int*>(s_gy + q.grid.M);                 // [nph] first ray to trace of a row
+    int* row_pre = row_lo + (q.rows ? q.ang.nph : 0);                      // [nph + 1] rays to trace before the row
+    __shared__ int s_queue_walk;
+    __shared__ double s_t2e[9];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
+    const FfGeom g = to_geom(q.g);
+    const Coef& sC = K_COEF;   // constant bank; a shared-memory copy measured 4 % slower (profiles/r01_variants.md)
+    {   // this pixel's record from ff_prep_kernel
+        const unsigned char* rec = q.rec + (size_t)pix * q.rec_stride;
+        const int* src = reinterpret_cast<const int*>(rec);
+        int* dst = reinterpret_cast<int*>(fr);
+        for (int i = tid; i < (int)(sizeof(FfFrames) / sizeof(int)); i += FF_T) dst[i] = __ldg(src + i);
+        if (tid == 0) s_queue_walk = __ldg(reinterpret_cast<const int*>(rec + FF_REC_FRAMES));
+        if (!PANEL && q.rows) {
+            const int* rows = reinterpret_cast<const int*>(rec + FF_REC_HEAD);
+            for (int i = tid; i < 2 * q.ang.nph + 1; i += FF_T) row_lo[i] = __ldg(rows + i);
+        }
+    }
+    for (int c = tid; c < cells; c += FF_T) win[c] = 0ull;
+    FfGrid grid = q.grid;                                   // grid axes on chip: the binning does 2-4 dependent reads per ray
+    for (int i = tid; i < grid.M; i += FF_T) {
+        s_gx[i] = __ldg(q.grid.gx + i);
+        if (grid.y_uniform) s_gy[i] = __ldg(q.grid.gy + (size_t)i * grid.M);
+    }
+    grid.gx = s_gx;
+    if (grid.y_uniform) { grid.gy = s_gy; grid.gy_cs = 0; grid.gy_rs = 1; }
+    __syncthreads();
+    if (PANEL) {
+        if (tid < 9) {
+            double v = fr->t2.a[tid];
+            if (g.src[2] != 0 && tid % 3 == 2) v /= cos(atan(1.0 / 3.0));   // saf:828-829
+            s_t2e[tid] = v;
+        }
+        __syncthreads();
+    }
+    const int nth = q.ang.nth, n_rays = nth * q.ang.nph;
     const bool queue_walk = PANEL || s_queue_walk != 0;
 
     int* wq = queues + warp * FF_WQ;
@@ -1375,6 +1437,7 @@ struct solat_ff_plan {
     DevBuf<int> status;
     DevBuf<short> pidx;                     // [2][npix][n_rays] panel columns of a panel-model map
     DevBuf<double> pan, xy;                 // panel models; mirror coordinates for identify_panel
+    DevBuf<unsigned char> rec;              // per-pixel records of ff_prep_kernel (frames, ray intervals)
     FfGrid grid;
     double k, key_base, key_unit;
     int M, n_rays, rows, shape, prefilter;
@@ -1406,17 +1469,45 @@ static int ff_map_set_smem(int shape, size_t smem)
     return SOLAT_OK;
 }
 
+// prep + map over the pixels in chunks (the per-pixel records are scratch: ~1.7 kB per pixel for a 100 x 100 fan,
+// ~9 kB for 1000 x 1000).  `panel`: ff_map_kernel<true> with q's panel fields set (queue walk, frames only).
+static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cudaStream_t s)
+{
+    const int rows = panel ? 0 : p->rows;
+    const size_t stride = ff_rec_stride(rows ? p->ang.tabs.nph : 0);
+    const int chunk = (int)std::min<size_t>((size_t)npix, std::max<size_t>(2048, ((size_t)192 << 20) / stride));
+    if (int rc = p->rec.reserve((size_t)chunk * stride)) return rc;
+    FfPrepParams pq;
+    pq.ang = p->ang.tabs; pq.g = p->g; pq.rows = rows; pq.prefilter = rows ? p->prefilter : 0;
+    pq.gx_max = (float)p->grid.gx_max; pq.gy_max = (float)p->grid.gy_max; pq.rec = p->rec.p; pq.stride = stride;
+    const size_t prep_smem = FF_REC_FRAMES + (rows ? (2 * (size_t)p->ang.tabs.nph + 1) * sizeof(int) : 0);
+    q.rows = rows; q.rec = p->rec.p; q.rec_stride = stride;
+    const double* azel = q.azel;
+    double *amp = q.amp, *phase = q.phase;
+    const short *i1 = q.pidx1, *i2 = q.pidx2;
+    for (int p0 = 0; p0 < npix; p0 += chunk) {
+        const int n = std::min(chunk, npix - p0);
+        pq.azel = azel + 2 * (size_t)p0;
+        ff_prep_kernel<<<n, FF_PREP_T, prep_smem, s>>>(pq);
+        LAUNCHED();
+        q.azel = azel + 2 * (size_t)p0; q.amp = amp + p0; q.phase = phase + p0;
+        if (panel) { q.pidx1 = i1 + (size_t)p0 * p->n_rays; q.pidx2 = i2 + (size_t)p0 * p->n_rays; }
+        if (panel) ff_map_dispatch<true>(p->shape, q, n, p->smem, s);
+        else ff_map_dispatch<false>(p->shape, q, n, p->smem, s);
+        LAUNCHED();
+    }
+    return SOLAT_OK;
+}
+
 static int ff_map_launch(solat_ff_plan* p, const double* d_azel, int npix, double* d_amp, double* d_phase, cudaStream_t s)
 {
     CK(cudaSetDevice(p->ctx->device));
     FfMapParams q;
     q.ang = p->ang.tabs; q.g = p->g; q.azel = d_azel; q.grid = p->grid; q.e_rec = p->e_rec.p;
     q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
-    q.amp = d_amp; q.phase = d_phase; q.status = p->status.p; q.rows = p->rows; q.prefilter = p->prefilter;
+    q.amp = d_amp; q.phase = d_phase; q.status = p->status.p;
     q.pidx1 = q.pidx2 = nullptr; q.pan1 = q.pan2 = nullptr; q.np1 = q.np2 = 0;
-    ff_map_dispatch<false>(p->shape, q, npix, p->smem, s);
-    LAUNCHED();
-    return SOLAT_OK;
+    return ff_map_run(p, q, npix, false, s);
 }
 
 extern "C" {
@@ -1562,10 +1653,9 @@ int solat_ff_map_panels_host(solat_ff_plan* p, const double* azel, int npix, con
     FfMapParams q;
     q.ang = p->ang.tabs; q.g = p->g; q.azel = p->ctx->stage_in.p; q.grid = p->grid; q.e_rec = p->e_rec.p;
     q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
-    q.amp = p->ctx->stage_out.p; q.phase = p->ctx->stage_out.p + n; q.status = p->status.p; q.rows = 0; q.prefilter = 0;
+    q.amp = p->ctx->stage_out.p; q.phase = p->ctx->stage_out.p + n; q.status = p->status.p;
     q.pidx1 = p->pidx.p; q.pidx2 = p->pidx.p + nr; q.pan1 = p->pan.p; q.pan2 = p->pan.p + 10 * (size_t)np1; q.np1 = np1; q.np2 = np2;
-    ff_map_dispatch<true>(p->shape, q, npix, p->smem, s);
-    LAUNCHED();
+    if (int rc = ff_map_run(p, q, npix, true, s)) return rc;
     pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->ctx->stage_out.p + 2 * n);
     LAUNCHED();
     CK(cudaMemcpyAsync(p->ctx->pin.p, p->ctx->stage_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
