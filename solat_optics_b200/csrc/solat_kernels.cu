@@ -551,7 +551,7 @@ __device__ __forceinline__ void ff_prefix_rows(int* row_pre, int nph, int lane)
 // interval walk the per-row ray intervals already shrunk by the focal-position predictor, as a record in global
 // memory the map kernel copies into its shared memory.  Record: FfFrames | int queue_walk, n_list, pad[2] |
 // row_lo[nph] | row_pre[nph + 1].
-constexpr int FF_PREP_T = 128;
+constexpr int FF_PREP_T = 64;     // = FF_PRED_SAMPLES; 12 CTAs per SM keep every pixel of a 41 x 41 map in flight
 constexpr size_t FF_REC_FRAMES = ((sizeof(FfFrames) + 15) / 16) * 16;
 constexpr size_t FF_REC_HEAD = FF_REC_FRAMES + 16;
 struct FfPrepParams {
@@ -565,7 +565,7 @@ struct FfPrepParams {
 };
 static size_t ff_rec_stride(int rows_nph) { return FF_REC_HEAD + (rows_nph ? ((2 * (size_t)rows_nph + 1) * sizeof(int) + 15) / 16 * 16 : 0); }
 
-__global__ void __launch_bounds__(FF_PREP_T) ff_prep_kernel(FfPrepParams q)
+__global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
 {
     constexpr int FF_T = FF_PREP_T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
