@@ -7,9 +7,12 @@
 //   nf_finalize_kernel     fixed-order sum of tile partials -> amp, phase
 //   ff_rows_kernel<STAGE>  thread-per-ray dump of ray_mirror_pts / aperature_fields_from_panel_model
 //   ff_project_*           last-write-wins scatter (atomicMax on the ray index) + phasor fill
-//   ff_map_kernel          fused far-field pixel: one CTA per (az, el); cheap aperture test feeds a
-//                          shared-memory work queue so every warp of the expensive mirror trace is full;
-//                          winner table (ray index, OPL) in shared memory; winners-only phasor sum
+//   ff_prep_kernel         per-pixel set-up of the fused far-field map: frames, per-row ray intervals, cull of the
+//                          rays the reference's projection would skip (focal-position predictor)
+//   ff_map_kernel          fused far-field pixel: one CTA per (az, el); every warp traces its share of the pixel's
+//                          dense ray list with full lanes; winner table (ray index, OPL) in shared memory;
+//                          winners-only phasor sum
+//   ff_mirror_xy_kernel    mirror coordinates of every (pixel, ray) for the host's identify_panel
 //   fp64_peak_kernel       DFMA issue-rate microbenchmark (roofline denominator)
 #include <cuda_runtime.h>
 
