@@ -483,6 +483,18 @@ def test_ff_ray_walks_agree(oracle, monkeypatch):
     np.testing.assert_array_equal(p_rows, p_q)
     oa, op = oracle.ff_map(geo, azel, th, phi, x, y, e, tgf.k)
     _assert_pixels(a_rows, p_rows, oa, op)
+    # the cull of rays beyond the E_rec grid (focal-position predictor) must not change a bit: the +-5 cm grid of
+    # ff_sim.py, where half of the accepted rays are culled, with the cull on and off, and against the oracle
+    x5, y5, e5 = gu.ff_grid("nf51")
+    a_on, p_on, st = maps.FarFieldPlan(tgf, th, phi, x5, y5, e5, device=0).run(azel)
+    assert st == 0
+    monkeypatch.setenv("SOLAT_FF_PREFILTER", "0")
+    a_off, p_off, st = maps.FarFieldPlan(tgf, th, phi, x5, y5, e5, device=0).run(azel)
+    monkeypatch.delenv("SOLAT_FF_PREFILTER")
+    np.testing.assert_array_equal(a_on, a_off)
+    np.testing.assert_array_equal(p_on, p_off)
+    oa5, op5 = oracle.ff_map(geo, azel, th, phi, x5, y5, e5, tgf.k)
+    _assert_pixels(a_on, p_on, oa5, op5)
     # a fan that crosses the aperture plane's horizon at this pointing: the interval walk must hand the pixel over
     t_h = np.linspace(np.pi - 1.0, np.pi + 1.0, 33)
     a_h, p_h, _ = maps.FarFieldPlan(tgf, t_h, phi, x, y, e, device=0).run([[0.0, 1.2], [0.0, gu.EL0]])
