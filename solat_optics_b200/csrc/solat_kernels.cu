@@ -565,6 +565,7 @@ struct FfPrepParams {
     float gx_max, gy_max;
     unsigned char* rec;
     size_t stride;
+    int* clear_status;       // host-buffer entries: the call's own status word (8-byte slot behind the results), zeroed here
 };
 static size_t ff_rec_stride(int rows_nph) { return FF_REC_HEAD + (rows_nph ? ((2 * (size_t)rows_nph + 1) * sizeof(int) + 15) / 16 * 16 : 0); }
 
@@ -587,6 +588,7 @@ __global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
         ff_build_frames(K_COEF, g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
         s_queue_walk = !q.rows;
         s_pred.on = 0;
+        if (pix == 0 && q.clear_status) { q.clear_status[0] = 0; q.clear_status[1] = 0; }
     }
     __syncthreads();
     const int nth = q.ang.nth;
@@ -1474,7 +1476,7 @@ static int ff_map_set_smem(int shape, size_t smem)
 
 // prep + map over the pixels in chunks (the per-pixel records are scratch: ~1.7 kB per pixel for a 100 x 100 fan,
 // ~9 kB for 1000 x 1000).  `panel`: ff_map_kernel<true> with q's panel fields set (queue walk, frames only).
-static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cudaStream_t s)
+static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cudaStream_t s, bool clear_status = false)
 {
     const int rows = panel ? 0 : p->rows;
     const size_t stride = ff_rec_stride(rows ? p->ang.tabs.nph : 0);
@@ -1491,6 +1493,7 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cud
     for (int p0 = 0; p0 < npix; p0 += chunk) {
         const int n = std::min(chunk, npix - p0);
         pq.azel = azel + 2 * (size_t)p0;
+        pq.clear_status = (clear_status && p0 == 0) ? q.status : nullptr;
         ff_prep_kernel<<<n, FF_PREP_T, prep_smem, s>>>(pq);
         LAUNCHED();
         q.azel = azel + 2 * (size_t)p0; q.amp = amp + p0; q.phase = phase + p0;
@@ -1502,15 +1505,18 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cud
     return SOLAT_OK;
 }
 
-static int ff_map_launch(solat_ff_plan* p, const double* d_azel, int npix, double* d_amp, double* d_phase, cudaStream_t s)
+// own_status: device word the launch reports its ray status in (zeroed by the launch itself); nullptr = the plan's
+// sticky status word (device-pointer entry, read with solat_ff_plan_status)
+static int ff_map_launch(solat_ff_plan* p, const double* d_azel, int npix, double* d_amp, double* d_phase, cudaStream_t s,
+                         int* own_status = nullptr)
 {
     CK(cudaSetDevice(p->ctx->device));
     FfMapParams q;
     q.ang = p->ang.tabs; q.g = p->g; q.azel = d_azel; q.grid = p->grid; q.e_rec = p->e_rec.p;
     q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
-    q.amp = d_amp; q.phase = d_phase; q.status = p->status.p;
+    q.amp = d_amp; q.phase = d_phase; q.status = own_status ? own_status : p->status.p;
     q.pidx1 = q.pidx2 = nullptr; q.pan1 = q.pan2 = nullptr; q.np1 = q.np2 = 0;
-    return ff_map_run(p, q, npix, false, s);
+    return ff_map_run(p, q, npix, false, s, own_status != nullptr);
 }
 
 extern "C" {
@@ -1600,15 +1606,15 @@ int solat_ff_map_host(solat_ff_plan* p, const double* azel, int npix, double* am
     if (int rc = p->ctx->stage_in.upload(azel, 2 * n, s)) return rc;
     if (int rc = p->ctx->stage_out.reserve(2 * n + 1)) return rc;
     if (int rc = p->ctx->pin.reserve(2 * n + 1)) return rc;
-    if (int rc = ff_map_launch(p, p->ctx->stage_in.p, npix, p->ctx->stage_out.p, p->ctx->stage_out.p + n, s)) return rc;
-    pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->ctx->stage_out.p + 2 * n);
-    LAUNCHED();
+    // the status word travels in the 8-byte slot behind the results: one D2H, no extra launch
+    int* d_status = reinterpret_cast<int*>(p->ctx->stage_out.p + 2 * n);
+    if (int rc = ff_map_launch(p, p->ctx->stage_in.p, npix, p->ctx->stage_out.p, p->ctx->stage_out.p + n, s, d_status)) return rc;
     CK(cudaMemcpyAsync(p->ctx->pin.p, p->ctx->stage_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     memcpy(amp, p->ctx->pin.p, n * sizeof(double));
     memcpy(phase, p->ctx->pin.p + n, n * sizeof(double));
-    const int st = (int)p->ctx->pin.p[2 * n];
-    if (st) CK(cudaMemset(p->status.p, 0, sizeof(int)));
+    int st = 0;
+    memcpy(&st, p->ctx->pin.p + 2 * n, sizeof(int));
     if (status) *status = st;
     return SOLAT_OK;
 }
