@@ -486,6 +486,7 @@ __global__ void ff_project_fill_kernel(const double* sim, int n_pts, const int* 
 constexpr int FF_T = SOLAT_FF_T;
 constexpr int FF_WQ = 64;            // per-warp queue capacity
 constexpr int FF_MAX_ROWS = 4096;    // phi rows the interval walk keeps on chip; larger fans take the queue walk
+struct FfItem;
 struct FfMapParams {
     AngleTabs ang;
     solat_ff_geom g;
@@ -500,6 +501,9 @@ struct FfMapParams {
     int rows;                // host: theta is strictly monotone inside one branch of tan -> interval walk allowed
     const unsigned char* rec;   // per-pixel records of ff_prep_kernel
     size_t rec_stride;
+    const FfItem* items;     // pair mode: work items (azel unused), counters[0] of them; two winner tables per CTA
+    const int* counters;
+    int item0;               // pair mode: CTA b handles item item0 + b (its record is record b)
     // panel models (ff_map_kernel<true> only): per (pixel, ray) column of pan1 / pan2, -1 = the ray sits on no panel
     const short *pidx1, *pidx2;
     const double *pan1, *pan2;   // (10, np) row-major [row, col, a, b, c, d, e, f, x0, y0]  (saf:667-674)
@@ -549,6 +553,94 @@ __device__ __forceinline__ void ff_prefix_rows(int* row_pre, int nph, int lane)
 //   * PANEL (adjuster-error studies, ff_sim.py:61-70 with non-zero offsets): every ray carries the panel-model
 //     columns the host derived with pan_mod.identify_panel; rays on no panel are dropped (saf:626-628,805-809), the
 //     others see their panels' error polynomials inside both Newton solves.  Always the queue walk.
+// Mirror pairs.  The LAT is symmetric under x -> -x (only even powers of x in both mirrors, source and rotation centre
+// at x = 0) and so is the reference's launch fan (phi = linspace(0, pi)): ray (i, j) of pixel (az, el) and ray
+// (i, nph-1-j) of pixel (-az, el) are mirror images -- same path length, focal x of opposite sign, same focal z.  A map
+// with an az grid symmetric about 0 (ff_sim.py:121-124) therefore needs every ray traced once for TWO pixels: the
+// work item is the canonical pixel (|az|, el); the traced ray is binned into the winner table of (+|az|, el) as ray
+// j*nth+i at (x, z) and into that of (-|az|, el) as ray (nph-1-j)*nth+i at (-x, z).  A pixel with az < 0 is ALWAYS
+// computed as the mirror of its canonical pixel, whether or not its partner is in the list, so a pixel's value never
+// depends on how the list is sharded.  Pairing runs on the device (open-addressing table keyed by (|az|, el)).
+struct FfItem {
+    double az, el;       // canonical pixel: az >= 0
+    int pos, neg;        // output index of (+az, el) and of (-az, el); -1 = not asked for
+};
+struct FfPairSlot { int owner, pos, neg; };
+// Partners are matched with an absolute tolerance of 1e-17 rad on |az|: np.linspace(-a, a, n) is symmetric only to a
+// few 1e-19 rad.  The item takes the az of its (+az) pixel; tracing the mirror pixel at an az that is off by 1e-17 rad
+// moves a focal position by 1e-13 mm and a path length by 3e-14 mm.  Buckets of 2e-17 rad: a partner is looked up in
+// its own bucket and both neighbours.
+constexpr double FF_PAIR_TOL = 1e-17;
+__device__ __forceinline__ long long ff_pair_bucket(double abs_az) { return (long long)(abs_az * 5e16); }
+__device__ __forceinline__ unsigned ff_pair_hash(long long bucket, double e)
+{
+    unsigned long long x = (unsigned long long)bucket * 0x9E3779B97F4A7C15ull;
+    x ^= (unsigned long long)__double_as_longlong(e) * 0xC2B2AE3D27D4EB4Full;
+    x ^= x >> 29;
+    return (unsigned)(x * 0xBF58476D1CE4E5B9ull >> 32);
+}
+// phase 1: every pixel with az >= 0 claims a slot.  ints[0] = number of items, ints[1] = length of the overflow list
+__global__ void ff_pair_insert_kernel(const double* azel, int npix, FfPairSlot* slots, unsigned nslots, int* over, int* ints)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const double az = azel[2 * p], el = azel[2 * p + 1];
+    if (!(az == az) || !(el == el)) { over[atomicAdd(ints + 1, 1)] = p; return; }   // NaN pointing: an item of its own
+    if (az < 0.0) return;
+    if (!(az < 1e2)) { over[atomicAdd(ints + 1, 1)] = p; return; }                   // beyond the bucket range: an item of its own
+    unsigned h = ff_pair_hash(ff_pair_bucket(az), el) % nslots;
+    for (;;) {
+        const int o = atomicCAS(&slots[h].owner, -1, p);
+        if (o == -1) { slots[h].pos = p; return; }
+        if (fabs(azel[2 * o]) == az && azel[2 * o + 1] == el) {                          // the same pixel twice in the list
+            over[atomicAdd(ints + 1, 1)] = p;
+            return;
+        }
+        h = h + 1 == nslots ? 0 : h + 1;
+    }
+}
+// phase 2: every pixel with az < 0 looks for the slot of its mirror pixel
+__global__ void ff_pair_attach_kernel(const double* azel, int npix, FfPairSlot* slots, unsigned nslots, int* over, int* ints)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const double az = azel[2 * p], el = azel[2 * p + 1];
+    if (!(az < 0.0) || !(el == el)) return;
+    const double a = -az;
+    for (int dk = 0; dk < 3 && a < 1e2; dk++) {
+        const long long bucket = ff_pair_bucket(a) + (dk == 0 ? 0 : (dk == 1 ? -1 : 1));
+        unsigned h = ff_pair_hash(bucket, el) % nslots;
+        for (;;) {
+            const int o = slots[h].owner;
+            if (o == -1) break;
+            if (azel[2 * o + 1] == el && fabs(fabs(azel[2 * o]) - a) <= FF_PAIR_TOL) {
+                if (atomicCAS(&slots[h].neg, -1, p) == -1) return;               // paired
+                dk = 3;                                                           // partner taken (duplicate): an item of its own
+                break;
+            }
+            h = h + 1 == nslots ? 0 : h + 1;
+        }
+    }
+    over[atomicAdd(ints + 1, 1)] = p;
+}
+__global__ void ff_pair_emit_kernel(const double* azel, const FfPairSlot* slots, unsigned nslots, const int* over, int* ints,
+                                    FfItem* items)
+{
+    const unsigned h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < nslots && slots[h].owner >= 0) {
+        FfItem it;
+        it.az = fabs(azel[2 * slots[h].owner]); it.el = azel[2 * slots[h].owner + 1]; it.pos = slots[h].pos; it.neg = slots[h].neg;
+        items[atomicAdd(ints, 1)] = it;
+    }
+    if (h < (unsigned)ints[1]) {
+        const int p = over[h];
+        const double az = azel[2 * p];
+        FfItem it;
+        it.az = fabs(az); it.el = azel[2 * p + 1]; it.pos = az < 0.0 ? -1 : p; it.neg = az < 0.0 ? p : -1;
+        items[atomicAdd(ints, 1)] = it;
+    }
+}
+
 // Per-pixel set-up of the fused map, one small CTA per pixel, all pixels of a launch in flight at once (the set-up is
 // latency bound: one thread builds the frames, one thread per phi row finds its interval): frames, and for the
 // interval walk the per-row ray intervals already shrunk by the focal-position predictor, as a record in global
@@ -560,7 +652,10 @@ constexpr size_t FF_REC_HEAD = FF_REC_FRAMES + 16;
 struct FfPrepParams {
     AngleTabs ang;
     solat_ff_geom g;
-    const double* azel;
+    const double* azel;      // direct mode: pixel list
+    const FfItem* items;     // pair mode: work items (azel unused); counters[0] = number of items
+    const int* counters;
+    int item0;               // pair mode: CTA b handles item item0 + b (its record is record b)
     int rows, prefilter;
     float gx_max, gy_max;
     unsigned char* rec;
@@ -582,10 +677,14 @@ __global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
     __shared__ float s_pres[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
+    if (q.items && q.item0 + pix >= __ldg(q.counters)) return;   // pair mode launches one CTA per pixel, items are fewer
+    const FfItem* item = q.items ? q.items + q.item0 + pix : nullptr;
     const FfGeom g = to_geom(q.g);
     const Coef& sC = K_COEF;
+    const double az = item ? item->az : __ldg(q.azel + 2 * pix), el = item ? item->el : __ldg(q.azel + 2 * pix + 1);
+    const bool need_pos = item ? item->pos >= 0 : true, need_neg = item ? item->neg >= 0 : false;
     if (tid == 0) {
-        ff_build_frames(K_COEF, g, __ldg(q.azel + 2 * pix + 1), __ldg(q.azel + 2 * pix), *fr);
+        ff_build_frames(K_COEF, g, el, az, *fr);
         s_queue_walk = !q.rows;
         s_pred.on = 0;
         if (pix == 0 && q.clear_status) { q.clear_status[0] = 0; q.clear_status[1] = 0; }
@@ -662,7 +761,9 @@ __global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
                     int lo = 0, hi = 0;
                     if (j < q.ang.nph) {
                         lo = row_lo[j]; hi = lo + (row_pre[j + 1] - row_pre[j]);
-                        ff_pred_shrink(s_pred, q.ang.stf, __ldg(q.ang.cpf + j), __ldg(q.ang.spf + j), q.gx_max, q.gy_max, lo, hi);
+                        // a ray is kept if the pixel or its mirror pixel (focal x negated, centre z shifted) can use it
+                        ff_pred_shrink(s_pred, q.ang.stf, __ldg(q.ang.cpf + j), __ldg(q.ang.spf + j), q.gx_max, q.gy_max, !need_neg,
+                                       !need_pos, need_neg ? 0.1f * fabsf((float)(fr->centre[2] - fr->centre_mz)) : 0.0f, lo, hi);
                     }
                     __syncthreads();                         // every count of this batch was read before any is replaced
                     if (j < q.ang.nph) { row_lo[j] = lo; row_pre[j + 1] = hi - lo; }
@@ -696,7 +797,8 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     const int cells = q.grid.M * q.grid.M;
     FfFrames* fr = reinterpret_cast<FfFrames*>(smem_raw);
     unsigned long long* win = reinterpret_cast<unsigned long long*>(smem_raw + ((sizeof(FfFrames) + 15) / 16) * 16);
-    int* queues = reinterpret_cast<int*>(win + cells);          // [FF_WARPS][FF_WQ]
+    unsigned long long* win_m = win + cells;                    // pair mode: winner table of the mirror pixel (-az, el)
+    int* queues = reinterpret_cast<int*>(win + (q.items ? 2 : 1) * cells);   // [FF_WARPS][FF_WQ]
     double* s_gx = reinterpret_cast<double*>(queues + FF_WARPS * FF_WQ);   // [M] data_x[0, :]
     double* s_gy = s_gx + q.grid.M;                                        // [M] data_y[:, 0] when all columns agree
     int* row_lo = reinterpret_cast<int*>(s_gy + q.grid.M);                 // [nph] first ray to trace of a row
@@ -705,6 +807,8 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     __shared__ double s_t2e[9];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
+    if (q.items && q.item0 + pix >= __ldg(q.counters)) return;   // pair mode launches one CTA per pixel, items are fewer
+    const int out_pos = q.items ? q.items[q.item0 + pix].pos : pix, out_neg = q.items ? q.items[q.item0 + pix].neg : -1;
     const FfGeom g = to_geom(q.g);
     const Coef& sC = K_COEF;   // constant bank; a shared-memory copy measured 4 % slower (profiles/r01_variants.md)
     {   // this pixel's record from ff_prep_kernel
@@ -718,7 +822,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             for (int i = tid; i < 2 * q.ang.nph + 1; i += FF_T) row_lo[i] = __ldg(rows + i);
         }
     }
-    for (int c = tid; c < cells; c += FF_T) win[c] = 0ull;
+    for (int c = tid; c < (q.items ? 2 : 1) * cells; c += FF_T) win[c] = 0ull;
     FfGrid grid = q.grid;                                   // grid axes on chip: the binning does 2-4 dependent reads per ray
     for (int i = tid; i < grid.M; i += FF_T) {
         s_gx[i] = __ldg(q.grid.gx + i);
@@ -824,12 +928,27 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             }
             st |= rst;
             if (opl != 0.0 && !not_finite(opl)) {                                   // ffl:10
-                const int cell = ff_cell(fx - cx, fz - cz, grid);
-                if (cell >= 0 && (win[cell] >> FF_KEY_SHIFT) < (unsigned long long)(r0 + 1)) {   // a later ray holds the cell already?
-                    bool exact;
-                    const unsigned long long key = ff_key(r0, opl, q.key_base, q.key_inv_unit, exact, q.key_unit);
-                    if (!exact) st |= ST_RANGE;
-                    atomicMax(win + cell, key);                                     // ffl:28: last write wins
+                if (out_pos >= 0) {
+                    const int cell = ff_cell(fx - cx, fz - cz, grid);
+                    if (cell >= 0 && (win[cell] >> FF_KEY_SHIFT) < (unsigned long long)(r0 + 1)) {   // a later ray holds the cell already?
+                        bool exact;
+                        const unsigned long long key = ff_key(r0, opl, q.key_base, q.key_inv_unit, exact, q.key_unit);
+                        if (!exact) st |= ST_RANGE;
+                        atomicMax(win + cell, key);                                 // ffl:28: last write wins
+                    }
+                }
+                if (out_neg >= 0) {
+                    // the mirror pixel (-az, el): this ray is its ray (nph-1-j, i), lands at (-x, z) about its own centre
+                    int i, j;
+                    ray_ij(q.ang, r0, i, j);
+                    const int rm = (q.ang.nph - 1 - j) * nth + i;
+                    const int cell = ff_cell(cx - fx, fz - fr->centre_mz, grid);
+                    if (cell >= 0 && (win_m[cell] >> FF_KEY_SHIFT) < (unsigned long long)(rm + 1)) {
+                        bool exact;
+                        const unsigned long long key = ff_key(rm, opl, q.key_base, q.key_inv_unit, exact, q.key_unit);
+                        if (!exact) st |= ST_RANGE;
+                        atomicMax(win_m + cell, key);
+                    }
                 }
             }
         }
@@ -837,41 +956,47 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     __syncthreads();
     // winners-only phasor sum: sum_cells exp(i k L/1e3) * E_rec / M^2   (ff_sim.py:215-221).  Only a fraction of the
     // cells holds a winner, so each warp compacts its winners through its queue and evaluates phasors with full lanes.
-    double re[1] = {0.0}, im[1] = {0.0};
-    cnt = 0;
-    for (int c0 = warp * 32;; c0 += FF_WARPS * 32) {
-        const bool more = c0 < cells;
-        if (more) {
-            const int c = c0 + lane;
-            const bool has = c < cells && win[c] != 0ull;
-            const unsigned m = __ballot_sync(0xffffffffu, has);
-            if (has) wq[cnt + __popc(m & ((1u << lane) - 1u))] = c;
-            cnt += __popc(m);
-            __syncwarp();
-        }
-        if (cnt >= 32 || (!more && cnt > 0)) {
-            const int n_take = min(cnt, 32);
-            const int c = lane < n_take ? wq[cnt - 1 - lane] : -1;
-            cnt -= n_take;
-            __syncwarp();
-            if (c >= 0) {
-                double cs, sn;
-                cis_large(q.k * ff_key_opl(win[c], q.key_base, q.key_unit) / 1e3, cs, sn);
-                const double2 e = __ldg(q.e_rec + c);
-                re[0] += cs * e.x - sn * e.y;
-                im[0] += cs * e.y + sn * e.x;
-            }
-        }
-        if (!more && cnt == 0) break;
-    }
     if (st) atomicOr(q.status, st);
     __shared__ double2 total;
-    block_reduce_store<1>(re, im, &total);
-    if (tid == 0) {
-        const double inv = 1.0 / ((double)q.grid.M * (double)q.grid.M);
-        const double a = total.x * inv, b = total.y * inv;
-        q.amp[pix] = hypot(a, b);
-        q.phase[pix] = atan2(b, a);
+    for (int side = 0; side < 2; side++) {
+        const int out = side ? out_neg : out_pos;
+        if (out < 0) continue;                                  // CTA-uniform
+        const unsigned long long* tab = side ? win_m : win;
+        double re[1] = {0.0}, im[1] = {0.0};
+        cnt = 0;
+        for (int c0 = warp * 32;; c0 += FF_WARPS * 32) {
+            const bool more = c0 < cells;
+            if (more) {
+                const int c = c0 + lane;
+                const bool has = c < cells && tab[c] != 0ull;
+                const unsigned m = __ballot_sync(0xffffffffu, has);
+                if (has) wq[cnt + __popc(m & ((1u << lane) - 1u))] = c;
+                cnt += __popc(m);
+                __syncwarp();
+            }
+            if (cnt >= 32 || (!more && cnt > 0)) {
+                const int n_take = min(cnt, 32);
+                const int c = lane < n_take ? wq[cnt - 1 - lane] : -1;
+                cnt -= n_take;
+                __syncwarp();
+                if (c >= 0) {
+                    double cs, sn;
+                    cis_large(q.k * ff_key_opl(tab[c], q.key_base, q.key_unit) / 1e3, cs, sn);
+                    const double2 e = __ldg(q.e_rec + c);
+                    re[0] += cs * e.x - sn * e.y;
+                    im[0] += cs * e.y + sn * e.x;
+                }
+            }
+            if (!more && cnt == 0) break;
+        }
+        block_reduce_store<1>(re, im, &total);
+        if (tid == 0) {
+            const double inv = 1.0 / ((double)q.grid.M * (double)q.grid.M);
+            const double a = total.x * inv, b = total.y * inv;
+            q.amp[out] = hypot(a, b);
+            q.phase[out] = atan2(b, a);
+        }
+        __syncthreads();                                        // `total` and the reduction scratch are reused
     }
 }
 
@@ -919,9 +1044,9 @@ static bool ff_rows_usable(const double* theta, int nth, int nph)
     return true;
 }
 
-static size_t ff_map_smem(int M, int rows_nph, int threads)
+static size_t ff_map_smem(int M, int rows_nph, int threads, int tables)
 {
-    const size_t cells = (size_t)M * M;
+    const size_t cells = (size_t)M * M * tables;
     return ((sizeof(FfFrames) + 15) / 16) * 16 + cells * sizeof(unsigned long long) + (size_t)(threads / 32) * FF_WQ * sizeof(int) +
            2 * (size_t)M * sizeof(double) + (rows_nph ? (2 * (size_t)rows_nph + 1) * sizeof(int) : 0);
 }
@@ -1443,6 +1568,10 @@ struct solat_ff_plan {
     DevBuf<short> pidx;                     // [2][npix][n_rays] panel columns of a panel-model map
     DevBuf<double> pan, xy;                 // panel models; mirror coordinates for identify_panel
     DevBuf<unsigned char> rec;              // per-pixel records of ff_prep_kernel (frames, ray intervals)
+    DevBuf<FfPairSlot> pair_slots;          // mirror pairing of a pixel list (ff_pair_*_kernel)
+    DevBuf<int> pair_ints;
+    DevBuf<FfItem> items;
+    int pairs;                              // geometry, fan and shared memory allow the mirror-pair walk
     FfGrid grid;
     double k, key_base, key_unit;
     int M, n_rays, rows, shape, prefilter;
@@ -1479,12 +1608,32 @@ static int ff_map_set_smem(int shape, size_t smem)
 static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cudaStream_t s, bool clear_status = false)
 {
     const int rows = panel ? 0 : p->rows;
+    const bool pairs = !panel && p->pairs;
     const size_t stride = ff_rec_stride(rows ? p->ang.tabs.nph : 0);
     const int chunk = (int)std::min<size_t>((size_t)npix, std::max<size_t>(2048, ((size_t)192 << 20) / stride));
     if (int rc = p->rec.reserve((size_t)chunk * stride)) return rc;
     FfPrepParams pq;
     pq.ang = p->ang.tabs; pq.g = p->g; pq.rows = rows; pq.prefilter = rows ? p->prefilter : 0;
     pq.gx_max = (float)p->grid.gx_max; pq.gy_max = (float)p->grid.gy_max; pq.rec = p->rec.p; pq.stride = stride;
+    pq.items = nullptr; pq.counters = nullptr; pq.item0 = 0;
+    q.items = nullptr; q.counters = nullptr; q.item0 = 0;
+    if (pairs) {
+        // work items = canonical pixels (|az|, el) with the output slots of (+az, el) and (-az, el)
+        const unsigned nslots = 2u * (unsigned)npix + 1u;
+        if (int rc = p->pair_slots.reserve(nslots)) return rc;
+        if (int rc = p->pair_ints.reserve((size_t)npix + 2)) return rc;       // [0..1] counters, then the overflow list
+        if (int rc = p->items.reserve((size_t)npix)) return rc;
+        CK(cudaMemsetAsync(p->pair_slots.p, 0xFF, nslots * sizeof(FfPairSlot), s));
+        CK(cudaMemsetAsync(p->pair_ints.p, 0, 2 * sizeof(int), s));
+        ff_pair_insert_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, p->pair_ints.p + 2, p->pair_ints.p);
+        LAUNCHED();
+        ff_pair_attach_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, p->pair_ints.p + 2, p->pair_ints.p);
+        LAUNCHED();
+        ff_pair_emit_kernel<<<(nslots + 255) / 256, 256, 0, s>>>(q.azel, p->pair_slots.p, nslots, p->pair_ints.p + 2, p->pair_ints.p,
+                                                                 p->items.p);
+        LAUNCHED();
+        pq.items = q.items = p->items.p; pq.counters = q.counters = p->pair_ints.p;
+    }
     const size_t prep_smem = FF_REC_FRAMES + (rows ? (2 * (size_t)p->ang.tabs.nph + 1) * sizeof(int) : 0);
     q.rows = rows; q.rec = p->rec.p; q.rec_stride = stride;
     const double* azel = q.azel;
@@ -1492,11 +1641,15 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cud
     const short *i1 = q.pidx1, *i2 = q.pidx2;
     for (int p0 = 0; p0 < npix; p0 += chunk) {
         const int n = std::min(chunk, npix - p0);
-        pq.azel = azel + 2 * (size_t)p0;
         pq.clear_status = (clear_status && p0 == 0) ? q.status : nullptr;
+        if (pairs) {
+            pq.item0 = q.item0 = p0;                        // CTAs past the last item return at once
+        } else {
+            pq.azel = azel + 2 * (size_t)p0;
+            q.azel = azel + 2 * (size_t)p0; q.amp = amp + p0; q.phase = phase + p0;
+        }
         ff_prep_kernel<<<n, FF_PREP_T, prep_smem, s>>>(pq);
         LAUNCHED();
-        q.azel = azel + 2 * (size_t)p0; q.amp = amp + p0; q.phase = phase + p0;
         if (panel) { q.pidx1 = i1 + (size_t)p0 * p->n_rays; q.pidx2 = i2 + (size_t)p0 * p->n_rays; }
         if (panel) ff_map_dispatch<true>(p->shape, q, n, p->smem, s);
         else ff_map_dispatch<false>(p->shape, q, n, p->smem, s);
@@ -1531,13 +1684,20 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
     int rows = ff_rows_usable(theta, nth, nph) ? 1 : 0;
     // CTA shape: the one that keeps the most warps resident next to the shared-memory winner table
     const size_t sm_smem = (size_t)c->prop.sharedMemPerMultiprocessor, cta_max = (size_t)c->prop.sharedMemPerBlockOptin;
+    // mirror pairs (see FfItem): the telescope and the fan must be symmetric under x -> -x
+    int pairs = rows && g->src_mm[0] == 0.0 && g->rotc_mm[0] == 0.0;
+    for (int j = 0; j < nph && pairs; j++)
+        if (!(fabs(phi[j] + phi[nph - 1 - j] - M_PI) <= 1e-12)) pairs = 0;
+    if (const char* env = getenv("SOLAT_FF_PAIRS")) if (env[0] == '0') pairs = 0;
     int shape = -1;
     size_t smem = 0;
-    for (int pass = 0; pass < 2 && shape < 0; pass++) {          // second pass: without the row tables (queue walk)
-        if (pass == 1) rows = 0;
+    // passes: pair walk (two winner tables), interval walk, queue walk (no row tables)
+    for (int pass = pairs ? 0 : 1; pass < 3 && shape < 0; pass++) {
+        if (pass >= 1) pairs = 0;
+        if (pass == 2) rows = 0;
         int best_warps = 0;
         for (int k = 0; k < FF_NSHAPES; k++) {
-            const size_t need = ff_map_smem(M, rows ? nph : 0, FF_SHAPES[k][0]) + 4608;     // + static shared memory
+            const size_t need = ff_map_smem(M, rows ? nph : 0, FF_SHAPES[k][0], pairs ? 2 : 1) + 4608;     // + static shared memory
             if (need > cta_max) continue;
             const int ctas = (int)std::min<size_t>((size_t)FF_SHAPES[k][1], sm_smem / (need + 1024));   // 1 KB reserved per CTA
             const int warps = ctas * FF_SHAPES[k][0] / 32;
@@ -1550,7 +1710,7 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
         return fail(SOLAT_ERR_ARG, "launch fan too large for the 20-bit ray index of the winner key (<= 1048575 rays)");
     if (int rc = ff_map_set_smem(shape, smem)) return rc;
     solat_ff_plan* p = new solat_ff_plan();
-    p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem; p->n_rays = nth * nph; p->rows = rows; p->shape = shape;
+    p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem; p->n_rays = nth * nph; p->rows = rows; p->shape = shape; p->pairs = pairs;
     {
         const char* env = getenv("SOLAT_FF_PREFILTER");   // "0": trace every accepted ray (experiments, strict status)
         p->prefilter = !(env && env[0] == '0');

@@ -607,6 +607,7 @@ struct FfFrames {
     double foc_row[3];     // second row of R(+el,+az)
     double foc_off;        // C.y - foc_row.C
     double centre[3];      // focal-plane centre, saf:323-339
+    double centre_mz;      // z of the focal-plane centre of the mirror pixel (-az, el); its x is -centre[0] (see ff_map_kernel)
     float apf[8];          // single-precision copy for the aperture prefilter: ap_row[3], ap_num, src.x, src.y - y_cent, R^2, margin
     // composites used by the fused map (ff_ray_lean): the ray stays in mirror-local coordinates from M1 on
     Affine t21;            // M1 local point  -> M2 local point   (t2 o t1^-1)
@@ -694,6 +695,7 @@ SOLAT_HD void ff_build_frames(const Coef& C_, const FfGeom& g, double el, double
     f.centre[0] = Rp[0] * (0.0 - C[0]) + Rp[1] * (0.0 - C[1]) + Rp[2] * (a50 - C[2]) + C[0];
     f.centre[1] = Rp[3] * (a50 - C[0]) + Rp[4] * (0.0 - C[1]) + Rp[5] * (0.0 - C[2]) + C[1];
     f.centre[2] = Rp[6] * (a50 - C[0]) + Rp[7] * (0.0 - C[1]) + Rp[8] * (0.0 - C[2]) + C[2];
+    f.centre_mz = (-Rp[6]) * (a50 - C[0]) + Rp[7] * (0.0 - C[1]) + Rp[8] * (0.0 - C[2]) + C[2];   // R(el, -az): only Rp[6] flips
 }
 
 // Panel-error polynomial of one panel (rows 2..9 of the reference's panel model, saf:667-674)
@@ -972,12 +974,19 @@ SOLAT_HD void ff_pred_set_margin(FfPred& p, float worst_mm)
 // times sin(theta_i), so the predicted x and z are monotone in i (sin(theta) is monotone on the fans the interval
 // walk accepts, and so are its single-precision table, the product and the FMA): the rays beyond one edge of the
 // grid are a prefix or a suffix of the row and the kept rays are again ONE interval, found by bisection.
-SOLAT_HD void ff_pred_shrink(const FfPred& p, const float* stf, float cpf, float spf, float gx_max_cm, float gy_max_cm, int& lo, int& hi)
+// cull_x_hi: drop rays beyond the high x edge (the pixel itself needs them not); cull_x_lo: the same for the mirror
+// pixel, whose focal x is the negative of this one's (ff_map_kernel); extra_z_cm widens the z margin (offset between
+// the two pixels' focal centres).
+SOLAT_HD void ff_pred_shrink(const FfPred& p, const float* stf, float cpf, float spf, float gx_max_cm, float gy_max_cm, bool cull_x_hi,
+                             bool cull_x_lo, float extra_z_cm, int& lo, int& hi)
 {
-    for (int k = 0; k < 2 && lo < hi; k++) {
-        const float* c = k ? p.cz : p.cx;
-        const float slope = fmaf(c[1], cpf, c[2] * spf), c0 = c[0], edge = (k ? gy_max_cm : gx_max_cm) + p.margin_cm;
-        auto miss = [&](int i) { return 0.1f * fmaf(stf[i] * FF_PRED_SCALE, slope, c0) > edge; };
+    for (int k = 0; k < 3 && lo < hi; k++) {
+        if ((k == 0 && !cull_x_hi) || (k == 1 && !cull_x_lo)) continue;
+        const float* c = k == 2 ? p.cz : p.cx;
+        const float sgn = k == 1 ? -0.1f : 0.1f;
+        const float slope = fmaf(c[1], cpf, c[2] * spf), c0 = c[0];
+        const float edge = (k == 2 ? gy_max_cm + extra_z_cm : gx_max_cm) + p.margin_cm;
+        auto miss = [&](int i) { return sgn * fmaf(stf[i] * FF_PRED_SCALE, slope, c0) > edge; };
         const bool m_lo = miss(lo), m_hi = miss(hi - 1);
         if (m_lo && m_hi) { hi = lo; return; }
         if (!m_lo && !m_hi) continue;

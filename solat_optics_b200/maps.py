@@ -408,6 +408,14 @@ class FarFieldPlan:
             pass
 
 
+def mirror_pair_order(pixels):
+    """Permutation of an (az, el) pixel list that puts (+az, el) next to (-az, el) (|az| compared to 1e-15 rad,
+    np.linspace grids are symmetric only to ~1e-19)."""
+    pixels = np.asarray(pixels, dtype=np.float64)
+    key = np.round(np.abs(pixels[:, 0]) / 1e-15)
+    return np.lexsort((np.signbit(pixels[:, 0]), pixels[:, 1], key))
+
+
 def ff_map(freq, res_arcmin, num, offset, data_x, data_y, e_rec, n_scan=100, device=None, strict=False, panel_models=None):
     """Far-field beam map `ff_sim.py <freq> <res> <num> <offset>`.  Returns on rank 0
     (pixels [npix,2] (az, el), amp [npix], phase [npix]); None on the other ranks.
@@ -419,11 +427,15 @@ def ff_map(freq, res_arcmin, num, offset, data_x, data_y, e_rec, n_scan=100, dev
     plan = FarFieldPlan(tg, theta, phi, data_x, data_y, e_rec, device)
     pixels = ff_pixels(tg, res_arcmin, num)
     rank, world = dist_info()
+    # ranks take contiguous blocks of the pixel list ordered so that mirror partners (+az, el), (-az, el) are
+    # neighbours: the kernel traces such a pair once (a pixel's value does not depend on the order or the sharding)
+    order = mirror_pair_order(pixels) if world > 1 else np.arange(len(pixels))
     lo, hi = shard_bounds(len(pixels), rank, world)
+    mine = pixels[order[lo:hi]]
     if hi > lo and panel_models is not None:
-        amp, phase, st = plan.run_panel_models(pixels[lo:hi], panel_models[0], panel_models[1])
+        amp, phase, st = plan.run_panel_models(mine, panel_models[0], panel_models[1])
     elif hi > lo:
-        amp, phase, st = plan.run(pixels[lo:hi])
+        amp, phase, st = plan.run(mine)
     else:
         amp, phase, st = np.zeros(0), np.zeros(0), 0
     _lib.raise_on_status(st, strict)
@@ -438,7 +450,9 @@ def ff_map(freq, res_arcmin, num, offset, data_x, data_y, e_rec, n_scan=100, dev
     if full is None:
         return None
     full = full.cpu().numpy()
-    return pixels, np.ascontiguousarray(full[:, 0]), np.ascontiguousarray(full[:, 1])
+    out = np.empty_like(full)
+    out[order] = full
+    return pixels, np.ascontiguousarray(out[:, 0]), np.ascontiguousarray(out[:, 1])
 
 
 def save_map_txt(path, c0, c1, amp, phase):

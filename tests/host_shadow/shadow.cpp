@@ -350,7 +350,7 @@ API int shadow_ff_pred_check(const double* geo, const double* th, int nth, const
             int lo, hi;
             ff_row_interval(K_COEF, g, f, st.data(), ct.data(), nth, sin(ph[j]), cos(ph[j]), lo, hi);
             int klo = lo, khi = hi;
-            ff_pred_shrink(p, stf.data(), (float)cos(ph[j]), (float)sin(ph[j]), (float)gx_max, (float)gy_max, klo, khi);
+            ff_pred_shrink(p, stf.data(), (float)cos(ph[j]), (float)sin(ph[j]), (float)gx_max, (float)gy_max, true, false, 0.0f, klo, khi);
             if (klo < lo || khi > hi || klo > khi) return 0;          // must stay inside the accepted interval
             for (int i = lo; i < hi; i++, at++) {
                 float u, v, x, z;

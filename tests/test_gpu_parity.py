@@ -551,6 +551,46 @@ def test_seeded_sweep_against_oracle(oracle):
         assert (a[~ok] == 0).all()
 
 
+def test_ff_mirror_pairs(oracle, monkeypatch):
+    """The x -> -x symmetry of the LAT lets the fused map trace a ray once for (+az, el) and (-az, el).  Pixels with
+    az >= 0 must come out bit-identical with the pair walk on and off, pixels with az < 0 (always computed as mirror
+    images) within 1e-9 of the direct computation and within the north-star tolerance of the oracle; a pixel's value
+    must not depend on whether its partner is in the list (to the 1e-17 rad the pairing tolerates)."""
+    from solat_optics_b200 import maps
+
+    tgf = maps.ff_tele_geo(140, 1.32)
+    geo = oracle.ff_geo_vec(rx_y_m=-1.32)
+    th, phi = gu.ff_fan(50)
+    x, y, e = gu.ff_grid("nf51")
+    px = maps.ff_pixels(tgf, 0.25, 6)                       # 13 x 13, az symmetric about 0 (to ~1e-19 rad)
+    a_on, p_on, st = maps.FarFieldPlan(tgf, th, phi, x, y, e, device=0).run(px)
+    assert st == 0
+    monkeypatch.setenv("SOLAT_FF_PAIRS", "0")
+    a_off, p_off, st = maps.FarFieldPlan(tgf, th, phi, x, y, e, device=0).run(px)
+    monkeypatch.delenv("SOLAT_FF_PAIRS")
+    pos = px[:, 0] >= 0
+    np.testing.assert_array_equal(a_on[pos], a_off[pos])
+    np.testing.assert_array_equal(p_on[pos], p_off[pos])
+    np.testing.assert_allclose(a_on, a_off, rtol=1e-9, atol=0)
+    assert np.abs(gu.wrap(p_on - p_off)).max() < 1e-9
+    oa, op = oracle.ff_map(geo, px, th, phi, x, y, e, tgf.k)
+    _assert_pixels(a_on, p_on, oa, op)
+    # partners present or not, list order, duplicates: same values
+    plan = maps.FarFieldPlan(tgf, th, phi, x, y, e, device=0)
+    neg_only = px[~pos]
+    a_n, p_n, _ = plan.run(neg_only)
+    np.testing.assert_allclose(a_n, a_on[~pos], rtol=1e-12, atol=0)
+    assert np.abs(gu.wrap(p_n - p_on[~pos])).max() < 1e-12
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(len(px))
+    a_p, p_p, _ = plan.run(px[perm])
+    np.testing.assert_array_equal(a_p, a_on[perm])
+    np.testing.assert_array_equal(p_p, p_on[perm])
+    dup = np.concatenate([px[:20], px[:20], px[-5:]])
+    a_d, p_d, _ = plan.run(dup)
+    np.testing.assert_allclose(a_d, np.concatenate([a_on[:20], a_on[:20], a_on[-5:]]), rtol=1e-12, atol=0)
+
+
 def test_ff_odd_sizes_and_edge_grids(oracle):
     """Ragged inputs: a fan that is not a multiple of the CTA size, a 1-pixel map, a 2x2 E_rec grid (every ray
     piles into cell 0 or is skipped), a grid entirely below the beam (all rays skipped -> 0)."""

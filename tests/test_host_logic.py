@@ -224,3 +224,23 @@ def test_near_field_table_to_e_rec():
     np.testing.assert_allclose(x[0, :], np.linspace(-5, 5, 5))     # ff_sim.py:55: x <- column 1, cm
     np.testing.assert_allclose(y[:, 0], np.linspace(-5, 5, 5))
     np.testing.assert_allclose(np.abs(e), amp.reshape(5, 5))
+
+
+def test_mirror_pair_order_keeps_partners_adjacent():
+    """Multi-rank far-field maps shard a pixel list ordered so that (+az, el) sits next to (-az, el); the order is a
+    permutation, tolerant of the 1e-19 rad asymmetry of np.linspace, and leaves az = 0 pixels alone."""
+    from solat_optics_b200 import maps
+
+    tg = maps.ff_tele_geo(140, 1.32)
+    px = maps.ff_pixels(tg, 0.25, 20)
+    order = maps.mirror_pair_order(px)
+    assert sorted(order.tolist()) == list(range(len(px)))
+    q = px[order]
+    n0 = int((q[:, 0] == 0).sum())
+    assert n0 == 41 and (q[:n0, 0] == 0).all()
+    rest = q[n0:]
+    assert len(rest) % 2 == 0
+    a, b = rest[0::2], rest[1::2]
+    assert (a[:, 0] > 0).all() and (b[:, 0] < 0).all()
+    np.testing.assert_array_equal(a[:, 1], b[:, 1])
+    np.testing.assert_allclose(a[:, 0], -b[:, 0], rtol=0, atol=1e-17)
