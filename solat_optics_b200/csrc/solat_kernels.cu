@@ -580,10 +580,8 @@ __device__ __forceinline__ unsigned ff_pair_hash(long long bucket, double e)
     return (unsigned)(x * 0xBF58476D1CE4E5B9ull >> 32);
 }
 // phase 1: every pixel with az >= 0 claims a slot.  ints[0] = number of items, ints[1] = length of the overflow list
-__global__ void ff_pair_insert_kernel(const double* azel, int npix, FfPairSlot* slots, unsigned nslots, int* over, int* ints)
+__device__ __forceinline__ void ff_pair_insert(int p, const double* azel, FfPairSlot* slots, unsigned nslots, int* over, int* ints)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npix) return;
     const double az = azel[2 * p], el = azel[2 * p + 1];
     if (!(az == az) || !(el == el)) { over[atomicAdd(ints + 1, 1)] = p; return; }   // NaN pointing: an item of its own
     if (az < 0.0) return;
@@ -600,10 +598,8 @@ __global__ void ff_pair_insert_kernel(const double* azel, int npix, FfPairSlot* 
     }
 }
 // phase 2: every pixel with az < 0 looks for the slot of its mirror pixel
-__global__ void ff_pair_attach_kernel(const double* azel, int npix, FfPairSlot* slots, unsigned nslots, int* over, int* ints)
+__device__ __forceinline__ void ff_pair_attach(int p, const double* azel, FfPairSlot* slots, unsigned nslots, int* over, int* ints)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npix) return;
     const double az = azel[2 * p], el = azel[2 * p + 1];
     if (!(az < 0.0) || !(el == el)) return;
     const double a = -az;
@@ -623,14 +619,16 @@ __global__ void ff_pair_attach_kernel(const double* azel, int npix, FfPairSlot* 
     }
     over[atomicAdd(ints + 1, 1)] = p;
 }
-__global__ void ff_pair_emit_kernel(const double* azel, const FfPairSlot* slots, unsigned nslots, const int* over, int* ints,
-                                    FfItem* items)
+// phase 3: slots and overflow list -> items; the table is left empty for the next call and the other call's counters
+// (ints_next) are zeroed
+__device__ __forceinline__ void ff_pair_emit(unsigned h, const double* azel, FfPairSlot* slots, unsigned nslots, const int* over, int* ints,
+                                             int* ints_next, FfItem* items)
 {
-    const unsigned h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h < nslots && slots[h].owner >= 0) {
         FfItem it;
         it.az = fabs(azel[2 * slots[h].owner]); it.el = azel[2 * slots[h].owner + 1]; it.pos = slots[h].pos; it.neg = slots[h].neg;
         items[atomicAdd(ints, 1)] = it;
+        slots[h].owner = slots[h].pos = slots[h].neg = -1;
     }
     if (h < (unsigned)ints[1]) {
         const int p = over[h];
@@ -639,6 +637,34 @@ __global__ void ff_pair_emit_kernel(const double* azel, const FfPairSlot* slots,
         it.az = fabs(az); it.el = azel[2 * p + 1]; it.pos = az < 0.0 ? -1 : p; it.neg = az < 0.0 ? p : -1;
         items[atomicAdd(ints, 1)] = it;
     }
+    if (h < 2) ints_next[h] = 0;
+}
+__global__ void ff_pair_insert_kernel(const double* azel, int npix, FfPairSlot* slots, unsigned nslots, int* over, int* ints)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npix) ff_pair_insert(p, azel, slots, nslots, over, ints);
+}
+__global__ void ff_pair_attach_kernel(const double* azel, int npix, FfPairSlot* slots, unsigned nslots, int* over, int* ints)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npix) ff_pair_attach(p, azel, slots, nslots, over, ints);
+}
+__global__ void ff_pair_emit_kernel(const double* azel, FfPairSlot* slots, unsigned nslots, const int* over, int* ints, int* ints_next,
+                                    FfItem* items)
+{
+    ff_pair_emit(blockIdx.x * blockDim.x + threadIdx.x, azel, slots, nslots, over, ints, ints_next, items);
+}
+// all three phases in one CTA (pixel lists up to FF_PAIR_ONE_CTA: one launch instead of three)
+constexpr int FF_PAIR_ONE_CTA = 16384;
+__global__ void __launch_bounds__(1024) ff_pair_kernel(const double* azel, int npix, FfPairSlot* slots, unsigned nslots, int* over, int* ints,
+                                                       int* ints_next, FfItem* items)
+{
+    for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_insert(p, azel, slots, nslots, over, ints);
+    __syncthreads();
+    for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_attach(p, azel, slots, nslots, over, ints);
+    __syncthreads();
+    const unsigned n = max(nslots, (unsigned)npix);
+    for (unsigned h = threadIdx.x; h < n; h += blockDim.x) ff_pair_emit(h, azel, slots, nslots, over, ints, ints_next, items);
 }
 
 // Per-pixel set-up of the fused map, one small CTA per pixel, all pixels of a launch in flight at once (the set-up is
@@ -1572,6 +1598,7 @@ struct solat_ff_plan {
     DevBuf<int> pair_ints;
     DevBuf<FfItem> items;
     int pairs;                              // geometry, fan and shared memory allow the mirror-pair walk
+    int pair_flip;                          // which of the two counter pairs the next call uses
     FfGrid grid;
     double k, key_base, key_unit;
     int M, n_rays, rows, shape, prefilter;
@@ -1618,21 +1645,34 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cud
     pq.items = nullptr; pq.counters = nullptr; pq.item0 = 0;
     q.items = nullptr; q.counters = nullptr; q.item0 = 0;
     if (pairs) {
-        // work items = canonical pixels (|az|, el) with the output slots of (+az, el) and (-az, el)
+        // work items = canonical pixels (|az|, el) with the output slots of (+az, el) and (-az, el).  The slot table is
+        // emptied by the emit phase itself and the two counter pairs alternate (each call zeroes the other's), so a call
+        // needs no memset once the buffers exist.
         const unsigned nslots = 2u * (unsigned)npix + 1u;
-        if (int rc = p->pair_slots.reserve(nslots)) return rc;
-        if (int rc = p->pair_ints.reserve((size_t)npix + 2)) return rc;       // [0..1] counters, then the overflow list
+        if (nslots > p->pair_slots.n || (size_t)npix + 4 > p->pair_ints.n) {
+            if (int rc = p->pair_slots.reserve(nslots)) return rc;
+            if (int rc = p->pair_ints.reserve((size_t)npix + 4)) return rc;   // [0..3] two counter pairs, then the overflow list
+            CK(cudaMemsetAsync(p->pair_slots.p, 0xFF, p->pair_slots.n * sizeof(FfPairSlot), s));
+            CK(cudaMemsetAsync(p->pair_ints.p, 0, 4 * sizeof(int), s));
+            p->pair_flip = 0;
+        }
         if (int rc = p->items.reserve((size_t)npix)) return rc;
-        CK(cudaMemsetAsync(p->pair_slots.p, 0xFF, nslots * sizeof(FfPairSlot), s));
-        CK(cudaMemsetAsync(p->pair_ints.p, 0, 2 * sizeof(int), s));
-        ff_pair_insert_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, p->pair_ints.p + 2, p->pair_ints.p);
-        LAUNCHED();
-        ff_pair_attach_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, p->pair_ints.p + 2, p->pair_ints.p);
-        LAUNCHED();
-        ff_pair_emit_kernel<<<(nslots + 255) / 256, 256, 0, s>>>(q.azel, p->pair_slots.p, nslots, p->pair_ints.p + 2, p->pair_ints.p,
-                                                                 p->items.p);
-        LAUNCHED();
-        pq.items = q.items = p->items.p; pq.counters = q.counters = p->pair_ints.p;
+        int* ints = p->pair_ints.p + 2 * p->pair_flip;
+        int* ints_next = p->pair_ints.p + 2 * (1 - p->pair_flip);
+        p->pair_flip = 1 - p->pair_flip;
+        int* over = p->pair_ints.p + 4;
+        if (npix <= FF_PAIR_ONE_CTA) {
+            ff_pair_kernel<<<1, 1024, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, over, ints, ints_next, p->items.p);
+            LAUNCHED();
+        } else {
+            ff_pair_insert_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, over, ints);
+            LAUNCHED();
+            ff_pair_attach_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, over, ints);
+            LAUNCHED();
+            ff_pair_emit_kernel<<<(nslots + 255) / 256, 256, 0, s>>>(q.azel, p->pair_slots.p, nslots, over, ints, ints_next, p->items.p);
+            LAUNCHED();
+        }
+        pq.items = q.items = p->items.p; pq.counters = q.counters = ints;
     }
     const size_t prep_smem = FF_REC_FRAMES + (rows ? (2 * (size_t)p->ang.tabs.nph + 1) * sizeof(int) : 0);
     q.rows = rows; q.rec = p->rec.p; q.rec_stride = stride;
