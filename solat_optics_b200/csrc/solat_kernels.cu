@@ -637,7 +637,7 @@ __device__ __forceinline__ void ff_pair_emit(unsigned h, const double* azel, FfP
         it.az = fabs(az); it.el = azel[2 * p + 1]; it.pos = az < 0.0 ? -1 : p; it.neg = az < 0.0 ? p : -1;
         items[atomicAdd(ints, 1)] = it;
     }
-    if (h < 2) ints_next[h] = 0;
+    if (ints_next && h < 2) ints_next[h] = 0;
 }
 __global__ void ff_pair_insert_kernel(const double* azel, int npix, FfPairSlot* slots, unsigned nslots, int* over, int* ints)
 {
@@ -654,17 +654,27 @@ __global__ void ff_pair_emit_kernel(const double* azel, FfPairSlot* slots, unsig
 {
     ff_pair_emit(blockIdx.x * blockDim.x + threadIdx.x, azel, slots, nslots, over, ints, ints_next, items);
 }
-// all three phases in one CTA (pixel lists up to FF_PAIR_ONE_CTA: one launch instead of three)
-constexpr int FF_PAIR_ONE_CTA = 16384;
-__global__ void __launch_bounds__(1024) ff_pair_kernel(const double* azel, int npix, FfPairSlot* slots, unsigned nslots, int* over, int* ints,
-                                                       int* ints_next, FfItem* items)
+// all three phases in one CTA with the table in shared memory (pixel lists up to FF_PAIR_ONE_CTA: one short launch
+// instead of three); ints[0] = number of items
+constexpr int FF_PAIR_ONE_CTA = 4096;
+static size_t ff_pair_smem(int npix) { return (2 * (size_t)npix + 1) * sizeof(FfPairSlot) + ((size_t)npix + 2) * sizeof(int); }
+__global__ void __launch_bounds__(1024) ff_pair_kernel(const double* azel, int npix, int* ints, FfItem* items)
 {
-    for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_insert(p, azel, slots, nslots, over, ints);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned nslots = 2u * (unsigned)npix + 1u;
+    FfPairSlot* slots = reinterpret_cast<FfPairSlot*>(smem_raw);
+    int* cnt = reinterpret_cast<int*>(slots + nslots);      // [0] items, [1] overflow length
+    int* over = cnt + 2;
+    for (unsigned h = threadIdx.x; h < nslots; h += blockDim.x) slots[h].owner = slots[h].pos = slots[h].neg = -1;
+    if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
     __syncthreads();
-    for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_attach(p, azel, slots, nslots, over, ints);
+    for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_insert(p, azel, slots, nslots, over, cnt);
     __syncthreads();
-    const unsigned n = max(nslots, (unsigned)npix);
-    for (unsigned h = threadIdx.x; h < n; h += blockDim.x) ff_pair_emit(h, azel, slots, nslots, over, ints, ints_next, items);
+    for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_attach(p, azel, slots, nslots, over, cnt);
+    __syncthreads();
+    for (unsigned h = threadIdx.x; h < nslots; h += blockDim.x) ff_pair_emit(h, azel, slots, nslots, over, cnt, nullptr, items);
+    __syncthreads();
+    if (threadIdx.x == 0) ints[0] = cnt[0];
 }
 
 // Per-pixel set-up of the fused map, one small CTA per pixel, all pixels of a launch in flight at once (the set-up is
@@ -1648,23 +1658,26 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cud
         // work items = canonical pixels (|az|, el) with the output slots of (+az, el) and (-az, el).  The slot table is
         // emptied by the emit phase itself and the two counter pairs alternate (each call zeroes the other's), so a call
         // needs no memset once the buffers exist.
-        const unsigned nslots = 2u * (unsigned)npix + 1u;
-        if (nslots > p->pair_slots.n || (size_t)npix + 4 > p->pair_ints.n) {
-            if (int rc = p->pair_slots.reserve(nslots)) return rc;
-            if (int rc = p->pair_ints.reserve((size_t)npix + 4)) return rc;   // [0..3] two counter pairs, then the overflow list
-            CK(cudaMemsetAsync(p->pair_slots.p, 0xFF, p->pair_slots.n * sizeof(FfPairSlot), s));
-            CK(cudaMemsetAsync(p->pair_ints.p, 0, 4 * sizeof(int), s));
-            p->pair_flip = 0;
-        }
         if (int rc = p->items.reserve((size_t)npix)) return rc;
-        int* ints = p->pair_ints.p + 2 * p->pair_flip;
-        int* ints_next = p->pair_ints.p + 2 * (1 - p->pair_flip);
-        p->pair_flip = 1 - p->pair_flip;
-        int* over = p->pair_ints.p + 4;
+        int* ints = nullptr;
         if (npix <= FF_PAIR_ONE_CTA) {
-            ff_pair_kernel<<<1, 1024, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, over, ints, ints_next, p->items.p);
+            if (int rc = p->pair_ints.reserve(8)) return rc;
+            ints = p->pair_ints.p;
+            ff_pair_kernel<<<1, 1024, ff_pair_smem(npix), s>>>(q.azel, npix, ints, p->items.p);
             LAUNCHED();
         } else {
+            const unsigned nslots = 2u * (unsigned)npix + 1u;
+            if (nslots > p->pair_slots.n || (size_t)npix + 4 > p->pair_ints.n) {
+                if (int rc = p->pair_slots.reserve(nslots)) return rc;
+                if (int rc = p->pair_ints.reserve((size_t)npix + 4)) return rc;   // [0..3] two counter pairs, then the overflow list
+                CK(cudaMemsetAsync(p->pair_slots.p, 0xFF, p->pair_slots.n * sizeof(FfPairSlot), s));
+                CK(cudaMemsetAsync(p->pair_ints.p, 0, 4 * sizeof(int), s));
+                p->pair_flip = 0;
+            }
+            ints = p->pair_ints.p + 2 * p->pair_flip;
+            int* ints_next = p->pair_ints.p + 2 * (1 - p->pair_flip);
+            p->pair_flip = 1 - p->pair_flip;
+            int* over = p->pair_ints.p + 4;
             ff_pair_insert_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, over, ints);
             LAUNCHED();
             ff_pair_attach_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, over, ints);
@@ -1749,6 +1762,7 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
     if ((long long)nth * nph > FF_MAX_RAYS)
         return fail(SOLAT_ERR_ARG, "launch fan too large for the 20-bit ray index of the winner key (<= 1048575 rays)");
     if (int rc = ff_map_set_smem(shape, smem)) return rc;
+    CK(cudaFuncSetAttribute(ff_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_pair_smem(FF_PAIR_ONE_CTA)));
     solat_ff_plan* p = new solat_ff_plan();
     p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem; p->n_rays = nth * nph; p->rows = rows; p->shape = shape; p->pairs = pairs;
     {
