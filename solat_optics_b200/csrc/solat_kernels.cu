@@ -1624,8 +1624,15 @@ static void ff_map_dispatch(int shape, const FfMapParams& q, int npix, size_t sm
     else if (shape == 1) ff_map_kernel<PANEL, 384, 2><<<npix, 384, smem, s>>>(q);
     else ff_map_kernel<PANEL, 768, 1><<<npix, 768, smem, s>>>(q);
 }
-static int ff_map_set_smem(int shape, size_t smem)
+// The dynamic shared-memory limit is an attribute of the kernel, not of a plan: plans with different grids or fans
+// coexist, so the limit of a shape only ever grows (per device).
+static int ff_map_set_smem(int device, int shape, size_t smem)
 {
+    static std::mutex mu;
+    static size_t granted[64][FF_NSHAPES] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = granted[device & 63][shape];
+    if (smem <= have) return SOLAT_OK;
     const int b = (int)smem;
     if (shape == 0) {
         CK(cudaFuncSetAttribute(ff_map_kernel<false, FF_T, SOLAT_FF_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
@@ -1637,6 +1644,7 @@ static int ff_map_set_smem(int shape, size_t smem)
         CK(cudaFuncSetAttribute(ff_map_kernel<false, 768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
         CK(cudaFuncSetAttribute(ff_map_kernel<true, 768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     }
+    have = smem;
     return SOLAT_OK;
 }
 
@@ -1761,7 +1769,7 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
     if (const char* pad = getenv("SOLAT_FF_SMEM_PAD")) smem += (size_t)atol(pad);   // occupancy experiments only
     if ((long long)nth * nph > FF_MAX_RAYS)
         return fail(SOLAT_ERR_ARG, "launch fan too large for the 20-bit ray index of the winner key (<= 1048575 rays)");
-    if (int rc = ff_map_set_smem(shape, smem)) return rc;
+    if (int rc = ff_map_set_smem(c->device, shape, smem)) return rc;
     CK(cudaFuncSetAttribute(ff_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_pair_smem(FF_PAIR_ONE_CTA)));
     solat_ff_plan* p = new solat_ff_plan();
     p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem; p->n_rays = nth * nph; p->rows = rows; p->shape = shape; p->pairs = pairs;

@@ -589,6 +589,27 @@ def test_ff_mirror_pairs(oracle, monkeypatch):
     dup = np.concatenate([px[:20], px[:20], px[-5:]])
     a_d, p_d, _ = plan.run(dup)
     np.testing.assert_allclose(a_d, np.concatenate([a_on[:20], a_on[:20], a_on[-5:]]), rtol=1e-12, atol=0)
+    # a list above 4096 pixels takes the three-kernel pairing (table in global memory, emptied by the emit phase,
+    # alternating counters): repeated calls on one plan, lists of different length in between, same answers
+    big = maps.ff_pixels(tgf, 0.1, 33)                      # 67 x 67 = 4489 pixels
+    th2, phi2 = gu.ff_fan(24)
+    plan2 = maps.FarFieldPlan(tgf, th2, phi2, x, y, e, device=0)
+    a1, p1, st = plan2.run(big)
+    assert st == 0
+    plan2.run(px)
+    a2, p2, _ = plan2.run(big)
+    a3, p3, _ = plan2.run(big[::-1].copy())
+    np.testing.assert_array_equal(a1, a2); np.testing.assert_array_equal(p1, p2)
+    np.testing.assert_array_equal(a1, a3[::-1]); np.testing.assert_array_equal(p1, p3[::-1])
+    pick = np.r_[0:4489:211, 4488]
+    oa, op = oracle.ff_map(geo, big[pick], th2, phi2, x, y, e, tgf.k)
+    _assert_pixels(a1[pick], p1[pick], oa, op)
+    # (plan2 needs less shared memory than plan: the kernels' dynamic shared-memory limit must not shrink with it)
+    # pointings that cannot be paired (az asymmetric beyond the tolerance, huge, NaN) are items of their own
+    odd = np.array([[3e-4, gu.EL0], [-3e-4 - 1e-15, gu.EL0], [-5e-4, gu.EL0], [2e2, gu.EL0], [np.nan, gu.EL0]])
+    a_o, p_o, _ = plan.run(odd)
+    oa, op = oracle.ff_map(geo, odd[:3], th, phi, x, y, e, tgf.k)
+    _assert_pixels(a_o[:3], p_o[:3], oa, op)
 
 
 def test_ff_odd_sizes_and_edge_grids(oracle):
