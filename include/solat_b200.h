@@ -117,6 +117,11 @@ SOLAT_API void solat_nf_plan_destroy(solat_nf_plan *plan);
 SOLAT_API int solat_nf_map_host(solat_nf_plan *plan, const double *src_xz, int npix, double *amp, double *phase, int *status);
 SOLAT_API int solat_nf_map_device(solat_nf_plan *plan, const double *d_src_xz, int npix, double *d_amp, double *d_phase,
                         void *stream);
+/* Receiver fields of nrx receiver positions p_rx[nrx][3] in one launch: rows 3 (path length) and 4 (feed-taper
+ * amplitude) of rx_to_lyot_model(...).output() (ray_trace_int.py:848-853), opl/amp [nrx][nth*nph] -- the receiver side
+ * of the per-pixel integral (scripts/holo_sim.py:157-176) for a receiver-offset sweep.                          */
+SOLAT_API int solat_nf_rx_fields(solat_ctx *ctx, const solat_nf_geom *g, const double *p_rx, int nrx, const double *theta, int nth,
+                       const double *phi, int nph, double *opl, double *amp, int *status);
 /* traced rays per pixel after culling (for FLOP accounting) */
 SOLAT_API int solat_nf_plan_active_rays(const solat_nf_plan *plan);
 /* number of output channels nrx * nfreq */

@@ -48,6 +48,7 @@ SIGNATURES = {
     "solat_nf_rx_trace": (c_i, [c_vp, ctypes.POINTER(NfGeom), c_dp, c_dp, c_i, c_dp, c_i, c_dp, c_ip]),
     "solat_nf_source_trace": (c_i, [c_vp, ctypes.POINTER(NfGeom), c_dp, c_dp, c_i, c_dp, c_i, c_dp, c_ip]),
     "solat_nf_toy_trace": (c_i, [c_vp, ctypes.POINTER(NfGeom), c_dp, c_dp, c_i, c_dp, c_i, c_dp, c_ip]),
+    "solat_nf_rx_fields": (c_i, [c_vp, ctypes.POINTER(NfGeom), c_dp, c_i, c_dp, c_i, c_dp, c_i, c_dp, c_dp, c_ip]),
     "solat_regrid_bicubic": (c_i, [c_vp, c_dp, c_i, c_i, c_dp]),
     "solat_nf_plan_create": (c_i, [c_vp, ctypes.POINTER(NfGeom), c_dp, c_i, c_dp, c_i, c_dp, c_dp, c_dp, c_i,
                                    ctypes.POINTER(c_vp)]),

@@ -267,6 +267,26 @@ __global__ void __launch_bounds__(128) nf_rows_kernel(NfRowsParams q)
     if (q.status) q.status[r] = st;
 }
 
+
+// Receiver fields of many receiver positions at once: path length and feed-taper amplitude of every ray (rows 3 and 4
+// of rx_to_lyot_model.output(), rti:848-853) -- what the per-pixel integral needs from the receiver side.
+// out_opl / out_amp [nrx][n_rays]; grid (ray blocks, receiver).
+__global__ void __launch_bounds__(128) nf_rx_fields_kernel(NfRowsParams q, const double* p_rx, double* out_opl, double* out_amp, int* status)
+{
+    const int n = q.ang.rays();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (r >= n) return;
+    const vec3 p0 = mk(__ldg(p_rx + 3 * k), __ldg(p_rx + 3 * k + 1), __ldg(p_rx + 3 * k + 2));
+    NfRxRay ray;
+    nf_rx_ray(K_COEF, p0, ray_dir(q.ang, r), q.n_si, q.n_vac, ray);
+    const int j = r / q.ang.nth, i = r - j * q.ang.nth;
+    double rows[20];
+    pack_nf_rx_rows(ray, p0, q.theta[i] - q.th_mean, q.phi[j] - q.ph_mean, q.inv_2sig2, rows);
+    out_opl[(size_t)k * n + r] = rows[3];
+    out_amp[(size_t)k * n + r] = rows[4];
+    if (ray.status) atomicOr(status, ray.status);
+}
+
 // ------------------------------------------------------------------------------------------------
 // near field: fused map
 // ------------------------------------------------------------------------------------------------
@@ -364,6 +384,18 @@ __global__ void __launch_bounds__(NF_T, SOLAT_NF_MINB) nf_map_kernel(NfMapParams
             base[(size_t)(q.j0 + t) * q.nfreq_total + q.f0 + f] = tmp[threadIdx.x];
         }
     }
+}
+
+// receiver phasor tables of a near-field plan: ph[(j * nfreq + f) * n_act + a] = w exp(i k_f L_rx / 1e3)
+__global__ void nf_phasor_kernel(const double2* opl_w, const double* k_per_m, int nrx, int nfreq, int n_act, double2* ph)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nrx * nfreq * n_act) return;
+    const int a = (int)(idx % n_act), f = (int)((idx / n_act) % nfreq), j = (int)(idx / ((long long)n_act * nfreq));
+    const double2 v = opl_w[(size_t)j * n_act + a];
+    double sn, cs;
+    sincos(v.x * k_per_m[f] / 1e3, &sn, &cs);
+    ph[idx] = make_double2(v.y * cs, v.y * sn);
 }
 
 __global__ void nf_finalize_kernel(const double2* partial, int npix, int tiles, int nfreq, double* amp, double* phase)
@@ -1307,6 +1339,46 @@ int solat_nf_rx_trace(solat_ctx* c, const solat_nf_geom* g, const double p[3], c
 {
     return nf_rows(c, NF_RX, g, p, th, nth, ph, nph, out, st);
 }
+int solat_nf_rx_fields(solat_ctx* c, const solat_nf_geom* g, const double* p_rx, int nrx, const double* theta, int nth,
+                       const double* phi, int nph, double* opl, double* amp, int* status)
+{
+    if (!c || !g || !p_rx || !theta || !phi || !opl || !amp || nrx <= 0 || nth <= 0 || nph <= 0 || nrx > 65535)
+        return fail(SOLAT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)nth * nph;
+    AngleTabsOwner ang;
+    if (int rc = ang.init(theta, nth, phi, nph, c->stream)) return rc;
+    DevBuf<double> d_raw, d_p, d_out;
+    DevBuf<int> d_st;
+    std::vector<double> raw(nth + nph);
+    memcpy(raw.data(), theta, sizeof(double) * nth);
+    memcpy(raw.data() + nth, phi, sizeof(double) * nph);
+    if (int rc = d_raw.upload(raw.data(), raw.size(), c->stream)) return rc;
+    if (int rc = d_p.upload(p_rx, 3 * (size_t)nrx, c->stream)) return rc;
+    if (int rc = d_out.reserve(2 * n * nrx)) return rc;
+    if (int rc = d_st.reserve(1)) return rc;
+    CK(cudaMemsetAsync(d_st.p, 0, sizeof(int), c->stream));
+    NfRowsParams q;
+    q.ang = ang.tabs; q.theta = d_raw.p; q.phi = d_raw.p + nth;
+    q.p[0] = q.p[1] = q.p[2] = 0.0;
+    q.n_si = g->n_si; q.n_vac = g->n_vac; q.y_ap = g->y_ap;
+    const double sig = g->th_fwhp / sqrt(8 * log(2.0));
+    q.inv_2sig2 = 0.5 / (sig * sig);
+    double mt = 0, mp = 0;
+    for (int i = 0; i < nth; i++) mt += theta[i];
+    for (int j = 0; j < nph; j++) mp += phi[j];
+    q.th_mean = mt / nth; q.ph_mean = mp / nph;
+    q.out = nullptr; q.status = nullptr;
+    nf_rx_fields_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)nrx), 128, 0, c->stream>>>(q, d_p.p, d_out.p, d_out.p + n * nrx, d_st.p);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(opl, d_out.p, n * nrx * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(amp, d_out.p + n * nrx, n * nrx * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    int st = 0;
+    CK(cudaMemcpyAsync(&st, d_st.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (status) *status = st;
+    return SOLAT_OK;
+}
 int solat_nf_source_trace(solat_ctx* c, const solat_nf_geom* g, const double p[3], const double* th, int nth,
                           const double* ph, int nph, double* out, int* st)
 {
@@ -1424,17 +1496,26 @@ int solat_nf_plan_create_multi(solat_ctx* c, const solat_nf_geom* g, const doubl
         if (any_w) idx.push_back((int)r);
     }
     p->n_act = (int)idx.size();
-    // receiver phasors w exp(i k L_rx / 1e3), one table per (receiver table, wavenumber)  (holo_sim.py:173-176)
-    std::vector<double2> ph((size_t)nrx * nfreq * p->n_act);
+    // receiver phasors w exp(i k L_rx / 1e3), one table per (receiver table, wavenumber)  (holo_sim.py:173-176):
+    // the compacted (L_rx, w) pairs go up, the sincos runs on the device
+    std::vector<double2> ow((size_t)nrx * p->n_act);
     for (int j = 0; j < nrx; j++)
-        for (int f = 0; f < nfreq; f++)
-            for (int a = 0; a < p->n_act; a++) {
-                const size_t r = (size_t)j * n + idx[a];
-                const double arg = rx_opl[r] * k_per_m[f] / 1e3;
-                ph[((size_t)j * nfreq + f) * p->n_act + a] = make_double2(rx_w[r] * cos(arg), rx_w[r] * sin(arg));
-            }
+        for (int a = 0; a < p->n_act; a++) {
+            const size_t r = (size_t)j * n + idx[a];
+            ow[(size_t)j * p->n_act + a] = make_double2(rx_opl[r], rx_w[r]);
+        }
+    DevBuf<double2> d_ow;
+    DevBuf<double> d_k;
     if (!rc && p->n_act) rc = p->act_idx.upload(idx.data(), idx.size(), c->stream);
-    if (!rc && p->n_act) rc = p->phasor.upload(ph.data(), ph.size(), c->stream);
+    if (!rc && p->n_act) rc = d_ow.upload(ow.data(), ow.size(), c->stream);
+    if (!rc && p->n_act) rc = d_k.upload(k_per_m, nfreq, c->stream);
+    if (!rc && p->n_act) rc = p->phasor.reserve((size_t)nrx * nfreq * p->n_act);
+    if (!rc && p->n_act) {
+        const long long total = (long long)nrx * nfreq * p->n_act;
+        nf_phasor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_ow.p, d_k.p, nrx, nfreq, p->n_act, p->phasor.p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "nf_phasor_kernel");
+    }
     if (!rc) rc = p->status.reserve(1);
     if (!rc && cudaMemsetAsync(p->status.p, 0, sizeof(int), c->stream) != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "memset");
     if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "sync");

@@ -99,11 +99,45 @@ def receiver_field(tele_geo, p_rx=(0, 0, 0), n_scan_rx=None, n_scan_so=None):
         out_rx = rti.rx_to_lyot_model(list(p_rx), tele_geo, PlotOpts).output()
     finally:
         tele_geo.n_scan = keep
+    if n_rx == n_so:
+        # equal grids: regrid is the identity on rows 3, 4 and puts the nominal +-70 mm index grid in rows 0, 2
+        return np.ascontiguousarray(out_rx[3, :]), np.where(_lyot_mask(n_so), out_rx[4, :], 0.0)
     so_like = np.zeros((26, n_so * n_so))
     _, rx_new = rti.regrid(out_rx, so_like)   # second return value carries the rx field (rti:1435-1438)
     lyot_r = np.sqrt(rx_new[0, :] ** 2 + rx_new[2, :] ** 2)
     w = np.where(lyot_r <= R_LYOT, rx_new[4, :], 0.0)
     return np.ascontiguousarray(rx_new[3, :]), np.ascontiguousarray(w)
+
+
+def receiver_fields(tele_geo, rx_positions, n_scan=None, device=None):
+    """receiver_field for many receiver positions in one launch (equal receiver and source grids):
+    (rx_opl [n_rx, n_scan^2], rx_w [n_rx, n_scan^2])."""
+    n = int(tele_geo.n_scan if n_scan is None else n_scan)
+    pos = _lib.as_f64(np.reshape(rx_positions, (-1, 3)))
+    # launch fan of rx_to_lyot_model (rti:593-598)
+    theta = np.linspace(-(np.pi / 2) - 0.28, -(np.pi / 2) + 0.28, n)
+    phi = np.linspace((np.pi / 2) - 0.28, (np.pi / 2) + 0.28, n)
+    opl = np.empty((len(pos), n * n))
+    amp = np.empty((len(pos), n * n))
+    st = _lib.c_i(0)
+    geom = _lib.nf_geom(tele_geo)
+    _lib.check(_lib.load().solat_nf_rx_fields(_lib.context(device).handle, ctypes.byref(geom), _lib.dptr(pos), len(pos),
+                                             _lib.dptr(theta), n, _lib.dptr(phi), n, _lib.dptr(opl), _lib.dptr(amp), ctypes.byref(st)))
+    _lib.raise_on_status(st.value, rti.strict)
+    return opl, np.where(_lyot_mask(n)[None, :], amp, 0.0)
+
+
+_LYOT_MASKS = {}
+
+
+def _lyot_mask(n):
+    """sqrt(X^2 + Z^2) <= R_LYOT on regrid's nominal index grid (rti:1403-1415, holo_sim.py:168-171)."""
+    m = _LYOT_MASKS.get(n)
+    if m is None:
+        axis = np.linspace(-70, 70, n)
+        X2, Z2 = np.meshgrid(axis, axis)
+        m = _LYOT_MASKS[n] = np.sqrt(np.ravel(X2) ** 2 + np.ravel(Z2) ** 2) <= R_LYOT
+    return m
 
 
 class NearFieldPlan:
@@ -226,8 +260,8 @@ def receiver_offset_sweep(freq, rx_positions, res=51, sweep=100, shift=0, n_scan
     table.  Single process (shard the receiver list over ranks for more GPUs).
     Returns (pixels [npix,2], amp [n_rx,npix], phase [n_rx,npix])."""
     tg = holo_tele_geo(float(freq), n_scan)
-    tabs = [receiver_field(tg, tuple(p), None, n_scan) for p in rx_positions]
-    plan = NearFieldPlan(tg, [tg.k], np.stack([t[0] for t in tabs]), np.stack([t[1] for t in tabs]), n_scan, device)
+    rx_opl, rx_w = receiver_fields(tg, rx_positions, n_scan, device)
+    plan = NearFieldPlan(tg, [tg.k], rx_opl, rx_w, n_scan, device)
     pixels = holo_pixels(res, sweep, shift)
     amp, phase, st = plan.run(pixels)
     _lib.raise_on_status(st, strict)

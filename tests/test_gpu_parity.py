@@ -205,6 +205,20 @@ def test_nf_receiver_offset_sweep_shares_the_source_trace(oracle):
         np.testing.assert_array_equal(a1, a[j]); np.testing.assert_array_equal(p1, p[j])
 
 
+def test_nf_batched_receiver_fields_equal_the_per_receiver_ones():
+    """solat_nf_rx_fields (all receiver positions of a sweep in one launch, only the path-length and taper rows)
+    against rx_to_lyot_model(...).output() + regrid + mask, receiver by receiver: bit for bit."""
+    from solat_optics_b200 import maps
+
+    tg = maps.holo_tele_geo(150.0, 37)
+    pos = [(0.0, 0.0, 0.0), (60.0, 0.0, -30.0), (-25.0, 3.0, 100.0)]
+    opl, w = maps.receiver_fields(tg, pos, device=0)
+    for k, p in enumerate(pos):
+        o1, w1 = maps.receiver_field(tg, p)
+        np.testing.assert_array_equal(opl[k], o1)
+        np.testing.assert_array_equal(w[k], w1)
+
+
 def test_nf_full_default_map_against_oracle(oracle):
     """BASELINE config 1 at full size: 51x51 pixels x 100^2 rays, every pixel against the oracle."""
     from solat_optics_b200 import maps
