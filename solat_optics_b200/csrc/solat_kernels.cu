@@ -996,27 +996,26 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             }
             st |= rst;
             if (opl != 0.0 && !not_finite(opl)) {                                   // ffl:10
+                // cells first (a later ray may hold them already), then ONE key for both pixels of a pair
+                int cell = -1, cell_m = -1, rm = 0;
                 if (out_pos >= 0) {
-                    const int cell = ff_cell(fx - cx, fz - cz, grid);
-                    if (cell >= 0 && (win[cell] >> FF_KEY_SHIFT) < (unsigned long long)(r0 + 1)) {   // a later ray holds the cell already?
-                        bool exact;
-                        const unsigned long long key = ff_key(r0, opl, q.key_base, q.key_inv_unit, exact, q.key_unit);
-                        if (!exact) st |= ST_RANGE;
-                        atomicMax(win + cell, key);                                 // ffl:28: last write wins
-                    }
+                    cell = ff_cell(fx - cx, fz - cz, grid);
+                    if (cell >= 0 && (win[cell] >> FF_KEY_SHIFT) >= (unsigned long long)(r0 + 1)) cell = -1;
                 }
                 if (out_neg >= 0) {
                     // the mirror pixel (-az, el): this ray is its ray (nph-1-j, i), lands at (-x, z) about its own centre
                     int i, j;
                     ray_ij(q.ang, r0, i, j);
-                    const int rm = (q.ang.nph - 1 - j) * nth + i;
-                    const int cell = ff_cell(cx - fx, fz - fr->centre_mz, grid);
-                    if (cell >= 0 && (win_m[cell] >> FF_KEY_SHIFT) < (unsigned long long)(rm + 1)) {
-                        bool exact;
-                        const unsigned long long key = ff_key(rm, opl, q.key_base, q.key_inv_unit, exact, q.key_unit);
-                        if (!exact) st |= ST_RANGE;
-                        atomicMax(win_m + cell, key);
-                    }
+                    rm = (q.ang.nph - 1 - j) * nth + i;
+                    cell_m = ff_cell(cx - fx, fz - fr->centre_mz, grid);
+                    if (cell_m >= 0 && (win_m[cell_m] >> FF_KEY_SHIFT) >= (unsigned long long)(rm + 1)) cell_m = -1;
+                }
+                if (cell >= 0 || cell_m >= 0) {
+                    bool exact;
+                    const unsigned long long low = ff_key(-1, opl, q.key_base, q.key_inv_unit, exact, q.key_unit);   // ray bits 0
+                    if (!exact) st |= ST_RANGE;
+                    if (cell >= 0) atomicMax(win + cell, low | ((unsigned long long)(r0 + 1) << FF_KEY_SHIFT));     // ffl:28: last write wins
+                    if (cell_m >= 0) atomicMax(win_m + cell_m, low | ((unsigned long long)(rm + 1) << FF_KEY_SHIFT));
                 }
             }
         }
