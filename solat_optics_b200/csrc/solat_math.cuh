@@ -624,9 +624,8 @@ SOLAT_HD void mat3_mul(const double* A, const double* B, double* C)
         for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
 // R(el,az) = Ry(az) Rx(el), latrt_geo.py:280-288
-SOLAT_HD void rot_el_az(double el, double az, double* R)
+SOLAT_HD void rot_from_trig(double se, double ce, double sa, double ca, double* R)
 {
-    const double ce = cos(el), se = sin(el), ca = cos(az), sa = sin(az);
     R[0] = ca;  R[1] = sa * se;  R[2] = sa * ce;
     R[3] = 0.0; R[4] = ce;       R[5] = -se;
     R[6] = -sa; R[7] = ca * se;  R[8] = ca * ce;
@@ -634,14 +633,20 @@ SOLAT_HD void rot_el_az(double el, double az, double* R)
 SOLAT_HD void ff_build_frames(const Coef& C_, const FfGeom& g, double el, double az, FfFrames& f)
 {
     double Rm[9], Rp[9];
-    rot_el_az(-el, -az, Rm);
-    rot_el_az(el, az, Rp);
+    // sin is odd and cos even to the bit, so R(-el, -az) comes from the same four values as R(el, az)
+    double se, ce, sa, ca;
+    sincos(el, &se, &ce);
+    sincos(az, &sa, &ca);
+    rot_from_trig(-se, ce, -sa, ca, Rm);
+    rot_from_trig(se, ce, sa, ca, Rp);
     const double C[3] = {g.rotc[0], g.rotc[1], g.rotc[2]};
     // aperture plane
     f.ap_row[0] = Rm[6]; f.ap_row[1] = Rm[7]; f.ap_row[2] = Rm[8];
     f.ap_num = C_.ff[4] - C[2] - (Rm[6] * (g.src[0] - C[0]) + Rm[7] * (g.src[1] - C[1]) + Rm[8] * (g.src[2] - C[2]));
     // F1 = diag(-1,1,-1) Rx(-th1), F2 = diag(-1,-1,1) Rx(-th2)
-    const double c1 = cos(g.th_1), s1 = sin(g.th_1), c2 = cos(g.th2), s2 = sin(g.th2);
+    double c1, s1, c2, s2;
+    sincos(g.th_1, &s1, &c1);
+    sincos(g.th2, &s2, &c2);
     const double F1[9] = {-1, 0, 0, 0, c1, s1, 0, s1, -c1};
     const double F2[9] = {-1, 0, 0, 0, -c2, -s2, 0, -s2, c2};
     const double o1[3] = {0.0, 7200.0, 3600.0}, o2[3] = {0.0, 4800.0 + 7200.0, 0.0};
