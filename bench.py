@@ -318,6 +318,72 @@ def cpu_baseline(tg, th, ph, pixels, data_x, data_y, e_rec):
                       % (len(sample), N_SCAN ** 2, cores, dt)}
 
 
+def run_nf(args):
+    """Optional second line (`--workload nf`, one GPU): BASELINE.json configs[0], the near-field holography map
+    `holo_sim.py 140` (51x51 source positions x 100^2 rays, 7328 traced per pixel after the receiver-mask cull)."""
+    import torch
+
+    from solat_optics_b200 import _lib, maps
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(0)
+    ctx = _lib.context(0)
+    tg = maps.holo_tele_geo(float(FREQ), 100)
+    rx_opl, rx_w = maps.receiver_field(tg)
+    plan = maps.NearFieldPlan(tg, [tg.k], rx_opl, rx_w, device=0)
+    px = maps.holo_pixels()
+    npix = len(px)
+    d_px = torch.from_numpy(px).cuda()
+    d_a = torch.empty(npix, dtype=torch.float64, device="cuda"); d_p = torch.empty_like(d_a)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(max(args.warmup, 3)):
+        plan.run_device(d_px, d_a, d_p, stream)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(physical_gpu_index(0))
+    sampler.start()
+    launches0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:
+        flush.fill_(1)
+        a.record(); plan.run_device(d_px, d_a, d_p, stream); b.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - launches0
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    amp = np.empty((1, npix)); ph = np.empty((1, npix))
+    for _ in range(max(args.warmup, 3)):
+        plan.run(px, amp, ph)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        plan.run(px, amp, ph)
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    clocks = sampler.finish()
+    peak = ctx.fp64_peak_tflops(5)
+    rays = npix * 100 ** 2
+    flop_model = 520.0 * npix * plan.active_rays                      # SURVEY 8d: 520 FLOP per traced source ray
+    flop_exec = 2 * 2801422656 + 1281023712 + 359073252             # ncu thread-level DFMA x2 + DMUL + DADD, profiles/r01k_op_counts.csv
+    achieved = flop_model / (ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": rays / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "holo_sim.py 140: near-field LATR holography map, 51x51 source positions x 100^2 rays, 140 GHz",
+                   "pixels_per_map": npix, "rays_per_pixel": 10000, "traced_rays_per_pixel": plan.active_rays,
+                   "l2": "flushed between timed steps (256 MiB write); the path reads <1 MB per step"},
+        "clocks": clocks,
+        "e2e": {"value": rays / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(px.nbytes), "d2h_bytes_per_step": int(2 * npix * 8),
+                "ms_per_step": e2e_ms, "api": "solat_nf_map_host via maps.NearFieldPlan.run"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": 210688, "flop_per_unit": 520.0, "units_per_launch": npix * plan.active_rays,
+                     "executed_tflops": flop_exec / (ms * 1e-3) / 1e12, "fp64_pipe_pct_ncu": 58.1,
+                     "kernel": "nf_map_kernel<1,1> + nf_finalize_kernel, CUDA events around the pair"},
+        "ray_status": int(plan.status()),
+    }
+    print(json.dumps(line))
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -325,8 +391,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="ff", choices=["ff", "nf"],
+                    help="ff (default): BASELINE.json configs[1], the bench line; nf: configs[0] on one GPU, an extra line")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "nf" and args.impl == "ours":
+        run_nf(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
