@@ -298,6 +298,7 @@ struct NfMapParams {
     const double* src_xz;      // [npix][2]
     const int* act_idx;        // [n_act] ray indices with a non-zero receiver weight in any table
     const double2* phasor;     // [nrx][nfreq][n_act]  w_rx exp(i k L_rx / 1e3)  (holo_sim.py:173-176)
+    const double2* first_leg;  // [n_act][4]  pixel-independent start of every active ray (nf_source_first_leg)
     double y_ap, n_si, n_vac;
     double kk[NF_MAXF];        // k/1e3 [rad/mm] of the wavenumbers of this launch
     int n_act, tiles, tile_len, nfreq_total, nch_total, f0, j0;
@@ -352,9 +353,13 @@ __global__ void __launch_bounds__(NF_T, SOLAT_NF_MINB) nf_map_kernel(NfMapParams
     int st = 0;
     const int q_end = min((tile + 1) * q.tile_len, q.n_act);
     for (int a = tile * q.tile_len + threadIdx.x; a < q_end; a += NF_T) {
-        const int r = __ldg(q.act_idx + a);
+        // the leg to the flat front of lens 1 does not depend on the source position: two 32-byte loads instead of a
+        // reciprocal, a square root and the launch direction
+        const double2 l0 = __ldg(q.first_leg + 4 * a), l1 = __ldg(q.first_leg + 4 * a + 1), l2 = __ldg(q.first_leg + 4 * a + 2),
+                      l3 = __ldg(q.first_leg + 4 * a + 3);          // {t1, d0.x}, {hit y, d0.z}, {d.x, d.y}, {d.z, status}
         NfSourceRay ray;
-        nf_source_ray(sC, p0, ray_dir(q.ang, r), q.n_si, q.n_vac, ray);
+        ray.p1b = mk(fma(l0.y, l0.x, p0.x), l1.x, fma(l1.y, l0.x, p0.z));
+        nf_source_ray_from_1b(sC, mk(l2.x, l2.y, l3.x), l0.x, (int)l3.y, q.n_si, q.n_vac, ray);
         st |= ray.status;
         if (ray.valid) {
 #pragma unroll
@@ -384,6 +389,17 @@ __global__ void __launch_bounds__(NF_T, SOLAT_NF_MINB) nf_map_kernel(NfMapParams
             base[(size_t)(q.j0 + t) * q.nfreq_total + q.f0 + f] = tmp[threadIdx.x];
         }
     }
+}
+
+// pixel-independent first leg of every active source ray of a near-field plan
+__global__ void nf_first_leg_kernel(AngleTabs ang, const int* act_idx, int n_act, double y_ap, double n_si, double n_vac, double2* tab)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_act) return;
+    double a4[4], b4[4];
+    nf_source_first_leg(K_COEF, ray_dir(ang, act_idx[a]), y_ap, n_si, n_vac, a4, b4);
+    tab[4 * a] = make_double2(a4[0], a4[1]); tab[4 * a + 1] = make_double2(a4[2], a4[3]);
+    tab[4 * a + 2] = make_double2(b4[0], b4[1]); tab[4 * a + 3] = make_double2(b4[2], b4[3]);
 }
 
 // receiver phasor tables of a near-field plan: ph[(j * nfreq + f) * n_act + a] = w exp(i k_f L_rx / 1e3)
@@ -1398,6 +1414,7 @@ struct solat_nf_plan {
     AngleTabsOwner ang;
     DevBuf<int> act_idx;
     DevBuf<double2> phasor;                 // [nrx][nfreq][n_act]
+    DevBuf<double2> first_leg;              // [n_act][4]
     DevBuf<double2> partial;
     DevBuf<int> status;
     std::vector<double> kk;
@@ -1442,7 +1459,7 @@ static int nf_map_launch(solat_nf_plan* p, const double* d_src, int npix, double
     nf_choose_tiling(p);
     if (int rc = p->partial.reserve((size_t)npix * p->tiles * nch)) return rc;
     NfMapParams q;
-    q.ang = p->ang.tabs; q.src_xz = d_src; q.act_idx = p->act_idx.p; q.phasor = p->phasor.p;
+    q.ang = p->ang.tabs; q.src_xz = d_src; q.act_idx = p->act_idx.p; q.phasor = p->phasor.p; q.first_leg = p->first_leg.p;
     q.y_ap = p->g.y_ap; q.n_si = p->g.n_si; q.n_vac = p->g.n_vac;
     q.n_act = p->n_act; q.tiles = p->tiles; q.tile_len = p->tile_len; q.nfreq_total = nfreq; q.nch_total = nch;
     q.partial = p->partial.p; q.status = p->status.p;
@@ -1514,6 +1531,13 @@ int solat_nf_plan_create_multi(solat_ctx* c, const solat_nf_geom* g, const doubl
         nf_phasor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_ow.p, d_k.p, nrx, nfreq, p->n_act, p->phasor.p);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (cudaGetLastError() != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "nf_phasor_kernel");
+    }
+    if (!rc && p->n_act) rc = p->first_leg.reserve(4 * (size_t)p->n_act);
+    if (!rc && p->n_act) {
+        nf_first_leg_kernel<<<(p->n_act + 127) / 128, 128, 0, c->stream>>>(p->ang.tabs, p->act_idx.p, p->n_act, g->y_ap, g->n_si, g->n_vac,
+                                                                           p->first_leg.p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "nf_first_leg_kernel");
     }
     if (!rc) rc = p->status.reserve(1);
     if (!rc && cudaMemsetAsync(p->status.p, 0, sizeof(int), c->stream) != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "memset");

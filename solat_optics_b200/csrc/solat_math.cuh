@@ -411,16 +411,16 @@ struct NfSourceRayT {
     typename Pack<R>::I status;
 };
 using NfSourceRay = NfSourceRayT<double>;
+// The ray from the flat front of lens 1 on: `d` is the direction inside the silicon, `st` the status of the 1B hit.
 template <class R>
-SOLAT_HD void nf_source_ray(const Coef& C, const vec3t<R>& p0, const vec3t<R>& d0, double n_si, double n_vac, NfSourceRayT<R>& r)
+SOLAT_HD void nf_source_ray_from_1b(const Coef& C, const vec3t<R>& d_in, R t1, typename Pack<R>::I st, double n_si, double n_vac,
+                                    NfSourceRayT<R>& r)
 {
     using I = typename Pack<R>::I;
     using B = typename Pack<R>::B;
     const double mu_in = n_vac / n_si, mu_out = n_si / n_vac;
-    R t1, t2, t3, t4, t5;
-    vec3t<R> N, d;
-    I st = plane_hit(p0, d0, C.plane[PLANE_1B], 5.0, 14000.0, t1, r.p1b);                   // rti:967
-    d = refract_flat_in(d0, mu_in);                                             // rti:992
+    R t2, t3, t4, t5;
+    vec3t<R> N, d = d_in;
     const I st1a = asphere_hit<SURF_1A>(C, r.p1b, d, 1.0, 900.0, t2, r.p1a, N);   // rti:1033
     // rti:1086 (radius >= 196 -> zero column; compared squared).  A NaN radius means the iterate left the domain of the conic
     // (r > 417 mm), where the reference's root function substitutes sag = 0 and then vignettes too.
@@ -442,6 +442,25 @@ SOLAT_HD void nf_source_ray(const Coef& C, const vec3t<R>& p0, const vec3t<R>& d
     st |= flag(band(alive, not_finite(opl)), ST_NAN);
     r.opl = select(alive, opl, R(0.0));
     r.status = st;
+}
+template <class R>
+SOLAT_HD void nf_source_ray(const Coef& C, const vec3t<R>& p0, const vec3t<R>& d0, double n_si, double n_vac, NfSourceRayT<R>& r)
+{
+    R t1;
+    const typename Pack<R>::I st = plane_hit(p0, d0, C.plane[PLANE_1B], 5.0, 14000.0, t1, r.p1b);   // rti:967
+    nf_source_ray_from_1b(C, refract_flat_in(d0, n_vac / n_si), t1, st, n_si, n_vac, r);     // rti:992
+}
+// What of a source ray does not depend on the source's x, z (every source of a map sits on the plane y = y_ap and the
+// front of lens 1 is flat): the path to the 1B plane, the direction after it and the hit's y.  The hit itself is
+// (x + t1 d0.x, hit_y, z + t1 d0.z).  Two double4 per ray: {t1, d0.x, hit_y, d0.z}, {d.x, d.y, d.z, status}.
+SOLAT_HD void nf_source_first_leg(const Coef& C, const vec3& d0, double y_ap, double n_si, double n_vac, double* a4, double* b4)
+{
+    double t1;
+    vec3 H;
+    const int st = plane_hit(mk(0.0, y_ap, 0.0), d0, C.plane[PLANE_1B], 5.0, 14000.0, t1, H);
+    const vec3 d = refract_flat_in(d0, n_vac / n_si);
+    a4[0] = t1; a4[1] = d0.x; a4[2] = H.y; a4[3] = d0.z;
+    b4[0] = d.x; b4[1] = d.y; b4[2] = d.z; b4[3] = (double)st;
 }
 
 // -- rx_to_lyot_model.trace_rays, ray_trace_int.py:614-876 -------------------------------------
