@@ -362,7 +362,7 @@ def run_nf(args):
     peak = ctx.fp64_peak_tflops(5)
     rays = npix * 100 ** 2
     flop_model = 520.0 * npix * plan.active_rays                      # 520 FLOP per traced source ray
-    flop_exec = 2 * 2801422656 + 1281023712 + 359073252             # ncu thread-level DFMA x2 + DMUL + DADD, profiles/r01k_op_counts.csv
+    flop_exec = 2 * 2610821376 + 1109482560 + 338681412             # ncu thread-level DFMA x2 + DMUL + DADD, profiles/r01l_nf_op_counts.csv
     achieved = flop_model / (ms * 1e-3) / 1e12
     line = {
         "metric": METRIC, "value": rays / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -375,8 +375,8 @@ def run_nf(args):
                 "ms_per_step": e2e_ms, "api": "solat_nf_map_host via maps.NearFieldPlan.run"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": 210688, "flop_per_unit": 520.0, "units_per_launch": npix * plan.active_rays,
-                     "executed_tflops": flop_exec / (ms * 1e-3) / 1e12, "fp64_pipe_pct_ncu": 58.1,
+                     "traffic": 645376, "flop_per_unit": 520.0, "units_per_launch": npix * plan.active_rays,
+                     "executed_tflops": flop_exec / (ms * 1e-3) / 1e12, "fp64_pipe_pct_ncu": 57.2,
                      "kernel": "nf_map_kernel<1,1> + nf_finalize_kernel, CUDA events around the pair"},
         "ray_status": int(plan.status()),
     }
