@@ -287,6 +287,138 @@ __global__ void __launch_bounds__(128) nf_rx_fields_kernel(NfRowsParams q, const
     if (ray.status) atomicOr(status, ray.status);
 }
 
+// Mirror pairs.  The LAT is symmetric under x -> -x (only even powers of x in both mirrors, source and rotation centre
+// at x = 0) and so is the reference's launch fan (phi = linspace(0, pi)): ray (i, j) of pixel (az, el) and ray
+// (i, nph-1-j) of pixel (-az, el) are mirror images -- same path length, focal x of opposite sign, same focal z.  A map
+// with an az grid symmetric about 0 (ff_sim.py:121-124) therefore needs every ray traced once for TWO pixels: the
+// work item is the canonical pixel (|az|, el); the traced ray is binned into the winner table of (+|az|, el) as ray
+// j*nth+i at (x, z) and into that of (-|az|, el) as ray (nph-1-j)*nth+i at (-x, z).  A pixel with az < 0 is ALWAYS
+// computed as the mirror of its canonical pixel, whether or not its partner is in the list, so a pixel's value never
+// depends on how the list is sharded.  Pairing runs on the device (open-addressing table keyed by (|az|, el)).
+struct FfItem {
+    double az, el;       // canonical pixel: az >= 0
+    int pos, neg;        // output index of (+az, el) and of (-az, el); -1 = not asked for
+};
+struct FfPairSlot { int owner, pos, neg; };
+// Partners are matched with an absolute tolerance of 1e-17 rad on |az|: np.linspace(-a, a, n) is symmetric only to a
+// few 1e-19 rad.  The item takes the az of its (+az) pixel; tracing the mirror pixel at an az that is off by 1e-17 rad
+// moves a focal position by 1e-13 mm and a path length by 3e-14 mm.  Buckets of 2e-17 rad: a partner is looked up in
+// its own bucket and both neighbours.
+// (The near-field map pairs source positions (x, z), (-x, z) the same way, with 1e-11 mm.)
+struct PairTol {
+    double tol, scale, limit;    // match tolerance, buckets per unit (= 1 / (2 tol)), largest |first coordinate| that is bucketed
+};
+constexpr PairTol FF_PAIR_TOL = {1e-17, 5e16, 1e2};
+constexpr PairTol NF_PAIR_TOL = {1e-11, 5e10, 1e8};
+__device__ __forceinline__ long long ff_pair_bucket(double abs_az, const PairTol& t) { return (long long)(abs_az * t.scale); }
+__device__ __forceinline__ unsigned ff_pair_hash(long long bucket, double e)
+{
+    unsigned long long x = (unsigned long long)bucket * 0x9E3779B97F4A7C15ull;
+    x ^= (unsigned long long)__double_as_longlong(e) * 0xC2B2AE3D27D4EB4Full;
+    x ^= x >> 29;
+    return (unsigned)(x * 0xBF58476D1CE4E5B9ull >> 32);
+}
+// phase 1: every pixel with az >= 0 claims a slot.  ints[0] = number of items, ints[1] = length of the overflow list
+__device__ __forceinline__ void ff_pair_insert(int p, const double* azel, FfPairSlot* slots, unsigned nslots, int* over, int* ints,
+                                               const PairTol& tol)
+{
+    const double az = azel[2 * p], el = azel[2 * p + 1];
+    if (!(az == az) || !(el == el)) { over[atomicAdd(ints + 1, 1)] = p; return; }   // NaN pointing: an item of its own
+    if (az < 0.0) return;
+    if (!(az < tol.limit)) { over[atomicAdd(ints + 1, 1)] = p; return; }             // beyond the bucket range: an item of its own
+    unsigned h = ff_pair_hash(ff_pair_bucket(az, tol), el) % nslots;
+    for (;;) {
+        const int o = atomicCAS(&slots[h].owner, -1, p);
+        if (o == -1) { slots[h].pos = p; return; }
+        if (fabs(azel[2 * o]) == az && azel[2 * o + 1] == el) {                          // the same pixel twice in the list
+            over[atomicAdd(ints + 1, 1)] = p;
+            return;
+        }
+        h = h + 1 == nslots ? 0 : h + 1;
+    }
+}
+// phase 2: every pixel with az < 0 looks for the slot of its mirror pixel
+__device__ __forceinline__ void ff_pair_attach(int p, const double* azel, FfPairSlot* slots, unsigned nslots, int* over, int* ints,
+                                               const PairTol& tol)
+{
+    const double az = azel[2 * p], el = azel[2 * p + 1];
+    if (!(az < 0.0) || !(el == el)) return;
+    const double a = -az;
+    for (int dk = 0; dk < 3 && a < tol.limit; dk++) {
+        const long long bucket = ff_pair_bucket(a, tol) + (dk == 0 ? 0 : (dk == 1 ? -1 : 1));
+        unsigned h = ff_pair_hash(bucket, el) % nslots;
+        for (;;) {
+            const int o = slots[h].owner;
+            if (o == -1) break;
+            if (azel[2 * o + 1] == el && fabs(fabs(azel[2 * o]) - a) <= tol.tol) {
+                if (atomicCAS(&slots[h].neg, -1, p) == -1) return;               // paired
+                dk = 3;                                                           // partner taken (duplicate): an item of its own
+                break;
+            }
+            h = h + 1 == nslots ? 0 : h + 1;
+        }
+    }
+    over[atomicAdd(ints + 1, 1)] = p;
+}
+// phase 3: slots and overflow list -> items; the table is left empty for the next call and the other call's counters
+// (ints_next) are zeroed
+__device__ __forceinline__ void ff_pair_emit(unsigned h, const double* azel, FfPairSlot* slots, unsigned nslots, const int* over, int* ints,
+                                             int* ints_next, FfItem* items)
+{
+    if (h < nslots && slots[h].owner >= 0) {
+        FfItem it;
+        it.az = fabs(azel[2 * slots[h].owner]); it.el = azel[2 * slots[h].owner + 1]; it.pos = slots[h].pos; it.neg = slots[h].neg;
+        items[atomicAdd(ints, 1)] = it;
+        slots[h].owner = slots[h].pos = slots[h].neg = -1;
+    }
+    if (h < (unsigned)ints[1]) {
+        const int p = over[h];
+        const double az = azel[2 * p];
+        FfItem it;
+        it.az = fabs(az); it.el = azel[2 * p + 1]; it.pos = az < 0.0 ? -1 : p; it.neg = az < 0.0 ? p : -1;
+        items[atomicAdd(ints, 1)] = it;
+    }
+    if (ints_next && h < 2) ints_next[h] = 0;
+}
+__global__ void ff_pair_insert_kernel(const double* azel, int npix, FfPairSlot* slots, unsigned nslots, int* over, int* ints, PairTol tol)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npix) ff_pair_insert(p, azel, slots, nslots, over, ints, tol);
+}
+__global__ void ff_pair_attach_kernel(const double* azel, int npix, FfPairSlot* slots, unsigned nslots, int* over, int* ints, PairTol tol)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npix) ff_pair_attach(p, azel, slots, nslots, over, ints, tol);
+}
+__global__ void ff_pair_emit_kernel(const double* azel, FfPairSlot* slots, unsigned nslots, const int* over, int* ints, int* ints_next,
+                                    FfItem* items)
+{
+    ff_pair_emit(blockIdx.x * blockDim.x + threadIdx.x, azel, slots, nslots, over, ints, ints_next, items);
+}
+// all three phases in one CTA with the table in shared memory (pixel lists up to FF_PAIR_ONE_CTA: one short launch
+// instead of three); ints[0] = number of items
+constexpr int FF_PAIR_ONE_CTA = 4096;
+static size_t ff_pair_smem(int npix) { return (2 * (size_t)npix + 1) * sizeof(FfPairSlot) + ((size_t)npix + 2) * sizeof(int); }
+__global__ void __launch_bounds__(1024) ff_pair_kernel(const double* azel, int npix, int* ints, FfItem* items, PairTol tol)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned nslots = 2u * (unsigned)npix + 1u;
+    FfPairSlot* slots = reinterpret_cast<FfPairSlot*>(smem_raw);
+    int* cnt = reinterpret_cast<int*>(slots + nslots);      // [0] items, [1] overflow length
+    int* over = cnt + 2;
+    for (unsigned h = threadIdx.x; h < nslots; h += blockDim.x) slots[h].owner = slots[h].pos = slots[h].neg = -1;
+    if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_insert(p, azel, slots, nslots, over, cnt, tol);
+    __syncthreads();
+    for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_attach(p, azel, slots, nslots, over, cnt, tol);
+    __syncthreads();
+    for (unsigned h = threadIdx.x; h < nslots; h += blockDim.x) ff_pair_emit(h, azel, slots, nslots, over, cnt, nullptr, items);
+    __syncthreads();
+    if (threadIdx.x == 0) ints[0] = cnt[0];
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // near field: fused map
 // ------------------------------------------------------------------------------------------------
@@ -299,6 +431,11 @@ struct NfMapParams {
     const int* act_idx;        // [n_act] ray indices with a non-zero receiver weight in any table
     const double2* phasor;     // [nrx][nfreq][n_act]  w_rx exp(i k L_rx / 1e3)  (holo_sim.py:173-176)
     const double2* first_leg;  // [n_act][4]  pixel-independent start of every active ray (nf_source_first_leg)
+    // mirror pairs (nf_map_kernel<.., true>): work items (|x|, z) with the output pixels of (+x, z) and (-x, z),
+    // counters[0] of them; amap[a] = active index of the mirror ray (theta_i, pi - phi_j) of active ray a
+    const FfItem* items;
+    const int* counters;
+    const int* amap;
     double y_ap, n_si, n_vac;
     double kk[NF_MAXF];        // k/1e3 [rad/mm] of the wavenumbers of this launch
     int n_act, tiles, tile_len, nfreq_total, nch_total, f0, j0;
@@ -340,16 +477,37 @@ __device__ __forceinline__ void block_reduce_store(double (&re)[NC], double (&im
 // NF wavenumbers x NT receiver tables: exp(i k L_source) is formed per wavenumber and multiplied into the
 // precomputed receiver phasor of every table (frequency sweeps of one band and receiver-offset sweeps share
 // the geometry: BASELINE configs 3 and 4).
-template <int NF, int NT>
+// PAIR: the optics tube is rotationally symmetric and the launch fan symmetric in phi about pi/2, so ray (i, j) from
+// the source (x, z) and ray (i, nph-1-j) from (-x, z) are mirror images with the same path length.  The work item is
+// then the source (|x|, z): every traced ray adds exp(i k L) times the receiver phasor of ray (i, j) to the pixel
+// (+|x|, z) and times that of the mirror ray to the pixel (-|x|, z).  A pixel with x < 0 is always computed this way,
+// partner in the list or not.  (NF * NT <= 4: two sets of accumulators.)
+template <int NF, int NT, bool PAIR>
 __global__ void __launch_bounds__(NF_T, SOLAT_NF_MINB) nf_map_kernel(NfMapParams q)
 {
     constexpr int NC = NF * NT;
     const Coef& sC = K_COEF;   // constant bank; a shared-memory copy measured 2-4 % slower (profiles/r01_variants.md)
     const int pix = blockIdx.x / q.tiles, tile = blockIdx.x - pix * q.tiles;
-    const vec3 p0 = mk(__ldg(q.src_xz + 2 * pix), q.y_ap, __ldg(q.src_xz + 2 * pix + 1));
-    double re[NC], im[NC];
+    int out_pos = pix, out_neg = -1;
+    bool mirror = false;
+    vec3 p0;
+    if (PAIR) {
+        if (pix >= __ldg(q.counters)) return;              // one CTA row per pixel is launched, items are fewer
+        const FfItem it = q.items[pix];
+        p0 = mk(it.az, q.y_ap, it.el);
+        out_pos = it.pos; out_neg = it.neg;
+    } else {
+        // a pixel with x < 0 is computed as the mirror image of (|x|, z) here too (when the plan is symmetric), so that
+        // its value does not depend on whether a launch pairs pixels or not
+        const double x = __ldg(q.src_xz + 2 * pix);
+        mirror = q.amap != nullptr && x < 0.0;
+        p0 = mk(mirror ? -x : x, q.y_ap, __ldg(q.src_xz + 2 * pix + 1));
+    }
+    double re[NC], im[NC], re_m[PAIR ? NC : 1], im_m[PAIR ? NC : 1];
 #pragma unroll
     for (int c = 0; c < NC; c++) re[c] = im[c] = 0.0;
+#pragma unroll
+    for (int c = 0; c < (PAIR ? NC : 1); c++) re_m[c] = im_m[c] = 0.0;
     int st = 0;
     const int q_end = min((tile + 1) * q.tile_len, q.n_act);
     for (int a = tile * q.tile_len + threadIdx.x; a < q_end; a += NF_T) {
@@ -362,32 +520,47 @@ __global__ void __launch_bounds__(NF_T, SOLAT_NF_MINB) nf_map_kernel(NfMapParams
         nf_source_ray_from_1b(sC, mk(l2.x, l2.y, l3.x), l0.x, (int)l3.y, q.n_si, q.n_vac, ray);
         st |= ray.status;
         if (ray.valid) {
+            const int am = (PAIR || mirror) ? __ldg(q.amap + a) : a;
 #pragma unroll
             for (int f = 0; f < NF; f++) {
                 double sn, cs;
                 sincos_mid(ray.opl * q.kk[f], sn, cs);                            // holo_sim.py:177
 #pragma unroll
                 for (int t = 0; t < NT; t++) {
-                    const double2 ph = __ldg(q.phasor + ((size_t)(q.j0 + t) * q.nfreq_total + (q.f0 + f)) * q.n_act + a);
-                    re[t * NF + f] = fma(ph.x, cs, fma(-ph.y, sn, re[t * NF + f]));
-                    im[t * NF + f] = fma(ph.x, sn, fma(ph.y, cs, im[t * NF + f]));
+                    const double2* tab = q.phasor + ((size_t)(q.j0 + t) * q.nfreq_total + (q.f0 + f)) * q.n_act;
+                    if (!PAIR || out_pos >= 0) {
+                        const double2 ph = __ldg(tab + (PAIR ? a : am));
+                        re[t * NF + f] = fma(ph.x, cs, fma(-ph.y, sn, re[t * NF + f]));
+                        im[t * NF + f] = fma(ph.x, sn, fma(ph.y, cs, im[t * NF + f]));
+                    }
+                    if (PAIR && out_neg >= 0) {
+                        const double2 ph = __ldg(tab + am);
+                        re_m[t * NF + f] = fma(ph.x, cs, fma(-ph.y, sn, re_m[t * NF + f]));
+                        im_m[t * NF + f] = fma(ph.x, sn, fma(ph.y, cs, im_m[t * NF + f]));
+                    }
                 }
             }
         }
     }
     if (st) atomicOr(q.status, st);
     // accumulators are ordered [t][f]; channel (j0 + t) * nfreq + f0 + f
-    double2* base = q.partial + ((size_t)pix * q.tiles + tile) * q.nch_total;
-    if (NT == 1) {
-        block_reduce_store<NC>(re, im, base + (size_t)q.j0 * q.nfreq_total + q.f0);
-    } else {
-        __shared__ double2 tmp[NF_MAXC];
-        block_reduce_store<NC>(re, im, tmp);
+    __shared__ double2 tmp[NF_MAXC];
+#pragma unroll
+    for (int side = 0; side < (PAIR ? 2 : 1); side++) {
+        const int out = side ? out_neg : out_pos;
+        if (out < 0) continue;                              // CTA-uniform
+        double2* base = q.partial + ((size_t)out * q.tiles + tile) * q.nch_total;
+        if constexpr (PAIR) {
+            if (side) block_reduce_store<NC>(re_m, im_m, tmp); else block_reduce_store<NC>(re, im, tmp);
+        } else {
+            block_reduce_store<NC>(re, im, tmp);
+        }
         __syncthreads();
         if (threadIdx.x < NC) {
             const int t = threadIdx.x / NF, f = threadIdx.x - t * NF;
             base[(size_t)(q.j0 + t) * q.nfreq_total + q.f0 + f] = tmp[threadIdx.x];
         }
+        __syncthreads();                                    // tmp and the reduction scratch are reused
     }
 }
 
@@ -534,7 +707,6 @@ __global__ void ff_project_fill_kernel(const double* sim, int n_pts, const int* 
 constexpr int FF_T = SOLAT_FF_T;
 constexpr int FF_WQ = 64;            // per-warp queue capacity
 constexpr int FF_MAX_ROWS = 4096;    // phi rows the interval walk keeps on chip; larger fans take the queue walk
-struct FfItem;
 struct FfMapParams {
     AngleTabs ang;
     solat_ff_geom g;
@@ -601,130 +773,6 @@ __device__ __forceinline__ void ff_prefix_rows(int* row_pre, int nph, int lane)
 //   * PANEL (adjuster-error studies, ff_sim.py:61-70 with non-zero offsets): every ray carries the panel-model
 //     columns the host derived with pan_mod.identify_panel; rays on no panel are dropped (saf:626-628,805-809), the
 //     others see their panels' error polynomials inside both Newton solves.  Always the queue walk.
-// Mirror pairs.  The LAT is symmetric under x -> -x (only even powers of x in both mirrors, source and rotation centre
-// at x = 0) and so is the reference's launch fan (phi = linspace(0, pi)): ray (i, j) of pixel (az, el) and ray
-// (i, nph-1-j) of pixel (-az, el) are mirror images -- same path length, focal x of opposite sign, same focal z.  A map
-// with an az grid symmetric about 0 (ff_sim.py:121-124) therefore needs every ray traced once for TWO pixels: the
-// work item is the canonical pixel (|az|, el); the traced ray is binned into the winner table of (+|az|, el) as ray
-// j*nth+i at (x, z) and into that of (-|az|, el) as ray (nph-1-j)*nth+i at (-x, z).  A pixel with az < 0 is ALWAYS
-// computed as the mirror of its canonical pixel, whether or not its partner is in the list, so a pixel's value never
-// depends on how the list is sharded.  Pairing runs on the device (open-addressing table keyed by (|az|, el)).
-struct FfItem {
-    double az, el;       // canonical pixel: az >= 0
-    int pos, neg;        // output index of (+az, el) and of (-az, el); -1 = not asked for
-};
-struct FfPairSlot { int owner, pos, neg; };
-// Partners are matched with an absolute tolerance of 1e-17 rad on |az|: np.linspace(-a, a, n) is symmetric only to a
-// few 1e-19 rad.  The item takes the az of its (+az) pixel; tracing the mirror pixel at an az that is off by 1e-17 rad
-// moves a focal position by 1e-13 mm and a path length by 3e-14 mm.  Buckets of 2e-17 rad: a partner is looked up in
-// its own bucket and both neighbours.
-constexpr double FF_PAIR_TOL = 1e-17;
-__device__ __forceinline__ long long ff_pair_bucket(double abs_az) { return (long long)(abs_az * 5e16); }
-__device__ __forceinline__ unsigned ff_pair_hash(long long bucket, double e)
-{
-    unsigned long long x = (unsigned long long)bucket * 0x9E3779B97F4A7C15ull;
-    x ^= (unsigned long long)__double_as_longlong(e) * 0xC2B2AE3D27D4EB4Full;
-    x ^= x >> 29;
-    return (unsigned)(x * 0xBF58476D1CE4E5B9ull >> 32);
-}
-// phase 1: every pixel with az >= 0 claims a slot.  ints[0] = number of items, ints[1] = length of the overflow list
-__device__ __forceinline__ void ff_pair_insert(int p, const double* azel, FfPairSlot* slots, unsigned nslots, int* over, int* ints)
-{
-    const double az = azel[2 * p], el = azel[2 * p + 1];
-    if (!(az == az) || !(el == el)) { over[atomicAdd(ints + 1, 1)] = p; return; }   // NaN pointing: an item of its own
-    if (az < 0.0) return;
-    if (!(az < 1e2)) { over[atomicAdd(ints + 1, 1)] = p; return; }                   // beyond the bucket range: an item of its own
-    unsigned h = ff_pair_hash(ff_pair_bucket(az), el) % nslots;
-    for (;;) {
-        const int o = atomicCAS(&slots[h].owner, -1, p);
-        if (o == -1) { slots[h].pos = p; return; }
-        if (fabs(azel[2 * o]) == az && azel[2 * o + 1] == el) {                          // the same pixel twice in the list
-            over[atomicAdd(ints + 1, 1)] = p;
-            return;
-        }
-        h = h + 1 == nslots ? 0 : h + 1;
-    }
-}
-// phase 2: every pixel with az < 0 looks for the slot of its mirror pixel
-__device__ __forceinline__ void ff_pair_attach(int p, const double* azel, FfPairSlot* slots, unsigned nslots, int* over, int* ints)
-{
-    const double az = azel[2 * p], el = azel[2 * p + 1];
-    if (!(az < 0.0) || !(el == el)) return;
-    const double a = -az;
-    for (int dk = 0; dk < 3 && a < 1e2; dk++) {
-        const long long bucket = ff_pair_bucket(a) + (dk == 0 ? 0 : (dk == 1 ? -1 : 1));
-        unsigned h = ff_pair_hash(bucket, el) % nslots;
-        for (;;) {
-            const int o = slots[h].owner;
-            if (o == -1) break;
-            if (azel[2 * o + 1] == el && fabs(fabs(azel[2 * o]) - a) <= FF_PAIR_TOL) {
-                if (atomicCAS(&slots[h].neg, -1, p) == -1) return;               // paired
-                dk = 3;                                                           // partner taken (duplicate): an item of its own
-                break;
-            }
-            h = h + 1 == nslots ? 0 : h + 1;
-        }
-    }
-    over[atomicAdd(ints + 1, 1)] = p;
-}
-// phase 3: slots and overflow list -> items; the table is left empty for the next call and the other call's counters
-// (ints_next) are zeroed
-__device__ __forceinline__ void ff_pair_emit(unsigned h, const double* azel, FfPairSlot* slots, unsigned nslots, const int* over, int* ints,
-                                             int* ints_next, FfItem* items)
-{
-    if (h < nslots && slots[h].owner >= 0) {
-        FfItem it;
-        it.az = fabs(azel[2 * slots[h].owner]); it.el = azel[2 * slots[h].owner + 1]; it.pos = slots[h].pos; it.neg = slots[h].neg;
-        items[atomicAdd(ints, 1)] = it;
-        slots[h].owner = slots[h].pos = slots[h].neg = -1;
-    }
-    if (h < (unsigned)ints[1]) {
-        const int p = over[h];
-        const double az = azel[2 * p];
-        FfItem it;
-        it.az = fabs(az); it.el = azel[2 * p + 1]; it.pos = az < 0.0 ? -1 : p; it.neg = az < 0.0 ? p : -1;
-        items[atomicAdd(ints, 1)] = it;
-    }
-    if (ints_next && h < 2) ints_next[h] = 0;
-}
-__global__ void ff_pair_insert_kernel(const double* azel, int npix, FfPairSlot* slots, unsigned nslots, int* over, int* ints)
-{
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < npix) ff_pair_insert(p, azel, slots, nslots, over, ints);
-}
-__global__ void ff_pair_attach_kernel(const double* azel, int npix, FfPairSlot* slots, unsigned nslots, int* over, int* ints)
-{
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < npix) ff_pair_attach(p, azel, slots, nslots, over, ints);
-}
-__global__ void ff_pair_emit_kernel(const double* azel, FfPairSlot* slots, unsigned nslots, const int* over, int* ints, int* ints_next,
-                                    FfItem* items)
-{
-    ff_pair_emit(blockIdx.x * blockDim.x + threadIdx.x, azel, slots, nslots, over, ints, ints_next, items);
-}
-// all three phases in one CTA with the table in shared memory (pixel lists up to FF_PAIR_ONE_CTA: one short launch
-// instead of three); ints[0] = number of items
-constexpr int FF_PAIR_ONE_CTA = 4096;
-static size_t ff_pair_smem(int npix) { return (2 * (size_t)npix + 1) * sizeof(FfPairSlot) + ((size_t)npix + 2) * sizeof(int); }
-__global__ void __launch_bounds__(1024) ff_pair_kernel(const double* azel, int npix, int* ints, FfItem* items)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const unsigned nslots = 2u * (unsigned)npix + 1u;
-    FfPairSlot* slots = reinterpret_cast<FfPairSlot*>(smem_raw);
-    int* cnt = reinterpret_cast<int*>(slots + nslots);      // [0] items, [1] overflow length
-    int* over = cnt + 2;
-    for (unsigned h = threadIdx.x; h < nslots; h += blockDim.x) slots[h].owner = slots[h].pos = slots[h].neg = -1;
-    if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
-    __syncthreads();
-    for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_insert(p, azel, slots, nslots, over, cnt);
-    __syncthreads();
-    for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_attach(p, azel, slots, nslots, over, cnt);
-    __syncthreads();
-    for (unsigned h = threadIdx.x; h < nslots; h += blockDim.x) ff_pair_emit(h, azel, slots, nslots, over, cnt, nullptr, items);
-    __syncthreads();
-    if (threadIdx.x == 0) ints[0] = cnt[0];
-}
-
 // Per-pixel set-up of the fused map, one small CTA per pixel, all pixels of a launch in flight at once (the set-up is
 // latency bound: one thread builds the frames, one thread per phi row finds its interval): frames, and for the
 // interval walk the per-row ray intervals already shrunk by the focal-position predictor, as a record in global
@@ -1415,6 +1463,10 @@ struct solat_nf_plan {
     DevBuf<int> act_idx;
     DevBuf<double2> phasor;                 // [nrx][nfreq][n_act]
     DevBuf<double2> first_leg;              // [n_act][4]
+    DevBuf<int> amap;                       // [n_act] active index of every ray's mirror ray (pairs)
+    DevBuf<FfItem> items;                   // work items of a paired map
+    DevBuf<int> pair_ints;
+    int pairs = 0;                          // fan and active set are mirror symmetric
     DevBuf<double2> partial;
     DevBuf<int> status;
     std::vector<double> kk;
@@ -1444,7 +1496,10 @@ static void nf_choose_tiling(solat_nf_plan* p)
 template <int NF, int NT>
 static void nf_launch_one(const NfMapParams& q, int grid, int threads, cudaStream_t s)
 {
-    nf_map_kernel<NF, NT><<<grid, threads, 0, s>>>(q);
+    if constexpr (NF * NT <= 4) {
+        if (q.items) { nf_map_kernel<NF, NT, true><<<grid, threads, 0, s>>>(q); return; }
+    }
+    nf_map_kernel<NF, NT, false><<<grid, threads, 0, s>>>(q);
 }
 
 static int nf_map_launch(solat_nf_plan* p, const double* d_src, int npix, double* d_amp, double* d_phase, cudaStream_t s)
@@ -1463,7 +1518,16 @@ static int nf_map_launch(solat_nf_plan* p, const double* d_src, int npix, double
     q.y_ap = p->g.y_ap; q.n_si = p->g.n_si; q.n_vac = p->g.n_vac;
     q.n_act = p->n_act; q.tiles = p->tiles; q.tile_len = p->tile_len; q.nfreq_total = nfreq; q.nch_total = nch;
     q.partial = p->partial.p; q.status = p->status.p;
-    const int grid = npix * p->tiles;
+    q.items = nullptr; q.counters = nullptr; q.amap = p->pairs ? p->amap.p : nullptr;
+    const bool pairs = p->pairs && nch <= 4 && npix <= FF_PAIR_ONE_CTA;
+    if (pairs) {
+        if (int rc = p->items.reserve((size_t)npix)) return rc;
+        if (int rc = p->pair_ints.reserve(8)) return rc;
+        ff_pair_kernel<<<1, 1024, ff_pair_smem(npix), s>>>(d_src, npix, p->pair_ints.p, p->items.p, NF_PAIR_TOL);
+        LAUNCHED();
+        q.items = p->items.p; q.counters = p->pair_ints.p;
+    }
+    const int grid = npix * p->tiles;                      // pairs: an upper bound, the CTAs past the last item return
     // every launch re-traces the rays, so pack as many channels as the accumulators allow (NF * NT <= 8)
     for (int f0 = 0; f0 < nfreq; f0 += NF_MAXF) {
         const int nf = std::min(NF_MAXF, nfreq - f0);
@@ -1512,6 +1576,25 @@ int solat_nf_plan_create_multi(solat_ctx* c, const solat_nf_geom* g, const doubl
         if (any_w) idx.push_back((int)r);
     }
     p->n_act = (int)idx.size();
+    // mirror pairs: the fan must be symmetric in phi about pi/2 and the active set closed under j -> nph-1-j
+    {
+        p->pairs = nph > 0 && !(getenv("SOLAT_NF_PAIRS") && getenv("SOLAT_NF_PAIRS")[0] == '0');
+        for (int j = 0; j < nph && p->pairs; j++)
+            if (!(fabs(phi[j] + phi[nph - 1 - j] - M_PI) <= 1e-12)) p->pairs = 0;
+        std::vector<int> am(idx.size());
+        for (size_t a = 0; a < idx.size() && p->pairs; a++) {
+            const int j = idx[a] / nth, i = idx[a] - j * nth;
+            const int rm = (nph - 1 - j) * nth + i;
+            const auto it = std::lower_bound(idx.begin(), idx.end(), rm);
+            if (it == idx.end() || *it != rm) p->pairs = 0; else am[a] = (int)(it - idx.begin());
+        }
+        if (p->pairs && p->n_act) {
+            if (!rc) rc = p->amap.upload(am.data(), am.size(), c->stream);
+            if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "sync");   // `am` goes out of scope
+            if (!rc && cudaFuncSetAttribute(ff_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_pair_smem(FF_PAIR_ONE_CTA)) != cudaSuccess)
+                rc = fail(SOLAT_ERR_CUDA, "cudaFuncSetAttribute");
+        }
+    }
     // receiver phasors w exp(i k L_rx / 1e3), one table per (receiver table, wavenumber)  (holo_sim.py:173-176):
     // the compacted (L_rx, w) pairs go up, the sincos runs on the device
     std::vector<double2> ow((size_t)nrx * p->n_act);
@@ -1775,7 +1858,7 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cud
         if (npix <= FF_PAIR_ONE_CTA) {
             if (int rc = p->pair_ints.reserve(8)) return rc;
             ints = p->pair_ints.p;
-            ff_pair_kernel<<<1, 1024, ff_pair_smem(npix), s>>>(q.azel, npix, ints, p->items.p);
+            ff_pair_kernel<<<1, 1024, ff_pair_smem(npix), s>>>(q.azel, npix, ints, p->items.p, FF_PAIR_TOL);
             LAUNCHED();
         } else {
             const unsigned nslots = 2u * (unsigned)npix + 1u;
@@ -1790,9 +1873,9 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cud
             int* ints_next = p->pair_ints.p + 2 * (1 - p->pair_flip);
             p->pair_flip = 1 - p->pair_flip;
             int* over = p->pair_ints.p + 4;
-            ff_pair_insert_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, over, ints);
+            ff_pair_insert_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, over, ints, FF_PAIR_TOL);
             LAUNCHED();
-            ff_pair_attach_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, over, ints);
+            ff_pair_attach_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, over, ints, FF_PAIR_TOL);
             LAUNCHED();
             ff_pair_emit_kernel<<<(nslots + 255) / 256, 256, 0, s>>>(q.azel, p->pair_slots.p, nslots, over, ints, ints_next, p->items.p);
             LAUNCHED();

@@ -205,6 +205,43 @@ def test_nf_receiver_offset_sweep_shares_the_source_trace(oracle):
         np.testing.assert_array_equal(a1, a[j]); np.testing.assert_array_equal(p1, p[j])
 
 
+def test_nf_mirror_pairs(oracle, monkeypatch):
+    """The optics tube is symmetric under x -> -x and so is the launch fan: the near-field map traces a ray once for
+    the source positions (+x, z) and (-x, z).  x >= 0 pixels bit-identical with the pair walk on and off, x < 0 pixels
+    (always computed as mirror images) within 1e-9 and within tolerance of the oracle; shuffled, one-sided and
+    duplicated lists give the same values; frequency sweeps (up to 4 channels) pair, larger channel counts do not."""
+    from solat_optics_b200 import maps
+
+    tg = maps.holo_tele_geo(150.0, 36)
+    rx_opl, rx_w = maps.receiver_field(tg, (20.0, 0.0, -35.0))          # an off-axis receiver: asymmetric weights
+    px = maps.holo_pixels(res=9, sweep=100)
+    kk = [tg.k, maps.holo_tele_geo(220.0, 36).k, maps.holo_tele_geo(280.0, 36).k]
+    plan = maps.NearFieldPlan(tg, kk, rx_opl, rx_w, device=0)
+    a_on, p_on, st = plan.run(px)
+    assert st == 0
+    monkeypatch.setenv("SOLAT_NF_PAIRS", "0")
+    a_off, p_off, st = maps.NearFieldPlan(tg, kk, rx_opl, rx_w, device=0).run(px)
+    monkeypatch.delenv("SOLAT_NF_PAIRS")
+    pos = px[:, 0] >= 0
+    np.testing.assert_array_equal(a_on[:, pos], a_off[:, pos])
+    np.testing.assert_array_equal(p_on[:, pos], p_off[:, pos])
+    np.testing.assert_allclose(a_on, a_off, rtol=1e-9, atol=0)
+    assert np.abs(gu.wrap(p_on - p_off)).max() < 1e-9
+    rx = oracle.nf_rx_trace((20.0, 0.0, -35.0), tg.th_fwhp, 36)
+    oa, op = oracle.nf_map(px, tg.y_ap, 36, rx[3], rx[4] * gu.lyot_mask(36), kk)
+    for f in range(3):
+        _assert_pixels(a_on[f], p_on[f], oa[f], op[f])
+    rng = np.random.default_rng(4)
+    perm = rng.permutation(len(px))
+    a_p, p_p, _ = plan.run(px[perm])
+    np.testing.assert_array_equal(a_p, a_on[:, perm]); np.testing.assert_array_equal(p_p, p_on[:, perm])
+    a_n, p_n, _ = plan.run(px[~pos])
+    np.testing.assert_allclose(a_n, a_on[:, ~pos], rtol=1e-12, atol=0)
+    dup = np.concatenate([px[:11], px[:11]])
+    a_d, _, _ = plan.run(dup)
+    np.testing.assert_allclose(a_d, np.concatenate([a_on[:, :11], a_on[:, :11]], axis=1), rtol=1e-12, atol=0)
+
+
 def test_nf_batched_receiver_fields_equal_the_per_receiver_ones():
     """solat_nf_rx_fields (all receiver positions of a sweep in one launch, only the path-length and taper rows)
     against rx_to_lyot_model(...).output() + regrid + mask, receiver by receiver: bit for bit."""
