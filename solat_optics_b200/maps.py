@@ -233,9 +233,12 @@ def holo_map(freqs, res=51, sweep=100, shift=0, n_scan=100, n_scan_rx=None, p_rx
     plan = NearFieldPlan(tg, [g.k for g in geos], rx_opl, rx_w, n_scan, device)
     pixels = holo_pixels(res, sweep, shift)
     rank, world = dist_info()
+    # ranks take contiguous blocks of the list ordered so that the mirror positions (+x, z), (-x, z) are neighbours:
+    # the kernel traces such a pair once
+    order = mirror_pair_order(pixels) if world > 1 else np.arange(len(pixels))
     lo, hi = shard_bounds(len(pixels), rank, world)
     if hi > lo:
-        amp, phase, st = plan.run(pixels[lo:hi])
+        amp, phase, st = plan.run(pixels[order[lo:hi]])
     else:
         amp, phase, st = np.zeros((len(freqs), 0)), np.zeros((len(freqs), 0)), 0
     _lib.raise_on_status(st, strict)
@@ -250,8 +253,10 @@ def holo_map(freqs, res=51, sweep=100, shift=0, n_scan=100, n_scan_rx=None, p_rx
     if full is None:
         return None
     full = full.cpu().numpy()
+    out = np.empty_like(full)
+    out[order] = full
     nf = len(freqs)
-    return pixels, np.ascontiguousarray(full[:, :nf].T), np.ascontiguousarray(full[:, nf:].T)
+    return pixels, np.ascontiguousarray(out[:, :nf].T), np.ascontiguousarray(out[:, nf:].T)
 
 
 def receiver_offset_sweep(freq, rx_positions, res=51, sweep=100, shift=0, n_scan=100, device=None, strict=False):
@@ -443,10 +448,11 @@ class FarFieldPlan:
 
 
 def mirror_pair_order(pixels):
-    """Permutation of an (az, el) pixel list that puts (+az, el) next to (-az, el) (|az| compared to 1e-15 rad,
-    np.linspace grids are symmetric only to ~1e-19)."""
+    """Permutation of an (az, el) -- or near-field (x, z) -- pixel list that puts (+az, el) next to (-az, el)
+    (|az| compared to 1e-15, np.linspace grids are not symmetric to the bit)."""
     pixels = np.asarray(pixels, dtype=np.float64)
-    key = np.round(np.abs(pixels[:, 0]) / 1e-15)
+    scale = float(np.max(np.abs(pixels[:, 0]))) if len(pixels) else 0.0
+    key = np.round(np.abs(pixels[:, 0]) * (1e9 / scale if scale > 0 else 1.0))     # 1e-9 of the map's extent
     return np.lexsort((np.signbit(pixels[:, 0]), pixels[:, 1], key))
 
 
