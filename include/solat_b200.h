@@ -122,7 +122,8 @@ SOLAT_API int solat_nf_map_device(solat_nf_plan *plan, const double *d_src_xz, i
  * of the per-pixel integral (scripts/holo_sim.py:157-176) for a receiver-offset sweep.                          */
 SOLAT_API int solat_nf_rx_fields(solat_ctx *ctx, const solat_nf_geom *g, const double *p_rx, int nrx, const double *theta, int nth,
                        const double *phi, int nph, double *opl, double *amp, int *status);
-/* traced rays per pixel after culling (for FLOP accounting) */
+/* (near-field maps share a trace between the source positions (x, z) and (-x, z) the same way)
+ * traced rays per pixel after culling (for FLOP accounting) */
 SOLAT_API int solat_nf_plan_active_rays(const solat_nf_plan *plan);
 /* number of output channels nrx * nfreq */
 SOLAT_API int solat_nf_plan_channels(const solat_nf_plan *plan);
@@ -152,7 +153,12 @@ SOLAT_API int solat_ff_project(solat_ctx *ctx, const double *sim17, int n_pts, c
  * replaces the worker body scripts/ff_sim.py:204-221 for a list of (az, el) pixels, with the
  * single-panel / zero-error panel model (adjuster offsets are identically zero in ff_sim.py:61-62):
  * per pixel  sum_cells  exp(i k L_winner/1e3) * e_rec[cell] / M^2 , winner = highest ray index
- * landing in the cell (last write wins, ffl:28).  azel is [npix][2] = (az, el).                  */
+ * landing in the cell (last write wins, ffl:28).  azel is [npix][2] = (az, el).
+ * How the kernels spend less than the reference: rays the projection would skip
+ * (ffl:19) are not traced, and when the telescope, the fan (phi symmetric about pi/2) and therefore the
+ * physics are symmetric under x -> -x, the pixels (az, el) and (-az, el) of one call share one trace;
+ * a pixel's value does not depend on which other pixels are in the call.  Calls on one plan must be
+ * stream-ordered by the caller.                                                                   */
 SOLAT_API int solat_ff_plan_create(solat_ctx *ctx, const solat_ff_geom *g, const double *theta, int nth, const double *phi,
                          int nph, const double *data_x, const double *data_y, const double *e_rec_reim, int M,
                          double k, solat_ff_plan **plan);
