@@ -706,7 +706,7 @@ __global__ void ff_project_fill_kernel(const double* sim, int n_pts, const int* 
 // 256 threads x 3 CTAs, 384 x 2 (grids up to ~118 x 118), 768 x 1 (up to 168 x 168).
 constexpr int FF_T = SOLAT_FF_T;
 constexpr int FF_WQ = 64;            // per-warp queue capacity
-constexpr int FF_MAX_ROWS = 4096;    // phi rows the interval walk keeps on chip; larger fans take the queue walk
+constexpr int FF_MAX_ROWS = 1024;    // phi rows the interval walk keeps on chip (FF_ROW_K intervals each); larger fans take the queue walk
 struct FfMapParams {
     AngleTabs ang;
     solat_ff_geom g;
@@ -777,7 +777,7 @@ __device__ __forceinline__ void ff_prefix_rows(int* row_pre, int nph, int lane)
 // latency bound: one thread builds the frames, one thread per phi row finds its interval): frames, and for the
 // interval walk the per-row ray intervals already shrunk by the focal-position predictor, as a record in global
 // memory the map kernel copies into its shared memory.  Record: FfFrames | int queue_walk, n_list, pad[2] |
-// row_lo[nph] | row_pre[nph + 1].
+// row_lo[K nph] | row_pre[K nph + 1]  (K = FF_ROW_K intervals per phi row: virtual row K j + k).
 constexpr int FF_PREP_T = 64;     // = FF_PRED_SAMPLES; 12 CTAs per SM keep every pixel of a 41 x 41 map in flight
 constexpr size_t FF_REC_FRAMES = ((sizeof(FfFrames) + 15) / 16) * 16;
 constexpr size_t FF_REC_HEAD = FF_REC_FRAMES + 16;
@@ -789,20 +789,21 @@ struct FfPrepParams {
     const int* counters;
     int item0;               // pair mode: CTA b handles item item0 + b (its record is record b)
     int rows, prefilter;
-    float gx_max, gy_max;
+    FfGrid grid;             // edges of the E_rec grid (ff_pred_row_keep)
     unsigned char* rec;
     size_t stride;
     int* clear_status;       // host-buffer entries: the call's own status word (8-byte slot behind the results), zeroed here
 };
-static size_t ff_rec_stride(int rows_nph) { return FF_REC_HEAD + (rows_nph ? ((2 * (size_t)rows_nph + 1) * sizeof(int) + 15) / 16 * 16 : 0); }
+static size_t ff_rec_stride(int rows_nph) { return FF_REC_HEAD + (rows_nph ? ((2 * (size_t)FF_ROW_K * rows_nph + 1) * sizeof(int) + 15) / 16 * 16 : 0); }
 
 __global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
 {
     constexpr int FF_T = FF_PREP_T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FfFrames* fr = reinterpret_cast<FfFrames*>(smem_raw);
-    int* row_lo = reinterpret_cast<int*>(smem_raw + FF_REC_FRAMES);        // [nph] first ray of a row
-    int* row_pre = row_lo + (q.rows ? q.ang.nph : 0);                      // [nph + 1] rays before the row
+    const int nvr = FF_ROW_K * q.ang.nph;                                  // virtual rows: FF_ROW_K intervals per phi row
+    int* row_lo = reinterpret_cast<int*>(smem_raw + FF_REC_FRAMES);        // [nvr] first ray of an interval
+    int* row_pre = row_lo + (q.rows ? nvr : 0);                            // [nvr + 1] rays before the interval
     __shared__ int s_queue_walk;
     __shared__ FfPred s_pred;
     __shared__ double s_psum[2][12];
@@ -824,30 +825,30 @@ __global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
     __syncthreads();
     const int nth = q.ang.nth;
     if (q.rows) {
-        // accepted interval [lo, hi) of every phi row
+        // accepted interval [lo, hi) of every phi row: interval 0 of the row, the others empty
         for (int j = tid; j < q.ang.nph; j += FF_T) {
             int lo, hi;
             if (!ff_row_interval(sC, g, *fr, q.ang.st, q.ang.ct, nth, __ldg(q.ang.sp + j), __ldg(q.ang.cp + j), lo, hi))
                 s_queue_walk = 1;                                // the row does not stay on one side of the plane's horizon
-            row_lo[j] = lo;
-            row_pre[j + 1] = hi - lo;
+            for (int k = 0; k < FF_ROW_K; k++) { row_lo[FF_ROW_K * j + k] = lo; row_pre[FF_ROW_K * j + k + 1] = k ? 0 : hi - lo; }
         }
         __syncthreads();
-        if (warp == 0) ff_prefix_rows(row_pre, q.ang.nph, lane);
+        if (warp == 0) ff_prefix_rows(row_pre, nvr, lane);
         __syncthreads();
         // focal-position predictor of this pixel (see FfPred): sample rays spread over the dense accepted list
-        const int n_list = row_pre[q.ang.nph];
+        const int n_list = row_pre[nvr];
         if (q.prefilter && !s_queue_walk && n_list >= 512) {
             float su = 0.0f, sv = 0.0f;
             double sX = 0.0, sZ = 0.0;
             if (tid < FF_PRED_SAMPLES) {
                 const int v = (int)((long long)tid * (n_list - 1) / (FF_PRED_SAMPLES - 1));
-                int a = 0, b = q.ang.nph - 1;              // last row with row_pre[row] <= v
+                int a = 0, b = nvr - 1;                    // last interval with row_pre[.] <= v
                 while (a < b) {
                     const int m = (a + b + 1) >> 1;
                     if (row_pre[m] <= v) a = m; else b = m - 1;
                 }
                 const int i = row_lo[a] + (v - row_pre[a]);
+                a /= FF_ROW_K;                             // its phi row
                 const vec3 d = launch_dir(__ldg(q.ang.st + i), __ldg(q.ang.ct + i), __ldg(q.ang.sp + a), __ldg(q.ang.cp + a));
                 vec3 Pa;
                 double t_ap, opl, fx, fz;
@@ -886,22 +887,23 @@ __global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
             if (tid == 0) ff_pred_set_margin(s_pred, fmaxf(s_pres[0], s_pres[1]));
             __syncthreads();
             if (s_pred.on) {
-                // keep only the rays the predictor cannot rule out: per row again one interval
-                // (batches from the last row down: a batch replaces entries (j0, j0 + FF_T] and the next one reads [.., j0])
+                // keep only the rays that can matter to the pixel or its mirror pixel (ff_pred_row_keep): up to FF_ROW_K
+                // intervals per row.  (Batches from the last row down: a batch replaces entries (K j0, K (j0 + FF_T)] and
+                // the next one reads [.., K j0].)
                 for (int j0 = ((q.ang.nph - 1) / FF_T) * FF_T; j0 >= 0; j0 -= FF_T) {
                     const int j = j0 + tid;
-                    int lo = 0, hi = 0;
+                    int klo[FF_ROW_K], kcnt[FF_ROW_K];
                     if (j < q.ang.nph) {
-                        lo = row_lo[j]; hi = lo + (row_pre[j + 1] - row_pre[j]);
-                        // a ray is kept if the pixel or its mirror pixel (focal x negated, centre z shifted) can use it
-                        ff_pred_shrink(s_pred, q.ang.stf, __ldg(q.ang.cpf + j), __ldg(q.ang.spf + j), q.gx_max, q.gy_max, !need_neg,
-                                       !need_pos, need_neg ? 0.1f * fabsf((float)(fr->centre[2] - fr->centre_mz)) : 0.0f, lo, hi);
+                        const int lo = row_lo[FF_ROW_K * j], hi = lo + (row_pre[FF_ROW_K * j + 1] - row_pre[FF_ROW_K * j]);
+                        ff_pred_row_keep(s_pred, q.ang.stf, __ldg(q.ang.cpf + j), __ldg(q.ang.spf + j), q.grid, need_pos, need_neg,
+                                         0.1f * (float)(fr->centre[2] - fr->centre_mz), lo, hi, klo, kcnt);
                     }
                     __syncthreads();                         // every count of this batch was read before any is replaced
-                    if (j < q.ang.nph) { row_lo[j] = lo; row_pre[j + 1] = hi - lo; }
+                    if (j < q.ang.nph)
+                        for (int k = 0; k < FF_ROW_K; k++) { row_lo[FF_ROW_K * j + k] = klo[k]; row_pre[FF_ROW_K * j + k + 1] = kcnt[k]; }
                 }
                 __syncthreads();
-                if (warp == 0) ff_prefix_rows(row_pre, q.ang.nph, lane);
+                if (warp == 0) ff_prefix_rows(row_pre, nvr, lane);
                 __syncthreads();
             }
         }
@@ -913,10 +915,10 @@ __global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
         int* dst = reinterpret_cast<int*>(rec);
         for (int i = tid; i < (int)(sizeof(FfFrames) / sizeof(int)); i += FF_T) dst[i] = src[i];
         int* head = reinterpret_cast<int*>(rec + FF_REC_FRAMES);
-        if (tid == 0) { head[0] = s_queue_walk; head[1] = q.rows ? row_pre[q.ang.nph] : 0; head[2] = head[3] = 0; }
+        if (tid == 0) { head[0] = s_queue_walk; head[1] = q.rows ? row_pre[nvr] : 0; head[2] = head[3] = 0; }
         if (q.rows) {
             int* rows = reinterpret_cast<int*>(rec + FF_REC_HEAD);
-            for (int i = tid; i < 2 * q.ang.nph + 1; i += FF_T) rows[i] = row_lo[i];   // row_lo and row_pre are contiguous
+            for (int i = tid; i < 2 * nvr + 1; i += FF_T) rows[i] = row_lo[i];   // row_lo and row_pre are contiguous
         }
     }
 }
@@ -933,8 +935,9 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     int* queues = reinterpret_cast<int*>(win + (q.items ? 2 : 1) * cells);   // [FF_WARPS][FF_WQ]
     double* s_gx = reinterpret_cast<double*>(queues + FF_WARPS * FF_WQ);   // [M] data_x[0, :]
     double* s_gy = s_gx + q.grid.M;                                        // [M] data_y[:, 0] when all columns agree
-    int* row_lo = reinterpret_cast<int*>(s_gy + q.grid.M);                 // [nph] first ray to trace of a row
-    int* row_pre = row_lo + (q.rows ? q.ang.nph : 0);                      // [nph + 1] rays to trace before the row
+    const int nvr = FF_ROW_K * q.ang.nph;                                  // virtual rows: FF_ROW_K intervals per phi row
+    int* row_lo = reinterpret_cast<int*>(s_gy + q.grid.M);                 // [nvr] first ray to trace of an interval
+    int* row_pre = row_lo + (q.rows ? nvr : 0);                            // [nvr + 1] rays to trace before the interval
     __shared__ int s_queue_walk;
     __shared__ double s_t2e[9];
 
@@ -951,7 +954,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
         if (tid == 0) s_queue_walk = __ldg(reinterpret_cast<const int*>(rec + FF_REC_FRAMES));
         if (!PANEL && q.rows) {
             const int* rows = reinterpret_cast<const int*>(rec + FF_REC_HEAD);
-            for (int i = tid; i < 2 * q.ang.nph + 1; i += FF_T) row_lo[i] = __ldg(rows + i);
+            for (int i = tid; i < 2 * nvr + 1; i += FF_T) row_lo[i] = __ldg(rows + i);
         }
     }
     for (int c = tid; c < (q.items ? 2 : 1) * cells; c += FF_T) win[c] = 0ull;
@@ -982,14 +985,14 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     // into row / column 0, ffl:22-23) settle at once -- the later, smaller ray indices only read the cell and move on.
     int chunk = (n_rays + 31) / 32 - 1 - warp;
     // interval walk: every warp owns a contiguous share of the pixel's dense list of rays to trace, 32 per step
-    const int n_acc = queue_walk ? 0 : row_pre[q.ang.nph];
-    int row = max(q.ang.nph - 1, 0);
+    const int n_acc = queue_walk ? 0 : row_pre[nvr];
+    int row = max(nvr - 1, 0);
     // warp w owns rays [v_bot, v_top] of the list
     const int per_warp = (n_acc + FF_WARPS - 1) / FF_WARPS;
     const int v_bot = min(warp * per_warp, n_acc);
     int v_top = min(v_bot + per_warp, n_acc) - 1;
     if (!queue_walk && v_top >= v_bot) {                  // row of the warp's first ray: last row with row_pre[row] <= v_top
-        int a = 0, b = q.ang.nph - 1;
+        int a = 0, b = nvr - 1;
         while (a < b) {
             const int m = (a + b + 1) >> 1;
             if (row_pre[m] <= v_top) a = m; else b = m - 1;
@@ -1003,7 +1006,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             const int v = v_top - lane;
             if (v >= v_bot) {
                 while (row_pre[row] > v) --row;           // the walk only moves down the list, so does the row cursor
-                r0 = row * nth + row_lo[row] + (v - row_pre[row]);
+                r0 = (row / FF_ROW_K) * nth + row_lo[row] + (v - row_pre[row]);
             }
             v_top -= 32;
         } else {
@@ -1179,7 +1182,7 @@ static size_t ff_map_smem(int M, int rows_nph, int threads, int tables)
 {
     const size_t cells = (size_t)M * M * tables;
     return ((sizeof(FfFrames) + 15) / 16) * 16 + cells * sizeof(unsigned long long) + (size_t)(threads / 32) * FF_WQ * sizeof(int) +
-           2 * (size_t)M * sizeof(double) + (rows_nph ? (2 * (size_t)rows_nph + 1) * sizeof(int) : 0);
+           2 * (size_t)M * sizeof(double) + (rows_nph ? (2 * (size_t)FF_ROW_K * rows_nph + 1) * sizeof(int) : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1746,6 +1749,9 @@ static FfGrid make_grid(const double* data_x, const double* data_y, int M, const
     double a = data_x[0], b = data_y[0];
     for (int i = 1; i < M; i++) { a = fmax(a, data_x[i]); b = fmax(b, data_y[(size_t)i * M]); }   // ffl:19
     G.gx_max = a; G.gy_max = b;
+    a = data_x[0]; b = data_y[0];
+    for (int i = 1; i < M; i++) { a = fmin(a, data_x[i]); b = fmin(b, data_y[(size_t)i * M]); }
+    G.gx_min = a; G.gy_min = b;
     const double sx = data_x[M - 1] - data_x[0], sy = data_y[(size_t)(M - 1) * M] - data_y[0];
     G.inv_dx = (M > 1 && sx > 0) ? (float)((M - 1) / sx) : 0.0f;   // first guess of searchsorted; the fix-up makes it exact
     G.inv_dy = (M > 1 && sy > 0) ? (float)((M - 1) / sy) : 0.0f;
@@ -1846,7 +1852,7 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cud
     if (int rc = p->rec.reserve((size_t)chunk * stride)) return rc;
     FfPrepParams pq;
     pq.ang = p->ang.tabs; pq.g = p->g; pq.rows = rows; pq.prefilter = rows ? p->prefilter : 0;
-    pq.gx_max = (float)p->grid.gx_max; pq.gy_max = (float)p->grid.gy_max; pq.rec = p->rec.p; pq.stride = stride;
+    pq.grid = p->grid; pq.rec = p->rec.p; pq.stride = stride;
     pq.items = nullptr; pq.counters = nullptr; pq.item0 = 0;
     q.items = nullptr; q.counters = nullptr; q.item0 = 0;
     if (pairs) {
@@ -1882,7 +1888,7 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cud
         }
         pq.items = q.items = p->items.p; pq.counters = q.counters = ints;
     }
-    const size_t prep_smem = FF_REC_FRAMES + (rows ? (2 * (size_t)p->ang.tabs.nph + 1) * sizeof(int) : 0);
+    const size_t prep_smem = FF_REC_FRAMES + (rows ? (2 * (size_t)FF_ROW_K * p->ang.tabs.nph + 1) * sizeof(int) : 0);
     q.rows = rows; q.rec = p->rec.p; q.rec_stride = stride;
     const double* azel = q.azel;
     double *amp = q.amp, *phase = q.phase;

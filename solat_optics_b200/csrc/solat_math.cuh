@@ -956,7 +956,8 @@ SOLAT_HD void ff_ray_lean(const Coef& C, const FfFrames& f, const vec3t<R>& d, R
 // the rest is aberration).  The fused map fits that affine map per pixel to a sample of exactly traced rays, measures
 // its worst error on the sample, and uses it ONLY to drop rays that the reference's projection would skip anyway
 // (ffl:19: x > max(data_x[0, :]) or y > max(data_y[:, 0])) when they miss the high edge of the E_rec grid by more
-// than 5 x that error + 2 mm; every other ray is traced in FP64 and binned exactly.  With the +-5 cm grid of
+// than 5 x that error + 2 mm (and rays certain to pile into cell (0, 0), of which one per row is kept, see
+// ff_pred_row_keep); every other ray is traced in FP64 and binned exactly.  With the +-5 cm grid of
 // ff_sim.py about half of the accepted rays land beyond the grid.
 constexpr float FF_PRED_SCALE = 2.0e4f;   // launch direction cosines of the fan are ~5e-5
 constexpr int FF_PRED_SAMPLES = 64;
@@ -994,35 +995,6 @@ SOLAT_HD void ff_pred_set_margin(FfPred& p, float worst_mm)
     p.on = p.on && worst_mm < 50.0f;     // NaN compares false
     p.margin_cm = 0.1f * (5.0f * worst_mm + 2.0f);
 }
-// Rays of one phi row [lo, hi) the predictor keeps.  Along a row u and v are the row constants cos(phi), sin(phi)
-// times sin(theta_i), so the predicted x and z are monotone in i (sin(theta) is monotone on the fans the interval
-// walk accepts, and so are its single-precision table, the product and the FMA): the rays beyond one edge of the
-// grid are a prefix or a suffix of the row and the kept rays are again ONE interval, found by bisection.
-// cull_x_hi: drop rays beyond the high x edge (the pixel itself needs them not); cull_x_lo: the same for the mirror
-// pixel, whose focal x is the negative of this one's (ff_map_kernel); extra_z_cm widens the z margin (offset between
-// the two pixels' focal centres).
-SOLAT_HD void ff_pred_shrink(const FfPred& p, const float* stf, float cpf, float spf, float gx_max_cm, float gy_max_cm, bool cull_x_hi,
-                             bool cull_x_lo, float extra_z_cm, int& lo, int& hi)
-{
-    for (int k = 0; k < 3 && lo < hi; k++) {
-        if ((k == 0 && !cull_x_hi) || (k == 1 && !cull_x_lo)) continue;
-        const float* c = k == 2 ? p.cz : p.cx;
-        const float sgn = k == 1 ? -0.1f : 0.1f;
-        const float slope = fmaf(c[1], cpf, c[2] * spf), c0 = c[0];
-        const float edge = (k == 2 ? gy_max_cm + extra_z_cm : gx_max_cm) + p.margin_cm;
-        auto miss = [&](int i) { return sgn * fmaf(stf[i] * FF_PRED_SCALE, slope, c0) > edge; };
-        const bool m_lo = miss(lo), m_hi = miss(hi - 1);
-        if (m_lo && m_hi) { hi = lo; return; }
-        if (!m_lo && !m_hi) continue;
-        int a = lo, b = hi - 1;                 // miss(a) != miss(b): bisect for the crossing
-        while (a + 1 < b) {
-            const int m = (a + b) >> 1;
-            if (miss(m) == m_lo) a = m; else b = m;
-        }
-        if (m_lo) lo = b; else hi = b;
-    }
-}
-
 // np.searchsorted(a, v, side='left') over a strided sorted array
 SOLAT_HD int searchsorted_left(const double* a, int n, int stride, double v)
 {
@@ -1155,6 +1127,7 @@ struct FfGrid {
     int M, gy_cs, gy_rs;   // (1, M) for the full array; (0, 1) when every column is the same and gy holds just one
     int y_uniform;         // host: all columns of data_y are identical (a kernel may then stage one column on chip)
     double gx_max, gy_max; // ffl:19: rays beyond these are skipped
+    double gx_min, gy_min; // min(data_x[0, :]), min(data_y[:, 0]): rays below both pile into cell (0, 0)  (ffl:22-23)
     float inv_dx, inv_dy;  // (M-1)/(last-first) of gx and of gy[:,0]; 0 when not usable as a guess
 };
 SOLAT_HD int ff_cell(double fx_mm, double fz_mm, const FfGrid& G)
@@ -1187,6 +1160,103 @@ SOLAT_HD double ff_key_opl(unsigned long long key, double base, double unit)
     const long long qi = (long long)(key & ((1ull << FF_KEY_SHIFT) - 1)) - (1ll << 43);
     return base + (double)qi * unit;
 }
+
+// Which rays of one phi row [lo, hi) does the map have to trace?  A ray is of use to the pixel itself (`pos`) unless
+// the predictor puts it beyond the high edge of the E_rec grid (ffl:19 skips it) or below BOTH low edges: such a ray
+// lands in cell (0, 0) for certain (ffl:22-23: searchsorted returns 0 below the first element), and of all the rays
+// of the row that do, only the last one -- the highest ray index -- can hold the cell (ffl:28).  The same for the
+// mirror pixel (`neg`: focal x negated, z shifted by dz_neg_cm, and its ray index grows with i as well).  Kept: the
+// runs of useful rays plus those two corner candidates, as at most FF_ROW_K intervals (more: the whole row is kept).
+// All thresholds carry the predictor's margin.  Along a row the predicted x and z are the row constants times
+// sin(theta_i) (monotone in i on the fans the interval walk accepts, and so are the single-precision table, the
+// product and the FMA), so each of the six comparisons changes its answer at most once along the row: the change
+// points are found by bisection and the row is classified segment by segment, with the very same expressions.
+constexpr int FF_ROW_K = 4;
+SOLAT_HD int ff_pred_row_keep(const FfPred& p, const float* stf, float cpf, float spf, const FfGrid& G, bool need_pos, bool need_neg,
+                              float dz_neg_cm, int lo, int hi, int* out_lo, int* out_cnt)
+{
+    for (int k = 0; k < FF_ROW_K; k++) { out_lo[k] = lo; out_cnt[k] = 0; }
+    if (hi <= lo) return 0;
+    const float kx = fmaf(p.cx[1], cpf, p.cx[2] * spf), kz = fmaf(p.cz[1], cpf, p.cz[2] * spf), m = p.margin_cm;
+    const float x_hi = (float)G.gx_max + m, z_hi = (float)G.gy_max + m, x_lo = (float)G.gx_min - m, z_lo = (float)G.gy_min - m;
+    const float ez = fabsf(dz_neg_cm);
+    // the six comparisons of ray i (NaN predictions compare false everywhere: the ray counts as useful)
+    auto test = [&](int i, int which) {
+        const float s = stf[i] * FF_PRED_SCALE;
+        const float x = 0.1f * fmaf(s, kx, p.cx[0]), z = 0.1f * fmaf(s, kz, p.cz[0]);
+        switch (which) {
+            case 0: return x > x_hi;
+            case 1: return -x > x_hi;
+            case 2: return z > z_hi + ez;
+            case 3: return x < x_lo;
+            case 4: return -x < x_lo;
+            default: return z < z_lo - ez;
+        }
+    };
+    // change points: first index whose answer differs from that of `lo` (hi if none)
+    int cut[8];
+    cut[0] = lo; cut[7] = hi;
+    for (int w = 0; w < 6; w++) {
+        const bool first = test(lo, w);
+        int a = lo, b = hi;                       // answer(a) == first; b = hi or answer(b) != first
+        if (test(hi - 1, w) == first) { cut[1 + w] = hi; continue; }
+        b = hi - 1;
+        while (a + 1 < b) {
+            const int mid = (a + b) >> 1;
+            if (test(mid, w) == first) a = mid; else b = mid;
+        }
+        cut[1 + w] = b;
+    }
+    for (int a = 1; a < 8; a++)                   // sort the eight cut points
+        for (int b = a; b > 0 && cut[b] < cut[b - 1]; b--) { const int t = cut[b]; cut[b] = cut[b - 1]; cut[b - 1] = t; }
+    int n = 0, run = -1, cand_pos = -1, cand_neg = -1;
+    bool overflow = false;
+    for (int sgm = 0; sgm < 7; sgm++) {
+        const int i0 = cut[sgm], i1 = cut[sgm + 1];
+        if (i1 <= i0) continue;
+        const bool beyond_z = test(i0, 2), corner_z = test(i0, 5);
+        const bool pos_corner = need_pos && test(i0, 3) && corner_z, neg_corner = need_neg && test(i0, 4) && corner_z;
+        const bool pos_use = need_pos && !test(i0, 0) && !beyond_z && !pos_corner;
+        const bool neg_use = need_neg && !test(i0, 1) && !beyond_z && !neg_corner;
+        if (pos_corner) cand_pos = i1 - 1;
+        if (neg_corner) cand_neg = i1 - 1;
+        if (pos_use || neg_use) {
+            if (run < 0) run = i0;
+        } else if (run >= 0) {
+            if (n < FF_ROW_K) { out_lo[n] = run; out_cnt[n] = i0 - run; }
+            ++n; run = -1;
+        }
+    }
+    if (run >= 0) {
+        if (n < FF_ROW_K) { out_lo[n] = run; out_cnt[n] = hi - run; }
+        ++n;
+    }
+    // the corner candidates, unless a kept run holds them already
+    for (int c = 0; c < 2; c++) {
+        const int i = c ? cand_neg : cand_pos;
+        if (i < 0 || (c == 1 && cand_neg == cand_pos)) continue;
+        bool inside = false;
+        for (int k = 0; k < n && k < FF_ROW_K; k++) inside = inside || (i >= out_lo[k] && i < out_lo[k] + out_cnt[k]);
+        if (inside) continue;
+        if (n < FF_ROW_K) { out_lo[n] = i; out_cnt[n] = 1; }
+        ++n;
+    }
+    overflow = n > FF_ROW_K;
+    if (overflow) {
+        out_lo[0] = lo; out_cnt[0] = hi - lo;
+        for (int k = 1; k < FF_ROW_K; k++) { out_lo[k] = lo; out_cnt[k] = 0; }
+        return 1;
+    }
+    // ascending order of the intervals (the walk's row cursor only moves one way): insertion sort of <= 4 entries
+    for (int a = 1; a < n; a++)
+        for (int b = a; b > 0 && out_lo[b] < out_lo[b - 1]; b--) {
+            const int tl = out_lo[b], tc = out_cnt[b];
+            out_lo[b] = out_lo[b - 1]; out_cnt[b] = out_cnt[b - 1];
+            out_lo[b - 1] = tl; out_cnt[b - 1] = tc;
+        }
+    return n;
+}
+
 
 // ------------------------------------------------------------------------------------------
 // regrid (ray_trace_int.py:1385-1440): one line of the separable interpolating bicubic spline.

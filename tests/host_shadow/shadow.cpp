@@ -2,6 +2,7 @@
 // EXACT per-ray source the kernels run can be checked against the golden fixtures in a container that
 // has no GPU.  Test infrastructure only (built into tests/_build/, never shipped, never loaded by the
 // product package).  The loops here stand in for the CUDA grid; they carry no arithmetic of their own.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -120,6 +121,8 @@ static FfGrid make_grid(const double* gx_full, const double* gy, int M)
 {
     FfGrid G;
     G.gx = gx_full; G.gy = gy; G.M = M; G.gy_cs = 1; G.gy_rs = M; G.y_uniform = 0;
+    G.gx_min = gx_full[0]; G.gy_min = gy[0];
+    for (int i = 1; i < M; i++) { G.gx_min = fmin(G.gx_min, gx_full[i]); G.gy_min = fmin(G.gy_min, gy[(size_t)i * M]); }
     G.gx_max = gx_full[0]; G.gy_max = gy[0];
     for (int i = 0; i < M; i++) { G.gx_max = fmax(G.gx_max, gx_full[i]); G.gy_max = fmax(G.gy_max, gy[(size_t)i * M]); }
     const double sx = gx_full[M - 1] - gx_full[0], sy = gy[(size_t)(M - 1) * M] - gy[0];
@@ -299,6 +302,14 @@ API int shadow_ff_pred_check(const double* geo, const double* th, int nth, const
     FfGeom g = unpack(geo);
     FfFrames f;
     ff_build_frames(K_COEF, g, el, az, f);
+    // uniform 51-point E_rec axes [-g_max, g_max]
+    const int M = 51;
+    std::vector<double> ax(M), ay(M);
+    for (int i = 0; i < M; i++) { ax[i] = -gx_max + 2.0 * gx_max * i / (M - 1); ay[i] = -gy_max + 2.0 * gy_max * i / (M - 1); }
+    FfGrid G;
+    G.gx = ax.data(); G.gy = ay.data(); G.M = M; G.gy_cs = 0; G.gy_rs = 1; G.y_uniform = 1;
+    G.gx_max = ax[M - 1]; G.gy_max = ay[M - 1]; G.gx_min = ax[0]; G.gy_min = ay[0];
+    G.inv_dx = gx_max > 0 ? (float)((M - 1) / (2.0 * gx_max)) : 0.0f; G.inv_dy = gy_max > 0 ? (float)((M - 1) / (2.0 * gy_max)) : 0.0f;
     std::vector<double> st(nth), ct(nth);
     for (int i = 0; i < nth; i++) { st[i] = sin(th[i]); ct[i] = cos(th[i]); }
     std::vector<int> rays;
@@ -342,31 +353,114 @@ API int shadow_ff_pred_check(const double* geo, const double* th, int nth, const
     }
     double worst = 0.0;
     long dropped = 0, wrong = 0;
-    if (p.on) {
-        std::vector<float> stf(nth);
-        for (int i = 0; i < nth; i++) stf[i] = (float)st[i];
-        size_t at = 0;
-        for (int j = 0; j < nph; j++) {
-            int lo, hi;
-            ff_row_interval(K_COEF, g, f, st.data(), ct.data(), nth, sin(ph[j]), cos(ph[j]), lo, hi);
-            int klo = lo, khi = hi;
-            ff_pred_shrink(p, stf.data(), (float)cos(ph[j]), (float)sin(ph[j]), (float)gx_max, (float)gy_max, true, false, 0.0f, klo, khi);
-            if (klo < lo || khi > hi || klo > khi) return 0;          // must stay inside the accepted interval
-            for (int i = lo; i < hi; i++, at++) {
-                float u, v, x, z;
-                double X, Z;
-                trace(j * nth + i, u, v, X, Z);
-                ff_pred_eval(p, u, v, x, z);
-                worst = fmax(worst, fmax(fabs(x - X), fabs(z - Z)));
-                if (i < klo || i >= khi) {
-                    ++dropped;
-                    if (!(div10(X) > gx_max || div10(Z) > gy_max)) ++wrong;
-                }
+    if (p.on)
+        for (int r : rays) {
+            float u, v, x, z;
+            double X, Z;
+            trace(r, u, v, X, Z);
+            ff_pred_eval(p, u, v, x, z);
+            worst = fmax(worst, fmax(fabs(x - X), fabs(z - Z)));
+            // rays the predictor calls "beyond the high edge" / "below both low edges" must be so
+            const float xc = 0.1f * x, zc = 0.1f * z;
+            if (xc > (float)gx_max + p.margin_cm || zc > (float)gy_max + p.margin_cm) {
+                ++dropped;
+                if (!(div10(X) > gx_max || div10(Z) > gy_max)) ++wrong;
             }
+            if (gx_max > 0 && xc < (float)G.gx_min - p.margin_cm && zc < (float)G.gy_min - p.margin_cm && ff_cell(X, Z, G) != 0) ++wrong;
         }
-    }
     out4[0] = worst; out4[1] = worst_sample; out4[2] = (double)dropped; out4[3] = (double)wrong;
     return p.on ? n_acc : -n_acc;
+}
+
+// The ray selection of the fused map (row intervals, predictor, ff_pred_row_keep) against tracing every accepted ray:
+// winner tables (ray index per cell) of the pixel and of its mirror pixel from the kept rays only must equal the
+// tables from all rays.  E_rec axes: M points on [g_lo, g_hi] cm.  out: accepted rays, kept rays, cells that differ.
+API int shadow_ff_keep_check(const double* geo, const double* th, int nth, const double* ph, int nph, double el, double az, int M,
+                             double g_lo, double g_hi, int need_pos, int need_neg, double* out3)
+{
+    FfGeom g = unpack(geo);
+    FfFrames f;
+    ff_build_frames(K_COEF, g, el, az, f);
+    std::vector<double> ax(M);
+    for (int i = 0; i < M; i++) ax[i] = g_lo + (g_hi - g_lo) * i / (M - 1);
+    FfGrid G;
+    G.gx = ax.data(); G.gy = ax.data(); G.M = M; G.gy_cs = 0; G.gy_rs = 1; G.y_uniform = 1;
+    G.gx_max = G.gy_max = ax[M - 1]; G.gx_min = G.gy_min = ax[0];
+    G.inv_dx = G.inv_dy = (float)((M - 1) / (g_hi - g_lo));
+    std::vector<double> st(nth), ct(nth);
+    std::vector<float> stf(nth);
+    for (int i = 0; i < nth; i++) { st[i] = sin(th[i]); ct[i] = cos(th[i]); stf[i] = (float)st[i]; }
+    std::vector<int> lo(nph), hi(nph), rays;
+    for (int j = 0; j < nph; j++) {
+        ff_row_interval(K_COEF, g, f, st.data(), ct.data(), nth, sin(ph[j]), cos(ph[j]), lo[j], hi[j]);
+        for (int i = lo[j]; i < hi[j]; i++) rays.push_back(j * nth + i);
+    }
+    const int n_acc = (int)rays.size();
+    struct Hit { double X, Z, Zm; };
+    auto trace = [&](int r) {
+        const int i = r % nth, j = r / nth;
+        vec3 d = launch_dir(st[i], ct[i], sin(ph[j]), cos(ph[j])), Pa;
+        double t_ap, opl, fx, fz;
+        int rst;
+        ff_aperture(K_COEF, g, f, d, t_ap, Pa);
+        ff_ray_lean<double>(K_COEF, f, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);
+        Hit h = {fx - f.centre[0], fz - f.centre[2], fz - f.centre_mz};
+        return h;
+    };
+    // predictor exactly as ff_prep_kernel builds it
+    FfPred p;
+    p.on = 0;
+    if (n_acc >= 512) {
+        double S[12] = {0};
+        float us[FF_PRED_SAMPLES], vs[FF_PRED_SAMPLES];
+        double Xs[FF_PRED_SAMPLES], Zs[FF_PRED_SAMPLES];
+        for (int k = 0; k < FF_PRED_SAMPLES; k++) {
+            const int r = rays[(long)k * (n_acc - 1) / (FF_PRED_SAMPLES - 1)], i = r % nth, j = r / nth;
+            const Hit h = trace(r);
+            us[k] = stf[i] * FF_PRED_SCALE * (float)cos(ph[j]); vs[k] = stf[i] * FF_PRED_SCALE * (float)sin(ph[j]);
+            Xs[k] = h.X; Zs[k] = h.Z;
+            const double u = us[k], v = vs[k];
+            S[0] += 1; S[1] += u; S[2] += v; S[3] += u * u; S[4] += u * v; S[5] += v * v;
+            S[6] += Xs[k]; S[7] += u * Xs[k]; S[8] += v * Xs[k]; S[9] += Zs[k]; S[10] += u * Zs[k]; S[11] += v * Zs[k];
+        }
+        ff_pred_solve(S, p);
+        double worst = 0.0;
+        for (int k = 0; k < FF_PRED_SAMPLES; k++) {
+            float x, z;
+            ff_pred_eval(p, us[k], vs[k], x, z);
+            worst = fmax(worst, fmax(fabs(x - Xs[k]), fabs(z - Zs[k])));
+        }
+        ff_pred_set_margin(p, (float)worst);
+    }
+    std::vector<char> keep(nth * (size_t)nph, 0);
+    long n_kept = 0;
+    for (int j = 0; j < nph; j++) {
+        int klo[FF_ROW_K], kcnt[FF_ROW_K];
+        if (p.on) {
+            ff_pred_row_keep(p, stf.data(), (float)cos(ph[j]), (float)sin(ph[j]), G, need_pos != 0, need_neg != 0,
+                             0.1f * (float)(f.centre[2] - f.centre_mz), lo[j], hi[j], klo, kcnt);
+        } else {
+            for (int k = 0; k < FF_ROW_K; k++) { klo[k] = lo[j]; kcnt[k] = 0; }
+            kcnt[0] = hi[j] - lo[j];
+        }
+        for (int k = 0; k < FF_ROW_K; k++)
+            for (int i = klo[k]; i < klo[k] + kcnt[k]; i++) {
+                if (i < lo[j] || i >= hi[j] || keep[(size_t)j * nth + i]) return -1;      // outside the row or twice
+                keep[(size_t)j * nth + i] = 1; ++n_kept;
+            }
+    }
+    std::vector<int> wp_all(M * M, -1), wn_all(M * M, -1), wp_k(M * M, -1), wn_k(M * M, -1);
+    for (int r : rays) {
+        const int i = r % nth, j = r / nth, rm = (nph - 1 - j) * nth + i;
+        const Hit h = trace(r);
+        const int cp = need_pos ? ff_cell(h.X, h.Z, G) : -1, cn = need_neg ? ff_cell(-h.X, h.Zm, G) : -1;
+        if (cp >= 0) { wp_all[cp] = std::max(wp_all[cp], r); if (keep[r]) wp_k[cp] = std::max(wp_k[cp], r); }
+        if (cn >= 0) { wn_all[cn] = std::max(wn_all[cn], rm); if (keep[r]) wn_k[cn] = std::max(wn_k[cn], rm); }
+    }
+    long diff = 0;
+    for (int c = 0; c < M * M; c++) diff += (wp_all[c] != wp_k[c]) + (wn_all[c] != wn_k[c]);
+    out3[0] = n_acc; out3[1] = (double)n_kept; out3[2] = (double)diff;
+    return p.on;
 }
 
 // one far-field pixel, zero-error single-panel model (fused-map semantics)

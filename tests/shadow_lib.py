@@ -123,6 +123,15 @@ def ff_pred_check(geo, th, ph, el, az, gx_max, gy_max):
     return nv, o[0], o[1], int(o[2]), int(o[3])
 
 
+def ff_keep_check(geo, th, ph, el, az, m, g_lo, g_hi, need_pos=True, need_neg=True):
+    """-> (predictor on, accepted rays, kept rays, winner-table cells that differ between kept-only and all rays)"""
+    g, gp = D(geo); th, thp = D(th); ph, php = D(ph)
+    o = np.zeros(3)
+    on = lib().shadow_ff_keep_check(gp, thp, ci(th.size), php, ci(ph.size), cd(el), cd(az), ci(m), cd(g_lo), cd(g_hi),
+                                    ci(int(need_pos)), ci(int(need_neg)), o.ctypes.data_as(dp))
+    return on, int(o[0]), int(o[1]), int(o[2])
+
+
 def regrid(field, n_new):
     f, fp = D(field)
     out = np.zeros((n_new, n_new))

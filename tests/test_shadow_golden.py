@@ -229,9 +229,10 @@ def test_ff_row_intervals_equal_the_per_ray_aperture_test(shadow, oracle):
 
 def test_ff_focal_predictor_is_conservative(shadow, oracle):
     """The fused far-field map drops rays before the FP64 trace when an affine predictor of the focal-plane position
-    (fitted per pixel to 64 exactly traced rays) puts them beyond the high edge of the E_rec grid by more than
-    5 x its worst sample error + 2 mm.  A dropped ray must be one the exact comparison (ffl:19) skips: checked on
-    every accepted ray for on- and far-off-axis pixels, three focal offsets, small and large fans, four grid sizes."""
+    (fitted per pixel to 64 exactly traced rays) puts them beyond the high edge of the E_rec grid -- or below both
+    low edges -- by more than 5 x its worst sample error + 2 mm.  Such a ray must be one the exact comparison
+    (ffl:19) skips, resp. one that lands in cell (0, 0): checked on every accepted ray for on- and far-off-axis
+    pixels, three focal offsets, small and large fans, four grid sizes."""
     ratio = 0.0
     for n in (100, 40, 317):
         th, phi = gu.ff_fan(n)
@@ -251,3 +252,25 @@ def test_ff_focal_predictor_is_conservative(shadow, oracle):
     # tiny fans: predictor off
     th, phi = gu.ff_fan(12)
     assert shadow.ff_pred_check(oracle.ff_geo_vec(rx_y_m=-1.32), th, phi, gu.EL0, 0.0, 5.0, 5.0)[0] < 0
+
+
+def test_ff_ray_selection_keeps_every_winner(shadow, oracle):
+    """The complete ray selection of the fused far-field map (row intervals, predictor, ff_pred_row_keep: rays beyond
+    the grid dropped, of the rays that pile into cell (0, 0) one per row kept) must leave the winner tables of the pixel
+    and of its mirror pixel exactly as tracing every accepted ray gives them -- for pairs and one-sided items, centred
+    and shifted grids, fine and coarse grids, on- and off-axis pixels, small and large fans."""
+    geo = oracle.ff_geo_vec(rx_y_m=-1.32)
+    saved = 0
+    for n in (100, 40, 211):
+        th, phi = gu.ff_fan(n)
+        for az, el in [(0.0, gu.EL0), (20 * gu.DE, gu.EL0 - 20 * gu.DE), (10 * gu.DE, gu.EL0 + 15 * gu.DE), (3e-3, -2e-3)]:
+            for m, g_lo, g_hi in [(51, -5.0, 5.0), (101, -5.0, 5.0), (21, -12.0, 3.0), (11, 2.0, 9.0), (61, -30.0, 30.0)]:
+                for need_pos, need_neg in [(True, True), (True, False), (False, True)]:
+                    if n != 100 and (m != 51 or not need_pos):
+                        continue
+                    on, n_acc, n_kept, diff = shadow.ff_keep_check(geo, th, phi, el, az, m, g_lo, g_hi, need_pos, need_neg)
+                    assert on == 1 and diff == 0, (n, az, m, g_lo, need_pos, need_neg, n_acc, n_kept, diff)
+                    assert 0 < n_kept <= n_acc
+                    if (m, g_lo) == (51, -5.0) and need_pos and need_neg and n == 100:
+                        saved = max(saved, n_acc - n_kept)
+    assert saved > 2000          # the +-5 cm grid of ff_sim.py: a pair needs ~3400 of its 6000 accepted rays
