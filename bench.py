@@ -27,9 +27,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-NCU_DRAM_BYTES_PER_LAUNCH = 1528064 + 95744 + 3072 + 76288   # ff_map + ff_prep + ff_pair kernels, r1k capture (read + write)
-NCU_EXECUTED_FP64_FLOP_PER_LAUNCH = (2 * 944665914 + 285574990 + 145724305      # ff_map_kernel: DFMA x2 + DMUL + DADD thread instructions
-                                     + 2 * 19214937 + 7779996 + 5708635)        # ff_prep_kernel (r1k capture)
+NCU_DRAM_BYTES_PER_LAUNCH = 3595520 + 192512 + 99072 + 35840   # ff_map + ff_prep + ff_pair kernels, r1n capture (read + write)
+NCU_EXECUTED_FP64_FLOP_PER_LAUNCH = (2 * 743942311 + 224236359 + 115551260      # ff_map_kernel: DFMA x2 + DMUL + DADD thread instructions
+                                     + 2 * 19158972 + 7770525 + 5705847)        # ff_prep_kernel (r1n capture)
 METRIC = "scan_pixel_rays_per_s"
 UNIT = "pixel*rays/s"
 FREQ, RES_ARCMIN, NUM, OFFSET, N_SCAN = 140, 0.25, 20, 1.32, 100
@@ -277,8 +277,8 @@ def run_ours(args):
             "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of ff_map_kernel, bytes per launch, ncu --set full "
-                                           "capture profiles/r01k_raw_metrics.csv (algorithmic: 27 kB pixel list + 27 kB results + "
-                                           "~45 kB E_rec and angle tables; the rest is the 1.7 kB per-pixel set-up record written by "
+                                           "capture profiles/r01n_raw_metrics.csv (algorithmic: 27 kB pixel list + 27 kB results + "
+                                           "~45 kB E_rec and angle tables; the rest is the 4 kB per-pixel set-up record written by "
                                            "ff_prep_kernel and read back by ff_map_kernel); the path is compute bound",
                          "peak_source": "burst DFMA issue-rate probe run in this process (best of 5 x 2 ms launches; MEASURED_PEAKS.json "
                                         "has no FP64 figure); nominal %.1f = 148 SM x 64 lanes x 2 x 1.965 GHz" % NOMINAL_FP64_TFLOPS,
@@ -286,12 +286,12 @@ def run_ours(args):
                          "flop_per_unit": FLOP_PER_LAUNCHED_RAY, "units_per_launch": npix * N_SCAN ** 2, "kernel": kernel_note,
                          "executed_tflops": NCU_EXECUTED_FP64_FLOP_PER_LAUNCH / (kernel_ms * 1e-3) / 1e12,
                          "executed_frac": NCU_EXECUTED_FP64_FLOP_PER_LAUNCH / (kernel_ms * 1e-3) / 1e12 / peak,
-                         "fp64_pipe_pct_ncu": 41.5,
+                         "fp64_pipe_pct_ncu": 38.4,
                          "note": "achieved/frac follow the contract: SURVEY 8d's reference-shaped model (626 FLOP per launched ray: the "
                                  "reference traces every accepted ray) over the measured time.  The kernel executes far fewer FP64 "
                                  "operations (mixed-precision Newton, mirror-local frames, about half of the accepted rays culled "
                                  "before the trace because the reference's projection would skip them, mirror pixels (+az, -az) "
-                                 "sharing one trace), so frac can exceed 1; executed_* = ncu thread-level DFMA/DMUL/DADD counts of profiles/r01k_op_counts.csv over the "
+                                 "sharing one trace), so frac can exceed 1; executed_* = ncu thread-level DFMA/DMUL/DADD counts of profiles/r01n_op_counts.csv over the "
                                  "same measured time, fp64_pipe_pct_ncu = sm__inst_executed_pipe_fp64 of that capture"},
             "ray_status": int(status),
         }
