@@ -2,16 +2,22 @@
 //
 // Kernels (all FP64 SIMT; the path has no dense contraction, so no tensor cores -- DESIGN.md):
 //   nf_rows_kernel<KIND>   thread-per-ray dump of the reference's .output() arrays (rx / source / toy)
-//   nf_map_kernel<NF>      fused source trace + phase + aperture integral: one CTA per (pixel, ray tile),
-//                          rays culled by the receiver weight, warp-shuffle + shared-memory block reduce
+//   nf_rx_fields_kernel    path length and taper of every ray for a list of receiver positions (offset sweeps)
+//   nf_first_leg_kernel,   per-plan tables of a near-field map: the pixel-independent first leg of every active ray,
+//   nf_phasor_kernel       the receiver phasors per (receiver table, wavenumber)
+//   nf_map_kernel<NF,NT,PAIR>  fused source trace + phase + aperture integral: one CTA per (work item, ray tile), a
+//                          work item being a source position or the mirror pair (+x, z), (-x, z); rays culled by the
+//                          receiver weight; warp-shuffle + shared-memory block reduce
 //   nf_finalize_kernel     fixed-order sum of tile partials -> amp, phase
 //   ff_rows_kernel<STAGE>  thread-per-ray dump of ray_mirror_pts / aperature_fields_from_panel_model
 //   ff_project_*           last-write-wins scatter (atomicMax on the ray index) + phasor fill
-//   ff_prep_kernel         per-pixel set-up of the fused far-field map: frames, per-row ray intervals, cull of the
-//                          rays the reference's projection would skip (focal-position predictor)
-//   ff_map_kernel          fused far-field pixel: one CTA per (az, el); every warp traces its share of the pixel's
-//                          dense ray list with full lanes; winner table (ray index, OPL) in shared memory;
-//                          winners-only phasor sum
+//   ff_pair_*_kernel       pixel list -> work items (a pixel or the mirror pair (+az, el), (-az, el)); also used for
+//                          the near-field source positions
+//   ff_prep_kernel         per-item set-up of the fused far-field map: frames, the rays that have to be traced as up
+//                          to four index intervals per phi row (aperture, focal-position predictor)
+//   ff_map_kernel<PANEL,T,B>  fused far-field map: one CTA per work item; every warp traces its share of the item's
+//                          dense ray list with full lanes; winner tables (ray index, OPL) in shared memory;
+//                          winners-only phasor sums
 //   ff_mirror_xy_kernel    mirror coordinates of every (pixel, ray) for the host's identify_panel
 //   fp64_peak_kernel       DFMA issue-rate microbenchmark (roofline denominator)
 #include <cuda_runtime.h>
@@ -757,25 +763,9 @@ __device__ __forceinline__ void ff_prefix_rows(int* row_pre, int nph, int lane)
     if (lane == 0) row_pre[0] = 0;
 }
 
-// One CTA per (az, el) pixel, warps fully autonomous inside the ray loop (no CTA barrier).
-//   * Which rays pass the aperture (saf:378, 60 % of the default fan):
-//     - interval walk (theta monotone, the reference's linspace fans): the rays of one phi row hit the aperture
-//       plane along a straight line, so the accepted rays of a row are ONE index interval.  One thread per row finds
-//       it with the exact FP64 test (bisection for the closest ray, then for both rim crossings: ~4 log2(nth)
-//       evaluations instead of nth); a prefix sum turns the intervals into a dense list every warp indexes directly.
-//     - queue walk (any other fan, or a pixel whose plane-hit denominator changes sign along a row): each warp
-//       tests chunks of 32 candidate rays (FP32 prefilter, FP64 near the rim) and compacts the survivors into its
-//       own shared-memory queue (ballot + popc), popping a full batch whenever there is one.
-//     Either way the expensive two-mirror trace always runs with full warps.
-//   * the reference's "later ray overwrites the cell" becomes one 64-bit shared-memory atomicMax per ray on a
-//     key that carries the ray index above an exact fixed-point copy of its path length;
-//   * after one barrier the winners -- and only they -- get their phasor, are weighted by E_rec and reduced.
-//   * PANEL (adjuster-error studies, ff_sim.py:61-70 with non-zero offsets): every ray carries the panel-model
-//     columns the host derived with pan_mod.identify_panel; rays on no panel are dropped (saf:626-628,805-809), the
-//     others see their panels' error polynomials inside both Newton solves.  Always the queue walk.
 // Per-pixel set-up of the fused map, one small CTA per pixel, all pixels of a launch in flight at once (the set-up is
-// latency bound: one thread builds the frames, one thread per phi row finds its interval): frames, and for the
-// interval walk the per-row ray intervals already shrunk by the focal-position predictor, as a record in global
+// latency bound: one thread builds the frames, one thread per phi row finds its intervals): frames, and for the
+// interval walk the per-row ray intervals (aperture, then ff_pred_row_keep), as a record in global
 // memory the map kernel copies into its shared memory.  Record: FfFrames | int queue_walk, n_list, pad[2] |
 // row_lo[K nph] | row_pre[K nph + 1]  (K = FF_ROW_K intervals per phi row: virtual row K j + k).
 constexpr int FF_PREP_T = 64;     // = FF_PRED_SAMPLES; 12 CTAs per SM keep every pixel of a 41 x 41 map in flight
@@ -923,6 +913,24 @@ __global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
     }
 }
 
+// One CTA per work item (a pixel, or a mirror pair of pixels), warps fully autonomous inside the ray loop (no CTA
+// barrier).
+//   * Which rays are traced:
+//     - interval walk (theta monotone, the reference's linspace fans): ff_prep_kernel has listed the rays that can
+//       matter as up to FF_ROW_K index intervals per phi row (accepted by the aperture, not ruled out by the
+//       focal-position predictor); the record's prefix sums turn them into a dense list and every warp walks its
+//       contiguous share of it, 32 rays per step, last ray first.
+//     - queue walk (any other fan, a pixel whose plane-hit denominator changes sign along a row, or PANEL): each warp
+//       tests chunks of 32 candidate rays (FP32 aperture prefilter, FP64 near the rim) and compacts the survivors
+//       into its own shared-memory queue (ballot + popc), popping a full batch whenever there is one.
+//     Either way the expensive two-mirror trace always runs with full warps.
+//   * the reference's "later ray overwrites the cell" becomes a 64-bit shared-memory atomicMax on a key that carries
+//     the ray index above an exact fixed-point copy of the path length, taken only if no later ray holds the cell; a
+//     pair item bins every ray twice (the pixel's table and the mirror pixel's);
+//   * after one barrier the winners -- and only they -- get their phasor, are weighted by E_rec and reduced.
+//   * PANEL (adjuster-error studies, ff_sim.py:61-70 with non-zero offsets): every ray carries the panel-model
+//     columns the host derived with pan_mod.identify_panel; rays on no panel are dropped (saf:626-628,805-809), the
+//     others see their panels' error polynomials inside both Newton solves.
 template <bool PANEL, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
 {
