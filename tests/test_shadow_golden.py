@@ -274,3 +274,58 @@ def test_ff_ray_selection_keeps_every_winner(shadow, oracle):
                     if (m, g_lo) == (51, -5.0) and need_pos and need_neg and n == 100:
                         saved = max(saved, n_acc - n_kept)
     assert saved > 2000          # the +-5 cm grid of ff_sim.py: a pair needs ~3400 of its 6000 accepted rays
+
+
+def _flip_cols(rows, nth, nph, flip_th, flip_ph):
+    r = rows.reshape(rows.shape[0], nph, nth)
+    if flip_th:
+        r = r[:, :, ::-1]
+    if flip_ph:
+        r = r[:, ::-1, :]
+    return r.reshape(rows.shape[0], -1)
+
+
+def test_ff_ray_mirror_symmetry(shadow, oracle):
+    """What the mirror-pair work items rest on: the telescope is symmetric under x -> -x, so the
+    ray (theta_i, pi - phi_j) of the pixel (el, -az) is the mirror image of the ray (theta_i, phi_j) of (el, az) -
+    x components change sign, everything else (the OPL above all) is equal."""
+    n = 21
+    th, ph = gu.ff_fan(n)
+    geo = oracle.ff_geo_vec(rx_y_m=-1.32)
+    xs = [0, 3, 6, 9, 12]
+    for el, az in ((0.0021, 0.0013), (-0.0037, 0.0044), (0.0, 0.0009)):
+        mp, _ = shadow.ff_mirror_rows(geo, th, ph, el, az)
+        mn, _ = shadow.ff_mirror_rows(geo, th, ph, el, -az)
+        fp, a1 = shadow.ff_field_rows(geo, th, ph, mp[6:9, 0], el, az)
+        fn, a2 = shadow.ff_field_rows(geo, th, ph, mn[6:9, 0], el, -az)
+        assert a1 == 0 and a2 == 0
+        fn = _flip_cols(fn, n, n, False, True)
+        assert np.array_equal(fp[16] != 0, fn[16] != 0)
+        # the reference centres each pixel on ITS ray 0 (saf:1170-1187), which is not the mirror image of the other
+        # pixel's ray 0: compare absolute focal positions (the kernels carry the mirrored centre as centre_mz)
+        hit = fp[16] != 0
+        fp[9:12, hit] += mp[6:9, :1]
+        fn[9:12, hit] += mn[6:9, :1]
+        sign = np.ones(17); sign[xs] = -1
+        np.testing.assert_allclose(fp[:15], sign[:15, None] * fn[:15], rtol=0, atol=1e-9)
+        assert np.abs(fp[15] - fn[15]).max() <= 2 * ULP_1E8
+
+
+def test_nf_ray_mirror_symmetry(shadow):
+    """The optics tube is a body of revolution about y: a source at (-x, y, z) sees the ray (theta_i, pi - phi_j) as the
+    mirror image of (theta_i, phi_j) from (x, y, z); likewise z with theta -> pi - theta."""
+    n = 23
+    a = _src_axis(n)
+    y_ap, _ = gu.nf_band(150)
+    for x, z in ((37.0, 0.0), (12.5, -61.0), (180.0, 95.0)):
+        base, st0, _ = shadow.nf_source_rows([x, y_ap, z], a, a)
+        for sx, sz in ((-1, 1), (1, -1), (-1, -1)):
+            out, st, _ = shadow.nf_source_rows([sx * x, y_ap, sz * z], a, a)
+            out = _flip_cols(out, n, n, sz < 0, sx < 0)
+            st = _flip_cols(st[None, :], n, n, sz < 0, sx < 0)[0]
+            assert np.array_equal(st, st0)
+            assert np.array_equal(out[4] == 0, base[4] == 0)
+            sign = np.ones(26)
+            sign[[0, 8, 11, 14, 17, 20, 23]] = sx
+            sign[[2, 10, 13, 16, 19, 22, 25]] = sz
+            np.testing.assert_allclose(np.nan_to_num(out), sign[:, None] * np.nan_to_num(base), rtol=0, atol=RAY_TOL)
