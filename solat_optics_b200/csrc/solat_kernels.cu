@@ -4,15 +4,16 @@
 //   nf_rows_kernel<KIND>   thread-per-ray dump of the reference's .output() arrays (rx / source / toy)
 //   nf_rx_fields_kernel    path length and taper of every ray for a list of receiver positions (offset sweeps)
 //   nf_first_leg_kernel,   per-plan tables of a near-field map: the pixel-independent first leg of every active ray,
-//   nf_phasor_kernel       the receiver phasors per (receiver table, wavenumber)
-//   nf_map_kernel<NF,NT,PAIR>  fused source trace + phase + aperture integral: one CTA per (work item, ray tile), a
-//                          work item being a source position or the mirror pair (+x, z), (-x, z); rays culled by the
-//                          receiver weight; warp-shuffle + shared-memory block reduce
+//   nf_phasor_kernel,      the receiver phasors per (receiver table, wavenumber), and for a mirror-symmetric plan the
+//   nf_phasor_mirror_kernel  phasors of every ray's three mirror rays next to its own
+//   nf_map_kernel<NF,NT,MODE>  fused source trace + phase + aperture integral: one CTA per (work item, ray tile), a
+//                          work item being a source position, the mirror pair (+-x, z) or the quad (+-x, +-z); rays
+//                          culled by the receiver weight; warp-shuffle + shared-memory block reduce
 //   nf_finalize_kernel     fixed-order sum of tile partials -> amp, phase
 //   ff_rows_kernel<STAGE>  thread-per-ray dump of ray_mirror_pts / aperature_fields_from_panel_model
 //   ff_project_*           last-write-wins scatter (atomicMax on the ray index) + phasor fill
 //   ff_pair_*_kernel       pixel list -> work items (a pixel or the mirror pair (+az, el), (-az, el)); also used for
-//                          the near-field source positions
+//                          the near-field source positions (a second stage there pairs the pairs into quads)
 //   ff_prep_kernel         per-item set-up of the fused far-field map: frames, the rays that have to be traced as up
 //                          to four index intervals per phi row (aperture, focal-position predictor)
 //   ff_map_kernel<PANEL,T,B>  fused far-field map: one CTA per work item; every warp traces its share of the item's
@@ -405,23 +406,36 @@ __global__ void ff_pair_emit_kernel(const double* azel, FfPairSlot* slots, unsig
 // instead of three); ints[0] = number of items
 constexpr int FF_PAIR_ONE_CTA = 4096;
 static size_t ff_pair_smem(int npix) { return (2 * (size_t)npix + 1) * sizeof(FfPairSlot) + ((size_t)npix + 2) * sizeof(int); }
-__global__ void __launch_bounds__(1024) ff_pair_kernel(const double* azel, int npix, int* ints, FfItem* items, PairTol tol)
+// Second stage (near-field quads, items2 != nullptr): the items of the first stage are paired once more on their
+// second coordinate -- item k -> (z, |x|) written to `scratch` -- and the items that come out hold |z|, |x| and the
+// indices of the first-stage items of (+z) and (-z); ints[2] = their number.
+__global__ void __launch_bounds__(1024) ff_pair_kernel(const double* azel, int npix, int* ints, FfItem* items, PairTol tol,
+                                                        FfItem* items2 = nullptr, double* scratch = nullptr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned nslots = 2u * (unsigned)npix + 1u;
     FfPairSlot* slots = reinterpret_cast<FfPairSlot*>(smem_raw);
     int* cnt = reinterpret_cast<int*>(slots + nslots);      // [0] items, [1] overflow length
     int* over = cnt + 2;
-    for (unsigned h = threadIdx.x; h < nslots; h += blockDim.x) slots[h].owner = slots[h].pos = slots[h].neg = -1;
-    if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
-    __syncthreads();
-    for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_insert(p, azel, slots, nslots, over, cnt, tol);
-    __syncthreads();
-    for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_attach(p, azel, slots, nslots, over, cnt, tol);
-    __syncthreads();
-    for (unsigned h = threadIdx.x; h < nslots; h += blockDim.x) ff_pair_emit(h, azel, slots, nslots, over, cnt, nullptr, items);
-    __syncthreads();
-    if (threadIdx.x == 0) ints[0] = cnt[0];
+    for (int stage = 0; stage < (items2 ? 2 : 1); stage++) {
+        for (unsigned h = threadIdx.x; h < nslots; h += blockDim.x) slots[h].owner = slots[h].pos = slots[h].neg = -1;
+        if (stage) {
+            npix = cnt[0];
+            for (int p = threadIdx.x; p < npix; p += blockDim.x) { scratch[2 * p] = items[p].el; scratch[2 * p + 1] = items[p].az; }
+            azel = scratch;                                 // global memory written by this CTA: visible after the barrier
+            items = items2;
+        }
+        __syncthreads();
+        if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
+        __syncthreads();
+        for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_insert(p, azel, slots, nslots, over, cnt, tol);
+        __syncthreads();
+        for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_attach(p, azel, slots, nslots, over, cnt, tol);
+        __syncthreads();
+        for (unsigned h = threadIdx.x; h < nslots; h += blockDim.x) ff_pair_emit(h, azel, slots, nslots, over, cnt, nullptr, items);
+        __syncthreads();
+        if (threadIdx.x == 0) ints[2 * stage] = cnt[0];
+    }
 }
 
 
@@ -431,17 +445,23 @@ __global__ void __launch_bounds__(1024) ff_pair_kernel(const double* azel, int n
 constexpr int NF_MAXF = 4;    // wavenumbers per launch
 constexpr int NF_MAXC = 8;    // channels (wavenumber x receiver table) per launch
 constexpr int NF_T = SOLAT_NF_T;
+constexpr int NF_MAX_SUMS = 16;   // complex accumulators per thread (outputs x channels) a launch may carry
 struct NfMapParams {
     AngleTabs ang;
     const double* src_xz;      // [npix][2]
     const int* act_idx;        // [n_act] ray indices with a non-zero receiver weight in any table
-    const double2* phasor;     // [nrx][nfreq][n_act]  w_rx exp(i k L_rx / 1e3)  (holo_sim.py:173-176)
+    const double2* phasor;     // ([4])[nrx][nfreq][n_act]  w_rx exp(i k L_rx / 1e3)  (holo_sim.py:173-176)
     const double2* first_leg;  // [n_act][4]  pixel-independent start of every active ray (nf_source_first_leg)
-    // mirror pairs (nf_map_kernel<.., true>): work items (|x|, z) with the output pixels of (+x, z) and (-x, z),
-    // counters[0] of them; amap[a] = active index of the mirror ray (theta_i, pi - phi_j) of active ray a
+    // Mirror images (see nf_map_kernel).  sym bit 0: sources (x, z), (-x, z) are mirror images, bit 1: (x, z), (x, -z).
+    // A symmetric plan (sym != 0) stores phasor[((m * nrx + table) * nfreq + f) * n_act + a], m = 0 the ray itself,
+    // 1 / 2 / 3 its mirror ray in x / z / both.
+    // MODE 1: items[k] = (|x|, z, pixel of +x, pixel of -x), counters[0] of them.
+    // MODE 2: items2[k] = (|z|, |x|, index in `items` of the +z pair, of the -z pair), counters2[0] of them.
     const FfItem* items;
+    const FfItem* items2;
     const int* counters;
-    const int* amap;
+    const int* counters2;
+    int sym;
     double y_ap, n_si, n_vac;
     double kk[NF_MAXF];        // k/1e3 [rad/mm] of the wavenumbers of this launch
     int n_act, tiles, tile_len, nfreq_total, nch_total, f0, j0;
@@ -451,7 +471,7 @@ struct NfMapParams {
 
 // CTA-wide sum of NC complex accumulators: warp shuffles, then one shared-memory hop.  dst[c * stride]
 template <int NC>
-__device__ __forceinline__ void block_reduce_store(double (&re)[NC], double (&im)[NC], double2* dst, int stride = 1)
+__device__ __forceinline__ void block_reduce_store(double* re, double* im, double2* dst, int stride = 1)
 {
     __shared__ double sh[2 * NF_MAXC][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
@@ -483,37 +503,55 @@ __device__ __forceinline__ void block_reduce_store(double (&re)[NC], double (&im
 // NF wavenumbers x NT receiver tables: exp(i k L_source) is formed per wavenumber and multiplied into the
 // precomputed receiver phasor of every table (frequency sweeps of one band and receiver-offset sweeps share
 // the geometry: BASELINE configs 3 and 4).
-// PAIR: the optics tube is rotationally symmetric and the launch fan symmetric in phi about pi/2, so ray (i, j) from
-// the source (x, z) and ray (i, nph-1-j) from (-x, z) are mirror images with the same path length.  The work item is
-// then the source (|x|, z): every traced ray adds exp(i k L) times the receiver phasor of ray (i, j) to the pixel
-// (+|x|, z) and times that of the mirror ray to the pixel (-|x|, z).  A pixel with x < 0 is always computed this way,
-// partner in the list or not.  (NF * NT <= 4: two sets of accumulators.)
-template <int NF, int NT, bool PAIR>
+// Mirror images.  The optics tube is a body of revolution about y.  With a launch fan symmetric in phi about pi/2, ray
+// (i, j) from the source (x, z) and ray (i, nph-1-j) from (-x, z) are mirror images with the same path length; with a
+// fan symmetric in theta about pi/2 the same holds for (x, -z) and ray (nth-1-i, j).  A pixel on the negative side of a
+// symmetric axis is ALWAYS computed as the mirror image of its canonical source (|x|, |z|) -- rays traced in the
+// canonical order, receiver phasors looked up at the mirror ray -- so its value does not depend on what else is in
+// the list or on how the list is sharded.
+// MODE 0: one output pixel per CTA row.  MODE 1: the work item is (|x|, z) and every traced ray feeds the two pixels
+// (+-x, z).  MODE 2: the work item is (|x|, |z|) and feeds the four pixels (+-x, +-z).  (Two / four sets of NF * NT
+// accumulators: beyond about 16 complex sums they live in local memory, a few loads and stores per traced ray, far
+// cheaper than tracing the ray again.)
+template <int NF, int NT, int MODE>
 __global__ void __launch_bounds__(NF_T, SOLAT_NF_MINB) nf_map_kernel(NfMapParams q)
 {
     constexpr int NC = NF * NT;
+    constexpr int NO = MODE == 2 ? 4 : (MODE == 1 ? 2 : 1);
     const Coef& sC = K_COEF;   // constant bank; a shared-memory copy measured 2-4 % slower (profiles/r01_variants.md)
     const int pix = blockIdx.x / q.tiles, tile = blockIdx.x - pix * q.tiles;
-    int out_pos = pix, out_neg = -1;
-    bool mirror = false;
+    int out[NO];
+    int msel = 0;                                           // MODE 0: which mirror image this pixel is
     vec3 p0;
-    if (PAIR) {
-        if (pix >= __ldg(q.counters)) return;              // one CTA row per pixel is launched, items are fewer
+    if (MODE == 2) {
+        if (pix >= __ldg(q.counters2)) return;             // one CTA row per pixel is launched, items are fewer
+        const FfItem it = q.items2[pix];
+        p0 = mk(it.el, q.y_ap, it.az);
+#pragma unroll
+        for (int o = 0; o < NO; o++) out[o] = -1;
+        if (it.pos >= 0) { out[0] = q.items[it.pos].pos; out[1] = q.items[it.pos].neg; }
+        if (it.neg >= 0) { out[2 % NO] = q.items[it.neg].pos; out[3 % NO] = q.items[it.neg].neg; }
+    } else if (MODE == 1) {
+        if (pix >= __ldg(q.counters)) return;
         const FfItem it = q.items[pix];
-        p0 = mk(it.az, q.y_ap, it.el);
-        out_pos = it.pos; out_neg = it.neg;
+        // the z mirror of a pair item is taken as a whole: (|x|, -z) -> trace (|x|, |z|), both pixels through the z map
+        msel = ((q.sym & 2) && it.el < 0.0) ? 2 : 0;
+        p0 = mk(it.az, q.y_ap, msel ? -it.el : it.el);
+        out[0] = it.pos; out[1 % NO] = it.neg;
     } else {
-        // a pixel with x < 0 is computed as the mirror image of (|x|, z) here too (when the plan is symmetric), so that
-        // its value does not depend on whether a launch pairs pixels or not
-        const double x = __ldg(q.src_xz + 2 * pix);
-        mirror = q.amap != nullptr && x < 0.0;
-        p0 = mk(mirror ? -x : x, q.y_ap, __ldg(q.src_xz + 2 * pix + 1));
+        const double x = __ldg(q.src_xz + 2 * pix), z = __ldg(q.src_xz + 2 * pix + 1);
+        msel = (((q.sym & 1) && x < 0.0) ? 1 : 0) + (((q.sym & 2) && z < 0.0) ? 2 : 0);
+        p0 = mk((msel & 1) ? -x : x, q.y_ap, (msel & 2) ? -z : z);
+        out[0] = pix;
     }
-    double re[NC], im[NC], re_m[PAIR ? NC : 1], im_m[PAIR ? NC : 1];
+    // which mirror ray's receiver phasor every output takes: MODE 0 {msel}, MODE 1 {msel, msel | 1}, MODE 2 {0, 1, 2, 3};
+    // a symmetric plan holds one copy of the tables per mirror image, gathered through the mirror map once
+    size_t mo[NO];
 #pragma unroll
-    for (int c = 0; c < NC; c++) re[c] = im[c] = 0.0;
+    for (int o = 0; o < NO; o++) mo[o] = (size_t)(MODE == 2 ? o : (msel | o)) * q.nch_total * q.n_act;
+    double re[NO * NC], im[NO * NC];
 #pragma unroll
-    for (int c = 0; c < (PAIR ? NC : 1); c++) re_m[c] = im_m[c] = 0.0;
+    for (int c = 0; c < NO * NC; c++) re[c] = im[c] = 0.0;
     int st = 0;
     const int q_end = min((tile + 1) * q.tile_len, q.n_act);
     for (int a = tile * q.tile_len + threadIdx.x; a < q_end; a += NF_T) {
@@ -526,47 +564,40 @@ __global__ void __launch_bounds__(NF_T, SOLAT_NF_MINB) nf_map_kernel(NfMapParams
         nf_source_ray_from_1b(sC, mk(l2.x, l2.y, l3.x), l0.x, (int)l3.y, q.n_si, q.n_vac, ray);
         st |= ray.status;
         if (ray.valid) {
-            const int am = (PAIR || mirror) ? __ldg(q.amap + a) : a;
 #pragma unroll
             for (int f = 0; f < NF; f++) {
                 double sn, cs;
                 sincos_mid(ray.opl * q.kk[f], sn, cs);                            // holo_sim.py:177
 #pragma unroll
                 for (int t = 0; t < NT; t++) {
-                    const double2* tab = q.phasor + ((size_t)(q.j0 + t) * q.nfreq_total + (q.f0 + f)) * q.n_act;
-                    if (!PAIR || out_pos >= 0) {
-                        const double2 ph = __ldg(tab + (PAIR ? a : am));
-                        re[t * NF + f] = fma(ph.x, cs, fma(-ph.y, sn, re[t * NF + f]));
-                        im[t * NF + f] = fma(ph.x, sn, fma(ph.y, cs, im[t * NF + f]));
-                    }
-                    if (PAIR && out_neg >= 0) {
-                        const double2 ph = __ldg(tab + am);
-                        re_m[t * NF + f] = fma(ph.x, cs, fma(-ph.y, sn, re_m[t * NF + f]));
-                        im_m[t * NF + f] = fma(ph.x, sn, fma(ph.y, cs, im_m[t * NF + f]));
+                    const double2* tab = q.phasor + ((size_t)(q.j0 + t) * q.nfreq_total + (q.f0 + f)) * q.n_act + a;
+#pragma unroll
+                    for (int o = 0; o < NO; o++) {
+                        if (MODE != 0 && out[o] < 0) continue;                      // CTA-uniform
+                        const double2 ph = __ldg(tab + mo[o]);
+                        const int c = o * NC + t * NF + f;
+                        re[c] = fma(ph.x, cs, fma(-ph.y, sn, re[c]));
+                        im[c] = fma(ph.x, sn, fma(ph.y, cs, im[c]));
                     }
                 }
             }
         }
     }
     if (st) atomicOr(q.status, st);
-    // accumulators are ordered [t][f]; channel (j0 + t) * nfreq + f0 + f
-    __shared__ double2 tmp[NF_MAXC];
+    // accumulators are ordered [output][t][f]; channel (j0 + t) * nfreq + f0 + f
+    __shared__ double2 tmp[4 * NF_MAXC];
 #pragma unroll
-    for (int side = 0; side < (PAIR ? 2 : 1); side++) {
-        const int out = side ? out_neg : out_pos;
-        if (out < 0) continue;                              // CTA-uniform
-        double2* base = q.partial + ((size_t)out * q.tiles + tile) * q.nch_total;
-        if constexpr (PAIR) {
-            if (side) block_reduce_store<NC>(re_m, im_m, tmp); else block_reduce_store<NC>(re, im, tmp);
-        } else {
-            block_reduce_store<NC>(re, im, tmp);
-        }
-        __syncthreads();
-        if (threadIdx.x < NC) {
-            const int t = threadIdx.x / NF, f = threadIdx.x - t * NF;
-            base[(size_t)(q.j0 + t) * q.nfreq_total + q.f0 + f] = tmp[threadIdx.x];
-        }
-        __syncthreads();                                    // tmp and the reduction scratch are reused
+    for (int o = 0; o < NO; o++) {
+        block_reduce_store<NC>(re + o * NC, im + o * NC, tmp + o * NC);
+        __syncthreads();                                    // tmp is complete, the reduction scratch free again
+    }
+    if (threadIdx.x < NO * NC) {
+        const int o = threadIdx.x / NC, c = threadIdx.x - o * NC, t = c / NF, f = c - t * NF;
+        int dst = out[0];
+#pragma unroll
+        for (int k = 1; k < NO; k++) if (o == k) dst = out[k];
+        if (dst >= 0)
+            q.partial[((size_t)dst * q.tiles + tile) * q.nch_total + (size_t)(q.j0 + t) * q.nfreq_total + q.f0 + f] = tmp[threadIdx.x];
     }
 }
 
@@ -593,6 +624,19 @@ __global__ void nf_phasor_kernel(const double2* opl_w, const double* k_per_m, in
     ph[idx] = make_double2(v.y * cs, v.y * sn);
 }
 
+// symmetric plans: one more copy of the phasor tables per mirror image, out[m][channel][a] = ph[channel][mirror_m(a)]
+// amap[(m - 1) * n_act + a], m = 1 (x), 2 (z), 3 (both) = active index of the mirror ray of active ray a
+__global__ void nf_phasor_mirror_kernel(const double2* ph, const int* amap, int n_act, long long per_image, double2* out)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (m * channels + channel) * n_act + a
+    if (idx >= 4 * per_image) return;
+    const int m = (int)(idx / per_image), a = (int)(idx % n_act);
+    const long long ch = (idx - m * per_image) / n_act;
+    out[idx] = ph[ch * n_act + (m ? amap[(size_t)(m - 1) * n_act + a] : a)];
+}
+
+// Fixed-order sum of the tile partials -> amp, phase (holo_sim.py:181-182).  (Folding this into nf_map_kernel -- the CTA
+// that stores an item's last tile adds them up -- measured the same time: profiles/r01_variants.md.)
 __global__ void nf_finalize_kernel(const double2* partial, int npix, int tiles, int nfreq, double* amp, double* phase)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // channel * npix + pix
@@ -603,7 +647,7 @@ __global__ void nf_finalize_kernel(const double2* partial, int npix, int tiles, 
         const double2 v = partial[((size_t)pix * tiles + t) * nfreq + f];
         re += v.x; im += v.y;
     }
-    amp[idx] = hypot(re, im);     // holo_sim.py:181-182
+    amp[idx] = hypot(re, im);
     phase[idx] = atan2(im, re);
 }
 
@@ -1474,10 +1518,12 @@ struct solat_nf_plan {
     DevBuf<int> act_idx;
     DevBuf<double2> phasor;                 // [nrx][nfreq][n_act]
     DevBuf<double2> first_leg;              // [n_act][4]
-    DevBuf<int> amap;                       // [n_act] active index of every ray's mirror ray (pairs)
-    DevBuf<FfItem> items;                   // work items of a paired map
+    DevBuf<int> amap;                       // [3][n_act] active index of every ray's x, z and xz mirror ray
+    DevBuf<FfItem> items;                   // work items of a paired map: [npix] pairs, then [npix] quads
     DevBuf<int> pair_ints;
-    int pairs = 0;                          // fan and active set are mirror symmetric
+    DevBuf<double> pair_xz;                 // (z, |x|) of the pair items, the list the quad stage pairs
+    int sym = 0;                            // bit 0 / bit 1: fan and active set are mirror symmetric in x / in z
+    int pairs = 1, quads = 1;               // work items of two / four pixels allowed (SOLAT_NF_QUADS=0: pairs only)
     DevBuf<double2> partial;
     DevBuf<int> status;
     std::vector<double> kk;
@@ -1487,7 +1533,9 @@ struct solat_nf_plan {
 
 // Ray tiling of one pixel.  It depends on the ray count ONLY (never on the number of pixels), so the
 // summation order of a pixel -- and therefore its bits -- is the same however the pixel list is sharded
-// over calls or ranks.  Picks the tile count with the fewest idle threads in the last loop iteration.
+// over calls or ranks.  Picks the tile count with the fewest idle threads in the last loop iteration; among equals the
+// largest that still gives a thread 8 rays (more, smaller CTAs fill the last wave better: 51x51 px, 7328 rays,
+// 2 / 3 / 5 / 6 tiles: 0.169 / 0.163 / 0.171 / 0.177 ms).
 static void nf_choose_tiling(solat_nf_plan* p)
 {
     const int min_tiles = std::max(1, (p->n_act + 4095) / 4096);
@@ -1498,7 +1546,7 @@ static void nf_choose_tiling(solat_nf_plan* p)
         const int granule = p->threads;                 // rays per CTA per loop trip
         const int iters = (len + granule - 1) / granule;
         const double thread_eff = (double)p->n_act / ((double)tiles * iters * granule);
-        if (thread_eff > best + 1e-9) { best = thread_eff; best_tiles = tiles; }
+        if (thread_eff > best + 1e-9 || (thread_eff > best - 1e-9 && iters >= 8)) { best = std::max(best, thread_eff); best_tiles = tiles; }
     }
     p->tiles = best_tiles;
     p->tile_len = (p->n_act + best_tiles - 1) / best_tiles;
@@ -1507,10 +1555,9 @@ static void nf_choose_tiling(solat_nf_plan* p)
 template <int NF, int NT>
 static void nf_launch_one(const NfMapParams& q, int grid, int threads, cudaStream_t s)
 {
-    if constexpr (NF * NT <= 4) {
-        if (q.items) { nf_map_kernel<NF, NT, true><<<grid, threads, 0, s>>>(q); return; }
-    }
-    nf_map_kernel<NF, NT, false><<<grid, threads, 0, s>>>(q);
+    if (q.items2) nf_map_kernel<NF, NT, 2><<<grid, threads, 0, s>>>(q);
+    else if (q.items) nf_map_kernel<NF, NT, 1><<<grid, threads, 0, s>>>(q);
+    else nf_map_kernel<NF, NT, 0><<<grid, threads, 0, s>>>(q);
 }
 
 static int nf_map_launch(solat_nf_plan* p, const double* d_src, int npix, double* d_amp, double* d_phase, cudaStream_t s)
@@ -1529,22 +1576,35 @@ static int nf_map_launch(solat_nf_plan* p, const double* d_src, int npix, double
     q.y_ap = p->g.y_ap; q.n_si = p->g.n_si; q.n_vac = p->g.n_vac;
     q.n_act = p->n_act; q.tiles = p->tiles; q.tile_len = p->tile_len; q.nfreq_total = nfreq; q.nch_total = nch;
     q.partial = p->partial.p; q.status = p->status.p;
-    q.items = nullptr; q.counters = nullptr; q.amap = p->pairs ? p->amap.p : nullptr;
-    const bool pairs = p->pairs && nch <= 4 && npix <= FF_PAIR_ONE_CTA;
+    q.items = q.items2 = nullptr; q.counters = q.counters2 = nullptr;
+    q.sym = p->sym;
+    // work items: pairs (+-x, z) when the plan is symmetric in x, quads (+-x, +-z) when it is symmetric in z as well
+    // (a sweep over many receiver tables is bound by the reads of the phasor tables, one per output pixel, ray and table
+    // whatever the work item is: 25 tables, 51x51 px: 2.47 ms one pixel per CTA, 2.70 ms as quads)
+    const bool pairs = (p->sym & 1) && p->pairs && npix <= FF_PAIR_ONE_CTA && nch <= NF_MAX_SUMS;
+    const bool quads = pairs && (p->sym & 2) && p->quads;
     if (pairs) {
-        if (int rc = p->items.reserve((size_t)npix)) return rc;
+        if (int rc = p->items.reserve((size_t)npix * (quads ? 2 : 1))) return rc;
         if (int rc = p->pair_ints.reserve(8)) return rc;
-        ff_pair_kernel<<<1, 1024, ff_pair_smem(npix), s>>>(d_src, npix, p->pair_ints.p, p->items.p, NF_PAIR_TOL);
+        if (quads)
+            if (int rc = p->pair_xz.reserve(2 * (size_t)npix)) return rc;
+        ff_pair_kernel<<<1, 1024, ff_pair_smem(npix), s>>>(d_src, npix, p->pair_ints.p, p->items.p, NF_PAIR_TOL,
+                                                           quads ? p->items.p + npix : nullptr, quads ? p->pair_xz.p : nullptr);
         LAUNCHED();
         q.items = p->items.p; q.counters = p->pair_ints.p;
+        if (quads) { q.items2 = p->items.p + npix; q.counters2 = p->pair_ints.p + 2; }
     }
     const int grid = npix * p->tiles;                      // pairs: an upper bound, the CTAs past the last item return
     // every launch re-traces the rays, so pack as many channels as the accumulators allow (NF * NT <= 8)
-    for (int f0 = 0; f0 < nfreq; f0 += NF_MAXF) {
-        const int nf = std::min(NF_MAXF, nfreq - f0);
+    const int n_out = quads ? 4 : (pairs ? 2 : 1);
+    int max_sums = NF_MAX_SUMS;
+    if (const char* e = getenv("SOLAT_NF_MAX_SUMS")) max_sums = std::max(1, atoi(e));
+    const int f_step = std::max(1, std::min(NF_MAXF, max_sums / n_out));
+    for (int f0 = 0; f0 < nfreq; f0 += f_step) {
+        const int nf = std::min(f_step, nfreq - f0);
         q.f0 = f0;
         for (int f = 0; f < NF_MAXF; f++) q.kk[f] = f < nf ? p->kk[f0 + f] / 1e3 : 0.0;
-        const int nt_cap = nf == 1 ? 8 : (nf == 2 ? 4 : 2);
+        const int nt_cap = std::min(nf == 1 ? 8 : (nf == 2 ? 4 : 2), std::max(1, max_sums / (n_out * nf)));
         for (int j0 = 0; j0 < p->nrx;) {
             int nt = 1;
             while (nt * 2 <= nt_cap && j0 + nt * 2 <= p->nrx) nt *= 2;
@@ -1587,19 +1647,30 @@ int solat_nf_plan_create_multi(solat_ctx* c, const solat_nf_geom* g, const doubl
         if (any_w) idx.push_back((int)r);
     }
     p->n_act = (int)idx.size();
-    // mirror pairs: the fan must be symmetric in phi about pi/2 and the active set closed under j -> nph-1-j
+    // mirror images: x needs the fan symmetric in phi about pi/2 and the active set closed under j -> nph-1-j,
+    // z the same in theta and i -> nth-1-i
     {
-        p->pairs = nph > 0 && !(getenv("SOLAT_NF_PAIRS") && getenv("SOLAT_NF_PAIRS")[0] == '0');
-        for (int j = 0; j < nph && p->pairs; j++)
-            if (!(fabs(phi[j] + phi[nph - 1 - j] - M_PI) <= 1e-12)) p->pairs = 0;
-        std::vector<int> am(idx.size());
-        for (size_t a = 0; a < idx.size() && p->pairs; a++) {
-            const int j = idx[a] / nth, i = idx[a] - j * nth;
-            const int rm = (nph - 1 - j) * nth + i;
-            const auto it = std::lower_bound(idx.begin(), idx.end(), rm);
-            if (it == idx.end() || *it != rm) p->pairs = 0; else am[a] = (int)(it - idx.begin());
+        const char* e = getenv("SOLAT_NF_PAIRS");
+        int sym = (e && e[0] == '0') ? 0 : 3;
+        e = getenv("SOLAT_NF_QUADS");
+        p->quads = !(e && e[0] == '0');
+        for (int j = 0; j < nph && (sym & 1); j++)
+            if (!(fabs(phi[j] + phi[nph - 1 - j] - M_PI) <= 1e-12)) sym &= ~1;
+        for (int i = 0; i < nth && (sym & 2); i++)
+            if (!(fabs(theta[i] + theta[nth - 1 - i] - M_PI) <= 1e-12)) sym &= ~2;
+        std::vector<int> am(3 * idx.size(), 0), where(sym ? n : 0, -1);      // where[ray] = its active index
+        for (size_t a = 0; a < idx.size() && sym; a++) where[idx[a]] = (int)a;
+        for (int m = 1; m <= 3 && sym; m++) {
+            if ((m & sym) != m) continue;
+            for (size_t a = 0; a < idx.size(); a++) {
+                const int j = idx[a] / nth, i = idx[a] - j * nth;
+                const int am_a = where[(size_t)((m & 1) ? nph - 1 - j : j) * nth + ((m & 2) ? nth - 1 - i : i)];
+                if (am_a < 0) { sym &= ~(m == 3 ? 3 : m); break; }
+                am[(size_t)(m - 1) * idx.size() + a] = am_a;
+            }
         }
-        if (p->pairs && p->n_act) {
+        p->sym = sym;
+        if (sym && p->n_act) {
             if (!rc) rc = p->amap.upload(am.data(), am.size(), c->stream);
             if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "sync");   // `am` goes out of scope
             if (!rc && cudaFuncSetAttribute(ff_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_pair_smem(FF_PAIR_ONE_CTA)) != cudaSuccess)
@@ -1619,12 +1690,21 @@ int solat_nf_plan_create_multi(solat_ctx* c, const solat_nf_geom* g, const doubl
     if (!rc && p->n_act) rc = p->act_idx.upload(idx.data(), idx.size(), c->stream);
     if (!rc && p->n_act) rc = d_ow.upload(ow.data(), ow.size(), c->stream);
     if (!rc && p->n_act) rc = d_k.upload(k_per_m, nfreq, c->stream);
-    if (!rc && p->n_act) rc = p->phasor.reserve((size_t)nrx * nfreq * p->n_act);
+    DevBuf<double2> d_ph;                                   // symmetric plans: the plain table, before the mirror gather
+    DevBuf<double2>& plain = p->sym ? d_ph : p->phasor;
+    if (!rc && p->n_act) rc = plain.reserve((size_t)nrx * nfreq * p->n_act);
     if (!rc && p->n_act) {
         const long long total = (long long)nrx * nfreq * p->n_act;
-        nf_phasor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_ow.p, d_k.p, nrx, nfreq, p->n_act, p->phasor.p);
+        nf_phasor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_ow.p, d_k.p, nrx, nfreq, p->n_act, plain.p);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (cudaGetLastError() != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "nf_phasor_kernel");
+    }
+    if (!rc && p->n_act && p->sym) rc = p->phasor.reserve(4 * (size_t)nrx * nfreq * p->n_act);
+    if (!rc && p->n_act && p->sym) {
+        const long long per_image = (long long)nrx * nfreq * p->n_act;
+        nf_phasor_mirror_kernel<<<(unsigned)((4 * per_image + 255) / 256), 256, 0, c->stream>>>(d_ph.p, p->amap.p, p->n_act, per_image, p->phasor.p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "nf_phasor_mirror_kernel");
     }
     if (!rc && p->n_act) rc = p->first_leg.reserve(4 * (size_t)p->n_act);
     if (!rc && p->n_act) {

@@ -233,9 +233,9 @@ def holo_map(freqs, res=51, sweep=100, shift=0, n_scan=100, n_scan_rx=None, p_rx
     plan = NearFieldPlan(tg, [g.k for g in geos], rx_opl, rx_w, n_scan, device)
     pixels = holo_pixels(res, sweep, shift)
     rank, world = dist_info()
-    # ranks take contiguous blocks of the list ordered so that the mirror positions (+x, z), (-x, z) are neighbours:
-    # the kernel traces such a pair once
-    order = mirror_pair_order(pixels) if world > 1 else np.arange(len(pixels))
+    # ranks take contiguous blocks of the list ordered so that the mirror positions (+-x, +-z) are neighbours: the
+    # kernel traces such a group once
+    order = mirror_pair_order(pixels, fold_second=True) if world > 1 else np.arange(len(pixels))
     lo, hi = shard_bounds(len(pixels), rank, world)
     if hi > lo:
         amp, phase, st = plan.run(pixels[order[lo:hi]])
@@ -447,13 +447,19 @@ class FarFieldPlan:
             pass
 
 
-def mirror_pair_order(pixels):
+def mirror_pair_order(pixels, fold_second=False):
     """Permutation of an (az, el) -- or near-field (x, z) -- pixel list that puts (+az, el) next to (-az, el)
-    (|az| compared to 1e-15, np.linspace grids are not symmetric to the bit)."""
+    (|az| compared to 1e-9 of the map's extent, np.linspace grids are not symmetric to the bit).  fold_second: the
+    four near-field positions (+-x, +-z) next to each other."""
     pixels = np.asarray(pixels, dtype=np.float64)
-    scale = float(np.max(np.abs(pixels[:, 0]))) if len(pixels) else 0.0
-    key = np.round(np.abs(pixels[:, 0]) * (1e9 / scale if scale > 0 else 1.0))     # 1e-9 of the map's extent
-    return np.lexsort((np.signbit(pixels[:, 0]), pixels[:, 1], key))
+
+    def folded(col):
+        scale = float(np.max(np.abs(col))) if len(col) else 0.0
+        return np.round(np.abs(col) * (1e9 / scale if scale > 0 else 1.0))
+
+    if fold_second:
+        return np.lexsort((np.signbit(pixels[:, 0]), np.signbit(pixels[:, 1]), folded(pixels[:, 1]), folded(pixels[:, 0])))
+    return np.lexsort((np.signbit(pixels[:, 0]), pixels[:, 1], folded(pixels[:, 0])))
 
 
 def ff_map(freq, res_arcmin, num, offset, data_x, data_y, e_rec, n_scan=100, device=None, strict=False, panel_models=None):

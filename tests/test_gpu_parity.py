@@ -207,9 +207,9 @@ def test_nf_receiver_offset_sweep_shares_the_source_trace(oracle):
 
 def test_nf_mirror_pairs(oracle, monkeypatch):
     """The optics tube is symmetric under x -> -x and so is the launch fan: the near-field map traces a ray once for
-    the source positions (+x, z) and (-x, z).  x >= 0 pixels bit-identical with the pair walk on and off, x < 0 pixels
-    (always computed as mirror images) within 1e-9 and within tolerance of the oracle; shuffled, one-sided and
-    duplicated lists give the same values; frequency sweeps (up to 4 channels) pair, larger channel counts do not."""
+    the source positions (+x, z) and (-x, z).  Canonical pixels (x >= 0, z >= 0) bit-identical with the pair walk on and
+    off, the others (always computed as mirror images) within 1e-9 and within tolerance of the oracle; shuffled, one-sided and
+    duplicated lists give the same values."""
     from solat_optics_b200 import maps
 
     tg = maps.holo_tele_geo(150.0, 36)
@@ -222,7 +222,7 @@ def test_nf_mirror_pairs(oracle, monkeypatch):
     monkeypatch.setenv("SOLAT_NF_PAIRS", "0")
     a_off, p_off, st = maps.NearFieldPlan(tg, kk, rx_opl, rx_w, device=0).run(px)
     monkeypatch.delenv("SOLAT_NF_PAIRS")
-    pos = px[:, 0] >= 0
+    pos = (px[:, 0] >= 0) & (px[:, 1] >= 0)              # the fan is symmetric in theta too: z < 0 pixels are mirror images as well
     np.testing.assert_array_equal(a_on[:, pos], a_off[:, pos])
     np.testing.assert_array_equal(p_on[:, pos], p_off[:, pos])
     np.testing.assert_allclose(a_on, a_off, rtol=1e-9, atol=0)
@@ -240,6 +240,45 @@ def test_nf_mirror_pairs(oracle, monkeypatch):
     dup = np.concatenate([px[:11], px[:11]])
     a_d, _, _ = plan.run(dup)
     np.testing.assert_allclose(a_d, np.concatenate([a_on[:, :11], a_on[:, :11]], axis=1), rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("nfreq", [1, 2, 4])
+def test_nf_mirror_quads(oracle, monkeypatch, nfreq):
+    """With a fan symmetric in theta as well the work item is the source (|x|, |z|) and feeds the four pixels (+-x, +-z).  Every pixel
+    is bit-identical to the pair walk (SOLAT_NF_QUADS=0) and to the one-pixel-per-CTA walk with mirrors, whatever subset
+    or order of the list is asked for; against no mirroring at all (SOLAT_NF_PAIRS=0) and the oracle within tolerance."""
+    from solat_optics_b200 import maps
+
+    tg = maps.holo_tele_geo(150.0, 36)
+    rx_opl, rx_w = maps.receiver_field(tg, (20.0, 0.0, -35.0))
+    px = maps.holo_pixels(res=9, sweep=100)
+    kk = [tg.k, maps.holo_tele_geo(220.0, 36).k, 1.31 * tg.k, 0.77 * tg.k][:nfreq]
+    plan = maps.NearFieldPlan(tg, kk, rx_opl, rx_w, device=0)
+    a_q, p_q, st = plan.run(px)
+    assert st == 0
+    monkeypatch.setenv("SOLAT_NF_QUADS", "0")
+    a_2, p_2, _ = maps.NearFieldPlan(tg, kk, rx_opl, rx_w, device=0).run(px)
+    monkeypatch.delenv("SOLAT_NF_QUADS")
+    np.testing.assert_array_equal(a_q, a_2); np.testing.assert_array_equal(p_q, p_2)
+    monkeypatch.setenv("SOLAT_NF_PAIRS", "0")
+    a_0, p_0, _ = maps.NearFieldPlan(tg, kk, rx_opl, rx_w, device=0).run(px)
+    monkeypatch.delenv("SOLAT_NF_PAIRS")
+    canon = (px[:, 0] >= 0) & (px[:, 1] >= 0)
+    np.testing.assert_array_equal(a_q[:, canon], a_0[:, canon])
+    np.testing.assert_allclose(a_q, a_0, rtol=1e-9, atol=0)
+    assert np.abs(gu.wrap(p_q - p_0)).max() < 1e-9
+    rx = oracle.nf_rx_trace((20.0, 0.0, -35.0), tg.th_fwhp, 36)
+    oa, op = oracle.nf_map(px, tg.y_ap, 36, rx[3], rx[4] * gu.lyot_mask(36), kk)
+    for f in range(nfreq):
+        _assert_pixels(a_q[f], p_q[f], oa[f], op[f])
+    rng = np.random.default_rng(11)
+    subsets = [rng.permutation(len(px)), np.nonzero(px[:, 1] < 0)[0], np.nonzero((px[:, 0] < 0) & (px[:, 1] > 0))[0],
+               np.nonzero(px[:, 0] * px[:, 1] > 0)[0], rng.permutation(len(px))[:37], np.concatenate([np.arange(9), np.arange(9)])]
+    # a list above 4096 positions is not paired (one pixel per CTA, mirror images all the same)
+    subsets.append(np.tile(np.arange(len(px)), 52)[:4200])
+    for sel in subsets:
+        a_s, p_s, _ = plan.run(px[sel])
+        np.testing.assert_array_equal(a_s, a_q[:, sel]); np.testing.assert_array_equal(p_s, p_q[:, sel])
 
 
 def test_nf_batched_receiver_fields_equal_the_per_receiver_ones():

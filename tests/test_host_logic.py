@@ -244,3 +244,12 @@ def test_mirror_pair_order_keeps_partners_adjacent():
     assert (a[:, 0] > 0).all() and (b[:, 0] < 0).all()
     np.testing.assert_array_equal(a[:, 1], b[:, 1])
     np.testing.assert_allclose(a[:, 0], -b[:, 0], rtol=0, atol=1e-17)
+    # near field: the four positions (+-x, +-z) of a group are neighbours
+    px = maps.holo_pixels(res=11, sweep=100)
+    order = maps.mirror_pair_order(px, fold_second=True)
+    assert sorted(order.tolist()) == list(range(len(px)))
+    q = np.abs(px[order])
+    key = np.round(q * 1e6)
+    change = 1 + np.nonzero((np.diff(key, axis=0) != 0).any(axis=1))[0]
+    groups = np.split(np.arange(len(px)), change)
+    assert len(groups) == 6 * 6 and max(len(g) for g in groups) == 4
