@@ -362,7 +362,7 @@ def run_nf(args):
     peak = ctx.fp64_peak_tflops(5)
     rays = npix * 100 ** 2
     flop_model = 520.0 * npix * plan.active_rays                      # 520 FLOP per traced source ray
-    flop_exec = 2 * 1368379776 + 565618560 + 180169536              # ncu thread-level DFMA x2 + DMUL + DADD, profiles/r01m_nf_op_counts.csv
+    flop_exec = 2 * 737400960 + 288873728 + 107575936               # ncu thread-level DFMA x2 + DMUL + DADD, profiles/r01o_nf_op_counts.csv
     achieved = flop_model / (ms * 1e-3) / 1e12
     line = {
         "metric": METRIC, "value": rays / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -375,11 +375,11 @@ def run_nf(args):
                 "ms_per_step": e2e_ms, "api": "solat_nf_map_host via maps.NearFieldPlan.run"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": 1127168 + 50432 + 93952, "flop_per_unit": 520.0, "units_per_launch": npix * plan.active_rays,
-                     "executed_tflops": flop_exec / (ms * 1e-3) / 1e12, "fp64_pipe_pct_ncu": 53.8,
-                     "kernel": "ff_pair_kernel + nf_map_kernel<1,1,true> + nf_finalize_kernel, CUDA events around the three",
+                     "traffic": 1244928 + 50944 + 135424, "flop_per_unit": 520.0, "units_per_launch": npix * plan.active_rays,
+                     "executed_tflops": flop_exec / (ms * 1e-3) / 1e12, "fp64_pipe_pct_ncu": 49.6,
+                     "kernel": "ff_pair_kernel + nf_map_kernel<1,1,2> + nf_finalize_kernel, CUDA events around the three",
                      "note": "achieved/frac follow SURVEY 8d's model (520 FLOP per traced source ray, every pixel traced on its own); "
-                             "the kernel traces a ray once for the mirror pixels (+x, z) and (-x, z), so frac can exceed what the "
+                             "the kernel traces a ray once for the four mirror pixels (+-x, +-z), so frac can exceed what the "
                              "pipes do; executed_tflops = ncu thread-level FP64 operation counts over the same measured time"},
         "ray_status": int(plan.status()),
     }
