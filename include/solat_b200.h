@@ -122,7 +122,8 @@ SOLAT_API int solat_nf_map_device(solat_nf_plan *plan, const double *d_src_xz, i
  * of the per-pixel integral (scripts/holo_sim.py:157-176) for a receiver-offset sweep.                          */
 SOLAT_API int solat_nf_rx_fields(solat_ctx *ctx, const solat_nf_geom *g, const double *p_rx, int nrx, const double *theta, int nth,
                        const double *phi, int nph, double *opl, double *amp, int *status);
-/* (near-field maps share a trace between the source positions (x, z) and (-x, z) the same way)
+/* (near-field maps share a trace between the source positions (+-x, +-z) the same way when the fan is symmetric
+ * in phi and theta about pi/2: a position on the negative side of an axis is computed as a mirror image)
  * traced rays per pixel after culling (for FLOP accounting) */
 SOLAT_API int solat_nf_plan_active_rays(const solat_nf_plan *plan);
 /* number of output channels nrx * nfreq */
