@@ -9,6 +9,8 @@
 //   nf_map_kernel<NF,NT,MODE>  fused source trace + phase + aperture integral: one CTA per (work item, ray tile), a
 //                          work item being a source position, the mirror pair (+-x, z) or the quad (+-x, +-z); rays
 //                          culled by the receiver weight; warp-shuffle + shared-memory block reduce
+//   nf_phase_kernel,       sweeps over more than 16 receiver tables: exp(i k L) of every (quad item, ray), traced once,
+//   nf_contract_kernel     and its complex matrix product with all the phasor tables (register-tiled FP64, 64 x 64 per CTA)
 //   nf_finalize_kernel     fixed-order sum of tile partials -> amp, phase
 //   ff_rows_kernel<STAGE>  thread-per-ray dump of ray_mirror_pts / aperature_fields_from_panel_model
 //   ff_project_*           last-write-wins scatter (atomicMax on the ray index) + phasor fill
@@ -633,6 +635,111 @@ __global__ void nf_phasor_mirror_kernel(const double2* ph, const int* amap, int 
     const int m = (int)(idx / per_image), a = (int)(idx % n_act);
     const long long ch = (idx - m * per_image) / n_act;
     out[idx] = ph[ch * n_act + (m ? amap[(size_t)(m - 1) * n_act + a] : a)];
+}
+
+// ------------------------------------------------------------------------------------------------
+// near field, sweeps over many receiver tables: trace once, contract against every table
+// ------------------------------------------------------------------------------------------------
+// With more than NF_MAX_SUMS channels the fused kernel has to re-trace (and re-read the phasor tables, 16 bytes per
+// output pixel, ray and table: the 25-table map of BASELINE config 4 moved 7.6 GB out of L2).  Here the quad items
+// are traced ONCE per wavenumber into E[item][a] = exp(i k L) (0 for a ray that does not arrive), and the maps are the
+// complex matrix product  out[item][m * nrx + j] = sum_a E[item][a] * phasor[m][j][f][a]  -- m the mirror image, j the
+// receiver table -- computed by a register-tiled FP64 kernel (64 x 64 outputs per CTA, 4 x 4 per thread; every table
+// entry read from L2 once per 64 items).  The ray range is cut into `splits` pieces that depend on the ray count only,
+// nf_finalize_kernel adds them up in order.
+__global__ void __launch_bounds__(NF_T, SOLAT_NF_MINB) nf_phase_kernel(NfMapParams q, int row0, int rows, double2* E, int ldE)
+{
+    const Coef& sC = K_COEF;
+    const int r = blockIdx.x / q.tiles, tile = blockIdx.x - r * q.tiles;
+    const int item = row0 + r;
+    if (r >= rows || item >= __ldg(q.counters2)) return;
+    const FfItem it = q.items2[item];
+    const vec3 p0 = mk(it.el, q.y_ap, it.az);
+    int st = 0;
+    const int q_end = min((tile + 1) * q.tile_len, q.n_act);
+    for (int a = tile * q.tile_len + threadIdx.x; a < q_end; a += NF_T) {
+        const double2 l0 = __ldg(q.first_leg + 4 * a), l1 = __ldg(q.first_leg + 4 * a + 1), l2 = __ldg(q.first_leg + 4 * a + 2),
+                      l3 = __ldg(q.first_leg + 4 * a + 3);
+        NfSourceRay ray;
+        ray.p1b = mk(fma(l0.y, l0.x, p0.x), l1.x, fma(l1.y, l0.x, p0.z));
+        nf_source_ray_from_1b(sC, mk(l2.x, l2.y, l3.x), l0.x, (int)l3.y, q.n_si, q.n_vac, ray);
+        st |= ray.status;
+        double sn = 0.0, cs = 0.0;
+        if (ray.valid) sincos_mid(ray.opl * q.kk[0], sn, cs);                     // holo_sim.py:177
+        E[(size_t)r * ldE + a] = make_double2(cs, sn);
+    }
+    if (st) atomicOr(q.status, st);
+}
+
+constexpr int NF_GM = 64, NF_GN = 64, NF_GK = 8;
+struct NfContractParams {
+    const double2* E;          // [rows][ldE]
+    const double2* phasor;     // [4][nrx][nfreq][n_act]
+    const FfItem* items;       // pair items
+    const FfItem* items2;      // quad items
+    const int* counters2;
+    int row0, rows, ldE, n_act, nrx, nfreq, f, nch_total, splits, k_len, pix0;
+    double2* partial;          // [npix][splits][nch_total]
+};
+__global__ void __launch_bounds__(256) nf_contract_kernel(NfContractParams q)
+{
+    __shared__ double2 As[NF_GK][NF_GM + 1], Bs[NF_GK][NF_GN + 1];
+    const int count = min(__ldg(q.counters2) - q.row0, q.rows);       // rows of E that hold an item
+    const int r0 = blockIdx.x * NF_GM;
+    if (r0 >= count) return;
+    const int N = 4 * q.nrx, c0 = blockIdx.y * NF_GN, split = blockIdx.z;
+    const int k_begin = split * q.k_len, k_end = min(k_begin + q.k_len, q.n_act);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double re[4][4], im[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) re[i][j] = im[i][j] = 0.0;
+    for (int k0 = k_begin; k0 < k_end; k0 += NF_GK) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int idx = threadIdx.x + 256 * u, r = idx >> 3, kk = idx & 7, k = k0 + kk;
+            double2 va = make_double2(0.0, 0.0), vb = va;
+            if (k < k_end) {
+                if (r0 + r < count) va = q.E[(size_t)(r0 + r) * q.ldE + k];
+                if (c0 + r < N) vb = __ldg(q.phasor + ((size_t)(c0 + r) * q.nfreq + q.f) * q.n_act + k);   // row m * nrx + j
+            }
+            As[kk][r] = va; Bs[kk][r] = vb;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < NF_GK; kk++) {
+            double2 a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { a[i] = As[kk][ty + 16 * i]; b[i] = Bs[kk][tx + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    re[i][j] = fma(b[j].x, a[i].x, fma(-b[j].y, a[i].y, re[i][j]));
+                    im[i][j] = fma(b[j].x, a[i].y, fma(b[j].y, a[i].x, im[i][j]));
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = r0 + ty + 16 * i;
+        if (r >= count) continue;
+        const FfItem it = q.items2[q.row0 + r];
+        int o0 = -1, o1 = -1, o2 = -1, o3 = -1;
+        if (it.pos >= 0) { o0 = q.items[it.pos].pos; o1 = q.items[it.pos].neg; }
+        if (it.neg >= 0) { o2 = q.items[it.neg].pos; o3 = q.items[it.neg].neg; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int c = c0 + tx + 16 * j;
+            if (c >= N) continue;
+            const int m = c / q.nrx, t = c - m * q.nrx;
+            const int pixel = m == 0 ? o0 : (m == 1 ? o1 : (m == 2 ? o2 : o3));
+            if (pixel >= 0)
+                q.partial[((size_t)(q.pix0 + pixel) * q.splits + split) * q.nch_total + (size_t)t * q.nfreq + q.f] = make_double2(re[i][j], im[i][j]);
+        }
+    }
 }
 
 // Fixed-order sum of the tile partials -> amp, phase (holo_sim.py:181-182).  (Folding this into nf_map_kernel -- the CTA
@@ -1522,6 +1629,7 @@ struct solat_nf_plan {
     DevBuf<FfItem> items;                   // work items of a paired map: [npix] pairs, then [npix] quads
     DevBuf<int> pair_ints;
     DevBuf<double> pair_xz;                 // (z, |x|) of the pair items, the list the quad stage pairs
+    DevBuf<double2> phase_e;                // many-table sweeps: exp(i k L) of every (quad item, ray)
     int sym = 0;                            // bit 0 / bit 1: fan and active set are mirror symmetric in x / in z
     int pairs = 1, quads = 1;               // work items of two / four pixels allowed (SOLAT_NF_QUADS=0: pairs only)
     DevBuf<double2> partial;
@@ -1560,6 +1668,61 @@ static void nf_launch_one(const NfMapParams& q, int grid, int threads, cudaStrea
     else nf_map_kernel<NF, NT, 0><<<grid, threads, 0, s>>>(q);
 }
 
+// Many-table sweeps of a plan with both mirror symmetries: quad items, one trace per wavenumber, one contraction
+// (nf_phase_kernel, nf_contract_kernel).  Lists above FF_PAIR_ONE_CTA pixels go through in pieces of that size and the
+// ray range is cut by the ray count alone, so a pixel's bits do not depend on the list it comes in.
+static int nf_map_contract(solat_nf_plan* p, const double* d_src, int npix, double* d_amp, double* d_phase, cudaStream_t s)
+{
+    const int nfreq = (int)p->kk.size(), nch = nfreq * p->nrx;
+    const int k_len = ((std::max(512, (p->n_act + 31) / 32) + NF_GK - 1) / NF_GK) * NF_GK;
+    const int splits = (p->n_act + k_len - 1) / k_len;
+    const int piece = std::min(npix, FF_PAIR_ONE_CTA);
+    // rows of E per pass: 256 MB at most
+    const int ldE = (p->n_act + 1) & ~1;
+    const int rows_max = (int)std::max<size_t>(NF_GM, std::min<size_t>((size_t)piece, ((size_t)256 << 20) / ((size_t)ldE * sizeof(double2))));
+    if (int rc = p->partial.reserve((size_t)npix * splits * nch)) return rc;
+    if (int rc = p->items.reserve(2 * (size_t)piece)) return rc;
+    if (int rc = p->pair_ints.reserve(8)) return rc;
+    if (int rc = p->pair_xz.reserve(2 * (size_t)piece)) return rc;
+    if (int rc = p->phase_e.reserve((size_t)rows_max * ldE)) return rc;
+    NfMapParams q;
+    q.ang = p->ang.tabs; q.src_xz = d_src; q.act_idx = p->act_idx.p; q.phasor = p->phasor.p; q.first_leg = p->first_leg.p;
+    q.y_ap = p->g.y_ap; q.n_si = p->g.n_si; q.n_vac = p->g.n_vac;
+    q.n_act = p->n_act; q.tiles = p->tiles; q.tile_len = p->tile_len; q.nfreq_total = nfreq; q.nch_total = nch;
+    q.partial = p->partial.p; q.status = p->status.p; q.sym = p->sym; q.f0 = q.j0 = 0;
+    q.items = p->items.p; q.items2 = p->items.p + piece; q.counters = p->pair_ints.p; q.counters2 = p->pair_ints.p + 2;
+    NfContractParams g;
+    g.E = p->phase_e.p; g.phasor = p->phasor.p; g.items = q.items; g.items2 = q.items2; g.counters2 = q.counters2;
+    g.ldE = ldE; g.n_act = p->n_act; g.nrx = p->nrx; g.nfreq = nfreq; g.nch_total = nch; g.splits = splits; g.k_len = k_len;
+    g.partial = p->partial.p;
+    for (int pix0 = 0; pix0 < npix; pix0 += piece) {
+        const int n = std::min(piece, npix - pix0);
+        ff_pair_kernel<<<1, 1024, ff_pair_smem(n), s>>>(d_src + 2 * (size_t)pix0, n, p->pair_ints.p, p->items.p, NF_PAIR_TOL,
+                                                        p->items.p + piece, p->pair_xz.p);
+        LAUNCHED();
+        g.pix0 = pix0;
+        // the number of quad items is known on the device only: passes over [row0, row0 + rows) up to the bound n, the
+        // CTAs of a pass past the last item return at once
+        for (int row0 = 0; row0 < n; row0 += rows_max) {
+            const int rows = std::min(rows_max, n - row0);
+            g.row0 = row0; g.rows = rows;
+            for (int f = 0; f < nfreq; f++) {
+                for (int k = 0; k < NF_MAXF; k++) q.kk[k] = k == 0 ? p->kk[f] / 1e3 : 0.0;
+                nf_phase_kernel<<<rows * p->tiles, p->threads, 0, s>>>(q, row0, rows, p->phase_e.p, ldE);
+                LAUNCHED();
+                g.f = f;
+                const dim3 grid((rows + NF_GM - 1) / NF_GM, (4 * p->nrx + NF_GN - 1) / NF_GN, splits);
+                nf_contract_kernel<<<grid, 256, 0, s>>>(g);
+                LAUNCHED();
+            }
+        }
+    }
+    const int tot = npix * nch;
+    nf_finalize_kernel<<<(tot + 127) / 128, 128, 0, s>>>(p->partial.p, npix, splits, nch, d_amp, d_phase);
+    LAUNCHED();
+    return SOLAT_OK;
+}
+
 static int nf_map_launch(solat_nf_plan* p, const double* d_src, int npix, double* d_amp, double* d_phase, cudaStream_t s)
 {
     CK(cudaSetDevice(p->ctx->device));
@@ -1570,6 +1733,9 @@ static int nf_map_launch(solat_nf_plan* p, const double* d_src, int npix, double
         return SOLAT_OK;
     }
     nf_choose_tiling(p);
+    // (the contraction traces once per wavenumber: it pays for many TABLES, 25 tables 51x51 px 2.44 -> 0.84 ms)
+    if (p->sym == 3 && p->pairs && p->quads && p->nrx > NF_MAX_SUMS && !(getenv("SOLAT_NF_CONTRACT") && getenv("SOLAT_NF_CONTRACT")[0] == '0'))
+        return nf_map_contract(p, d_src, npix, d_amp, d_phase, s);
     if (int rc = p->partial.reserve((size_t)npix * p->tiles * nch)) return rc;
     NfMapParams q;
     q.ang = p->ang.tabs; q.src_xz = d_src; q.act_idx = p->act_idx.p; q.phasor = p->phasor.p; q.first_leg = p->first_leg.p;
@@ -1579,8 +1745,9 @@ static int nf_map_launch(solat_nf_plan* p, const double* d_src, int npix, double
     q.items = q.items2 = nullptr; q.counters = q.counters2 = nullptr;
     q.sym = p->sym;
     // work items: pairs (+-x, z) when the plan is symmetric in x, quads (+-x, +-z) when it is symmetric in z as well
-    // (a sweep over many receiver tables is bound by the reads of the phasor tables, one per output pixel, ray and table
-    // whatever the work item is: 25 tables, 51x51 px: 2.47 ms one pixel per CTA, 2.70 ms as quads)
+    // (with more channels than that the fused kernel is bound by the reads of the phasor tables, one per output pixel,
+    // ray and table whatever the work item is: 25 tables, 51x51 px: 2.47 ms one pixel per CTA, 2.70 ms as quads;
+    // sweeps over many tables take nf_map_contract above)
     const bool pairs = (p->sym & 1) && p->pairs && npix <= FF_PAIR_ONE_CTA && nch <= NF_MAX_SUMS;
     const bool quads = pairs && (p->sym & 2) && p->quads;
     if (pairs) {

@@ -205,6 +205,44 @@ def test_nf_receiver_offset_sweep_shares_the_source_trace(oracle):
         np.testing.assert_array_equal(a1, a[j]); np.testing.assert_array_equal(p1, p[j])
 
 
+def test_nf_many_table_sweep_contraction(oracle, monkeypatch):
+    """More than 16 receiver tables on a plan with both mirror symmetries: the quad items are traced once into
+    exp(i k L) and contracted against every table (nf_phase_kernel + nf_contract_kernel).  Against one plan per table
+    (the fused kernel; another summation order: 1e-11 of the map's peak), against the fused kernel on the same plan
+    (SOLAT_NF_CONTRACT=0), against the oracle; bit-identical under permutation, subsets and lists above 4096 pixels."""
+    from solat_optics_b200 import maps
+
+    tg = maps.holo_tele_geo(150.0, 36)
+    ax = np.linspace(-60.0, 60.0, 5)
+    offsets = [(x, 0.0, z) for x in ax for z in ax][:21]
+    opl, w = maps.receiver_fields(tg, offsets, device=0)
+    px = maps.holo_pixels(res=9, sweep=100)
+    k2 = [tg.k, 1.31 * tg.k]
+    for kk in ([tg.k], k2):
+        plan = maps.NearFieldPlan(tg, kk, opl, w, device=0)
+        a, p, st = plan.run(px)                                   # [21, nfreq, 81]
+        assert st == 0 and a.shape == (21, len(kk), 81)
+        monkeypatch.setenv("SOLAT_NF_CONTRACT", "0")
+        a_f, p_f, _ = plan.run(px)
+        monkeypatch.delenv("SOLAT_NF_CONTRACT")
+        e, e_f = a * np.exp(1j * p), a_f * np.exp(1j * p_f)
+        assert np.abs(e - e_f).max() <= 1e-11 * np.abs(e_f).max()
+        for j in (0, 7, 20):
+            a1, p1, _ = maps.NearFieldPlan(tg, kk, opl[j], w[j], device=0).run(px)
+            e1 = a1 * np.exp(1j * p1)
+            assert np.abs(e[j] - e1).max() <= 1e-11 * np.abs(e1).max()
+            orx = oracle.nf_rx_trace(offsets[j], tg.th_fwhp, 36)
+            oa, op = oracle.nf_map(px, tg.y_ap, 36, orx[3], orx[4] * gu.lyot_mask(36), kk)
+            for f in range(len(kk)):
+                _assert_pixels(a[j, f], p[j, f], oa[f], op[f])
+        rng = np.random.default_rng(5)
+        for sel in (rng.permutation(len(px)), np.nonzero(px[:, 1] < 0)[0], rng.permutation(len(px))[:29],
+                    np.tile(np.arange(len(px)), 52)[:4200]):
+            a_s, p_s, _ = plan.run(px[sel])
+            np.testing.assert_array_equal(a_s, a[:, :, sel]); np.testing.assert_array_equal(p_s, p[:, :, sel])
+        plan.close()
+
+
 def test_nf_mirror_pairs(oracle, monkeypatch):
     """The optics tube is symmetric under x -> -x and so is the launch fan: the near-field map traces a ray once for
     the source positions (+x, z) and (-x, z).  Canonical pixels (x >= 0, z >= 0) bit-identical with the pair walk on and
