@@ -681,7 +681,7 @@ struct NfContractParams {
     int row0, rows, ldE, n_act, nrx, nfreq, f, nch_total, splits, k_len, pix0;
     double2* partial;          // [npix][splits][nch_total]
 };
-__global__ void __launch_bounds__(256) nf_contract_kernel(NfContractParams q)
+__global__ void __launch_bounds__(256, 2) nf_contract_kernel(NfContractParams q)
 {
     __shared__ double2 As[NF_GK][NF_GM + 1], Bs[NF_GK][NF_GN + 1];
     const int count = min(__ldg(q.counters2) - q.row0, q.rows);       // rows of E that hold an item
@@ -690,35 +690,50 @@ __global__ void __launch_bounds__(256) nf_contract_kernel(NfContractParams q)
     const int N = 4 * q.nrx, c0 = blockIdx.y * NF_GN, split = blockIdx.z;
     const int k_begin = split * q.k_len, k_end = min(k_begin + q.k_len, q.n_act);
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    // staging: thread -> rows sr and sr + 32 of both tiles, ray k0 + sk
+    const int sr = threadIdx.x >> 3, sk = threadIdx.x & 7;
+    const bool a_on0 = r0 + sr < count, a_on1 = r0 + sr + 32 < count, b_on0 = c0 + sr < N, b_on1 = c0 + sr + 32 < N;
+    const double2* pa0 = q.E + (size_t)(r0 + sr) * q.ldE + sk;
+    const double2* pa1 = pa0 + (size_t)32 * q.ldE;
+    const double2* pb0 = q.phasor + ((size_t)(c0 + sr) * q.nfreq + q.f) * q.n_act + sk;     // row m * nrx + j
+    const double2* pb1 = pb0 + (size_t)32 * q.nfreq * q.n_act;
+    const double2 zero = make_double2(0.0, 0.0);
     double re[4][4], im[4][4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) re[i][j] = im[i][j] = 0.0;
+    // the columns of this tile come in four groups of 16 (one per j): groups past the last column are skipped
+    const int groups = min(4, (N - c0 + 15) >> 4);
+    double2 va0, va1, vb0, vb1;
+    {
+        const bool k_on = k_begin + sk < k_end;
+        va0 = k_on && a_on0 ? pa0[k_begin] : zero; va1 = k_on && a_on1 ? pa1[k_begin] : zero;
+        vb0 = k_on && b_on0 ? __ldg(pb0 + k_begin) : zero; vb1 = k_on && b_on1 ? __ldg(pb1 + k_begin) : zero;
+    }
     for (int k0 = k_begin; k0 < k_end; k0 += NF_GK) {
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int idx = threadIdx.x + 256 * u, r = idx >> 3, kk = idx & 7, k = k0 + kk;
-            double2 va = make_double2(0.0, 0.0), vb = va;
-            if (k < k_end) {
-                if (r0 + r < count) va = q.E[(size_t)(r0 + r) * q.ldE + k];
-                if (c0 + r < N) vb = __ldg(q.phasor + ((size_t)(c0 + r) * q.nfreq + q.f) * q.n_act + k);   // row m * nrx + j
-            }
-            As[kk][r] = va; Bs[kk][r] = vb;
-        }
+        As[sk][sr] = va0; As[sk][sr + 32] = va1; Bs[sk][sr] = vb0; Bs[sk][sr + 32] = vb1;
         __syncthreads();
+        {   // the next stretch of rays is on its way while this one is multiplied
+            const int kn = k0 + NF_GK;
+            const bool k_on = kn + sk < k_end;
+            va0 = k_on && a_on0 ? pa0[kn] : zero; va1 = k_on && a_on1 ? pa1[kn] : zero;
+            vb0 = k_on && b_on0 ? __ldg(pb0 + kn) : zero; vb1 = k_on && b_on1 ? __ldg(pb1 + kn) : zero;
+        }
 #pragma unroll
         for (int kk = 0; kk < NF_GK; kk++) {
             double2 a[4], b[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) { a[i] = As[kk][ty + 16 * i]; b[i] = Bs[kk][tx + 16 * i]; }
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) {
+                if (j >= groups) break;                                            // CTA-uniform
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
+                for (int i = 0; i < 4; i++) {
                     re[i][j] = fma(b[j].x, a[i].x, fma(-b[j].y, a[i].y, re[i][j]));
                     im[i][j] = fma(b[j].x, a[i].y, fma(b[j].y, a[i].x, im[i][j]));
                 }
+            }
         }
         __syncthreads();
     }
@@ -1674,7 +1689,7 @@ static void nf_launch_one(const NfMapParams& q, int grid, int threads, cudaStrea
 static int nf_map_contract(solat_nf_plan* p, const double* d_src, int npix, double* d_amp, double* d_phase, cudaStream_t s)
 {
     const int nfreq = (int)p->kk.size(), nch = nfreq * p->nrx;
-    const int k_len = ((std::max(512, (p->n_act + 31) / 32) + NF_GK - 1) / NF_GK) * NF_GK;
+    const int k_len = ((std::max(256, (p->n_act + 31) / 32) + NF_GK - 1) / NF_GK) * NF_GK;
     const int splits = (p->n_act + k_len - 1) / k_len;
     const int piece = std::min(npix, FF_PAIR_ONE_CTA);
     // rows of E per pass: 256 MB at most
