@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- scan-pixel*rays/s of the beam-simulation hot path on N B200 GPUs of one node.
+"""bench.py -- scan-pixel*rays/s and full-map wall time of the beam-simulation hot path on N B200 GPUs of one node.
 
-Workload (BASELINE.json configs[1], the far-field LAT simulation `ff_sim.py 140 0.25 20 1.32`):
-one step = one full 41x41-pixel far-field map, 100^2 rays launched per pixel, 140 GHz, focal plane
-1.32 m, E_rec = the 51x51 near-field map of config 0 produced by this build (outside the timed region).
-With N GPUs every rank computes one such map (focal-plane offset 1.32 m + 1 cm * rank, the
-quant-systematics sweep of configs[3]): weak scaling, the pixels are independent and there is no data-path
-collective.  The only collective of the path is the final gather of the (amp, phase) blocks to rank 0; it is
-part of the end-to-end step (e2e), where the results have to reach rank 0's host memory, not of the
-device-resident step (value), whose results stay in each rank's HBM.
+Headline workload (BASELINE.json configs[4], the north-star scaling case; SURVEY.md section 8d "Config 5"):
+one step = ONE far-field LAT map of 401 x 401 scan pixels x 1000^2 rays launched per pixel (1.608e11 pixel*rays),
+140 GHz, focal plane 1.32 m, closed-form E_rec on a 101 x 101 grid, computed the way `scripts/ff_sim.py` does it
+through `maps.ff_map`: STRONG scaling -- the mirror pairs (+-az, el) of the one map are dealt over the N ranks
+(maps.shard_groups), every rank runs the fused kernels over its pixels and ONE NCCL gather brings (amp, phase, status)
+to rank 0, inside the timed region.  It replaces the reference's fan-out scripts/beamsim_set.sh:7 and the master /
+worker loop scripts/ff_sim.py:135-227.
 
-  value : whole-job pixel*rays/s with inputs resident in HBM, timed with CUDA events per step
-  e2e   : the same through the host-buffer C-ABI call (pinned host in, host out, copies inside)
-  --impl reference : the reference's CPU algorithm (oracle port, all host threads) on a bounded sample
+  value : pixel*rays/s of the whole job, pixel shards resident in HBM, kernels + NCCL gather timed with CUDA events
+  e2e   : the same map through the public call `maps.ff_map(...)` with HOST buffers: pixel upload, kernels, gather,
+          download of the gathered map to rank 0's host memory and the un-permute, wall clock (same call at every N)
+  configs : BASELINE.json configs[0..3] (near field 140 GHz; far field 41x41; frequency sweep; 25 receiver offsets)
+          as extra objects: device-resident ms, whole-call wall time warm / cold (plan creation included), roofline
+  parity_checked : 64 stratified pixels of the TIMED map (centre, edges, corners, az < 0, az = 0) against the CPU
+          oracle at the north-star tolerance (power 1e-6 relative, phase 1e-5 rad); the run fails if it breaks
+  --impl reference : the reference's CPU implementation on the host cores (the unmodified Python reference staged in
+          oracle/_ref when present, else the C port of the oracle), bounded sample per step
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -27,39 +33,72 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-NCU_DRAM_BYTES_PER_LAUNCH = 3595520 + 192512 + 99072 + 35840   # ff_map + ff_prep + ff_pair kernels, r1n capture (read + write)
-NCU_EXECUTED_FP64_FLOP_PER_LAUNCH = (2 * 743942311 + 224236359 + 115551260      # ff_map_kernel: DFMA x2 + DMUL + DADD thread instructions
-                                     + 2 * 19158972 + 7770525 + 5705847)        # ff_prep_kernel (r1n capture)
 METRIC = "scan_pixel_rays_per_s"
 UNIT = "pixel*rays/s"
-FREQ, RES_ARCMIN, NUM, OFFSET, N_SCAN = 140, 0.25, 20, 1.32, 100
-FLOP_PER_LAUNCHED_RAY = 626.0        # 1030 per valid ray, 20 per rejected, 60 % valid
-NOMINAL_FP64_TFLOPS = 37.2           # 148 SM x 64 DFMA lanes x 2 x 1.965 GHz
+# headline: BASELINE config 5
+FREQ, RES_ARCMIN, NUM, OFFSET, N_SCAN = 140, 0.05, 200, 1.32, 1000
+FLOP_FF_RAY = 626.0          # reference-shaped model, FP64 FLOP per launched far-field ray
+FLOP_NF_RAY = 520.0          # per traced near-field source ray
+NOMINAL_FP64_TFLOPS = 37.2   # 148 SM x 64 DFMA lanes x 2 x 1.965 GHz
+P_TOL, PHI_TOL = 1e-6, 1e-5  # north_star parity tolerance
+PROFILE_JSON = os.path.join(ROOT, "profiles", "r02_kernels.json")
 
 
 def workload_config(n_gpus):
+    side = 2 * NUM + 1
     return {
-        "workload": "ff_sim.py 140 0.25 20 1.32: far-field LAT map, 41x41 px x 100^2 rays, 140 GHz, focal plane 1.32 m"
-                    + ("" if n_gpus == 1 else "; one map per rank (offset +1 cm*rank), results left in each rank's HBM (e2e adds the NCCL gather to rank 0)"),
-        "pixels_per_map": (2 * NUM + 1) ** 2, "rays_per_pixel": N_SCAN ** 2, "maps": n_gpus,
-        "e_rec": "51x51 near-field map (holo_sim.py 140 defaults) computed by this build before timing",
-        "l2": "flushed between timed steps (256 MiB write); the path reads <1 MB per step",
+        "workload": "BASELINE configs[4]: ff_sim.py %d %g %d %g with a %d^2-ray fan: far-field LAT map, %dx%d px x %d^2 rays, "
+                    "closed-form E_rec on a 101x101 grid" % (FREQ, RES_ARCMIN, NUM, OFFSET, N_SCAN, side, side, N_SCAN),
+        "pixels_per_map": side * side, "rays_per_pixel": N_SCAN ** 2, "maps_per_step": 1,
+        "sharding": "one map per step; mirror pairs (+-az, el) dealt cyclically over %d rank(s); NCCL gather of (amp, phase, "
+                    "status) to rank 0 inside the timed region" % n_gpus,
+        "l2": "flushed between timed steps (256 MiB write); the path reads < 4 MB per step",
         "parallelism": "pixel-sharded x%d" % n_gpus,
     }
 
 
-def cpu_e_rec_stub():
-    """Closed-form stand-in for E_rec used only by the CPU reference arm when no GPU is present
-    (the arithmetic per ray does not depend on E_rec's values)."""
-    ax = np.linspace(-50, 50, 51) / 1e1
-    y, x = np.meshgrid(ax, ax, indexing="ij")
-    return x, y, np.exp(-(x ** 2 + y ** 2) / 4.5) * np.exp(0.3j * (x ** 2 + y ** 2))
+def e_rec_config5():
+    """x, y in linspace(-5, 5, 101) cm, amp exp(-(x^2+y^2)/(2 1.5^2)), phase 0.3 (x^2+y^2)."""
+    ax = np.linspace(-5, 5, 101)
+    yy, xx = np.meshgrid(ax, ax, indexing="ij")
+    return xx, yy, np.exp(-(xx ** 2 + yy ** 2) / (2 * 1.5 ** 2)) * np.exp(1j * 0.3 * (xx ** 2 + yy ** 2))
+
+
+def stratified_pixel_indices(side, k=8):
+    """k x k pixels of a side x side map: corners, edges, the centre row / column (az = 0), both signs of az."""
+    idx = np.round(np.linspace(0, side - 1, k)).astype(int)
+    idx[k // 2] = (side - 1) // 2
+    idx = np.unique(idx)
+    return np.array([i * side + j for i in idx for j in idx])
+
+
+def wrap(a):
+    return (a + np.pi) % (2 * np.pi) - np.pi
+
+
+def csrc_hash():
+    h = hashlib.sha256()
+    for f in ("solat_kernels.cu", "solat_math.cuh"):
+        h.update(open(os.path.join(ROOT, "solat_optics_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
+
+
+def load_profile():
+    """ncu figures of the timed kernels (tools/ncu_to_profile.py), valid only for the csrc/ they were captured on."""
+    try:
+        prof = json.load(open(PROFILE_JSON))
+    except Exception:
+        return None, "profiles/r02_kernels.json missing"
+    if prof.get("csrc_sha256") != csrc_hash():
+        return None, "profiles/r02_kernels.json was captured on another csrc/ (sha %s..., now %s...): executed figures withheld" % (
+            str(prof.get("csrc_sha256"))[:12], csrc_hash()[:12])
+    return prof, None
 
 
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.004):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self._stop_evt = [], set(), threading.Event()
@@ -116,45 +155,267 @@ def physical_gpu_index(local_rank):
 
 
 # --------------------------------------------------------------------------------------------------
-def run_reference(args):
-    """CPU arm: the oracle port of the reference algorithm (brentq per surface per ray, both passes of
-    ff_sim.py:208-209) with all host threads, on a bounded sample of the same map per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+# reference arm
+# --------------------------------------------------------------------------------------------------
+def ref_python_available():
+    return os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "solat_optics"))
+
+
+def port_sample(pixels, th, ph, x, y, e, k, rx_y, idx, two_pass=True):
+    """C port of the reference algorithm (oracle/solat_oracle.c: brentq per surface per ray, both passes of
+    ff_sim.py:208-209) on `idx` pixels of the map, all host threads.  Returns (amp, phase, seconds, threads)."""
     from oracle import oracle_lib as orc
+
+    geo = orc.ff_geo_vec(rx_y_m=rx_y)
+    t0 = time.perf_counter()
+    amp, pha = orc.ff_map(geo, pixels[idx], th, ph, x, y, e, k, two_pass=two_pass)
+    return amp, pha, time.perf_counter() - t0, orc.num_threads()
+
+
+def run_reference(args):
+    """CPU arm on the box's host cores, rank 0 only, a bounded sample of the headline workload per step.
+    kind "reference": the UNMODIFIED Python reference (staged by oracle/stage_ref.py into oracle/_ref, git-ignored)
+    run through its own functions ray_mirror_pts -> aperature_fields_from_panel_model -> project_to_data
+    (ff_sim.py:204-221), one multiprocessing worker per core, each step = one pixel per worker with the fan
+    subsampled to n_sub^2 rays (the reference's cost is per ray: a Python loop with brentq per surface).
+    kind "port": the C restatement of the same algorithm (second CPU line; the only one when oracle/_ref is absent)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
     from solat_optics_b200 import maps
 
     tg = maps.ff_tele_geo(FREQ, OFFSET)
     th, ph = maps.ff_fan(N_SCAN)
     pixels = maps.ff_pixels(tg, RES_ARCMIN, NUM)
-    x, y, e = cpu_e_rec_stub()
-    geo = orc.ff_geo_vec(rx_y_m=-OFFSET)
-    cores = orc.num_threads()
-    stride = 8
-    sample = pixels[::stride]
-    rays = len(sample) * N_SCAN ** 2
-    for _ in range(args.warmup):
-        orc.ff_map(geo, sample[: max(1, len(sample) // 8)], th, ph, x, y, e, tg.k, two_pass=True)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.ff_map(geo, sample, th, ph, x, y, e, tg.k, two_pass=True)
-    dt = (time.perf_counter() - t0) / args.steps
-    val = rays / dt
-    desc = "every %dth pixel of the 41x41 map (%d px x %d rays) per step, %d host threads" % (stride, len(sample), N_SCAN ** 2, cores)
-    line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
-                         "note": "C restatement of the reference's Python algorithm (oracle/solat_oracle.c); the "
-                                 "unmodified Python reference measured 5.3e2 pixel*rays/s per core (BASELINE.md)"},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
+    side = 2 * NUM + 1
+    x, y, e = e_rec_config5()
+    strat = stratified_pixel_indices(side)
+    # second CPU line: the C port on 16 stratified pixels at the full fan
+    _, _, port_s, port_threads = port_sample(pixels, th, ph, x, y, e, tg.k, tg.rx_y, strat[::4])
+    port = {"value": len(strat[::4]) * N_SCAN ** 2 / port_s, "unit": UNIT, "cores": port_threads, "kind": "port",
+            "sample": "%d stratified pixels x %d rays, both reference passes, %.1f s" % (len(strat[::4]), N_SCAN ** 2, port_s)}
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus)}
+    if ref_python_available() and not args.port_only:
+        from oracle import ref_bench
+
+        cores = os.cpu_count() or 1
+        n_sub = args.ref_rays
+        with ref_bench.Pool(cores) as pool:
+            order = np.resize(strat, cores * (args.steps + args.warmup))
+            jobs = [(FREQ, OFFSET, n_sub, float(pixels[i, 0]), float(pixels[i, 1])) for i in order]
+            for w in range(args.warmup):
+                pool.ff_pixels(jobs[w * cores:(w + 1) * cores])
+            t0 = time.perf_counter()
+            for s in range(args.steps):
+                pool.ff_pixels(jobs[(args.warmup + s) * cores:(args.warmup + s + 1) * cores])
+            dt = (time.perf_counter() - t0) / args.steps
+        val = cores * n_sub ** 2 / dt
+        full_map_h = side * side * float(N_SCAN) ** 2 / val / 3600.0
+        line.update({
+            "value": val, "ms_per_step": dt * 1e3,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "per_core": val / cores, "extrapolated_full_map_hours": full_map_h,
+                             "sample": "unmodified Python reference (oracle/_ref), %d workers x 1 stratified pixel x %d^2 rays "
+                                       "(fan subsampled from %d^2) per step" % (cores, n_sub, N_SCAN)},
+            "cpu_port": port,
+        })
+    else:
+        idx = strat[::4]
+        for _ in range(min(args.warmup, 1)):
+            port_sample(pixels, th, ph, x, y, e, tg.k, tg.rx_y, idx[:4])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            port_sample(pixels, th, ph, x, y, e, tg.k, tg.rx_y, idx[:max(2, port_threads // 8)])
+        dt = (time.perf_counter() - t0) / args.steps
+        val = max(2, port_threads // 8) * N_SCAN ** 2 / dt
+        line.update({"value": val, "ms_per_step": dt * 1e3,
+                     "cpu_baseline": {"value": val, "unit": UNIT, "cores": port_threads, "kind": "port",
+                                      "sample": "%d pixels x %d rays per step, C port of the reference algorithm"
+                                                % (max(2, port_threads // 8), N_SCAN ** 2),
+                                      "note": "oracle/_ref (the staged Python reference) is absent on this box"}})
+    line["e2e"] = {"value": line["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     print(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+class Timer:
+    """Device time with CUDA events on the current stream + host wall clock with barrier / synchronize fences."""
+
+    def __init__(self, world):
+        import torch
+
+        self.torch, self.world = torch, world
+
+    def fence(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return float(v)
+        import torch.distributed as dist
+
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def device_ms(self, fn, steps, warmup, flush=None):
+        """mean ms per call of fn() (device work enqueued on the current stream), L2 flushed between calls"""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.fence()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            if flush is not None:
+                flush.fill_(1)
+            a.record()
+            fn()
+            b.record()
+        self.fence()
+        return self.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / steps
+
+    def wall_s(self, fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        self.fence()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        self.fence()
+        return self.max_over_ranks(time.perf_counter() - t0) / steps
+
+
+def executed_entry(prof, workload, pixel_rays, ms, peak):
+    """FP64 operations the kernels of `workload` executed (ncu thread-level DFMA x2 + DMUL + DADD, per pixel*ray of the
+    captured launch) over the live-measured time."""
+    if prof is None or workload not in prof.get("workloads", {}):
+        return {}
+    w = prof["workloads"][workload]
+    flop = w["fp64_flop_per_pixel_ray"] * pixel_rays
+    tf = flop / (ms * 1e-3) / 1e12
+    dram = w.get("dram_bytes_per_pixel_ray")
+    return {"executed_fp64_flop": flop, "executed_tflops": tf, "frac": tf / peak, "frac_of_nominal": tf / NOMINAL_FP64_TFLOPS,
+            "traffic": None if dram is None else dram * pixel_rays,
+            "ncu": {k: w[k] for k in ("kernels", "captured_on") if k in w}}
+
+
+def sub_configs(tm, rank, world, local_rank, prof, peak, steps):
+    """BASELINE configs[0..3] through the public API (every rank calls; maps this small run on rank 0 alone)."""
+    import torch
+
+    from solat_optics_b200 import maps
+
+    out = {}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    ax = np.linspace(-60, 60, 5)
+    rx_pos = [(a, 0.0, b) for a in ax for b in ax]
+    nf = maps.holo_map(140.0, device=local_rank)
+    calls = {
+        "1_nf_140GHz": (lambda: maps.holo_map(140.0, device=local_rank), 2601 * 10 ** 4,
+                        "holo_sim.py 140: 51x51 source positions x 100^2 rays"),
+        "3_nf_sweep": (lambda: (maps.holo_map(90.0, device=local_rank), maps.holo_map([150.0, 220.0, 280.0], device=local_rank)),
+                       4 * 2601 * 10 ** 4, "near-field maps at 90 | 150, 220, 280 GHz (the three of one band share a trace)"),
+        "4_rx_offsets": (lambda: maps.receiver_offset_sweep(150.0, rx_pos, device=local_rank) if rank == 0 else None,
+                         25 * 2601 * 10 ** 4, "25 receiver offsets x near-field map at 150 GHz (one source trace, rank 0)"),
+    }
+    if world > 1:
+        obj = [nf]
+        import torch.distributed as dist
+
+        dist.broadcast_object_list(obj, src=0)
+        nf = obj[0]
+    px_nf, amp_nf, ph_nf = nf
+    dx, dy, e2 = maps.near_field_to_e_rec(np.c_[px_nf[:, 0], px_nf[:, 1], amp_nf[0], ph_nf[0]])
+    calls["2_ff_41x41"] = (lambda: maps.ff_map(140, 0.25, 20, 1.32, dx, dy, e2, device=local_rank), 1681 * 10 ** 4,
+                           "ff_sim.py 140 0.25 20 1.32: 41x41 px x 100^2 rays, E_rec = the 51x51 near-field map of config 1")
+    for name, (fn, pixel_rays, desc) in calls.items():
+        warm = tm.wall_s(fn, steps, 2)
+        maps.clear_plan_cache()
+        cold = tm.wall_s(fn, 1, 0)
+        out[name] = {"workload": desc, "pixel_rays": pixel_rays, "full_map_wall_s": warm, "full_map_wall_s_cold": cold,
+                     "pixel_rays_per_s_wall": pixel_rays / warm,
+                     "note": "wall clock of the public call, max over ranks; cold = plan cache cleared (table uploads, receiver trace)"}
+    if rank == 0:
+        # device-resident kernels of the same maps on one GPU
+        tg1 = maps.holo_tele_geo(140.0, 100)
+        rx_opl, rx_w = maps.receiver_field(tg1)
+        one = Timer(1)
+
+        def nf_dev(tg, ks, opl, w, key, flop_rays, wl):
+            plan = maps.near_field_plan(tg, ks, opl, w, 100, local_rank)
+            px = maps.holo_pixels()
+            d_px = torch.from_numpy(px).cuda()
+            n = plan.channels * len(px)
+            d_a = torch.empty(n, dtype=torch.float64, device="cuda")
+            d_p = torch.empty_like(d_a)
+            l0 = _lib_launches()
+            ms = one.device_ms(lambda: plan.run_device(d_px, d_a, d_p, stream), steps, 3, flush)
+            launches = (_lib_launches() - l0) // (steps + 3)
+            model = FLOP_NF_RAY * len(px) * plan.active_rays * flop_rays / (ms * 1e-3) / 1e12
+            out[key].update({"ms": ms, "pixel_rays_per_s": out[key]["pixel_rays"] / (ms * 1e-3), "launches_per_map": int(launches),
+                             "roofline": dict({"bound": "fp64_simt", "peak": peak, "unit": "TFLOP/s", "model_tflops": model,
+                                               "model_speedup": model / peak},
+                                              **executed_entry(prof, wl, out[key]["pixel_rays"], ms, peak))})
+
+        nf_dev(tg1, [tg1.k], rx_opl, rx_w, "1_nf_140GHz", 1, "cfg1")
+        tg3 = maps.holo_tele_geo(150.0, 100)
+        opl3, w3 = maps.receiver_field(tg3)
+        opl4, w4 = maps.receiver_fields(tg3, rx_pos, 100, local_rank)
+        nf_dev(tg3, [tg3.k], opl4, w4, "4_rx_offsets", 25, "cfg4")
+        # config 3 = one map at 90 GHz + one three-wavenumber map
+        tg90 = maps.holo_tele_geo(90.0, 100)
+        o90, w90 = maps.receiver_field(tg90)
+        ks3 = [maps.holo_tele_geo(f, 100).k for f in (150.0, 220.0, 280.0)]
+        pa, pb = maps.near_field_plan(tg90, [tg90.k], o90, w90, 100, local_rank), maps.near_field_plan(tg3, ks3, opl3, w3, 100, local_rank)
+        px = maps.holo_pixels()
+        d_px = torch.from_numpy(px).cuda()
+        d_a = torch.empty(3 * len(px), dtype=torch.float64, device="cuda")
+        d_p = torch.empty_like(d_a)
+        ms3 = one.device_ms(lambda: (pa.run_device(d_px, d_a, d_p, stream), pb.run_device(d_px, d_a, d_p, stream)), steps, 3, flush)
+        out["3_nf_sweep"].update({"ms": ms3, "pixel_rays_per_s": out["3_nf_sweep"]["pixel_rays"] / (ms3 * 1e-3)})
+        # config 2
+        tg2 = maps.ff_tele_geo(140, 1.32)
+        th2, ph2 = maps.ff_fan(100)
+        plan2 = maps.far_field_plan(tg2, th2, ph2, dx, dy, e2, local_rank)
+        fpx = maps.ff_pixels(tg2, 0.25, 20)
+        d_az = torch.from_numpy(fpx).cuda()
+        d_a = torch.empty(len(fpx), dtype=torch.float64, device="cuda")
+        d_p = torch.empty_like(d_a)
+        l0 = _lib_launches()
+        ms2 = one.device_ms(lambda: plan2.run_device(d_az, d_a, d_p, stream), steps, 3, flush)
+        launches = (_lib_launches() - l0) // (steps + 3)
+        model = FLOP_FF_RAY * 1681 * 10 ** 4 / (ms2 * 1e-3) / 1e12
+        out["2_ff_41x41"].update({"ms": ms2, "pixel_rays_per_s": 1681 * 10 ** 4 / (ms2 * 1e-3), "launches_per_map": int(launches),
+                                  "ray_status": int(plan2.status()),
+                                  "roofline": dict({"bound": "fp64_simt", "peak": peak, "unit": "TFLOP/s", "model_tflops": model,
+                                                    "model_speedup": model / peak},
+                                                   **executed_entry(prof, "cfg2", 1681 * 10 ** 4, ms2, peak))})
+        # parity of the config-2 map the bench itself timed (its own E_rec): every 8th pixel against the oracle
+        amp2, pha2 = d_a.cpu().numpy(), d_p.cpu().numpy()
+        idx = np.arange(0, len(fpx), 8)
+        o_amp, o_pha, _, _ = port_sample(fpx, th2, ph2, dx, dy, e2, tg2.k, tg2.rx_y, idx, two_pass=False)
+        dP = np.max(np.abs(amp2[idx] ** 2 - o_amp ** 2) / o_amp ** 2)
+        dphi = np.max(np.abs(wrap(pha2[idx] - o_pha)))
+        out["2_ff_41x41"]["parity_checked"] = {"pixels": int(len(idx)), "max_dP_rel": float(dP), "max_dphi_rad": float(dphi),
+                                               "ok": bool(dP <= P_TOL and dphi <= PHI_TOL)}
+    return out
+
+
+def _lib_launches():
+    from solat_optics_b200 import _lib
+
+    return _lib.launch_count()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -171,235 +432,154 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=dev)
-
+    tm = Timer(world)
     ctx = _lib.context(local_rank)
-    # ---- untimed set-up: E_rec from our own near-field map (config 0), plans, pinned buffers
-    tgn = maps.holo_tele_geo(float(FREQ), 100)
-    rx_opl, rx_w = maps.receiver_field(tgn)
-    nplan = maps.NearFieldPlan(tgn, [tgn.k], rx_opl, rx_w, device=local_rank)
-    px_nf = maps.holo_pixels()
-    amp_nf, ph_nf, _ = nplan.run(px_nf)          # every rank builds the same 51x51 table (a few ms)
-    nplan.close()
-    data_x, data_y, e_rec = maps.near_field_to_e_rec(np.c_[px_nf[:, 0], px_nf[:, 1], amp_nf[0], ph_nf[0]])
-    tg = maps.ff_tele_geo(FREQ, OFFSET + 0.01 * rank)
-    th, ph = maps.ff_fan(N_SCAN)
-    plan = maps.FarFieldPlan(tg, th, ph, data_x, data_y, e_rec, device=local_rank)
-    pixels = maps.ff_pixels(tg, RES_ARCMIN, NUM)
-    npix = len(pixels)
-    rays_per_step = npix * N_SCAN ** 2 * world
+    warmup = max(args.warmup, 3)
 
-    h_azel = torch.from_numpy(pixels.copy()).pin_memory()
-    h_amp = torch.empty(npix, dtype=torch.float64).pin_memory()
-    h_phase = torch.empty(npix, dtype=torch.float64).pin_memory()
-    d_azel = h_azel.to(dev)
-    d_out = torch.empty((2, npix), dtype=torch.float64, device=dev)      # rows: amp, phase
-    # rank 0 gathers into views of ONE device tensor, so the gathered map leaves with a single D2H copy
-    d_all = torch.empty((world, 2, npix), dtype=torch.float64, device=dev) if (world > 1 and rank == 0) else None
-    gathered = list(d_all.unbind(0)) if d_all is not None else None
+    # ---- headline workload: one config-5 map per step, dealt over the ranks
+    num = args.num if args.num else NUM
+    n_scan = args.n_scan if args.n_scan else N_SCAN
+    side = 2 * num + 1
+    x, y, e = e_rec_config5()
+    tg = maps.ff_tele_geo(FREQ, OFFSET)
+    th, ph = maps.ff_fan(n_scan)
+    pixels = maps.ff_pixels(tg, RES_ARCMIN, num)
+    pixel_rays = len(pixels) * float(n_scan) ** 2
+
+    def public_call():
+        return maps.ff_map(FREQ, RES_ARCMIN, num, OFFSET, x, y, e, n_scan=n_scan, device=local_rank)
+
+    # cold call first: context, plan creation, table uploads, scratch allocation all inside
+    tm.fence()
+    t0 = time.perf_counter()
+    public_call()
+    tm.fence()
+    first_call_s = tm.max_over_ranks(time.perf_counter() - t0)
+
+    plan = maps.far_field_plan(tg, th, ph, x, y, e, local_rank)
+    sm = maps.ShardedMap(plan, pixels, False, rank, world)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
 
-    def device_step():
-        plan.run_device(d_azel, d_out[0], d_out[1], stream)
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident throughput (value): CUDA events per step, L2 flushed between steps
-    for _ in range(max(args.warmup, 3)):
-        device_step()
-    sync_all()
+    # ---- value: device-resident step = fused kernels + NCCL gather, CUDA events, max over ranks
+    for _ in range(warmup):
+        sm.step()
+    tm.fence()
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
     launches0 = _lib.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b in ev:
-        flush.fill_(1)
-        a.record()
-        device_step()
-        b.record()
-    sync_all()
+    ms_per_step = tm.device_ms(sm.step, args.steps, 0, flush)
     launches = _lib.launch_count() - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    kernel_ms = dev_ms / args.steps
-    # ---- end-to-end: pinned host buffers in, host buffer out on rank 0, copies inside the timed region.
-    #      N = 1: the host-buffer C-ABI call (solat_ff_map_host).  N > 1: the same kernel through the device-pointer
-    #      entry with explicit H2D from pinned memory, one NCCL gather, and the D2H of the gathered map on rank 0.
-    amp_np, phase_np, az_np = h_amp.numpy(), h_phase.numpy(), h_azel.numpy()
-    h_all = torch.empty((world, 2, npix), dtype=torch.float64).pin_memory() if rank == 0 else None
+    # kernels alone (no gather) on this rank, for the roofline of the dominant kernel
+    ms_kernels = tm.device_ms(lambda: plan.run_device(sm.d_pix, sm.d_amp, sm.d_phase, torch.cuda.current_stream().cuda_stream,
+                                                       sm.d_status) if sm.n_local else None, max(3, args.steps // 4), 0, flush)
+
+    # ---- e2e: the public call with host buffers, wall clock
+    last = [None]
 
     def e2e_step():
-        if world == 1:
-            plan.run(az_np, amp_np, phase_np)
-            return
-        d_azel.copy_(h_azel, non_blocking=True)
-        plan.run_device(d_azel, d_out[0], d_out[1], stream)
-        dist.gather(d_out, gathered, dst=0)
-        if rank == 0:
-            h_all.copy_(d_all, non_blocking=True)
-        torch.cuda.synchronize()
+        last[0] = public_call()
 
-    for _ in range(max(args.warmup, 3)):
-        e2e_step()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    sync_all()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = tm.wall_s(e2e_step, args.steps, 1)
     clocks = sampler.finish()
-    status = plan.status()
+    d2h_bytes = int(sm.bytes_d2h())
+    maps.clear_plan_cache()
+    cold_s = tm.wall_s(public_call, 1, 0)
+    plan = maps.far_field_plan(tg, th, ph, x, y, e, local_rank)    # (re-created by the cold call)
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # ---- parity of the timed map: stratified pixels against the oracle
+    parity, cpu_base = None, None
+    if rank == 0:
+        strat = stratified_pixel_indices(side)
+        if args.parity_pixels < len(strat):
+            strat = strat[:: max(1, len(strat) // max(1, args.parity_pixels))]
+        _, amp_map, pha_map = last[0]
+        o_amp, o_pha, secs, threads = port_sample(pixels, th, ph, x, y, e, tg.k, tg.rx_y, strat, two_pass=(world == 1))
+        dP = float(np.max(np.abs(amp_map[strat] ** 2 - o_amp ** 2) / o_amp ** 2))
+        dphi = float(np.max(np.abs(wrap(pha_map[strat] - o_pha))))
+        parity = {"pixels": int(len(strat)), "max_dP_rel": dP, "max_dphi_rad": dphi, "tol_dP_rel": P_TOL, "tol_dphi_rad": PHI_TOL,
+                  "ok": bool(dP <= P_TOL and dphi <= PHI_TOL),
+                  "what": "stratified pixels (corners, edges, az = 0 column, both signs of az) of the map returned by the last "
+                          "timed e2e step vs oracle.ff_map (C restatement of the reference, brentq per surface)"}
+        if world == 1:
+            cpu_base = {"value": len(strat) * float(n_scan) ** 2 / secs, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": "%d stratified pixels of the same map x %d rays, both reference passes (ff_sim.py:208-209), "
+                                  "%d threads, %.1f s" % (len(strat), n_scan ** 2, threads, secs),
+                        "note": "C restatement of the reference's algorithm; `--impl reference` times the unmodified Python "
+                                "reference (oracle/_ref) when it is staged"}
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+        dist.barrier()
+
+    prof, prof_note = load_profile()
+    peak = ctx.fp64_peak_tflops(5)
+    status = plan.status()
+    del plan, sm
+    configs = {} if args.headline_only else sub_configs(tm, rank, world, local_rank, prof, peak, max(5, args.steps))
 
     if rank == 0:
-        ms_per_step = dev_ms_max / args.steps
-        value = rays_per_step / (ms_per_step * 1e-3)
-        e2e_value = rays_per_step / (e2e_ms_max / args.steps * 1e-3)
-        peak = ctx.fp64_peak_tflops(5)
-        flop_per_launch = FLOP_PER_LAUNCHED_RAY * npix * N_SCAN ** 2
-        achieved = flop_per_launch / (kernel_ms * 1e-3) / 1e12      # rank 0's own launches
-        kernel_note = "ff_pair_kernel + ff_prep_kernel + ff_map_kernel, one launch each per step and rank, CUDA events around the three (rank 0's)"
+        value = pixel_rays / (ms_per_step * 1e-3)
+        model_tf = FLOP_FF_RAY * pixel_rays / world / (ms_kernels * 1e-3) / 1e12      # this rank's share over its kernels' time
+        roof = {"bound": "fp64_simt", "peak": peak, "unit": "TFLOP/s", "achieved": None, "frac": None, "traffic": None,
+                "model_tflops": model_tf, "model_speedup": model_tf / peak,
+                "flop_per_unit_model": FLOP_FF_RAY, "units_per_launch": pixel_rays / world,
+                "kernel": "ff_map_kernel (dominant) + ff_pair_* + ff_prep_kernel of one rank's share, CUDA events around them: %.3f ms"
+                          % ms_kernels,
+                "peak_source": "burst DFMA issue-rate probe run in this process (solat_fp64_peak, best of 5 x 2 ms launches); "
+                               "MEASURED_PEAKS.json carries no FP64 figure; nominal %.1f = 148 SM x 64 lanes x 2 x 1.965 GHz" % NOMINAL_FP64_TFLOPS,
+                "note": "frac = EXECUTED FP64 FLOP (ncu thread-level DFMA x2 + DMUL + DADD of the profile capture, scaled per "
+                        "pixel*ray) / live-measured kernel time / peak.  model_* = SURVEY 8d's reference-shaped count (626 FLOP per "
+                        "launched ray: the reference traces every accepted ray twice) over the same time; the kernels execute far "
+                        "fewer operations (rays the projection would skip are not traced, mirror pixels share a trace, "
+                        "mixed-precision Newton), so model_speedup can exceed 1 and is not a utilisation"}
+        ex = executed_entry(prof, "cfg5", pixel_rays / world, ms_kernels, peak)
+        if ex:
+            roof.update({"achieved": ex["executed_tflops"], "frac": ex["frac"], "frac_of_nominal": ex["frac_of_nominal"],
+                         "traffic": ex["traffic"], "executed_fp64_flop": ex["executed_fp64_flop"], "ncu": ex["ncu"]})
+        else:
+            roof["profile_note"] = prof_note or "no cfg5 entry in profiles/r02_kernels.json"
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_azel.numel() * 8 * world),
-                    "d2h_bytes_per_step": int(2 * npix * 8 * world), "ms_per_step": e2e_ms_max / args.steps,
-                    "api": "solat_ff_map_host via maps.FarFieldPlan.run (pinned host buffers)" if world == 1 else
-                           "pinned H2D + solat_ff_map_device + NCCL gather + D2H of the gathered map on rank 0"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of ff_map_kernel, bytes per launch, ncu --set full "
-                                           "capture profiles/r01n_raw_metrics.csv (algorithmic: 27 kB pixel list + 27 kB results + "
-                                           "~45 kB E_rec and angle tables; the rest is the 4 kB per-pixel set-up record written by "
-                                           "ff_prep_kernel and read back by ff_map_kernel); the path is compute bound",
-                         "peak_source": "burst DFMA issue-rate probe run in this process (best of 5 x 2 ms launches; MEASURED_PEAKS.json "
-                                        "has no FP64 figure); nominal %.1f = 148 SM x 64 lanes x 2 x 1.965 GHz" % NOMINAL_FP64_TFLOPS,
-                         "frac_of_nominal": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None,
-                         "flop_per_unit": FLOP_PER_LAUNCHED_RAY, "units_per_launch": npix * N_SCAN ** 2, "kernel": kernel_note,
-                         "executed_tflops": NCU_EXECUTED_FP64_FLOP_PER_LAUNCH / (kernel_ms * 1e-3) / 1e12,
-                         "executed_frac": NCU_EXECUTED_FP64_FLOP_PER_LAUNCH / (kernel_ms * 1e-3) / 1e12 / peak,
-                         "fp64_pipe_pct_ncu": 38.4,
-                         "note": "achieved/frac follow the contract: SURVEY 8d's reference-shaped model (626 FLOP per launched ray: the "
-                                 "reference traces every accepted ray) over the measured time.  The kernel executes far fewer FP64 "
-                                 "operations (mixed-precision Newton, mirror-local frames, about half of the accepted rays culled "
-                                 "before the trace because the reference's projection would skip them, mirror pixels (+az, -az) "
-                                 "sharing one trace), so frac can exceed 1; executed_* = ncu thread-level DFMA/DMUL/DADD counts of profiles/r01n_op_counts.csv over the "
-                                 "same measured time, fp64_pipe_pct_ncu = sm__inst_executed_pipe_fp64 of that capture"},
-            "ray_status": int(status),
+            "e2e": {"value": pixel_rays / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(16 * len(pixels)),
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1e3,
+                    "api": "maps.ff_map (what scripts/ff_sim.py calls): host pixel list -> "
+                           + ("solat_ff_map_host (C ABI, copies inside)" if world == 1 else
+                              "pinned H2D per rank, solat_ff_map_device_st, NCCL gather to rank 0, D2H, un-permute")},
+            "full_map_wall_s": e2e_s, "full_map_wall_s_cold": cold_s, "first_call_s": first_call_s,
+            "gpu_launches": int(launches), "roofline": roof, "parity_checked": parity, "configs": configs,
+            "ray_status": int(status), "csrc_sha256": csrc_hash()[:16],
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(tg, th, ph, pixels, data_x, data_y, e_rec)
+        if num != NUM or n_scan != N_SCAN:
+            line["config"]["workload"] += " [REDUCED for a smoke run: %dx%d px x %d^2 rays]" % (side, side, n_scan)
+        if cpu_base:
+            line["cpu_baseline"] = cpu_base
         print(json.dumps(line))
+        bad = (parity and not parity["ok"]) or any(c.get("parity_checked", {}).get("ok") is False for c in configs.values())
+        if bad:
+            sys.stderr.write("bench.py: parity check against the oracle FAILED: %s\n" % json.dumps(parity))
+    else:
+        bad = False
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def cpu_baseline(tg, th, ph, pixels, data_x, data_y, e_rec):
-    from oracle import oracle_lib as orc
-
-    geo = orc.ff_geo_vec(rx_y_m=tg.rx_y)
-    cores = orc.num_threads()
-    sample = pixels[::4]
-    orc.ff_map(geo, sample[:8], th, ph, data_x, data_y, e_rec, tg.k, two_pass=True)
-    t0 = time.perf_counter()
-    orc.ff_map(geo, sample, th, ph, data_x, data_y, e_rec, tg.k, two_pass=True)
-    dt = time.perf_counter() - t0
-    return {"value": len(sample) * N_SCAN ** 2 / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "every 4th pixel of the same 41x41 map (%d px x %d rays), both reference passes, %d threads, %.1f s"
-                      % (len(sample), N_SCAN ** 2, cores, dt)}
-
-
-def run_nf(args):
-    """Optional second line (`--workload nf`, one GPU): BASELINE.json configs[0], the near-field holography map
-    `holo_sim.py 140` (51x51 source positions x 100^2 rays, 7328 traced per pixel after the receiver-mask cull)."""
-    import torch
-
-    from solat_optics_b200 import _lib, maps
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(0)
-    ctx = _lib.context(0)
-    tg = maps.holo_tele_geo(float(FREQ), 100)
-    rx_opl, rx_w = maps.receiver_field(tg)
-    plan = maps.NearFieldPlan(tg, [tg.k], rx_opl, rx_w, device=0)
-    px = maps.holo_pixels()
-    npix = len(px)
-    d_px = torch.from_numpy(px).cuda()
-    d_a = torch.empty(npix, dtype=torch.float64, device="cuda"); d_p = torch.empty_like(d_a)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
-    for _ in range(max(args.warmup, 3)):
-        plan.run_device(d_px, d_a, d_p, stream)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(physical_gpu_index(0))
-    sampler.start()
-    launches0 = _lib.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b in ev:
-        flush.fill_(1)
-        a.record(); plan.run_device(d_px, d_a, d_p, stream); b.record()
-    torch.cuda.synchronize()
-    launches = _lib.launch_count() - launches0
-    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    amp = np.empty((1, npix)); ph = np.empty((1, npix))
-    for _ in range(max(args.warmup, 3)):
-        plan.run(px, amp, ph)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        plan.run(px, amp, ph)
-    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
-    clocks = sampler.finish()
-    peak = ctx.fp64_peak_tflops(5)
-    rays = npix * 100 ** 2
-    flop_model = 520.0 * npix * plan.active_rays                      # SURVEY 8d: 520 FLOP per traced source ray
-    flop_exec = 2 * 737400960 + 288873728 + 107575936               # ncu thread-level DFMA x2 + DMUL + DADD, profiles/r01o_nf_op_counts.csv
-    achieved = flop_model / (ms * 1e-3) / 1e12
-    line = {
-        "metric": METRIC, "value": rays / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "holo_sim.py 140: near-field LATR holography map, 51x51 source positions x 100^2 rays, 140 GHz",
-                   "pixels_per_map": npix, "rays_per_pixel": 10000, "traced_rays_per_pixel": plan.active_rays,
-                   "l2": "flushed between timed steps (256 MiB write); the path reads <1 MB per step"},
-        "clocks": clocks,
-        "e2e": {"value": rays / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(px.nbytes), "d2h_bytes_per_step": int(2 * npix * 8),
-                "ms_per_step": e2e_ms, "api": "solat_nf_map_host via maps.NearFieldPlan.run"},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "fp64_simt", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": 1244928 + 50944 + 135424, "flop_per_unit": 520.0, "units_per_launch": npix * plan.active_rays,
-                     "executed_tflops": flop_exec / (ms * 1e-3) / 1e12, "fp64_pipe_pct_ncu": 49.6,
-                     "kernel": "ff_pair_kernel + nf_map_kernel<1,1,2> + nf_finalize_kernel, CUDA events around the three",
-                     "note": "achieved/frac follow SURVEY 8d's model (520 FLOP per traced source ray, every pixel traced on its own); "
-                             "the kernel traces a ray once for the four mirror pixels (+-x, +-z), so frac can exceed what the "
-                             "pipes do; executed_tflops = ncu thread-level FP64 operation counts over the same measured time"},
-        "ray_status": int(plan.status()),
-    }
-    print(json.dumps(line))
-
+    if bad:
+        sys.exit(3)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="ff", choices=["ff", "nf"],
-                    help="ff (default): BASELINE.json configs[1], the bench line; nf: configs[0] on one GPU, an extra line")
+    ap.add_argument("--headline-only", action="store_true", help="skip the configs[0..3] objects")
+    ap.add_argument("--parity-pixels", type=int, default=64)
+    ap.add_argument("--num", type=int, default=0, help="smoke runs only: pixels each side of the centre (default 200)")
+    ap.add_argument("--n-scan", type=int, default=0, help="smoke runs only: rays per fan axis (default 1000)")
+    ap.add_argument("--ref-rays", type=int, default=24, help="--impl reference: rays per fan axis of the Python sample")
+    ap.add_argument("--port-only", action="store_true", help="--impl reference: time the C port even if oracle/_ref exists")
     args = ap.parse_args()
-    if args.workload == "nf" and args.impl == "ours":
-        run_nf(args)
-    elif args.impl == "reference":
+    if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -117,6 +117,10 @@ SOLAT_API void solat_nf_plan_destroy(solat_nf_plan *plan);
 SOLAT_API int solat_nf_map_host(solat_nf_plan *plan, const double *src_xz, int npix, double *amp, double *phase, int *status);
 SOLAT_API int solat_nf_map_device(solat_nf_plan *plan, const double *d_src_xz, int npix, double *d_amp, double *d_phase,
                         void *stream);
+/* Device-pointer map that also reports its ray status on the device: d_status is an 8-byte device slot, the OR of the
+ * launch's ray status bits as an int in its low word (the multi-GPU path gathers it with the results).        */
+SOLAT_API int solat_nf_map_device_st(solat_nf_plan *plan, const double *d_src_xz, int npix, double *d_amp, double *d_phase,
+                           void *d_status, void *stream);
 /* Receiver fields of nrx receiver positions p_rx[nrx][3] in one launch: rows 3 (path length) and 4 (feed-taper
  * amplitude) of rx_to_lyot_model(...).output() (ray_trace_int.py:848-853), opl/amp [nrx][nth*nph] -- the receiver side
  * of the per-pixel integral (scripts/holo_sim.py:157-176) for a receiver-offset sweep.                          */
@@ -167,6 +171,9 @@ SOLAT_API void solat_ff_plan_destroy(solat_ff_plan *plan);
 SOLAT_API int solat_ff_map_host(solat_ff_plan *plan, const double *azel, int npix, double *amp, double *phase, int *status);
 SOLAT_API int solat_ff_map_device(solat_ff_plan *plan, const double *d_azel, int npix, double *d_amp, double *d_phase,
                         void *stream);
+/* as solat_nf_map_device_st */
+SOLAT_API int solat_ff_map_device_st(solat_ff_plan *plan, const double *d_azel, int npix, double *d_amp, double *d_phase,
+                           void *d_status, void *stream);
 SOLAT_API int solat_ff_plan_status(solat_ff_plan *plan, int *status);
 
 /* Far-field map with panel models (ff_sim.py:61-70,204-221 with non-zero adjuster offsets), two steps around the

@@ -18,8 +18,10 @@ Shims, none of which touch the reference's arithmetic:
 import os
 import sys
 
-REF_ROOT = os.environ.get("SOLAT_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# /root/reference in the build container; on the GPU box the byte-for-byte staged copy oracle/_ref (oracle/stage_ref.py)
+REF_ROOT = os.environ.get("SOLAT_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/solat_optics") else os.path.join(_HERE, "_ref"))
 _REPO = os.path.dirname(_HERE)
 
 

@@ -41,7 +41,10 @@ def main():
     ap.add_argument("--nf-input", default=None, help="near-field map (.txt from holo_sim.py)")
     ap.add_argument("--out", default=None)
     ap.add_argument("--n-scan", type=int, default=100)
-    ap.add_argument("--strict", action="store_true")
+    ap.add_argument("--strict", action="store_true",
+                    help="raise where the reference's brentq would (a root outside its bracket).  Rays the projection "
+                         "would skip anyway are not traced and report no status: set SOLAT_FF_PREFILTER=0 to trace and check "
+                         "every accepted ray as the reference does (saf:706)")
     ap.add_argument("--panels", choices=["auto", "off"], default="auto",
                     help="auto: when holosim-ml's pan_mod is importable, build the panel models as ff_sim.py:61-70 does "
                          "(identify_panel on the host, panel errors in the kernel); off: every ray on an error-free panel")
@@ -50,8 +53,10 @@ def main():
                          "(default: zeros, ff_sim.py:61-62)")
     a = ap.parse_args()
 
-    sim_d = 1.25 if a.freq <= 120 else 1.32                      # ff_sim.py:36-41
-    nf_path = a.nf_input or "data/source_test_%sm_%dGHz.txt" % (sim_d, a.freq)
+    # default input: the file `holo_sim.py <freq>` of this package writes (the reference's own default, ff_sim.py:36-49,
+    # names a 1.25 m / 1.32 m file under the author's home directory that no script in the repository produces)
+    y_ap = maps.holo_tele_geo(float(a.freq)).y_ap
+    nf_path = a.nf_input or "data/source_test_%sm_%dGHz.txt" % (round(-y_ap / 1e3, 2), a.freq)
     out_path = a.out or "output_files/ff_%sm_%dGHz.txt" % (a.offset, a.freq)
 
     rank, world = _launch.init_distributed()

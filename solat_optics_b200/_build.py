@@ -31,13 +31,30 @@ def stale():
 
 
 def build(force=False, verbose=False, extra=()):
-    """Compile the CUDA library if it is missing or older than its sources."""
+    """Compile the CUDA library if it is missing or older than its sources.  Safe under torchrun on a fresh checkout:
+    ranks serialise on a file lock, the first one compiles into a temporary file and renames it into place, the others
+    find the library fresh when they get the lock."""
     if os.environ.get("SOLAT_B200_LIB"):
         return LIB          # an explicitly chosen prebuilt variant is never rebuilt
     if not force and not stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ["-o", LIB, SRC]
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    import fcntl
+
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not stale():
+                return LIB
+            tmp = "%s.tmp.%d" % (LIB, os.getpid())
+            cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ["-o", tmp, SRC]
+            if verbose:
+                print(" ".join(cmd))
+            try:
+                subprocess.check_call(cmd)
+                os.replace(tmp, LIB)
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB

@@ -57,6 +57,7 @@ SIGNATURES = {
     "solat_nf_plan_destroy": (None, [c_vp]),
     "solat_nf_map_host": (c_i, [c_vp, c_dp, c_i, c_dp, c_dp, c_ip]),
     "solat_nf_map_device": (c_i, [c_vp, c_vp, c_i, c_vp, c_vp, c_vp]),
+    "solat_nf_map_device_st": (c_i, [c_vp, c_vp, c_i, c_vp, c_vp, c_vp, c_vp]),
     "solat_nf_plan_active_rays": (c_i, [c_vp]),
     "solat_nf_plan_channels": (c_i, [c_vp]),
     "solat_nf_plan_status": (c_i, [c_vp, c_ip]),
@@ -69,6 +70,7 @@ SIGNATURES = {
     "solat_ff_plan_destroy": (None, [c_vp]),
     "solat_ff_map_host": (c_i, [c_vp, c_dp, c_i, c_dp, c_dp, c_ip]),
     "solat_ff_map_device": (c_i, [c_vp, c_vp, c_i, c_vp, c_vp, c_vp]),
+    "solat_ff_map_device_st": (c_i, [c_vp, c_vp, c_i, c_vp, c_vp, c_vp, c_vp]),
     "solat_ff_plan_status": (c_i, [c_vp, c_ip]),
     "solat_ff_map_mirror_xy_host": (c_i, [c_vp, c_dp, c_i, c_dp, c_ip]),
     "solat_ff_map_panels_host": (c_i, [c_vp, c_dp, c_i, c_sp, c_sp, c_dp, c_i, c_dp, c_i, c_dp, c_dp, c_ip]),

@@ -1923,6 +1923,17 @@ int solat_nf_map_device(solat_nf_plan* p, const double* d_src, int npix, double*
     if (!p || !d_src || !d_amp || !d_phase || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
     return nf_map_launch(p, d_src, npix, d_amp, d_phase, (cudaStream_t)stream);
 }
+// copy the plan's sticky status word into an 8-byte slot (int in the low word) and clear it
+__global__ void move_status_kernel(int* status, int* slot) { slot[0] = *status; slot[1] = 0; *status = 0; }
+int solat_nf_map_device_st(solat_nf_plan* p, const double* d_src, int npix, double* d_amp, double* d_phase, void* d_status,
+                           void* stream)
+{
+    if (!p || !d_src || !d_amp || !d_phase || !d_status || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    if (int rc = nf_map_launch(p, d_src, npix, d_amp, d_phase, (cudaStream_t)stream)) return rc;
+    move_status_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p->status.p, static_cast<int*>(d_status));
+    LAUNCHED();
+    return SOLAT_OK;
+}
 int solat_nf_plan_status(solat_nf_plan* p, int* status)
 {
     if (!p || !status) return fail(SOLAT_ERR_ARG, "bad argument");
@@ -2071,7 +2082,6 @@ struct solat_ff_plan {
     DevBuf<int> pair_ints;
     DevBuf<FfItem> items;
     int pairs;                              // geometry, fan and shared memory allow the mirror-pair walk
-    int pair_flip;                          // which of the two counter pairs the next call uses
     FfGrid grid;
     double k, key_base, key_unit;
     int M, n_rays, rows, shape, prefilter;
@@ -2127,8 +2137,7 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cud
     q.items = nullptr; q.counters = nullptr; q.item0 = 0;
     if (pairs) {
         // work items = canonical pixels (|az|, el) with the output slots of (+az, el) and (-az, el).  The slot table is
-        // emptied by the emit phase itself and the two counter pairs alternate (each call zeroes the other's), so a call
-        // needs no memset once the buffers exist.
+        // emptied by the emit phase itself.
         if (int rc = p->items.reserve((size_t)npix)) return rc;
         int* ints = nullptr;
         if (npix <= FF_PAIR_ONE_CTA) {
@@ -2140,20 +2149,18 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cud
             const unsigned nslots = 2u * (unsigned)npix + 1u;
             if (nslots > p->pair_slots.n || (size_t)npix + 4 > p->pair_ints.n) {
                 if (int rc = p->pair_slots.reserve(nslots)) return rc;
-                if (int rc = p->pair_ints.reserve((size_t)npix + 4)) return rc;   // [0..3] two counter pairs, then the overflow list
+                if (int rc = p->pair_ints.reserve((size_t)npix + 4)) return rc;   // [0..1] counters, [4..] the overflow list
                 CK(cudaMemsetAsync(p->pair_slots.p, 0xFF, p->pair_slots.n * sizeof(FfPairSlot), s));
-                CK(cudaMemsetAsync(p->pair_ints.p, 0, 4 * sizeof(int), s));
-                p->pair_flip = 0;
             }
-            ints = p->pair_ints.p + 2 * p->pair_flip;
-            int* ints_next = p->pair_ints.p + 2 * (1 - p->pair_flip);
-            p->pair_flip = 1 - p->pair_flip;
+            // the counters are zeroed per call: the one-CTA path above leaves its item count in ints[0]
+            ints = p->pair_ints.p;
+            CK(cudaMemsetAsync(ints, 0, 2 * sizeof(int), s));
             int* over = p->pair_ints.p + 4;
             ff_pair_insert_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, over, ints, FF_PAIR_TOL);
             LAUNCHED();
             ff_pair_attach_kernel<<<(npix + 255) / 256, 256, 0, s>>>(q.azel, npix, p->pair_slots.p, nslots, over, ints, FF_PAIR_TOL);
             LAUNCHED();
-            ff_pair_emit_kernel<<<(nslots + 255) / 256, 256, 0, s>>>(q.azel, p->pair_slots.p, nslots, over, ints, ints_next, p->items.p);
+            ff_pair_emit_kernel<<<(nslots + 255) / 256, 256, 0, s>>>(q.azel, p->pair_slots.p, nslots, over, ints, nullptr, p->items.p);
             LAUNCHED();
         }
         pq.items = q.items = p->items.p; pq.counters = q.counters = ints;
@@ -2271,6 +2278,12 @@ int solat_ff_map_device(solat_ff_plan* p, const double* d_azel, int npix, double
 {
     if (!p || !d_azel || !d_amp || !d_phase || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
     return ff_map_launch(p, d_azel, npix, d_amp, d_phase, (cudaStream_t)stream);
+}
+int solat_ff_map_device_st(solat_ff_plan* p, const double* d_azel, int npix, double* d_amp, double* d_phase, void* d_status,
+                           void* stream)
+{
+    if (!p || !d_azel || !d_amp || !d_phase || !d_status || npix <= 0) return fail(SOLAT_ERR_ARG, "bad argument");
+    return ff_map_launch(p, d_azel, npix, d_amp, d_phase, (cudaStream_t)stream, static_cast<int*>(d_status));
 }
 int solat_ff_plan_status(solat_ff_plan* p, int* status)
 {

@@ -28,6 +28,11 @@ class PlotOpts:
 # ------------------------------------------------------------------------------------------------
 # sharding / gather
 # ------------------------------------------------------------------------------------------------
+# Below this much work (scan pixels x launched rays) a map runs on rank 0 alone: the reference-sized maps take a
+# fraction of a millisecond on one GPU, less than a collective costs.
+SHARD_MIN_PIXEL_RAYS = 2.0e8
+
+
 def shard_bounds(n_items, rank, world_size):
     """Contiguous block [lo, hi) of the flattened pixel index owned by `rank`."""
     blk = -(-n_items // world_size)
@@ -64,6 +69,183 @@ def gather_blocks(local, n_items, dst=0):
     if rank != dst:
         return None
     return torch.cat(out, dim=0)[:n_items]
+
+
+def _fold(col):
+    """|col| rounded to 1e-9 of its extent: np.linspace grids are symmetric about 0 only to a few ulp."""
+    scale = float(np.max(np.abs(col))) if len(col) else 0.0
+    return np.round(np.abs(col) * (1e9 / scale if scale > 0 else 1.0))
+
+
+def mirror_pair_order(pixels, fold_second=False):
+    """Permutation of an (az, el) -- or near-field (x, z) -- pixel list that puts (+az, el) next to (-az, el).
+    fold_second: the four near-field positions (+-x, +-z) next to each other."""
+    pixels = np.asarray(pixels, dtype=np.float64)
+    if fold_second:
+        return np.lexsort((np.signbit(pixels[:, 0]), np.signbit(pixels[:, 1]), _fold(pixels[:, 1]), _fold(pixels[:, 0])))
+    return np.lexsort((np.signbit(pixels[:, 0]), pixels[:, 1], _fold(pixels[:, 0])))
+
+
+def shard_groups(pixels, world_size, fold_second=False):
+    """Which pixels every rank computes: list of `world_size` index arrays into `pixels`.
+    The mirror groups -- (+-az, el), or (+-x, +-z) with fold_second -- stay whole (the kernel traces a group once) and
+    are dealt to the ranks cyclically in (|az|, el) order, so every rank gets an even sample of the map: the cost of
+    a pixel varies smoothly over the map (how much of the fan reaches the E_rec grid), contiguous blocks do not
+    balance.  Replaces the master/worker queue of scripts/ff_sim.py:135-227 by a static deal."""
+    pixels = np.asarray(pixels, dtype=np.float64).reshape(-1, 2)
+    order = mirror_pair_order(pixels, fold_second)
+    if len(order) == 0:
+        return [order.copy() for _ in range(world_size)]
+    k0 = _fold(pixels[:, 0])[order]
+    k1 = (_fold(pixels[:, 1]) if fold_second else pixels[:, 1])[order]
+    first = np.ones(len(order), dtype=bool)
+    first[1:] = (k0[1:] != k0[:-1]) | (k1[1:] != k1[:-1])
+    gid = np.cumsum(first) - 1
+    return [order[gid % world_size == r] for r in range(world_size)]
+
+
+def _digest(*arrays):
+    import hashlib
+
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str((a.shape, a.dtype.str)).encode())
+        h.update(a.view(np.uint8).reshape(-1).data if a.size else b"")
+    return h.digest()
+
+
+class _PlanCache:
+    """Plans (device tables, scratch buffers) are kept across calls: a map call with the same geometry, fan, grid and
+    receiver field reuses them instead of uploading everything again.  LRU; an entry that falls out (or
+    `clear_plan_cache()`) is freed when its last user lets go of it."""
+
+    def __init__(self, size=8):
+        self.size, self.items = size, {}
+
+    def get(self, key, make):
+        hit = self.items.pop(key, None)
+        if hit is None:
+            hit = make()
+            while len(self.items) >= self.size:
+                self.items.pop(next(iter(self.items)))
+        self.items[key] = hit
+        return hit
+
+    def clear(self):
+        self.items.clear()
+
+
+_plans = _PlanCache()
+_rx_fields = _PlanCache(16)
+_sharded = _PlanCache(2)
+
+
+def clear_plan_cache():
+    _sharded.clear()
+    _plans.clear()
+    _rx_fields.clear()
+
+
+class ShardedMap:
+    """One map dealt over the ranks of the process group (one process per GPU).  Every rank keeps its pixels in HBM;
+    `step()` enqueues, on the current CUDA stream, the rank's fused map kernel and -- with more than one rank -- the
+    single collective of the path: the NCCL gather of (amp, phase, ray status) to rank 0.  `fetch()` brings the
+    gathered map to rank 0's host memory and puts it back in the caller's pixel order.
+    `plan`: NearFieldPlan / FarFieldPlan (channels = outputs per pixel)."""
+
+    def __init__(self, plan, pixels, fold_second, rank=None, world=None):
+        import torch
+
+        if rank is None:
+            rank, world = dist_info()
+        self.plan, self.rank, self.world = plan, rank, world
+        pixels = _lib.as_f64(np.reshape(pixels, (-1, 2)))
+        self.npix = len(pixels)
+        self.parts = shard_groups(pixels, world, fold_second)
+        self.nch = plan.channels
+        mine = self.parts[rank]
+        self.n_local = len(mine)
+        self.blk = max(len(p) for p in self.parts)
+        self.dev = _gather_device(plan.ctx.device, default_cuda=True)   # CPU only under the gloo tests
+        self.cuda = self.dev.type == "cuda"
+        pin = (lambda t: t.pin_memory()) if self.cuda else (lambda t: t)
+        self.flat = 2 * self.nch * self.blk + 1                       # [amp | phase] of this rank, then the status slot
+        self.h_pix = pin(torch.from_numpy(pixels[mine].copy()))
+        self.d_pix = self.h_pix.to(self.dev, non_blocking=True) if self.cuda else self.h_pix.clone()
+        self.d_buf = torch.zeros(self.flat, dtype=torch.float64, device=self.dev)
+        n = self.nch * self.n_local
+        self.d_amp, self.d_phase, self.d_status = self.d_buf[:n], self.d_buf[n:2 * n], self.d_buf[self.flat - 1:]
+        self.d_all = self.h_all = self.gather_list = None
+        if rank == 0:
+            self.d_all = torch.zeros((world, self.flat), dtype=torch.float64, device=self.dev) if world > 1 else None
+            self.gather_list = list(self.d_all.unbind(0)) if world > 1 else None
+            self.h_all = pin(torch.zeros((world, self.flat), dtype=torch.float64))
+
+    def _stream(self):
+        import torch
+
+        return torch.cuda.current_stream() if self.cuda else None
+
+    def upload(self):
+        """pinned host -> HBM copy of this rank's pixel list (part of an end-to-end step)"""
+        self.d_pix.copy_(self.h_pix, non_blocking=True)
+
+    def step(self):
+        import torch
+
+        if self.n_local:
+            self.plan.run_device(self.d_pix, self.d_amp, self.d_phase, self._stream().cuda_stream if self.cuda else 0, self.d_status)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.gather(self.d_buf, self.gather_list, dst=0)
+
+    def fetch(self):
+        """Rank 0: (amp [channels, npix], phase [channels, npix], status) in the caller's pixel order; None elsewhere."""
+        import torch
+
+        if self.rank != 0:
+            if self.cuda:
+                self._stream().synchronize()
+            return None
+        self.h_all.copy_(self.d_all if self.world > 1 else self.d_buf.unsqueeze(0), non_blocking=True)
+        if self.cuda:
+            self._stream().synchronize()
+        h = self.h_all.numpy()
+        amp = np.empty((self.nch, self.npix))
+        phase = np.empty((self.nch, self.npix))
+        status = 0
+        for r, idx in enumerate(self.parts):
+            n = self.nch * len(idx)
+            if n:
+                amp[:, idx] = h[r, :n].reshape(self.nch, len(idx))
+                phase[:, idx] = h[r, n:2 * n].reshape(self.nch, len(idx))
+                status |= int(h[r, self.flat - 1:].view(np.int32)[0])
+        return amp, phase, status
+
+    def bytes_h2d(self):
+        return int(self.h_pix.numel() * 8)
+
+    def bytes_d2h(self):
+        return int(self.world * self.flat * 8) if self.rank == 0 else 0
+
+
+def _use_ranks(n_pixel_rays, world):
+    """How many ranks a map of this size is dealt to (all of them, or rank 0 alone)."""
+    return world if (world > 1 and n_pixel_rays >= SHARD_MIN_PIXEL_RAYS) else 1
+
+
+def _finish_status(st, strict, sharded):
+    """Strict mode raises on every rank together (the reference's workers raise where brentq does)."""
+    if strict and sharded:
+        import torch
+        import torch.distributed as dist
+
+        t = torch.tensor([int(st or 0)], dtype=torch.int64, device=_gather_device(int(os.environ.get("LOCAL_RANK", "0"))))
+        dist.broadcast(t, src=0)
+        st = int(t.item())
+    _lib.raise_on_status(st or 0, strict)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -188,11 +370,16 @@ class NearFieldPlan:
                                                  ctypes.byref(st)))
         return amp, phase, st.value
 
-    def run_device(self, d_src, d_amp, d_phase, stream=0):
-        """torch CUDA float64 tensors ([npix,2], [channels*npix], [channels*npix]); asynchronous on `stream`."""
+    def run_device(self, d_src, d_amp, d_phase, stream=0, d_status=None):
+        """torch CUDA float64 tensors ([npix,2], [channels*npix], [channels*npix]); asynchronous on `stream`.
+        d_status: optional 8-byte device slot that receives the launch's ray status (else: the plan's sticky word)."""
         npix = d_src.shape[0]
-        _lib.check(_lib.load().solat_nf_map_device(self.handle, d_src.data_ptr(), npix, d_amp.data_ptr(),
-                                                   d_phase.data_ptr(), stream))
+        if d_status is None:
+            _lib.check(_lib.load().solat_nf_map_device(self.handle, d_src.data_ptr(), npix, d_amp.data_ptr(),
+                                                       d_phase.data_ptr(), stream))
+        else:
+            _lib.check(_lib.load().solat_nf_map_device_st(self.handle, d_src.data_ptr(), npix, d_amp.data_ptr(),
+                                                          d_phase.data_ptr(), d_status.data_ptr(), stream))
 
     def status(self):
         st = _lib.c_i(0)
@@ -218,45 +405,60 @@ def holo_pixels(res=51, sweep=100, shift=0):
     return np.stack([xx.ravel(), zz.ravel()], axis=1)
 
 
+def _cached_receiver_field(tg, p_rx, n_scan_rx, n_scan):
+    key = ("rx", _lib.context().device, tg.n_si, tg.n_vac, tg.th_fwhp, tg.y_ap, tuple(float(v) for v in p_rx), n_scan_rx, n_scan)
+    return _rx_fields.get(key, lambda: receiver_field(tg, p_rx, n_scan_rx, n_scan))
+
+
+def near_field_plan(tg, k_list, rx_opl, rx_w, n_scan, device=None):
+    """NearFieldPlan from the plan cache (same geometry, wavenumbers and receiver field -> the same plan)."""
+    dev = _lib.context(device).device
+    key = ("nf", dev, tg.n_si, tg.n_vac, tg.th_fwhp, tg.y_ap, int(n_scan), _digest(np.asarray(k_list, dtype=np.float64), rx_opl, rx_w))
+    return _plans.get(key, lambda: NearFieldPlan(tg, k_list, rx_opl, rx_w, n_scan, device))
+
+
+def _run_map(plan, pixels, fold_second, n_pixel_rays, strict):
+    """Run `plan` over `pixels` on the ranks the map is worth dealing to.  Rank 0: (amp [channels, npix], phase);
+    other ranks: None."""
+    rank, world = dist_info()
+    use = _use_ranks(n_pixel_rays, world)
+    if use == 1:
+        if rank != 0:
+            return None
+        amp, phase, st = plan.run(pixels)
+        _lib.raise_on_status(st, strict)
+        return np.reshape(amp, (plan.channels, -1)), np.reshape(phase, (plan.channels, -1))
+    sm = _sharded.get((id(plan), _digest(pixels), world, fold_second), lambda: ShardedMap(plan, pixels, fold_second, rank, world))
+    sm.upload()
+    sm.step()
+    res = sm.fetch()
+    _finish_status(res[2] if res else 0, strict, True)
+    return None if res is None else (res[0], res[1])
+
+
 def holo_map(freqs, res=51, sweep=100, shift=0, n_scan=100, n_scan_rx=None, p_rx=(0, 0, 0), device=None,
              strict=False):
     """Near-field holography map(s) for one band.  `freqs`: scalar or list of GHz values that share
-    the band geometry (holo_sim.py:40-45).  Shards over ranks when torch.distributed is initialised.
+    the band geometry (holo_sim.py:40-45).  Under torch.distributed a map large enough to be worth it is dealt over
+    the ranks (shard_groups), smaller ones run on rank 0.
     Returns on rank 0: (pixels [npix,2], amp [nfreq,npix], phase [nfreq,npix]); None elsewhere."""
     freqs = np.atleast_1d(np.asarray(freqs, dtype=np.float64))
     geos = [holo_tele_geo(f, n_scan) for f in freqs]
     if len({g.y_ap for g in geos}) != 1:
         raise ValueError("frequencies of different bands (y_ap differs) need separate maps")
     tg = geos[0]
-    # the feed taper differs per band only; one geometry -> one rx field
-    rx_opl, rx_w = receiver_field(tg, p_rx, n_scan_rx, n_scan)
-    plan = NearFieldPlan(tg, [g.k for g in geos], rx_opl, rx_w, n_scan, device)
-    pixels = holo_pixels(res, sweep, shift)
     rank, world = dist_info()
-    # ranks take contiguous blocks of the list ordered so that the mirror positions (+-x, +-z) are neighbours: the
-    # kernel traces such a group once
-    order = mirror_pair_order(pixels, fold_second=True) if world > 1 else np.arange(len(pixels))
-    lo, hi = shard_bounds(len(pixels), rank, world)
-    if hi > lo:
-        amp, phase, st = plan.run(pixels[order[lo:hi]])
-    else:
-        amp, phase, st = np.zeros((len(freqs), 0)), np.zeros((len(freqs), 0)), 0
-    _lib.raise_on_status(st, strict)
-    plan.close()
-    if world == 1:
-        return pixels, amp, phase
-    import torch
-
-    dev = _gather_device(plan.ctx.device)
-    local = torch.from_numpy(np.concatenate([amp.T, phase.T], axis=1)).to(dev)
-    full = gather_blocks(local, len(pixels))
-    if full is None:
+    pixels = holo_pixels(res, sweep, shift)
+    work = len(pixels) * float(n_scan) ** 2
+    if _use_ranks(work, world) == 1 and rank != 0:
         return None
-    full = full.cpu().numpy()
-    out = np.empty_like(full)
-    out[order] = full
-    nf = len(freqs)
-    return pixels, np.ascontiguousarray(out[:, :nf].T), np.ascontiguousarray(out[:, nf:].T)
+    # the feed taper differs per band only; one geometry -> one rx field
+    rx_opl, rx_w = _cached_receiver_field(tg, p_rx, n_scan_rx, n_scan)
+    plan = near_field_plan(tg, [g.k for g in geos], rx_opl, rx_w, n_scan, device)
+    out = _run_map(plan, pixels, True, work, strict)
+    if out is None:
+        return None
+    return pixels, out[0], out[1]
 
 
 def receiver_offset_sweep(freq, rx_positions, res=51, sweep=100, shift=0, n_scan=100, device=None, strict=False):
@@ -265,22 +467,24 @@ def receiver_offset_sweep(freq, rx_positions, res=51, sweep=100, shift=0, n_scan
     table.  Single process (shard the receiver list over ranks for more GPUs).
     Returns (pixels [npix,2], amp [n_rx,npix], phase [n_rx,npix])."""
     tg = holo_tele_geo(float(freq), n_scan)
-    rx_opl, rx_w = receiver_fields(tg, rx_positions, n_scan, device)
-    plan = NearFieldPlan(tg, [tg.k], rx_opl, rx_w, n_scan, device)
+    pos = _lib.as_f64(np.reshape(rx_positions, (-1, 3)))
+    key = ("rxs", _lib.context(device).device, tg.n_si, tg.n_vac, tg.th_fwhp, tg.y_ap, int(n_scan), _digest(pos))
+    rx_opl, rx_w = _rx_fields.get(key, lambda: receiver_fields(tg, pos, n_scan, device))
+    plan = near_field_plan(tg, [tg.k], rx_opl, rx_w, n_scan, device)
     pixels = holo_pixels(res, sweep, shift)
     amp, phase, st = plan.run(pixels)
     _lib.raise_on_status(st, strict)
-    plan.close()
     return pixels, amp[:, 0, :], phase[:, 0, :]
 
 
-def _gather_device(device_index):
+def _gather_device(device_index, default_cuda=False):
+    """Device the collectives run on: the rank's GPU under NCCL, the CPU under gloo (CPU tests)."""
     import torch
     import torch.distributed as dist
 
-    if dist.is_initialized() and dist.get_backend() == "nccl":
-        return torch.device("cuda", device_index)
-    return torch.device("cpu")
+    if dist.is_available() and dist.is_initialized():
+        return torch.device("cuda", device_index) if dist.get_backend() == "nccl" else torch.device("cpu")
+    return torch.device("cuda", device_index) if default_cuda else torch.device("cpu")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -347,6 +551,7 @@ class FarFieldPlan:
         if data_x.shape != (m, m) or data_y.shape != (m, m) or e.shape != (m, m):
             raise ValueError("data_x, data_y, e_rec must be (M, M)")
         self.n_rays = theta.size * phi.size
+        self.channels = 1
         geom = _lib.ff_geom(tele_geo)
         h = _lib.c_vp()
         _lib.check(lib.solat_ff_plan_create(self.ctx.handle, ctypes.byref(geom), _lib.dptr(theta), theta.size,
@@ -366,9 +571,15 @@ class FarFieldPlan:
                                                  ctypes.byref(st)))
         return amp, phase, st.value
 
-    def run_device(self, d_azel, d_amp, d_phase, stream=0):
-        _lib.check(_lib.load().solat_ff_map_device(self.handle, d_azel.data_ptr(), d_azel.shape[0], d_amp.data_ptr(),
-                                                   d_phase.data_ptr(), stream))
+    def run_device(self, d_azel, d_amp, d_phase, stream=0, d_status=None):
+        """torch CUDA float64 tensors ([npix,2], [npix], [npix]); asynchronous on `stream`.
+        d_status: optional 8-byte device slot that receives the launch's ray status (else: the plan's sticky word)."""
+        if d_status is None:
+            _lib.check(_lib.load().solat_ff_map_device(self.handle, d_azel.data_ptr(), d_azel.shape[0], d_amp.data_ptr(),
+                                                       d_phase.data_ptr(), stream))
+        else:
+            _lib.check(_lib.load().solat_ff_map_device_st(self.handle, d_azel.data_ptr(), d_azel.shape[0], d_amp.data_ptr(),
+                                                          d_phase.data_ptr(), d_status.data_ptr(), stream))
 
     def mirror_xy(self, azel):
         """(npix, 4, n_rays): M2 hit x, z and M1 hit x, y of the error-free trace -- the coordinates the reference
@@ -447,52 +658,59 @@ class FarFieldPlan:
             pass
 
 
-def mirror_pair_order(pixels, fold_second=False):
-    """Permutation of an (az, el) -- or near-field (x, z) -- pixel list that puts (+az, el) next to (-az, el)
-    (|az| compared to 1e-9 of the map's extent, np.linspace grids are not symmetric to the bit).  fold_second: the
-    four near-field positions (+-x, +-z) next to each other."""
-    pixels = np.asarray(pixels, dtype=np.float64)
-
-    def folded(col):
-        scale = float(np.max(np.abs(col))) if len(col) else 0.0
-        return np.round(np.abs(col) * (1e9 / scale if scale > 0 else 1.0))
-
-    if fold_second:
-        return np.lexsort((np.signbit(pixels[:, 0]), np.signbit(pixels[:, 1]), folded(pixels[:, 1]), folded(pixels[:, 0])))
-    return np.lexsort((np.signbit(pixels[:, 0]), pixels[:, 1], folded(pixels[:, 0])))
+def far_field_plan(tg, theta, phi, data_x, data_y, e_rec, device=None):
+    """FarFieldPlan from the plan cache (same telescope, fan, E_rec grid and values -> the same plan)."""
+    g = _lib.ff_geom(tg)
+    key = ("ff", _lib.context(device).device, bytes(g), float(tg.k),
+           _digest(theta, phi, np.real(data_x), np.real(data_y), np.asarray(e_rec, dtype=np.complex128)))
+    return _plans.get(key, lambda: FarFieldPlan(tg, theta, phi, data_x, data_y, e_rec, device))
 
 
 def ff_map(freq, res_arcmin, num, offset, data_x, data_y, e_rec, n_scan=100, device=None, strict=False, panel_models=None):
     """Far-field beam map `ff_sim.py <freq> <res> <num> <offset>`.  Returns on rank 0
     (pixels [npix,2] (az, el), amp [npix], phase [npix]); None on the other ranks.
+    Under torch.distributed the mirror pairs (+-az, el) are dealt cyclically over the ranks (shard_groups), every
+    rank runs the fused kernels over its pixels in HBM and one NCCL gather brings (amp, phase, status) to rank 0;
+    maps too small to be worth a collective run on rank 0 alone.
     `panel_models` = (pan_mod1, pan_mod2) of ff_sim.py:69-70 switches on panel identification through the panel
     backend (solat_apert_field.set_panel_backend / an importable pan_mod) and the panel-error polynomials; without
     it every ray sits on an error-free panel (the zero-offset case of ff_sim.py:61-62 with the stand-in layout)."""
     tg = ff_tele_geo(freq, offset)
-    theta, phi = ff_fan(n_scan)
-    plan = FarFieldPlan(tg, theta, phi, data_x, data_y, e_rec, device)
     pixels = ff_pixels(tg, res_arcmin, num)
     rank, world = dist_info()
-    # ranks take contiguous blocks of the pixel list ordered so that mirror partners (+az, el), (-az, el) are
-    # neighbours: the kernel traces such a pair once (a pixel's value does not depend on the order or the sharding)
-    order = mirror_pair_order(pixels) if world > 1 else np.arange(len(pixels))
-    lo, hi = shard_bounds(len(pixels), rank, world)
-    mine = pixels[order[lo:hi]]
-    if hi > lo and panel_models is not None:
-        amp, phase, st = plan.run_panel_models(mine, panel_models[0], panel_models[1])
-    elif hi > lo:
-        amp, phase, st = plan.run(mine)
+    work = len(pixels) * float(n_scan) ** 2
+    if _use_ranks(work, world) == 1 and rank != 0:
+        return None
+    theta, phi = ff_fan(n_scan)
+    plan = far_field_plan(tg, theta, phi, data_x, data_y, e_rec, device)
+    if panel_models is not None:
+        return _ff_map_panels(plan, pixels, panel_models, work, strict)
+    out = _run_map(plan, pixels, False, work, strict)
+    if out is None:
+        return None
+    return pixels, out[0][0], out[1][0]
+
+
+def _ff_map_panels(plan, pixels, panel_models, work, strict):
+    """ff_map with panel models: contiguous blocks of the pair-ordered list per rank, host-side gather."""
+    rank, world = dist_info()
+    use = _use_ranks(work, world)
+    order = mirror_pair_order(pixels) if use > 1 else np.arange(len(pixels))
+    lo, hi = shard_bounds(len(pixels), rank, use)
+    if hi > lo:
+        amp, phase, st = plan.run_panel_models(pixels[order[lo:hi]], panel_models[0], panel_models[1])
     else:
         amp, phase, st = np.zeros(0), np.zeros(0), 0
-    _lib.raise_on_status(st, strict)
-    plan.close()
-    if world == 1:
+    if use == 1:
+        _lib.raise_on_status(st, strict)
         return pixels, amp, phase
     import torch
 
     dev = _gather_device(plan.ctx.device)
-    local = torch.from_numpy(np.stack([amp, phase], axis=1)).to(dev)
+    local = torch.from_numpy(np.stack([amp, phase, np.full(len(amp), float(st))], axis=1)).to(dev)
     full = gather_blocks(local, len(pixels))
+    st_all = 0 if full is None else int(np.bitwise_or.reduce(full[:, 2].cpu().numpy().astype(np.int64)))
+    _finish_status(st_all, strict, True)
     if full is None:
         return None
     full = full.cpu().numpy()

@@ -51,6 +51,7 @@ class _LyotTracer:
         self._p = p
         self.out = np.zeros((17, self.n_pts))
         self.status = None
+        self._cache = None
 
     def _run(self, theta, nth, phi, nph):
         lib = _lib.load()
@@ -74,17 +75,26 @@ class _LyotTracer:
         t, p = np.meshgrid(self._theta_axis, self._phi_axis)
         return np.array_equal(self.theta, t.ravel()) and np.array_equal(self.phi, p.ravel())
 
-    def trace_rays(self, ii):
-        out, status = self._run(self.theta[ii:ii + 1], 1, self.phi[ii:ii + 1], 0)
-        _lib.raise_on_status(status[0], strict)
-        return list(out[:, 0])
-
-    def output(self):
+    def _trace_all(self):
         if self._grid_is_default():
             n = len(self._theta_axis)
-            out, status = self._run(self._theta_axis, n, self._phi_axis, n)
-        else:  # the caller edited .theta/.phi: trace the rays as listed
-            out, status = self._run(self.theta, len(self.theta), self.phi, 0)
+            return self._run(self._theta_axis, n, self._phi_axis, n)
+        # the caller edited .theta/.phi: trace the rays as listed
+        return self._run(self.theta, len(self.theta), self.phi, 0)
+
+    def trace_rays(self, ii):
+        """Column ii of output().  The feed taper of the receiver trace is taken about np.mean(self.theta),
+        np.mean(self.phi) over the WHOLE fan (rti:849-853), so a single ray cannot be traced on its own: the fan is
+        traced once (one launch) and kept until .theta/.phi change."""
+        c = self._cache
+        if c is None or not (np.array_equal(c[0], self.theta) and np.array_equal(c[1], self.phi)):
+            out, status = self._trace_all()
+            c = self._cache = (np.array(self.theta, copy=True), np.array(self.phi, copy=True), out, status)
+        _lib.raise_on_status(c[3][ii], strict)
+        return list(c[2][:, ii])
+
+    def output(self):
+        out, status = self._trace_all()
         self.status = status
         _lib.raise_on_status(np.bitwise_or.reduce(status) if len(status) else 0, strict)
         self.out = out

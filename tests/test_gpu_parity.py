@@ -76,6 +76,11 @@ def test_nf_rx_rows():
         out = m.output()
         assert out.shape == (20, m.n_pts) and out.flags["C_CONTIGUOUS"] and out is m.out
         np.testing.assert_allclose(out, d["out_%d" % i], rtol=0, atol=RAY_TOL)
+        if i == 0:
+            # the feed taper (row 4) is taken about the means of the whole fan (rti:849-853): one ray == its column
+            for ii in (0, 3, m.n_pts - 1):
+                np.testing.assert_array_equal(np.array(m.trace_rays(ii)), out[:, ii])
+            assert len({m.trace_rays(ii)[4] for ii in (0, m.n_pts // 2 + 1)}) == 2
 
 
 def test_nf_source_rows_and_trace_rays():
@@ -848,3 +853,145 @@ def test_cli_holo_sim_writes_reference_format(tmp_path):
     t2 = np.loadtxt(ff)
     assert t2.shape == (25, 4) and np.isfinite(t2).all()
     np.testing.assert_allclose(t2[0, :2], (-2 * gu.DE, gu.EL0 - 2 * gu.DE), atol=1e-15)
+
+
+# ------------------------------------------------------------------------------------------------ round 2: the timed configurations
+def _bench_e_rec():
+    """E_rec exactly as bench.py / ff_sim.py build it for config 2: the build's own 51x51 near-field map at 140 GHz
+    through near_field_to_e_rec (+-5 cm grid: the predictor cull, the corner-cell rule and the mirror pairs all act)."""
+    from solat_optics_b200 import maps
+
+    px, amp, ph = maps.holo_map(140.0, device=0)
+    return maps.near_field_to_e_rec(np.c_[px[:, 0], px[:, 1], amp[0], ph[0]])
+
+
+def test_ff_full_map_on_the_bench_e_rec_against_oracle(oracle):
+    """BASELINE config 2 exactly as bench.py times it (ff_sim.py 140 0.25 20 1.32, 41x41 px x 100^2 rays, E_rec = the
+    near-field map of config 1 computed by this build): every pixel against the oracle.  far_field_latrt.py:19-30."""
+    from solat_optics_b200 import maps
+
+    x, y, e = _bench_e_rec()
+    px, amp, ph = maps.ff_map(140, 0.25, 20, 1.32, x, y, e, device=0)
+    tg = maps.ff_tele_geo(140, 1.32)
+    th, phi = maps.ff_fan(100)
+    oa, op = oracle.ff_map(oracle.ff_geo_vec(rx_y_m=-1.32), px, th, phi, x, y, e, tg.k)
+    assert np.count_nonzero(oa) == len(oa)
+    _assert_pixels(amp, ph, oa, op, max_bad=2)
+
+
+def _config5():
+    import bench
+    from solat_optics_b200 import maps
+
+    x, y, e = bench.e_rec_config5()
+    tg = maps.ff_tele_geo(bench.FREQ, bench.OFFSET)
+    return tg, maps.ff_pixels(tg, bench.RES_ARCMIN, bench.NUM), x, y, e
+
+
+def test_ff_config5_stratified_pixels_against_oracle(oracle):
+    """BASELINE config 5 (401x401 px x 1000^2 rays, 101x101 E_rec grid: the 768-thread CTA shape with two winner tables,
+    95 % of the 20-bit ray-index range): 64 stratified pixels -- corners, edges, az = 0, both signs of az -- against
+    the oracle at the full fan."""
+    import bench
+    from solat_optics_b200 import maps
+
+    tg, px, x, y, e = _config5()
+    th, phi = maps.ff_fan(bench.N_SCAN)
+    idx = bench.stratified_pixel_indices(2 * bench.NUM + 1)
+    assert len(idx) == 64 and (2 * bench.NUM + 1) * bench.NUM + bench.NUM in idx
+    plan = maps.far_field_plan(tg, th, phi, x, y, e, 0)
+    amp, ph, st = plan.run(px[idx])
+    assert st == 0
+    oa, op = oracle.ff_map(oracle.ff_geo_vec(rx_y_m=-bench.OFFSET), px[idx], th, phi, x, y, e, tg.k)
+    _assert_pixels(amp, ph, oa, op)
+    # a pixel's value does not depend on the list it comes in: the same pixels inside a longer list, other order
+    more = np.r_[px[idx[::-1]], px[1000:1010]]
+    a2, p2, st = plan.run(more)
+    canon = px[idx[::-1], 0] >= 0
+    np.testing.assert_array_equal(a2[:64][canon], amp[::-1][canon])
+    np.testing.assert_allclose(a2[:64], amp[::-1], rtol=1e-12)
+    assert np.abs(gu.wrap(p2[:64] - ph[::-1])).max() < 1e-12
+
+
+def test_ff_large_pixel_lists_and_mixed_sizes_on_one_plan(oracle):
+    """Lists above 4096 pixels pair on the device with three kernels (ff_pair_insert / attach / emit) instead of one
+    CTA, and their per-item records are chunked; calls of both kinds alternate on ONE plan (the small path must not
+    leave a stale item counter behind for the large one).  Config-5 pointing grid (121 x 121 of its pixels), 40^2 rays."""
+    import bench
+    from solat_optics_b200 import maps
+
+    x, y, e = bench.e_rec_config5()
+    tg = maps.ff_tele_geo(bench.FREQ, bench.OFFSET)
+    th, phi = maps.ff_fan(40)
+    px = maps.ff_pixels(tg, bench.RES_ARCMIN * 3, 60)              # 121 x 121 = 14641 pixels
+    plan = maps.far_field_plan(tg, th, phi, x, y, e, 0)
+    big1 = plan.run(px)
+    assert big1[2] == 0
+    big2 = plan.run(px[:9001])
+    small = plan.run(px[:3000])
+    big3 = plan.run(px)
+    np.testing.assert_array_equal(big3[0], big1[0]); np.testing.assert_array_equal(big3[1], big1[1])
+    canon = px[:, 0] >= 0
+    for part, n in ((big2, 9001), (small, 3000)):
+        np.testing.assert_array_equal(part[0][canon[:n]], big1[0][:n][canon[:n]])
+        np.testing.assert_allclose(part[0], big1[0][:n], rtol=1e-12)
+        assert np.abs(gu.wrap(part[1] - big1[1][:n])).max() < 1e-12
+    idx = np.arange(0, len(px), 37)
+    oa, op = oracle.ff_map(oracle.ff_geo_vec(rx_y_m=-bench.OFFSET), px[idx], th, phi, x, y, e, tg.k)
+    ok = oa > 0
+    _assert_pixels(big1[0][idx][ok], big1[1][idx][ok], oa[ok], op[ok])
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import bench
+    from solat_optics_b200 import maps
+
+    maps.SHARD_MIN_PIXEL_RAYS = 0.0                                # deal even these small maps over the ranks
+    x, y, e = bench.e_rec_config5()
+    ff = maps.ff_map(140, 0.25, 9, 1.32, x, y, e, n_scan=60, device=rank)
+    nf = maps.holo_map([150.0, 220.0], res=21, n_scan=40, device=rank)
+    if rank == 0:
+        q.put((ff, nf))
+    else:
+        assert ff is None and nf is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_nccl_sharded_maps_equal_single_rank_maps():
+    """the map dealt over 2 ranks (cyclic mirror groups, NCCL gather to rank 0, un-permute) equals the
+    1-rank map: bit for bit for az >= 0 / x, z >= 0 (a mirror group is traced whole on one rank either way)."""
+    import socket
+
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import bench
+    from solat_optics_b200 import maps
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ff, nf = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    x, y, e = bench.e_rec_config5()
+    ff1 = maps.ff_map(140, 0.25, 9, 1.32, x, y, e, n_scan=60, device=0)
+    nf1 = maps.holo_map([150.0, 220.0], res=21, n_scan=40, device=0)
+    for got, ref in ((ff, ff1), (nf, nf1)):
+        np.testing.assert_array_equal(got[0], ref[0])
+        np.testing.assert_array_equal(got[1], ref[1])
+        np.testing.assert_array_equal(got[2], ref[2])
