@@ -189,6 +189,23 @@ SOLAT_API int solat_ff_map_panels_host(solat_ff_plan *plan, const double *azel, 
                              const short *pan_idx2, const double *pan1, int np1, const double *pan2, int np2,
                              double *amp, double *phase, int *status);
 
+/* The same map with the panels identified ON THE DEVICE (no per-ray round trip through the host).  A panel layout is
+ * what an identify_panel that loops over rectangular panels computes (the external pan_mod's is not part of the
+ * reference; call sites saf:596-617): panel k of a mirror covers [x0, x1) x [y0, y1) in the coordinates the reference
+ * hands to identify_panel -- M1: (x, y - y_cent_m1), M2: (x, z) of the ideal-mirror hit, telescope frame, mm -- a later
+ * panel overrides an earlier one, a point in no panel sits on no panel.  model_col[k] = column of the mirror's panel
+ * model whose (row, col) ids are panel k's (first match, saf:626,805), -1 = the panel is not in the model: rays there
+ * are dropped (saf:626-628,805-809).  Per ray the kernel runs the reference's two passes (ff_sim.py:208-209): ideal
+ * trace -> panels -> trace with the panels' error polynomials.                                                  */
+typedef struct {
+    const double *rect;    /* [n][4]: x0, x1, y0, y1 */
+    const int *model_col;  /* [n] */
+    int n;
+} solat_panel_layout;
+SOLAT_API int solat_ff_map_panel_layout_host(solat_ff_plan *plan, const double *azel, int npix, const solat_panel_layout *m1,
+                                   const solat_panel_layout *m2, const double *pan1, int np1, const double *pan2, int np2,
+                                   double *amp, double *phase, int *status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,10 @@ class FfGeom(ctypes.Structure):
     _fields_ = [("th_1", c_d), ("th2", c_d), ("rotc_mm", c_d * 3), ("src_mm", c_d * 3), ("foc_y_mm", c_d)]
 
 
+class PanelLayoutC(ctypes.Structure):
+    _fields_ = [("rect", c_dp), ("model_col", c_ip), ("n", c_i)]
+
+
 # name -> (restype, argtypes); mirrors include/solat_b200.h one to one
 SIGNATURES = {
     "solat_abi_version": (c_i, []),
@@ -74,6 +78,8 @@ SIGNATURES = {
     "solat_ff_plan_status": (c_i, [c_vp, c_ip]),
     "solat_ff_map_mirror_xy_host": (c_i, [c_vp, c_dp, c_i, c_dp, c_ip]),
     "solat_ff_map_panels_host": (c_i, [c_vp, c_dp, c_i, c_sp, c_sp, c_dp, c_i, c_dp, c_i, c_dp, c_dp, c_ip]),
+    "solat_ff_map_panel_layout_host": (c_i, [c_vp, c_dp, c_i, ctypes.POINTER(PanelLayoutC), ctypes.POINTER(PanelLayoutC), c_dp, c_i,
+                                             c_dp, c_i, c_dp, c_dp, c_ip]),
 }
 
 _lib = None

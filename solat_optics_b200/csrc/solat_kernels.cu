@@ -879,6 +879,45 @@ __global__ void ff_project_fill_kernel(const double* sim, int n_pts, const int* 
 constexpr int FF_T = SOLAT_FF_T;
 constexpr int FF_WQ = 64;            // per-warp queue capacity
 constexpr int FF_MAX_ROWS = 1024;    // phi rows the interval walk keeps on chip (FF_ROW_K intervals each); larger fans take the queue walk
+// Rectangular panel layout of one mirror on the device: panel k covers [x0, x1) x [y0, y1) in the coordinates the
+// reference hands to pan_mod.identify_panel (saf:596-612: M2 hit (x, z), M1 hit (x, y - y_cent), telescope frame, ideal
+// mirrors); a later panel overrides an earlier one (an identify_panel that loops over the panels and writes their ids);
+// col[k] = column of the panel model (first match of the panel's (row, col) ids, saf:626,805) or -1.  A G x G bucket
+// grid over the bounding box lists, per bucket, the panels that overlap it (ascending): the exact FP64 test runs on
+// those only.
+constexpr int PANEL_G = 32, PANEL_BK = 8;
+struct PanelLayoutDev {
+    const double4* rect;             // [n] (x0, x1, y0, y1)
+    const int* col;                  // [n]
+    const unsigned short* bucket;    // [G * G][BK] panel indices, 0xffff = end of list
+    int n, linear;                   // linear: a bucket overflowed, scan all panels
+    float bx0, by0, inv_bw, inv_bh;
+};
+__device__ __forceinline__ bool panel_holds(const PanelLayoutDev& L, int k, double x, double y)
+{
+    const double2* r = reinterpret_cast<const double2*>(L.rect + k);
+    const double2 rx = __ldg(r), ry = __ldg(r + 1);
+    return x >= rx.x && x < rx.y && y >= ry.x && y < ry.y;
+}
+__device__ __forceinline__ int panel_lookup(const PanelLayoutDev& L, double x, double y)
+{
+    int found = -1;
+    if (L.linear) {
+        for (int k = 0; k < L.n; k++)
+            if (panel_holds(L, k, x, y)) found = k;
+    } else {
+        const int gx = (int)floorf(((float)x - L.bx0) * L.inv_bw), gy = (int)floorf(((float)y - L.by0) * L.inv_bh);
+        if (gx < 0 || gx >= PANEL_G || gy < 0 || gy >= PANEL_G) return -1;
+        const unsigned short* b = L.bucket + (size_t)(gy * PANEL_G + gx) * PANEL_BK;
+        for (int i = 0; i < PANEL_BK; i++) {
+            const int k = __ldg(b + i);
+            if (k == 0xffff) break;
+            if (panel_holds(L, k, x, y)) found = k;
+        }
+    }
+    return found >= 0 ? __ldg(L.col + found) : -1;
+}
+
 struct FfMapParams {
     AngleTabs ang;
     solat_ff_geom g;
@@ -896,10 +935,12 @@ struct FfMapParams {
     const FfItem* items;     // pair mode: work items (azel unused), counters[0] of them; two winner tables per CTA
     const int* counters;
     int item0;               // pair mode: CTA b handles item item0 + b (its record is record b)
-    // panel models (ff_map_kernel<true> only): per (pixel, ray) column of pan1 / pan2, -1 = the ray sits on no panel
+    // panel models.  PANEL = 1: per (pixel, ray) column of pan1 / pan2 derived on the host, -1 = the ray sits on no
+    // panel.  PANEL = 2: the panels are looked up on the device from the ideal-mirror hits (lay1, lay2).
     const short *pidx1, *pidx2;
     const double *pan1, *pan2;   // (10, np) row-major [row, col, a, b, c, d, e, f, x0, y0]  (saf:667-674)
     int np1, np2;
+    PanelLayoutDev lay1, lay2;
 };
 
 __device__ __forceinline__ PanelErr load_panel(const double* pan, int np, int col)
@@ -1097,7 +1138,7 @@ __global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
 //   * PANEL (adjuster-error studies, ff_sim.py:61-70 with non-zero offsets): every ray carries the panel-model
 //     columns the host derived with pan_mod.identify_panel; rays on no panel are dropped (saf:626-628,805-809), the
 //     others see their panels' error polynomials inside both Newton solves.
-template <bool PANEL, int T, int MINB>
+template <int PANEL, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
 {
     constexpr int FF_T = T, FF_WARPS = T / 32;
@@ -1126,7 +1167,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
         int* dst = reinterpret_cast<int*>(fr);
         for (int i = tid; i < (int)(sizeof(FfFrames) / sizeof(int)); i += FF_T) dst[i] = __ldg(src + i);
         if (tid == 0) s_queue_walk = __ldg(reinterpret_cast<const int*>(rec + FF_REC_FRAMES));
-        if (!PANEL && q.rows) {
+        if (PANEL != 1 && q.rows) {
             const int* rows = reinterpret_cast<const int*>(rec + FF_REC_HEAD);
             for (int i = tid; i < 2 * nvr + 1; i += FF_T) row_lo[i] = __ldg(rows + i);
         }
@@ -1149,7 +1190,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
         __syncthreads();
     }
     const int nth = q.ang.nth, n_rays = nth * q.ang.nph;
-    const bool queue_walk = PANEL || s_queue_walk != 0;
+    const bool queue_walk = PANEL == 1 || s_queue_walk != 0;
 
     int* wq = queues + warp * FF_WQ;
     const double cx = fr->centre[0], cz = fr->centre[2];
@@ -1173,92 +1214,124 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
         }
         row = a;
     }
-    for (;;) {
-        int r0 = -1;
-        if (!queue_walk) {
-            if (v_top < v_bot) break;
+    // bin one traced ray (i, j) into the winner table(s): cells first (a later ray may hold them already), then ONE key
+    // for both pixels of a pair
+    auto bin = [&](int i, int j, double opl, double fx, double fz) {
+        if (opl != 0.0 && !not_finite(opl)) {                                   // ffl:10
+            const int r0 = j * nth + i;
+            int cell = -1, cell_m = -1, rm = 0;
+            if (out_pos >= 0) {
+                cell = ff_cell(fx - cx, fz - cz, grid);
+                if (cell >= 0 && (win[cell] >> FF_KEY_SHIFT) >= (unsigned long long)(r0 + 1)) cell = -1;
+            }
+            if (out_neg >= 0) {
+                // the mirror pixel (-az, el): this ray is its ray (nph-1-j, i), lands at (-x, z) about its own centre
+                rm = (q.ang.nph - 1 - j) * nth + i;
+                cell_m = ff_cell(cx - fx, fz - fr->centre_mz, grid);
+                if (cell_m >= 0 && (win_m[cell_m] >> FF_KEY_SHIFT) >= (unsigned long long)(rm + 1)) cell_m = -1;
+            }
+            if (cell >= 0 || cell_m >= 0) {
+                bool exact;
+                const unsigned long long low = ff_key(-1, opl, q.key_base, q.key_inv_unit, exact, q.key_unit);   // ray bits 0
+                if (!exact) st |= ST_RANGE;
+                if (cell >= 0) atomicMax(win + cell, low | ((unsigned long long)(r0 + 1) << FF_KEY_SHIFT));     // ffl:28: last write wins
+                if (cell_m >= 0) atomicMax(win_m + cell_m, low | ((unsigned long long)(rm + 1) << FF_KEY_SHIFT));
+            }
+        }
+    };
+    // trace ray (i, j) and bin it
+    auto trace = [&](int i, int j) {
+        const vec3 d = launch_dir(__ldg(q.ang.st + i), __ldg(q.ang.ct + i), __ldg(q.ang.sp + j), __ldg(q.ang.cp + j));
+        vec3 Pa;
+        double t_ap;
+        ff_aperture(sC, g, *fr, d, t_ap, Pa);
+        double opl, fx, fz;
+        int rst;
+        if (PANEL == 1) {
+            const size_t at = (size_t)pix * n_rays + (j * nth + i);
+            const PanelErr e1 = load_panel(q.pan1, q.np1, __ldg(q.pidx1 + at)), e2 = load_panel(q.pan2, q.np2, __ldg(q.pidx2 + at));
+            FfRay ray;
+            ff_ray_trace<false, true>(sC, *fr, d, t_ap, Pa, g.foc_y, &e1, &e2, s_t2e, ray);
+            opl = ray.opl; fx = ray.foc.x; fz = ray.foc.z; rst = ray.status;
+        } else if (PANEL == 2) {
+            // the reference's two passes (ff_sim.py:208-209): ideal mirrors -> which panels (saf:596-628), then the
+            // trace with those panels' error polynomials; a ray on no panel of either model is dropped (saf:626-628,805-809)
+            FfRay ray;
+            ff_ray_trace<true, false>(sC, *fr, d, t_ap, Pa, g.foc_y, nullptr, nullptr, nullptr, ray);
+            rst = ray.status;
+            const int c1 = panel_lookup(q.lay1, ray.m1.x, ray.m1.y - sC.ff[2]);
+            const int c2 = c1 >= 0 ? panel_lookup(q.lay2, ray.m2.x, ray.m2.z) : -1;
+            opl = 0.0; fx = fz = 0.0;
+            if (c2 >= 0) {
+                const PanelErr e1 = load_panel(q.pan1, q.np1, c1), e2 = load_panel(q.pan2, q.np2, c2);
+                ff_ray_trace<false, true>(sC, *fr, d, t_ap, Pa, g.foc_y, &e1, &e2, s_t2e, ray);
+                opl = ray.opl; fx = ray.foc.x; fz = ray.foc.z; rst |= ray.status;
+            }
+        } else {
+            ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);
+        }
+        st |= rst;
+        bin(i, j, opl, fx, fz);
+    };
+    if (PANEL == 0 && !queue_walk) {
+        // interval walk, the hot loop of the plain map on its own (no queue state alive): 32 rays of the warp's share of
+        // the dense list per step
+        for (; v_top >= v_bot; v_top -= 32) {
             const int v = v_top - lane;
             if (v >= v_bot) {
-                while (row_pre[row] > v) --row;           // the walk only moves down the list, so does the row cursor
-                r0 = (row / FF_ROW_K) * nth + row_lo[row] + (v - row_pre[row]);
+                while (row_pre[row] > v) --row;               // the walk only moves down the list, so does the row cursor
+                trace(row_lo[row] + (v - row_pre[row]), row / FF_ROW_K);
             }
-            v_top -= 32;
-        } else {
-            const bool more = chunk >= 0;
-            if (cnt < 32 && more) {
-                // fill: aperture test (saf:359-379) on 32 candidate rays
-                const int r = chunk * 32 + lane;
-                bool ok = false;
-                if (r < n_rays) {
-                    // FP32 prefilter on the FMA pipe; only rays within ~0.02 mm of the rim need the FP64 test
-                    int i, j;
-                    ray_ij(q.ang, r, i, j);
-                    const float stf = __ldg(q.ang.stf + i);
-                    const int c = ff_aperture_coarse(*fr, stf * __ldg(q.ang.cpf + j), stf * __ldg(q.ang.spf + j), __ldg(q.ang.ctf + i));
-                    ok = c > 0;
-                    if (c < 0) {
-                        vec3 Pa;
-                        double t_ap;
-                        ok = ff_aperture(sC, g, *fr, ray_dir(q.ang, r), t_ap, Pa);
-                    }
-                    if (PANEL) {
-                        const size_t at = (size_t)pix * n_rays + r;
-                        ok = ok && __ldg(q.pidx1 + at) >= 0 && __ldg(q.pidx2 + at) >= 0;
-                    }
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) wq[cnt + __popc(m & ((1u << lane) - 1u))] = r;
-                cnt += __popc(m);
-                chunk -= FF_WARPS;
-                __syncwarp();
-                continue;
-            }
-            if (cnt == 0) break;
-            const int n_take = min(cnt, 32);
-            r0 = lane < n_take ? wq[cnt - 1 - lane] : -1;
-            cnt -= n_take;
-            __syncwarp();
         }
-        if (r0 >= 0) {
-            const vec3 d = ray_dir(q.ang, r0);
-            vec3 Pa;
-            double t_ap;
-            ff_aperture(sC, g, *fr, d, t_ap, Pa);
-            double opl, fx, fz;
-            int rst;
-            if (PANEL) {
-                const size_t at = (size_t)pix * n_rays + r0;
-                const PanelErr e1 = load_panel(q.pan1, q.np1, __ldg(q.pidx1 + at)), e2 = load_panel(q.pan2, q.np2, __ldg(q.pidx2 + at));
-                FfRay ray;
-                ff_ray_trace<false, true>(sC, *fr, d, t_ap, Pa, g.foc_y, &e1, &e2, s_t2e, ray);
-                opl = ray.opl; fx = ray.foc.x; fz = ray.foc.z; rst = ray.status;
+    } else {
+        for (;;) {
+            int ti = -1, tj = 0;
+            if (!queue_walk) {
+                if (v_top < v_bot) break;
+                const int v = v_top - lane;
+                if (v >= v_bot) {
+                    while (row_pre[row] > v) --row;
+                    ti = row_lo[row] + (v - row_pre[row]); tj = row / FF_ROW_K;
+                }
+                v_top -= 32;
             } else {
-                ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);
+                const bool more = chunk >= 0;
+                if (cnt < 32 && more) {
+                    // fill: aperture test (saf:359-379) on 32 candidate rays
+                    const int r = chunk * 32 + lane;
+                    bool ok = false;
+                    if (r < n_rays) {
+                        // FP32 prefilter on the FMA pipe; only rays within ~0.02 mm of the rim need the FP64 test
+                        int i, j;
+                        ray_ij(q.ang, r, i, j);
+                        const float stf = __ldg(q.ang.stf + i);
+                        const int c = ff_aperture_coarse(*fr, stf * __ldg(q.ang.cpf + j), stf * __ldg(q.ang.spf + j), __ldg(q.ang.ctf + i));
+                        ok = c > 0;
+                        if (c < 0) {
+                            vec3 Pa;
+                            double t_ap;
+                            ok = ff_aperture(sC, g, *fr, ray_dir(q.ang, r), t_ap, Pa);
+                        }
+                        if (PANEL == 1) {
+                            const size_t at = (size_t)pix * n_rays + r;
+                            ok = ok && __ldg(q.pidx1 + at) >= 0 && __ldg(q.pidx2 + at) >= 0;
+                        }
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, ok);
+                    if (ok) wq[cnt + __popc(m & ((1u << lane) - 1u))] = r;
+                    cnt += __popc(m);
+                    chunk -= FF_WARPS;
+                    __syncwarp();
+                    continue;
+                }
+                if (cnt == 0) break;
+                const int n_take = min(cnt, 32);
+                const int r0 = lane < n_take ? wq[cnt - 1 - lane] : -1;
+                cnt -= n_take;
+                __syncwarp();
+                if (r0 >= 0) ray_ij(q.ang, r0, ti, tj);
             }
-            st |= rst;
-            if (opl != 0.0 && !not_finite(opl)) {                                   // ffl:10
-                // cells first (a later ray may hold them already), then ONE key for both pixels of a pair
-                int cell = -1, cell_m = -1, rm = 0;
-                if (out_pos >= 0) {
-                    cell = ff_cell(fx - cx, fz - cz, grid);
-                    if (cell >= 0 && (win[cell] >> FF_KEY_SHIFT) >= (unsigned long long)(r0 + 1)) cell = -1;
-                }
-                if (out_neg >= 0) {
-                    // the mirror pixel (-az, el): this ray is its ray (nph-1-j, i), lands at (-x, z) about its own centre
-                    int i, j;
-                    ray_ij(q.ang, r0, i, j);
-                    rm = (q.ang.nph - 1 - j) * nth + i;
-                    cell_m = ff_cell(cx - fx, fz - fr->centre_mz, grid);
-                    if (cell_m >= 0 && (win_m[cell_m] >> FF_KEY_SHIFT) >= (unsigned long long)(rm + 1)) cell_m = -1;
-                }
-                if (cell >= 0 || cell_m >= 0) {
-                    bool exact;
-                    const unsigned long long low = ff_key(-1, opl, q.key_base, q.key_inv_unit, exact, q.key_unit);   // ray bits 0
-                    if (!exact) st |= ST_RANGE;
-                    if (cell >= 0) atomicMax(win + cell, low | ((unsigned long long)(r0 + 1) << FF_KEY_SHIFT));     // ffl:28: last write wins
-                    if (cell_m >= 0) atomicMax(win_m + cell_m, low | ((unsigned long long)(rm + 1) << FF_KEY_SHIFT));
-                }
-            }
+            if (ti >= 0) trace(ti, tj);
         }
     }
     __syncthreads();
@@ -2077,6 +2150,9 @@ struct solat_ff_plan {
     DevBuf<int> status;
     DevBuf<short> pidx;                     // [2][npix][n_rays] panel columns of a panel-model map
     DevBuf<double> pan, xy;                 // panel models; mirror coordinates for identify_panel
+    DevBuf<double4> lay_rect;               // device panel layouts of both mirrors (solat_ff_map_panel_layout_host)
+    DevBuf<int> lay_col;
+    DevBuf<unsigned short> lay_bucket;
     DevBuf<unsigned char> rec;              // per-pixel records of ff_prep_kernel (frames, ray intervals)
     DevBuf<FfPairSlot> pair_slots;          // mirror pairing of a pixel list (ff_pair_*_kernel)
     DevBuf<int> pair_ints;
@@ -2090,7 +2166,7 @@ struct solat_ff_plan {
 
 constexpr int FF_NSHAPES = 3;
 static const int FF_SHAPES[FF_NSHAPES][2] = {{FF_T, SOLAT_FF_MINB}, {384, 2}, {768, 1}};   // threads, CTAs per SM
-template <bool PANEL>
+template <int PANEL>
 static void ff_map_dispatch(int shape, const FfMapParams& q, int npix, size_t smem, cudaStream_t s)
 {
     if (shape == 0) ff_map_kernel<PANEL, FF_T, SOLAT_FF_MINB><<<npix, FF_T, smem, s>>>(q);
@@ -2107,31 +2183,33 @@ static int ff_map_set_smem(int device, int shape, size_t smem)
     size_t& have = granted[device & 63][shape];
     if (smem <= have) return SOLAT_OK;
     const int b = (int)smem;
-    if (shape == 0) {
-        CK(cudaFuncSetAttribute(ff_map_kernel<false, FF_T, SOLAT_FF_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-        CK(cudaFuncSetAttribute(ff_map_kernel<true, FF_T, SOLAT_FF_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-    } else if (shape == 1) {
-        CK(cudaFuncSetAttribute(ff_map_kernel<false, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-        CK(cudaFuncSetAttribute(ff_map_kernel<true, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-    } else {
-        CK(cudaFuncSetAttribute(ff_map_kernel<false, 768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-        CK(cudaFuncSetAttribute(ff_map_kernel<true, 768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-    }
+#define SOLAT_FF_SMEM_ATTR(T_, B_)                                                                                       \
+    CK(cudaFuncSetAttribute(ff_map_kernel<0, T_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));                   \
+    CK(cudaFuncSetAttribute(ff_map_kernel<1, T_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));                   \
+    CK(cudaFuncSetAttribute(ff_map_kernel<2, T_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    if (shape == 0) { SOLAT_FF_SMEM_ATTR(FF_T, SOLAT_FF_MINB) }
+    else if (shape == 1) { SOLAT_FF_SMEM_ATTR(384, 2) }
+    else { SOLAT_FF_SMEM_ATTR(768, 1) }
+#undef SOLAT_FF_SMEM_ATTR
     have = smem;
     return SOLAT_OK;
 }
 
 // prep + map over the pixels in chunks (the per-pixel records are scratch: ~1.7 kB per pixel for a 100 x 100 fan,
 // ~9 kB for 1000 x 1000).  `panel`: ff_map_kernel<true> with q's panel fields set (queue walk, frames only).
-static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cudaStream_t s, bool clear_status = false)
+// `panel`: 0 none; 1 ff_map_kernel<1> with q's per-ray panel columns (queue walk, frames only); 2 ff_map_kernel<2> with
+// q's panel layouts (interval walk; the focal-position cull only when `cull`: every panel error is zero).
+static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cudaStream_t s, bool clear_status = false, bool cull = true)
 {
-    const int rows = panel ? 0 : p->rows;
+    const int rows = panel == 1 ? 0 : p->rows;
     const bool pairs = !panel && p->pairs;
     const size_t stride = ff_rec_stride(rows ? p->ang.tabs.nph : 0);
-    const int chunk = (int)std::min<size_t>((size_t)npix, std::max<size_t>(2048, ((size_t)192 << 20) / stride));
+    // records of up to 1.5 GB per call (HBM holds 180 GB): every chunk boundary drains the GPU (tail of a wave of CTAs
+    // that each run for milliseconds on a 10^6-ray fan), so a 401 x 401 map goes through in 2 chunks instead of 14
+    const int chunk = (int)std::min<size_t>((size_t)npix, std::max<size_t>(2048, ((size_t)1536 << 20) / stride));
     if (int rc = p->rec.reserve((size_t)chunk * stride)) return rc;
     FfPrepParams pq;
-    pq.ang = p->ang.tabs; pq.g = p->g; pq.rows = rows; pq.prefilter = rows ? p->prefilter : 0;
+    pq.ang = p->ang.tabs; pq.g = p->g; pq.rows = rows; pq.prefilter = (rows && cull) ? p->prefilter : 0;
     pq.grid = p->grid; pq.rec = p->rec.p; pq.stride = stride;
     pq.items = nullptr; pq.counters = nullptr; pq.item0 = 0;
     q.items = nullptr; q.counters = nullptr; q.item0 = 0;
@@ -2181,9 +2259,10 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, bool panel, cud
         }
         ff_prep_kernel<<<n, FF_PREP_T, prep_smem, s>>>(pq);
         LAUNCHED();
-        if (panel) { q.pidx1 = i1 + (size_t)p0 * p->n_rays; q.pidx2 = i2 + (size_t)p0 * p->n_rays; }
-        if (panel) ff_map_dispatch<true>(p->shape, q, n, p->smem, s);
-        else ff_map_dispatch<false>(p->shape, q, n, p->smem, s);
+        if (panel == 1) { q.pidx1 = i1 + (size_t)p0 * p->n_rays; q.pidx2 = i2 + (size_t)p0 * p->n_rays; }
+        if (panel == 1) ff_map_dispatch<1>(p->shape, q, n, p->smem, s);
+        else if (panel == 2) ff_map_dispatch<2>(p->shape, q, n, p->smem, s);
+        else ff_map_dispatch<0>(p->shape, q, n, p->smem, s);
         LAUNCHED();
     }
     return SOLAT_OK;
@@ -2200,7 +2279,8 @@ static int ff_map_launch(solat_ff_plan* p, const double* d_azel, int npix, doubl
     q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
     q.amp = d_amp; q.phase = d_phase; q.status = own_status ? own_status : p->status.p;
     q.pidx1 = q.pidx2 = nullptr; q.pan1 = q.pan2 = nullptr; q.np1 = q.np2 = 0;
-    return ff_map_run(p, q, npix, false, s, own_status != nullptr);
+    memset(&q.lay1, 0, sizeof(q.lay1)); memset(&q.lay2, 0, sizeof(q.lay2));
+    return ff_map_run(p, q, npix, 0, s, own_status != nullptr);
 }
 
 extern "C" {
@@ -2362,11 +2442,111 @@ int solat_ff_map_panels_host(solat_ff_plan* p, const double* azel, int npix, con
     q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
     q.amp = p->ctx->stage_out.p; q.phase = p->ctx->stage_out.p + n; q.status = p->status.p;
     q.pidx1 = p->pidx.p; q.pidx2 = p->pidx.p + nr; q.pan1 = p->pan.p; q.pan2 = p->pan.p + 10 * (size_t)np1; q.np1 = np1; q.np2 = np2;
-    if (int rc = ff_map_run(p, q, npix, true, s)) return rc;
+    memset(&q.lay1, 0, sizeof(q.lay1)); memset(&q.lay2, 0, sizeof(q.lay2));
+    if (int rc = ff_map_run(p, q, npix, 1, s)) return rc;
     pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->ctx->stage_out.p + 2 * n);
     LAUNCHED();
     CK(cudaMemcpyAsync(p->ctx->pin.p, p->ctx->stage_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    memcpy(amp, p->ctx->pin.p, n * sizeof(double));
+    memcpy(phase, p->ctx->pin.p + n, n * sizeof(double));
+    const int st = (int)p->ctx->pin.p[2 * n];
+    if (st) CK(cudaMemset(p->status.p, 0, sizeof(int)));
+    if (status) *status = st;
+    return SOLAT_OK;
+}
+
+
+// host side of a device panel layout: bucket grid over the bounding box of the panels
+struct PanelLayoutHost {
+    std::vector<double4> rect;
+    std::vector<int> col;
+    std::vector<unsigned short> bucket;
+    int linear = 0;
+    float bx0 = 0, by0 = 0, inv_bw = 0, inv_bh = 0;
+};
+static int build_layout(const solat_panel_layout* in, int np_model, PanelLayoutHost& out)
+{
+    if (!in || in->n < 0 || in->n > 65000 || (in->n && (!in->rect || !in->model_col))) return fail(SOLAT_ERR_ARG, "bad panel layout");
+    const int n = in->n;
+    out.rect.resize(n); out.col.resize(n);
+    double x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+    for (int k = 0; k < n; k++) {
+        const double* r = in->rect + 4 * (size_t)k;
+        if (!(r[0] < r[1]) || !(r[2] < r[3])) return fail(SOLAT_ERR_ARG, "panel rectangle with x0 >= x1 or y0 >= y1");
+        if (in->model_col[k] >= np_model) return fail(SOLAT_ERR_ARG, "panel layout names a column outside its panel model");
+        out.rect[k] = make_double4(r[0], r[1], r[2], r[3]);
+        out.col[k] = in->model_col[k];
+        if (k == 0) { x0 = r[0]; x1 = r[1]; y0 = r[2]; y1 = r[3]; }
+        x0 = std::min(x0, r[0]); x1 = std::max(x1, r[1]); y0 = std::min(y0, r[2]); y1 = std::max(y1, r[3]);
+    }
+    out.bucket.assign((size_t)PANEL_G * PANEL_G * PANEL_BK, 0xffff);
+    if (n == 0) { out.inv_bw = out.inv_bh = 0.0f; return SOLAT_OK; }
+    // a little wider than the panels, and every panel is entered into the buckets its bounds padded by `pad` touch:
+    // the bucket index is computed in single precision on the device
+    const double pad = 1e-3 * std::max(x1 - x0, y1 - y0) + 1e-2;
+    x0 -= 2 * pad; y0 -= 2 * pad; x1 += 2 * pad; y1 += 2 * pad;
+    const double bw = (x1 - x0) / PANEL_G, bh = (y1 - y0) / PANEL_G;
+    out.bx0 = (float)x0; out.by0 = (float)y0; out.inv_bw = (float)(1.0 / bw); out.inv_bh = (float)(1.0 / bh);
+    std::vector<int> fill((size_t)PANEL_G * PANEL_G, 0);
+    for (int k = 0; k < n && !out.linear; k++) {
+        const double4 r = out.rect[k];
+        const int gx0 = std::max(0, (int)floor((r.x - pad - x0) / bw)), gx1 = std::min(PANEL_G - 1, (int)floor((r.y + pad - x0) / bw));
+        const int gy0 = std::max(0, (int)floor((r.z - pad - y0) / bh)), gy1 = std::min(PANEL_G - 1, (int)floor((r.w + pad - y0) / bh));
+        for (int gy = gy0; gy <= gy1 && !out.linear; gy++)
+            for (int gx = gx0; gx <= gx1; gx++) {
+                int& f = fill[(size_t)gy * PANEL_G + gx];
+                if (f >= PANEL_BK) { out.linear = 1; break; }
+                out.bucket[((size_t)gy * PANEL_G + gx) * PANEL_BK + f++] = (unsigned short)k;
+            }
+    }
+    return SOLAT_OK;
+}
+
+int solat_ff_map_panel_layout_host(solat_ff_plan* p, const double* azel, int npix, const solat_panel_layout* m1,
+                                   const solat_panel_layout* m2, const double* pan1, int np1, const double* pan2, int np2,
+                                   double* amp, double* phase, int* status)
+{
+    if (!p || !azel || !m1 || !m2 || !pan1 || !pan2 || !amp || !phase || npix <= 0 || np1 <= 0 || np2 <= 0)
+        return fail(SOLAT_ERR_ARG, "bad argument");
+    PanelLayoutHost h1, h2;
+    if (int rc = build_layout(m1, np1, h1)) return rc;
+    if (int rc = build_layout(m2, np2, h2)) return rc;
+    std::lock_guard<std::mutex> lock(p->ctx->stage_mu);
+    CK(cudaSetDevice(p->ctx->device));
+    cudaStream_t s = p->ctx->stream;
+    const size_t n = (size_t)npix, n1 = h1.rect.size(), n2 = h2.rect.size(), nb = (size_t)PANEL_G * PANEL_G * PANEL_BK;
+    if (int rc = p->ctx->stage_in.upload(azel, 2 * n, s)) return rc;
+    if (int rc = p->ctx->stage_out.reserve(2 * n + 1)) return rc;
+    if (int rc = p->ctx->pin.reserve(2 * n + 1)) return rc;
+    if (int rc = p->pan.reserve(10 * ((size_t)np1 + np2))) return rc;
+    if (int rc = p->lay_rect.reserve(n1 + n2 + 1)) return rc;
+    if (int rc = p->lay_col.reserve(n1 + n2 + 1)) return rc;
+    if (int rc = p->lay_bucket.reserve(2 * nb)) return rc;
+    CK(cudaMemcpyAsync(p->pan.p, pan1, 10 * (size_t)np1 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->pan.p + 10 * (size_t)np1, pan2, 10 * (size_t)np2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (n1) CK(cudaMemcpyAsync(p->lay_rect.p, h1.rect.data(), n1 * sizeof(double4), cudaMemcpyHostToDevice, s));
+    if (n2) CK(cudaMemcpyAsync(p->lay_rect.p + n1, h2.rect.data(), n2 * sizeof(double4), cudaMemcpyHostToDevice, s));
+    if (n1) CK(cudaMemcpyAsync(p->lay_col.p, h1.col.data(), n1 * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (n2) CK(cudaMemcpyAsync(p->lay_col.p + n1, h2.col.data(), n2 * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->lay_bucket.p, h1.bucket.data(), nb * sizeof(unsigned short), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->lay_bucket.p + nb, h2.bucket.data(), nb * sizeof(unsigned short), cudaMemcpyHostToDevice, s));
+    // every panel error zero (the default of ff_sim.py:61-62): the focal-position cull stays valid
+    bool zero_err = true;
+    for (int k = 0; k < np1 && zero_err; k++) for (int r = 2; r <= 6; r++) zero_err = zero_err && pan1[(size_t)r * np1 + k] == 0.0;
+    for (int k = 0; k < np2 && zero_err; k++) for (int r = 2; r <= 6; r++) zero_err = zero_err && pan2[(size_t)r * np2 + k] == 0.0;
+    FfMapParams q;
+    q.ang = p->ang.tabs; q.g = p->g; q.azel = p->ctx->stage_in.p; q.grid = p->grid; q.e_rec = p->e_rec.p;
+    q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
+    q.amp = p->ctx->stage_out.p; q.phase = p->ctx->stage_out.p + n; q.status = p->status.p;
+    q.pidx1 = q.pidx2 = nullptr; q.pan1 = p->pan.p; q.pan2 = p->pan.p + 10 * (size_t)np1; q.np1 = np1; q.np2 = np2;
+    q.lay1 = PanelLayoutDev{p->lay_rect.p, p->lay_col.p, p->lay_bucket.p, (int)n1, h1.linear, h1.bx0, h1.by0, h1.inv_bw, h1.inv_bh};
+    q.lay2 = PanelLayoutDev{p->lay_rect.p + n1, p->lay_col.p + n1, p->lay_bucket.p + nb, (int)n2, h2.linear, h2.bx0, h2.by0, h2.inv_bw, h2.inv_bh};
+    if (int rc = ff_map_run(p, q, npix, 2, s, false, zero_err)) return rc;
+    pack_status_kernel<<<1, 1, 0, s>>>(p->status.p, p->ctx->stage_out.p + 2 * n);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(p->ctx->pin.p, p->ctx->stage_out.p, (2 * n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));      // h1, h2 go out of scope
     memcpy(amp, p->ctx->pin.p, n * sizeof(double));
     memcpy(phase, p->ctx->pin.p + n, n * sizeof(double));
     const int st = (int)p->ctx->pin.p[2 * n];

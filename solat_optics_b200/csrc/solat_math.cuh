@@ -284,7 +284,7 @@ struct Asphere {
     double y0;                 // surface vertex at y = -y0 in the telescope frame
 };
 struct AsphereF {              // single-precision copy for the coarse first Newton update
-    float c, K, a1, a2, a3, a4, g1, g2, g3, g4;
+    float c, K, a1, a2, a3, a4, g1, g2, g3, g4, Kinv;
 };
 constexpr Asphere make_asphere(double R, double k, double a1, double a2, double a3, double a4, double y0)
 {
@@ -294,7 +294,7 @@ constexpr Asphere make_asphere(double R, double k, double a1, double a2, double 
 constexpr AsphereF make_asphere_f(double R, double k, double a1, double a2, double a3, double a4)
 {
     return AsphereF{(float)(1.0 / R), (float)((1.0 + k) * (1.0 / R) * (1.0 / R)), (float)a1, (float)a2, (float)a3, (float)a4,
-                    (float)(2.0 * a1), (float)(4.0 * a2), (float)(6.0 * a3), (float)(8.0 * a4)};
+                    (float)(2.0 * a1), (float)(4.0 * a2), (float)(6.0 * a3), (float)(8.0 * a4), (float)(1.0 / ((1.0 + k) * (1.0 / R)))};
 }
 constexpr double LENS1_Y = 975.08;                                             // ot_geo.py:68
 constexpr double LENS2_Y = 592.76;                                             // ot_geo.py:69
@@ -354,9 +354,12 @@ SOLAT_HD typename Pack<R>::I asphere_hit(const Coef& C, const vec3t<R>& P, const
         const F dxf = to_f(d.x), dyf = to_f(d.y), dzf = to_f(d.z);
         const F xf = to_f(fma(d.x, t, P.x)), zf = to_f(fma(d.z, t, P.z));
         const F uf = fmaf(xf, xf, zf * zf);
-        const F rsf = rsqrt_f(fmaf(F(-Af.K), uf, F(1.0f)));
-        const F sagf = div_f(F(Af.c) * uf, F(1.0f) + div_f(F(1.0f), rsf)) +
-                       uf * fmaf(uf, fmaf(uf, fmaf(uf, F(Af.a4), F(Af.a3)), F(Af.a2)), F(Af.a1));
+        const F wf = fmaf(F(-Af.K), uf, F(1.0f));
+        const F rsf = rsqrt_f(wf);
+        // conic term in the division-free form of the FP64 evaluation, (1 - S) / ((1 + k) c) with S = w rsqrt(w): the
+        // cancellation costs ~1e-5 mm in single precision, far below this step's own truncation error
+        const F sagf = fmaf(fmaf(-wf, rsf, F(1.0f)), F(Af.Kinv),
+                            uf * fmaf(uf, fmaf(uf, fmaf(uf, F(Af.a4), F(Af.a3)), F(Af.a2)), F(Af.a1)));
         const F Gf = fmaf(F(Af.c), rsf, fmaf(uf, fmaf(uf, fmaf(uf, F(Af.g4), F(Af.g3)), F(Af.g2)), F(Af.g1)));
         const F fpf = fmaf(-Gf, fmaf(xf, dxf, zf * dzf), dyf);
         t += to_r(div_f(sagf, fpf), t);

@@ -7,6 +7,7 @@ its block, and a single gather (NCCL over NVLink; gloo in the CPU tests) brings 
 rank 0.  Pixels are independent, so there is no other exchange step.
 """
 import ctypes
+import functools
 import os
 
 import numpy as np
@@ -104,15 +105,29 @@ def shard_groups(pixels, world_size, fold_second=False):
     return [order[gid % world_size == r] for r in range(world_size)]
 
 
-def _digest(*arrays):
-    import hashlib
+class _digest:
+    """Cache key over the CONTENTS of arrays: hashes a cheap fingerprint (shapes + 64-bit word sums), compares the full
+    contents (kept as private copies) on a hit -- exact, and ~10x faster than a cryptographic digest of the tables."""
 
-    h = hashlib.blake2b(digest_size=16)
-    for a in arrays:
-        a = np.ascontiguousarray(a)
-        h.update(str((a.shape, a.dtype.str)).encode())
-        h.update(a.view(np.uint8).reshape(-1).data if a.size else b"")
-    return h.digest()
+    __slots__ = ("arrays", "_hash")
+
+    def __init__(self, *arrays):
+        self.arrays = [np.array(a, copy=True, order="C") for a in arrays]
+        fp = []
+        for a in self.arrays:
+            raw = a.reshape(-1).view(np.uint8)
+            n8 = raw.size // 8
+            fp.append((a.shape, a.dtype.str, int(raw[: n8 * 8].view(np.uint64).sum(dtype=np.uint64)) if n8 else 0,
+                       raw[n8 * 8:].tobytes()))
+        self._hash = hash(tuple(fp))
+
+    def __hash__(self):
+        return self._hash
+
+    def __eq__(self, other):
+        return (isinstance(other, _digest) and self._hash == other._hash and len(self.arrays) == len(other.arrays)
+                and all(a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+                        for a, b in zip(self.arrays, other.arrays)))
 
 
 class _PlanCache:
@@ -398,22 +413,34 @@ class NearFieldPlan:
             pass
 
 
-def holo_pixels(res=51, sweep=100, shift=0):
-    """Source-position grid of scripts/holo_sim.py:90-108: row index i*res+j <-> (x_i, z_j)."""
+@functools.lru_cache(maxsize=8)
+def _holo_pixels(res, sweep, shift):
     rx = np.linspace(-sweep / 2 + shift, sweep / 2 + shift, res)
     xx, zz = np.meshgrid(rx, rx, indexing="ij")
     return np.stack([xx.ravel(), zz.ravel()], axis=1)
 
 
+def holo_pixels(res=51, sweep=100, shift=0):
+    """Source-position grid of scripts/holo_sim.py:90-108: row index i*res+j <-> (x_i, z_j)."""
+    return _holo_pixels(int(res), float(sweep), float(shift)).copy()
+
+
+def _with_digest(field):
+    opl, w = field
+    return opl, w, _digest(opl, w)
+
+
 def _cached_receiver_field(tg, p_rx, n_scan_rx, n_scan):
+    """(rx_opl, rx_w, digest of both) -- the digest keys the plan cache without hashing the tables on every call"""
     key = ("rx", _lib.context().device, tg.n_si, tg.n_vac, tg.th_fwhp, tg.y_ap, tuple(float(v) for v in p_rx), n_scan_rx, n_scan)
-    return _rx_fields.get(key, lambda: receiver_field(tg, p_rx, n_scan_rx, n_scan))
+    return _rx_fields.get(key, lambda: _with_digest(receiver_field(tg, p_rx, n_scan_rx, n_scan)))
 
 
-def near_field_plan(tg, k_list, rx_opl, rx_w, n_scan, device=None):
+def near_field_plan(tg, k_list, rx_opl, rx_w, n_scan, device=None, field_digest=None):
     """NearFieldPlan from the plan cache (same geometry, wavenumbers and receiver field -> the same plan)."""
     dev = _lib.context(device).device
-    key = ("nf", dev, tg.n_si, tg.n_vac, tg.th_fwhp, tg.y_ap, int(n_scan), _digest(np.asarray(k_list, dtype=np.float64), rx_opl, rx_w))
+    key = ("nf", dev, tg.n_si, tg.n_vac, tg.th_fwhp, tg.y_ap, int(n_scan), tuple(float(k) for k in np.atleast_1d(k_list)),
+           field_digest or _digest(rx_opl, rx_w))
     return _plans.get(key, lambda: NearFieldPlan(tg, k_list, rx_opl, rx_w, n_scan, device))
 
 
@@ -453,8 +480,8 @@ def holo_map(freqs, res=51, sweep=100, shift=0, n_scan=100, n_scan_rx=None, p_rx
     if _use_ranks(work, world) == 1 and rank != 0:
         return None
     # the feed taper differs per band only; one geometry -> one rx field
-    rx_opl, rx_w = _cached_receiver_field(tg, p_rx, n_scan_rx, n_scan)
-    plan = near_field_plan(tg, [g.k for g in geos], rx_opl, rx_w, n_scan, device)
+    rx_opl, rx_w, dig = _cached_receiver_field(tg, p_rx, n_scan_rx, n_scan)
+    plan = near_field_plan(tg, [g.k for g in geos], rx_opl, rx_w, n_scan, device, dig)
     out = _run_map(plan, pixels, True, work, strict)
     if out is None:
         return None
@@ -469,8 +496,8 @@ def receiver_offset_sweep(freq, rx_positions, res=51, sweep=100, shift=0, n_scan
     tg = holo_tele_geo(float(freq), n_scan)
     pos = _lib.as_f64(np.reshape(rx_positions, (-1, 3)))
     key = ("rxs", _lib.context(device).device, tg.n_si, tg.n_vac, tg.th_fwhp, tg.y_ap, int(n_scan), _digest(pos))
-    rx_opl, rx_w = _rx_fields.get(key, lambda: receiver_fields(tg, pos, n_scan, device))
-    plan = near_field_plan(tg, [tg.k], rx_opl, rx_w, n_scan, device)
+    rx_opl, rx_w, dig = _rx_fields.get(key, lambda: _with_digest(receiver_fields(tg, pos, n_scan, device)))
+    plan = near_field_plan(tg, [tg.k], rx_opl, rx_w, n_scan, device, dig)
     pixels = holo_pixels(res, sweep, shift)
     amp, phase, st = plan.run(pixels)
     _lib.raise_on_status(st, strict)
@@ -506,19 +533,29 @@ def ff_tele_geo(freq, offset):
     return tg
 
 
+@functools.lru_cache(maxsize=8)
+def _ff_fan(n_scan):
+    return np.linspace(np.pi - 0.00005, np.pi + 0.00005, n_scan), np.linspace(0, np.pi, n_scan)
+
+
 def ff_fan(n_scan=100):
     """Polar launch fan of scripts/ff_sim.py:64-66."""
-    return np.linspace(np.pi - 0.00005, np.pi + 0.00005, n_scan), np.linspace(0, np.pi, n_scan)
+    th, ph = _ff_fan(int(n_scan))
+    return th.copy(), ph.copy()
+
+
+@functools.lru_cache(maxsize=8)
+def _ff_pixels(az0, el0, res_arcmin, n):
+    de_ang = res_arcmin / 60 * np.pi / 180
+    azs = np.linspace(-n * de_ang + az0, n * de_ang + az0, 2 * n + 1)
+    els = np.linspace(-n * de_ang + el0, n * de_ang + el0, 2 * n + 1)
+    aa, ee = np.meshgrid(azs, els, indexing="ij")
+    return np.stack([aa.ravel(), ee.ravel()], axis=1)
 
 
 def ff_pixels(tele_geo, res_arcmin, num):
     """(az, el) grid of scripts/ff_sim.py:94,121-128: row index i*len+j <-> (az_i, el_j)."""
-    de_ang = res_arcmin / 60 * np.pi / 180
-    n = int(num)
-    azs = np.linspace(-n * de_ang + tele_geo.az0, n * de_ang + tele_geo.az0, 2 * n + 1)
-    els = np.linspace(-n * de_ang + tele_geo.el0, n * de_ang + tele_geo.el0, 2 * n + 1)
-    aa, ee = np.meshgrid(azs, els, indexing="ij")
-    return np.stack([aa.ravel(), ee.ravel()], axis=1)
+    return _ff_pixels(float(tele_geo.az0), float(tele_geo.el0), float(res_arcmin), int(num)).copy()
 
 
 def near_field_to_e_rec(foc_fields):
@@ -611,13 +648,44 @@ class FarFieldPlan:
             pm1.shape[1], _lib.dptr(pm2), pm2.shape[1], _lib.dptr(amp), _lib.dptr(phase), ctypes.byref(st)))
         return amp, phase, st.value
 
+    def run_panel_layout(self, azel, layout1, layout2, panel_model1, panel_model2):
+        """Fused map with panel models, the panels identified on the device: layout1 / layout2 are the
+        solat_apert_field.PanelLayout of M1 / M2.  Per ray the reference's two passes (ff_sim.py:208-209)."""
+        azel = _lib.as_f64(np.reshape(azel, (-1, 2)))
+        npix = azel.shape[0]
+        amp, phase = np.empty(npix), np.empty(npix)
+        if npix == 0:
+            return amp, phase, 0
+        pm1, pm2 = _lib.as_f64(panel_model1), _lib.as_f64(panel_model2)
+        if pm1.ndim != 2 or pm2.ndim != 2 or pm1.shape[0] != 10 or pm2.shape[0] != 10:
+            raise ValueError("panel models must be (10, n_panels)")
+        keep = []
+
+        def c_layout(lay, pm):
+            rect = _lib.as_f64(lay.rect)
+            col = np.ascontiguousarray(lay.model_columns(pm), dtype=np.int32)
+            keep.extend([rect, col])
+            return _lib.PanelLayoutC(_lib.dptr(rect), col.ctypes.data_as(_lib.c_ip), len(col))
+
+        l1, l2 = c_layout(layout1, pm1), c_layout(layout2, pm2)
+        st = _lib.c_i(0)
+        _lib.check(_lib.load().solat_ff_map_panel_layout_host(
+            self.handle, _lib.dptr(azel), npix, ctypes.byref(l1), ctypes.byref(l2), _lib.dptr(pm1), pm1.shape[1], _lib.dptr(pm2),
+            pm2.shape[1], _lib.dptr(amp), _lib.dptr(phase), ctypes.byref(st)))
+        return amp, phase, st.value
+
     def run_panel_models(self, azel, panel_model1, panel_model2, backend=None, batch=64):
-        """ff_sim.py:204-221 for a list of pixels with the panel models of pan_mod: mirror coordinates on the GPU ->
-        `identify_panel` of the panel backend on the host, pixel by pixel exactly as the reference calls it
-        (saf:587-621) -> fused GPU map.  `batch` pixels share one round trip."""
+        """ff_sim.py:204-221 for a list of pixels with the panel models of pan_mod.  A backend that describes its panels
+        as rectangles (`panel_layouts()`, see solat_apert_field.PanelLayout) is evaluated on the device
+        (run_panel_layout).  Any other backend is opaque: mirror coordinates on the GPU -> its `identify_panel` on the
+        host, pixel by pixel exactly as the reference calls it (saf:587-621) -> fused GPU map; `batch` pixels share one
+        round trip."""
         from . import solat_apert_field as saf
 
         backend = backend or saf.panel_backend()
+        if hasattr(backend, "panel_layouts"):
+            lay1, lay2 = backend.panel_layouts()
+            return self.run_panel_layout(azel, lay1, lay2, panel_model1, panel_model2)
         azel = _lib.as_f64(np.reshape(azel, (-1, 2)))
         adj1, adj2 = backend.get_single_vert_adj_positions()
         n = int(round(np.sqrt(self.n_rays)))

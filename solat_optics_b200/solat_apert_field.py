@@ -49,6 +49,53 @@ class _SinglePanel:
         pm[0, 0] = pm[1, 0] = 1.0
         return pm
 
+    @staticmethod
+    def panel_layouts():
+        big = 1e9
+        one = PanelLayout([-big], [big], [-big], [big], [1.0], [1.0])
+        return one, one
+
+
+class PanelLayout:
+    """Rectangular panel layout of one mirror, the form in which panel identification runs on the GPU.
+
+    Panel k covers [x0[k], x1[k]) x [y0[k], y1[k]) in the coordinates the reference hands to `identify_panel`
+    (saf:596-612: M1 -> (x, y - y_cent_m1), M2 -> (x, z) of the ideal-mirror hit, telescope frame, mm) and carries the ids
+    (row[k], col[k]); a later panel overrides an earlier one; a point in no panel gets ids (0, 0) -- what an
+    `identify_panel` that loops over the panels and writes their ids into zero-initialised arrays returns.
+    A panel backend that can describe itself this way exposes `panel_layouts() -> (layout_m1, layout_m2)`; maps with
+    panel models then never leave the GPU.  The layout of holosim-ml's own pan_mod is not part of the reference:
+    "parity unpinned" (DESIGN.md); `from_adjusters` builds the obvious candidate (one rectangle per adjuster-defined
+    panel centre)."""
+
+    def __init__(self, x0, x1, y0, y1, row, col):
+        self.rect = np.ascontiguousarray(np.stack([np.asarray(v, dtype=np.float64).ravel() for v in (x0, x1, y0, y1)], axis=1))
+        self.row = np.asarray(row, dtype=np.float64).ravel()
+        self.col = np.asarray(col, dtype=np.float64).ravel()
+        if not (len(self.rect) == len(self.row) == len(self.col)):
+            raise ValueError("x0, x1, y0, y1, row, col must have one entry per panel")
+
+    @classmethod
+    def from_adjusters(cls, x_cent, y_cent, col, row, size_x, size_y):
+        """One size_x x size_y rectangle centred on every (x_cent, y_cent) (e.g. the mean adjuster position of a panel)."""
+        x_cent, y_cent = np.asarray(x_cent, dtype=np.float64), np.asarray(y_cent, dtype=np.float64)
+        return cls(x_cent - size_x / 2, x_cent + size_x / 2, y_cent - size_y / 2, y_cent + size_y / 2, row, col)
+
+    def identify_panel(self, x2d, y2d, *_unused):
+        """Host evaluation with the call shape of pan_mod.identify_panel: (2, ...) row ids, col ids."""
+        x2d, y2d = np.asarray(x2d, dtype=np.float64), np.asarray(y2d, dtype=np.float64)
+        out = np.zeros((2,) + x2d.shape)
+        for k in range(len(self.rect)):
+            x0, x1, y0, y1 = self.rect[k]
+            m = (x2d >= x0) & (x2d < x1) & (y2d >= y0) & (y2d < y1)
+            out[0][m] = self.row[k]
+            out[1][m] = self.col[k]
+        return out
+
+    def model_columns(self, panel_model):
+        """Per panel: first column of `panel_model` with the panel's (row, col) ids, -1 if none (saf:626, :805-809)."""
+        return _first_match_index(panel_model, self.row, self.col)
+
 
 def set_panel_backend(module):
     """Register the object providing identify_panel / get_single_vert_adj_positions (e.g. holosim-ml's

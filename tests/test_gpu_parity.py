@@ -995,3 +995,74 @@ def test_nccl_sharded_maps_equal_single_rank_maps():
         np.testing.assert_array_equal(got[0], ref[0])
         np.testing.assert_array_equal(got[1], ref[1])
         np.testing.assert_array_equal(got[2], ref[2])
+
+
+def _synthetic_layouts():
+    """The fixture's synthetic panel layout (gu.panel_identify: ids = floor(coordinate / 1000) + 10) as rectangles."""
+    from solat_optics_b200 import solat_apert_field as saf
+
+    ids = [(r, c) for r in range(0, 20) for c in range(0, 20)]
+    r = np.array([i[0] for i in ids], dtype=float); c = np.array([i[1] for i in ids], dtype=float)
+    lay = saf.PanelLayout((c - 10) * 1000.0, (c - 9) * 1000.0, (r - 10) * 1000.0, (r - 9) * 1000.0, r, c)
+    return lay, lay
+
+
+def test_ff_panel_identification_on_the_device(oracle):
+    """Panels identified on the device from a rectangular layout (solat_ff_map_panel_layout_host) against (a) the
+    reference fixture ff_panels, (b) the host round trip through an opaque identify_panel, bit for bit, (c) overlapping
+    panels (a later panel overrides an earlier one) and a crowded bucket (linear scan), (d) all-zero panel errors with
+    missing panels: the cull stays on and only the dropped rays change the map."""
+    from solat_optics_b200 import maps
+    from solat_optics_b200 import solat_apert_field as saf
+
+    class Opaque:
+        @staticmethod
+        def get_single_vert_adj_positions():
+            z = np.zeros(1)
+            return [z, z, z, z, z], [z, z, z, z, z]
+
+        identify_panel = staticmethod(gu.panel_identify)
+
+    d = gu.load("ff_panels")
+    pan1, pan2 = d["pan1"], d["pan2"]
+    lay1, lay2 = _synthetic_layouts()
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(-3900, 3900, (2, 50, 50))
+    np.testing.assert_array_equal(lay1.identify_panel(pts[0], pts[1]), gu.panel_identify(pts[0], pts[1]))
+    n = int(d["in_n_scan"][0])
+    th, ph = gu.ff_fan(n)
+    x, y, e = gu.ff_grid("wide61")
+    tgf = maps.ff_tele_geo(140, 1.32)
+    azel = np.c_[d["in_az"], d["in_el"]]
+    plan = maps.FarFieldPlan(tgf, th, ph, x, y, e, device=0)
+    a, p, st = plan.run_panel_layout(azel, lay1, lay2, pan1, pan2)
+    assert st == 0
+    _assert_pixels(a, p, d["amp"], d["phi"])                                    # (a) the unmodified reference
+    th, ph = gu.ff_fan(64)
+    plan = maps.FarFieldPlan(tgf, th, ph, x, y, e, device=0)
+    azel = np.array([[0.3 * gu.DE, gu.EL0], [11 * gu.DE, gu.EL0 - 7 * gu.DE], [-20 * gu.DE, gu.EL0 + 20 * gu.DE], [0.0, gu.EL0 + 3 * gu.DE]])
+    a_dev, p_dev, st = plan.run_panel_layout(azel, lay1, lay2, pan1, pan2)
+    a_host, p_host, st2 = plan.run_panel_models(azel, pan1, pan2, backend=Opaque)
+    assert st == 0 and st2 == 0
+    np.testing.assert_array_equal(a_dev, a_host); np.testing.assert_array_equal(p_dev, p_host)   # (b)
+    # (c) a second, shifted set of panels laid over the first with other ids; 12 thin panels crowd one bucket
+    r2 = np.r_[lay1.rect, lay1.rect + [333.0, 333.0, -250.0, -250.0]]
+    over = saf.PanelLayout(r2[:, 0], r2[:, 1], r2[:, 2], r2[:, 3], np.r_[lay1.row, lay1.row[::-1]], np.r_[lay1.col, lay1.col[::-1]])
+    thin = saf.PanelLayout(np.r_[over.rect[:, 0], np.full(12, -100.0)], np.r_[over.rect[:, 1], 100.0 + np.arange(12)],
+                           np.r_[over.rect[:, 2], np.full(12, -100.0)], np.r_[over.rect[:, 3], 100.0 + np.arange(12)],
+                           np.r_[over.row, 8 + np.arange(12) % 3], np.r_[over.col, 9 + np.arange(12) % 4])
+    for lay in (over, thin):
+        class Host(Opaque):
+            identify_panel = staticmethod(lambda xx, yy, *a_, _l=lay: _l.identify_panel(xx, yy))
+
+        a_dev, p_dev, st = plan.run_panel_layout(azel, lay, lay, pan1, pan2)
+        a_host, p_host, st2 = plan.run_panel_models(azel, pan1, pan2, backend=Host)
+        np.testing.assert_array_equal(a_dev, a_host); np.testing.assert_array_equal(p_dev, p_host)
+    # (d) zero errors, some panels missing from the model
+    z1, z2 = pan1.copy(), pan2.copy()
+    z1[2:8] = 0.0; z2[2:8] = 0.0
+    a_dev, p_dev, st = plan.run_panel_layout(azel, lay1, lay2, z1, z2)
+    a_host, p_host, st2 = plan.run_panel_models(azel, z1, z2, backend=Opaque)
+    np.testing.assert_array_equal(a_dev, a_host); np.testing.assert_array_equal(p_dev, p_host)
+    plain, _, _ = plan.run(azel)
+    assert np.all(np.abs(a_dev - plain) > 1e-6 * plain)

@@ -253,3 +253,22 @@ def test_mirror_pair_order_keeps_partners_adjacent():
     change = 1 + np.nonzero((np.diff(key, axis=0) != 0).any(axis=1))[0]
     groups = np.split(np.arange(len(px)), change)
     assert len(groups) == 6 * 6 and max(len(g) for g in groups) == 4
+
+
+def test_panel_layout_host_semantics():
+    """solat_apert_field.PanelLayout: half-open rectangles, later panels override, ids (0, 0) outside, first-match
+    model columns (saf:626, :805-809)."""
+    from solat_optics_b200 import solat_apert_field as saf
+
+    lay = saf.PanelLayout([0, 5, -10], [10, 15, -5], [0, 5, -10], [10, 15, -5], [1, 2, 3], [4, 5, 6])
+    xs = np.array([[0.0, 9.999, 10.0], [7.0, 12.0, -7.0]]); ys = np.array([[0.0, 9.999, 10.0], [7.0, 12.0, -7.0]])
+    ids = lay.identify_panel(xs, ys)
+    np.testing.assert_array_equal(ids[0], [[1, 2, 2], [2, 2, 3]])
+    np.testing.assert_array_equal(ids[1], [[4, 5, 5], [5, 5, 6]])
+    assert (lay.identify_panel(np.array([20.0]), np.array([20.0])) == 0).all()
+    pm = np.zeros((10, 4)); pm[0] = [9, 2, 2, 1]; pm[1] = [9, 5, 5, 4]
+    np.testing.assert_array_equal(lay.model_columns(pm), [3, 1, -1])
+    adj = saf.PanelLayout.from_adjusters([0.0, 100.0], [0.0, 0.0], [1, 2], [7, 7], 90.0, 50.0)
+    np.testing.assert_allclose(adj.rect, [[-45, 45, -25, 25], [55, 145, -25, 25]])
+    one, two = saf.panel_backend().panel_layouts()
+    assert (one.identify_panel(np.array([[123.0]]), np.array([[-4e3]])) == 1).all()
