@@ -926,6 +926,7 @@ struct FfMapParams {
     const double2* e_rec;    // (M, M)
     double k;
     double key_base, key_unit, key_inv_unit;   // fixed-point frame of the winner keys
+    int key_shift;           // bits of the path-length field below the ray index (44, or 40 for fans above 2^20 - 1 rays)
     double* amp;
     double* phase;
     int* status;
@@ -941,6 +942,7 @@ struct FfMapParams {
     const double *pan1, *pan2;   // (10, np) row-major [row, col, a, b, c, d, e, f, x0, y0]  (saf:667-674)
     int np1, np2;
     PanelLayoutDev lay1, lay2;
+    unsigned long long* win_g;   // winner tables in global memory, [CTAs of the launch][tables][M * M]; nullptr: shared memory
 };
 
 __device__ __forceinline__ PanelErr load_panel(const double* pan, int np, int col)
@@ -1145,9 +1147,12 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cells = q.grid.M * q.grid.M;
     FfFrames* fr = reinterpret_cast<FfFrames*>(smem_raw);
-    unsigned long long* win = reinterpret_cast<unsigned long long*>(smem_raw + ((sizeof(FfFrames) + 15) / 16) * 16);
+    // winner table(s): in shared memory, or -- E_rec grids too large for that (M > 168) -- this CTA's slice of a
+    // global scratch buffer (L2 resident: 64-bit atomicMax on global memory, slower but unbounded)
+    unsigned long long* win_s = reinterpret_cast<unsigned long long*>(smem_raw + ((sizeof(FfFrames) + 15) / 16) * 16);
+    unsigned long long* win = q.win_g ? q.win_g + (size_t)blockIdx.x * (q.items ? 2 : 1) * cells : win_s;
     unsigned long long* win_m = win + cells;                    // pair mode: winner table of the mirror pixel (-az, el)
-    int* queues = reinterpret_cast<int*>(win + (q.items ? 2 : 1) * cells);   // [FF_WARPS][FF_WQ]
+    int* queues = reinterpret_cast<int*>(win_s + (q.win_g ? 0 : (q.items ? 2 : 1) * cells));   // [FF_WARPS][FF_WQ]
     double* s_gx = reinterpret_cast<double*>(queues + FF_WARPS * FF_WQ);   // [M] data_x[0, :]
     double* s_gy = s_gx + q.grid.M;                                        // [M] data_y[:, 0] when all columns agree
     const int nvr = FF_ROW_K * q.ang.nph;                                  // virtual rows: FF_ROW_K intervals per phi row
@@ -1222,20 +1227,20 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             int cell = -1, cell_m = -1, rm = 0;
             if (out_pos >= 0) {
                 cell = ff_cell(fx - cx, fz - cz, grid);
-                if (cell >= 0 && (win[cell] >> FF_KEY_SHIFT) >= (unsigned long long)(r0 + 1)) cell = -1;
+                if (cell >= 0 && (win[cell] >> q.key_shift) >= (unsigned long long)(r0 + 1)) cell = -1;
             }
             if (out_neg >= 0) {
                 // the mirror pixel (-az, el): this ray is its ray (nph-1-j, i), lands at (-x, z) about its own centre
                 rm = (q.ang.nph - 1 - j) * nth + i;
                 cell_m = ff_cell(cx - fx, fz - fr->centre_mz, grid);
-                if (cell_m >= 0 && (win_m[cell_m] >> FF_KEY_SHIFT) >= (unsigned long long)(rm + 1)) cell_m = -1;
+                if (cell_m >= 0 && (win_m[cell_m] >> q.key_shift) >= (unsigned long long)(rm + 1)) cell_m = -1;
             }
             if (cell >= 0 || cell_m >= 0) {
                 bool exact;
-                const unsigned long long low = ff_key(-1, opl, q.key_base, q.key_inv_unit, exact, q.key_unit);   // ray bits 0
+                const unsigned long long low = ff_key(-1, opl, q.key_base, q.key_inv_unit, exact, q.key_unit, q.key_shift);   // ray bits 0
                 if (!exact) st |= ST_RANGE;
-                if (cell >= 0) atomicMax(win + cell, low | ((unsigned long long)(r0 + 1) << FF_KEY_SHIFT));     // ffl:28: last write wins
-                if (cell_m >= 0) atomicMax(win_m + cell_m, low | ((unsigned long long)(rm + 1) << FF_KEY_SHIFT));
+                if (cell >= 0) atomicMax(win + cell, low | ((unsigned long long)(r0 + 1) << q.key_shift));     // ffl:28: last write wins
+                if (cell_m >= 0) atomicMax(win_m + cell_m, low | ((unsigned long long)(rm + 1) << q.key_shift));
             }
         }
     };
@@ -1349,7 +1354,8 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             const bool more = c0 < cells;
             if (more) {
                 const int c = c0 + lane;
-                const bool has = c < cells && tab[c] != 0ull;
+                // (a table in global memory was updated with atomics at L2: read it there, not through a stale L1 line)
+                const bool has = c < cells && (q.win_g ? __ldcg(tab + c) : tab[c]) != 0ull;
                 const unsigned m = __ballot_sync(0xffffffffu, has);
                 if (has) wq[cnt + __popc(m & ((1u << lane) - 1u))] = c;
                 cnt += __popc(m);
@@ -1362,7 +1368,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
                 __syncwarp();
                 if (c >= 0) {
                     double cs, sn;
-                    cis_large(q.k * ff_key_opl(tab[c], q.key_base, q.key_unit) / 1e3, cs, sn);
+                    cis_large(q.k * ff_key_opl(q.win_g ? __ldcg(tab + c) : tab[c], q.key_base, q.key_unit, q.key_shift) / 1e3, cs, sn);
                     const double2 e = __ldg(q.e_rec + c);
                     re[0] += cs * e.x - sn * e.y;
                     im[0] += cs * e.y + sn * e.x;
@@ -2160,7 +2166,10 @@ struct solat_ff_plan {
     int pairs;                              // geometry, fan and shared memory allow the mirror-pair walk
     FfGrid grid;
     double k, key_base, key_unit;
+    int key_shift;
     int M, n_rays, rows, shape, prefilter;
+    int win_global;                         // the winner tables do not fit in shared memory: global scratch
+    DevBuf<unsigned long long> win_g;
     size_t smem;
 };
 
@@ -2206,7 +2215,14 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
     const size_t stride = ff_rec_stride(rows ? p->ang.tabs.nph : 0);
     // records of up to 1.5 GB per call (HBM holds 180 GB): every chunk boundary drains the GPU (tail of a wave of CTAs
     // that each run for milliseconds on a 10^6-ray fan), so a 401 x 401 map goes through in 2 chunks instead of 14
-    const int chunk = (int)std::min<size_t>((size_t)npix, std::max<size_t>(2048, ((size_t)1536 << 20) / stride));
+    int chunk = (int)std::min<size_t>((size_t)npix, std::max<size_t>(2048, ((size_t)1536 << 20) / stride));
+    q.win_g = nullptr;
+    if (p->win_global) {
+        const size_t per_cta = (size_t)(pairs ? 2 : 1) * p->M * p->M;
+        chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)chunk, ((size_t)1 << 27) / per_cta));   // <= 1 GiB of tables
+        if (int rc = p->win_g.reserve((size_t)chunk * per_cta)) return rc;
+        q.win_g = p->win_g.p;
+    }
     if (int rc = p->rec.reserve((size_t)chunk * stride)) return rc;
     FfPrepParams pq;
     pq.ang = p->ang.tabs; pq.g = p->g; pq.rows = rows; pq.prefilter = (rows && cull) ? p->prefilter : 0;
@@ -2276,7 +2292,7 @@ static int ff_map_launch(solat_ff_plan* p, const double* d_azel, int npix, doubl
     CK(cudaSetDevice(p->ctx->device));
     FfMapParams q;
     q.ang = p->ang.tabs; q.g = p->g; q.azel = d_azel; q.grid = p->grid; q.e_rec = p->e_rec.p;
-    q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
+    q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit; q.key_shift = p->key_shift;
     q.amp = d_amp; q.phase = d_phase; q.status = own_status ? own_status : p->status.p;
     q.pidx1 = q.pidx2 = nullptr; q.pan1 = q.pan2 = nullptr; q.np1 = q.np2 = 0;
     memset(&q.lay1, 0, sizeof(q.lay1)); memset(&q.lay2, 0, sizeof(q.lay2));
@@ -2315,14 +2331,28 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
             if (warps > best_warps) { best_warps = warps; shape = k; smem = need - 4608; }
         }
     }
-    if (shape < 0) return fail(SOLAT_ERR_ARG, "E_rec grid too large for the shared-memory winner table (M <= 168)");
+    int win_global = 0;
+    if (const char* env = getenv("SOLAT_FF_WIN_GLOBAL")) if (env[0] == '1') shape = -1;   // tests: force the global tables
+    if (shape < 0) {
+        // the winner table does not fit in shared memory (M > 168): keep it in global memory (L2), smallest CTA shape
+        win_global = 1;
+        rows = ff_rows_usable(theta, nth, nph) ? 1 : 0;
+        pairs = rows && g->src_mm[0] == 0.0 && g->rotc_mm[0] == 0.0;
+        for (int j = 0; j < nph && pairs; j++)
+            if (!(fabs(phi[j] + phi[nph - 1 - j] - M_PI) <= 1e-12)) pairs = 0;
+        if (const char* env = getenv("SOLAT_FF_PAIRS")) if (env[0] == '0') pairs = 0;
+        shape = 0;
+        smem = ff_map_smem(M, rows ? nph : 0, FF_SHAPES[0][0], 0);
+        if (smem + 4608 > cta_max) { rows = 0; pairs = 0; smem = ff_map_smem(M, 0, FF_SHAPES[0][0], 0); }
+        if (smem + 4608 > cta_max) return fail(SOLAT_ERR_ARG, "E_rec grid axes too large for shared memory");
+    }
     if (const char* pad = getenv("SOLAT_FF_SMEM_PAD")) smem += (size_t)atol(pad);   // occupancy experiments only
-    if ((long long)nth * nph > FF_MAX_RAYS)
-        return fail(SOLAT_ERR_ARG, "launch fan too large for the 20-bit ray index of the winner key (<= 1048575 rays)");
+    if ((long long)nth * nph > FF_MAX_RAYS_WIDE)
+        return fail(SOLAT_ERR_ARG, "launch fan too large for the 24-bit ray index of the winner key (<= 16777215 rays)");
     if (int rc = ff_map_set_smem(c->device, shape, smem)) return rc;
     CK(cudaFuncSetAttribute(ff_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_pair_smem(FF_PAIR_ONE_CTA)));
     solat_ff_plan* p = new solat_ff_plan();
-    p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem; p->n_rays = nth * nph; p->rows = rows; p->shape = shape; p->pairs = pairs;
+    p->ctx = c; p->g = *g; p->M = M; p->k = k; p->smem = smem; p->n_rays = nth * nph; p->rows = rows; p->shape = shape; p->pairs = pairs; p->win_global = win_global;
     {
         const char* env = getenv("SOLAT_FF_PREFILTER");   // "0": trace every accepted ray (experiments, strict status)
         p->prefilter = !(env && env[0] == '0');
@@ -2333,6 +2363,7 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
         const double dx = g->src_mm[0] - g->rotc_mm[0], dy = g->src_mm[1] - g->rotc_mm[1], dz = g->src_mm[2] - g->rotc_mm[2];
         p->key_base = rint(sqrt(dx * dx + dy * dy + dz * dz) + 2.2e4);
         p->key_unit = ldexp(1.0, ilogb(p->key_base) - 53);
+        p->key_shift = (long long)nth * nph > FF_MAX_RAYS ? FF_KEY_SHIFT_WIDE : FF_KEY_SHIFT;
     }
     cudaStream_t s = c->stream;
     int rc = p->ang.init(theta, nth, phi, nph, s);
@@ -2406,9 +2437,12 @@ int solat_ff_map_mirror_xy_host(solat_ff_plan* p, const double* azel, int npix, 
     const size_t n = (size_t)npix * 4 * p->n_rays;
     if (int rc = p->ctx->stage_in.upload(azel, 2 * (size_t)npix, s)) return rc;
     if (int rc = p->xy.reserve(n)) return rc;
-    if (npix > 65535) return fail(SOLAT_ERR_ARG, "at most 65535 pixels per call");
-    ff_mirror_xy_kernel<<<dim3((p->n_rays + 127) / 128, npix), 128, 0, s>>>(p->ang.tabs, p->g, p->ctx->stage_in.p, p->xy.p, p->status.p);
-    LAUNCHED();
+    for (int p0 = 0; p0 < npix; p0 += 65535) {               // gridDim.y is limited to 65535
+        const int np_ = std::min(65535, npix - p0);
+        ff_mirror_xy_kernel<<<dim3((p->n_rays + 127) / 128, np_), 128, 0, s>>>(p->ang.tabs, p->g, p->ctx->stage_in.p + 2 * (size_t)p0,
+                                                                              p->xy.p + (size_t)p0 * 4 * p->n_rays, p->status.p);
+        LAUNCHED();
+    }
     CK(cudaMemcpyAsync(xy, p->xy.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     int st = 0;
     CK(cudaMemcpyAsync(&st, p->status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -2439,7 +2473,7 @@ int solat_ff_map_panels_host(solat_ff_plan* p, const double* azel, int npix, con
     CK(cudaMemcpyAsync(p->pan.p + 10 * (size_t)np1, pan2, 10 * (size_t)np2 * sizeof(double), cudaMemcpyHostToDevice, s));
     FfMapParams q;
     q.ang = p->ang.tabs; q.g = p->g; q.azel = p->ctx->stage_in.p; q.grid = p->grid; q.e_rec = p->e_rec.p;
-    q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
+    q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit; q.key_shift = p->key_shift;
     q.amp = p->ctx->stage_out.p; q.phase = p->ctx->stage_out.p + n; q.status = p->status.p;
     q.pidx1 = p->pidx.p; q.pidx2 = p->pidx.p + nr; q.pan1 = p->pan.p; q.pan2 = p->pan.p + 10 * (size_t)np1; q.np1 = np1; q.np2 = np2;
     memset(&q.lay1, 0, sizeof(q.lay1)); memset(&q.lay2, 0, sizeof(q.lay2));
@@ -2537,7 +2571,7 @@ int solat_ff_map_panel_layout_host(solat_ff_plan* p, const double* azel, int npi
     for (int k = 0; k < np2 && zero_err; k++) for (int r = 2; r <= 6; r++) zero_err = zero_err && pan2[(size_t)r * np2 + k] == 0.0;
     FfMapParams q;
     q.ang = p->ang.tabs; q.g = p->g; q.azel = p->ctx->stage_in.p; q.grid = p->grid; q.e_rec = p->e_rec.p;
-    q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit;
+    q.k = p->k; q.key_base = p->key_base; q.key_unit = p->key_unit; q.key_inv_unit = 1.0 / p->key_unit; q.key_shift = p->key_shift;
     q.amp = p->ctx->stage_out.p; q.phase = p->ctx->stage_out.p + n; q.status = p->status.p;
     q.pidx1 = q.pidx2 = nullptr; q.pan1 = p->pan.p; q.pan2 = p->pan.p + 10 * (size_t)np1; q.np1 = np1; q.np2 = np2;
     q.lay1 = PanelLayoutDev{p->lay_rect.p, p->lay_col.p, p->lay_bucket.p, (int)n1, h1.linear, h1.bx0, h1.by0, h1.inv_bw, h1.inv_bh};

@@ -1146,21 +1146,25 @@ SOLAT_HD int ff_cell(double fx_mm, double fz_mm, const FfGrid& G)
     return iy * G.M + ix;
 }
 
-// Last-write-wins table entry (ffl:28: a later ray overwrites an earlier one): the ray index in the top 20 bits
+// Last-write-wins table entry (ffl:28: a later ray overwrites an earlier one): the ray index in the top bits
 // so that a 64-bit atomicMax keeps the highest index, and the ray's path length below it as an exact
-// fixed-point offset from a per-pixel base (unit = half an ulp of the base, 44 bits = +-65 m at 1e8 mm).
+// fixed-point offset from a per-plan base (unit = half an ulp of the base).  `shift` = bits of the offset: 44 for
+// fans up to 2^20 - 1 rays (+-65 m at 1e8 mm), 40 for fans up to 2^24 - 1 rays (+-4 m); a path length outside the
+// range is reported (ST_RANGE), never silently wrapped.
 constexpr int FF_KEY_SHIFT = 44;
+constexpr int FF_KEY_SHIFT_WIDE = 40;
 constexpr int FF_MAX_RAYS = (1 << 20) - 1;
-SOLAT_HD unsigned long long ff_key(int ray, double opl, double base, double inv_unit, bool& exact, double unit)
+constexpr int FF_MAX_RAYS_WIDE = (1 << 24) - 1;
+SOLAT_HD unsigned long long ff_key(int ray, double opl, double base, double inv_unit, bool& exact, double unit, int shift = FF_KEY_SHIFT)
 {
     const double q = (opl - base) * inv_unit;
-    const long long qi = (long long)rint(q);
-    exact = (base + (double)qi * unit == opl) && (qi > -(1ll << 43)) && (qi < (1ll << 43));
-    return ((unsigned long long)(ray + 1) << FF_KEY_SHIFT) | (unsigned long long)(qi + (1ll << 43));
+    const long long qi = (long long)rint(q), half = 1ll << (shift - 1);
+    exact = (base + (double)qi * unit == opl) && (qi > -half) && (qi < half);
+    return ((unsigned long long)(ray + 1) << shift) | (unsigned long long)(qi + half);
 }
-SOLAT_HD double ff_key_opl(unsigned long long key, double base, double unit)
+SOLAT_HD double ff_key_opl(unsigned long long key, double base, double unit, int shift = FF_KEY_SHIFT)
 {
-    const long long qi = (long long)(key & ((1ull << FF_KEY_SHIFT) - 1)) - (1ll << 43);
+    const long long qi = (long long)(key & ((1ull << shift) - 1)) - (1ll << (shift - 1));
     return base + (double)qi * unit;
 }
 

@@ -1066,3 +1066,47 @@ def test_ff_panel_identification_on_the_device(oracle):
     np.testing.assert_array_equal(a_dev, a_host); np.testing.assert_array_equal(p_dev, p_host)
     plain, _, _ = plan.run(azel)
     assert np.all(np.abs(a_dev - plain) > 1e-6 * plain)
+
+
+def test_ff_beyond_the_former_limits(oracle):
+    """E_rec grids above 168 x 168 (winner tables in global memory instead of shared memory) and fans above
+    1 048 575 rays (24-bit ray index in the winner key) used to be errors: both against the oracle, and a grid that
+    fits shared memory computed both ways (SOLAT_FF_WIN_GLOBAL=1 forces the global tables)."""
+    from solat_optics_b200 import maps
+
+    tg = maps.ff_tele_geo(140, 1.32)
+    geo = oracle.ff_geo_vec(rx_y_m=-1.32)
+    azel = np.array([[0.0, gu.EL0], [7 * gu.DE, gu.EL0 - 3 * gu.DE], [-7 * gu.DE, gu.EL0 - 3 * gu.DE], [-12 * gu.DE, gu.EL0 + 9 * gu.DE]])
+    ax = np.linspace(-30, 30, 201)
+    y, x = np.meshgrid(ax, ax, indexing="ij")
+    e = np.exp(-(x ** 2 + y ** 2) / 162.0) * np.exp(1j * 0.009 * (x ** 2 + y ** 2))
+    th, ph = gu.ff_fan(80)
+    a, p, st = maps.FarFieldPlan(tg, th, ph, x, y, e, device=0).run(azel)
+    assert st == 0
+    oa, op = oracle.ff_map(geo, azel, th, ph, x, y, e, tg.k)
+    _assert_pixels(a, p, oa, op)
+    # the same map with the tables in shared memory and in global memory
+    x6, y6, e6 = gu.ff_grid("wide61")
+    a_s, p_s, _ = maps.FarFieldPlan(tg, th, ph, x6, y6, e6, device=0).run(azel)
+    os.environ["SOLAT_FF_WIN_GLOBAL"] = "1"
+    try:
+        a_g, p_g, st = maps.FarFieldPlan(tg, th, ph, x6, y6, e6, device=0).run(azel)
+    finally:
+        del os.environ["SOLAT_FF_WIN_GLOBAL"]
+    assert st == 0
+    np.testing.assert_allclose(a_g, a_s, rtol=1e-13)       # (another CTA shape: the winners are summed in another order)
+    assert np.abs(gu.wrap(p_g - p_s)).max() < 1e-12
+    # 1100 x 1100 = 1.21e6 rays per pixel
+    th, ph = gu.ff_fan(1100)
+    x5, y5, e5 = gu.ff_grid("nf51")
+    a, p, st = maps.FarFieldPlan(tg, th, ph, x5, y5, e5, device=0).run(azel[:3])
+    assert st == 0
+    oa, op = oracle.ff_map(geo, azel[:3], th, ph, x5, y5, e5, tg.k)
+    _assert_pixels(a, p, oa, op)
+    # more than 65535 pixels through the mirror-coordinate entry (host identify_panel path)
+    th, ph = gu.ff_fan(4)
+    plan = maps.FarFieldPlan(tg, th, ph, x6, y6, e6, device=0)
+    many = np.c_[np.linspace(-20, 20, 70001) * gu.DE, np.full(70001, gu.EL0)]
+    xy, st = plan.mirror_xy(many)
+    one, _ = plan.mirror_xy(many[69990:69991])
+    np.testing.assert_array_equal(xy[69990], one[0])
