@@ -757,6 +757,120 @@ __global__ void __launch_bounds__(256, 2) nf_contract_kernel(NfContractParams q)
     }
 }
 
+// The same contraction on the FP64 tensor path (DMMA, mma.sync.m8n8k4.f64: one warp instruction = 8 x 8 x 4 FMAs and holds
+// the FP64 pipe for 16 cycles -- measured 37.0 TFLOP/s on B200, the DFMA issue peak -- so one issue slot feeds the pipe
+// for as long as 8 DFMA instructions would, and the loads ride in its shadow).  The complex product is a real one of
+// twice the depth: with E and the phasors viewed as arrays of doubles (re, im interleaved along the ray index),
+//   Re out[i][c] = sum_k' E'[i][k'] * Bre[c][k'],  Bre[c][2k] = P.re, Bre[c][2k+1] = -P.im
+//   Im out[i][c] = sum_k' E'[i][k'] * Bim[c][k'],  Bim[c][2k] = P.im, Bim[c][2k+1] =  P.re
+// and in the m8n8k4 fragment layout the 8 columns of a tile are (re, im) of 4 complex columns: lane l holds
+// A'[row l/4][k' l%4], B[column (l/4)/2, part (l/4)%2][k' l%4] and the accumulators (re, im) of (row l/4, column l%4): a
+// B operand is one double of the phasor element, offset part ^ (l & 1), negated for (part 0, odd k').
+// CTA: 64 items x up to 112 complex columns x one ray split; 8 warps as 2 (rows) x 4 (columns), 4 x up to 7 MMA tiles per
+// warp; 16 rays (32 doubles) per stage, two stages filled with cp.async (zero fill past the edges).
+constexpr int DM_ROWS = 64, DM_COLS = 112, DM_KS = 16, DM_LD = 2 * DM_KS + 4;   // row pitch in doubles: conflict-free fragment loads
+constexpr size_t DM_STAGE = (size_t)(DM_ROWS + DM_COLS) * DM_LD;                 // doubles per stage
+static size_t nf_dmma_smem() { return 2 * DM_STAGE * sizeof(double); }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool on)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = on ? 16 : 0;                         // src-size 0: the 16 bytes are zero filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes));
+}
+#ifndef SOLAT_DMMA_MINB
+#define SOLAT_DMMA_MINB 2
+#endif
+__global__ void __launch_bounds__(256, SOLAT_DMMA_MINB) nf_contract_dmma_kernel(NfContractParams q)
+{
+    extern __shared__ __align__(16) double dm_smem[];
+    const int count = min(__ldg(q.counters2) - q.row0, q.rows);       // rows of E that hold an item
+    const int r0 = blockIdx.x * DM_ROWS;
+    if (r0 >= count) return;
+    const int N = 4 * q.nrx, c0 = blockIdx.y * DM_COLS, ncols = min(DM_COLS, N - c0), split = blockIdx.z;
+    const int k_begin = split * q.k_len, k_end = min(k_begin + q.k_len, q.n_act);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
+    const int tiles = (ncols + 3) >> 2;                                // 8-wide MMA tiles = 4 complex columns each
+    const int t_lo = (wn * tiles) >> 2, t_hi = ((wn + 1) * tiles) >> 2; // this warp's tiles (<= 7)
+    const int nsteps = (k_end - k_begin + DM_KS - 1) / DM_KS;
+
+    auto fill = [&](int stage, int step) {
+        double* As = dm_smem + stage * DM_STAGE;
+        double* Bs = As + DM_ROWS * DM_LD;
+        const int k0 = k_begin + step * DM_KS;
+        for (int e = tid; e < DM_ROWS * DM_KS; e += 256) {             // E rows: 16 double2 per row
+            const int r = e / DM_KS, k = e - r * DM_KS;
+            const bool on = r0 + r < count && k0 + k < k_end;
+            cp_async16(As + r * DM_LD + 2 * k, q.E + (size_t)(on ? r0 + r : 0) * q.ldE + (on ? k0 + k : 0), on);
+        }
+        for (int e = tid; e < DM_COLS * DM_KS; e += 256) {             // phasor rows m * nrx + j
+            const int c = e / DM_KS, k = e - c * DM_KS;
+            const bool on = c < ncols && k0 + k < k_end;
+            cp_async16(Bs + c * DM_LD + 2 * k, q.phasor + ((size_t)(on ? c0 + c : 0) * q.nfreq + q.f) * q.n_act + (on ? k0 + k : 0), on);
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+
+    double acc[4][7][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 7; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int part = (lane >> 2) & 1, kq = lane & 3;
+    const int b_off = (kq & ~1) | ((kq & 1) ^ part);                   // which double of the phasor pair
+    const double b_sign = (part == 0 && (kq & 1)) ? -1.0 : 1.0;
+    const int a_base = (wm * 32 + (lane >> 2)) * DM_LD + kq;           // + i * 8 * DM_LD + 4 * kk
+    const int b_base = (lane >> 3) * DM_LD + b_off;                    // + tile * 4 * DM_LD + 4 * kk
+
+    if (nsteps > 0) fill(0, 0);
+    for (int step = 0; step < nsteps; step++) {
+        if (step + 1 < nsteps) {
+            fill((step + 1) & 1, step + 1);
+            asm volatile("cp.async.wait_group 1;");
+        } else {
+            asm volatile("cp.async.wait_group 0;");
+        }
+        __syncthreads();
+        const double* As = dm_smem + (step & 1) * DM_STAGE;
+        const double* Bs = As + DM_ROWS * DM_LD;
+#pragma unroll
+        for (int kk = 0; kk < DM_KS / 2; kk++) {                       // 4 doubles = 2 rays per MMA
+            double a[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[a_base + i * 8 * DM_LD + 4 * kk];
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                if (t_lo + j >= t_hi) break;                           // warp-uniform
+                const double b = b_sign * Bs[b_base + (t_lo + j) * 4 * DM_LD + 4 * kk];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(a[i]), "d"(b));
+            }
+        }
+        __syncthreads();                                               // the stage is refilled two steps on
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = r0 + wm * 32 + i * 8 + (lane >> 2);
+        if (r >= count) continue;
+        const FfItem it = q.items2[q.row0 + r];
+        int o0 = -1, o1 = -1, o2 = -1, o3 = -1;
+        if (it.pos >= 0) { o0 = q.items[it.pos].pos; o1 = q.items[it.pos].neg; }
+        if (it.neg >= 0) { o2 = q.items[it.neg].pos; o3 = q.items[it.neg].neg; }
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            if (t_lo + j >= t_hi) break;
+            const int c = c0 + (t_lo + j) * 4 + (lane & 3);
+            if (c >= N) continue;
+            const int m = c / q.nrx, t = c - m * q.nrx;
+            const int pixel = m == 0 ? o0 : (m == 1 ? o1 : (m == 2 ? o2 : o3));
+            if (pixel >= 0)
+                q.partial[((size_t)(q.pix0 + pixel) * q.splits + split) * q.nch_total + (size_t)t * q.nfreq + q.f] =
+                    make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+    }
+}
+
 // Fixed-order sum of the tile partials -> amp, phase (holo_sim.py:181-182).  (Folding this into nf_map_kernel -- the CTA
 // that stores an item's last tile adds them up -- measured the same time: profiles/r01_variants.md.)
 __global__ void nf_finalize_kernel(const double2* partial, int npix, int tiles, int nfreq, double* amp, double* phase)
@@ -1768,7 +1882,9 @@ static void nf_launch_one(const NfMapParams& q, int grid, int threads, cudaStrea
 static int nf_map_contract(solat_nf_plan* p, const double* d_src, int npix, double* d_amp, double* d_phase, cudaStream_t s)
 {
     const int nfreq = (int)p->kk.size(), nch = nfreq * p->nrx;
-    const int k_len = ((std::max(256, (p->n_act + 31) / 32) + NF_GK - 1) / NF_GK) * NF_GK;
+    int k_min = 256;
+    if (const char* e = getenv("SOLAT_NF_KLEN")) k_min = std::max(16, atoi(e));   // experiments
+    const int k_len = ((std::max(k_min, (p->n_act + 31) / 32) + 15) / 16) * 16;
     const int splits = (p->n_act + k_len - 1) / k_len;
     const int piece = std::min(npix, FF_PAIR_ONE_CTA);
     // rows of E per pass: 256 MB at most
@@ -1785,6 +1901,20 @@ static int nf_map_contract(solat_nf_plan* p, const double* d_src, int npix, doub
     q.n_act = p->n_act; q.tiles = p->tiles; q.tile_len = p->tile_len; q.nfreq_total = nfreq; q.nch_total = nch;
     q.partial = p->partial.p; q.status = p->status.p; q.sym = p->sym; q.f0 = q.j0 = 0;
     q.items = p->items.p; q.items2 = p->items.p + piece; q.counters = p->pair_ints.p; q.counters2 = p->pair_ints.p + 2;
+    // register-tiled SIMT contraction (default) or the FP64 tensor-core one (SOLAT_NF_DMMA=1).  Measured on B200, 25 tables
+    // x 51 x 51 px (profiles/r02_variants.md): the two tie (0.378 vs 0.380 ms per map) -- a DMMA holds the same FP64 pipe for
+    // as long as the 8 DFMAs it replaces (37.0 TFLOP/s either way), and both kernels are bound by the tail of their
+    // (row block x ray split) grid, which is fixed by the ray count for the sake of list-independent bits.
+    const bool dmma = getenv("SOLAT_NF_DMMA") && getenv("SOLAT_NF_DMMA")[0] == '1';
+    if (dmma) {
+        static std::mutex mu;
+        static bool set[64] = {};
+        std::lock_guard<std::mutex> lock(mu);
+        if (!set[p->ctx->device & 63]) {
+            CK(cudaFuncSetAttribute(nf_contract_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nf_dmma_smem()));
+            set[p->ctx->device & 63] = true;
+        }
+    }
     NfContractParams g;
     g.E = p->phase_e.p; g.phasor = p->phasor.p; g.items = q.items; g.items2 = q.items2; g.counters2 = q.counters2;
     g.ldE = ldE; g.n_act = p->n_act; g.nrx = p->nrx; g.nfreq = nfreq; g.nch_total = nch; g.splits = splits; g.k_len = k_len;
@@ -1805,8 +1935,13 @@ static int nf_map_contract(solat_nf_plan* p, const double* d_src, int npix, doub
                 nf_phase_kernel<<<rows * p->tiles, p->threads, 0, s>>>(q, row0, rows, p->phase_e.p, ldE);
                 LAUNCHED();
                 g.f = f;
-                const dim3 grid((rows + NF_GM - 1) / NF_GM, (4 * p->nrx + NF_GN - 1) / NF_GN, splits);
-                nf_contract_kernel<<<grid, 256, 0, s>>>(g);
+                if (dmma) {
+                    const dim3 grid((rows + DM_ROWS - 1) / DM_ROWS, (4 * p->nrx + DM_COLS - 1) / DM_COLS, splits);
+                    nf_contract_dmma_kernel<<<grid, 256, nf_dmma_smem(), s>>>(g);
+                } else {
+                    const dim3 grid((rows + NF_GM - 1) / NF_GM, (4 * p->nrx + NF_GN - 1) / NF_GN, splits);
+                    nf_contract_kernel<<<grid, 256, 0, s>>>(g);
+                }
                 LAUNCHED();
             }
         }
