@@ -1119,7 +1119,8 @@ __global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
     int* row_pre = row_lo + (q.rows ? nvr : 0);                            // [nvr + 1] rays before the interval
     __shared__ int s_queue_walk;
     __shared__ FfPred s_pred;
-    __shared__ double s_psum[2][12];
+    __shared__ double s_samp[FF_PRED_SAMPLES * FF_PRED_LD];   // sample rays: basis values, X, Z
+    __shared__ double s_A[FF_PRED_NB * FF_PRED_LD], s_diag[FF_PRED_NB];
     __shared__ float s_pres[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
@@ -1154,7 +1155,7 @@ __global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
             float su = 0.0f, sv = 0.0f;
             double sX = 0.0, sZ = 0.0;
             if (tid < FF_PRED_SAMPLES) {
-                const int v = (int)((long long)tid * (n_list - 1) / (FF_PRED_SAMPLES - 1));
+                const int v = ff_pred_sample_pos(tid, n_list);
                 int a = 0, b = nvr - 1;                    // last interval with row_pre[.] <= v
                 while (a < b) {
                     const int m = (a + b + 1) >> 1;
@@ -1171,20 +1172,27 @@ __global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
                 const float sf = __ldg(q.ang.stf + i) * FF_PRED_SCALE;
                 su = sf * __ldg(q.ang.cpf + a); sv = sf * __ldg(q.ang.spf + a);
                 sX = fx - fr->centre[0]; sZ = fz - fr->centre[2];
-                const double u = su, w = sv;
-                double S[12] = {1.0, u, w, u * u, u * w, w * w, sX, u * sX, w * sX, sZ, u * sZ, w * sZ};
-#pragma unroll
-                for (int k = 0; k < 12; k++) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) S[k] += __shfl_down_sync(0xffffffffu, S[k], o);
-                    if (lane == 0) s_psum[warp][k] = S[k];
-                }
+                double* row = s_samp + tid * FF_PRED_LD;
+                ff_pred_basis<double>((double)su, (double)sv, row);
+                row[FF_PRED_NB] = sX; row[FF_PRED_NB + 1] = sZ;
             }
             __syncthreads();
-            if (tid == 0) {
-                double S[12];
-                for (int k = 0; k < 12; k++) S[k] = s_psum[0][k] + s_psum[1][k];
-                ff_pred_solve(S, s_pred);
+            // cubic least-squares fit (ff_pred_fit, spread over the CTA): normal equations, entry (a, c) per thread
+            for (int t = tid; t < FF_PRED_NB * FF_PRED_LD; t += FF_T) {
+                const int a = t / FF_PRED_LD, c = t - a * FF_PRED_LD;
+                const bool low = c < FF_PRED_NB && c < a;                         // symmetric part: the same sum as (c, a)
+                s_A[t] = ff_pred_normal_entry(s_samp, FF_PRED_SAMPLES, low ? c : a, low ? a : c);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                if (lane < FF_PRED_NB) s_diag[lane] = s_A[lane * FF_PRED_LD + lane];
+                for (int k = 0; k < FF_PRED_NB - 1; k++) {
+                    __syncwarp();
+                    const int i = k + 1 + lane;
+                    if (i < FF_PRED_NB) ff_pred_eliminate(s_A, k, i);
+                }
+                __syncwarp();
+                if (lane == 0) ff_pred_backsub(s_A, s_diag, s_pred);
             }
             __syncthreads();
             if (tid < FF_PRED_SAMPLES) {

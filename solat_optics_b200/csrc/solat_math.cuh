@@ -954,43 +954,137 @@ SOLAT_HD void ff_ray_lean(const Coef& C, const FfFrames& f, const vec3t<R>& d, R
     status = st;
 }
 
-// Where on the focal plane will a ray land?  For one pixel the focal-plane position is, to a few mm over the whole
-// aperture, an affine function of the ray's launch direction cosines (the beam is a defocused image of the aperture;
-// the rest is aberration).  The fused map fits that affine map per pixel to a sample of exactly traced rays, measures
-// its worst error on the sample, and uses it ONLY to drop rays that the reference's projection would skip anyway
-// (ffl:19: x > max(data_x[0, :]) or y > max(data_y[:, 0])) when they miss the high edge of the E_rec grid by more
-// than 5 x that error + 2 mm (and rays certain to pile into cell (0, 0), of which one per row is kept, see
-// ff_pred_row_keep); every other ray is traced in FP64 and binned exactly.  With the +-5 cm grid of
-// ff_sim.py about half of the accepted rays land beyond the grid.
+// Where on the focal plane will a ray land?  For one pixel the focal-plane position is a smooth function of the ray's
+// launch direction cosines: an affine map (the beam is a defocused image of the aperture) plus aberrations of a few
+// mm.  The fused map fits a CUBIC polynomial in the two direction cosines per pixel to a sample of exactly traced
+// rays (worst error over a whole aperture 0.1-0.4 mm; the affine fit of round 1 left 2.5 mm), measures its worst
+// error on the sample, and uses it ONLY to drop rays that the reference's projection would skip anyway (ffl:19:
+// x > max(data_x[0, :]) or y > max(data_y[:, 0])) when they miss the high edge of the E_rec grid by more than
+// 5 x that error + 2 mm (and rays certain to pile into cell (0, 0), of which one per row is kept, see
+// ff_pred_row_keep); every other ray is traced in FP64 and binned exactly.  With the +-5 cm grid of ff_sim.py about
+// half of the accepted rays land beyond the grid.
 constexpr float FF_PRED_SCALE = 2.0e4f;   // launch direction cosines of the fan are ~5e-5
 constexpr int FF_PRED_SAMPLES = 64;
+constexpr int FF_PRED_NB = 10;            // basis 1, u, v, u^2, uv, v^2, u^3, u^2 v, u v^2, v^3
 struct FfPred {
-    float cx[3], cz[3];    // x - centre.x = cx[0] + cx[1] u + cx[2] v  [mm], u = d.x * FF_PRED_SCALE, v = d.y * FF_PRED_SCALE
-    float margin_cm;       // (5 x worst sample error + 2 mm) / 10
+    float cx[FF_PRED_NB], cz[FF_PRED_NB];   // x - centre.x = sum cx[k] b_k(u, v) [mm], u = d.x * FF_PRED_SCALE, v = d.y * FF_PRED_SCALE
+    float margin_cm;                        // (5 x worst sample error + 2 mm) / 10
     int on;
 };
-// Least squares over the sample.  S = {n, Su, Sv, Suu, Suv, Svv, SX, SuX, SvX, SZ, SuZ, SvZ}
-SOLAT_HD void ff_pred_solve(const double* S, FfPred& p)
+// Position of sample k in the pixel's dense list of n_list accepted rays: one per stratum of n_list / SAMPLES rays,
+// at a golden-ratio offset inside it -- an even stride alone can put every sample at the same place of its phi row
+// (a stride that is a multiple of the row length), which leaves the cubic unconstrained along the rows.
+SOLAT_HD int ff_pred_sample_pos(int k, int n_list)
 {
-    const double a = S[0], b = S[1], c = S[2], d = S[3], e = S[4], f = S[5];
-    // inverse of the symmetric normal matrix [[a b c] [b d e] [c e f]] by cofactors
-    const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d, c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
-    const double det = a * c00 + b * c01 + c * c02;
-    p.on = det > 1e-9 * a * d * f && det == det;
-    const double id = p.on ? 1.0 / det : 0.0;
-    for (int k = 0; k < 2; k++) {
-        const double r0 = S[6 + 3 * k], r1 = S[7 + 3 * k], r2 = S[8 + 3 * k];
-        float* o = k ? p.cz : p.cx;
-        o[0] = (float)((c00 * r0 + c01 * r1 + c02 * r2) * id);
-        o[1] = (float)((c01 * r0 + c11 * r1 + c12 * r2) * id);
-        o[2] = (float)((c02 * r0 + c12 * r1 + c22 * r2) * id);
+    const double g = (double)k * 0.6180339887498949;
+    const double pos = ((double)k + (g - floor(g))) * ((double)n_list / (double)FF_PRED_SAMPLES);
+    const int v = (int)pos;
+    return v < 0 ? 0 : (v >= n_list ? n_list - 1 : v);
+}
+template <class T>
+SOLAT_HD void ff_pred_basis(T u, T v, T* b)
+{
+    b[0] = T(1); b[1] = u; b[2] = v; b[3] = u * u; b[4] = u * v; b[5] = v * v;
+    b[6] = b[3] * u; b[7] = b[3] * v; b[8] = u * b[5]; b[9] = b[5] * v;
+}
+// Least squares over the sample.  The normal equations live in an augmented 10 x 12 matrix A (row-major: the
+// symmetric 10 x 10 matrix of basis products, then the right-hand sides for x and z); they are solved by Gaussian
+// elimination without pivoting (the matrix is positive definite; u, v span [-1, 1]: well conditioned in FP64) in steps
+// a warp can share: entry (a, b) <- sum over the samples, row i <- row i - (A[i][k] / A[k][k]) row k, back substitution.
+constexpr int FF_PRED_LD = FF_PRED_NB + 2;
+// samples: [n][FF_PRED_LD] = basis values b_0..b_9, X, Z of every sample ray.  Entry (a, c) of A, c < 12.
+SOLAT_HD double ff_pred_normal_entry(const double* samples, int n, int a, int c)
+{
+    double acc = 0.0;
+    for (int k = 0; k < n; k++) acc = fma(samples[k * FF_PRED_LD + a], samples[k * FF_PRED_LD + c], acc);
+    return acc;
+}
+SOLAT_HD void ff_pred_eliminate(double* A, int k, int i)
+{
+    const double f = A[i * FF_PRED_LD + k] / A[k * FF_PRED_LD + k];
+    for (int j = k; j < FF_PRED_LD; j++) A[i * FF_PRED_LD + j] = fma(-f, A[k * FF_PRED_LD + j], A[i * FF_PRED_LD + j]);
+}
+// A after the elimination (upper triangular), diag0 = the diagonal before it: a pivot that lost 12 digits means a rank
+// deficient sample (e.g. all rays on one row): predictor off
+SOLAT_HD void ff_pred_backsub(const double* A, const double* diag0, FfPred& p)
+{
+    bool ok = true;
+    for (int k = 0; k < FF_PRED_NB; k++) {
+        const double d = A[k * FF_PRED_LD + k];
+        if (!(d > 1e-12 * diag0[k]) || !(d == d)) ok = false;
     }
+    p.on = ok;
     p.margin_cm = 0.0f;
+    for (int which = 0; which < 2; which++) {
+        double y[FF_PRED_NB];
+        float* o = which ? p.cz : p.cx;
+        for (int i = FF_PRED_NB - 1; i >= 0; i--) {
+            double v = A[i * FF_PRED_LD + FF_PRED_NB + which];
+            for (int k = i + 1; k < FF_PRED_NB; k++) v = fma(-A[i * FF_PRED_LD + k], y[k], v);
+            y[i] = ok ? v / A[i * FF_PRED_LD + i] : 0.0;
+            o[i] = (float)y[i];
+        }
+    }
+}
+// the whole solve on one thread (host shadow; the kernel spreads the same steps over a warp)
+SOLAT_HD void ff_pred_fit(const double* samples, int n, FfPred& p)
+{
+    double A[FF_PRED_NB * FF_PRED_LD], diag0[FF_PRED_NB];
+    for (int a = 0; a < FF_PRED_NB; a++)
+        for (int c = 0; c < FF_PRED_LD; c++) A[a * FF_PRED_LD + c] = ff_pred_normal_entry(samples, n, c < FF_PRED_NB && c < a ? c : a, c < FF_PRED_NB && c < a ? a : c);
+    for (int a = 0; a < FF_PRED_NB; a++) diag0[a] = A[a * FF_PRED_LD + a];
+    for (int k = 0; k < FF_PRED_NB - 1; k++)
+        for (int i = k + 1; i < FF_PRED_NB; i++) ff_pred_eliminate(A, k, i);
+    ff_pred_backsub(A, diag0, p);
 }
 SOLAT_HD void ff_pred_eval(const FfPred& p, float u, float v, float& x, float& z)
 {
-    x = fmaf(p.cx[1], u, fmaf(p.cx[2], v, p.cx[0]));
-    z = fmaf(p.cz[1], u, fmaf(p.cz[2], v, p.cz[0]));
+    float b[FF_PRED_NB];
+    ff_pred_basis<float>(u, v, b);
+    x = p.cx[0]; z = p.cz[0];
+    for (int k = 1; k < FF_PRED_NB; k++) { x = fmaf(p.cx[k], b[k], x); z = fmaf(p.cz[k], b[k], z); }
+}
+// Along one phi row u = s cos(phi), v = s sin(phi) with s = sin(theta_i) * FF_PRED_SCALE: the prediction is the cubic
+// a[0] + a[1] s + a[2] s^2 + a[3] s^3
+SOLAT_HD void ff_pred_row_cubic(const float* c, float cpf, float spf, float* a)
+{
+    a[0] = c[0];
+    a[1] = fmaf(c[1], cpf, c[2] * spf);
+    a[2] = fmaf(c[3] * cpf, cpf, fmaf(c[4] * cpf, spf, c[5] * spf * spf));
+    a[3] = fmaf(c[6] * cpf * cpf, cpf, fmaf(c[7] * cpf * cpf, spf, fmaf(c[8] * cpf * spf, spf, c[9] * spf * spf * spf)));
+}
+// Range of the cubic on [s0, s1] and whether it is strictly monotone there (its derivative keeps one sign at both
+// ends and has no root inside).
+SOLAT_HD bool ff_pred_row_range(const float* a, float s0, float s1, float& pmin, float& pmax)
+{
+    const float lo = fminf(s0, s1), hi = fmaxf(s0, s1);
+    auto val = [&](float t) { return fmaf(fmaf(fmaf(a[3], t, a[2]), t, a[1]), t, a[0]); };
+    auto der = [&](float t) { return fmaf(fmaf(3.0f * a[3], t, 2.0f * a[2]), t, a[1]); };
+    const float v0 = val(lo), v1 = val(hi);
+    pmin = fminf(v0, v1); pmax = fmaxf(v0, v1);
+    bool mono = der(lo) * der(hi) > 0.0f;
+    // roots of the derivative 3 a3 t^2 + 2 a2 t + a1
+    float r[2];
+    int nr = 0;
+    if (a[3] != 0.0f) {
+        const float disc = fmaf(a[2], a[2], -3.0f * a[3] * a[1]);
+        if (disc >= 0.0f) {
+            const float sq = sqrtf(disc);
+            r[0] = (-a[2] - sq) / (3.0f * a[3]); r[1] = (-a[2] + sq) / (3.0f * a[3]);
+            nr = 2;
+        }
+    } else if (a[2] != 0.0f) {
+        r[0] = -a[1] / (2.0f * a[2]);
+        nr = 1;
+    }
+    for (int k = 0; k < nr; k++)
+        if (r[k] >= lo && r[k] <= hi) {
+            mono = false;
+            const float v = val(r[k]);
+            pmin = fminf(pmin, v); pmax = fmaxf(pmax, v);
+        }
+    if (!(pmin == pmin) || !(pmax == pmax)) { mono = false; pmin = -3.0e38f; pmax = 3.0e38f; }
+    return mono;
 }
 // worst sample error [mm] -> margin; a sample that is not finite or an error above 5 cm switches the predictor off
 SOLAT_HD void ff_pred_set_margin(FfPred& p, float worst_mm)
@@ -1174,23 +1268,43 @@ SOLAT_HD double ff_key_opl(unsigned long long key, double base, double unit, int
 // of the row that do, only the last one -- the highest ray index -- can hold the cell (ffl:28).  The same for the
 // mirror pixel (`neg`: focal x negated, z shifted by dz_neg_cm, and its ray index grows with i as well).  Kept: the
 // runs of useful rays plus those two corner candidates, as at most FF_ROW_K intervals (more: the whole row is kept).
-// All thresholds carry the predictor's margin.  Along a row the predicted x and z are the row constants times
-// sin(theta_i) (monotone in i on the fans the interval walk accepts, and so are the single-precision table, the
-// product and the FMA), so each of the six comparisons changes its answer at most once along the row: the change
-// points are found by bisection and the row is classified segment by segment, with the very same expressions.
+// All thresholds carry the predictor's margin.  Along a row the predicted x and z are cubics in s = sin(theta_i)
+// (ff_pred_row_cubic), dominated by their linear term; where a cubic is monotone over the row's accepted rays, or its
+// whole range stays on one side of a threshold (ff_pred_row_range; otherwise the whole row is kept), the comparison
+// changes its answer at most once along the row: the change points are found by bisection and the row is classified
+// segment by segment, with the very same expressions.
 constexpr int FF_ROW_K = 4;
 SOLAT_HD int ff_pred_row_keep(const FfPred& p, const float* stf, float cpf, float spf, const FfGrid& G, bool need_pos, bool need_neg,
                               float dz_neg_cm, int lo, int hi, int* out_lo, int* out_cnt)
 {
     for (int k = 0; k < FF_ROW_K; k++) { out_lo[k] = lo; out_cnt[k] = 0; }
     if (hi <= lo) return 0;
-    const float kx = fmaf(p.cx[1], cpf, p.cx[2] * spf), kz = fmaf(p.cz[1], cpf, p.cz[2] * spf), m = p.margin_cm;
+    float ax[4], az[4];
+    ff_pred_row_cubic(p.cx, cpf, spf, ax);
+    ff_pred_row_cubic(p.cz, cpf, spf, az);
+    const float m = p.margin_cm;
+    const float s_a = stf[lo] * FF_PRED_SCALE, s_b = stf[hi - 1] * FF_PRED_SCALE;
+    float xmin, xmax, zmin, zmax;
+    const bool x_mono = ff_pred_row_range(ax, s_a, s_b, xmin, xmax), z_mono = ff_pred_row_range(az, s_a, s_b, zmin, zmax);
     const float x_hi = (float)G.gx_max + m, z_hi = (float)G.gy_max + m, x_lo = (float)G.gx_min - m, z_lo = (float)G.gy_min - m;
     const float ez = fabsf(dz_neg_cm);
+    {   // The bisections below need every comparison to change its answer at most once along the row: true where the
+        // cubic is monotone, or where its whole range (0.1 mm slack) lies on one side of the threshold.  Otherwise the
+        // row is kept whole.
+        auto clear = [](bool mono, float pmin, float pmax, float t) { return mono || t > pmax + 0.01f || t < pmin - 0.01f; };
+        const float x0 = 0.1f * xmin, x1 = 0.1f * xmax, z0 = 0.1f * zmin, z1 = 0.1f * zmax;     // cm
+        const bool ok = clear(x_mono, x0, x1, x_hi) && clear(x_mono, x0, x1, -x_hi) && clear(x_mono, x0, x1, x_lo) &&
+                        clear(x_mono, x0, x1, -x_lo) && clear(z_mono, z0, z1, z_hi + ez) && clear(z_mono, z0, z1, z_lo - ez);
+        if (!ok) {
+            out_cnt[0] = hi - lo;
+            return 1;
+        }
+    }
     // the six comparisons of ray i (NaN predictions compare false everywhere: the ray counts as useful)
     auto test = [&](int i, int which) {
         const float s = stf[i] * FF_PRED_SCALE;
-        const float x = 0.1f * fmaf(s, kx, p.cx[0]), z = 0.1f * fmaf(s, kz, p.cz[0]);
+        const float x = 0.1f * fmaf(fmaf(fmaf(ax[3], s, ax[2]), s, ax[1]), s, ax[0]);
+        const float z = 0.1f * fmaf(fmaf(fmaf(az[3], s, az[2]), s, az[1]), s, az[0]);
         switch (which) {
             case 0: return x > x_hi;
             case 1: return -x > x_hi;

@@ -292,6 +292,18 @@ API int shadow_ff_row_intervals(const double* geo, const double* th, int nth, co
     return bad;
 }
 
+// the cubic fit exactly as ff_prep_kernel forms it (same entries, same elimination steps)
+static void pred_fit(const float* us, const float* vs, const double* Xs, const double* Zs, FfPred& p)
+{
+    std::vector<double> samples((size_t)FF_PRED_SAMPLES * FF_PRED_LD);
+    for (int k = 0; k < FF_PRED_SAMPLES; k++) {
+        double* row = samples.data() + (size_t)k * FF_PRED_LD;
+        ff_pred_basis<double>((double)us[k], (double)vs[k], row);
+        row[FF_PRED_NB] = Xs[k]; row[FF_PRED_NB + 1] = Zs[k];
+    }
+    ff_pred_fit(samples.data(), FF_PRED_SAMPLES, p);
+}
+
 // The fused map's focal-position predictor, as the kernel builds it: FF_PRED_SAMPLES rays spread over the pixel's
 // dense list of accepted rays are traced exactly, the affine map is fitted and its worst sample error sets the
 // margin.  out4: worst predictor error over ALL accepted rays [mm], worst sample error [mm], rays the predictor
@@ -333,17 +345,13 @@ API int shadow_ff_pred_check(const double* geo, const double* th, int nth, const
     p.on = 0;
     double worst_sample = 0.0;
     if (n_acc >= 512) {
-        double S[12] = {0};
         float us[FF_PRED_SAMPLES], vs[FF_PRED_SAMPLES];
         double Xs[FF_PRED_SAMPLES], Zs[FF_PRED_SAMPLES];
         for (int k = 0; k < FF_PRED_SAMPLES; k++) {
-            const int r = rays[(long)k * (n_acc - 1) / (FF_PRED_SAMPLES - 1)];
+            const int r = rays[ff_pred_sample_pos(k, n_acc)];
             trace(r, us[k], vs[k], Xs[k], Zs[k]);
-            const double u = us[k], v = vs[k];
-            S[0] += 1; S[1] += u; S[2] += v; S[3] += u * u; S[4] += u * v; S[5] += v * v;
-            S[6] += Xs[k]; S[7] += u * Xs[k]; S[8] += v * Xs[k]; S[9] += Zs[k]; S[10] += u * Zs[k]; S[11] += v * Zs[k];
         }
-        ff_pred_solve(S, p);
+        pred_fit(us, vs, Xs, Zs, p);
         for (int k = 0; k < FF_PRED_SAMPLES; k++) {
             float x, z;
             ff_pred_eval(p, us[k], vs[k], x, z);
@@ -411,19 +419,15 @@ API int shadow_ff_keep_check(const double* geo, const double* th, int nth, const
     FfPred p;
     p.on = 0;
     if (n_acc >= 512) {
-        double S[12] = {0};
         float us[FF_PRED_SAMPLES], vs[FF_PRED_SAMPLES];
         double Xs[FF_PRED_SAMPLES], Zs[FF_PRED_SAMPLES];
         for (int k = 0; k < FF_PRED_SAMPLES; k++) {
-            const int r = rays[(long)k * (n_acc - 1) / (FF_PRED_SAMPLES - 1)], i = r % nth, j = r / nth;
+            const int r = rays[ff_pred_sample_pos(k, n_acc)], i = r % nth, j = r / nth;
             const Hit h = trace(r);
             us[k] = stf[i] * FF_PRED_SCALE * (float)cos(ph[j]); vs[k] = stf[i] * FF_PRED_SCALE * (float)sin(ph[j]);
             Xs[k] = h.X; Zs[k] = h.Z;
-            const double u = us[k], v = vs[k];
-            S[0] += 1; S[1] += u; S[2] += v; S[3] += u * u; S[4] += u * v; S[5] += v * v;
-            S[6] += Xs[k]; S[7] += u * Xs[k]; S[8] += v * Xs[k]; S[9] += Zs[k]; S[10] += u * Zs[k]; S[11] += v * Zs[k];
         }
-        ff_pred_solve(S, p);
+        pred_fit(us, vs, Xs, Zs, p);
         double worst = 0.0;
         for (int k = 0; k < FF_PRED_SAMPLES; k++) {
             float x, z;

@@ -228,27 +228,28 @@ def test_ff_row_intervals_equal_the_per_ray_aperture_test(shadow, oracle):
 
 
 def test_ff_focal_predictor_is_conservative(shadow, oracle):
-    """The fused far-field map drops rays before the FP64 trace when an affine predictor of the focal-plane position
+    """The fused far-field map drops rays before the FP64 trace when a cubic predictor of the focal-plane position
     (fitted per pixel to 64 exactly traced rays) puts them beyond the high edge of the E_rec grid -- or below both
     low edges -- by more than 5 x its worst sample error + 2 mm.  Such a ray must be one the exact comparison
     (ffl:19) skips, resp. one that lands in cell (0, 0): checked on every accepted ray for on- and far-off-axis
-    pixels, three focal offsets, small and large fans, four grid sizes."""
+    pixels, three focal offsets, small and large fans (also fans whose row length divides the sample stride), four
+    grid sizes.  The worst error over ALL accepted rays must stay below HALF the margin."""
     ratio = 0.0
-    for n in (100, 40, 317):
+    for n in (100, 40, 317, 211, 1000):
         th, phi = gu.ff_fan(n)
-        for offset in (1.25, 1.32, 1.4):
+        for offset in (1.25, 1.32, 1.4) if n < 1000 else (1.32,):
             geo = oracle.ff_geo_vec(rx_y_m=-offset)
-            for az, el in [(0.0, gu.EL0), (20 * gu.DE, gu.EL0 - 20 * gu.DE), (-30 * gu.DE, gu.EL0 + 30 * gu.DE), (3e-3, -2e-3), (0.02, 0.01)]:
+            pixels = [(0.0, gu.EL0), (20 * gu.DE, gu.EL0 - 20 * gu.DE), (-30 * gu.DE, gu.EL0 + 30 * gu.DE), (3e-3, -2e-3), (0.02, 0.01)]
+            for az, el in pixels if n < 1000 else pixels[:2]:
                 for gmax in (5.0, 0.0, 20.0, 30.0) if n == 100 else (5.0,):
                     nv, worst, worst_sample, dropped, wrong = shadow.ff_pred_check(geo, th, phi, el, az, gmax, gmax)
                     assert nv > 0 and wrong == 0
-                    assert worst < 5.0 * worst_sample + 2.0                    # the margin really covers every ray
-                    ratio = max(ratio, worst / worst_sample)
+                    ratio = max(ratio, worst / (5.0 * worst_sample + 2.0))
                     if gmax == 5.0 and abs(az) < 1e-3 and n >= 100:
                         assert dropped > 0.3 * nv      # the +-5 cm grid of ff_sim.py: about half of the rays miss it
                     if gmax == 30.0 and abs(az) < 1e-3:
                         assert dropped == 0
-    assert ratio < 2.0, ratio          # worst error anywhere stays within 2x the sampled one (margin is 5x + 2 mm)
+    assert ratio < 0.5, ratio          # the margin (5 x sampled error + 2 mm) covers every ray twice over
     # tiny fans: predictor off
     th, phi = gu.ff_fan(12)
     assert shadow.ff_pred_check(oracle.ff_geo_vec(rx_y_m=-1.32), th, phi, gu.EL0, 0.0, 5.0, 5.0)[0] < 0
