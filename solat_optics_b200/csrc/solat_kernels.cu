@@ -1343,7 +1343,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     }
     // bin one traced ray (i, j) into the winner table(s): cells first (a later ray may hold them already), then ONE key
     // for both pixels of a pair
-    auto bin = [&](int i, int j, double opl, double fx, double fz) {
+    auto bin = [&](int i, int j, double opl, double fx, double fz) __attribute__((always_inline)) {
         if (opl != 0.0 && !not_finite(opl)) {                                   // ffl:10
             const int r0 = j * nth + i;
             int cell = -1, cell_m = -1, rm = 0;
@@ -1367,7 +1367,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
         }
     };
     // trace ray (i, j) and bin it
-    auto trace = [&](int i, int j) {
+    auto trace = [&](int i, int j) __attribute__((always_inline)) {
         const vec3 d = launch_dir(__ldg(q.ang.st + i), __ldg(q.ang.ct + i), __ldg(q.ang.sp + j), __ldg(q.ang.cp + j));
         vec3 Pa;
         double t_ap;
