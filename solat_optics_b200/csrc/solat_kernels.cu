@@ -163,6 +163,7 @@ struct solat_ctx {
 struct AngleTabs {
     const double *st, *ct, *sp, *cp;   // sin/cos of theta[nth], phi[nph]
     const float *stf, *ctf, *spf, *cpf; // single-precision copies (far-field aperture prefilter)
+    const double2 *tsc, *psc;          // (sin, cos) of theta[nth] / phi[nph] interleaved: one 16-byte load per axis in the hot loop
     int nth, nph;                      // nph == 0: paired mode, ray ii uses theta[ii], phi[ii] (phi has nth entries)
     unsigned magic;                    // ceil(2^32 / nth): r / nth == __umulhi(r, magic) (+1 fix-up) for r < 2^32 / nth
     __host__ __device__ int rays() const { return nph == 0 ? nth : nth * nph; }
@@ -170,6 +171,7 @@ struct AngleTabs {
 struct AngleTabsOwner {
     DevBuf<double> buf;
     DevBuf<float> fbuf;
+    DevBuf<double2> pbuf;
     AngleTabs tabs;
     int init(const double* theta, int nth, const double* phi, int nph_arg, cudaStream_t s)
     {
@@ -179,11 +181,16 @@ struct AngleTabsOwner {
         for (int j = 0; j < nph; j++) { h[2 * nth + j] = sin(phi[j]); h[2 * nth + nph + j] = cos(phi[j]); }
         std::vector<float> hf(h.size());
         for (size_t i = 0; i < h.size(); i++) hf[i] = (float)h[i];
+        std::vector<double2> hp((size_t)nth + nph);
+        for (int i = 0; i < nth; i++) hp[i] = make_double2(h[i], h[nth + i]);
+        for (int j = 0; j < nph; j++) hp[nth + j] = make_double2(h[2 * nth + j], h[2 * nth + nph + j]);
         int rc = buf.upload(h.data(), h.size(), s);
         if (!rc) rc = fbuf.upload(hf.data(), hf.size(), s);
+        if (!rc) rc = pbuf.upload(hp.data(), hp.size(), s);
         if (rc) return rc;
         CK(cudaStreamSynchronize(s));   // h, hf go out of scope
         tabs.stf = fbuf.p; tabs.ctf = fbuf.p + nth; tabs.spf = fbuf.p + 2 * nth; tabs.cpf = fbuf.p + 2 * nth + nph;
+        tabs.tsc = pbuf.p; tabs.psc = pbuf.p + nth;
         tabs.st = buf.p; tabs.ct = buf.p + nth; tabs.sp = buf.p + 2 * nth; tabs.cp = buf.p + 2 * nth + nph;
         tabs.nth = nth; tabs.nph = nph_arg;
         const unsigned long long rays = (unsigned long long)nth * (unsigned long long)nph;
@@ -1368,7 +1375,8 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     };
     // trace ray (i, j) and bin it
     auto trace = [&](int i, int j) __attribute__((always_inline)) {
-        const vec3 d = launch_dir(__ldg(q.ang.st + i), __ldg(q.ang.ct + i), __ldg(q.ang.sp + j), __ldg(q.ang.cp + j));
+        const double2 tsc = __ldg(q.ang.tsc + i), psc = __ldg(q.ang.psc + j);
+        const vec3 d = launch_dir(tsc.x, tsc.y, psc.x, psc.y);
         vec3 Pa;
         double t_ap;
         ff_aperture(sC, g, *fr, d, t_ap, Pa);

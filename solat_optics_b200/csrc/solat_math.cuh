@@ -149,6 +149,7 @@ SOLAT_HD bool abs_gt(double a, double tol) { return (hi_word(a) & 0x7fffffff) > 
 SOLAT_HD bool not_finite(double a) { return (hi_word(a) & 0x7ff00000) == 0x7ff00000; }
 SOLAT_HD bool bnot(bool a) { return !a; }
 SOLAT_HD bool band(bool a, bool b) { return a && b; }
+SOLAT_HD bool bor(bool a, bool b) { return a || b; }
 SOLAT_HD bool any(bool a) { return a; }
 SOLAT_HD double select(bool m, double a, double b) { return m ? a : b; }
 SOLAT_HD int flag(bool m, int bit) { return m ? bit : 0; }
@@ -210,6 +211,7 @@ SOLAT_HD b2 abs_gt(d2 a, double tol) { return mkb(abs_gt(a.a, tol), abs_gt(a.b, 
 SOLAT_HD b2 not_finite(d2 a) { return mkb(not_finite(a.a), not_finite(a.b)); }
 SOLAT_HD b2 bnot(b2 x) { return mkb(!x.a, !x.b); }
 SOLAT_HD b2 band(b2 x, b2 y) { return mkb(x.a && y.a, x.b && y.b); }
+SOLAT_HD b2 bor(b2 x, b2 y) { return mkb(x.a || y.a, x.b || y.b); }
 SOLAT_HD bool any(b2 x) { return x.a || x.b; }
 SOLAT_HD d2 select(b2 m, d2 x, d2 y) { return d2(m.a ? x.a : y.a, m.b ? x.b : y.b); }
 SOLAT_HD i2 flag(b2 m, int bit) { return i2(m.a ? bit : 0, m.b ? bit : 0); }
@@ -734,9 +736,17 @@ struct PanelErr {
 // One FP32 coarse update, then two FP64 updates; the gradient of the last evaluation is also used for
 // the normal (the last step is ~1e-11 mm, so the normal is exact to 1e-16).  PE (scalar rays only): optional
 // panel error, evaluated along its own affine image (pe + t de) of the ray (saf:676-703, :820-852).
+// status of a mirror hit from its ray parameter and last Newton step
+template <class R>
+SOLAT_HD typename Pack<R>::I mirror_status(R t, R dt, double lo, double hi)
+{
+    typename Pack<R>::I st = imask(bnot(not_finite(dt)), flag(abs_gt(dt, 1e-8), ST_NOCONV)) | flag(not_finite(dt), ST_NAN);
+    st |= flag(out_of_range(t, lo, hi), ST_BRACKET);
+    return st;
+}
 template <int M, bool PANEL, class R>
 SOLAT_HD typename Pack<R>::I mirror_hit(const Coef& C, const vec3t<R>& P, const vec3t<R>& D, double lo, double hi, const PanelErr* pe,
-                                        const vec3t<R>& pE, const vec3t<R>& dE, R& t, vec3t<R>& H, vec3t<R>& N)
+                                        const vec3t<R>& pE, const vec3t<R>& dE, R& t, vec3t<R>& H, vec3t<R>& N, R* dt_out = nullptr)
 {
     using F = typename Pack<R>::F;
     using I = typename Pack<R>::I;
@@ -771,9 +781,8 @@ SOLAT_HD typename Pack<R>::I mirror_hit(const Coef& C, const vec3t<R>& P, const 
     if (PANEL) mirror_sag<M, R>(C, H.x, H.y, z, zx, zy);   // reference normal = ideal-mirror gradient (saf:718-720, :869-871)
     const R nn = rsqrt_fast(fma(zx, zx, fma(zy, zy, R(1.0))));
     N = mk<R>(-zx * nn, -zy * nn, nn);
-    I st = imask(bnot(not_finite(dt)), flag(abs_gt(dt, 1e-8), ST_NOCONV)) | flag(not_finite(dt), ST_NAN);
-    st |= flag(out_of_range(t, lo, hi), ST_BRACKET);
-    return st;
+    if (dt_out) { *dt_out = dt; return I(0); }            // the caller forms the status itself (mirror_status)
+    return mirror_status(t, dt, lo, hi);
 }
 
 // cheap first stage of every far-field ray: aperture-plane hit and the 3 m radius test
@@ -937,20 +946,29 @@ SOLAT_HD void ff_ray_lean(const Coef& C, const FfFrames& f, const vec3t<R>& d, R
     vec3t<R> H, N;
     const vec3t<R> none = mk<R>(R(0.0), R(0.0), R(0.0));
     const vec3t<R> p1 = apply(f.t1, Pa), d1 = apply_lin(f.t1.a, d);
-    I st = mirror_hit<1, false, R>(C, p1, d1, 0.0, 1e4, nullptr, none, none, t1, H, N);
+    R dt1, dt2;
+    mirror_hit<1, false, R>(C, p1, d1, 0.0, 1e4, nullptr, none, none, t1, H, N, &dt1);
     const vec3t<R> p2 = apply(f.t21, H), d2 = apply_lin(f.b12, reflect(d1, N));
-    st |= mirror_hit<2, false, R>(C, p2, d2, 1e3, 13e3, nullptr, none, none, t2, H, N);
+    mirror_hit<2, false, R>(C, p2, d2, 1e3, 13e3, nullptr, none, none, t2, H, N, &dt2);
     const vec3t<R> r2 = reflect(d2, N);
     const R num = R(foc_y) - fma(R(f.foc_l[0]), H.x, fma(R(f.foc_l[1]), H.y, fma(R(f.foc_l[2]), H.z, R(f.foc_l[3]))));
     const R den = fma(R(f.foc_d[0]), r2.x, fma(R(f.foc_d[1]), r2.y, R(f.foc_d[2]) * r2.z));
     const R tf = num * rcp_fast(den);                                                        // saf:947-962
-    st |= flag(out_of_range(tf, 1e3, 15e3), ST_BRACKET);
     fx = fma(tf, fma(R(f.fx_d[0]), r2.x, fma(R(f.fx_d[1]), r2.y, R(f.fx_d[2]) * r2.z)),
              fma(R(f.fx_l[0]), H.x, fma(R(f.fx_l[1]), H.y, fma(R(f.fx_l[2]), H.z, R(f.fx_l[3])))));
     fz = fma(tf, fma(R(f.fz_d[0]), r2.x, fma(R(f.fz_d[1]), r2.y, R(f.fz_d[2]) * r2.z)),
              fma(R(f.fz_l[0]), H.x, fma(R(f.fz_l[1]), H.y, fma(R(f.fz_l[2]), H.z, R(f.fz_l[3])))));
     opl = ((t_ap + t1) + t2) + tf;                                                           // saf:970
-    st |= flag(not_finite(opl), ST_NAN);
+    // Status: nominal rays raise none of the six conditions, so they are tested together (integer compares on the high
+    // words) and the individual bits are formed only on the rare ray that trips one.
+    const auto odd = bor(bor(bor(out_of_range(t1, 0.0, 1e4), abs_gt(dt1, 1e-8)), bor(out_of_range(t2, 1e3, 13e3), abs_gt(dt2, 1e-8))),
+                         bor(out_of_range(tf, 1e3, 15e3), not_finite(opl)));
+    I st = I(0);
+    if (any(odd)) {
+        st = mirror_status(t1, dt1, 0.0, 1e4) | mirror_status(t2, dt2, 1e3, 13e3);
+        st |= flag(out_of_range(tf, 1e3, 15e3), ST_BRACKET);
+        st |= flag(not_finite(opl), ST_NAN);
+    }
     status = st;
 }
 
