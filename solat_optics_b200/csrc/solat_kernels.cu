@@ -1099,6 +1099,7 @@ __device__ __forceinline__ void ff_prefix_rows(int* row_pre, int nph, int lane)
 // memory the map kernel copies into its shared memory.  Record: FfFrames | int queue_walk, n_list, pad[2] |
 // row_lo[K nph] | row_pre[K nph + 1]  (K = FF_ROW_K intervals per phi row: virtual row K j + k).
 constexpr int FF_PREP_T = 64;     // = FF_PRED_SAMPLES; 12 CTAs per SM keep every pixel of a 41 x 41 map in flight
+constexpr int FF_PREP_T_BIG = 256; // fans of at least FF_PILE_MIN rays
 constexpr size_t FF_REC_FRAMES = ((sizeof(FfFrames) + 15) / 16) * 16;
 constexpr size_t FF_REC_HEAD = FF_REC_FRAMES + 16;
 struct FfPrepParams {
@@ -1109,6 +1110,7 @@ struct FfPrepParams {
     const int* counters;
     int item0;               // pair mode: CTA b handles item item0 + b (its record is record b)
     int rows, prefilter;
+    int pile;                // scouts + pile shrinking for items that list at least FF_PILE_MIN rays
     FfGrid grid;             // edges of the E_rec grid (ff_pred_row_keep)
     unsigned char* rec;
     size_t stride;
@@ -1116,9 +1118,12 @@ struct FfPrepParams {
 };
 static size_t ff_rec_stride(int rows_nph) { return FF_REC_HEAD + (rows_nph ? ((2 * (size_t)FF_ROW_K * rows_nph + 1) * sizeof(int) + 15) / 16 * 16 : 0); }
 
-__global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
+// T = 64 (FF_PREP_T): the small items of reference-sized maps, all in flight at once; T = 256 (FF_PREP_T_BIG): items of
+// large fans, where the scout stage scans hundreds of thousands of listed rays per item.
+template <int T>
+__global__ void __launch_bounds__(T, T == 64 ? 12 : 3) ff_prep_kernel(FfPrepParams q)
 {
-    constexpr int FF_T = FF_PREP_T;
+    constexpr int FF_T = T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FfFrames* fr = reinterpret_cast<FfFrames*>(smem_raw);
     const int nvr = FF_ROW_K * q.ang.nph;                                  // virtual rows: FF_ROW_K intervals per phi row
@@ -1233,6 +1238,115 @@ __global__ void __launch_bounds__(FF_PREP_T, 12) ff_prep_kernel(FfPrepParams q)
                 __syncthreads();
                 if (warp == 0) ff_prefix_rows(row_pre, nvr, lane);
                 __syncthreads();
+                // ---- pile shrinking (FfPile): scouts, their exact landings, second pass over the rows
+                if (q.pile && row_pre[nvr] >= FF_PILE_MIN) {
+                    const int M = q.grid.M, nph = q.ang.nph;
+                    int* scout = row_pre + nvr + 1;                      // [2 tables][2 lines][2 M] latest ray predicted into the half cell
+                    int* L1 = scout + 8 * M;                             // [2][2][M] latest scout that landed in the cell
+                    int* L2 = L1 + 4 * M;                                // the same from the surviving scouts only
+                    int* sc = L2 + 4 * M;                                // [2 tables][8 M] landing cell of every scout in both tables
+                    for (int i = tid; i < 16 * M; i += FF_T) scout[i] = 0;   // scout, L1, L2
+                    __syncthreads();
+                    const float mg = s_pred.margin_cm, dz_m = 0.1f * (float)(fr->centre[2] - fr->centre_mz);
+                    const float x_lo = (float)q.grid.gx_min - mg, z_lo = (float)q.grid.gy_min - mg, x_hi = (float)q.grid.gx_max + mg,
+                                z_hi = (float)q.grid.gy_max + mg;
+                    // pile line of a predicted landing point in a table: 0 column 0, 1 row 0, -1 none (inside, corner, beyond)
+                    auto pile_line = [&](float X, float Z, float& c) {
+                        if (X > x_hi || Z > z_hi) return -1;
+                        const bool left = X < x_lo, below = Z < z_lo;
+                        if (left == below) return -1;
+                        c = left ? Z : X;
+                        return left ? 0 : 1;
+                    };
+                    for (int j = tid; j < nph; j += FF_T) {
+                        float ax[4], az[4];
+                        ff_pred_row_cubic(s_pred.cx, __ldg(q.ang.cpf + j), __ldg(q.ang.spf + j), ax);
+                        ff_pred_row_cubic(s_pred.cz, __ldg(q.ang.cpf + j), __ldg(q.ang.spf + j), az);
+                        for (int k = 0; k < FF_ROW_K; k++) {
+                            const int lo = row_lo[FF_ROW_K * j + k], cnt = row_pre[FF_ROW_K * j + k + 1] - row_pre[FF_ROW_K * j + k];
+#pragma unroll 4
+                            for (int i = lo + cnt - 1; i >= lo; i -= FF_SCOUT_STEP) {
+                                const float sf = __ldg(q.ang.stf + i) * FF_PRED_SCALE;
+                                const float X = 0.1f * fmaf(fmaf(fmaf(ax[3], sf, ax[2]), sf, ax[1]), sf, ax[0]);
+                                const float Z = 0.1f * fmaf(fmaf(fmaf(az[3], sf, az[2]), sf, az[1]), sf, az[0]);
+                                float c;
+                                if (need_pos) {
+                                    const int line = pile_line(X, Z, c);
+                                    if (line >= 0)
+                                        atomicMax(scout + line * 2 * M + ff_pile_slot(line ? q.grid.gx : q.grid.gy, M, line ? 1 : q.grid.gy_rs, c), j * nth + i + 1);
+                                }
+                                if (need_neg) {
+                                    const int line = pile_line(-X, Z + dz_m, c);
+                                    if (line >= 0)
+                                        atomicMax(scout + (2 + line) * 2 * M + ff_pile_slot(line ? q.grid.gx : q.grid.gy, M, line ? 1 : q.grid.gy_rs, c),
+                                                  (nph - 1 - j) * nth + i + 1);
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    // every landing of a scout on a pile line of either table: fn(table, line, cell on the line, index + 1)
+                    auto landings = [&](int e, int cp, int cn, int i, int j, auto&& fn) {
+                        (void)e;
+                        if (cp >= 0) {
+                            if (cp % M == 0) fn(0, 0, cp / M, j * nth + i + 1);
+                            if (cp / M == 0) fn(0, 1, cp % M, j * nth + i + 1);
+                        }
+                        if (cn >= 0) {
+                            if (cn % M == 0) fn(1, 0, cn / M, (nph - 1 - j) * nth + i + 1);
+                            if (cn / M == 0) fn(1, 1, cn % M, (nph - 1 - j) * nth + i + 1);
+                        }
+                    };
+                    auto scout_ray = [&](int e, int& i, int& j) {
+                        const int sidx = scout[e] - 1;
+                        j = sidx / nth; i = sidx - j * nth;
+                        if (e >= 4 * M) j = nph - 1 - j;                  // the mirror table counts the rows backwards
+                    };
+                    for (int e = tid; e < 8 * M; e += FF_T) {             // trace the scouts
+                        sc[e] = sc[8 * M + e] = -1;
+                        if (scout[e] <= 0) continue;
+                        int i, j;
+                        scout_ray(e, i, j);
+                        const vec3 d = launch_dir(__ldg(q.ang.st + i), __ldg(q.ang.ct + i), __ldg(q.ang.sp + j), __ldg(q.ang.cp + j));
+                        vec3 Pa;
+                        double t_ap, opl, fx, fz;
+                        int rst;
+                        ff_aperture(sC, g, *fr, d, t_ap, Pa);
+                        ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);
+                        if (opl != 0.0 && !not_finite(opl)) {
+                            const double X = fx - fr->centre[0];
+                            if (need_pos) sc[e] = ff_cell(X, fz - fr->centre[2], q.grid);
+                            if (need_neg) sc[8 * M + e] = ff_cell(-X, fz - fr->centre_mz, q.grid);
+                        }
+                        landings(e, sc[e], sc[8 * M + e], i, j, [&](int t, int line, int c, int v) { atomicMax(L1 + (2 * t + line) * M + c, v); });
+                    }
+                    __syncthreads();
+                    // a scout survives when it is the latest in the cell of ITS OWN line (then its row segment keeps it,
+                    // see ff_pred_row_keep); only survivors may stand for a cell
+                    for (int e = tid; e < 8 * M; e += FF_T) {
+                        if (scout[e] <= 0) continue;
+                        const int t = e / (4 * M), line = (e / (2 * M)) & 1, cell = sc[t * 8 * M + e];
+                        if (cell < 0 || (line == 0 ? cell % M != 0 : cell / M != 0)) continue;
+                        if (L1[(2 * t + line) * M + (line == 0 ? cell / M : cell % M)] != scout[e]) continue;
+                        int i, j;
+                        scout_ray(e, i, j);
+                        landings(e, sc[e], sc[8 * M + e], i, j, [&](int t2, int l2, int c, int v) { atomicMax(L2 + (2 * t2 + l2) * M + c, v); });
+                    }
+                    __syncthreads();
+                    FfPile pile;
+                    pile.L = L2; pile.nth = nth; pile.nph = nph;
+                    for (int j = tid; j < nph; j += FF_T) {
+                        int lo, hi, klo[FF_ROW_K], kcnt[FF_ROW_K];
+                        ff_row_interval(sC, g, *fr, q.ang.st, q.ang.ct, nth, __ldg(q.ang.sp + j), __ldg(q.ang.cp + j), lo, hi);
+                        pile.j = j;
+                        ff_pred_row_keep(s_pred, q.ang.stf, __ldg(q.ang.cpf + j), __ldg(q.ang.spf + j), q.grid, need_pos, need_neg, dz_m, lo, hi,
+                                         klo, kcnt, &pile);
+                        for (int k = 0; k < FF_ROW_K; k++) { row_lo[FF_ROW_K * j + k] = klo[k]; row_pre[FF_ROW_K * j + k + 1] = kcnt[k]; }
+                    }
+                    __syncthreads();
+                    if (warp == 0) ff_prefix_rows(row_pre, nvr, lane);
+                    __syncthreads();
+                }
             }
         }
     }
@@ -2410,7 +2524,21 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
         }
         pq.items = q.items = p->items.p; pq.counters = q.counters = ints;
     }
-    const size_t prep_smem = FF_REC_FRAMES + (rows ? (2 * (size_t)FF_ROW_K * p->ang.tabs.nph + 1) * sizeof(int) : 0);
+    const bool big_prep = p->n_rays >= FF_PILE_MIN;          // (an item lists at most n_rays rays)
+    const char* pile_env = getenv("SOLAT_FF_PILE");
+    pq.pile = big_prep && (pairs || !panel) && rows && pq.prefilter && !(pile_env && pile_env[0] == '0');
+    const size_t prep_smem = FF_REC_FRAMES + (rows ? (2 * (size_t)FF_ROW_K * p->ang.tabs.nph + 1) * sizeof(int) : 0) +
+                             (pq.pile ? 32 * (size_t)p->M * sizeof(int) : 0);
+    if (prep_smem + 8192 > 48 * 1024) {        // (static shared memory counts towards the 48 kB a launch gets without opting in)
+        static std::mutex mu;
+        static size_t granted[64] = {};
+        std::lock_guard<std::mutex> lock(mu);
+        if (prep_smem > granted[p->ctx->device & 63]) {
+            CK(cudaFuncSetAttribute(ff_prep_kernel<FF_PREP_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+            CK(cudaFuncSetAttribute(ff_prep_kernel<FF_PREP_T_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+            granted[p->ctx->device & 63] = prep_smem;
+        }
+    }
     q.rows = rows; q.rec = p->rec.p; q.rec_stride = stride;
     const double* azel = q.azel;
     double *amp = q.amp, *phase = q.phase;
@@ -2424,7 +2552,8 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
             pq.azel = azel + 2 * (size_t)p0;
             q.azel = azel + 2 * (size_t)p0; q.amp = amp + p0; q.phase = phase + p0;
         }
-        ff_prep_kernel<<<n, FF_PREP_T, prep_smem, s>>>(pq);
+        if (big_prep) ff_prep_kernel<FF_PREP_T_BIG><<<n, FF_PREP_T_BIG, prep_smem, s>>>(pq);
+        else ff_prep_kernel<FF_PREP_T><<<n, FF_PREP_T, prep_smem, s>>>(pq);
         LAUNCHED();
         if (panel == 1) { q.pidx1 = i1 + (size_t)p0 * p->n_rays; q.pidx2 = i2 + (size_t)p0 * p->n_rays; }
         if (panel == 1) ff_map_dispatch<1>(p->shape, q, n, p->smem, s);

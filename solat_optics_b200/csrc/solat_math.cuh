@@ -1292,8 +1292,32 @@ SOLAT_HD double ff_key_opl(unsigned long long key, double base, double unit, int
 // changes its answer at most once along the row: the change points are found by bisection and the row is classified
 // segment by segment, with the very same expressions.
 constexpr int FF_ROW_K = 4;
+// Pile cells.  A ray below a low edge of the E_rec grid lands in column 0 (x <= gx[0]) or row 0 of a winner table
+// (ffl:22-23) and only the latest ray of each such cell counts (ffl:28): on a +-5 cm grid more than half of the listed
+// rays are "pile" rays and all but a few hundred lose.  Before the map is traced, the set-up kernel traces a few
+// hundred SCOUTS per work item -- per half cell of each pile line the latest ray the predictor places there -- and
+// records, per pile cell, the latest scout that really landed in it (L, exact).  A pile ray whose every reachable cell
+// (predicted position +- margin) already holds a later scout cannot win and is dropped from the list
+// (ff_pred_row_keep with `pile`).  Exact by construction: a ray is dropped only if a later ray THAT STAYS LISTED sits
+// in each cell it could reach (L only holds scouts that are the latest in a cell of their own line, and such a scout's
+// row segment always keeps it).
+struct FfPile {
+    const int* L;          // [2 tables][2 lines][M]: (ray index in the table's own numbering) + 1 of the latest surviving scout in
+                           // cell (c, 0) [line 0: column 0, c = iz] / (0, c) [line 1: row 0, c = ix]; 0 = none
+    int nth, nph, j;       // fan, and the phi row the call is about
+};
+constexpr int FF_PILE_MIN = 20000;     // listed rays per work item from which the scouts pay (a 100 x 100 fan lists ~3000)
+constexpr int FF_SCOUT_STEP = 4;       // every n-th listed ray of a row interval (from its last ray down) is offered as a scout
+// half-cell slot [0, 2M) of a pile coordinate c [cm] on an axis g (M values, stride gs)
+SOLAT_HD int ff_pile_slot(const double* g, int M, int gs, float c)
+{
+    int k = searchsorted_left(g, M, gs, (double)c);
+    if (k > M - 1) k = M - 1;
+    const bool upper = k > 0 && (double)c > 0.5 * (g[(long)(k - 1) * gs] + g[(long)k * gs]);
+    return 2 * k + (upper ? 1 : 0);
+}
 SOLAT_HD int ff_pred_row_keep(const FfPred& p, const float* stf, float cpf, float spf, const FfGrid& G, bool need_pos, bool need_neg,
-                              float dz_neg_cm, int lo, int hi, int* out_lo, int* out_cnt)
+                              float dz_neg_cm, int lo, int hi, int* out_lo, int* out_cnt, const FfPile* pile = nullptr)
 {
     for (int k = 0; k < FF_ROW_K; k++) { out_lo[k] = lo; out_cnt[k] = 0; }
     if (hi <= lo) return 0;
@@ -1348,28 +1372,96 @@ SOLAT_HD int ff_pred_row_keep(const FfPred& p, const float* stf, float cpf, floa
     }
     for (int a = 1; a < 8; a++)                   // sort the eight cut points
         for (int b = a; b > 0 && cut[b] < cut[b - 1]; b--) { const int t = cut[b]; cut[b] = cut[b - 1]; cut[b - 1] = t; }
-    int n = 0, run = -1, cand_pos = -1, cand_neg = -1;
+    // bounding sub-range [a, b) of the rays of the pile-only segment [i0, i1) that may still win a cell of pile line
+    // `line` of table t (see FfPile): the cells the segment can reach are scanned for "open" ones (no scout later than
+    // the segment's last ray), and the rays whose +-margin window touches the span of the open cells are kept
+    auto shrink = [&](int i0, int i1, int t, int line, int& a, int& b) {
+        const float eps = 1e-3f;
+        auto coord = [&](int i) {
+            const float s = stf[i] * FF_PRED_SCALE;
+            const float x = 0.1f * fmaf(fmaf(fmaf(ax[3], s, ax[2]), s, ax[1]), s, ax[0]);
+            const float z = 0.1f * fmaf(fmaf(fmaf(az[3], s, az[2]), s, az[1]), s, az[0]);
+            return line == 0 ? (t ? z + dz_neg_cm : z) : (t ? -x : x);
+        };
+        const double* g = line == 0 ? G.gy : G.gx;
+        const int gs = line == 0 ? G.gy_rs : 1, M = G.M;
+        const float c0 = coord(i0), c1 = coord(i1 - 1);
+        const float cmin = fminf(c0, c1) - m - eps, cmax = fmaxf(c0, c1) + m + eps;
+        a = b = i0;
+        if (!(cmin <= (float)g[(long)(M - 1) * gs]) || !(c0 == c0) || !(c1 == c1)) {
+            if (!(c0 == c0) || !(c1 == c1)) { a = i0; b = i1; }                 // NaN prediction: keep
+            return;                                                           // all beyond the last value: no cell at all
+        }
+        const int ka = searchsorted_left(g, M, gs, (double)cmin);
+        int kb = searchsorted_left(g, M, gs, (double)cmax);
+        if (kb > M - 1) kb = M - 1;
+        const int* L = pile->L + (2 * t + line) * M;
+        const int top = (t ? pile->nph - 1 - pile->j : pile->j) * pile->nth + i1;     // (index of the segment's last ray) + 1
+        int k_lo = -1, k_hi = -1;
+        for (int k = ka; k <= kb; k++)
+            if (L[k] <= top) { if (k_lo < 0) k_lo = k; k_hi = k; }            // open: its scout is not later than the segment
+        if (k_lo < 0) return;
+        const float lo_edge = k_lo == 0 ? -3.0e38f : (float)g[(long)(k_lo - 1) * gs] - m - eps, hi_edge = (float)g[(long)k_hi * gs] + m + eps;
+        // coord is monotone along the segment: the rays with lo_edge < coord <= hi_edge form one range
+        const bool inc = c1 >= c0;
+        auto first_true = [&](auto&& pred) {                                  // pred: false ... false true ... true on [i0, i1)
+            int u = i0, v = i1;                                               // answer in [u, v]
+            while (u < v) {
+                const int mid = (u + v) >> 1;
+                if (pred(mid)) v = mid; else u = mid + 1;
+            }
+            return u;
+        };
+        if (inc) {
+            a = first_true([&](int i) { return coord(i) > lo_edge; });
+            b = first_true([&](int i) { return coord(i) > hi_edge; });
+        } else {
+            a = first_true([&](int i) { return coord(i) <= hi_edge; });
+            b = first_true([&](int i) { return coord(i) <= lo_edge; });
+        }
+        if (b < a) b = a;
+    };
+    int n = 0, run = -1, run_end = -1, cand_pos = -1, cand_neg = -1;
     bool overflow = false;
+    auto flush_run = [&]() {
+        if (run >= 0) {
+            if (n < FF_ROW_K) { out_lo[n] = run; out_cnt[n] = run_end - run; }
+            ++n; run = -1;
+        }
+    };
     for (int sgm = 0; sgm < 7; sgm++) {
         const int i0 = cut[sgm], i1 = cut[sgm + 1];
         if (i1 <= i0) continue;
-        const bool beyond_z = test(i0, 2), corner_z = test(i0, 5);
-        const bool pos_corner = need_pos && test(i0, 3) && corner_z, neg_corner = need_neg && test(i0, 4) && corner_z;
+        const bool beyond_z = test(i0, 2), below = test(i0, 5);
+        const bool left_p = test(i0, 3), left_n = test(i0, 4);
+        const bool pos_corner = need_pos && left_p && below, neg_corner = need_neg && left_n && below;
         const bool pos_use = need_pos && !test(i0, 0) && !beyond_z && !pos_corner;
         const bool neg_use = need_neg && !test(i0, 1) && !beyond_z && !neg_corner;
         if (pos_corner) cand_pos = i1 - 1;
         if (neg_corner) cand_neg = i1 - 1;
-        if (pos_use || neg_use) {
-            if (run < 0) run = i0;
-        } else if (run >= 0) {
-            if (n < FF_ROW_K) { out_lo[n] = run; out_cnt[n] = i0 - run; }
-            ++n; run = -1;
+        int pa = i0, pb = (pos_use || neg_use) ? i1 : i0;                     // the piece of this segment that is kept
+        if (pile && pb > pa) {
+            const bool pos_in = pos_use && !left_p && !below, neg_in = neg_use && !left_n && !below;
+            if (!pos_in && !neg_in) {                                         // pile rays only: keep what may still win
+                int ua = i1, ub = i0;
+                for (int t = 0; t < 2; t++) {
+                    if (!(t ? neg_use : pos_use)) continue;
+                    int a, b;
+                    shrink(i0, i1, t, (t ? left_n : left_p) ? 0 : 1, a, b);
+                    if (b > a) { ua = a < ua ? a : ua; ub = b > ub ? b : ub; }
+                }
+                pa = ua; pb = ub;
+                if (pb <= pa) { pa = i0; pb = i0; }
+            }
+        }
+        if (pb > pa) {
+            if (run >= 0 && pa == run_end) run_end = pb;                      // joins the run
+            else { flush_run(); run = pa; run_end = pb; }
+        } else {
+            flush_run();
         }
     }
-    if (run >= 0) {
-        if (n < FF_ROW_K) { out_lo[n] = run; out_cnt[n] = hi - run; }
-        ++n;
-    }
+    flush_run();
     // the corner candidates, unless a kept run holds them already
     for (int c = 0; c < 2; c++) {
         const int i = c ? cand_neg : cand_pos;
@@ -1381,6 +1473,8 @@ SOLAT_HD int ff_pred_row_keep(const FfPred& p, const float* stf, float cpf, floa
         ++n;
     }
     overflow = n > FF_ROW_K;
+    if (overflow && pile)                      // the shrunk pieces do not fit: the row as it is without pile information
+        return ff_pred_row_keep(p, stf, cpf, spf, G, need_pos, need_neg, dz_neg_cm, lo, hi, out_lo, out_cnt, nullptr);
     if (overflow) {
         out_lo[0] = lo; out_cnt[0] = hi - lo;
         for (int k = 1; k < FF_ROW_K; k++) { out_lo[k] = lo; out_cnt[k] = 0; }

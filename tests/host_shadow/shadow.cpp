@@ -384,7 +384,7 @@ API int shadow_ff_pred_check(const double* geo, const double* th, int nth, const
 // winner tables (ray index per cell) of the pixel and of its mirror pixel from the kept rays only must equal the
 // tables from all rays.  E_rec axes: M points on [g_lo, g_hi] cm.  out: accepted rays, kept rays, cells that differ.
 API int shadow_ff_keep_check(const double* geo, const double* th, int nth, const double* ph, int nph, double el, double az, int M,
-                             double g_lo, double g_hi, int need_pos, int need_neg, double* out3)
+                             double g_lo, double g_hi, int need_pos, int need_neg, double* out3, int pile_min)
 {
     FfGeom g = unpack(geo);
     FfFrames f;
@@ -438,21 +438,113 @@ API int shadow_ff_keep_check(const double* geo, const double* th, int nth, const
     }
     std::vector<char> keep(nth * (size_t)nph, 0);
     long n_kept = 0;
-    for (int j = 0; j < nph; j++) {
-        int klo[FF_ROW_K], kcnt[FF_ROW_K];
-        if (p.on) {
-            ff_pred_row_keep(p, stf.data(), (float)cos(ph[j]), (float)sin(ph[j]), G, need_pos != 0, need_neg != 0,
-                             0.1f * (float)(f.centre[2] - f.centre_mz), lo[j], hi[j], klo, kcnt);
-        } else {
-            for (int k = 0; k < FF_ROW_K; k++) { klo[k] = lo[j]; kcnt[k] = 0; }
-            kcnt[0] = hi[j] - lo[j];
+    const float dz_m = 0.1f * (float)(f.centre[2] - f.centre_mz);
+    std::vector<int> KLO((size_t)nph * FF_ROW_K), KCNT((size_t)nph * FF_ROW_K);
+    auto keep_pass = [&](const FfPile* pile_in) {
+        n_kept = 0;
+        for (int j = 0; j < nph; j++) {
+            int* klo = &KLO[(size_t)j * FF_ROW_K];
+            int* kcnt = &KCNT[(size_t)j * FF_ROW_K];
+            if (p.on) {
+                FfPile pl;
+                if (pile_in) { pl = *pile_in; pl.j = j; }
+                ff_pred_row_keep(p, stf.data(), (float)cos(ph[j]), (float)sin(ph[j]), G, need_pos != 0, need_neg != 0, dz_m, lo[j], hi[j], klo,
+                                 kcnt, pile_in ? &pl : nullptr);
+            } else {
+                for (int k = 0; k < FF_ROW_K; k++) { klo[k] = lo[j]; kcnt[k] = 0; }
+                kcnt[0] = hi[j] - lo[j];
+            }
+            for (int k = 0; k < FF_ROW_K; k++) n_kept += kcnt[k];
         }
-        for (int k = 0; k < FF_ROW_K; k++)
-            for (int i = klo[k]; i < klo[k] + kcnt[k]; i++) {
+    };
+    keep_pass(nullptr);
+    std::vector<int> L2v(4 * (size_t)M, 0);
+    if (p.on && pile_min >= 0 && n_kept >= pile_min) {
+        // the scout stage exactly as ff_prep_kernel runs it
+        std::vector<int> scout(8 * (size_t)M, 0), L1(4 * (size_t)M, 0), sc(16 * (size_t)M, -1);
+        const float mg = p.margin_cm;
+        const float x_lo = (float)G.gx_min - mg, z_lo = (float)G.gy_min - mg, x_hi = (float)G.gx_max + mg, z_hi = (float)G.gy_max + mg;
+        auto pile_line = [&](float X, float Z, float& c) {
+            if (X > x_hi || Z > z_hi) return -1;
+            const bool left = X < x_lo, below = Z < z_lo;
+            if (left == below) return -1;
+            c = left ? Z : X;
+            return left ? 0 : 1;
+        };
+        for (int j = 0; j < nph; j++) {
+            float ax[4], az[4];
+            ff_pred_row_cubic(p.cx, (float)cos(ph[j]), (float)sin(ph[j]), ax);
+            ff_pred_row_cubic(p.cz, (float)cos(ph[j]), (float)sin(ph[j]), az);
+            for (int k = 0; k < FF_ROW_K; k++) {
+                const int l0 = KLO[(size_t)j * FF_ROW_K + k], cnt = KCNT[(size_t)j * FF_ROW_K + k];
+                for (int i = l0 + cnt - 1; i >= l0; i -= FF_SCOUT_STEP) {
+                    const float sf = stf[i] * FF_PRED_SCALE;
+                    const float X = 0.1f * fmaf(fmaf(fmaf(ax[3], sf, ax[2]), sf, ax[1]), sf, ax[0]);
+                    const float Z = 0.1f * fmaf(fmaf(fmaf(az[3], sf, az[2]), sf, az[1]), sf, az[0]);
+                    float c;
+                    if (need_pos) {
+                        const int line = pile_line(X, Z, c);
+                        if (line >= 0) {
+                            int& s = scout[(size_t)line * 2 * M + ff_pile_slot(line ? G.gx : G.gy, M, line ? 1 : G.gy_rs, c)];
+                            s = std::max(s, j * nth + i + 1);
+                        }
+                    }
+                    if (need_neg) {
+                        const int line = pile_line(-X, Z + dz_m, c);
+                        if (line >= 0) {
+                            int& s = scout[(size_t)(2 + line) * 2 * M + ff_pile_slot(line ? G.gx : G.gy, M, line ? 1 : G.gy_rs, c)];
+                            s = std::max(s, (nph - 1 - j) * nth + i + 1);
+                        }
+                    }
+                }
+            }
+        }
+        auto scout_ray = [&](int e, int& i, int& j) {
+            const int sidx = scout[e] - 1;
+            j = sidx / nth; i = sidx - j * nth;
+            if (e >= 4 * M) j = nph - 1 - j;
+        };
+        auto landings = [&](int cp, int cn, int i, int j, std::vector<int>& L) {
+            if (cp >= 0) {
+                if (cp % M == 0) L[0 * M + cp / M] = std::max(L[0 * M + cp / M], j * nth + i + 1);
+                if (cp / M == 0) L[1 * M + cp % M] = std::max(L[1 * M + cp % M], j * nth + i + 1);
+            }
+            if (cn >= 0) {
+                if (cn % M == 0) L[2 * M + cn / M] = std::max(L[2 * M + cn / M], (nph - 1 - j) * nth + i + 1);
+                if (cn / M == 0) L[3 * M + cn % M] = std::max(L[3 * M + cn % M], (nph - 1 - j) * nth + i + 1);
+            }
+        };
+        for (int e = 0; e < 8 * M; e++) {
+            if (scout[e] <= 0) continue;
+            int i, j;
+            scout_ray(e, i, j);
+            const Hit h = trace(j * nth + i);
+            if (need_pos) sc[e] = ff_cell(h.X, h.Z, G);
+            if (need_neg) sc[8 * M + e] = ff_cell(-h.X, h.Zm, G);
+            landings(sc[e], sc[8 * M + e], i, j, L1);
+        }
+        for (int e = 0; e < 8 * M; e++) {
+            if (scout[e] <= 0) continue;
+            const int t = e / (4 * M), line = (e / (2 * M)) & 1, cell = sc[(size_t)t * 8 * M + e];
+            if (cell < 0 || (line == 0 ? cell % M != 0 : cell / M != 0)) continue;
+            if (L1[(size_t)(2 * t + line) * M + (line == 0 ? cell / M : cell % M)] != scout[e]) continue;
+            int i, j;
+            scout_ray(e, i, j);
+            landings(sc[e], sc[8 * M + e], i, j, L2v);
+        }
+        FfPile pile;
+        pile.L = L2v.data(); pile.nth = nth; pile.nph = nph; pile.j = 0;
+        keep_pass(&pile);
+    }
+    n_kept = 0;
+    for (int j = 0; j < nph; j++)
+        for (int k = 0; k < FF_ROW_K; k++) {
+            const int kl = KLO[(size_t)j * FF_ROW_K + k], kc = KCNT[(size_t)j * FF_ROW_K + k];
+            for (int i = kl; i < kl + kc; i++) {
                 if (i < lo[j] || i >= hi[j] || keep[(size_t)j * nth + i]) return -1;      // outside the row or twice
                 keep[(size_t)j * nth + i] = 1; ++n_kept;
             }
-    }
+        }
     std::vector<int> wp_all(M * M, -1), wn_all(M * M, -1), wp_k(M * M, -1), wn_k(M * M, -1);
     for (int r : rays) {
         const int i = r % nth, j = r / nth, rm = (nph - 1 - j) * nth + i;

@@ -123,12 +123,13 @@ def ff_pred_check(geo, th, ph, el, az, gx_max, gy_max):
     return nv, o[0], o[1], int(o[2]), int(o[3])
 
 
-def ff_keep_check(geo, th, ph, el, az, m, g_lo, g_hi, need_pos=True, need_neg=True):
-    """-> (predictor on, accepted rays, kept rays, winner-table cells that differ between kept-only and all rays)"""
+def ff_keep_check(geo, th, ph, el, az, m, g_lo, g_hi, need_pos=True, need_neg=True, pile_min=-1):
+    """-> (predictor on, accepted rays, kept rays, winner-table cells that differ between kept-only and all rays).
+    pile_min >= 0: items that list at least that many rays also go through the scout stage (pile shrinking)."""
     g, gp = D(geo); th, thp = D(th); ph, php = D(ph)
     o = np.zeros(3)
     on = lib().shadow_ff_keep_check(gp, thp, ci(th.size), php, ci(ph.size), cd(el), cd(az), ci(m), cd(g_lo), cd(g_hi),
-                                    ci(int(need_pos)), ci(int(need_neg)), o.ctypes.data_as(dp))
+                                    ci(int(need_pos)), ci(int(need_neg)), o.ctypes.data_as(dp), ci(int(pile_min)))
     return on, int(o[0]), int(o[1]), int(o[2])
 
 

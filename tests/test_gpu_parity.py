@@ -904,6 +904,13 @@ def test_ff_config5_stratified_pixels_against_oracle(oracle):
     assert st == 0
     oa, op = oracle.ff_map(oracle.ff_geo_vec(rx_y_m=-bench.OFFSET), px[idx], th, phi, x, y, e, tg.k)
     _assert_pixels(amp, ph, oa, op)
+    # the scout stage (pile rays that cannot win are dropped from the list) must not change a bit
+    os.environ["SOLAT_FF_PILE"] = "0"
+    try:
+        a0, p0, st = maps.FarFieldPlan(tg, th, phi, x, y, e, device=0).run(px[idx[::7]])
+    finally:
+        del os.environ["SOLAT_FF_PILE"]
+    np.testing.assert_array_equal(a0, amp[::7]); np.testing.assert_array_equal(p0, ph[::7])
     # a pixel's value does not depend on the list it comes in: the same pixels inside a longer list, other order
     more = np.r_[px[idx[::-1]], px[1000:1010]]
     a2, p2, st = plan.run(more)

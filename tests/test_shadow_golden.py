@@ -274,7 +274,21 @@ def test_ff_ray_selection_keeps_every_winner(shadow, oracle):
                     assert 0 < n_kept <= n_acc
                     if (m, g_lo) == (51, -5.0) and need_pos and need_neg and n == 100:
                         saved = max(saved, n_acc - n_kept)
-    assert saved > 2000          # the +-5 cm grid of ff_sim.py: a pair needs ~3400 of its 6000 accepted rays
+    assert saved > 2000          # the +-5 cm grid of ff_sim.py: a pair needs ~3100 of its 6000 accepted rays
+    # large fans also go through the scout stage (FfPile: pile rays that a later, listed scout beats in every cell they
+    # could reach are dropped): same winner tables, far fewer rays
+    for n, cases in ((400, [(0.0, gu.EL0), (20 * gu.DE, gu.EL0 - 20 * gu.DE), (3e-3, -2e-3), (-11 * gu.DE, gu.EL0 + 7 * gu.DE)]),
+                     (1000, [(5 * gu.DE, gu.EL0 - 3 * gu.DE)])):
+        th, phi = gu.ff_fan(n)
+        for az, el in cases:
+            for m, g_lo, g_hi in [(101, -5.0, 5.0), (51, -5.0, 5.0), (21, -12.0, 3.0), (61, -30.0, 30.0)] if n == 400 else [(101, -5.0, 5.0)]:
+                for need_pos, need_neg in [(True, True), (True, False), (False, True)]:
+                    plain = shadow.ff_keep_check(geo, th, phi, el, az, m, g_lo, g_hi, need_pos, need_neg)
+                    on, n_acc, n_kept, diff = shadow.ff_keep_check(geo, th, phi, el, az, m, g_lo, g_hi, need_pos, need_neg, pile_min=0)
+                    assert on == 1 and diff == 0, (n, az, m, g_lo, need_pos, need_neg, n_acc, n_kept, diff)
+                    assert 0 < n_kept <= plain[2]
+                    if (m, g_lo) == (101, -5.0) and need_pos and need_neg and abs(az) < 1e-3:
+                        assert n_kept < 0.75 * plain[2]
 
 
 def _flip_cols(rows, nth, nph, flip_th, flip_ph):
