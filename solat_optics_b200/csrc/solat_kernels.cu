@@ -1098,7 +1098,7 @@ __device__ __forceinline__ void ff_prefix_rows(int* row_pre, int nph, int lane)
 // interval walk the per-row ray intervals (aperture, then ff_pred_row_keep), as a record in global
 // memory the map kernel copies into its shared memory.  Record: FfFrames | int queue_walk, n_list, pad[2] |
 // row_lo[K nph] | row_pre[K nph + 1]  (K = FF_ROW_K intervals per phi row: virtual row K j + k).
-constexpr int FF_PREP_T = 64;     // = FF_PRED_SAMPLES; 12 CTAs per SM keep every pixel of a 41 x 41 map in flight
+constexpr int FF_PREP_T = 64;     // = FF_PRED_SAMPLES; 6 CTAs per SM (164 registers, no spills) keep every pixel of a 41 x 41 map in flight
 constexpr int FF_PREP_T_BIG = 256; // fans of at least FF_PILE_MIN rays
 constexpr size_t FF_REC_FRAMES = ((sizeof(FfFrames) + 15) / 16) * 16;
 constexpr size_t FF_REC_HEAD = FF_REC_FRAMES + 16;
@@ -1121,7 +1121,7 @@ static size_t ff_rec_stride(int rows_nph) { return FF_REC_HEAD + (rows_nph ? ((2
 // T = 64 (FF_PREP_T): the small items of reference-sized maps, all in flight at once; T = 256 (FF_PREP_T_BIG): items of
 // large fans, where the scout stage scans hundreds of thousands of listed rays per item.
 template <int T>
-__global__ void __launch_bounds__(T, T == 64 ? 12 : 3) ff_prep_kernel(FfPrepParams q)
+__global__ void __launch_bounds__(T, T == 64 ? 6 : 3) ff_prep_kernel(FfPrepParams q)
 {
     constexpr int FF_T = T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1239,7 +1239,7 @@ __global__ void __launch_bounds__(T, T == 64 ? 12 : 3) ff_prep_kernel(FfPrepPara
                 if (warp == 0) ff_prefix_rows(row_pre, nvr, lane);
                 __syncthreads();
                 // ---- pile shrinking (FfPile): scouts, their exact landings, second pass over the rows
-                if (q.pile && row_pre[nvr] >= FF_PILE_MIN) {
+                if (T != FF_PREP_T && q.pile && row_pre[nvr] >= FF_PILE_MIN) {   // (compiled into the large-fan variant only)
                     const int M = q.grid.M, nph = q.ang.nph;
                     int* scout = row_pre + nvr + 1;                      // [2 tables][2 lines][2 M] latest ray predicted into the half cell
                     int* L1 = scout + 8 * M;                             // [2][2][M] latest scout that landed in the cell
