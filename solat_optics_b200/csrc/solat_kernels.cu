@@ -1273,12 +1273,12 @@ __global__ void __launch_bounds__(T, T == 64 ? 6 : 3) ff_prep_kernel(FfPrepParam
                                 if (need_pos) {
                                     const int line = pile_line(X, Z, c);
                                     if (line >= 0)
-                                        atomicMax(scout + line * 2 * M + ff_pile_slot(line ? q.grid.gx : q.grid.gy, M, line ? 1 : q.grid.gy_rs, c), j * nth + i + 1);
+                                        atomicMax(scout + line * 2 * M + ff_pile_slot(q.grid, line, c), j * nth + i + 1);
                                 }
                                 if (need_neg) {
                                     const int line = pile_line(-X, Z + dz_m, c);
                                     if (line >= 0)
-                                        atomicMax(scout + (2 + line) * 2 * M + ff_pile_slot(line ? q.grid.gx : q.grid.gy, M, line ? 1 : q.grid.gy_rs, c),
+                                        atomicMax(scout + (2 + line) * 2 * M + ff_pile_slot(q.grid, line, c),
                                                   (nph - 1 - j) * nth + i + 1);
                                 }
                             }

@@ -1308,9 +1308,18 @@ struct FfPile {
 };
 constexpr int FF_PILE_MIN = 20000;     // listed rays per work item from which the scouts pay (a 100 x 100 fan lists ~3000)
 constexpr int FF_SCOUT_STEP = 4;       // every n-th listed ray of a row interval (from its last ray down) is offered as a scout
-// half-cell slot [0, 2M) of a pile coordinate c [cm] on an axis g (M values, stride gs)
-SOLAT_HD int ff_pile_slot(const double* g, int M, int gs, float c)
+// half-cell slot [0, 2M) of a pile coordinate c [cm] on pile line `line` (0: the y axis, 1: the x axis).  Only a
+// bucket for choosing scouts: arithmetic on a uniform axis (first-guess step known), binary search otherwise.
+SOLAT_HD int ff_pile_slot(const FfGrid& G, int line, float c)
 {
+    const int M = G.M;
+    const float inv = line ? G.inv_dx : G.inv_dy;
+    if (inv > 0.0f) {
+        const float h = floorf((c - (float)(line ? G.gx_min : G.gy_min)) * inv * 2.0f) + 1.0f;
+        return h < 0.0f ? 0 : (h > (float)(2 * M - 1) ? 2 * M - 1 : (int)h);
+    }
+    const double* g = line ? G.gx : G.gy;
+    const int gs = line ? 1 : G.gy_rs;
     int k = searchsorted_left(g, M, gs, (double)c);
     if (k > M - 1) k = M - 1;
     const bool upper = k > 0 && (double)c > 0.5 * (g[(long)(k - 1) * gs] + g[(long)k * gs]);

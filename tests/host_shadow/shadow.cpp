@@ -485,14 +485,14 @@ API int shadow_ff_keep_check(const double* geo, const double* th, int nth, const
                     if (need_pos) {
                         const int line = pile_line(X, Z, c);
                         if (line >= 0) {
-                            int& s = scout[(size_t)line * 2 * M + ff_pile_slot(line ? G.gx : G.gy, M, line ? 1 : G.gy_rs, c)];
+                            int& s = scout[(size_t)line * 2 * M + ff_pile_slot(G, line, c)];
                             s = std::max(s, j * nth + i + 1);
                         }
                     }
                     if (need_neg) {
                         const int line = pile_line(-X, Z + dz_m, c);
                         if (line >= 0) {
-                            int& s = scout[(size_t)(2 + line) * 2 * M + ff_pile_slot(line ? G.gx : G.gy, M, line ? 1 : G.gy_rs, c)];
+                            int& s = scout[(size_t)(2 + line) * 2 * M + ff_pile_slot(G, line, c)];
                             s = std::max(s, (nph - 1 - j) * nth + i + 1);
                         }
                     }
