@@ -1064,6 +1064,12 @@ struct FfMapParams {
     int np1, np2;
     PanelLayoutDev lay1, lay2;
     unsigned long long* win_g;   // winner tables in global memory, [CTAs of the launch][tables][M * M]; nullptr: shared memory
+    // large fans (ff_map_interp_kernel): cells from interpolated focal positions, exact traces for the winners only
+    int interp_s;                // lattice spacing in rays (both fan axes)
+    double th0, dth, ph0, dph;   // the fan's axes are uniform: theta_i = th0 + i dth, phi_j = ph0 + j dph (lattice nodes beyond the fan)
+    double interp_eps, interp_chk;   // [cm] a ray closer than eps to a cell edge is traced exactly; winners must match their prediction to chk
+    int* redo;                   // [CTAs of the launch] interp kernel: 1 = prediction check failed, the exact kernel redoes the item;
+                                 // exact kernel: when set, only the flagged CTAs run
 };
 
 __device__ __forceinline__ PanelErr load_panel(const double* pan, int np, int col)
@@ -1383,7 +1389,13 @@ __global__ void __launch_bounds__(T, T == 64 ? 6 : 3) ff_prep_kernel(FfPrepParam
 //   * PANEL (adjuster-error studies, ff_sim.py:61-70 with non-zero offsets): every ray carries the panel-model
 //     columns the host derived with pan_mod.identify_panel; rays on no panel are dropped (saf:626-628,805-809), the
 //     others see their panels' error polynomials inside both Newton solves.
-template <int PANEL, int T, int MINB>
+//   * LEAN (plain maps whose winner tables sit in shared memory and whose E_rec axes are sorted, near-uniform and
+//     shared by all columns -- every grid ff_sim.py builds): the binning of a ray runs on shared-memory addresses
+//     only (the generic version pays for pointers that may be global: LD.E / ATOM.E + QSPC), finds its cell with a
+//     branch-free searchsorted (interpolated guess, exact +-1 correction against the staged axis, sentinels at both
+//     ends), tests "a later ray holds the cell" on the high word of the key alone, and raises the key with a CAS loop
+//     seeded by nothing but that read.  Same cells, same keys, same maps; a third fewer instructions per traced ray.
+template <int PANEL, int T, int MINB, bool LEAN = false>
 __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
 {
     constexpr int FF_T = T, FF_WARPS = T / 32;
@@ -1393,19 +1405,21 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     // winner table(s): in shared memory, or -- E_rec grids too large for that (M > 168) -- this CTA's slice of a
     // global scratch buffer (L2 resident: 64-bit atomicMax on global memory, slower but unbounded)
     unsigned long long* win_s = reinterpret_cast<unsigned long long*>(smem_raw + ((sizeof(FfFrames) + 15) / 16) * 16);
-    unsigned long long* win = q.win_g ? q.win_g + (size_t)blockIdx.x * (q.items ? 2 : 1) * cells : win_s;
+    unsigned long long* win = (!LEAN && q.win_g) ? q.win_g + (size_t)blockIdx.x * (q.items ? 2 : 1) * cells : win_s;
     unsigned long long* win_m = win + cells;                    // pair mode: winner table of the mirror pixel (-az, el)
-    int* queues = reinterpret_cast<int*>(win_s + (q.win_g ? 0 : (q.items ? 2 : 1) * cells));   // [FF_WARPS][FF_WQ]
-    double* s_gx = reinterpret_cast<double*>(queues + FF_WARPS * FF_WQ);   // [M] data_x[0, :]
-    double* s_gy = s_gx + q.grid.M;                                        // [M] data_y[:, 0] when all columns agree
+    int* queues = reinterpret_cast<int*>(win_s + ((!LEAN && q.win_g) ? 0 : (q.items ? 2 : 1) * cells));   // [FF_WARPS][FF_WQ]
+    // grid axes on chip, one sentinel either side (LEAN: -inf below, +inf above)
+    double* s_gx = reinterpret_cast<double*>(queues + FF_WARPS * FF_WQ) + 1;   // [-1 .. M] data_x[0, :]
+    double* s_gy = s_gx + q.grid.M + 2;                                    // [-1 .. M] data_y[:, 0] when all columns agree
     const int nvr = FF_ROW_K * q.ang.nph;                                  // virtual rows: FF_ROW_K intervals per phi row
-    int* row_lo = reinterpret_cast<int*>(s_gy + q.grid.M);                 // [nvr] first ray to trace of an interval
+    int* row_lo = reinterpret_cast<int*>(s_gy + q.grid.M + 1);             // [nvr] first ray to trace of an interval
     int* row_pre = row_lo + (q.rows ? nvr : 0);                            // [nvr + 1] rays to trace before the interval
     __shared__ int s_queue_walk;
     __shared__ double s_t2e[9];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
     if (q.items && q.item0 + pix >= __ldg(q.counters)) return;   // pair mode launches one CTA per pixel, items are fewer
+    if (q.redo && q.redo[pix] == 0) return;                      // second pass behind ff_map_interp_kernel: flagged items only
     const int out_pos = q.items ? q.items[q.item0 + pix].pos : pix, out_neg = q.items ? q.items[q.item0 + pix].neg : -1;
     const FfGeom g = to_geom(q.g);
     const Coef& sC = K_COEF;   // constant bank; a shared-memory copy measured 4 % slower (profiles/r01_variants.md)
@@ -1425,6 +1439,10 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     for (int i = tid; i < grid.M; i += FF_T) {
         s_gx[i] = __ldg(q.grid.gx + i);
         if (grid.y_uniform) s_gy[i] = __ldg(q.grid.gy + (size_t)i * grid.M);
+    }
+    if (LEAN && tid < 4) {
+        const double inf = __longlong_as_double(0x7ff0000000000000ll);
+        (tid & 2 ? s_gy : s_gx)[tid & 1 ? grid.M : -1] = tid & 1 ? inf : -inf;
     }
     grid.gx = s_gx;
     if (grid.y_uniform) { grid.gy = s_gy; grid.gy_cs = 0; grid.gy_rs = 1; }
@@ -1487,6 +1505,42 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             }
         }
     };
+    // the same on shared-memory addresses only (LEAN, see above)
+    const float lean_nf = (float)grid.M;
+    const int kh_shift = q.key_shift - 32;                  // the ray index sits in the high word of a key (shift 40 or 44)
+    auto lean_cell = [&](double xx, double yy, const unsigned long long* tab, unsigned rkey) __attribute__((always_inline)) {
+        if (!(xx <= grid.gx_max && yy <= grid.gy_max)) return -1;                  // ffl:19
+        const int ix = searchsorted_lean(s_gx, lean_nf, xx, grid.gx_min, grid.inv_dx);   // ffl:22
+        const int iy = searchsorted_lean(s_gy, lean_nf, yy, grid.gy_min, grid.inv_dy);   // ffl:23
+        const int cell = iy * grid.M + ix;
+        // a later ray holds the cell already: its key's high word is at least this ray's (equal: never, one ray per table)
+        const unsigned held = reinterpret_cast<const volatile unsigned*>(tab)[2 * cell + 1];
+        return held >= rkey ? -1 : cell;
+    };
+    auto lean_raise = [&](unsigned long long* cellp, unsigned long long key) __attribute__((always_inline)) {
+        unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(cellp);
+        while (old < key) {                                                        // ffl:28: the later ray wins
+            const unsigned long long prev = atomicCAS(cellp, old, key);
+            if (prev == old) break;
+            old = prev;
+        }
+    };
+    auto bin_lean = [&](int i, int j, double opl, double fx, double fz) __attribute__((always_inline)) {
+        if (opl == 0.0 || not_finite(opl) || not_finite(fx) || not_finite(fz)) return;      // ffl:10
+        const unsigned r0 = (unsigned)(j * nth + i + 1), rm = (unsigned)((q.ang.nph - 1 - j) * nth + i + 1);
+        const double xx = div10(fx - cx);                                           // ffl:12-13
+        int cell = -1, cell_m = -1;
+        if (out_pos >= 0) cell = lean_cell(xx, div10(fz - cz), win_s, r0 << kh_shift);
+        // the mirror pixel (-az, el): this ray is its ray (nph-1-j, i) and lands at (-x, z) about its own centre
+        if (out_neg >= 0) cell_m = lean_cell(-xx, div10(fz - fr->centre_mz), win_s + cells, rm << kh_shift);
+        if ((cell & cell_m) >= 0) {
+            bool exact;
+            const unsigned long long low = ff_key(-1, opl, q.key_base, q.key_inv_unit, exact, q.key_unit, q.key_shift);   // ray bits 0
+            if (!exact) st |= ST_RANGE;
+            if (cell >= 0) lean_raise(win_s + cell, low | ((unsigned long long)r0 << q.key_shift));
+            if (cell_m >= 0) lean_raise(win_s + cells + cell_m, low | ((unsigned long long)rm << q.key_shift));
+        }
+    };
     // trace ray (i, j) and bin it
     auto trace = [&](int i, int j) __attribute__((always_inline)) {
         const double2 tsc = __ldg(q.ang.tsc + i), psc = __ldg(q.ang.psc + j);
@@ -1520,7 +1574,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);
         }
         st |= rst;
-        bin(i, j, opl, fx, fz);
+        if (LEAN) bin_lean(i, j, opl, fx, fz); else bin(i, j, opl, fx, fz);
     };
     if (PANEL == 0 && !queue_walk) {
         // interval walk, the hot loop of the plain map on its own (no queue state alive): 32 rays of the warp's share of
@@ -1591,7 +1645,8 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
     for (int side = 0; side < 2; side++) {
         const int out = side ? out_neg : out_pos;
         if (out < 0) continue;                                  // CTA-uniform
-        const unsigned long long* tab = side ? win_m : win;
+        const unsigned long long* tab = LEAN ? win_s + (side ? cells : 0) : (side ? win_m : win);
+        const bool tab_g = !LEAN && q.win_g;
         double re[1] = {0.0}, im[1] = {0.0};
         cnt = 0;
         for (int c0 = warp * 32;; c0 += FF_WARPS * 32) {
@@ -1599,7 +1654,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
             if (more) {
                 const int c = c0 + lane;
                 // (a table in global memory was updated with atomics at L2: read it there, not through a stale L1 line)
-                const bool has = c < cells && (q.win_g ? __ldcg(tab + c) : tab[c]) != 0ull;
+                const bool has = c < cells && (tab_g ? __ldcg(tab + c) : tab[c]) != 0ull;
                 const unsigned m = __ballot_sync(0xffffffffu, has);
                 if (has) wq[cnt + __popc(m & ((1u << lane) - 1u))] = c;
                 cnt += __popc(m);
@@ -1612,7 +1667,7 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
                 __syncwarp();
                 if (c >= 0) {
                     double cs, sn;
-                    cis_large(q.k * ff_key_opl(q.win_g ? __ldcg(tab + c) : tab[c], q.key_base, q.key_unit, q.key_shift) / 1e3, cs, sn);
+                    cis_large(q.k * ff_key_opl(tab_g ? __ldcg(tab + c) : tab[c], q.key_base, q.key_unit, q.key_shift) / 1e3, cs, sn);
                     const double2 e = __ldg(q.e_rec + c);
                     re[0] += cs * e.x - sn * e.y;
                     im[0] += cs * e.y + sn * e.x;
@@ -1629,6 +1684,332 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
         }
         __syncthreads();                                        // `total` and the reduction scratch are reused
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Large fans: the cells come from INTERPOLATED focal positions, only the winners are traced exactly.
+//
+// The reference keeps, per E_rec cell, the last ray that lands in it (ffl:22-28): of the ~177 000 rays a config-5 pair
+// item lists, at most 2 x 101^2 = 20 402 count.  Which cell a ray lands in is a smooth function of its fan indices
+// (i, j): cubic interpolation between exactly traced rays 16 apart is good to 2e-4 mm (measured against the oracle
+// on a 1000^2 fan) against cells of 1 mm.  So:
+//   1a  the CTA traces a lattice of rays, every S-th in both fan directions (one ring beyond the fan on either side,
+//       so that every ray has a full 4 x 4 stencil; the fan's axes are uniform, the host checks it): 66^2 rays;
+//   1b  a warp takes a phi row: row nodes by cubic interpolation across the four lattice rows around it, then, for
+//       every LISTED ray of the row (the intervals ff_prep_kernel left), the focal position by cubic interpolation
+//       along the row -> cell of the pixel's table and of the mirror pixel's.  A ray more than eps = 2e-3 mm inside
+//       a cell offers its index to the cell (32-bit atomicMax: ffl:28, the later ray wins); a ray surely beyond the
+//       high edges is dropped (ffl:19); a ray within eps of an edge is AMBIGUOUS: it is traced exactly and offered to
+//       the cells it really lands in;
+//   2   every cell's winner is traced exactly: path length -> phasor x E_rec, summed exactly as in ff_map_kernel (same
+//       scan order, same compaction, same lanes: identical bits).  Each winner's exact landing point is compared with
+//       its prediction: it must sit in the predicted cell and within chk = eps / 4 of the predicted position -- 20 000
+//       probes per item, one in every cell, of an error field that is smooth on the scale of S rays.  An item that
+//       fails any of them (or has no row intervals) is flagged and ff_map_kernel, launched behind this kernel, redoes it.
+// Exact by construction as long as the interpolation error stays below eps, which is what the probes watch; the maps
+// are bit-identical to the exact walk (tests: test_ff_interp_*).  A ray that is never traced reports no status.
+constexpr int FF_INTERP_T = 768;
+constexpr int FF_INTERP_MIN_N = 256;           // fans below 256 x 256 rays keep the exact walk (the lattice would not pay)
+constexpr double FF_INTERP_EPS_CM = 2.0e-4;    // 2e-3 mm: ten times the interpolation error measured at S = 16 on a 1000^2 fan
+struct FfInterpLayout {
+    size_t axes, lat, rown, wts, cand, queues, rows, total;
+    int nk;
+};
+__host__ __device__ inline FfInterpLayout ff_interp_layout(int M, int nth, int nph, int S, int tables)
+{
+    FfInterpLayout L;
+    L.nk = (nth - 1) / S + 4;                      // lattice nodes k = -1 .. (nth-1)/S + 2 per axis (nth == nph)
+    size_t o = ((sizeof(FfFrames) + 15) / 16) * 16;
+    L.axes = o;   o += 2 * ((size_t)M + 2) * sizeof(double);
+    o = (o + 15) / 16 * 16;
+    L.lat = o;    o += (size_t)L.nk * L.nk * sizeof(double2);
+    L.rown = o;   o += (size_t)(FF_INTERP_T / 32) * L.nk * sizeof(double2);
+    L.wts = o;    o += (size_t)S * 4 * sizeof(double);
+    L.cand = o;   o += (size_t)tables * M * M * sizeof(unsigned);
+    L.queues = o; o += (size_t)(FF_INTERP_T / 32) * FF_WQ * sizeof(int);
+    L.rows = o;   o += (2 * (size_t)FF_ROW_K * nph + 1) * sizeof(int);
+    L.total = o;
+    return L;
+}
+// np.searchsorted on a lean axis plus how sure the answer is: >= 0 the cell index, the value being more than eps away
+// from both edges of the cell; -1 surely beyond the last element (ffl:19 skips the ray); -2 within eps of an edge (or NaN)
+__device__ __forceinline__ int ff_axis_class(const double* a, float nf, int M, double v, double a0, float inv_step, double eps)
+{
+    const int i = searchsorted_lean(a, nf, v, a0, inv_step);
+    const double lo = a[i - 1], hi = a[i];                    // sentinels: a[-1] = -inf, a[M] = +inf
+    const bool sure = (v - lo > eps) && (hi - v > eps);
+    return sure ? (i < M ? i : -1) : -2;
+}
+__global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapParams q)
+{
+    constexpr int T = FF_INTERP_T, WARPS = T / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int M = q.grid.M, cells = M * M, S = q.interp_s;
+    const int nth = q.ang.nth, nph = q.ang.nph;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pix = blockIdx.x;
+    if (q.items && q.item0 + pix >= __ldg(q.counters)) return;
+    const int out_pos = q.items ? q.items[q.item0 + pix].pos : pix, out_neg = q.items ? q.items[q.item0 + pix].neg : -1;
+    const int tables = q.items ? 2 : 1;
+    const FfInterpLayout L = ff_interp_layout(M, nth, nph, S, tables);
+    const int NK = L.nk;
+    FfFrames* fr = reinterpret_cast<FfFrames*>(smem_raw);
+    double* s_gx = reinterpret_cast<double*>(smem_raw + L.axes) + 1;
+    double* s_gy = s_gx + M + 2;
+    double2* lat = reinterpret_cast<double2*>(smem_raw + L.lat);            // [NK][NK] (row of phi node, theta node): (x, z) / 10 about the centre [cm]
+    double2* rown = reinterpret_cast<double2*>(smem_raw + L.rown) + warp * NK;   // this warp's row nodes
+    double* wts = reinterpret_cast<double*>(smem_raw + L.wts);              // [S][4] cubic Lagrange weights at t = 1 + f / S
+    unsigned* cand = reinterpret_cast<unsigned*>(smem_raw + L.cand);        // [tables][cells] ray index + 1 of the latest ray
+    int* wq = reinterpret_cast<int*>(smem_raw + L.queues) + warp * FF_WQ;
+    const int nvr = FF_ROW_K * nph;
+    int* row_lo = reinterpret_cast<int*>(smem_raw + L.rows);
+    int* row_pre = row_lo + nvr;
+    __shared__ int s_queue_walk, s_row, s_bad;
+    __shared__ double2 total;
+
+    const FfGeom g = to_geom(q.g);
+    const Coef& sC = K_COEF;
+    {
+        const unsigned char* rec = q.rec + (size_t)pix * q.rec_stride;
+        const int* src = reinterpret_cast<const int*>(rec);
+        int* dst = reinterpret_cast<int*>(fr);
+        for (int i = tid; i < (int)(sizeof(FfFrames) / sizeof(int)); i += T) dst[i] = __ldg(src + i);
+        if (tid == 0) { s_queue_walk = __ldg(reinterpret_cast<const int*>(rec + FF_REC_FRAMES)); s_row = nph - 1; s_bad = 0; }
+        const int* rows = reinterpret_cast<const int*>(rec + FF_REC_HEAD);
+        for (int i = tid; i < 2 * nvr + 1; i += T) row_lo[i] = __ldg(rows + i);
+    }
+    for (int c = tid; c < tables * cells; c += T) cand[c] = 0u;
+    for (int i = tid; i < M; i += T) {
+        s_gx[i] = __ldg(q.grid.gx + i);
+        s_gy[i] = __ldg(q.grid.gy + (size_t)i * M);
+    }
+    if (tid < 4) {
+        const double inf = __longlong_as_double(0x7ff0000000000000ll);
+        (tid & 2 ? s_gy : s_gx)[tid & 1 ? M : -1] = tid & 1 ? inf : -inf;
+    }
+    for (int f = tid; f < S; f += T) {
+        const double t = 1.0 + (double)f / (double)S;
+        wts[4 * f + 0] = -(t - 1.0) * (t - 2.0) * (t - 3.0) / 6.0;
+        wts[4 * f + 1] = t * (t - 2.0) * (t - 3.0) / 2.0;
+        wts[4 * f + 2] = -t * (t - 1.0) * (t - 3.0) / 2.0;
+        wts[4 * f + 3] = t * (t - 1.0) * (t - 2.0) / 6.0;
+    }
+    __syncthreads();
+    if (s_queue_walk) {                                        // no row intervals for this pixel: the exact kernel does it
+        if (tid == 0) q.redo[pix] = 1;
+        return;
+    }
+    const double cx = fr->centre[0], cz = fr->centre[2];
+    const double dzm = div10(cz - fr->centre_mz);              // the mirror pixel's z offset is this much larger [cm]
+    const double eps = q.interp_eps, chk = q.interp_chk;
+    const float nf = (float)M;
+    int st = 0;
+
+    // exact trace of ray (i, j): path length and focal-plane offsets / 10 about the pixel's centre (ffl:12-13)
+    auto trace = [&](int i, int j, double& opl, double& xx, double& yy, double& yym) __attribute__((always_inline)) {
+        const double2 tsc = __ldg(q.ang.tsc + i), psc = __ldg(q.ang.psc + j);
+        const vec3 d = launch_dir(tsc.x, tsc.y, psc.x, psc.y);
+        vec3 Pa;
+        double t_ap, fx, fz;
+        int rst;
+        ff_aperture(sC, g, *fr, d, t_ap, Pa);
+        ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);
+        st |= rst;
+        xx = div10(fx - cx); yy = div10(fz - cz); yym = div10(fz - fr->centre_mz);
+        return !(opl == 0.0 || not_finite(opl) || not_finite(fx) || not_finite(fz));   // ffl:10
+    };
+    // exact cell of a traced ray, -1 when ffl:19 skips it
+    auto cell_of = [&](double xx, double yy) __attribute__((always_inline)) {
+        if (!(xx <= q.grid.gx_max && yy <= q.grid.gy_max)) return -1;
+        return searchsorted_lean(s_gy, nf, yy, q.grid.gy_min, q.grid.inv_dy) * M + searchsorted_lean(s_gx, nf, xx, q.grid.gx_min, q.grid.inv_dx);
+    };
+    auto offer = [&](unsigned* tab, int cell, unsigned r) __attribute__((always_inline)) {
+        if (*reinterpret_cast<volatile unsigned*>(tab + cell) < r) atomicMax(tab + cell, r);   // ffl:28
+    };
+
+    // ---- 1a: the lattice
+    for (int n = tid; n < NK * NK; n += T) {
+        const int mm = n / NK, kk = n - mm * NK;
+        const int i = (kk - 1) * S, j = (mm - 1) * S;
+        double sth, cth, sph, cph;
+        if (i >= 0 && i < nth) { const double2 v = __ldg(q.ang.tsc + i); sth = v.x; cth = v.y; }
+        else sincos(q.th0 + (double)i * q.dth, &sth, &cth);
+        if (j >= 0 && j < nph) { const double2 v = __ldg(q.ang.psc + j); sph = v.x; cph = v.y; }
+        else sincos(q.ph0 + (double)j * q.dph, &sph, &cph);
+        const vec3 d = launch_dir(sth, cth, sph, cph);
+        vec3 Pa;
+        double t_ap, opl, fx, fz;
+        int rst;
+        ff_aperture(sC, g, *fr, d, t_ap, Pa);
+        ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);   // (a node's status is nobody's: it may lie outside the aperture)
+        lat[n] = make_double2(div10(fx - cx), div10(fz - cz));
+    }
+    __syncthreads();
+
+    // ---- 1b: rows, last row first
+    int cnt = 0;                                              // queue of ambiguous rays (ray index j * nth + i), warp-uniform
+    auto exact_offer = [&](int r) __attribute__((always_inline)) {
+        const int j = r / nth, i = r - j * nth;
+        double opl, xx, yy, yym;
+        if (trace(i, j, opl, xx, yy, yym)) {
+            if (out_pos >= 0) { const int c = cell_of(xx, yy); if (c >= 0) offer(cand, c, (unsigned)(r + 1)); }
+            if (out_neg >= 0) { const int c = cell_of(-xx, yym); if (c >= 0) offer(cand + cells, c, (unsigned)((nph - 1 - j) * nth + i + 1)); }
+        }
+    };
+    for (;;) {
+        int j = 0;
+        if (lane == 0) j = atomicSub(&s_row, 1);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        if (j < 0) break;
+        const int vr0 = FF_ROW_K * j, base = row_pre[vr0], n_row = row_pre[vr0 + FF_ROW_K] - base;
+        if (n_row <= 0) continue;
+        int p[FF_ROW_K + 1], lo[FF_ROW_K];
+        int imin = 0x7fffffff, imax = -1;
+#pragma unroll
+        for (int k = 0; k < FF_ROW_K; k++) {
+            p[k] = row_pre[vr0 + k] - base; lo[k] = row_lo[vr0 + k];
+            const int c = row_pre[vr0 + k + 1] - row_pre[vr0 + k];
+            if (c > 0) { imin = min(imin, lo[k]); imax = max(imax, lo[k] + c - 1); }
+        }
+        {   // row nodes the listed rays reach: theta nodes imin / S - 1 .. imax / S + 2 (array index + 1)
+            const int m0 = j / S;
+            const double* wj = wts + 4 * (j - m0 * S);
+            const double w0 = wj[0], w1 = wj[1], w2 = wj[2], w3 = wj[3];
+            for (int k = imin / S + lane; k <= imax / S + 3; k += 32) {
+                const double2 a0 = lat[m0 * NK + k], a1 = lat[(m0 + 1) * NK + k], a2 = lat[(m0 + 2) * NK + k], a3 = lat[(m0 + 3) * NK + k];
+                rown[k] = make_double2(fma(w0, a0.x, fma(w1, a1.x, fma(w2, a2.x, w3 * a3.x))),
+                                       fma(w0, a0.y, fma(w1, a1.y, fma(w2, a2.y, w3 * a3.y))));
+            }
+        }
+        __syncwarp();
+        const unsigned r_row = (unsigned)(j * nth + 1), rm_row = (unsigned)((nph - 1 - j) * nth + 1);
+        for (int v_top = n_row - 1; v_top >= 0; v_top -= 32) {
+            const int v = v_top - lane;
+            bool amb = false;
+            int i = 0;
+            if (v >= 0) {
+                int k = 0;
+#pragma unroll
+                for (int t = 1; t < FF_ROW_K; t++) k += (v >= p[t]) ? 1 : 0;
+                // (intervals may be empty: p[t] == p[t+1]; the count above lands on the last interval that starts at or before v)
+                int lo_k = lo[0], p_k = p[0];
+#pragma unroll
+                for (int t = 1; t < FF_ROW_K; t++) if (k == t) { lo_k = lo[t]; p_k = p[t]; }
+                i = lo_k + (v - p_k);
+                const int kb = i / S;
+                const double* wi = wts + 4 * (i - kb * S);
+                const double2 n0 = rown[kb], n1 = rown[kb + 1], n2 = rown[kb + 2], n3 = rown[kb + 3];
+                const double w0 = wi[0], w1 = wi[1], w2 = wi[2], w3 = wi[3];
+                const double xx = fma(w0, n0.x, fma(w1, n1.x, fma(w2, n2.x, w3 * n3.x)));
+                const double yy = fma(w0, n0.y, fma(w1, n1.y, fma(w2, n2.y, w3 * n3.y)));
+                if (out_pos >= 0) {
+                    int c = ff_axis_class(s_gx, nf, M, xx, q.grid.gx_min, q.grid.inv_dx, eps);
+                    if (c != -1) {
+                        const int cy = ff_axis_class(s_gy, nf, M, yy, q.grid.gy_min, q.grid.inv_dy, eps);
+                        c = cy == -1 ? -1 : ((c | cy) < 0 ? -2 : cy * M + c);
+                    }
+                    if (c >= 0) offer(cand, c, r_row + (unsigned)i);
+                    amb = c == -2;
+                }
+                if (out_neg >= 0) {
+                    int c = ff_axis_class(s_gx, nf, M, -xx, q.grid.gx_min, q.grid.inv_dx, eps);
+                    if (c != -1) {
+                        const int cy = ff_axis_class(s_gy, nf, M, yy + dzm, q.grid.gy_min, q.grid.inv_dy, eps);
+                        c = cy == -1 ? -1 : ((c | cy) < 0 ? -2 : cy * M + c);
+                    }
+                    if (c >= 0) offer(cand + cells, c, rm_row + (unsigned)i);
+                    amb = amb || c == -2;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, amb);
+            if (m) {
+                if (amb) wq[cnt + __popc(m & ((1u << lane) - 1u))] = j * nth + i;
+                cnt += __popc(m);
+                __syncwarp();
+                if (cnt >= 32) {
+                    const int r = wq[cnt - 1 - lane];
+                    cnt -= 32;
+                    __syncwarp();
+                    exact_offer(r);
+                }
+            }
+        }
+        __syncwarp();                                         // the row nodes are overwritten by the next row
+    }
+    if (cnt > 0) {
+        const int r = lane < cnt ? wq[cnt - 1 - lane] : -1;
+        __syncwarp();
+        if (r >= 0) exact_offer(r);
+        cnt = 0;
+    }
+    __syncthreads();
+
+    // ---- 2: the winners, traced exactly; sum_cells exp(i k L/1e3) * E_rec / M^2   (ff_sim.py:215-221)
+    bool bad = false;
+    for (int side = 0; side < 2; side++) {
+        const int out = side ? out_neg : out_pos;
+        if (out < 0) continue;                                  // CTA-uniform
+        const unsigned* tab = cand + (side ? cells : 0);
+        double re[1] = {0.0}, im[1] = {0.0};
+        cnt = 0;
+        for (int c0 = warp * 32;; c0 += WARPS * 32) {
+            const bool more = c0 < cells;
+            if (more) {
+                const int c = c0 + lane;
+                const bool has = c < cells && tab[c] != 0u;
+                const unsigned m = __ballot_sync(0xffffffffu, has);
+                if (has) wq[cnt + __popc(m & ((1u << lane) - 1u))] = c;
+                cnt += __popc(m);
+                __syncwarp();
+            }
+            if (cnt >= 32 || (!more && cnt > 0)) {
+                const int n_take = min(cnt, 32);
+                const int c = lane < n_take ? wq[cnt - 1 - lane] : -1;
+                cnt -= n_take;
+                __syncwarp();
+                if (c >= 0) {
+                    const int r = (int)tab[c] - 1;
+                    const int jr = r / nth, i = r - jr * nth, j = side ? nph - 1 - jr : jr;
+                    double opl, xx, yy, yym;
+                    const bool ok = trace(i, j, opl, xx, yy, yym);
+                    // the prediction this winner was chosen by: bicubic on the lattice
+                    const int m0 = j / S, kb = i / S;
+                    const double* wj = wts + 4 * (j - m0 * S);
+                    const double* wi = wts + 4 * (i - kb * S);
+                    double xi = 0.0, yi = 0.0;
+#pragma unroll
+                    for (int a = 0; a < 4; a++) {
+                        const double2* row = lat + (m0 + a) * NK + kb;
+                        const double2 n0 = row[0], n1 = row[1], n2 = row[2], n3 = row[3];
+                        xi = fma(wj[a], fma(wi[0], n0.x, fma(wi[1], n1.x, fma(wi[2], n2.x, wi[3] * n3.x))), xi);
+                        yi = fma(wj[a], fma(wi[0], n0.y, fma(wi[1], n1.y, fma(wi[2], n2.y, wi[3] * n3.y))), yi);
+                    }
+                    const double xs = side ? -xx : xx, ys = side ? yym : yy;
+                    if (side) { xi = -xi; yi += dzm; }
+                    if (!(ok && fabs(xs - xi) <= chk && fabs(ys - yi) <= chk && cell_of(xs, ys) == c)) bad = true;
+                    double cs, sn;
+                    cis_large(q.k * opl / 1e3, cs, sn);
+                    const double2 e = __ldg(q.e_rec + c);
+                    re[0] += cs * e.x - sn * e.y;
+                    im[0] += cs * e.y + sn * e.x;
+                }
+            }
+            if (!more && cnt == 0) break;
+        }
+        block_reduce_store<1>(re, im, &total);
+        if (tid == 0) {
+            const double inv = 1.0 / ((double)M * (double)M);
+            const double a = total.x * inv, b = total.y * inv;
+            q.amp[out] = hypot(a, b);
+            q.phase[out] = atan2(b, a);
+        }
+        __syncthreads();
+    }
+    if (bad) s_bad = 1;
+    __syncthreads();
+    if (tid == 0 && s_bad) q.redo[pix] = 1;
+    // the status of an item that is redone comes from the exact kernel (which traces a superset of these rays)
+    if (st) atomicOr(q.status, st);
 }
 
 // What the reference hands to pan_mod.identify_panel for every pixel (saf:596-612 = rows 0, 2, 3, 4 of ray_mirror_pts'
@@ -1679,7 +2060,7 @@ static size_t ff_map_smem(int M, int rows_nph, int threads, int tables)
 {
     const size_t cells = (size_t)M * M * tables;
     return ((sizeof(FfFrames) + 15) / 16) * 16 + cells * sizeof(unsigned long long) + (size_t)(threads / 32) * FF_WQ * sizeof(int) +
-           2 * (size_t)M * sizeof(double) + (rows_nph ? (2 * (size_t)FF_ROW_K * rows_nph + 1) * sizeof(int) : 0);
+           2 * ((size_t)M + 2) * sizeof(double) + (rows_nph ? (2 * (size_t)FF_ROW_K * rows_nph + 1) * sizeof(int) : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2380,6 +2761,7 @@ static FfGrid make_grid(const double* data_x, const double* data_y, int M, const
     const double sx = data_x[M - 1] - data_x[0], sy = data_y[(size_t)(M - 1) * M] - data_y[0];
     G.inv_dx = (M > 1 && sx > 0) ? (float)((M - 1) / sx) : 0.0f;   // first guess of searchsorted; the fix-up makes it exact
     G.inv_dy = (M > 1 && sy > 0) ? (float)((M - 1) / sy) : 0.0f;
+    G.lean = G.y_uniform && axis_is_lean(data_x, M, 1) && axis_is_lean(data_y, M, M);
     return G;
 }
 
@@ -2434,18 +2816,28 @@ struct solat_ff_plan {
     int key_shift;
     int M, n_rays, rows, shape, prefilter;
     int win_global;                         // the winner tables do not fit in shared memory: global scratch
+    int lean;                               // plain maps take ff_map_kernel<0, .., LEAN> (shared tables, lean E_rec axes)
+    int interp_s;                           // > 0: large uniform fan, plain maps go through ff_map_interp_kernel with this lattice spacing
+    double th0, dth, ph0, dph;
+    DevBuf<int> redo;
     DevBuf<unsigned long long> win_g;
     size_t smem;
 };
 
 constexpr int FF_NSHAPES = 3;
-static const int FF_SHAPES[FF_NSHAPES][2] = {{FF_T, SOLAT_FF_MINB}, {384, 2}, {768, 1}};   // threads, CTAs per SM
-template <int PANEL>
+#ifndef SOLAT_FF_T2
+#define SOLAT_FF_T2 384
+#endif
+#ifndef SOLAT_FF_T1
+#define SOLAT_FF_T1 768
+#endif
+static const int FF_SHAPES[FF_NSHAPES][2] = {{FF_T, SOLAT_FF_MINB}, {SOLAT_FF_T2, 2}, {SOLAT_FF_T1, 1}};   // threads, CTAs per SM
+template <int PANEL, bool LEAN = false>
 static void ff_map_dispatch(int shape, const FfMapParams& q, int npix, size_t smem, cudaStream_t s)
 {
-    if (shape == 0) ff_map_kernel<PANEL, FF_T, SOLAT_FF_MINB><<<npix, FF_T, smem, s>>>(q);
-    else if (shape == 1) ff_map_kernel<PANEL, 384, 2><<<npix, 384, smem, s>>>(q);
-    else ff_map_kernel<PANEL, 768, 1><<<npix, 768, smem, s>>>(q);
+    if (shape == 0) ff_map_kernel<PANEL, FF_T, SOLAT_FF_MINB, LEAN><<<npix, FF_T, smem, s>>>(q);
+    else if (shape == 1) ff_map_kernel<PANEL, SOLAT_FF_T2, 2, LEAN><<<npix, SOLAT_FF_T2, smem, s>>>(q);
+    else ff_map_kernel<PANEL, SOLAT_FF_T1, 1, LEAN><<<npix, SOLAT_FF_T1, smem, s>>>(q);
 }
 // The dynamic shared-memory limit is an attribute of the kernel, not of a plan: plans with different grids or fans
 // coexist, so the limit of a shape only ever grows (per device).
@@ -2459,11 +2851,12 @@ static int ff_map_set_smem(int device, int shape, size_t smem)
     const int b = (int)smem;
 #define SOLAT_FF_SMEM_ATTR(T_, B_)                                                                                       \
     CK(cudaFuncSetAttribute(ff_map_kernel<0, T_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));                   \
+    CK(cudaFuncSetAttribute(ff_map_kernel<0, T_, B_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));             \
     CK(cudaFuncSetAttribute(ff_map_kernel<1, T_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));                   \
     CK(cudaFuncSetAttribute(ff_map_kernel<2, T_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     if (shape == 0) { SOLAT_FF_SMEM_ATTR(FF_T, SOLAT_FF_MINB) }
-    else if (shape == 1) { SOLAT_FF_SMEM_ATTR(384, 2) }
-    else { SOLAT_FF_SMEM_ATTR(768, 1) }
+    else if (shape == 1) { SOLAT_FF_SMEM_ATTR(SOLAT_FF_T2, 2) }
+    else { SOLAT_FF_SMEM_ATTR(SOLAT_FF_T1, 1) }
 #undef SOLAT_FF_SMEM_ATTR
     have = smem;
     return SOLAT_OK;
@@ -2540,6 +2933,10 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
         }
     }
     q.rows = rows; q.rec = p->rec.p; q.rec_stride = stride;
+    const bool interp = !panel && p->interp_s > 0 && rows && !q.win_g && p->lean;
+    q.redo = nullptr; q.interp_s = p->interp_s; q.th0 = p->th0; q.dth = p->dth; q.ph0 = p->ph0; q.dph = p->dph;
+    q.interp_eps = FF_INTERP_EPS_CM; q.interp_chk = FF_INTERP_EPS_CM / 4;
+    if (interp) if (int rc = p->redo.reserve((size_t)chunk)) return rc;
     const double* azel = q.azel;
     double *amp = q.amp, *phase = q.phase;
     const short *i1 = q.pidx1, *i2 = q.pidx2;
@@ -2558,6 +2955,25 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
         if (panel == 1) { q.pidx1 = i1 + (size_t)p0 * p->n_rays; q.pidx2 = i2 + (size_t)p0 * p->n_rays; }
         if (panel == 1) ff_map_dispatch<1>(p->shape, q, n, p->smem, s);
         else if (panel == 2) ff_map_dispatch<2>(p->shape, q, n, p->smem, s);
+        else if (interp) {
+            // cells from interpolated positions, winners traced exactly; items whose predictions fail their probes
+            // (none on the reference's geometry) are flagged and redone by the exact kernel right behind
+            CK(cudaMemsetAsync(p->redo.p, 0, sizeof(int) * (size_t)n, s));
+            q.redo = p->redo.p;
+            const FfInterpLayout L = ff_interp_layout(p->M, p->ang.tabs.nth, p->ang.tabs.nph, p->interp_s, pairs ? 2 : 1);
+            ff_map_interp_kernel<<<n, FF_INTERP_T, L.total, s>>>(q);
+            LAUNCHED();
+            ff_map_dispatch<0, true>(p->shape, q, n, p->smem, s);
+            if (const char* dbg = getenv("SOLAT_FF_INTERP_DEBUG")) if (dbg[0] == '1') {      // how many items were redone
+                std::vector<int> h((size_t)n);
+                CK(cudaMemcpyAsync(h.data(), p->redo.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                long bad = 0;
+                for (int v : h) bad += v != 0;
+                fprintf(stderr, "[solat] ff_map_interp_kernel: %ld of %d items redone by the exact kernel (S = %d)\n", bad, n, p->interp_s);
+            }
+        }
+        else if (p->lean && !q.win_g) ff_map_dispatch<0, true>(p->shape, q, n, p->smem, s);
         else ff_map_dispatch<0>(p->shape, q, n, p->smem, s);
         LAUNCHED();
     }
@@ -2650,6 +3066,28 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
     if (!rc) rc = p->gx.upload(data_x, M, s);                      // data_x[0, :]
     if (!rc) rc = p->gy.upload(data_y, (size_t)M * M, s);
     if (!rc) p->grid = make_grid(data_x, data_y, M, p->gx.p, p->gy.p);
+    {
+        const char* env = getenv("SOLAT_FF_LEAN");        // "0": the generic binning (A/B runs, tests)
+        p->lean = !rc && p->grid.lean && !win_global && !(env && env[0] == '0');
+    }
+    // large fans: interpolated cells + exact winners (ff_map_interp_kernel).  Needs the lean grid, the interval walk,
+    // a square fan with uniform axes, and room for the lattice next to the candidate tables.
+    p->interp_s = 0;
+    if (!rc && p->lean && rows && nth == nph && nth >= FF_INTERP_MIN_N) {
+        const char* env = getenv("SOLAT_FF_INTERP");       // "0": off; a number >= 2: that lattice spacing
+        int S = std::max(4, std::min(32, (nth + 32) / 64));
+        if (env && atoi(env) >= 2) S = atoi(env);
+        const double dth = (theta[nth - 1] - theta[0]) / (nth - 1), dph = (phi[nph - 1] - phi[0]) / (nph - 1);
+        bool uniform = true;
+        for (int i = 0; i < nth && uniform; i++)
+            uniform = fabs(theta[i] - (theta[0] + i * dth)) <= 1e-9 * fabs(dth) && fabs(phi[i] - (phi[0] + i * dph)) <= 1e-9 * fabs(dph);
+        const FfInterpLayout L = ff_interp_layout(M, nth, nph, S, pairs ? 2 : 1);
+        if (uniform && !(env && env[0] == '0' && env[1] == 0) && L.total + 4608 <= cta_max && nth >= 4 * S) {
+            p->interp_s = S; p->th0 = theta[0]; p->dth = dth; p->ph0 = phi[0]; p->dph = dph;
+            if (cudaFuncSetAttribute(ff_map_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_max - 4608) != cudaSuccess)
+                p->interp_s = 0;
+        }
+    }
     if (!rc) rc = p->e_rec.upload(reinterpret_cast<const double2*>(e_rec), (size_t)M * M, s);
     if (!rc) rc = p->status.reserve(1);
     if (!rc && cudaMemsetAsync(p->status.p, 0, sizeof(int), s) != cudaSuccess) rc = fail(SOLAT_ERR_CUDA, "memset");

@@ -1226,6 +1226,31 @@ SOLAT_HD int searchsorted_guess(const double* a, int n, int stride, double v, do
     return i;
 }
 
+// The same on an axis the host has found sorted and uniform to within a quarter of its step (axis_is_lean): the
+// interpolated guess is then within one of the answer, and one comparison against each neighbour a[i-1], a[i] -- the
+// staged axis carries -inf at a[-1] and +inf at a[n] -- settles it without a branch or a loop.
+SOLAT_HD int searchsorted_lean(const double* a, float n, double v, double a0, float inv_step)
+{
+    const float g = ceilf((float)(v - a0) * inv_step);
+    const int i = (int)fminf(fmaxf(g, 0.0f), n);
+    const double lo = a[i - 1], hi = a[i];
+    return i + (hi < v ? 1 : 0) - (lo >= v ? 1 : 0);
+}
+// Host-side condition for searchsorted_lean: strictly increasing and |a[i] - (a[0] + i step)| < step / 4, so that the
+// single-precision guess (relative error 2e-7 on an index below 2^12) cannot miss by more than one.
+inline bool axis_is_lean(const double* a, int n, long stride)
+{
+    if (n < 2 || n > 4096) return false;
+    const double a0 = a[0], step = (a[(long)(n - 1) * stride] - a0) / (n - 1);
+    if (!(step > 0.0) || !(step < 1e300)) return false;
+    for (int i = 0; i < n; i++) {
+        const double v = a[(long)i * stride];
+        if (i && !(v > a[(long)(i - 1) * stride])) return false;
+        if (!(fabs(v - (a0 + i * step)) < 0.25 * step)) return false;
+    }
+    return true;
+}
+
 // x / 10 correctly rounded without the division subroutine: q = RN(x * 0.1) is within 1 ulp, the FMA
 // residual r = x - 10 q is exact, and RN(q + r * 0.1) is the correctly rounded quotient (Markstein).
 SOLAT_HD double div10(double x)
@@ -1244,6 +1269,7 @@ struct FfGrid {
     double gx_max, gy_max; // ffl:19: rays beyond these are skipped
     double gx_min, gy_min; // min(data_x[0, :]), min(data_y[:, 0]): rays below both pile into cell (0, 0)  (ffl:22-23)
     float inv_dx, inv_dy;  // (M-1)/(last-first) of gx and of gy[:,0]; 0 when not usable as a guess
+    int lean;              // host: both axes pass axis_is_lean and all columns of data_y agree (searchsorted_lean applies)
 };
 SOLAT_HD int ff_cell(double fx_mm, double fz_mm, const FfGrid& G)
 {
