@@ -1065,7 +1065,7 @@ struct FfMapParams {
     PanelLayoutDev lay1, lay2;
     unsigned long long* win_g;   // winner tables in global memory, [CTAs of the launch][tables][M * M]; nullptr: shared memory
     // large fans (ff_map_interp_kernel): cells from interpolated focal positions, exact traces for the winners only
-    int interp_s;                // lattice spacing in rays (both fan axes)
+    int interp_s, interp_ls;     // lattice spacing in rays (both fan axes), a power of two: S = 1 << ls
     double th0, dth, ph0, dph;   // the fan's axes are uniform: theta_i = th0 + i dth, phi_j = ph0 + j dph (lattice nodes beyond the fan)
     double interp_eps, interp_chk;   // [cm] a ray closer than eps to a cell edge is traced exactly; winners must match their prediction to chk
     int* redo;                   // [CTAs of the launch] interp kernel: 1 = prediction check failed, the exact kernel redoes the item;
@@ -1710,8 +1710,8 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
 // Exact by construction as long as the interpolation error stays below eps, which is what the probes watch; the maps
 // are bit-identical to the exact walk (tests: test_ff_interp_*).  A ray that is never traced reports no status.
 constexpr int FF_INTERP_T = 768;
-constexpr int FF_INTERP_MIN_N = 256;           // fans below 256 x 256 rays keep the exact walk (the lattice would not pay)
-constexpr double FF_INTERP_EPS_CM = 2.0e-4;    // 2e-3 mm: ten times the interpolation error measured at S = 16 on a 1000^2 fan
+constexpr int FF_INTERP_MIN_N = 400;           // smaller fans keep the exact walk (measured: no gain at 300 x 300 rays)
+constexpr double FF_INTERP_EPS_CM = 3.0e-4;    // 3e-3 mm: ten times the interpolation error measured at S = 16 on a 1000^2 fan
 struct FfInterpLayout {
     size_t axes, lat, rown, wts, cand, queues, rows, total;
     int nk;
@@ -1723,23 +1723,29 @@ __host__ __device__ inline FfInterpLayout ff_interp_layout(int M, int nth, int n
     size_t o = ((sizeof(FfFrames) + 15) / 16) * 16;
     L.axes = o;   o += 2 * ((size_t)M + 2) * sizeof(double);
     o = (o + 15) / 16 * 16;
-    L.lat = o;    o += (size_t)L.nk * L.nk * sizeof(double2);
-    L.rown = o;   o += (size_t)(FF_INTERP_T / 32) * L.nk * sizeof(double2);
-    L.wts = o;    o += (size_t)S * 4 * sizeof(double);
-    L.cand = o;   o += (size_t)tables * M * M * sizeof(unsigned);
+    L.lat = o;    o += ((size_t)L.nk * L.nk * sizeof(float2) + 15) / 16 * 16;
+    L.rown = o;   o += ((size_t)(FF_INTERP_T / 32) * L.nk * sizeof(float2) + 15) / 16 * 16;
+    L.wts = o;    o += (size_t)S * 4 * sizeof(float);
+    L.cand = o;   o += ((size_t)tables * M * M * sizeof(unsigned) + 15) / 16 * 16;
     L.queues = o; o += (size_t)(FF_INTERP_T / 32) * FF_WQ * sizeof(int);
     L.rows = o;   o += (2 * (size_t)FF_ROW_K * nph + 1) * sizeof(int);
     L.total = o;
     return L;
 }
-// np.searchsorted on a lean axis plus how sure the answer is: >= 0 the cell index, the value being more than eps away
-// from both edges of the cell; -1 surely beyond the last element (ffl:19 skips the ray); -2 within eps of an edge (or NaN)
-__device__ __forceinline__ int ff_axis_class(const double* a, float nf, int M, double v, double a0, float inv_step, double eps)
+// np.searchsorted(a, v, 'left') on a uniform axis from u = (v - a[0]) / step alone, plus how sure the answer is.
+// c = the cell index, valid when neither flag is set: u is more than tol away from every integer, i.e. v more than eps
+// away from every element (below the first element searchsorted returns 0); skip: surely beyond the last element
+// (ffl:19 drops the ray); amb: within tol of an element, or NaN: the ray has to be traced.  Branch-free.  Single
+// precision is enough: |u| < 2^9, tol ~ 3e-3, of which 5e-4 are slack for the roundings (lattice values and weights in
+// single precision) and the axis' measured deviation from uniform (FfGrid::dev_u).
+// Returns (c << 2) | (amb ? 2 : 0) | (skip ? 1 : 0).
+__device__ __forceinline__ int ff_axis_class(float u, float u_last, float tol)
 {
-    const int i = searchsorted_lean(a, nf, v, a0, inv_step);
-    const double lo = a[i - 1], hi = a[i];                    // sentinels: a[-1] = -inf, a[M] = +inf
-    const bool sure = (v - lo > eps) && (hi - v > eps);
-    return sure ? (i < M ? i : -1) : -2;
+    const float r = rintf(u);
+    const bool below = u < -tol, skip = u - u_last > tol;     // (the same subtraction as the edge test below: no gap at u_last + tol)
+    const bool amb = !(fabsf(u - r) > tol) && !below && !skip;
+    const int c = (below || skip) ? 0 : (int)r + (u > r ? 1 : 0);          // ceil(u): the number of elements below v
+    return (c << 2) | (amb ? 2 : 0) | (skip ? 1 : 0);
 }
 __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapParams q)
 {
@@ -1756,9 +1762,10 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
     FfFrames* fr = reinterpret_cast<FfFrames*>(smem_raw);
     double* s_gx = reinterpret_cast<double*>(smem_raw + L.axes) + 1;
     double* s_gy = s_gx + M + 2;
-    double2* lat = reinterpret_cast<double2*>(smem_raw + L.lat);            // [NK][NK] (row of phi node, theta node): (x, z) / 10 about the centre [cm]
-    double2* rown = reinterpret_cast<double2*>(smem_raw + L.rown) + warp * NK;   // this warp's row nodes
-    double* wts = reinterpret_cast<double*>(smem_raw + L.wts);              // [S][4] cubic Lagrange weights at t = 1 + f / S
+    // [NK][NK] (phi node, theta node): focal-plane position in CELL UNITS of the pixel's table, u = (x/10 - gx[0]) / step
+    float2* lat = reinterpret_cast<float2*>(smem_raw + L.lat);
+    float2* rown = reinterpret_cast<float2*>(smem_raw + L.rown) + warp * NK;     // this warp's row nodes
+    float4* wts = reinterpret_cast<float4*>(smem_raw + L.wts);              // [S] cubic Lagrange weights at t = 1 + f / S
     unsigned* cand = reinterpret_cast<unsigned*>(smem_raw + L.cand);        // [tables][cells] ray index + 1 of the latest ray
     int* wq = reinterpret_cast<int*>(smem_raw + L.queues) + warp * FF_WQ;
     const int nvr = FF_ROW_K * nph;
@@ -1789,10 +1796,8 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
     }
     for (int f = tid; f < S; f += T) {
         const double t = 1.0 + (double)f / (double)S;
-        wts[4 * f + 0] = -(t - 1.0) * (t - 2.0) * (t - 3.0) / 6.0;
-        wts[4 * f + 1] = t * (t - 2.0) * (t - 3.0) / 2.0;
-        wts[4 * f + 2] = -t * (t - 1.0) * (t - 3.0) / 2.0;
-        wts[4 * f + 3] = t * (t - 1.0) * (t - 2.0) / 6.0;
+        wts[f] = make_float4((float)(-(t - 1.0) * (t - 2.0) * (t - 3.0) / 6.0), (float)(t * (t - 2.0) * (t - 3.0) / 2.0),
+                             (float)(-t * (t - 1.0) * (t - 3.0) / 2.0), (float)(t * (t - 1.0) * (t - 2.0) / 6.0));
     }
     __syncthreads();
     if (s_queue_walk) {                                        // no row intervals for this pixel: the exact kernel does it
@@ -1801,8 +1806,16 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
     }
     const double cx = fr->centre[0], cz = fr->centre[2];
     const double dzm = div10(cz - fr->centre_mz);              // the mirror pixel's z offset is this much larger [cm]
-    const double eps = q.interp_eps, chk = q.interp_chk;
     const float nf = (float)M;
+    // cell units: u = (v - a[0]) * inv_step; the mirror pixel's ray lands at (-x, z + dzm): u_x' = umx - u_x, u_y' = u_y + umy
+    const double inv_x = (double)q.grid.inv_dx, inv_y = (double)q.grid.inv_dy;
+    __shared__ float4 s_cls[2];      // (tol_x, tol_y, umx, umy), (M - 1, M - 1, chk_x, chk_y)
+    if (tid == 0) {
+        const float tol_x = (float)(q.interp_eps * inv_x) + q.grid.dev_u + 5.0e-4f, tol_y = (float)(q.interp_eps * inv_y) + q.grid.dev_u + 5.0e-4f;
+        s_cls[0] = make_float4(tol_x, tol_y, (float)(-2.0 * q.grid.gx_min * inv_x), (float)(dzm * inv_y));
+        s_cls[1] = make_float4((float)(M - 1), (float)(M - 1), (float)(q.interp_chk * inv_x), (float)(q.interp_chk * inv_y));
+    }
+    const int ls = q.interp_ls;                               // S = 1 << ls
     int st = 0;
 
     // exact trace of ray (i, j): path length and focal-plane offsets / 10 about the pixel's centre (ffl:12-13)
@@ -1842,7 +1855,7 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
         int rst;
         ff_aperture(sC, g, *fr, d, t_ap, Pa);
         ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);   // (a node's status is nobody's: it may lie outside the aperture)
-        lat[n] = make_double2(div10(fx - cx), div10(fz - cz));
+        lat[n] = make_float2((float)((div10(fx - cx) - q.grid.gx_min) * inv_x), (float)((div10(fz - cz) - q.grid.gy_min) * inv_y));
     }
     __syncthreads();
 
@@ -1872,13 +1885,12 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
             if (c > 0) { imin = min(imin, lo[k]); imax = max(imax, lo[k] + c - 1); }
         }
         {   // row nodes the listed rays reach: theta nodes imin / S - 1 .. imax / S + 2 (array index + 1)
-            const int m0 = j / S;
-            const double* wj = wts + 4 * (j - m0 * S);
-            const double w0 = wj[0], w1 = wj[1], w2 = wj[2], w3 = wj[3];
-            for (int k = imin / S + lane; k <= imax / S + 3; k += 32) {
-                const double2 a0 = lat[m0 * NK + k], a1 = lat[(m0 + 1) * NK + k], a2 = lat[(m0 + 2) * NK + k], a3 = lat[(m0 + 3) * NK + k];
-                rown[k] = make_double2(fma(w0, a0.x, fma(w1, a1.x, fma(w2, a2.x, w3 * a3.x))),
-                                       fma(w0, a0.y, fma(w1, a1.y, fma(w2, a2.y, w3 * a3.y))));
+            const int m0 = j >> ls;
+            const float4 wj = wts[j - (m0 << ls)];
+            for (int k = (imin >> ls) + lane; k <= (imax >> ls) + 3; k += 32) {
+                const float2 a0 = lat[m0 * NK + k], a1 = lat[(m0 + 1) * NK + k], a2 = lat[(m0 + 2) * NK + k], a3 = lat[(m0 + 3) * NK + k];
+                rown[k] = make_float2(fmaf(wj.x, a0.x, fmaf(wj.y, a1.x, fmaf(wj.z, a2.x, wj.w * a3.x))),
+                                      fmaf(wj.x, a0.y, fmaf(wj.y, a1.y, fmaf(wj.z, a2.y, wj.w * a3.y))));
             }
         }
         __syncwarp();
@@ -1896,29 +1908,21 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
 #pragma unroll
                 for (int t = 1; t < FF_ROW_K; t++) if (k == t) { lo_k = lo[t]; p_k = p[t]; }
                 i = lo_k + (v - p_k);
-                const int kb = i / S;
-                const double* wi = wts + 4 * (i - kb * S);
-                const double2 n0 = rown[kb], n1 = rown[kb + 1], n2 = rown[kb + 2], n3 = rown[kb + 3];
-                const double w0 = wi[0], w1 = wi[1], w2 = wi[2], w3 = wi[3];
-                const double xx = fma(w0, n0.x, fma(w1, n1.x, fma(w2, n2.x, w3 * n3.x)));
-                const double yy = fma(w0, n0.y, fma(w1, n1.y, fma(w2, n2.y, w3 * n3.y)));
+                const int kb = i >> ls;
+                const float4 wi = wts[i - (kb << ls)];
+                const float2 n0 = rown[kb], n1 = rown[kb + 1], n2 = rown[kb + 2], n3 = rown[kb + 3];
+                const float ux = fmaf(wi.x, n0.x, fmaf(wi.y, n1.x, fmaf(wi.z, n2.x, wi.w * n3.x)));
+                const float uy = fmaf(wi.x, n0.y, fmaf(wi.y, n1.y, fmaf(wi.z, n2.y, wi.w * n3.y)));
+                const float4 k0 = s_cls[0], k1 = s_cls[1];
                 if (out_pos >= 0) {
-                    int c = ff_axis_class(s_gx, nf, M, xx, q.grid.gx_min, q.grid.inv_dx, eps);
-                    if (c != -1) {
-                        const int cy = ff_axis_class(s_gy, nf, M, yy, q.grid.gy_min, q.grid.inv_dy, eps);
-                        c = cy == -1 ? -1 : ((c | cy) < 0 ? -2 : cy * M + c);
-                    }
-                    if (c >= 0) offer(cand, c, r_row + (unsigned)i);
-                    amb = c == -2;
+                    const int kx = ff_axis_class(ux, k1.x, k0.x), ky = ff_axis_class(uy, k1.y, k0.y), f = kx | ky;
+                    if (!(f & 3)) offer(cand, (ky >> 2) * M + (kx >> 2), r_row + (unsigned)i);
+                    amb = (f & 3) == 2;                      // not surely skipped, and within tol of an edge on either axis
                 }
                 if (out_neg >= 0) {
-                    int c = ff_axis_class(s_gx, nf, M, -xx, q.grid.gx_min, q.grid.inv_dx, eps);
-                    if (c != -1) {
-                        const int cy = ff_axis_class(s_gy, nf, M, yy + dzm, q.grid.gy_min, q.grid.inv_dy, eps);
-                        c = cy == -1 ? -1 : ((c | cy) < 0 ? -2 : cy * M + c);
-                    }
-                    if (c >= 0) offer(cand + cells, c, rm_row + (unsigned)i);
-                    amb = amb || c == -2;
+                    const int kx = ff_axis_class(k0.z - ux, k1.x, k0.x), ky = ff_axis_class(uy + k0.w, k1.y, k0.y), f = kx | ky;
+                    if (!(f & 3)) offer(cand + cells, (ky >> 2) * M + (kx >> 2), rm_row + (unsigned)i);
+                    amb = amb || (f & 3) == 2;
                 }
             }
             const unsigned m = __ballot_sync(0xffffffffu, amb);
@@ -1945,7 +1949,7 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
     __syncthreads();
 
     // ---- 2: the winners, traced exactly; sum_cells exp(i k L/1e3) * E_rec / M^2   (ff_sim.py:215-221)
-    bool bad = false;
+    int bad = 0;
     for (int side = 0; side < 2; side++) {
         const int out = side ? out_neg : out_pos;
         if (out < 0) continue;                                  // CTA-uniform
@@ -1973,20 +1977,25 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
                     double opl, xx, yy, yym;
                     const bool ok = trace(i, j, opl, xx, yy, yym);
                     // the prediction this winner was chosen by: bicubic on the lattice
-                    const int m0 = j / S, kb = i / S;
-                    const double* wj = wts + 4 * (j - m0 * S);
-                    const double* wi = wts + 4 * (i - kb * S);
-                    double xi = 0.0, yi = 0.0;
+                    const int m0 = j >> ls, kb = i >> ls;
+                    const float4 wj = wts[j - (m0 << ls)], wi = wts[i - (kb << ls)];
+                    const float wja[4] = {wj.x, wj.y, wj.z, wj.w};
+                    float ui = 0.0f, vi = 0.0f;
 #pragma unroll
                     for (int a = 0; a < 4; a++) {
-                        const double2* row = lat + (m0 + a) * NK + kb;
-                        const double2 n0 = row[0], n1 = row[1], n2 = row[2], n3 = row[3];
-                        xi = fma(wj[a], fma(wi[0], n0.x, fma(wi[1], n1.x, fma(wi[2], n2.x, wi[3] * n3.x))), xi);
-                        yi = fma(wj[a], fma(wi[0], n0.y, fma(wi[1], n1.y, fma(wi[2], n2.y, wi[3] * n3.y))), yi);
+                        const float2* row = lat + (m0 + a) * NK + kb;
+                        const float2 n0 = row[0], n1 = row[1], n2 = row[2], n3 = row[3];
+                        ui = fmaf(wja[a], fmaf(wi.x, n0.x, fmaf(wi.y, n1.x, fmaf(wi.z, n2.x, wi.w * n3.x))), ui);
+                        vi = fmaf(wja[a], fmaf(wi.x, n0.y, fmaf(wi.y, n1.y, fmaf(wi.z, n2.y, wi.w * n3.y))), vi);
                     }
+                    const float4 k0 = s_cls[0], k1 = s_cls[1];
                     const double xs = side ? -xx : xx, ys = side ? yym : yy;
-                    if (side) { xi = -xi; yi += dzm; }
-                    if (!(ok && fabs(xs - xi) <= chk && fabs(ys - yi) <= chk && cell_of(xs, ys) == c)) bad = true;
+                    if (side) { ui = k0.z - ui; vi += k0.w; }
+                    const float ue = (float)((xs - q.grid.gx_min) * inv_x), ve = (float)((ys - q.grid.gy_min) * inv_y);
+#ifdef SOLAT_INTERP_DEBUG
+                    if (cell_of(xs, ys) != c) printf("pix %d side %d c %d exact %d r %d i %d j %d ue %.5f ui %.5f ve %.5f vi %.5f\n", pix, side, c, cell_of(xs, ys), r, i, j, ue, ui, ve, vi);
+#endif
+                    bad |= (ok ? 0 : 1) | (fabsf(ue - ui) <= k1.z ? 0 : 2) | (fabsf(ve - vi) <= k1.w ? 0 : 4) | (cell_of(xs, ys) == c ? 0 : 8) | (side ? 16 : 32) * ((fabsf(ue - ui) <= k1.z && fabsf(ve - vi) <= k1.w) ? 0 : 1);
                     double cs, sn;
                     cis_large(q.k * opl / 1e3, cs, sn);
                     const double2 e = __ldg(q.e_rec + c);
@@ -2005,9 +2014,9 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
         }
         __syncthreads();
     }
-    if (bad) s_bad = 1;
+    if (bad) atomicOr(&s_bad, bad);
     __syncthreads();
-    if (tid == 0 && s_bad) q.redo[pix] = 1;
+    if (tid == 0 && s_bad) q.redo[pix] = s_bad;
     // the status of an item that is redone comes from the exact kernel (which traces a superset of these rays)
     if (st) atomicOr(q.status, st);
 }
@@ -2762,6 +2771,7 @@ static FfGrid make_grid(const double* data_x, const double* data_y, int M, const
     G.inv_dx = (M > 1 && sx > 0) ? (float)((M - 1) / sx) : 0.0f;   // first guess of searchsorted; the fix-up makes it exact
     G.inv_dy = (M > 1 && sy > 0) ? (float)((M - 1) / sy) : 0.0f;
     G.lean = G.y_uniform && axis_is_lean(data_x, M, 1) && axis_is_lean(data_y, M, M);
+    G.dev_u = (float)fmax(axis_deviation(data_x, M, 1), axis_deviation(data_y, M, M));
     return G;
 }
 
@@ -2934,8 +2944,9 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
     }
     q.rows = rows; q.rec = p->rec.p; q.rec_stride = stride;
     const bool interp = !panel && p->interp_s > 0 && rows && !q.win_g && p->lean;
-    q.redo = nullptr; q.interp_s = p->interp_s; q.th0 = p->th0; q.dth = p->dth; q.ph0 = p->ph0; q.dph = p->dph;
-    q.interp_eps = FF_INTERP_EPS_CM; q.interp_chk = FF_INTERP_EPS_CM / 4;
+    q.redo = nullptr; q.interp_s = p->interp_s; q.interp_ls = 0;
+    while ((1 << q.interp_ls) < p->interp_s) q.interp_ls++; q.th0 = p->th0; q.dth = p->dth; q.ph0 = p->ph0; q.dph = p->dph;
+    q.interp_eps = FF_INTERP_EPS_CM; q.interp_chk = FF_INTERP_EPS_CM / 3;
     if (interp) if (int rc = p->redo.reserve((size_t)chunk)) return rc;
     const double* azel = q.azel;
     double *amp = q.amp, *phase = q.phase;
@@ -2968,9 +2979,10 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
                 std::vector<int> h((size_t)n);
                 CK(cudaMemcpyAsync(h.data(), p->redo.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
                 CK(cudaStreamSynchronize(s));
-                long bad = 0;
-                for (int v : h) bad += v != 0;
-                fprintf(stderr, "[solat] ff_map_interp_kernel: %ld of %d items redone by the exact kernel (S = %d)\n", bad, n, p->interp_s);
+                long bad = 0, bits[6] = {0, 0, 0, 0, 0, 0};
+                for (int v : h) { bad += v != 0; for (int b = 0; b < 6; b++) bits[b] += (v >> b) & 1; }
+                fprintf(stderr, "[solat] ff_map_interp_kernel: %ld of %d items redone by the exact kernel (S = %d; invalid %ld, dx %ld, dy %ld, cell %ld, mirror %ld, own %ld)\n",
+                        bad, n, p->interp_s, bits[0], bits[1], bits[2], bits[3], bits[4], bits[5]);
             }
         }
         else if (p->lean && !q.win_g) ff_map_dispatch<0, true>(p->shape, q, n, p->smem, s);
@@ -3075,14 +3087,15 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
     p->interp_s = 0;
     if (!rc && p->lean && rows && nth == nph && nth >= FF_INTERP_MIN_N) {
         const char* env = getenv("SOLAT_FF_INTERP");       // "0": off; a number >= 2: that lattice spacing
-        int S = std::max(4, std::min(32, (nth + 32) / 64));
-        if (env && atoi(env) >= 2) S = atoi(env);
+        int S = 4;                                         // a power of two near nth / 64
+        while (S < 32 && 96 * S <= nth) S *= 2;
+        if (env && atoi(env) >= 2) { S = 2; while (S < atoi(env)) S *= 2; }
         const double dth = (theta[nth - 1] - theta[0]) / (nth - 1), dph = (phi[nph - 1] - phi[0]) / (nph - 1);
         bool uniform = true;
         for (int i = 0; i < nth && uniform; i++)
             uniform = fabs(theta[i] - (theta[0] + i * dth)) <= 1e-9 * fabs(dth) && fabs(phi[i] - (phi[0] + i * dph)) <= 1e-9 * fabs(dph);
         const FfInterpLayout L = ff_interp_layout(M, nth, nph, S, pairs ? 2 : 1);
-        if (uniform && !(env && env[0] == '0' && env[1] == 0) && L.total + 4608 <= cta_max && nth >= 4 * S) {
+        if (uniform && p->grid.dev_u < 1e-6f && !(env && env[0] == '0' && env[1] == 0) && L.total + 4608 <= cta_max && nth >= 4 * S) {
             p->interp_s = S; p->th0 = theta[0]; p->dth = dth; p->ph0 = phi[0]; p->dph = dph;
             if (cudaFuncSetAttribute(ff_map_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_max - 4608) != cudaSuccess)
                 p->interp_s = 0;

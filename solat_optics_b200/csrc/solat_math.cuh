@@ -1238,6 +1238,15 @@ SOLAT_HD int searchsorted_lean(const double* a, float n, double v, double a0, fl
 }
 // Host-side condition for searchsorted_lean: strictly increasing and |a[i] - (a[0] + i step)| < step / 4, so that the
 // single-precision guess (relative error 2e-7 on an index below 2^12) cannot miss by more than one.
+inline double axis_deviation(const double* a, int n, long stride)   // max |a[i] - (a[0] + i step)| / step
+{
+    if (n < 2) return 1.0;
+    const double a0 = a[0], step = (a[(long)(n - 1) * stride] - a0) / (n - 1);
+    if (!(step > 0.0)) return 1.0;
+    double d = 0.0;
+    for (int i = 0; i < n; i++) d = fmax(d, fabs(a[(long)i * stride] - (a0 + i * step)) / step);
+    return d;
+}
 inline bool axis_is_lean(const double* a, int n, long stride)
 {
     if (n < 2 || n > 4096) return false;
@@ -1270,6 +1279,7 @@ struct FfGrid {
     double gx_min, gy_min; // min(data_x[0, :]), min(data_y[:, 0]): rays below both pile into cell (0, 0)  (ffl:22-23)
     float inv_dx, inv_dy;  // (M-1)/(last-first) of gx and of gy[:,0]; 0 when not usable as a guess
     int lean;              // host: both axes pass axis_is_lean and all columns of data_y agree (searchsorted_lean applies)
+    float dev_u;           // host: largest deviation of either axis from a[0] + i step, in steps (ff_map_interp_kernel)
 };
 SOLAT_HD int ff_cell(double fx_mm, double fz_mm, const FfGrid& G)
 {

@@ -35,4 +35,7 @@ for tag, env in (("exact", {"SOLAT_FF_INTERP": "0"}), ("interp", {"SOLAT_FF_INTE
     outs.append(f)
 import numpy as np
 a, b = np.load(outs[0]), np.load(outs[1])
+d = np.nonzero((a[0] != b[0]) | (a[1] != b[1]))[0]
+side = int(round(np.sqrt(a.shape[1])))
+print("differing pixels", len(d), "of", a.shape[1], "first index // side:", sorted(set((d // side).tolist()))[:50], "index % side:", sorted(set((d % side).tolist()))[:50])
 print("bit-identical:", np.array_equal(a, b), "max |d amp| %.3e  max |d phase| %.3e" % (np.abs(a[0] - b[0]).max(), np.abs(a[1] - b[1]).max()))
