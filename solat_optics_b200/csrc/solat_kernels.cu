@@ -1692,19 +1692,21 @@ __global__ void __launch_bounds__(T, MINB) ff_map_kernel(FfMapParams q)
 //
 // The reference keeps, per E_rec cell, the last ray that lands in it (ffl:22-28): of the ~177 000 rays a config-5 pair
 // item lists, at most 2 x 101^2 = 20 402 count.  Which cell a ray lands in is a smooth function of its fan indices
-// (i, j): cubic interpolation between exactly traced rays 16 apart is good to 2e-4 mm (measured against the oracle
-// on a 1000^2 fan) against cells of 1 mm.  So:
+// (i, j): cubic interpolation between exactly traced rays 16 apart is good to 2e-4 mm (measured against exact traces
+// on a 1000^2 fan) against cells of 1 mm.  The lattice, the row nodes and the weights are kept in single precision and
+// in CELL UNITS u = (x - gx[0]) / step of the pixel's own table (|u| < 2^9: 3e-5 per rounding), so that a ray's cell is
+// ceil(u) and its distance to the nearest edge |u - rint(u)|, without a look at the axis.  So:
 //   1a  the CTA traces a lattice of rays, every S-th in both fan directions (one ring beyond the fan on either side,
 //       so that every ray has a full 4 x 4 stencil; the fan's axes are uniform, the host checks it): 66^2 rays;
 //   1b  a warp takes a phi row: row nodes by cubic interpolation across the four lattice rows around it, then, for
 //       every LISTED ray of the row (the intervals ff_prep_kernel left), the focal position by cubic interpolation
-//       along the row -> cell of the pixel's table and of the mirror pixel's.  A ray more than eps = 2e-3 mm inside
+//       along the row -> cell of the pixel's table and of the mirror pixel's.  A ray more than eps = 3e-3 mm inside
 //       a cell offers its index to the cell (32-bit atomicMax: ffl:28, the later ray wins); a ray surely beyond the
 //       high edges is dropped (ffl:19); a ray within eps of an edge is AMBIGUOUS: it is traced exactly and offered to
 //       the cells it really lands in;
 //   2   every cell's winner is traced exactly: path length -> phasor x E_rec, summed exactly as in ff_map_kernel (same
 //       scan order, same compaction, same lanes: identical bits).  Each winner's exact landing point is compared with
-//       its prediction: it must sit in the predicted cell and within chk = eps / 4 of the predicted position -- 20 000
+//       its prediction: it must sit in the predicted cell and within chk = eps / 3 of the predicted position -- 20 000
 //       probes per item, one in every cell, of an error field that is smooth on the scale of S rays.  An item that
 //       fails any of them (or has no row intervals) is flagged and ff_map_kernel, launched behind this kernel, redoes it.
 // Exact by construction as long as the interpolation error stays below eps, which is what the probes watch; the maps
@@ -2826,9 +2828,9 @@ struct solat_ff_plan {
     int key_shift;
     int M, n_rays, rows, shape, prefilter;
     int win_global;                         // the winner tables do not fit in shared memory: global scratch
-    int lean;                               // plain maps take ff_map_kernel<0, .., LEAN> (shared tables, lean E_rec axes)
+    int lean, lean_grid;                    // lean_grid: shared tables and lean E_rec axes (ff_map_kernel<0, .., LEAN> applies); lean: plain maps take it
     int interp_s;                           // > 0: large uniform fan, plain maps go through ff_map_interp_kernel with this lattice spacing
-    double th0, dth, ph0, dph;
+    double th0, dth, ph0, dph, interp_chk;
     DevBuf<int> redo;
     DevBuf<unsigned long long> win_g;
     size_t smem;
@@ -2943,10 +2945,10 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
         }
     }
     q.rows = rows; q.rec = p->rec.p; q.rec_stride = stride;
-    const bool interp = !panel && p->interp_s > 0 && rows && !q.win_g && p->lean;
+    const bool interp = !panel && p->interp_s > 0 && rows && !q.win_g && p->lean_grid;
     q.redo = nullptr; q.interp_s = p->interp_s; q.interp_ls = 0;
     while ((1 << q.interp_ls) < p->interp_s) q.interp_ls++; q.th0 = p->th0; q.dth = p->dth; q.ph0 = p->ph0; q.dph = p->dph;
-    q.interp_eps = FF_INTERP_EPS_CM; q.interp_chk = FF_INTERP_EPS_CM / 3;
+    q.interp_eps = FF_INTERP_EPS_CM; q.interp_chk = p->interp_chk;
     if (interp) if (int rc = p->redo.reserve((size_t)chunk)) return rc;
     const double* azel = q.azel;
     double *amp = q.amp, *phase = q.phase;
@@ -3080,12 +3082,17 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
     if (!rc) p->grid = make_grid(data_x, data_y, M, p->gx.p, p->gy.p);
     {
         const char* env = getenv("SOLAT_FF_LEAN");        // "0": the generic binning (A/B runs, tests)
-        p->lean = !rc && p->grid.lean && !win_global && !(env && env[0] == '0');
+        p->lean_grid = !rc && p->grid.lean && !win_global && !(env && env[0] == '0');
+        // measured (profiles/r02_variants.md): the lean binning pays on the 768 x 1 shape (config 5: -10 %), not on the
+        // small items of the 256 x 3 shape (config 2: +2 %)
+        p->lean = p->lean_grid && (shape == 2 || (env && env[0] == '1'));
     }
     // large fans: interpolated cells + exact winners (ff_map_interp_kernel).  Needs the lean grid, the interval walk,
     // a square fan with uniform axes, and room for the lattice next to the candidate tables.
     p->interp_s = 0;
-    if (!rc && p->lean && rows && nth == nph && nth >= FF_INTERP_MIN_N) {
+    p->interp_chk = FF_INTERP_EPS_CM / 3;
+    if (const char* env = getenv("SOLAT_FF_INTERP_CHK")) p->interp_chk = atof(env);   // tests: 0 fails every probe -> every item is redone
+    if (!rc && p->lean_grid && rows && p->prefilter && nth == nph && nth >= FF_INTERP_MIN_N) {
         const char* env = getenv("SOLAT_FF_INTERP");       // "0": off; a number >= 2: that lattice spacing
         int S = 4;                                         // a power of two near nth / 64
         while (S < 32 && 96 * S <= nth) S *= 2;

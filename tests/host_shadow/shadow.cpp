@@ -610,3 +610,17 @@ API void shadow_regrid(const double* field, int n_old, int n_new, double* out)
     for (int c = 0; c < n_new; c++)
         spline_line(tmp.data() + c, n_new, n_old, M.data(), M.data() + n_old, n_new, out + c, n_new);
 }
+
+// searchsorted_lean / axis_is_lean (the lean binning of ff_map_kernel): the axis is staged with its two sentinels
+// exactly as the kernel does it.  out[k] = index of v[k]; returns axis_is_lean(a).
+API int shadow_searchsorted_lean(const double* a, int n, const double* v, int nv, int* out)
+{
+    const bool lean = axis_is_lean(a, n, 1);
+    std::vector<double> s((size_t)n + 2);
+    s[0] = -INFINITY; s[(size_t)n + 1] = INFINITY;
+    for (int i = 0; i < n; i++) s[(size_t)i + 1] = a[i];
+    const double sx = a[n - 1] - a[0];
+    const float inv = (n > 1 && sx > 0) ? (float)((n - 1) / sx) : 0.0f;
+    for (int k = 0; k < nv; k++) out[k] = searchsorted_lean(s.data() + 1, (float)n, v[k], a[0], inv);
+    return lean ? 1 : 0;
+}

@@ -138,3 +138,12 @@ def regrid(field, n_new):
     out = np.zeros((n_new, n_new))
     lib().shadow_regrid(fp, ci(f.shape[0]), ci(n_new), out.ctypes.data_as(dp))
     return out
+
+
+def searchsorted_lean(axis, v):
+    """(indices, axis_is_lean) of the kernel's branch-free searchsorted on a staged axis."""
+    (a, ap), (v, vp) = D(axis), D(v)
+    out = np.zeros(len(v), dtype=np.int32)
+    lean = lib().shadow_searchsorted_lean(ap, ctypes.c_int(len(a)), vp, ctypes.c_int(len(v)),
+                                          out.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    return out, bool(lean)

@@ -1117,3 +1117,67 @@ def test_ff_beyond_the_former_limits(oracle):
     xy, st = plan.mirror_xy(many)
     one, _ = plan.mirror_xy(many[69990:69991])
     np.testing.assert_array_equal(xy[69990], one[0])
+
+
+def _env_plan(env, *args):
+    """A far-field plan created under temporary environment switches (read at plan creation)."""
+    from solat_optics_b200 import maps
+
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return maps.FarFieldPlan(*args, device=0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+def test_ff_interpolated_cells_equal_the_exact_walk(oracle):
+    """Large fans take ff_map_interp_kernel: cells from focal positions interpolated on a traced lattice, exact traces
+    for the winners only, every winner probed against its prediction, failed items redone by the exact kernel.  The
+    maps must not differ by a bit from the exact walk (SOLAT_FF_INTERP=0) -- with the lean binning on and off, with
+    every probe forced to fail (all items redone), for single pixels and mirror pairs -- and agree with the oracle."""
+    import bench
+    from solat_optics_b200 import maps
+
+    tg, px, x, y, e = _config5()
+    side = 2 * bench.NUM + 1
+    grid = px.reshape(side, side, 2)
+    # both signs of az, the az = 0 column, corners, and a list where some pixels have no mirror partner
+    sel = np.ascontiguousarray(np.r_[grid[::50, ::100].reshape(-1, 2), grid[3:200:37, 120]])
+    for n in (512, 1000):
+        th, phi = maps.ff_fan(n)
+        pts = sel if n == 512 else sel[::3]
+        a_i, p_i, st = _env_plan({}, tg, th, phi, x, y, e).run(pts)
+        assert st == 0
+        a_x, p_x, st = _env_plan({"SOLAT_FF_INTERP": "0"}, tg, th, phi, x, y, e).run(pts)
+        assert st == 0
+        np.testing.assert_array_equal(a_i, a_x); np.testing.assert_array_equal(p_i, p_x)
+        a_g, p_g, st = _env_plan({"SOLAT_FF_INTERP": "0", "SOLAT_FF_LEAN": "0"}, tg, th, phi, x, y, e).run(pts)
+        np.testing.assert_array_equal(a_g, a_x); np.testing.assert_array_equal(p_g, p_x)
+        if n == 512:
+            a_r, p_r, st = _env_plan({"SOLAT_FF_INTERP_CHK": "0"}, tg, th, phi, x, y, e).run(pts)   # every item redone
+            np.testing.assert_array_equal(a_r, a_x); np.testing.assert_array_equal(p_r, p_x)
+            a_s, p_s, st = _env_plan({"SOLAT_FF_INTERP": "4"}, tg, th, phi, x, y, e).run(pts)       # finer lattice
+            np.testing.assert_array_equal(a_s, a_x); np.testing.assert_array_equal(p_s, p_x)
+            oa, op = oracle.ff_map(oracle.ff_geo_vec(rx_y_m=-bench.OFFSET), pts[::4], th, phi, x, y, e, tg.k)
+            _assert_pixels(a_i[::4], p_i[::4], oa, op)
+    # an E_rec grid whose axes are not uniform, and a fan that is not: both keep the exact walk and still agree
+    xs = np.sign(x) * np.abs(x) ** 1.1
+    th, phi = maps.ff_fan(448)
+    a1, p1, st = _env_plan({}, tg, th, phi, xs, y, e).run(sel[:6])
+    a0, p0, st = _env_plan({"SOLAT_FF_INTERP": "0", "SOLAT_FF_LEAN": "0"}, tg, th, phi, xs, y, e).run(sel[:6])
+    np.testing.assert_array_equal(a1, a0); np.testing.assert_array_equal(p1, p0)
+    th2 = th[0] + (th - th[0]) * (1 + 0.02 * (th - th[0]) / (th[-1] - th[0]))
+    a1, p1, st = _env_plan({}, tg, th2, phi, x, y, e).run(sel[:6])
+    a0, p0, st = _env_plan({"SOLAT_FF_INTERP": "0", "SOLAT_FF_LEAN": "0"}, tg, th2, phi, x, y, e).run(sel[:6])
+    np.testing.assert_array_equal(a1, a0); np.testing.assert_array_equal(p1, p0)
+    # the lean binning on the small CTA shapes (off by default there: no gain measured) gives the same bits
+    th, phi = maps.ff_fan(100)
+    xc, yc, ec = x[::2, ::2], y[::2, ::2], e[::2, ::2]
+    a1, p1, st = _env_plan({"SOLAT_FF_LEAN": "1"}, tg, th, phi, xc, yc, ec).run(sel)
+    a0, p0, st = _env_plan({"SOLAT_FF_LEAN": "0"}, tg, th, phi, xc, yc, ec).run(sel)
+    np.testing.assert_array_equal(a1, a0); np.testing.assert_array_equal(p1, p0)

@@ -344,3 +344,26 @@ def test_nf_ray_mirror_symmetry(shadow):
             sign[[0, 8, 11, 14, 17, 20, 23]] = sx
             sign[[2, 10, 13, 16, 19, 22, 25]] = sz
             np.testing.assert_allclose(np.nan_to_num(out), sign[:, None] * np.nan_to_num(base), rtol=0, atol=RAY_TOL)
+
+
+def test_lean_searchsorted_equals_numpy(shadow):
+    """The branch-free searchsorted of the lean far-field binning (interpolated guess, one +-1 correction against
+    the staged axis with sentinels) equals np.searchsorted(a, v, 'left') on every axis the host check admits --
+    exact linspace axes, axes perturbed by up to a tenth of a step, values on, beside and far beyond the elements --
+    and the host check turns down axes it must not be used on."""
+    rng = np.random.default_rng(5)
+    for n in (2, 3, 51, 101, 168, 1000):
+        for jitter in (0.0, 1e-9, 0.1):
+            a = np.linspace(-5.0, 5.0, n) if n != 51 else np.linspace(-50.0, 50.0, n)
+            step = a[1] - a[0]
+            if jitter:
+                a = a + rng.uniform(-jitter, jitter, n) * step
+                a[0], a[-1] = min(a[0], a[1] - 1e-3 * step), max(a[-1], a[-2] + 1e-3 * step)
+            v = np.r_[a, np.nextafter(a, np.inf), np.nextafter(a, -np.inf), rng.uniform(a[0] - 3 * step, a[-1] + 3 * step, 4000),
+                      a[0] - 1e6, a[-1] + 1e6, 0.5 * (a[:-1] + a[1:])]
+            idx, lean = shadow.searchsorted_lean(a, v)
+            assert lean, (n, jitter)
+            np.testing.assert_array_equal(idx, np.searchsorted(a, v, "left"))
+    # not sorted, not uniform enough, degenerate: the generic binning keeps those
+    for bad in (np.r_[0.0, 2.0, 1.0, 3.0], np.r_[0.0, 1.0, 1.0, 3.0], np.linspace(0, 1, 50) ** 2, np.r_[1.0], np.zeros(5)):
+        assert not shadow.searchsorted_lean(bad, np.r_[0.5])[1]
