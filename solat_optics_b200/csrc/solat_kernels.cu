@@ -1902,14 +1902,11 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
             bool amb = false;
             int i = 0;
             if (v >= 0) {
-                int k = 0;
+                // the interval v falls in (prefix counts ascend; an empty interval never wins the comparison for long)
+                int d = lo[0] - p[0];
 #pragma unroll
-                for (int t = 1; t < FF_ROW_K; t++) k += (v >= p[t]) ? 1 : 0;
-                // (intervals may be empty: p[t] == p[t+1]; the count above lands on the last interval that starts at or before v)
-                int lo_k = lo[0], p_k = p[0];
-#pragma unroll
-                for (int t = 1; t < FF_ROW_K; t++) if (k == t) { lo_k = lo[t]; p_k = p[t]; }
-                i = lo_k + (v - p_k);
+                for (int t = 1; t < FF_ROW_K; t++) if (v >= p[t]) d = lo[t] - p[t];
+                i = v + d;
                 const int kb = i >> ls;
                 const float4 wi = wts[i - (kb << ls)];
                 const float2 n0 = rown[kb], n1 = rown[kb + 1], n2 = rown[kb + 2], n3 = rown[kb + 3];
@@ -3094,8 +3091,8 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
     if (const char* env = getenv("SOLAT_FF_INTERP_CHK")) p->interp_chk = atof(env);   // tests: 0 fails every probe -> every item is redone
     if (!rc && p->lean_grid && rows && p->prefilter && nth == nph && nth >= FF_INTERP_MIN_N) {
         const char* env = getenv("SOLAT_FF_INTERP");       // "0": off; a number >= 2: that lattice spacing
-        int S = 4;                                         // a power of two near nth / 64
-        while (S < 32 && 96 * S <= nth) S *= 2;
+        int S = 4;                                         // the largest power of two up to nth / 60: the probes were measured at 16 / 1000
+        while (S < 32 && 120 * S <= nth) S *= 2;
         if (env && atoi(env) >= 2) { S = 2; while (S < atoi(env)) S *= 2; }
         const double dth = (theta[nth - 1] - theta[0]) / (nth - 1), dph = (phi[nph - 1] - phi[0]) / (nph - 1);
         bool uniform = true;
