@@ -43,7 +43,8 @@ def main():
     ap.add_argument("--n-scan", type=int, default=100)
     ap.add_argument("--strict", action="store_true",
                     help="raise where the reference's brentq would (a root outside its bracket).  Rays the projection "
-                         "would skip anyway are not traced and report no status: set SOLAT_FF_PREFILTER=0 to trace and check "
+                         "would skip anyway are not traced and report no status (fans of 400^2 rays and more: only the "
+                         "lattice rays and the winner of every cell are): set SOLAT_FF_PREFILTER=0 to trace and check "
                          "every accepted ray as the reference does (saf:706)")
     ap.add_argument("--panels", choices=["auto", "off"], default="auto",
                     help="auto: when holosim-ml's pan_mod is importable, build the panel models as ff_sim.py:61-70 does "
