@@ -521,15 +521,17 @@ def run_ours(args):
         roof = {"bound": "fp64_simt", "peak": peak, "unit": "TFLOP/s", "achieved": None, "frac": None, "traffic": None,
                 "model_tflops": model_tf, "model_speedup": model_tf / peak,
                 "flop_per_unit_model": FLOP_FF_RAY, "units_per_launch": pixel_rays / world,
-                "kernel": "ff_map_kernel (dominant) + ff_pair_* + ff_prep_kernel of one rank's share, CUDA events around them: %.3f ms"
-                          % ms_kernels,
+                "kernel": "ff_map_interp_kernel (dominant: lattice + interpolated cells + exact winners) + ff_prep_kernel + ff_pair_* "
+                          "(+ the exact ff_map_kernel for flagged items) of one rank's share, CUDA events around them: %.3f ms" % ms_kernels,
                 "peak_source": "burst DFMA issue-rate probe run in this process (solat_fp64_peak, best of 5 x 2 ms launches); "
                                "MEASURED_PEAKS.json carries no FP64 figure; nominal %.1f = 148 SM x 64 lanes x 2 x 1.965 GHz" % NOMINAL_FP64_TFLOPS,
                 "note": "frac = EXECUTED FP64 FLOP (ncu thread-level DFMA x2 + DMUL + DADD of the profile capture, scaled per "
                         "pixel*ray) / live-measured kernel time / peak.  model_* = SURVEY 8d's reference-shaped count (626 FLOP per "
                         "launched ray: the reference traces every accepted ray twice) over the same time; the kernels execute far "
                         "fewer operations (rays the projection would skip are not traced, mirror pixels share a trace, "
-                        "mixed-precision Newton), so model_speedup can exceed 1 and is not a utilisation"}
+                        "mixed-precision Newton, and on fans of 400^2 rays and more only lattice rays and cell winners are traced "
+                        "at all: the dominant kernel is bound by issue slots, 76 % active, not by the FP64 pipe, 26 %), so "
+                        "model_speedup can exceed 1 and is not a utilisation"}
         ex = executed_entry(prof, "cfg5", pixel_rays / world, ms_kernels, peak)
         if ex:
             roof.update({"achieved": ex["executed_tflops"], "frac": ex["frac"], "frac_of_nominal": ex["frac_of_nominal"],

@@ -1735,19 +1735,27 @@ __host__ __device__ inline FfInterpLayout ff_interp_layout(int M, int nth, int n
     return L;
 }
 // np.searchsorted(a, v, 'left') on a uniform axis from u = (v - a[0]) / step alone, plus how sure the answer is.
-// c = the cell index, valid when neither flag is set: u is more than tol away from every integer, i.e. v more than eps
-// away from every element (below the first element searchsorted returns 0); skip: surely beyond the last element
-// (ffl:19 drops the ray); amb: within tol of an element, or NaN: the ray has to be traced.  Branch-free.  Single
-// precision is enough: |u| < 2^9, tol ~ 3e-3, of which 5e-4 are slack for the roundings (lattice values and weights in
-// single precision) and the axis' measured deviation from uniform (FfGrid::dev_u).
-// Returns (c << 2) | (amb ? 2 : 0) | (skip ? 1 : 0).
-__device__ __forceinline__ int ff_axis_class(float u, float u_last, float tol)
+// Returns ceil(u) -- the number of elements below v -- of u clamped to [-1/4, u_last + 3/4]: 0 at and below the first
+// element (searchsorted returns 0 there), M = u_last + 1 beyond the last one (ffl:19 drops the ray); `sure`: u is more
+// than tol away from every integer of [0, u_last], i.e. v more than eps away from every element (the clamp bounds sit
+// a quarter step away from one, so a value beyond them is sure).  NaN is the caller's business.  Branch-free.  Single
+// precision is enough: |u| < 2^9, tol ~ 3.5e-3, of which 5e-4 are slack for the roundings (lattice values and weights
+// in single precision) and the axis' measured deviation from uniform (FfGrid::dev_u).
+__device__ __forceinline__ int ff_axis_cell(float u, float u_hi, float tol, bool& sure)
 {
-    const float r = rintf(u);
-    const bool below = u < -tol, skip = u - u_last > tol;     // (the same subtraction as the edge test below: no gap at u_last + tol)
-    const bool amb = !(fabsf(u - r) > tol) && !below && !skip;
-    const int c = (below || skip) ? 0 : (int)r + (u > r ? 1 : 0);          // ceil(u): the number of elements below v
-    return (c << 2) | (amb ? 2 : 0) | (skip ? 1 : 0);
+    const float uc = fminf(fmaxf(u, -0.25f), u_hi);
+    const float r = rintf(uc), t = uc - r;
+    sure = fabsf(t) > tol;
+    return (int)r + (t > 0.0f ? 1 : 0);
+}
+// A ray's cell in one winner table from its predicted position: >= 0 the cell, surely; -1 surely dropped (beyond the
+// last element of either axis); -2 within tol of an edge that matters.
+__device__ __forceinline__ int ff_cell_class(float ux, float uy, float u_hi, float tol_x, float tol_y, int M)
+{
+    bool sx, sy;
+    const int cx = ff_axis_cell(ux, u_hi, tol_x, sx), cy = ff_axis_cell(uy, u_hi, tol_y, sy);
+    if ((cx == M && sx) || (cy == M && sy)) return -1;
+    return (sx && sy) ? cy * M + cx : -2;
 }
 __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapParams q)
 {
@@ -1811,11 +1819,11 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
     const float nf = (float)M;
     // cell units: u = (v - a[0]) * inv_step; the mirror pixel's ray lands at (-x, z + dzm): u_x' = umx - u_x, u_y' = u_y + umy
     const double inv_x = (double)q.grid.inv_dx, inv_y = (double)q.grid.inv_dy;
-    __shared__ float4 s_cls[2];      // (tol_x, tol_y, umx, umy), (M - 1, M - 1, chk_x, chk_y)
+    __shared__ float4 s_cls[2];      // (tol_x, tol_y, umx, umy), (M - 1 + 3/4, -, chk_x, chk_y)
     if (tid == 0) {
         const float tol_x = (float)(q.interp_eps * inv_x) + q.grid.dev_u + 5.0e-4f, tol_y = (float)(q.interp_eps * inv_y) + q.grid.dev_u + 5.0e-4f;
         s_cls[0] = make_float4(tol_x, tol_y, (float)(-2.0 * q.grid.gx_min * inv_x), (float)(dzm * inv_y));
-        s_cls[1] = make_float4((float)(M - 1), (float)(M - 1), (float)(q.interp_chk * inv_x), (float)(q.interp_chk * inv_y));
+        s_cls[1] = make_float4((float)(M - 1) + 0.75f, 0.0f, (float)(q.interp_chk * inv_x), (float)(q.interp_chk * inv_y));
     }
     const int ls = q.interp_ls;                               // S = 1 << ls
     int st = 0;
@@ -1857,7 +1865,12 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
         int rst;
         ff_aperture(sC, g, *fr, d, t_ap, Pa);
         ff_ray_lean<double>(sC, *fr, d, t_ap, Pa, g.foc_y, opl, fx, fz, rst);   // (a node's status is nobody's: it may lie outside the aperture)
-        lat[n] = make_float2((float)((div10(fx - cx) - q.grid.gx_min) * inv_x), (float)((div10(fz - cz) - q.grid.gy_min) * inv_y));
+        // a node whose trace did not end well (Newton not converged, a root outside its bracket, not finite) is NaN: every
+        // ray whose stencil holds it becomes ambiguous and is traced exactly, instead of being placed by a garbage value
+        const float qnan = __int_as_float(0x7fc00000);
+        const bool good = rst == 0 && !not_finite(fx) && !not_finite(fz);
+        lat[n] = good ? make_float2((float)((div10(fx - cx) - q.grid.gx_min) * inv_x), (float)((div10(fz - cz) - q.grid.gy_min) * inv_y))
+                      : make_float2(qnan, qnan);
     }
     __syncthreads();
 
@@ -1913,16 +1926,18 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
                 const float ux = fmaf(wi.x, n0.x, fmaf(wi.y, n1.x, fmaf(wi.z, n2.x, wi.w * n3.x)));
                 const float uy = fmaf(wi.x, n0.y, fmaf(wi.y, n1.y, fmaf(wi.z, n2.y, wi.w * n3.y)));
                 const float4 k0 = s_cls[0], k1 = s_cls[1];
+                const bool nan = !(ux + uy == ux + uy);          // a stencil node that could not be traced
                 if (out_pos >= 0) {
-                    const int kx = ff_axis_class(ux, k1.x, k0.x), ky = ff_axis_class(uy, k1.y, k0.y), f = kx | ky;
-                    if (!(f & 3)) offer(cand, (ky >> 2) * M + (kx >> 2), r_row + (unsigned)i);
-                    amb = (f & 3) == 2;                      // not surely skipped, and within tol of an edge on either axis
+                    const int c = ff_cell_class(ux, uy, k1.x, k0.x, k0.y, M);
+                    if (c >= 0 && !nan) offer(cand, c, r_row + (unsigned)i);
+                    amb = c == -2;
                 }
                 if (out_neg >= 0) {
-                    const int kx = ff_axis_class(k0.z - ux, k1.x, k0.x), ky = ff_axis_class(uy + k0.w, k1.y, k0.y), f = kx | ky;
-                    if (!(f & 3)) offer(cand + cells, (ky >> 2) * M + (kx >> 2), rm_row + (unsigned)i);
-                    amb = amb || (f & 3) == 2;
+                    const int c = ff_cell_class(k0.z - ux, uy + k0.w, k1.x, k0.x, k0.y, M);
+                    if (c >= 0 && !nan) offer(cand + cells, c, rm_row + (unsigned)i);
+                    amb = amb || c == -2;
                 }
+                amb = amb || nan;
             }
             const unsigned m = __ballot_sync(0xffffffffu, amb);
             if (m) {
@@ -1991,10 +2006,10 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
                     const double xs = side ? -xx : xx, ys = side ? yym : yy;
                     if (side) { ui = k0.z - ui; vi += k0.w; }
                     const float ue = (float)((xs - q.grid.gx_min) * inv_x), ve = (float)((ys - q.grid.gy_min) * inv_y);
-#ifdef SOLAT_INTERP_DEBUG
-                    if (cell_of(xs, ys) != c) printf("pix %d side %d c %d exact %d r %d i %d j %d ue %.5f ui %.5f ve %.5f vi %.5f\n", pix, side, c, cell_of(xs, ys), r, i, j, ue, ui, ve, vi);
-#endif
-                    bad |= (ok ? 0 : 1) | (fabsf(ue - ui) <= k1.z ? 0 : 2) | (fabsf(ve - vi) <= k1.w ? 0 : 4) | (cell_of(xs, ys) == c ? 0 : 8) | (side ? 16 : 32) * ((fabsf(ue - ui) <= k1.z && fabsf(ve - vi) <= k1.w) ? 0 : 1);
+                    // (no prediction where a stencil node could not be traced: that ray was placed by its exact trace)
+                    const bool pred = ui + vi == ui + vi;
+                    const bool near_x = !pred || fabsf(ue - ui) <= k1.z, near_y = !pred || fabsf(ve - vi) <= k1.w;
+                    bad |= (ok ? 0 : 1) | (near_x ? 0 : 2) | (near_y ? 0 : 4) | (cell_of(xs, ys) == c ? 0 : 8);
                     double cs, sn;
                     cis_large(q.k * opl / 1e3, cs, sn);
                     const double2 e = __ldg(q.e_rec + c);
@@ -2978,10 +2993,10 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
                 std::vector<int> h((size_t)n);
                 CK(cudaMemcpyAsync(h.data(), p->redo.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
                 CK(cudaStreamSynchronize(s));
-                long bad = 0, bits[6] = {0, 0, 0, 0, 0, 0};
-                for (int v : h) { bad += v != 0; for (int b = 0; b < 6; b++) bits[b] += (v >> b) & 1; }
-                fprintf(stderr, "[solat] ff_map_interp_kernel: %ld of %d items redone by the exact kernel (S = %d; invalid %ld, dx %ld, dy %ld, cell %ld, mirror %ld, own %ld)\n",
-                        bad, n, p->interp_s, bits[0], bits[1], bits[2], bits[3], bits[4], bits[5]);
+                long bad = 0, bits[4] = {0, 0, 0, 0};
+                for (int v : h) { bad += v != 0; for (int b = 0; b < 4; b++) bits[b] += (v >> b) & 1; }
+                fprintf(stderr, "[solat] ff_map_interp_kernel: %ld of %d items redone by the exact kernel (S = %d; winner invalid %ld, off in x %ld, off in y %ld, other cell %ld)\n",
+                        bad, n, p->interp_s, bits[0], bits[1], bits[2], bits[3]);
             }
         }
         else if (p->lean && !q.win_g) ff_map_dispatch<0, true>(p->shape, q, n, p->smem, s);

@@ -1165,6 +1165,16 @@ def test_ff_interpolated_cells_equal_the_exact_walk(oracle):
             np.testing.assert_array_equal(a_s, a_x); np.testing.assert_array_equal(p_s, p_x)
             oa, op = oracle.ff_map(oracle.ff_geo_vec(rx_y_m=-bench.OFFSET), pts[::4], th, phi, x, y, e, tg.k)
             _assert_pixels(a_i[::4], p_i[::4], oa, op)
+    # another telescope set-up (90 GHz, focal plane at 1.25 m), a coarser E_rec grid and a pixel list of a different scan
+    tg2 = maps.ff_tele_geo(90, 1.25)
+    px2 = maps.ff_pixels(tg2, 0.5, 6)
+    th, phi = maps.ff_fan(640)
+    xc, yc, ec = x[::2, ::2], y[::2, ::2], e[::2, ::2]
+    a1, p1, st = _env_plan({}, tg2, th, phi, xc, yc, ec).run(px2[::5])
+    a0, p0, st0 = _env_plan({"SOLAT_FF_INTERP": "0"}, tg2, th, phi, xc, yc, ec).run(px2[::5])
+    assert st == 0 and st0 == 0
+    # (51 x 51 tables: the exact walk runs 256- or 384-thread CTAs here and sums the same winners in another order)
+    np.testing.assert_allclose(a1, a0, rtol=1e-14, atol=0); assert np.abs(gu.wrap(p1 - p0)).max() < 1e-14
     # an E_rec grid whose axes are not uniform, and a fan that is not: both keep the exact walk and still agree
     xs = np.sign(x) * np.abs(x) ** 1.1
     th, phi = maps.ff_fan(448)
