@@ -1070,6 +1070,7 @@ struct FfMapParams {
     double interp_eps, interp_chk;   // [cm] a ray closer than eps to a cell edge is traced exactly; winners must match their prediction to chk
     int* redo;                   // [CTAs of the launch] interp kernel: 1 = prediction check failed, the exact kernel redoes the item;
                                  // exact kernel: when set, only the flagged CTAs run
+    float* probe_err;            // [CTAs of the launch] or nullptr (SOLAT_FF_INTERP_DEBUG): largest |exact - predicted| of an item's winners [cells]
 };
 
 __device__ __forceinline__ PanelErr load_panel(const double* pan, int np, int col)
@@ -1781,7 +1782,7 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
     const int nvr = FF_ROW_K * nph;
     int* row_lo = reinterpret_cast<int*>(smem_raw + L.rows);
     int* row_pre = row_lo + nvr;
-    __shared__ int s_queue_walk, s_row, s_bad;
+    __shared__ int s_queue_walk, s_row, s_bad, s_err;
     __shared__ double2 total;
 
     const FfGeom g = to_geom(q.g);
@@ -1791,7 +1792,7 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
         const int* src = reinterpret_cast<const int*>(rec);
         int* dst = reinterpret_cast<int*>(fr);
         for (int i = tid; i < (int)(sizeof(FfFrames) / sizeof(int)); i += T) dst[i] = __ldg(src + i);
-        if (tid == 0) { s_queue_walk = __ldg(reinterpret_cast<const int*>(rec + FF_REC_FRAMES)); s_row = nph - 1; s_bad = 0; }
+        if (tid == 0) { s_queue_walk = __ldg(reinterpret_cast<const int*>(rec + FF_REC_FRAMES)); s_row = nph - 1; s_bad = 0; s_err = 0; }
         const int* rows = reinterpret_cast<const int*>(rec + FF_REC_HEAD);
         for (int i = tid; i < 2 * nvr + 1; i += T) row_lo[i] = __ldg(rows + i);
     }
@@ -1964,6 +1965,7 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
 
     // ---- 2: the winners, traced exactly; sum_cells exp(i k L/1e3) * E_rec / M^2   (ff_sim.py:215-221)
     int bad = 0;
+    float worst = 0.0f;
     for (int side = 0; side < 2; side++) {
         const int out = side ? out_neg : out_pos;
         if (out < 0) continue;                                  // CTA-uniform
@@ -2009,6 +2011,7 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
                     // (no prediction where a stencil node could not be traced: that ray was placed by its exact trace)
                     const bool pred = ui + vi == ui + vi;
                     const bool near_x = !pred || fabsf(ue - ui) <= k1.z, near_y = !pred || fabsf(ve - vi) <= k1.w;
+                    if (pred) worst = fmaxf(worst, fmaxf(fabsf(ue - ui), fabsf(ve - vi)));
                     bad |= (ok ? 0 : 1) | (near_x ? 0 : 2) | (near_y ? 0 : 4) | (cell_of(xs, ys) == c ? 0 : 8);
                     double cs, sn;
                     cis_large(q.k * opl / 1e3, cs, sn);
@@ -2029,7 +2032,9 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
         __syncthreads();
     }
     if (bad) atomicOr(&s_bad, bad);
+    if (q.probe_err) atomicMax(&s_err, __float_as_int(worst));     // (non-negative floats order like their bit patterns)
     __syncthreads();
+    if (tid == 0 && q.probe_err) q.probe_err[pix] = __int_as_float(s_err);
     if (tid == 0 && s_bad) q.redo[pix] = s_bad;
     // the status of an item that is redone comes from the exact kernel (which traces a superset of these rays)
     if (st) atomicOr(q.status, st);
@@ -2843,6 +2848,7 @@ struct solat_ff_plan {
     int lean, lean_grid;                    // lean_grid: shared tables and lean E_rec axes (ff_map_kernel<0, .., LEAN> applies); lean: plain maps take it
     int interp_s;                           // > 0: large uniform fan, plain maps go through ff_map_interp_kernel with this lattice spacing
     double th0, dth, ph0, dph, interp_chk;
+    DevBuf<float> probe_err;
     DevBuf<int> redo;
     DevBuf<unsigned long long> win_g;
     size_t smem;
@@ -2958,7 +2964,7 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
     }
     q.rows = rows; q.rec = p->rec.p; q.rec_stride = stride;
     const bool interp = !panel && p->interp_s > 0 && rows && !q.win_g && p->lean_grid;
-    q.redo = nullptr; q.interp_s = p->interp_s; q.interp_ls = 0;
+    q.redo = nullptr; q.probe_err = nullptr; q.interp_s = p->interp_s; q.interp_ls = 0;
     while ((1 << q.interp_ls) < p->interp_s) q.interp_ls++; q.th0 = p->th0; q.dth = p->dth; q.ph0 = p->ph0; q.dph = p->dph;
     q.interp_eps = FF_INTERP_EPS_CM; q.interp_chk = p->interp_chk;
     if (interp) if (int rc = p->redo.reserve((size_t)chunk)) return rc;
@@ -2985,18 +2991,30 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
             // (none on the reference's geometry) are flagged and redone by the exact kernel right behind
             CK(cudaMemsetAsync(p->redo.p, 0, sizeof(int) * (size_t)n, s));
             q.redo = p->redo.p;
+            const char* dbg = getenv("SOLAT_FF_INTERP_DEBUG");
+            q.probe_err = nullptr;
+            if (dbg && dbg[0] == '1') {
+                if (int rc = p->probe_err.reserve((size_t)n)) return rc;
+                CK(cudaMemsetAsync(p->probe_err.p, 0, sizeof(float) * (size_t)n, s));
+                q.probe_err = p->probe_err.p;
+            }
             const FfInterpLayout L = ff_interp_layout(p->M, p->ang.tabs.nth, p->ang.tabs.nph, p->interp_s, pairs ? 2 : 1);
             ff_map_interp_kernel<<<n, FF_INTERP_T, L.total, s>>>(q);
             LAUNCHED();
             ff_map_dispatch<0, true>(p->shape, q, n, p->smem, s);
-            if (const char* dbg = getenv("SOLAT_FF_INTERP_DEBUG")) if (dbg[0] == '1') {      // how many items were redone
+            if (dbg && dbg[0] == '1') {      // how many items were redone, and how far the probes were from their predictions
                 std::vector<int> h((size_t)n);
+                std::vector<float> he((size_t)n);
+                CK(cudaMemcpyAsync(he.data(), p->probe_err.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, s));
                 CK(cudaMemcpyAsync(h.data(), p->redo.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
                 CK(cudaStreamSynchronize(s));
                 long bad = 0, bits[4] = {0, 0, 0, 0};
                 for (int v : h) { bad += v != 0; for (int b = 0; b < 4; b++) bits[b] += (v >> b) & 1; }
-                fprintf(stderr, "[solat] ff_map_interp_kernel: %ld of %d items redone by the exact kernel (S = %d; winner invalid %ld, off in x %ld, off in y %ld, other cell %ld)\n",
-                        bad, n, p->interp_s, bits[0], bits[1], bits[2], bits[3]);
+                float worst = 0.0f;
+                for (float v : he) worst = std::max(worst, v);
+                fprintf(stderr, "[solat] ff_map_interp_kernel: %ld of %d items redone by the exact kernel (S = %d; winner invalid %ld, off in x %ld, off in y %ld, other cell %ld); "
+                        "worst probe %.3g cells (allowed %.3g, ambiguity margin %.3g)\n",
+                        bad, n, p->interp_s, bits[0], bits[1], bits[2], bits[3], worst, q.interp_chk * p->grid.inv_dx, q.interp_eps * p->grid.inv_dx);
             }
         }
         else if (p->lean && !q.win_g) ff_map_dispatch<0, true>(p->shape, q, n, p->smem, s);
