@@ -335,6 +335,8 @@ __device__ __forceinline__ unsigned ff_pair_hash(long long bucket, double e)
     return (unsigned)(x * 0xBF58476D1CE4E5B9ull >> 32);
 }
 // phase 1: every pixel with az >= 0 claims a slot.  ints[0] = number of items, ints[1] = length of the overflow list
+// (POW2: the table has a power-of-two number of slots, h & (nslots - 1) instead of the integer division)
+template <bool POW2 = false>
 __device__ __forceinline__ void ff_pair_insert(int p, const double* azel, FfPairSlot* slots, unsigned nslots, int* over, int* ints,
                                                const PairTol& tol)
 {
@@ -342,7 +344,7 @@ __device__ __forceinline__ void ff_pair_insert(int p, const double* azel, FfPair
     if (!(az == az) || !(el == el)) { over[atomicAdd(ints + 1, 1)] = p; return; }   // NaN pointing: an item of its own
     if (az < 0.0) return;
     if (!(az < tol.limit)) { over[atomicAdd(ints + 1, 1)] = p; return; }             // beyond the bucket range: an item of its own
-    unsigned h = ff_pair_hash(ff_pair_bucket(az, tol), el) % nslots;
+    unsigned h = POW2 ? ff_pair_hash(ff_pair_bucket(az, tol), el) & (nslots - 1) : ff_pair_hash(ff_pair_bucket(az, tol), el) % nslots;
     for (;;) {
         const int o = atomicCAS(&slots[h].owner, -1, p);
         if (o == -1) { slots[h].pos = p; return; }
@@ -354,6 +356,7 @@ __device__ __forceinline__ void ff_pair_insert(int p, const double* azel, FfPair
     }
 }
 // phase 2: every pixel with az < 0 looks for the slot of its mirror pixel
+template <bool POW2 = false>
 __device__ __forceinline__ void ff_pair_attach(int p, const double* azel, FfPairSlot* slots, unsigned nslots, int* over, int* ints,
                                                const PairTol& tol)
 {
@@ -362,7 +365,7 @@ __device__ __forceinline__ void ff_pair_attach(int p, const double* azel, FfPair
     const double a = -az;
     for (int dk = 0; dk < 3 && a < tol.limit; dk++) {
         const long long bucket = ff_pair_bucket(a, tol) + (dk == 0 ? 0 : (dk == 1 ? -1 : 1));
-        unsigned h = ff_pair_hash(bucket, el) % nslots;
+        unsigned h = POW2 ? ff_pair_hash(bucket, el) & (nslots - 1) : ff_pair_hash(bucket, el) % nslots;
         for (;;) {
             const int o = slots[h].owner;
             if (o == -1) break;
@@ -414,32 +417,36 @@ __global__ void ff_pair_emit_kernel(const double* azel, FfPairSlot* slots, unsig
 // all three phases in one CTA with the table in shared memory (pixel lists up to FF_PAIR_ONE_CTA: one short launch
 // instead of three); ints[0] = number of items
 constexpr int FF_PAIR_ONE_CTA = 4096;
-static size_t ff_pair_smem(int npix) { return (2 * (size_t)npix + 1) * sizeof(FfPairSlot) + ((size_t)npix + 2) * sizeof(int); }
+static unsigned ff_pair_slots(int npix) { unsigned n = 2; while (n < 2u * (unsigned)npix) n *= 2; return n; }   // power of two, load factor <= 1/2
+static size_t ff_pair_smem(int npix) { return (size_t)ff_pair_slots(npix) * sizeof(FfPairSlot) + ((size_t)npix + 2) * sizeof(int) + 8 + 2 * (size_t)npix * sizeof(double); }
 // Second stage (near-field quads, items2 != nullptr): the items of the first stage are paired once more on their
-// second coordinate -- item k -> (z, |x|) written to `scratch` -- and the items that come out hold |z|, |x| and the
-// indices of the first-stage items of (+z) and (-z); ints[2] = their number.
-__global__ void __launch_bounds__(1024) ff_pair_kernel(const double* azel, int npix, int* ints, FfItem* items, PairTol tol,
-                                                        FfItem* items2 = nullptr, double* scratch = nullptr)
+// second coordinate -- item k -> (z, |x|) -- and the items that come out hold |z|, |x| and the indices of the
+// first-stage items of (+z) and (-z); ints[2] = their number.  The pixel list is staged in shared memory (every phase
+// reads it several times, and a lone CTA has nothing to hide global latency behind).
+__global__ void __launch_bounds__(1024) ff_pair_kernel(const double* azel_g, int npix, unsigned nslots, int* ints, FfItem* items, PairTol tol,
+                                                        FfItem* items2 = nullptr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const unsigned nslots = 2u * (unsigned)npix + 1u;
     FfPairSlot* slots = reinterpret_cast<FfPairSlot*>(smem_raw);
     int* cnt = reinterpret_cast<int*>(slots + nslots);      // [0] items, [1] overflow length
     int* over = cnt + 2;
+    double* azel = reinterpret_cast<double*>((reinterpret_cast<size_t>(over + npix) + 7) / 8 * 8);   // [npix][2]
     for (int stage = 0; stage < (items2 ? 2 : 1); stage++) {
         for (unsigned h = threadIdx.x; h < nslots; h += blockDim.x) slots[h].owner = slots[h].pos = slots[h].neg = -1;
         if (stage) {
             npix = cnt[0];
-            for (int p = threadIdx.x; p < npix; p += blockDim.x) { scratch[2 * p] = items[p].el; scratch[2 * p + 1] = items[p].az; }
-            azel = scratch;                                 // global memory written by this CTA: visible after the barrier
+            __syncthreads();                                // (cnt[0] is cleared below)
+            for (int p = threadIdx.x; p < npix; p += blockDim.x) { azel[2 * p] = items[p].el; azel[2 * p + 1] = items[p].az; }   // this CTA's own writes
             items = items2;
+        } else {
+            for (int p = threadIdx.x; p < 2 * npix; p += blockDim.x) azel[p] = __ldg(azel_g + p);
         }
         __syncthreads();
         if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
         __syncthreads();
-        for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_insert(p, azel, slots, nslots, over, cnt, tol);
+        for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_insert<true>(p, azel, slots, nslots, over, cnt, tol);
         __syncthreads();
-        for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_attach(p, azel, slots, nslots, over, cnt, tol);
+        for (int p = threadIdx.x; p < npix; p += blockDim.x) ff_pair_attach<true>(p, azel, slots, nslots, over, cnt, tol);
         __syncthreads();
         for (unsigned h = threadIdx.x; h < nslots; h += blockDim.x) ff_pair_emit(h, azel, slots, nslots, over, cnt, nullptr, items);
         __syncthreads();
@@ -2460,8 +2467,8 @@ static int nf_map_contract(solat_nf_plan* p, const double* d_src, int npix, doub
     g.partial = p->partial.p;
     for (int pix0 = 0; pix0 < npix; pix0 += piece) {
         const int n = std::min(piece, npix - pix0);
-        ff_pair_kernel<<<1, 1024, ff_pair_smem(n), s>>>(d_src + 2 * (size_t)pix0, n, p->pair_ints.p, p->items.p, NF_PAIR_TOL,
-                                                        p->items.p + piece, p->pair_xz.p);
+        ff_pair_kernel<<<1, 1024, ff_pair_smem(n), s>>>(d_src + 2 * (size_t)pix0, n, ff_pair_slots(n), p->pair_ints.p, p->items.p, NF_PAIR_TOL,
+                                                        p->items.p + piece);
         LAUNCHED();
         g.pix0 = pix0;
         // the number of quad items is known on the device only: passes over [row0, row0 + rows) up to the bound n, the
@@ -2523,8 +2530,8 @@ static int nf_map_launch(solat_nf_plan* p, const double* d_src, int npix, double
         if (int rc = p->pair_ints.reserve(8)) return rc;
         if (quads)
             if (int rc = p->pair_xz.reserve(2 * (size_t)npix)) return rc;
-        ff_pair_kernel<<<1, 1024, ff_pair_smem(npix), s>>>(d_src, npix, p->pair_ints.p, p->items.p, NF_PAIR_TOL,
-                                                           quads ? p->items.p + npix : nullptr, quads ? p->pair_xz.p : nullptr);
+        ff_pair_kernel<<<1, 1024, ff_pair_smem(npix), s>>>(d_src, npix, ff_pair_slots(npix), p->pair_ints.p, p->items.p, NF_PAIR_TOL,
+                                                           quads ? p->items.p + npix : nullptr);
         LAUNCHED();
         q.items = p->items.p; q.counters = p->pair_ints.p;
         if (quads) { q.items2 = p->items.p + npix; q.counters2 = p->pair_ints.p + 2; }
@@ -2925,7 +2932,7 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
         if (npix <= FF_PAIR_ONE_CTA) {
             if (int rc = p->pair_ints.reserve(8)) return rc;
             ints = p->pair_ints.p;
-            ff_pair_kernel<<<1, 1024, ff_pair_smem(npix), s>>>(q.azel, npix, ints, p->items.p, FF_PAIR_TOL);
+            ff_pair_kernel<<<1, 1024, ff_pair_smem(npix), s>>>(q.azel, npix, ff_pair_slots(npix), ints, p->items.p, FF_PAIR_TOL);
             LAUNCHED();
         } else {
             const unsigned nslots = 2u * (unsigned)npix + 1u;
