@@ -417,7 +417,7 @@ __global__ void ff_pair_emit_kernel(const double* azel, FfPairSlot* slots, unsig
 // all three phases in one CTA with the table in shared memory (pixel lists up to FF_PAIR_ONE_CTA: one short launch
 // instead of three); ints[0] = number of items
 constexpr int FF_PAIR_ONE_CTA = 4096;
-static unsigned ff_pair_slots(int npix) { unsigned n = 2; while (n < 2u * (unsigned)npix) n *= 2; return n; }   // power of two, load factor <= 1/2
+static unsigned ff_pair_slots(int npix) { unsigned n = 2; while (2 * n < 3u * (unsigned)npix) n *= 2; return n; }   // power of two, load factor <= 2/3
 static size_t ff_pair_smem(int npix) { return (size_t)ff_pair_slots(npix) * sizeof(FfPairSlot) + ((size_t)npix + 2) * sizeof(int) + 8 + 2 * (size_t)npix * sizeof(double); }
 // Second stage (near-field quads, items2 != nullptr): the items of the first stage are paired once more on their
 // second coordinate -- item k -> (z, |x|) -- and the items that come out hold |z|, |x| and the indices of the
@@ -1789,7 +1789,7 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
     const int nvr = FF_ROW_K * nph;
     int* row_lo = reinterpret_cast<int*>(smem_raw + L.rows);
     int* row_pre = row_lo + nvr;
-    __shared__ int s_queue_walk, s_row, s_bad, s_err;
+    __shared__ int s_queue_walk, s_row, s_bad, s_err, s_hull[4];   // s_hull: min / max listed theta index, min / max listed phi row
     __shared__ double2 total;
 
     const FfGeom g = to_geom(q.g);
@@ -1799,7 +1799,10 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
         const int* src = reinterpret_cast<const int*>(rec);
         int* dst = reinterpret_cast<int*>(fr);
         for (int i = tid; i < (int)(sizeof(FfFrames) / sizeof(int)); i += T) dst[i] = __ldg(src + i);
-        if (tid == 0) { s_queue_walk = __ldg(reinterpret_cast<const int*>(rec + FF_REC_FRAMES)); s_row = nph - 1; s_bad = 0; s_err = 0; }
+        if (tid == 0) {
+            s_queue_walk = __ldg(reinterpret_cast<const int*>(rec + FF_REC_FRAMES)); s_row = nph - 1; s_bad = 0; s_err = 0;
+            s_hull[0] = s_hull[2] = 0x7fffffff; s_hull[1] = s_hull[3] = -1;
+        }
         const int* rows = reinterpret_cast<const int*>(rec + FF_REC_HEAD);
         for (int i = tid; i < 2 * nvr + 1; i += T) row_lo[i] = __ldg(rows + i);
     }
@@ -1858,9 +1861,20 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
         if (*reinterpret_cast<volatile unsigned*>(tab + cell) < r) atomicMax(tab + cell, r);   // ffl:28
     };
 
-    // ---- 1a: the lattice
-    for (int n = tid; n < NK * NK; n += T) {
-        const int mm = n / NK, kk = n - mm * NK;
+    // ---- 1a: the lattice, as far as the stencils of the listed rays reach
+    {
+        int i0 = 0x7fffffff, i1 = -1, j0 = 0x7fffffff, j1 = -1;
+        for (int vr = tid; vr < nvr; vr += T) {
+            const int c = row_pre[vr + 1] - row_pre[vr];
+            if (c > 0) { const int lo = row_lo[vr], j = vr / FF_ROW_K; i0 = min(i0, lo); i1 = max(i1, lo + c - 1); j0 = min(j0, j); j1 = max(j1, j); }
+        }
+        if (i1 >= 0) { atomicMin(&s_hull[0], i0); atomicMax(&s_hull[1], i1); atomicMin(&s_hull[2], j0); atomicMax(&s_hull[3], j1); }
+        __syncthreads();
+    }
+    const int hk0 = s_hull[0] >> ls, hk1 = (s_hull[1] >> ls) + 3, hm0 = s_hull[2] >> ls, hm1 = (s_hull[3] >> ls) + 3;   // node indices (array)
+    const int hw = max(hk1 - hk0 + 1, 0), hn = hw * max(hm1 - hm0 + 1, 0);     // (an item without a listed ray: no node)
+    for (int nn = tid; nn < hn; nn += T) {
+        const int mm = hm0 + nn / hw, kk = hk0 + nn % hw, n = mm * NK + kk;
         const int i = (kk - 1) * S, j = (mm - 1) * S;
         double sth, cth, sph, cph;
         if (i >= 0 && i < nth) { const double2 v = __ldg(q.ang.tsc + i); sth = v.x; cth = v.y; }
