@@ -1077,6 +1077,8 @@ struct FfMapParams {
     double interp_eps, interp_chk;   // [cm] a ray closer than eps to a cell edge is traced exactly; winners must match their prediction to chk
     int* redo;                   // [CTAs of the launch] interp kernel: 1 = prediction check failed, the exact kernel redoes the item;
                                  // exact kernel: when set, only the flagged CTAs run
+    float i_tol_x, i_tol_y, i_uhi, i_umx, i_chk_x, i_chk_y;   // the classifier's constants in cell units (ff_map_run): they reach the
+                                 // single-precision instructions as constant-bank operands, no register, no load
     float* probe_err;            // [CTAs of the launch] or nullptr (SOLAT_FF_INTERP_DEBUG): largest |exact - predicted| of an item's winners [cells]
 };
 
@@ -1830,12 +1832,8 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
     const float nf = (float)M;
     // cell units: u = (v - a[0]) * inv_step; the mirror pixel's ray lands at (-x, z + dzm): u_x' = umx - u_x, u_y' = u_y + umy
     const double inv_x = (double)q.grid.inv_dx, inv_y = (double)q.grid.inv_dy;
-    __shared__ float4 s_cls[2];      // (tol_x, tol_y, umx, umy), (M - 1 + 3/4, -, chk_x, chk_y)
-    if (tid == 0) {
-        const float tol_x = (float)(q.interp_eps * inv_x) + q.grid.dev_u + 5.0e-4f, tol_y = (float)(q.interp_eps * inv_y) + q.grid.dev_u + 5.0e-4f;
-        s_cls[0] = make_float4(tol_x, tol_y, (float)(-2.0 * q.grid.gx_min * inv_x), (float)(dzm * inv_y));
-        s_cls[1] = make_float4((float)(M - 1) + 0.75f, 0.0f, (float)(q.interp_chk * inv_x), (float)(q.interp_chk * inv_y));
-    }
+    __shared__ float s_umy;          // the mirror pixel's z offset in cell units (the only item-dependent constant of the classifier)
+    if (tid == 0) s_umy = (float)(dzm * inv_y);
     const int ls = q.interp_ls;                               // S = 1 << ls
     int st = 0;
 
@@ -1947,15 +1945,14 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
                 const float2 n0 = rown[kb], n1 = rown[kb + 1], n2 = rown[kb + 2], n3 = rown[kb + 3];
                 const float ux = fmaf(wi.x, n0.x, fmaf(wi.y, n1.x, fmaf(wi.z, n2.x, wi.w * n3.x)));
                 const float uy = fmaf(wi.x, n0.y, fmaf(wi.y, n1.y, fmaf(wi.z, n2.y, wi.w * n3.y)));
-                const float4 k0 = s_cls[0], k1 = s_cls[1];
                 const bool nan = !(ux + uy == ux + uy);          // a stencil node that could not be traced
                 if (out_pos >= 0) {
-                    const int c = ff_cell_class(ux, uy, k1.x, k0.x, k0.y, M);
+                    const int c = ff_cell_class(ux, uy, q.i_uhi, q.i_tol_x, q.i_tol_y, M);
                     if (c >= 0 && !nan) offer(cand, c, r_row + (unsigned)i);
                     amb = c == -2;
                 }
                 if (out_neg >= 0) {
-                    const int c = ff_cell_class(k0.z - ux, uy + k0.w, k1.x, k0.x, k0.y, M);
+                    const int c = ff_cell_class(q.i_umx - ux, uy + s_umy, q.i_uhi, q.i_tol_x, q.i_tol_y, M);
                     if (c >= 0 && !nan) offer(cand + cells, c, rm_row + (unsigned)i);
                     amb = amb || c == -2;
                 }
@@ -2025,13 +2022,12 @@ __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapPara
                         ui = fmaf(wja[a], fmaf(wi.x, n0.x, fmaf(wi.y, n1.x, fmaf(wi.z, n2.x, wi.w * n3.x))), ui);
                         vi = fmaf(wja[a], fmaf(wi.x, n0.y, fmaf(wi.y, n1.y, fmaf(wi.z, n2.y, wi.w * n3.y))), vi);
                     }
-                    const float4 k0 = s_cls[0], k1 = s_cls[1];
                     const double xs = side ? -xx : xx, ys = side ? yym : yy;
-                    if (side) { ui = k0.z - ui; vi += k0.w; }
+                    if (side) { ui = q.i_umx - ui; vi += s_umy; }
                     const float ue = (float)((xs - q.grid.gx_min) * inv_x), ve = (float)((ys - q.grid.gy_min) * inv_y);
                     // (no prediction where a stencil node could not be traced: that ray was placed by its exact trace)
                     const bool pred = ui + vi == ui + vi;
-                    const bool near_x = !pred || fabsf(ue - ui) <= k1.z, near_y = !pred || fabsf(ve - vi) <= k1.w;
+                    const bool near_x = !pred || fabsf(ue - ui) <= q.i_chk_x, near_y = !pred || fabsf(ve - vi) <= q.i_chk_y;
                     if (pred) worst = fmaxf(worst, fmaxf(fabsf(ue - ui), fabsf(ve - vi)));
                     bad |= (ok ? 0 : 1) | (near_x ? 0 : 2) | (near_y ? 0 : 4) | (cell_of(xs, ys) == c ? 0 : 8);
                     double cs, sn;
@@ -2988,6 +2984,12 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
     q.redo = nullptr; q.probe_err = nullptr; q.interp_s = p->interp_s; q.interp_ls = 0;
     while ((1 << q.interp_ls) < p->interp_s) q.interp_ls++; q.th0 = p->th0; q.dth = p->dth; q.ph0 = p->ph0; q.dph = p->dph;
     q.interp_eps = FF_INTERP_EPS_CM; q.interp_chk = p->interp_chk;
+    {   // cell units: u = (v - a[0]) * inv_step; 5e-4 of slack for the single-precision lattice, weights and roundings
+        const double ix = (double)p->grid.inv_dx, iy = (double)p->grid.inv_dy;
+        q.i_tol_x = (float)(q.interp_eps * ix) + p->grid.dev_u + 5.0e-4f; q.i_tol_y = (float)(q.interp_eps * iy) + p->grid.dev_u + 5.0e-4f;
+        q.i_uhi = (float)(p->M - 1) + 0.75f; q.i_umx = (float)(-2.0 * p->grid.gx_min * ix);   // the mirror pixel's ray lands at (-x, z + dzm)
+        q.i_chk_x = (float)(q.interp_chk * ix); q.i_chk_y = (float)(q.interp_chk * iy);
+    }
     if (interp) if (int rc = p->redo.reserve((size_t)chunk)) return rc;
     const double* azel = q.azel;
     double *amp = q.amp, *phase = q.phase;
