@@ -1744,29 +1744,6 @@ __host__ __device__ inline FfInterpLayout ff_interp_layout(int M, int nth, int n
     L.total = o;
     return L;
 }
-// np.searchsorted(a, v, 'left') on a uniform axis from u = (v - a[0]) / step alone, plus how sure the answer is.
-// Returns ceil(u) -- the number of elements below v -- of u clamped to [-1/4, u_last + 3/4]: 0 at and below the first
-// element (searchsorted returns 0 there), M = u_last + 1 beyond the last one (ffl:19 drops the ray); `sure`: u is more
-// than tol away from every integer of [0, u_last], i.e. v more than eps away from every element (the clamp bounds sit
-// a quarter step away from one, so a value beyond them is sure).  NaN is the caller's business.  Branch-free.  Single
-// precision is enough: |u| < 2^9, tol ~ 3.5e-3, of which 5e-4 are slack for the roundings (lattice values and weights
-// in single precision) and the axis' measured deviation from uniform (FfGrid::dev_u).
-__device__ __forceinline__ int ff_axis_cell(float u, float u_hi, float tol, bool& sure)
-{
-    const float uc = fminf(fmaxf(u, -0.25f), u_hi);
-    const float r = rintf(uc), t = uc - r;
-    sure = fabsf(t) > tol;
-    return (int)r + (t > 0.0f ? 1 : 0);
-}
-// A ray's cell in one winner table from its predicted position: >= 0 the cell, surely; -1 surely dropped (beyond the
-// last element of either axis); -2 within tol of an edge that matters.
-__device__ __forceinline__ int ff_cell_class(float ux, float uy, float u_hi, float tol_x, float tol_y, int M)
-{
-    bool sx, sy;
-    const int cx = ff_axis_cell(ux, u_hi, tol_x, sx), cy = ff_axis_cell(uy, u_hi, tol_y, sy);
-    if ((cx == M && sx) || (cy == M && sy)) return -1;
-    return (sx && sy) ? cy * M + cx : -2;
-}
 __global__ void __launch_bounds__(FF_INTERP_T, 1) ff_map_interp_kernel(FfMapParams q)
 {
     constexpr int T = FF_INTERP_T, WARPS = T / 32;

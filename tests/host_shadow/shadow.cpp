@@ -624,3 +624,9 @@ API int shadow_searchsorted_lean(const double* a, int n, const double* v, int nv
     for (int k = 0; k < nv; k++) out[k] = searchsorted_lean(s.data() + 1, (float)n, v[k], a[0], inv);
     return lean ? 1 : 0;
 }
+
+// ff_cell_class (ff_map_interp_kernel): class of predicted positions (ux, uy) in cell units on an M x M table
+API void shadow_cell_class(const float* ux, const float* uy, int n, int M, float tol_x, float tol_y, int* out)
+{
+    for (int k = 0; k < n; k++) out[k] = ff_cell_class(ux[k], uy[k], (float)(M - 1) + 0.75f, tol_x, tol_y, M);
+}

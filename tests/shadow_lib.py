@@ -147,3 +147,13 @@ def searchsorted_lean(axis, v):
     lean = lib().shadow_searchsorted_lean(ap, ctypes.c_int(len(a)), vp, ctypes.c_int(len(v)),
                                           out.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
     return out, bool(lean)
+
+
+def cell_class(ux, uy, M, tol_x, tol_y):
+    """ff_cell_class of the interpolated-cell kernel for predicted positions in cell units."""
+    ux = np.ascontiguousarray(ux, dtype=np.float32); uy = np.ascontiguousarray(uy, dtype=np.float32)
+    out = np.zeros(len(ux), dtype=np.int32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib().shadow_cell_class(ux.ctypes.data_as(fp), uy.ctypes.data_as(fp), ctypes.c_int(len(ux)), ctypes.c_int(M),
+                            ctypes.c_float(tol_x), ctypes.c_float(tol_y), out.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    return out

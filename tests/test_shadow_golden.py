@@ -367,3 +367,39 @@ def test_lean_searchsorted_equals_numpy(shadow):
     # not sorted, not uniform enough, degenerate: the generic binning keeps those
     for bad in (np.r_[0.0, 2.0, 1.0, 3.0], np.r_[0.0, 1.0, 1.0, 3.0], np.linspace(0, 1, 50) ** 2, np.r_[1.0], np.zeros(5)):
         assert not shadow.searchsorted_lean(bad, np.r_[0.5])[1]
+
+
+def test_interpolated_cell_class_is_conservative(shadow):
+    """The classifier of ff_map_interp_kernel works on predicted positions u = (v - a[0]) / step.  Its contract: a
+    class >= 0 is the cell np.searchsorted gives for EVERY true position within tol of the prediction; -1 means every
+    such position lies beyond the last element of an axis (far_field_latrt.py:19 drops the ray); anything that a
+    perturbation of up to tol could move to another cell, or in or out of the grid, is -2 (traced exactly)."""
+    rng = np.random.default_rng(11)
+    M, tol = 101, 3.5e-3
+    ax = np.arange(M, dtype=np.float64)                      # the axis in cell units: element i sits at u = i
+    n = 200000
+    u = np.r_[rng.uniform(-3, M + 2, n), np.repeat(np.arange(-1, M + 1), 40) + rng.uniform(-2 * tol, 2 * tol, 40 * (M + 2)),
+              M - 1 + tol * np.linspace(0.9, 1.1, 41), -tol * np.linspace(0.9, 1.1, 41)]
+    v = np.r_[rng.uniform(-3, M + 2, len(u) - 1000), np.repeat(np.arange(0, 100), 10) + rng.uniform(-2 * tol, 2 * tol, 1000)]
+    rng.shuffle(v)
+    cls = shadow.cell_class(u, v, M, tol, tol)
+    u32, v32 = u.astype(np.float32).astype(np.float64), v.astype(np.float32).astype(np.float64)
+
+    def cells(du, dv):
+        x, y = u32 + du, v32 + dv
+        ix, iy = np.searchsorted(ax, x, "left"), np.searchsorted(ax, y, "left")
+        return np.where((x > ax[-1]) | (y > ax[-1]), -1, iy * M + ix)           # ffl:19, ffl:22-23
+
+    d = 0.999 * (tol - 2e-5)                                 # (single-precision rounding of u + tol itself)
+    corners = [cells(su * d, sv * d) for su in (-1, 0, 1) for sv in (-1, 0, 1)]
+    same = np.all([c == corners[4] for c in corners], axis=0)
+    sure = cls != -2
+    # whatever is classified is right under every perturbation
+    for c in corners:
+        np.testing.assert_array_equal(c[sure], cls[sure])
+    # and the classifier is not lazy: well inside a cell (2 tol from every edge) it commits
+    deep = np.all([cells(su * 2.2 * tol, sv * 2.2 * tol) == corners[4] for su in (-1, 1) for sv in (-1, 1)], axis=0)
+    assert sure[deep].all() and same[sure].all()
+    assert (cls[sure] == -1).sum() > 1000 and (cls[sure] >= 0).sum() > 100000 and (~sure).sum() > 1000
+    # (a NaN prediction -- a lattice node that could not be traced -- never reaches the classifier: the kernel tests
+    #  ux + uy == ux + uy first and traces such a ray exactly)
