@@ -701,7 +701,10 @@ __global__ void __launch_bounds__(256, 2) nf_contract_kernel(NfContractParams q)
     const int count = min(__ldg(q.counters2) - q.row0, q.rows);       // rows of E that hold an item
     const int r0 = blockIdx.x * NF_GM;
     if (r0 >= count) return;
-    const int N = 4 * q.nrx, c0 = blockIdx.y * NF_GN, split = blockIdx.z;
+    // launch order: all splits of the first (full) column tile, then those of the next ones -- the last tile is
+    // usually the narrowest (dead column groups are skipped), and the cheap CTAs fill the tail of the last wave
+    const int lin = blockIdx.y + gridDim.y * blockIdx.z, ytile = lin / gridDim.z;
+    const int N = 4 * q.nrx, c0 = ytile * NF_GN, split = lin - ytile * gridDim.z;
     const int k_begin = split * q.k_len, k_end = min(k_begin + q.k_len, q.n_act);
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     // staging: thread -> rows sr and sr + 32 of both tiles, ray k0 + sk
