@@ -2372,7 +2372,6 @@ struct solat_nf_plan {
     DevBuf<int> amap;                       // [3][n_act] active index of every ray's x, z and xz mirror ray
     DevBuf<FfItem> items;                   // work items of a paired map: [npix] pairs, then [npix] quads
     DevBuf<int> pair_ints;
-    DevBuf<double> pair_xz;                 // (z, |x|) of the pair items, the list the quad stage pairs
     DevBuf<double2> phase_e;                // many-table sweeps: exp(i k L) of every (quad item, ray)
     int sym = 0;                            // bit 0 / bit 1: fan and active set are mirror symmetric in x / in z
     int pairs = 1, quads = 1;               // work items of two / four pixels allowed (SOLAT_NF_QUADS=0: pairs only)
@@ -2429,7 +2428,6 @@ static int nf_map_contract(solat_nf_plan* p, const double* d_src, int npix, doub
     if (int rc = p->partial.reserve((size_t)npix * splits * nch)) return rc;
     if (int rc = p->items.reserve(2 * (size_t)piece)) return rc;
     if (int rc = p->pair_ints.reserve(8)) return rc;
-    if (int rc = p->pair_xz.reserve(2 * (size_t)piece)) return rc;
     if (int rc = p->phase_e.reserve((size_t)rows_max * ldE)) return rc;
     NfMapParams q;
     q.ang = p->ang.tabs; q.src_xz = d_src; q.act_idx = p->act_idx.p; q.phasor = p->phasor.p; q.first_leg = p->first_leg.p;
@@ -2518,8 +2516,6 @@ static int nf_map_launch(solat_nf_plan* p, const double* d_src, int npix, double
     if (pairs) {
         if (int rc = p->items.reserve((size_t)npix * (quads ? 2 : 1))) return rc;
         if (int rc = p->pair_ints.reserve(8)) return rc;
-        if (quads)
-            if (int rc = p->pair_xz.reserve(2 * (size_t)npix)) return rc;
         ff_pair_kernel<<<1, 1024, ff_pair_smem(npix), s>>>(d_src, npix, ff_pair_slots(npix), p->pair_ints.p, p->items.p, NF_PAIR_TOL,
                                                            quads ? p->items.p + npix : nullptr);
         LAUNCHED();
