@@ -530,7 +530,7 @@ def run_ours(args):
                         "launched ray: the reference traces every accepted ray twice) over the same time; the kernels execute far "
                         "fewer operations (rays the projection would skip are not traced, mirror pixels share a trace, "
                         "mixed-precision Newton, and on fans of 400^2 rays and more only lattice rays and cell winners are traced "
-                        "at all: the dominant kernel is bound by issue slots, 76 % active, not by the FP64 pipe, 26 %), so "
+                        "at all: the dominant kernel is bound by issue slots, 73 % active, not by the FP64 pipe, 24 %), so "
                         "model_speedup can exceed 1 and is not a utilisation"}
         ex = executed_entry(prof, "cfg5", pixel_rays / world, ms_kernels, peak)
         if ex:
