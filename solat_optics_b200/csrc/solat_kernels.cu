@@ -2840,7 +2840,7 @@ struct solat_ff_plan {
     int win_global;                         // the winner tables do not fit in shared memory: global scratch
     int lean, lean_grid;                    // lean_grid: shared tables and lean E_rec axes (ff_map_kernel<0, .., LEAN> applies); lean: plain maps take it
     int interp_s;                           // > 0: large uniform fan, plain maps go through ff_map_interp_kernel with this lattice spacing
-    double th0, dth, ph0, dph, interp_chk, interp_eps;
+    double th0, dth, ph0, dph, interp_chk;
     DevBuf<float> probe_err;
     DevBuf<int> redo;
     DevBuf<unsigned long long> win_g;
@@ -2959,7 +2959,7 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
     const bool interp = !panel && p->interp_s > 0 && rows && !q.win_g && p->lean_grid;
     q.redo = nullptr; q.probe_err = nullptr; q.interp_s = p->interp_s; q.interp_ls = 0;
     while ((1 << q.interp_ls) < p->interp_s) q.interp_ls++; q.th0 = p->th0; q.dth = p->dth; q.ph0 = p->ph0; q.dph = p->dph;
-    q.interp_eps = p->interp_eps; q.interp_chk = p->interp_chk;
+    q.interp_eps = FF_INTERP_EPS_CM; q.interp_chk = p->interp_chk;
     {   // cell units: u = (v - a[0]) * inv_step; 5e-4 of slack for the single-precision lattice, weights and roundings
         const double ix = (double)p->grid.inv_dx, iy = (double)p->grid.inv_dy;
         q.i_tol_x = (float)(q.interp_eps * ix) + p->grid.dev_u + 5.0e-4f; q.i_tol_y = (float)(q.interp_eps * iy) + p->grid.dev_u + 5.0e-4f;
@@ -3119,13 +3119,9 @@ int solat_ff_plan_create(solat_ctx* c, const solat_ff_geom* g, const double* the
     // large fans: interpolated cells + exact winners (ff_map_interp_kernel).  Needs the lean grid, the interval walk,
     // a square fan with uniform axes, and room for the lattice next to the candidate tables.
     p->interp_s = 0;
-    p->interp_eps = FF_INTERP_EPS_CM;
-    if (const char* env = getenv("SOLAT_FF_INTERP_EPS")) p->interp_eps = atof(env);   // experiments: ambiguity margin [cm]
-    p->interp_chk = p->interp_eps / 3;
+    p->interp_chk = FF_INTERP_EPS_CM / 3;
     if (const char* env = getenv("SOLAT_FF_INTERP_CHK")) p->interp_chk = atof(env);   // tests: 0 fails every probe -> every item is redone
-    int interp_min_n = FF_INTERP_MIN_N;
-    if (const char* env = getenv("SOLAT_FF_INTERP_MIN_N")) interp_min_n = atoi(env);  // experiments
-    if (!rc && p->lean_grid && rows && p->prefilter && nth == nph && nth >= interp_min_n) {
+    if (!rc && p->lean_grid && rows && p->prefilter && nth == nph && nth >= FF_INTERP_MIN_N) {
         const char* env = getenv("SOLAT_FF_INTERP");       // "0": off; a number >= 2: that lattice spacing
         int S = 4;                                         // the largest power of two up to nth / 60: the probes were measured at 16 / 1000
         while (S < 32 && 120 * S <= nth) S *= 2;
