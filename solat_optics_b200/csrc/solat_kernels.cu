@@ -18,9 +18,12 @@
 //                          the near-field source positions (a second stage there pairs the pairs into quads)
 //   ff_prep_kernel         per-item set-up of the fused far-field map: frames, the rays that have to be traced as up
 //                          to four index intervals per phi row (aperture, focal-position predictor)
-//   ff_map_kernel<PANEL,T,B>  fused far-field map: one CTA per work item; every warp traces its share of the item's
-//                          dense ray list with full lanes; winner tables (ray index, OPL) in shared memory;
-//                          winners-only phasor sums
+//   ff_map_kernel<PANEL,T,B,LEAN>  fused far-field map, the exact walk: one CTA per work item; every warp traces its
+//                          share of the item's dense ray list with full lanes; winner tables (ray index, OPL) in shared
+//                          memory; winners-only phasor sums (LEAN: the binning on shared-memory addresses only)
+//   ff_map_interp_kernel   fused far-field map of large fans: a lattice of rays traced exactly, the cell of every
+//                          listed ray from its interpolated focal position, exact traces for the winner of every cell
+//                          (each one a probe of its prediction); flagged items are redone by ff_map_kernel
 //   ff_mirror_xy_kernel    mirror coordinates of every (pixel, ray) for the host's identify_panel
 //   fp64_peak_kernel       DFMA issue-rate microbenchmark (roofline denominator)
 #include <cuda_runtime.h>
@@ -2958,7 +2961,8 @@ static int ff_map_run(solat_ff_plan* p, FfMapParams q, int npix, int panel, cuda
     q.rows = rows; q.rec = p->rec.p; q.rec_stride = stride;
     const bool interp = !panel && p->interp_s > 0 && rows && !q.win_g && p->lean_grid;
     q.redo = nullptr; q.probe_err = nullptr; q.interp_s = p->interp_s; q.interp_ls = 0;
-    while ((1 << q.interp_ls) < p->interp_s) q.interp_ls++; q.th0 = p->th0; q.dth = p->dth; q.ph0 = p->ph0; q.dph = p->dph;
+    while ((1 << q.interp_ls) < p->interp_s) q.interp_ls++;
+    q.th0 = p->th0; q.dth = p->dth; q.ph0 = p->ph0; q.dph = p->dph;
     q.interp_eps = FF_INTERP_EPS_CM; q.interp_chk = p->interp_chk;
     {   // cell units: u = (v - a[0]) * inv_step; 5e-4 of slack for the single-precision lattice, weights and roundings
         const double ix = (double)p->grid.inv_dx, iy = (double)p->grid.inv_dy;

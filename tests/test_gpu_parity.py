@@ -1165,6 +1165,12 @@ def test_ff_interpolated_cells_equal_the_exact_walk(oracle):
             np.testing.assert_array_equal(a_s, a_x); np.testing.assert_array_equal(p_s, p_x)
             oa, op = oracle.ff_map(oracle.ff_geo_vec(rx_y_m=-bench.OFFSET), pts[::4], th, phi, x, y, e, tg.k)
             _assert_pixels(a_i[::4], p_i[::4], oa, op)
+    # one pixel per work item (no mirror pairs: one candidate table per CTA)
+    th, phi = maps.ff_fan(512)
+    a1, p1, st = _env_plan({"SOLAT_FF_PAIRS": "0"}, tg, th, phi, x, y, e).run(sel[::2])
+    a0, p0, st0 = _env_plan({"SOLAT_FF_PAIRS": "0", "SOLAT_FF_INTERP": "0"}, tg, th, phi, x, y, e).run(sel[::2])
+    assert st == 0 and st0 == 0
+    np.testing.assert_array_equal(a1, a0); np.testing.assert_array_equal(p1, p0)
     # another telescope set-up (90 GHz, focal plane at 1.25 m), a coarser E_rec grid and a pixel list of a different scan
     tg2 = maps.ff_tele_geo(90, 1.25)
     px2 = maps.ff_pixels(tg2, 0.5, 6)
