@@ -1170,7 +1170,8 @@ def test_ff_interpolated_cells_equal_the_exact_walk(oracle):
     a1, p1, st = _env_plan({"SOLAT_FF_PAIRS": "0"}, tg, th, phi, x, y, e).run(sel[::2])
     a0, p0, st0 = _env_plan({"SOLAT_FF_PAIRS": "0", "SOLAT_FF_INTERP": "0"}, tg, th, phi, x, y, e).run(sel[::2])
     assert st == 0 and st0 == 0
-    np.testing.assert_array_equal(a1, a0); np.testing.assert_array_equal(p1, p0)
+    # (one 101 x 101 table per CTA: the exact walk runs 384-thread CTAs here and sums the same winners in another order)
+    np.testing.assert_allclose(a1, a0, rtol=1e-14, atol=0); assert np.abs(gu.wrap(p1 - p0)).max() < 1e-14
     # another telescope set-up (90 GHz, focal plane at 1.25 m), a coarser E_rec grid and a pixel list of a different scan
     tg2 = maps.ff_tele_geo(90, 1.25)
     px2 = maps.ff_pixels(tg2, 0.5, 6)
