@@ -124,9 +124,16 @@ class _digest:
     def __hash__(self):
         return self._hash
 
+    @staticmethod
+    def _same_bytes(a, b):
+        """bit-for-bit equality of two C-contiguous arrays (NaN-safe), compared 8 bytes at a time"""
+        ra, rb = a.reshape(-1).view(np.uint8), b.reshape(-1).view(np.uint8)
+        n8 = ra.size // 8 * 8
+        return (np.array_equal(ra[:n8].view(np.uint64), rb[:n8].view(np.uint64)) and ra[n8:].tobytes() == rb[n8:].tobytes())
+
     def __eq__(self, other):
         return (isinstance(other, _digest) and self._hash == other._hash and len(self.arrays) == len(other.arrays)
-                and all(a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+                and all(a.shape == b.shape and a.dtype == b.dtype and self._same_bytes(a, b)
                         for a, b in zip(self.arrays, other.arrays)))
 
 
@@ -196,6 +203,20 @@ class ShardedMap:
             self.d_all = torch.zeros((world, self.flat), dtype=torch.float64, device=self.dev) if world > 1 else None
             self.gather_list = list(self.d_all.unbind(0)) if world > 1 else None
             self.h_all = pin(torch.zeros((world, self.flat), dtype=torch.float64))
+            # where every output element sits in the gathered buffer: the un-permute of fetch() is one gather per array
+            src = np.empty((self.nch, self.npix), dtype=np.int64)
+            for r, idx in enumerate(self.parts):
+                if len(idx):
+                    src[:, idx] = r * self.flat + np.arange(self.nch)[:, None] * len(idx) + np.arange(len(idx))[None, :]
+            self._src_amp = src
+            self._src_phase = src + self.nch * np.array([len(p) for p in self.parts], dtype=np.int64)[self._rank_of()][None, :]
+
+    def _rank_of(self):
+        """rank that computes each pixel"""
+        owner = np.empty(self.npix, dtype=np.int64)
+        for r, idx in enumerate(self.parts):
+            owner[idx] = r
+        return owner
 
     def _stream(self):
         import torch
@@ -228,14 +249,11 @@ class ShardedMap:
         if self.cuda:
             self._stream().synchronize()
         h = self.h_all.numpy()
-        amp = np.empty((self.nch, self.npix))
-        phase = np.empty((self.nch, self.npix))
+        flat = h.reshape(-1)
+        amp, phase = flat[self._src_amp], flat[self._src_phase]
         status = 0
         for r, idx in enumerate(self.parts):
-            n = self.nch * len(idx)
-            if n:
-                amp[:, idx] = h[r, :n].reshape(self.nch, len(idx))
-                phase[:, idx] = h[r, n:2 * n].reshape(self.nch, len(idx))
+            if len(idx):
                 status |= int(h[r, self.flat - 1:].view(np.int32)[0])
         return amp, phase, status
 
