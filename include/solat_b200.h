@@ -162,7 +162,12 @@ SOLAT_API int solat_ff_project(solat_ctx *ctx, const double *sim17, int n_pts, c
  * How the kernels spend less than the reference: rays the projection would skip
  * (ffl:19) are not traced, and when the telescope, the fan (phi symmetric about pi/2) and therefore the
  * physics are symmetric under x -> -x, the pixels (az, el) and (-az, el) of one call share one trace;
- * a pixel's value does not depend on which other pixels are in the call.  Calls on one plan must be
+ * a pixel's value does not depend on which other pixels are in the call.  Square uniform fans of 400^2
+ * rays and more go through the interpolated-cell kernel: a lattice of rays and the winner of every cell
+ * are traced exactly, every other listed ray only has its cell worked out from interpolated focal
+ * positions (maps bit-identical to the exact walk; every winner is checked against its prediction and an
+ * item that fails is redone exactly).  A ray that is never traced reports no status; the environment
+ * switch SOLAT_FF_PREFILTER=0 traces and checks every accepted ray.  Calls on one plan must be
  * stream-ordered by the caller.                                                                   */
 SOLAT_API int solat_ff_plan_create(solat_ctx *ctx, const solat_ff_geom *g, const double *theta, int nth, const double *phi,
                          int nph, const double *data_x, const double *data_y, const double *e_rec_reim, int M,
