@@ -82,13 +82,15 @@ def ff_grid(kind):
     the interior binning is exercised.  Field = SURVEY.md §8d config-5 closed form."""
     if kind == "nf51":
         ax = np.linspace(-50, 50, 51) / 1e1
+    elif kind == "cfg5":
+        ax = np.linspace(-5, 5, 101)                     # bench.e_rec_config5: the E_rec of BASELINE config 5
     else:
         ax = np.linspace(-30, 30, 61)
     # ff_sim.py:55-56: x <- column 1 (fast axis), y <- column 0 (slow axis)
     y, x = np.meshgrid(ax, ax, indexing="ij")
-    sig = 1.5 if kind == "nf51" else 9.0
+    sig = 1.5 if kind in ("nf51", "cfg5") else 9.0
     amp = np.exp(-(x ** 2 + y ** 2) / (2 * sig ** 2))
-    ph = 0.3 * (x ** 2 + y ** 2) * (1.0 if kind == "nf51" else 0.03)
+    ph = 0.3 * (x ** 2 + y ** 2) * (1.0 if kind in ("nf51", "cfg5") else 0.03)
     e = amp * np.exp(1j * ph)
     return x, y, e
 
@@ -220,6 +222,13 @@ def build_jobs():
         ("t_ff_pixel", dict(freq=150, offset=1.33, n_scan=30, az=a * D1, el=EL0 + e * D1, grid="wide61"))
         for a, e in [(0, 0), (10, 0), (-10, 10), (10, -10), (3, -7)]
     ]
+    # -- the large-fan path (fans of 400^2 rays and more take the interpolated-cell kernel): three pixels of the
+    #    401 x 401 config-5 scan -- a mirror pair and an az = 0 pixel -- at 448^2 rays on the config-5 E_rec
+    D5 = 0.05 / 60 * np.pi / 180
+    J["ff_pixels_big"] = [
+        ("t_ff_pixel", dict(freq=140, offset=1.32, n_scan=448, az=a * D5, el=EL0 + e * D5, grid="cfg5"))
+        for a, e in [(-190, -163), (190, -163), (0, 50)]
+    ]
     # -- far-field small map: ff_sim.py 140 0.25 2 1.32 with N_scan=16, wide grid
     azs = np.linspace(-2 * DE, 2 * DE, 5)
     els = np.linspace(-2 * DE + EL0, 2 * DE + EL0, 5)
@@ -262,7 +271,7 @@ def pack(name, jobs, results):
         for i, (m, f) in enumerate(results):
             out["mirror_%d" % i] = m
             out["field_%d" % i] = f
-    elif name in ("ff_pixels", "ff_map5", "ff_pixels_150"):
+    elif name in ("ff_pixels", "ff_map5", "ff_pixels_150", "ff_pixels_big"):
         out["amp"] = np.array([r[0] for r in results])
         out["phi"] = np.array([r[1] for r in results])
         out["n_valid"] = np.array([r[2] for r in results])

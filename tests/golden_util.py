@@ -35,15 +35,17 @@ def ff_fan(n):
 
 
 def ff_grid(kind):
-    """Same two E_rec grids as oracle/gen_golden.py:ff_grid."""
+    """Same E_rec grids as oracle/gen_golden.py:ff_grid ("cfg5" = bench.e_rec_config5)."""
     if kind == "nf51":
         ax = np.linspace(-50, 50, 51) / 1e1
+    elif kind == "cfg5":
+        ax = np.linspace(-5, 5, 101)
     else:
         ax = np.linspace(-30, 30, 61)
     y, x = np.meshgrid(ax, ax, indexing="ij")
-    sig = 1.5 if kind == "nf51" else 9.0
+    sig = 1.5 if kind in ("nf51", "cfg5") else 9.0
     amp = np.exp(-(x ** 2 + y ** 2) / (2 * sig ** 2))
-    ph = 0.3 * (x ** 2 + y ** 2) * (1.0 if kind == "nf51" else 0.03)
+    ph = 0.3 * (x ** 2 + y ** 2) * (1.0 if kind in ("nf51", "cfg5") else 0.03)
     return x, y, amp * np.exp(1j * ph)
 
 

@@ -530,7 +530,7 @@ def test_ff_project_to_data(oracle):
         np.testing.assert_allclose(out, ref, rtol=0, atol=1e-9)   # same k*L/1e3 argument; reduction error only
 
 
-@pytest.mark.parametrize("name", ["ff_pixels", "ff_map5", "ff_pixels_150"])
+@pytest.mark.parametrize("name", ["ff_pixels", "ff_map5", "ff_pixels_150", "ff_pixels_big"])
 def test_ff_pixel_known_answers(name):
     from solat_optics_b200 import maps
 

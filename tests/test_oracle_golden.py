@@ -75,7 +75,7 @@ def test_ff_rays(oracle):
         assert np.abs(f[15] - ref[15]).max() <= 2 * ULP_1E8
 
 
-@pytest.mark.parametrize("name", ["ff_pixels", "ff_map5", "ff_pixels_150"])
+@pytest.mark.parametrize("name", ["ff_pixels", "ff_map5", "ff_pixels_150", "ff_pixels_big"])
 def test_ff_pixels(oracle, name):
     d = gu.load(name)
     for i in range(int(d["n_cases"])):
