@@ -223,10 +223,10 @@ def build_jobs():
         for a, e in [(0, 0), (10, 0), (-10, 10), (10, -10), (3, -7)]
     ]
     # -- the large-fan path (fans of 400^2 rays and more take the interpolated-cell kernel): three pixels of the
-    #    401 x 401 config-5 scan -- a mirror pair and an az = 0 pixel -- at 448^2 rays on the config-5 E_rec
+    #    401 x 401 config-5 scan -- a mirror pair and an az = 0 pixel -- at 400^2 rays on the config-5 E_rec
     D5 = 0.05 / 60 * np.pi / 180
     J["ff_pixels_big"] = [
-        ("t_ff_pixel", dict(freq=140, offset=1.32, n_scan=448, az=a * D5, el=EL0 + e * D5, grid="cfg5"))
+        ("t_ff_pixel", dict(freq=140, offset=1.32, n_scan=400, az=a * D5, el=EL0 + e * D5, grid="cfg5"))
         for a, e in [(-190, -163), (190, -163), (0, 50)]
     ]
     # -- far-field small map: ff_sim.py 140 0.25 2 1.32 with N_scan=16, wide grid
