@@ -52,7 +52,8 @@ def workload_config(n_gpus):
         "pixels_per_map": side * side, "rays_per_pixel": N_SCAN ** 2, "maps_per_step": 1,
         "sharding": "one map per step; mirror pairs (+-az, el) dealt cyclically over %d rank(s); NCCL gather of (amp, phase, "
                     "status) to rank 0 inside the timed region" % n_gpus,
-        "l2": "flushed between timed steps (256 MiB write); the path reads < 4 MB per step",
+        "l2": "flushed between timed steps (256 MiB write); the path's own traffic is the per-item set-up records, 33 kB per work "
+              "item written once and read once (2.6 GB per map: larger than L2)",
         "parallelism": "pixel-sharded x%d" % n_gpus,
     }
 
